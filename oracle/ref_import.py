@@ -1,0 +1,75 @@
+"""oracle/ref_import.py -- TEST INFRASTRUCTURE ONLY; works only where /root/reference exists.
+
+Imports the UNMODIFIED reference package (`transform`) from /root/reference in the
+authoring container so that golden vectors can be generated from the real thing
+(tests/golden/make_golden.py) and the numpy/C restatement in this directory can be pinned
+against it.  Nothing here is reachable from transform_b200, bench.py's product arm, or the
+`-m gpu` tests (the GPU box has no /root/reference).
+
+How: (1) oracle/build_ref.py compiles helpers.pyx / SVD.pyx where they lie into
+oracle/_ref/*.so; (2) that helpers module is registered as `transform.helpers` before the
+package is imported (the package directory is read-only, so the .so cannot sit next to
+core.py); (3) oracle/astropy_stub provides the `astropy.units` surface core.py/basic.py
+need at import time (astropy itself is not installed).
+"""
+import importlib
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("TFM_REFERENCE_ROOT", "/root/reference")
+_REFDIR = os.path.join(HERE, "_ref")
+
+
+def have_reference_sources():
+    return os.path.exists(os.path.join(REF, "transform", "core.py"))
+
+
+def _load_ext(modname, fullname):
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    path = os.path.join(_REFDIR, modname + suffix)
+    if not os.path.exists(path):
+        raise ImportError("oracle/_ref/%s%s not built (run oracle/build_ref.py)" % (modname, suffix))
+    loader = importlib.machinery.ExtensionFileLoader(modname, path)
+    spec = importlib.util.spec_from_file_location(modname, path, loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    sys.modules[fullname] = mod
+    return mod
+
+
+def load_ref_helpers():
+    """The reference's compiled helpers module alone (travels to the GPU box as a .so)."""
+    if "tfm_ref_helpers" in sys.modules:
+        return sys.modules["tfm_ref_helpers"]
+    return _load_ext("helpers", "tfm_ref_helpers")
+
+
+def load_ref_svd():
+    if "tfm_ref_SVD" in sys.modules:
+        return sys.modules["tfm_ref_SVD"]
+    return _load_ext("SVD", "tfm_ref_SVD")
+
+
+def load_reference():
+    """Import the unmodified reference package; container only."""
+    if not have_reference_sources():
+        raise ImportError("reference sources not present at %s" % REF)
+    if "transform" in sys.modules and getattr(sys.modules["transform"], "_tfm_is_reference", False):
+        return sys.modules["transform"]
+    try:
+        import astropy  # noqa: F401  (a real astropy, if one ever appears, wins)
+    except ImportError:
+        sys.path.insert(0, os.path.join(HERE, "astropy_stub"))
+    helpers = load_ref_helpers()
+    sys.modules["transform.helpers"] = helpers
+    sys.path.insert(0, REF)
+    try:
+        mod = importlib.import_module("transform")
+    finally:
+        sys.path.remove(REF)
+    mod._tfm_is_reference = True
+    return mod
