@@ -1,0 +1,251 @@
+/* tfm_b200.h -- C ABI of libtfm_b200.so: the B200 (sm_100a) replacement for the image-resampling
+ * hot path of drzowie/transform.
+ *
+ * The reference has no FFI: its seam for this path is Python-level.  Each
+ * entry point below names the reference interface it stands in for (paths under
+ * /root/reference/transform/).  The Python host side (transform_b200/) mirrors the reference's
+ * classes and binds these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions (same as the reference, core.py:48-59): vectors are (X,Y) in the last axis, images
+ * are row-major [Y][X]; pixel centres sit on integers; (0,0) is the centre of the first pixel.
+ * All data pointers are DEVICE pointers unless a name ends in _host.  Calls are stream-ordered on
+ * the cudaStream_t passed as `stream` (a void* here so the header needs no CUDA include), keep no
+ * hidden global state, and may be issued concurrently on different streams / devices.  Nothing
+ * throws across the boundary: every function returns a tfm_status.
+ */
+#ifndef TFM_B200_H
+#define TFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TFM_API __attribute__((visibility("default")))
+#else
+#define TFM_API
+#endif
+
+#define TFM_ABI_VERSION 1
+#define TFM_MAX_OPS 16          /* flattened chain length (Composition flattening, core.py:1534-1537) */
+#define TFM_OP_NPARAM 24
+
+/* ---- status codes: 1:1 with the exceptions of the reference (SURVEY.md section 8b "Errors") ---- */
+typedef enum tfm_status {
+    TFM_OK = 0,
+    TFM_EVALUE = 1,        /* ValueError: bad dims / shape / method / boundary (core.py:566-571,
+                              helpers.pyx:174-176, 840-844, 1505, 1516) */
+    TFM_EDIRECTION = 2,    /* AssertionError: transform invalid in that direction (core.py:265-266) */
+    TFM_EFORBID = 3,       /* ValueError: 'forbid' boundary violated (helpers.pyx:141-144, 1753) */
+    TFM_ECUDA = 4,         /* CUDA runtime error (no reference counterpart) */
+    TFM_EUNSUPPORTED = 5,  /* valid in the reference but outside this library's scope (fails loudly) */
+    TFM_ESTAGED = 6        /* a tap fell outside the staged source sub-rectangle of a shard */
+} tfm_status;
+
+/* ---- transform chain ----
+ * A chain is the reference's flattened Composition AFTER direction resolution: element i is
+ * applied i-th; `dir` says whether that element runs its _forward or its _reverse.
+ * Transform.invert(grid) on Composition([A,B,C]) lowers to {A rev, B rev, C rev}
+ * (core.py:1556-1559); Transform.apply lowers to {C fwd, B fwd, A fwd} (core.py:1551-1554). */
+typedef enum tfm_op_kind {
+    TFM_OP_IDENTITY = 0,   /* core.py:1345-1401 */
+    TFM_OP_LINEAR = 1,     /* basic.py:12-218 (+Scale 224-336, Rotation 338-506, Offset 508-551) */
+    TFM_OP_RADIAL = 2,     /* basic.py:553-716 */
+    TFM_OP_WCS = 3,        /* core.py:1650-1747 (astropy.wcs all_pix2world/all_world2pix, origin 0) */
+    TFM_OP_INDEX = 4       /* coordinate lookup: (x,y) = index[y][x][0..1].  Not a Transform of the
+                              reference: it is how interpND(source, index, ...) / interpND_grid
+                              (helpers.pyx:379, 1293), which take a precomputed coordinate array,
+                              run through the same kernels.  Must be the first element of a chain. */
+} tfm_op_kind;
+
+typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
+
+/* TFM_OP_LINEAR  fwd: out = post + M.(in + pre)   (basic.py:141-158)
+ *                rev: out = Minv.(in - post) - pre (basic.py:160-176)
+ *   p[0..3]  2x2 matrix used in THIS direction, row-major (matrix for fwd, matinv for rev)
+ *   p[4..5]  pre     p[6..7] post
+ *   Matrix-vector rounding in the fp64-exact mode follows NumPy's gemv as measured:
+ *   C-contiguous matrix: fma(m[i][0], x, fl(m[i][1]*y)); transposed view (TFM_LIN_MAT_FORDER,
+ *   e.g. Rotation's matinv = out.transpose(), basic.py:501): fma(m[i][1], y, fl(m[i][0]*x)). */
+#define TFM_LIN_HAS_PRE 1
+#define TFM_LIN_HAS_POST 2
+#define TFM_LIN_HAS_MATRIX 4
+#define TFM_LIN_MAT_FORDER 8
+
+/* TFM_OP_RADIAL  (basic.py:670-711)
+ *   p[0..1] origin   p[2] r0   p[3] ang_coeff (radians per output angle unit) */
+#define TFM_RAD_CCW 1
+#define TFM_RAD_POS_ONLY 2
+#define TFM_RAD_R0_NOT_NONE 4   /* reverse tests `r0 is not None` (basic.py:703) */
+#define TFM_RAD_R0_TRUTHY 8     /* forward tests truthiness of r0   (basic.py:686) */
+#define TFM_RAD_ORIGIN_NONZERO 16 /* `if not np.all(origin == 0)` (basic.py:675, 709) */
+
+/* TFM_OP_WCS  fwd = pixel(origin 0) -> world, rev = world -> pixel (core.py:1719-1747).
+ *   p[0..1]  CRPIX (1-based, FITS)          p[2..5]  CD matrix (PC*CDELT folded), row-major
+ *   p[6..9]  inverse of the CD matrix        p[10..11] CRVAL
+ *   flags low byte = projection: 0 none (purely linear axes, e.g. 'Solar-X'), 1 TAN, 2 CAR
+ *   p[12..20] 3x3 native->celestial rotation matrix (Calabretta & Greisen 2002 eq. 2/5, from
+ *             CRVAL, LONPOLE, LATPOLE), row-major; the transpose is used for celestial->native */
+#define TFM_WCS_PROJ_NONE 0
+#define TFM_WCS_PROJ_TAN 1
+#define TFM_WCS_PROJ_CAR 2
+
+/* TFM_OP_INDEX
+ *   p[0] the BIT PATTERN of a device pointer to float64 index[ny][nx][2] (dense, (X,Y) last axis)
+ *   p[1] nx   p[2] ny   (grid points outside [0,nx) x [0,ny) yield NaN coordinates) */
+
+typedef struct tfm_op {
+    int32_t kind;          /* tfm_op_kind */
+    int32_t dir;           /* tfm_dir */
+    int32_t flags;         /* per-kind bits above */
+    int32_t reserved;
+    double p[TFM_OP_NPARAM];
+} tfm_op;
+
+/* ---- enumerations shared by the resamplers ---- */
+typedef enum tfm_dtype { TFM_F32 = 0, TFM_F64 = 1 } tfm_dtype;
+
+/* interpND methods (helpers.pyx:541-611, 703-787); first letter in the reference */
+typedef enum tfm_method { TFM_NEAREST = 0, TFM_LINEAR = 1, TFM_CUBIC = 2 } tfm_method;
+
+/* boundary codes: the reference's own table (helpers.pyx:1511) */
+typedef enum tfm_bound {
+    TFM_B_FORBID = 1, TFM_B_TRUNCATE = 2, TFM_B_EXTEND = 3, TFM_B_PERIODIC = 4, TFM_B_MIRROR = 5
+} tfm_bound;
+
+/* Jacobian-filter shapes: the reference's own table (helpers.pyx:1501) */
+typedef enum tfm_filter {
+    TFM_FILT_TENT = 1, TFM_FILT_LANCZOS = 2, TFM_FILT_HANNING = 3, TFM_FILT_TUKEY = 4,
+    TFM_FILT_GAUSSIAN = 5
+} tfm_filter;
+
+typedef enum tfm_precision {
+    TFM_PREC_EXACT64 = 0,  /* parity mode: chain evaluated op by op in fp64 in the reference's
+                              operation order (no FMA contraction except the documented gemv fma);
+                              interpolation arithmetic in fp64 in the reference's order */
+    TFM_PREC_FAST32 = 1    /* throughput mode: coordinates still fp64 (adjacent affine ops are
+                              pre-composed by the host), interpolation weights/accumulation fp32 */
+} tfm_precision;
+
+/* tfm_image.flags / tfm_resample_args.flags */
+#define TFM_F_REGION_SRC_DTYPE 1 /* cubic, exact mode: first Hermite pass in the SOURCE dtype (float32)
+                                    because the reference's region was not promoted by the truncation
+                                    pass (helpers.pyx:373-374, 755-762) */
+
+/* One 2-D image plane in device memory.  (x0,y0) is the position of element [0][0] in the
+ * coordinate system of the FULL image of size full_w x full_h: a whole image has x0=y0=0 and
+ * full_* == w,h; a shard (output row block, or staged input sub-rectangle) has its own origin. */
+typedef struct tfm_image {
+    void *data;
+    int32_t dtype;         /* tfm_dtype */
+    int32_t reserved;
+    int64_t h, w;          /* rows, columns held at `data` */
+    int64_t pitch;         /* bytes between rows */
+    int64_t x0, y0;        /* global origin of element [0][0] */
+    int64_t full_h, full_w;/* extent of the full image (boundary conditions act on this) */
+    int64_t n_planes;      /* >= 1: leading (broadcast) axes flattened -- image cubes, frame batches
+                              (core.py:566-571); src and dst must agree; plane k of dst is resampled
+                              from plane k of src with the same chain */
+    int64_t plane_pitch;   /* bytes between planes */
+} tfm_image;
+
+/* ---- K1: fused inverse-chain evaluation + nearest / linear / cubic gather ----
+ * Replaces, for one call of Transform.resample (core.py:573-584):
+ *   output-grid enumeration  np.mgrid[...].transpose()        core.py:574-578   (zero bytes here)
+ *   icoords = self.invert(grid)                               core.py:574, 1556-1559
+ *   interpND(data, icoords, method, bound)                    core.py:584, helpers.pyx:379-844
+ * `chain` (host memory) is the inverse chain in execution order.  dst pixel (x,y) of the shard maps
+ * to grid point (dst.x0 + x, dst.y0 + y).  `status_dev` (device int32, may be NULL unless a
+ * boundary is TFM_B_FORBID or src is a sub-rectangle) receives OR-ed bits: 1 = forbid violated,
+ * 2 = tap outside staged sub-rectangle. */
+typedef struct tfm_resample_args {
+    int32_t abi_version;   /* TFM_ABI_VERSION */
+    int32_t n_ops;
+    const tfm_op *chain;   /* host pointer */
+    tfm_image src;
+    tfm_image dst;
+    int32_t method;        /* tfm_method */
+    int32_t bound_x, bound_y; /* tfm_bound, (X,Y) order like the reference's per-axis list */
+    int32_t precision;     /* tfm_precision */
+    int32_t flags;
+    int32_t tuning;        /* 0 = auto; otherwise a kernel-variant selector (bench / ncu only) */
+    double fillvalue;      /* helpers.pyx:373-374 */
+    int32_t *status_dev;
+} tfm_resample_args;
+
+TFM_API int tfm_resample(const tfm_resample_args *args, void *stream);
+
+/* ---- K2: Jacobian-adaptive (DeForest 2004) anti-aliased resampler ----
+ * Replaces interpND_grid(..., antialias=True) (helpers.pyx:1293-1530):
+ *   jacobian(index, jump_detect)  = simple_jacobian + jump_detect + grid-centring
+ *                                   (helpers.pyx:846-958, 960-1141, 1145-1290)
+ *   interpND_jacobian(...)        = per-pixel svd2x2_fast, singular-value padding, footprint loop
+ *                                   (helpers.pyx:1542-1803, 1845-1916)
+ * with the coordinates produced in-kernel from `chain` instead of read from an index array, and
+ * with the repair list of oracle/oracle_np.py::interp_grid_jacobian.  grid_h/grid_w (via dst.full_*)
+ * give the FULL output grid so that the reference's grid-edge rules fire on true edges only when
+ * the output is sharded by rows. */
+typedef struct tfm_jacobian_args {
+    int32_t abi_version;
+    int32_t n_ops;
+    const tfm_op *chain;   /* host pointer */
+    tfm_image src;
+    tfm_image dst;
+    int32_t filter;        /* tfm_filter */
+    int32_t bound_x, bound_y;
+    int32_t precision;
+    int32_t flags;
+    int32_t tuning;
+    double fillvalue;      /* accepted, unused -- as in the reference (helpers.pyx:1547) */
+    double oblur;          /* helpers.pyx:1417-1422 */
+    double iblur;          /* accepted, unused -- as in the reference (helpers.pyx:1549) */
+    double pad_pow;        /* helpers.pyx:1431-1439, applied as coded at 1661-1662 */
+    double jump_thresh;    /* interpND_grid's jump_detect; 0 disables (helpers.pyx:1447-1459) */
+    int64_t max_reg;       /* cap on the footprint size reg_size (0 = none); stands in for the
+                              reference's accepted-but-unused sv_limit (helpers.pyx:1441-1445) */
+    int32_t *status_dev;
+} tfm_jacobian_args;
+
+TFM_API int tfm_resample_jacobian(const tfm_jacobian_args *args, void *stream);
+
+/* ---- K3: streaming Transform.apply over vector arrays ----
+ * Replaces Transform.apply / invert on [..., vec_len] arrays (core.py:218-315) including the
+ * pass-through of components beyond the transform's dimension (core.py:271-276, 287-292).
+ * in/out: n_vec rows of vec_len elements of `dtype`, densely packed; may alias (in-place). */
+typedef struct tfm_apply_args {
+    int32_t abi_version;
+    int32_t n_ops;
+    const tfm_op *chain;   /* host pointer, execution order */
+    const void *in;
+    void *out;
+    int64_t n_vec;
+    int32_t vec_len;       /* >= 2; components 2.. are copied through */
+    int32_t dtype;         /* tfm_dtype of in and out (arithmetic is fp64 either way) */
+    int32_t precision;
+    int32_t tuning;
+} tfm_apply_args;
+
+TFM_API int tfm_apply(const tfm_apply_args *args, void *stream);
+
+/* ---- host-side test hooks mirroring helpers.pyx:1807-1810 (svd2x2 / svc2x2) ----
+ * M, U, V: 4 doubles row-major; s: 2 doubles.  Run the device routines on one matrix on the
+ * current device and copy the result back (used by parity tests only). */
+TFM_API int tfm_svd2x2(const double *M_host, double *U_host, double *s_host, double *V_host);
+TFM_API int tfm_svc2x2(const double *U_host, const double *s_host, const double *V_host, double *M_host);
+
+/* ---- misc ---- */
+TFM_API int tfm_abi_version(void);
+TFM_API const char *tfm_strerror(int status);
+/* Number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
+TFM_API int64_t tfm_launch_count(void);
+/* Name of the kernel variant chosen by the last tfm_resample / tfm_resample_jacobian / tfm_apply
+ * call on this thread (for bench.py / profiles). */
+TFM_API const char *tfm_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFM_B200_H */

@@ -674,3 +674,111 @@ def _jacobian_rows(coords, ya, yb, ny, jump_thresh):
     # rows whose edge rules fired spuriously (block edges that are not grid edges) are inside the
     # margin and are discarded by the caller; nothing to fix up.
     return J
+
+
+# --------------------------------------------------------------------------------------
+# FITS WCS (core.py:1719-1747 -> astropy.wcs.WCS.all_pix2world / all_world2pix, origin 0)
+# --------------------------------------------------------------------------------------
+class WCS(Op):
+    """pixel (origin 0) <-> world for two axes.
+
+    The reference delegates to astropy/wcslib, absent from /root/reference and unpinned
+    (setup.py:27-32).  Restated from Greisen & Calabretta 2002 (paper I: linear part) and
+    Calabretta & Greisen 2002 (paper II: spherical rotation eq. 2 and 5, TAN eq. 54-55, CAR
+    eq. 83-84, LONPOLE/LATPOLE defaults and the celestial pole, eq. 8-10).
+      * linear part: PINNED by tests/test_01_core.py:160-169 (sample.fits, CD matrix).
+      * TAN / CAR:   PARITY UNPINNED (nothing in the reference's tests exercises them).
+    Deliberately written with the explicit Euler-angle formulas per point -- not with the 3x3
+    rotation matrix the CUDA path uses -- so that the two derivations check each other.
+    proj: None (linear axes), 'TAN' or 'CAR'.  cd = CDELT_i * PC_ij."""
+
+    def __init__(self, crpix, cd, crval, proj=None, lonpole=None, latpole=None):
+        self.crpix = np.asarray(crpix, dtype=np.float64)
+        self.cd = np.asarray(cd, dtype=np.float64)
+        self.cdinv = np.linalg.inv(self.cd)
+        self.crval = np.asarray(crval, dtype=np.float64)
+        self.proj = proj
+        if proj is not None:
+            phi0, theta0 = {"TAN": (0.0, 90.0), "CAR": (0.0, 0.0)}[proj]
+            a0, d0 = self.crval
+            self.phi_p = lonpole if lonpole is not None else phi0 + (0.0 if d0 >= theta0 else 180.0)
+            theta_p = 90.0 if latpole is None else latpole
+            if theta0 == 90.0:
+                self.alpha_p, self.delta_p = a0, d0
+            else:
+                dphi = np.radians(self.phi_p - phi0)
+                t0, dd = np.radians(theta0), np.radians(d0)
+                a = np.degrees(np.arctan2(np.sin(t0), np.cos(t0) * np.cos(dphi)))
+                b = np.degrees(np.arccos(np.clip(
+                    np.sin(dd) / np.sqrt(1.0 - (np.cos(t0) * np.sin(dphi)) ** 2), -1, 1)))
+                cands = [c for c in (a + b, a - b) if -90.0 - 1e-10 <= c <= 90.0 + 1e-10]
+                self.delta_p = float(np.clip(min(cands, key=lambda c: abs(c - theta_p)), -90, 90))
+                dp = np.radians(self.delta_p)
+                if abs(abs(d0) - 90.0) < 1e-12:
+                    self.alpha_p = a0
+                elif abs(self.delta_p - 90.0) < 1e-12:
+                    self.alpha_p = a0 + self.phi_p - phi0 - 180.0
+                elif abs(self.delta_p + 90.0) < 1e-12:
+                    self.alpha_p = a0 - self.phi_p + phi0
+                else:
+                    self.alpha_p = a0 - np.degrees(np.arctan2(
+                        np.sin(dphi) * np.cos(t0) / np.cos(dd),
+                        (np.sin(t0) - np.sin(dp) * np.sin(dd)) / (np.cos(dp) * np.cos(dd))))
+
+    def forward(self, v):
+        v = np.asarray(v, dtype=np.float64)
+        d = (v + 1.0) - self.crpix                                # FITS pixels are 1-based
+        ix = self.cd[0, 0] * d[..., 0] + self.cd[0, 1] * d[..., 1]
+        iy = self.cd[1, 0] * d[..., 0] + self.cd[1, 1] * d[..., 1]
+        out = np.empty(v.shape, dtype=np.float64)
+        if self.proj is None:
+            out[..., 0] = ix + self.crval[0]
+            out[..., 1] = iy + self.crval[1]
+            return out
+        if self.proj == "TAN":
+            r = np.sqrt(ix * ix + iy * iy)
+            phi = np.where(r == 0, 0.0, np.degrees(np.arctan2(ix, -iy)))
+            theta = np.degrees(np.arctan2(180.0 / np.pi, r))
+        else:
+            phi, theta = ix, iy
+        ph, th, dp = np.radians(phi - self.phi_p), np.radians(theta), np.radians(self.delta_p)
+        # eq. (2); the latitude is taken with atan2(z, hypot(x, y)) instead of asin(z) -- the
+        # well-conditioned form wcslib switches to near the poles (sphx2s)
+        xx = np.sin(th) * np.cos(dp) - np.cos(th) * np.sin(dp) * np.cos(ph)
+        yy = -np.cos(th) * np.sin(ph)
+        zz = np.sin(th) * np.sin(dp) + np.cos(th) * np.cos(dp) * np.cos(ph)
+        lon = self.alpha_p + np.degrees(np.arctan2(yy, xx))
+        lat = np.degrees(np.arctan2(zz, np.hypot(xx, yy)))
+        lon = np.where(lon < 0, lon + 360.0, lon)
+        lon = np.where(lon >= 360.0, lon - 360.0, lon)
+        out[..., 0] = lon
+        out[..., 1] = lat
+        return out
+
+    def reverse(self, v):
+        v = np.asarray(v, dtype=np.float64)
+        if self.proj is None:
+            ix = v[..., 0] - self.crval[0]
+            iy = v[..., 1] - self.crval[1]
+        else:
+            al, de, dp = np.radians(v[..., 0] - self.alpha_p), np.radians(v[..., 1]), np.radians(self.delta_p)
+            xx = np.sin(de) * np.cos(dp) - np.cos(de) * np.sin(dp) * np.cos(al)      # eq. (5)
+            yy = -np.cos(de) * np.sin(al)
+            zz = np.sin(de) * np.sin(dp) + np.cos(de) * np.cos(dp) * np.cos(al)
+            phi = self.phi_p + np.degrees(np.arctan2(yy, xx))
+            theta = np.degrees(np.arctan2(zz, np.hypot(xx, yy)))
+            phi = np.where(phi > 180.0, phi - 360.0, phi)
+            phi = np.where(phi <= -180.0, phi + 360.0, phi)
+            if self.proj == "TAN":
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    r = np.where(zz > 0, (180.0 / np.pi) * np.hypot(xx, yy) / zz, np.nan)   # r0 cot(theta)
+                ix = r * np.sin(np.radians(phi))
+                iy = -r * np.cos(np.radians(phi))
+            else:
+                ix, iy = phi, theta
+        px = self.cdinv[0, 0] * ix + self.cdinv[0, 1] * iy
+        py = self.cdinv[1, 0] * ix + self.cdinv[1, 1] * iy
+        out = np.empty(v.shape, dtype=np.float64)
+        out[..., 0] = (px + self.crpix[0]) - 1.0
+        out[..., 1] = (py + self.crpix[1]) - 1.0
+        return out

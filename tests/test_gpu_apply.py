@@ -1,0 +1,132 @@
+"""GPU parity: K3 (streaming Transform.apply) against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import to_oracle, assert_close_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _chains(t):
+    aff = t.Composition([t.Scale([1.5, 2]), t.Rotation(30, unit='deg'), t.Offset([3, 4])])
+    rad = t.Composition([t.Scale([1.5, 2]), t.Radial(origin=[0.1, 0.2]), t.Offset([3, 4])])
+    return {"affine": aff, "affine_inv": aff.inverse(), "radial": rad, "radial_inv": rad.inverse(),
+            "linear_general": t.Linear(matrix=np.array([[1.2, 0.3], [-0.4, 0.9]]),
+                                       pre=np.array([1., 2.]), post=np.array([-3., 4.])),
+            "wrap": t.Wrap(t.Rotation(0.4), t.Offset([10.0, -7.0])),
+            "radial_log": t.Radial(origin=[0.1, 0.2], r0=3.0, ccw=True, pos_only=False)}
+
+
+@pytest.mark.parametrize("name", ["affine", "affine_inv", "linear_general", "wrap"])
+@pytest.mark.parametrize("n", [0, 1, 7, 1000, 100003])
+def test_apply_affine_bitwise(tfm, oracle, name, n):
+    tr = _chains(tfm)[name]
+    v = np.random.default_rng(2).random((n, 2)) * 8192 - 4096
+    for inv in (False, True):
+        got = tr.apply(v, invert=inv)
+        want = oracle.apply(to_oracle(tr), v, invert=inv)
+        assert got.shape == want.shape and got.dtype == np.float64
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["radial", "radial_inv", "radial_log"])
+def test_apply_radial(tfm, oracle, name):
+    tr = _chains(tfm)[name]
+    v = np.random.default_rng(3).random((5000, 2)) * 40 - 20
+    if name != "radial":
+        v = np.abs(v) * np.array([0.15, 0.5])           # (theta, r) style inputs for inverse chains
+    for inv in (False, True):
+        got = tr.apply(v, invert=inv)
+        want = oracle.apply(to_oracle(tr), v, invert=inv)
+        assert_close_rel(got, want, 1e-13, name)
+
+
+def test_extra_components_pass_through(tfm, oracle):
+    """core.py:271-276, 287-292: components beyond the transform's dimension are untouched."""
+    tr = _chains(tfm)["affine"]
+    v = np.random.default_rng(4).random((6, 5, 4)) * 100
+    got = tr.apply(v)
+    want = oracle.apply(to_oracle(tr), v)
+    assert got.shape == v.shape
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[..., 2:], v[..., 2:])
+
+
+def test_roundtrip_and_fast32(tfm):
+    tr = _chains(tfm)["radial"]
+    v = np.random.default_rng(5).random((4096, 2)) * 200 + 5
+    back = tr.invert(tr.apply(v))
+    assert np.allclose(back, v, atol=1e-9)
+    v32 = v.astype(np.float32)
+    got = tr.apply(v32, precision='fp32')
+    assert got.dtype == np.float32
+    assert np.allclose(got, tr.apply(v), rtol=2e-6, atol=1e-4)
+
+
+def test_reference_kats(tfm):
+    """tests/test_02_basic.py:104-113, 139-153, 209-223 of the reference."""
+    assert all(tfm.Scale(np.array([1, 2])).apply(np.array([10, 20])) == np.array([10, 40]))
+    assert all(tfm.Scale(3).apply(np.array([5, 50])) == np.array([15, 150]))
+    a = tfm.Rotation(90, unit='deg')
+    d0 = np.array([[1, 0], [0, 1]])
+    d1 = a.apply(d0)
+    assert np.all(np.isclose(d1, np.array([[0, 1], [-1, 0]]), atol=1e-15))
+    assert np.all(np.isclose(a.invert(d1), d0, atol=1e-15))
+    x = np.arange(4.).reshape(2, 2)
+    b = tfm.Radial(origin=[130, 130])
+    assert np.all(np.isclose(np.array([[131.0, 130.0], [128.75, 127.27]]), b.invert(x), atol=1e-2))
+    assert np.all(np.isclose(np.array([[2.3600555, 183.14202], [2.360116, 180.31362]]), b.apply(x), atol=1e-2))
+    cd = tfm.Radial(origin=[130, 130], r0=5)
+    assert np.allclose(np.array([[2.3600555, 3.600824], [2.360116, 3.5852597]]), cd.apply(x), atol=1e-2)
+    assert np.allclose(np.array([[143.59141, 130], [88.207337, 38.681365]]), cd.invert(x), atol=1e-2)
+    g = np.mgrid[0:7, 0:7].T - 3
+    tr = tfm.Radial()
+    bb = tr.apply(g)
+    assert np.isclose(bb[0, -1, 0], 0.25 * np.pi, atol=1e-5) and np.isclose(bb[-1, 0, 0], 1.25 * np.pi, atol=1e-5)
+    assert np.all(np.isclose(g, tr.invert(bb), atol=1e-10))
+
+
+def test_direction_and_dimension_errors(tfm):
+    with pytest.raises(AssertionError):
+        tfm.Scale([0.0, 1.0]).invert(np.zeros((3, 2)))
+    with pytest.raises(ValueError):
+        tfm.Scale(2.0).apply(np.zeros((3, 1)))
+
+
+def test_wcs_linear_pin(tfm, oracle):
+    """tests/test_01_core.py:160-169: WCS(sample.fits).apply([[0,0]]) ~ [[-386.15825, -676.1092]].
+    The header values are those of the reference's sample.fits."""
+    hdr = {'NAXIS': 2, 'NAXIS1': 485, 'NAXIS2': 512, 'CTYPE1': 'Solar-X', 'CTYPE2': 'Solar-Y',
+           'CUNIT1': 'arcsec', 'CUNIT2': 'arcsec', 'CRPIX1': 243, 'CRPIX2': 256.5,
+           'CRVAL1': -178.95728450798, 'CRVAL2': -469.237931837451,
+           'CD1_1': 0.831675615713575, 'CD1_2': 0.0232308034180093,
+           'CD2_1': -0.0232308034180093, 'CD2_2': 0.831675615713575}
+    a = tfm.WCS(hdr)
+    assert a.idim == 2 and a.odim == 2
+    assert a.itype == ['X', 'Y'] and a.iunit == ['Pixels', 'Pixels']
+    assert a.ounit == ['arcsec', 'arcsec'] and a.otype == ['Solar-X', 'Solar-Y']
+    got = a.apply([[0, 0]], 0)
+    assert np.all(np.isclose(got, np.array([[-386.15825, -676.1092]]), atol=1e-4))
+    p = np.random.default_rng(0).random((1000, 2)) * 500
+    w = a.apply(p)
+    assert np.array_equal(w, oracle.apply(to_oracle(a), p))
+    assert np.allclose(a.invert(w), p, atol=1e-9)
+
+
+@pytest.mark.parametrize("proj", ["TAN", "CAR"])
+@pytest.mark.parametrize("crval", [(150.0, 2.2), (10.0, -45.0), (0.3, 0.0), (200.0, 60.0)])
+def test_wcs_projections(tfm, oracle, proj, crval):
+    """TAN / CAR: PARITY UNPINNED by the reference (astropy absent); GPU vs the independent
+    Euler-angle restatement in the oracle, tolerance 1e-9 pixel / 1e-11 degree."""
+    hdr = {'NAXIS': 2, 'NAXIS1': 4096, 'NAXIS2': 4096, 'CTYPE1': 'RA---' + proj, 'CTYPE2': 'DEC--' + proj,
+           'CRPIX1': 2048.5, 'CRPIX2': 2048.5, 'CRVAL1': crval[0], 'CRVAL2': crval[1],
+           'CDELT1': -0.0004, 'CDELT2': 0.0004, 'CUNIT1': 'deg', 'CUNIT2': 'deg'}
+    a = tfm.WCS(hdr)
+    p = np.random.default_rng(1).random((4000, 2)) * 4096
+    w = a.apply(p)
+    ow = oracle.apply(to_oracle(a), p)
+    dlon = (w[:, 0] - ow[:, 0] + 180.0) % 360.0 - 180.0
+    assert np.abs(dlon).max() < 1e-11 and np.abs(w[:, 1] - ow[:, 1]).max() < 1e-11
+    back = a.invert(w)
+    assert np.abs(back - p).max() < 1e-8
+    assert np.abs(a.invert(ow) - oracle.apply(to_oracle(a), ow, invert=True)).max() < 1e-8

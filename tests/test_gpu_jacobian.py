@@ -1,0 +1,109 @@
+"""GPU parity: K2 (Jacobian-adaptive anti-aliased resampler) against the oracle's repaired
+restatement of interpND_grid / interpND_jacobian (helpers.pyx:1293-1803).
+
+PARITY UNPINNED by the reference for this kernel (it ships non-functional).
+Tolerances: fp64 mode 1e-11 relative (the sums are in the oracle's order; exp/log/atan2 differ
+from glibc by <= 2 ulp), fp32 fast path 2e-4 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import to_oracle, assert_close_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _polar(t, ny, nx, origin):
+    rmax = np.hypot(*origin) * 1.02
+    return t.Composition([t.Scale([nx / (2 * np.pi), ny / rmax]), t.Radial(origin=list(origin))])
+
+
+@pytest.mark.parametrize("filt,letter", [('g', 'G'), ('h', 'H'), ('t', 'R'), ('l', 'L')])
+@pytest.mark.parametrize("bound", ['t', 'e', 'p', 'm'])
+def test_affine_downsample(tfm, oracle, filt, letter, bound):
+    ny, nx = 45, 61
+    src = np.random.default_rng(0).random((ny, nx))
+    tr = tfm.Composition([tfm.Scale([0.45, 0.7]), tfm.Rotation(20, unit='deg'), tfm.Offset([-30.0, -22.0])])
+    got = tr.resample(src, method=letter, bound=bound)
+    want = oracle.resample_jacobian(to_oracle(tr), src, method=filt, bound=bound)
+    assert got.dtype == np.float64 and got.shape == want.shape
+    assert_close_rel(got, want, 1e-11, "%s/%s" % (filt, bound))
+
+
+@pytest.mark.parametrize("shape", [(33, 33), (64, 96), (40, 65), (3, 3), (9, 129)])
+def test_polar_unwrap_with_jump_detection(tfm, oracle, shape):
+    """The polar unwrap has the 2*pi branch cut that jump_detect exists for; odd shapes exercise
+    the grid-edge rules (edge cells use 2x3 lags, edge pixels copy their neighbour's Jacobian) and
+    the tile whose first column is the last grid column (65, 129, 33)."""
+    ny, nx = shape
+    src = np.random.default_rng(1).random((48, 56)).astype(np.float32)
+    tr = _polar(tfm, ny, nx, (27.5, 23.5))
+    got = tr.resample(src, method='G', shape=shape)
+    want = oracle.resample_jacobian(to_oracle(tr), src, method='g', shape=shape)
+    assert_close_rel(got, want, 1e-11, str(shape))
+
+
+@pytest.mark.parametrize("jd", [0, 4.0, 1.5])
+def test_jump_threshold_variants(tfm, oracle, jd):
+    src = np.random.default_rng(2).random((40, 40))
+    tr = _polar(tfm, 48, 48, (19.5, 19.5))
+    got = tr.resample(src, method='G', shape=(48, 48), jump_detect=jd)
+    want = oracle.resample_jacobian(to_oracle(tr), src, method='g', shape=(48, 48), jump_detect=jd)
+    assert_close_rel(got, want, 1e-11, "jd=%s" % jd)
+
+
+def test_oblur_and_padpow(tfm, oracle):
+    src = np.random.default_rng(3).random((30, 30))
+    tr = tfm.Composition([tfm.Scale(0.6, dim=2), tfm.Offset([-1.0, -2.0])])
+    for kw in (dict(oblur=1.7), dict(pad_pow=4), dict(oblur=0.8, pad_pow=12)):
+        got = tr.resample(src, method='G', **kw)
+        want = oracle.resample_jacobian(to_oracle(tr), src, method='g', **kw)
+        assert_close_rel(got, want, 1e-11, str(kw))
+
+
+def test_constant_image_is_reproduced(tfm):
+    """Weighted mean of a constant is the constant (under 'e' no tap is dropped)."""
+    src = np.full((64, 64), 3.25)
+    tr = _polar(tfm, 64, 64, (31.5, 31.5))
+    out = tr.resample(src, method='G', bound='e')
+    assert np.allclose(out, 3.25, rtol=0, atol=1e-12)
+
+
+def test_fast32(tfm, oracle):
+    src = np.random.default_rng(4).random((96, 96)).astype(np.float32)
+    tr = _polar(tfm, 128, 128, (47.5, 47.5))
+    got = tr.resample(src, method='G', shape=(128, 128), precision='fp32')
+    want = oracle.resample_jacobian(to_oracle(tr), src, method='g', shape=(128, 128))
+    assert got.dtype == np.float32
+    assert_close_rel(got, want, 2e-4, "fast32")
+
+
+def test_interpND_grid_entry_point(tfm, oracle):
+    """helpers.pyx:1293: a precomputed index array instead of a transform chain."""
+    src = np.random.default_rng(5).random((40, 50))
+    idx = to_oracle(_polar(tfm, 36, 44, (24.5, 19.5))).reverse(oracle.pixel_grid(36, 44))
+    got = tfm.interpND_grid(src, idx, method='g')
+    want = oracle.interp_grid_jacobian(src, idx, method='g')
+    assert_close_rel(got, want, 1e-11, "interpND_grid")
+    with pytest.raises(ValueError):
+        tfm.interpND_grid(src, idx, method='q')
+
+
+def test_svd_hooks(tfm, oracle):
+    """tests/test_03_helpers.py:667-711 of the reference, on the device routines."""
+    for M in (np.array(((1.0, 0.0), (0, 1))), np.array(((0, 2.0), (0.333, 0))), np.array(((1.0, 2.0), (4, 3)))):
+        U, s, V = np.zeros((2, 2)), np.zeros(2), np.zeros((2, 2))
+        M2 = np.zeros((2, 2))
+        tfm.svd2x2(M, U, s, V)
+        tfm.svc2x2(U, s, V, M2)
+        assert np.all(np.isclose(M2, M, 1e-8))
+        assert s[0] >= s[1] >= 0
+        oU, os_, oV = oracle.svd2x2(M)
+        assert np.allclose(U, oU, atol=1e-14) and np.allclose(s, os_, atol=1e-14) and np.allclose(V, oV, atol=1e-14)
+    M = np.array(((0, 2.0), (0.333, 0)))
+    tfm.svd2x2(M, U, s, V)
+    assert np.isclose(s[0], 2, 1e-8) and np.isclose(s[1], 0.333, 1e-8)
+    M = np.array(((1.0, 2.0), (4, 3)))
+    tfm.svd2x2(M, U, s, V)
+    tfm.svc2x2(V, 1.0 / s, U, M2)
+    assert np.all(np.isclose(np.matmul(M, M2), np.eye(2), 1e-8))

@@ -1,0 +1,184 @@
+"""GPU parity: K1 (fused chain + nearest/linear/cubic gather) against the oracle, through the
+Python host side and the C ABI.  Bars (BASELINE.json north_star):
+  nearest: bit-exact;  linear/cubic: <= 1e-12 relative in the fp64 mode (asserted bit-exact for
+  affine chains, whose arithmetic convention is fully defined), <= 1e-5 relative in the fp32 path.
+"""
+import numpy as np
+import pytest
+
+from conftest import to_oracle, assert_close_rel
+
+pytestmark = pytest.mark.gpu
+
+BOUNDS = ['t', 'e', 'p', 'm', ['p', 'e'], ['m', 't'], 'extend', 'truncate']
+
+
+def _affine(t, ny, nx):
+    return t.Composition([t.Scale(1.3, dim=2), t.Rotation(30, unit='deg'),
+                          t.Offset([-nx / 2.0, -ny / 2.0])])
+
+
+def _src(ny, nx, dtype, seed=0):
+    return np.random.default_rng(seed).random((ny, nx)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("method", ['nearest', 'linear', 'cubic'])
+@pytest.mark.parametrize("bound", BOUNDS)
+def test_affine_exact_bitwise(tfm, oracle, dtype, method, bound):
+    ny, nx = 67, 93                                   # ragged: not multiples of the 32x32 tile
+    src = _src(ny, nx, dtype)
+    tr = _affine(tfm, ny, nx)
+    got = tr.resample(src, method=method, bound=bound)
+    want = oracle.resample(to_oracle(tr), src, method=method, bound=bound)
+    assert got.dtype == want.dtype
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), "max diff %g" % np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("method", ['nearest', 'linear', 'cubic'])
+def test_affine_fast32(tfm, oracle, method):
+    ny, nx = 300, 411
+    src = _src(ny, nx, np.float32, 3)
+    tr = _affine(tfm, ny, nx)
+    got = tr.resample(src, method=method, precision='fp32')
+    want = oracle.resample(to_oracle(tr), src, method=method)
+    assert got.dtype == np.float32
+    if method == 'nearest':
+        assert np.array_equal(got, want.astype(np.float32))
+    else:
+        assert_close_rel(got, want, 1e-5, method)
+
+
+@pytest.mark.parametrize("shape", [(5, 7), (40, 33), (64, 64), (1, 1), (200, 3)])
+def test_output_shape_argument(tfm, oracle, shape):
+    src = _src(37, 53, np.float64, 1)
+    tr = tfm.Composition([tfm.Scale([0.7, 1.9]), tfm.Offset([-3.0, 2.0])])
+    for m in ('n', 'l', 'c'):
+        got = tr.resample(src, method=m, shape=shape)
+        want = oracle.resample(to_oracle(tr), src, method=m, shape=shape)
+        assert got.shape == tuple(shape)
+        assert np.array_equal(got, want)
+
+
+def test_empty_output(tfm):
+    src = _src(8, 8, np.float32)
+    out = tfm.Scale(2.0).resample(src, method='linear', shape=(0, 5))
+    assert out.shape == (0, 5)
+
+
+@pytest.mark.parametrize("kw", [dict(origin=[31.5, 25.5]), dict(origin=[31.5, 25.5], r0=2.0),
+                                dict(ccw=True, pos_only=False, origin=[20.0, 30.0]),
+                                dict(unit='deg', origin=[31.5, 25.5])])
+@pytest.mark.parametrize("method", ['nearest', 'linear', 'cubic'])
+def test_radial_unwrap(tfm, oracle, kw, method):
+    ny, nx = 52, 64
+    src = _src(ny, nx, np.float64, 2)
+    rad = tfm.Radial(**kw)
+    coeff = rad.params['ang_coeff']
+    if kw.get('r0'):
+        sc = tfm.Scale([nx / (2 * np.pi) * coeff, ny / 3.0])
+    else:
+        sc = tfm.Scale([nx / (2 * np.pi) * coeff, ny / 40.0])
+    tr = tfm.Composition([sc, rad])
+    got = tr.resample(src, method=method, bound='t')
+    want = oracle.resample(to_oracle(tr), src, method=method, bound='t')
+    if method == 'nearest':
+        # CUDA's sincos/exp differ from glibc's by <= 2 ulp: an index can only flip within a hair
+        # of a half-integer.  Count mismatches and demand that each is such a near-tie.
+        bad = np.argwhere(got != want)
+        coords = to_oracle(tr).reverse(oracle.pixel_grid(ny, nx))
+        for (y, x) in bad:
+            frac = np.abs((coords[y, x] + 0.5) - np.round(coords[y, x] + 0.5))
+            assert frac.min() < 1e-9, "non-tie mismatch at %s: %s" % ((y, x), coords[y, x])
+        assert len(bad) <= 4
+    else:
+        assert_close_rel(got, want, 1e-12, method)
+
+
+def test_reference_kat_resample(tfm):
+    """tests/test_01_core.py:259-294 of the reference, through the GPU path."""
+    a = np.zeros([7, 5])
+    a[2, 2] = 1
+    b = tfm.Identity().resample(a, method='nearest')
+    assert b.shape == (7, 5) and np.all(b == a)
+    b = tfm.Identity().resample(a, shape=[5, 5], method='nearest')
+    assert b.shape == (5, 5) and np.all(a[0:5, 0:5] == b)
+    b = tfm.Scale(2.5, post=[2, 2], pre=[-2, -2]).resample(a, method='neares')
+    chk = np.zeros([7, 5])
+    chk[1:4, 1:4] = 1
+    assert np.all(b == chk)
+    b = tfm.Scale([1, 2.5], post=[2, 2], pre=[-2, -2]).resample(a, method='nearest')
+    chk = np.zeros([7, 5])
+    chk[1:4, 2] = 1
+    assert np.all(b == chk)
+
+
+def test_forbid_boundary_raises(tfm):
+    src = _src(16, 16, np.float64)
+    with pytest.raises(ValueError):
+        tfm.Offset([5.0, 0.0]).resample(src, method='nearest', bound='f')
+    out = tfm.Identity().resample(src, method='nearest', bound='f')
+    assert np.array_equal(out, src)
+
+
+def test_errors_match_reference(tfm):
+    src = _src(16, 16, np.float64)
+    with pytest.raises(ValueError):
+        tfm.Scale(2.0).resample(src, method='quux')
+    with pytest.raises(ValueError):
+        tfm.Scale(2.0).resample(src, method='n', bound='x')
+    with pytest.raises(ValueError):
+        tfm.Scale(2.0).resample("not an array")
+    with pytest.raises(AssertionError):
+        tfm.Scale([0.0, 1.0]).resample(src)             # not invertible (basic.py:321)
+    with pytest.raises(NotImplementedError):
+        tfm.Scale(2.0).resample(src, method='sinc')      # outside the GPU path: loud, no fallback
+
+
+def test_nan_and_absurd_coordinates(tfm, oracle):
+    """interpND through the coordinate-lookup opcode with NaN / inf / 1e300 coordinates."""
+    rng = np.random.default_rng(5)
+    src = rng.random((37, 53))
+    idx = rng.random((40, 45, 2)) * np.array([70, 60]) - 8
+    idx[3, 4] = [np.nan, 2]
+    idx[5, 6] = [1e300, -1e300]
+    idx[7, 7] = [np.inf, 3]
+    idx[8, 8] = [-0.5, 0.5]
+    idx[9, 9] = [36.5, 52.5]
+    for m in 'nlc':
+        for b in ['t', 'e', 'p', 'm', ['p', 'e']]:
+            for fv in (0, -9):
+                got = tfm.interpND(src, idx, method=m, bound=b, fillvalue=fv)
+                want = oracle.interpND(src, idx, method=m, bound=b, fillvalue=fv)
+                same = (got == want) | (np.isnan(got) & np.isnan(want))
+                assert same.all(), (m, b, fv, np.argwhere(~same)[:5])
+
+
+def test_image_cube_planes(tfm, oracle):
+    cube = np.random.default_rng(7).random((3, 40, 50)).astype(np.float32)
+    tr = tfm.Composition([tfm.Rotation(0.3), tfm.Offset([-25.0, -20.0])])
+    got = tr.resample(cube, method='linear')
+    for k in range(3):
+        want = oracle.resample(to_oracle(tr), cube[k], method='linear')
+        assert np.array_equal(got[k], want)
+
+
+def test_full_size_properties(tfm):
+    """BASELINE config 2 size (4096^2): size-independent properties.
+    identity map reproduces the image; a pure integer offset is a shifted copy; linearity."""
+    import torch
+    n = 4096
+    g = torch.Generator(device='cuda').manual_seed(0)
+    src = torch.rand((n, n), generator=g, device='cuda', dtype=torch.float32)
+    out = tfm.Identity().resample(src, method='linear', precision='fp32')
+    assert torch.equal(out, src)
+    out = tfm.Offset([3.0, -5.0]).resample(src, method='nearest', precision='fp32')
+    # out[y, x] = src[y + 5, x - 3]
+    assert torch.equal(out[:n - 5, 3:], src[5:, :n - 3])
+    assert float(out[n - 5:, :].abs().max()) == 0.0 and float(out[:, :3].abs().max()) == 0.0
+    tr = tfm.Composition([tfm.Scale(1.3, dim=2), tfm.Rotation(30, unit='deg'), tfm.Offset([-2048, -2048])])
+    a = tr.resample(src, method='linear', precision='fp32')
+    b = tr.resample(2 * src, method='linear', precision='fp32')
+    assert torch.allclose(b, 2 * a, rtol=1e-6, atol=1e-6)
+    assert a.dtype == torch.float32 and a.shape == (n, n)

@@ -1,0 +1,288 @@
+"""Linear / Scale / Rotation / Offset and Radial: parameter objects for the GPU opcode chain.
+
+Host-side mirror of /root/reference/transform/basic.py:12-716 -- same constructors, the same
+`params` dictionaries (pre, post, matrix, matinv, ...), the same validation errors.  The
+arithmetic of _forward/_reverse (basic.py:141-176, 670-711) is not restated here: `_lower`
+packs the parameters into a tfm_op and the CUDA library evaluates it.
+"""
+import numpy as np
+
+from . import _lib as L
+from .core import Transform
+from .units import angular_coefficient
+
+
+def _vec2(v, fill):
+    """1- or 2-vector -> (x, y) with the missing component neutral."""
+    a = np.asarray(v, dtype=np.float64).reshape(-1)
+    return (float(a[0]), float(a[1]) if a.size > 1 else fill)
+
+
+class Linear(Transform):
+    """out = post + matrix x (in + pre)   (basic.py:12-176).  pre, post, matrix all optional."""
+
+    def __init__(self, *, pre=None, post=None, matrix=None, iunit=None, ounit=None,
+                 itype=None, otype=None):
+        idim = odim = None
+        if matrix is not None:
+            if not isinstance(matrix, np.ndarray):
+                raise ValueError("Linear: matrix must be a 2D numpy.ndarray or None")
+            if matrix.ndim != 2:
+                raise ValueError("Linear: matrix must be 2D")
+            odim, idim = matrix.shape
+        idim = self._parse_prepost(idim, pre, 'Linear', 'Pre-offset', 'idim')
+        odim = self._parse_prepost(odim, post, 'Linear', 'Post-offset', 'odim')
+        if matrix is not None:
+            if odim is None:
+                odim = idim
+            elif idim is None:
+                idim = odim
+            elif idim != odim:
+                raise ValueError("Linear: idim and odim must match if no matrix is supplied")
+        idim = 2 if idim is None else idim
+        odim = 2 if odim is None else odim
+        matinv = None
+        if matrix is not None:
+            try:
+                matinv = np.linalg.inv(matrix)           # basic.py:115-119 (C-contiguous result)
+            except Exception:
+                matinv = None
+        self.idim = idim
+        self.odim = odim
+        self.no_forward = False
+        self.no_reverse = matinv is None and matrix is not None
+        self.iunit, self.ounit, self.itype, self.otype = iunit, ounit, itype, otype
+        self.params = {'pre': pre, 'post': post, 'matrix': matrix, 'matinv': matinv}
+
+    def __str__(self):
+        if not hasattr(self, '_strtmp'):
+            self._strtmp = 'Linear'
+        return super().__str__()
+
+    def _parse_prepost(self, dimspec, vec, objname, prepostname, dimname):
+        """basic.py:180-218."""
+        if dimspec is not None and not isinstance(dimspec, np.ndarray):
+            dimspec = np.array(dimspec)
+        if dimspec is not None and dimspec.size > 1:
+            raise ValueError("%s: %s must be a scalar" % (objname, dimname))
+        if vec is not None:
+            if not isinstance(vec, (np.ndarray, list, tuple)):
+                raise ValueError("%s: %s must be a 1-D numpy.ndarray vector or None" % (objname, prepostname))
+            if len(np.shape(vec)) != 1:
+                raise ValueError("%s: %s must be a 1-D vector" % (objname, prepostname))
+            if dimspec is not None and dimspec != np.shape(vec)[0]:
+                raise ValueError("%s: %s size must match %s" % (objname, prepostname, dimname))
+            dimspec = np.shape(vec)[0]
+        return dimspec
+
+    def _lower(self, direction):
+        if self.idim > 2 or self.odim > 2 or self.idim != self.odim:
+            raise NotImplementedError("transform_b200: Linear transforms of dimension > 2 (or "
+                                      "non-square) are outside the GPU hot path")
+        p = self.params
+        op = L.TfmOp()
+        op.kind, op.dir = L.OP_LINEAR, direction
+        flags = 0
+        m = p['matrix'] if direction == L.FWD else p['matinv']
+        if m is not None:
+            m = np.asarray(m)
+            flags |= L.LIN_HAS_MATRIX
+            # np.matmul rounds differently for a transposed view (e.g. Rotation's matinv):
+            # carry the memory order so that the fp64-exact kernel reproduces it
+            if m.ndim == 2 and not m.flags.c_contiguous:
+                flags |= L.LIN_MAT_FORDER
+            mm = np.eye(2)
+            mm[:m.shape[0], :m.shape[1]] = m
+            op.p[0], op.p[1], op.p[2], op.p[3] = (float(mm[0, 0]), float(mm[0, 1]),
+                                                  float(mm[1, 0]), float(mm[1, 1]))
+        if p['pre'] is not None:
+            flags |= L.LIN_HAS_PRE
+            op.p[4], op.p[5] = _vec2(p['pre'], 0.0)
+        if p['post'] is not None:
+            flags |= L.LIN_HAS_POST
+            op.p[6], op.p[7] = _vec2(p['post'], 0.0)
+        op.flags = flags
+        return [op] if flags else []
+
+
+class Scale(Linear):
+    """Diagonal Linear (basic.py:224-336)."""
+
+    def __init__(self, /, scale, dim=None, *, post=None, pre=None, iunit=None, ounit=None,
+                 itype=None, otype=None):
+        dim = self._parse_prepost(dim, pre, 'Scale', 'Pre-offset', 'dim')
+        dim = self._parse_prepost(dim, post, 'Scale', 'Post-offset', 'dim')
+        if pre is not None:
+            pre = pre + np.array(0)
+        if post is not None:
+            post = post + np.array(0)
+        if not isinstance(scale, np.ndarray):
+            scale = np.array(scale) if isinstance(scale, (list, tuple)) else np.array([scale])
+        if scale.ndim > 1:
+            raise ValueError('Scale: scale parameter must be scalar or vector')
+        if dim is not None:
+            dim = int(dim)
+            if scale.shape[0] != dim and scale.shape[0] != 1:
+                raise ValueError('Scale d must agree with size of scale vector')
+            if scale.shape[0] == 1:
+                scale = scale + np.zeros(dim)
+        elif scale.shape[0] == 1:
+            dim = 2
+            scale = scale + np.zeros(2)
+        else:
+            dim = scale.shape[0]
+        m = np.zeros([dim, dim])
+        m1 = np.zeros([dim, dim])
+        nonzero = all(scale != 0)
+        for i in range(dim):
+            m[i, i] = scale[i]
+            if nonzero:
+                m1[i, i] = 1.0 / scale[i]
+        self.idim = dim
+        self.odim = dim
+        self.no_forward = False
+        self.no_reverse = bool(any(scale == 0))
+        self.iunit, self.ounit, self.itype, self.otype = iunit, ounit, itype, otype
+        self.params = {'pre': pre, 'post': post, 'matrix': m, 'matinv': m1, 'scale': scale}
+
+    def __str__(self):
+        self._strtmp = "Linear/Scale (%s)" % (self.params['scale'],)
+        return super().__str__()
+
+
+class Rotation(Linear):
+    """Rotation matrices from axis pairs / Euler angles (basic.py:338-506)."""
+
+    def __init__(self, rot=None, *, post=None, pre=None, euler=None, unit='rad', iunit=None,
+                 ounit=None, itype=None, otype=None):
+        d_offs = self._parse_prepost(None, pre, 'Rotation', 'Pre-offset', 'd')
+        d_offs = self._parse_prepost(d_offs, post, 'Rotation', 'Post-offset', 'd')
+        if rot is None:
+            if euler is None:
+                raise ValueError("Rotation: either rot or euler angles must be specified")
+            if len(euler) != 3:
+                raise ValueError("Rotation: euler angles must have 3 components (axial vector)")
+            rot = np.array([[0, 1, euler[2]], [2, 0, euler[1]], [1, 2, euler[0]]])
+        else:
+            assert euler is None, "Rotation: must specify only one of rot and euler angles"
+            if not isinstance(rot, np.ndarray):
+                rot = np.array(rot)
+        if rot.ndim > 2:
+            raise ValueError("Rotation: rot parameter must be a collection of 3-vectors")
+        if rot.size == 1:
+            rot = np.array([[0, 1, rot]])
+        if rot.ndim == 1:
+            rot = np.expand_dims(rot, 0)
+        fr_axes = rot[:, 0].astype(int)
+        to_axes = rot[:, 1].astype(int)
+        if any(fr_axes == to_axes):
+            raise ValueError('Rotation: invalid axis-to-self rotation is not allowed')
+        coeff, _ = angular_coefficient(unit, "Radial")       # the reference's messages say "Radial"
+        angs = rot[:, 2] * coeff
+        d_fr = int(max(fr_axes.max(), to_axes.max())) + 1
+        if d_offs is None:
+            d = d_fr
+        elif d_offs < d_fr:
+            raise ValueError('Rotation: offset vectors must have at least the dims of the rotation')
+        else:
+            d = int(d_offs)
+        out = np.eye(d)
+        for i in range(fr_axes.shape[0])[::-1]:              # last listed rotation acts first
+            m = np.eye(d)
+            c, s = np.cos(angs[i]), np.sin(angs[i])
+            m[fr_axes[i], fr_axes[i]] = c
+            m[to_axes[i], to_axes[i]] = c
+            m[to_axes[i], fr_axes[i]] = s
+            m[fr_axes[i], to_axes[i]] = -s
+            out = np.matmul(m, out)
+        self.idim = d
+        self.odim = d
+        self.no_forward = False
+        self.no_reverse = False
+        self.iunit, self.ounit, self.itype, self.otype = iunit, ounit, itype, otype
+        # matinv is a transposed VIEW, as in the reference (basic.py:501): its memory order
+        # decides how NumPy's gemv rounds, and _lower carries that into the opcode
+        self.params = {'pre': pre, 'post': post, 'matrix': out, 'matinv': out.transpose()}
+
+    def __str__(self):
+        self._strtmp = "Linear/Rotation"
+        return super().__str__()
+
+
+class Offset(Linear):
+    """data + offset (basic.py:508-551)."""
+
+    def __init__(self, offset):
+        if not isinstance(offset, np.ndarray):
+            offset = offset + np.array(0)
+        if len(np.shape(offset)) > 1:
+            raise ValueError("Offset: input must be a vector")
+        d = np.shape(offset)[0]
+        self.idim = d
+        self.odim = d
+        self.no_forward = False
+        self.no_reverse = False
+        self.iunit = self.ounit = self.itype = self.otype = None
+        self.params = {'pre': offset, 'post': None, 'matrix': None, 'matinv': None}
+
+    def __str__(self):
+        self._strtmp = "Linear/Offset"
+        return super().__str__()
+
+
+class Radial(Transform):
+    """Cartesian -> (azimuth, radius | ln radius/r0) and back (basic.py:553-716)."""
+
+    def __init__(self, *, r0=None, iunit=None, ounit=None, itype=None, otype=None, idim=2, odim=2,
+                 origin=np.zeros(2), unit='radian', ccw=False, pos_only=True):
+        if not isinstance(origin, np.ndarray):
+            origin = np.array([origin])                      # basic.py:620-621 (note the extra axis)
+        if r0 is not None:
+            otype = ["Azimuth", "Ln radius"]
+            r0_sq = r0 * r0
+        else:
+            otype = ["Azimuth", "Radius"]
+            r0_sq = None
+        coeff, uname = angular_coefficient(unit, "Radial")
+        if ounit is None:
+            ounit = ["rad", None]                            # unit of the converted quantity (basic.py:646-647)
+        elif ounit[0] is None:
+            ounit[0] = "rad"
+        self.idim = idim
+        self.odim = odim
+        self.no_forward = False
+        self.no_reverse = False
+        self.iunit, self.ounit, self.itype, self.otype = iunit, ounit, itype, otype
+        self.params = {'origin': origin, 'r0': r0, 'r0_sq': r0_sq, 'ang_coeff': coeff,
+                       'ccw': ccw, 'pos': pos_only}
+
+    def _lower(self, direction):
+        p = self.params
+        if self.idim != 2 or self.odim != 2:
+            raise NotImplementedError("transform_b200: Radial is on the GPU path for 2-D only")
+        origin = np.asarray(p['origin'], dtype=np.float64)
+        o2 = origin[0:2]                                     # basic.py:674, 708 (slices the FIRST axis)
+        ox, oy = _vec2(o2.reshape(-1)[0:2], 0.0)
+        op = L.TfmOp()
+        op.kind, op.dir = L.OP_RADIAL, direction
+        flags = 0
+        if p['ccw']:
+            flags |= L.RAD_CCW
+        if p['pos']:
+            flags |= L.RAD_POS_ONLY
+        if p['r0'] is not None:
+            flags |= L.RAD_R0_NOT_NONE
+            if p['r0']:
+                flags |= L.RAD_R0_TRUTHY
+            op.p[2] = float(p['r0'])
+        if not np.all(o2 == 0):
+            flags |= L.RAD_ORIGIN_NONZERO
+        op.flags = flags
+        op.p[0], op.p[1] = ox, oy
+        op.p[3] = float(p['ang_coeff'])
+        return [op]
+
+    def __str__(self):
+        if not hasattr(self, '_strtmp'):
+            self._strtmp = 'Radial'
+        return super().__str__()

@@ -1,0 +1,172 @@
+// tfm_apply.cu -- K3: streaming Transform.apply over [n_vec, vec_len] arrays.
+//
+// Replaces Transform.apply / invert (core.py:218-315) for 2-D transforms: the first two
+// components go through the chain in registers, components 2.. are copied through
+// (core.py:271-276, 287-292).  The reference materialises one full float64 temporary per chain
+// stage; here every vector is read once and written once (HBM-bound for affine chains,
+// fp64-pipe-bound once a chain contains sincos/atan2).
+//
+// Layout: interleaved (x, y[, extras]) rows, densely packed.  vec_len == 2 is the hot case:
+// one thread moves whole 16-byte packets (one fp64 vector, or two fp32 vectors) so that every
+// warp access is a contiguous 512-byte run; a persistent grid-stride loop (grid = SMs x resident
+// CTAs) keeps UNROLL packets in flight per thread.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tfm_chain.cuh"
+#include "tfm_common.cuh"
+
+namespace tfm {
+
+struct ApplyParams {
+    const void *in;
+    void *out;
+    long long n_vec;
+    int vec_len;
+    ChainDev chain;
+};
+
+template <class A, int UNROLL>
+__global__ void __launch_bounds__(256)
+k_apply_f64x2(const __grid_constant__ ApplyParams P)
+{
+    const double2 *in = static_cast<const double2 *>(P.in);
+    double2 *out = static_cast<double2 *>(P.out);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < P.n_vec; i += UNROLL * stride) {
+        double2 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = __ldcs(in + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            chain_eval<A>(P.chain, v[u].x, v[u].y);
+            __stcs(out + i + u * stride, v[u]);
+        }
+    }
+    for (; i < P.n_vec; i += stride) {
+        double2 v = __ldcs(in + i);
+        chain_eval<A>(P.chain, v.x, v.y);
+        __stcs(out + i, v);
+    }
+}
+
+// two fp32 vectors per 16-byte packet
+template <class A, int UNROLL>
+__global__ void __launch_bounds__(256)
+k_apply_f32x2(const __grid_constant__ ApplyParams P)
+{
+    const long long n_pk = P.n_vec >> 1;
+    const float4 *in = static_cast<const float4 *>(P.in);
+    float4 *out = static_cast<float4 *>(P.out);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < n_pk; i += UNROLL * stride) {
+        float4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = __ldcs(in + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            double x0 = v[u].x, y0 = v[u].y, x1 = v[u].z, y1 = v[u].w;
+            chain_eval<A>(P.chain, x0, y0);
+            chain_eval<A>(P.chain, x1, y1);
+            __stcs(out + i + u * stride, make_float4((float)x0, (float)y0, (float)x1, (float)y1));
+        }
+    }
+    for (; i < n_pk; i += stride) {
+        float4 v = __ldcs(in + i);
+        double x0 = v.x, y0 = v.y, x1 = v.z, y1 = v.w;
+        chain_eval<A>(P.chain, x0, y0);
+        chain_eval<A>(P.chain, x1, y1);
+        __stcs(out + i, make_float4((float)x0, (float)y0, (float)x1, (float)y1));
+    }
+    if ((P.n_vec & 1) && blockIdx.x == 0 && threadIdx.x == 0) {       // odd tail vector
+        const float *fi = static_cast<const float *>(P.in) + 2 * (P.n_vec - 1);
+        float *fo = static_cast<float *>(P.out) + 2 * (P.n_vec - 1);
+        double x = fi[0], y = fi[1];
+        chain_eval<A>(P.chain, x, y);
+        fo[0] = (float)x;
+        fo[1] = (float)y;
+    }
+}
+
+// general vec_len (>= 2): one thread per vector, extras copied through
+template <class A, typename T>
+__global__ void __launch_bounds__(256)
+k_apply_generic(const __grid_constant__ ApplyParams P)
+{
+    const T *in = static_cast<const T *>(P.in);
+    T *out = static_cast<T *>(P.out);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int L = P.vec_len;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_vec; i += stride) {
+        const T *vi = in + i * L;
+        T *vo = out + i * L;
+        double x = (double)vi[0], y = (double)vi[1];
+        chain_eval<A>(P.chain, x, y);
+        for (int k = 2; k < L; ++k) vo[k] = vi[k];
+        vo[0] = (T)x;
+        vo[1] = (T)y;
+    }
+}
+
+static int resident_grid(const void *kernel, long long work_items)
+{
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
+    long long want = (work_items + 255) / 256;
+    long long grid = (long long)sms * per_sm;              // a whole number of waves, persistent
+    if (want < grid) grid = want;
+    return (int)(grid < 1 ? 1 : grid);
+}
+
+int apply_dispatch(const tfm_apply_args *a, cudaStream_t st)
+{
+    if (!a || a->abi_version != TFM_ABI_VERSION) return TFM_EVALUE;
+    if (a->n_ops < 0 || a->n_ops > TFM_MAX_OPS || (a->n_ops && !a->chain)) return TFM_EVALUE;
+    if (a->n_vec < 0 || a->vec_len < 2) return TFM_EVALUE;          // core.py:268-269, 284-285
+    if (a->dtype != TFM_F32 && a->dtype != TFM_F64) return TFM_EVALUE;
+    if (a->n_vec == 0) return TFM_OK;
+    if (!a->in || !a->out) return TFM_EVALUE;
+    for (int i = 0; i < a->n_ops; ++i)
+        if (a->chain[i].kind < TFM_OP_IDENTITY || a->chain[i].kind > TFM_OP_INDEX) return TFM_EVALUE;
+
+    ApplyParams P;
+    P.in = a->in; P.out = a->out; P.n_vec = a->n_vec; P.vec_len = a->vec_len;
+    P.chain.n = a->n_ops; P.chain.pad = 0;
+    for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
+
+    const bool exact = (a->precision == TFM_PREC_EXACT64);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a->in) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0;
+    const char *name;
+#define TFM_LAUNCH(KERNEL, ITEMS)                                                       \
+    do {                                                                                \
+        int grid = resident_grid((const void *)KERNEL, (ITEMS));                        \
+        KERNEL<<<grid, 256, 0, st>>>(P);                                                \
+    } while (0)
+    if (a->vec_len == 2 && aligned && a->dtype == TFM_F64) {
+        if (exact) TFM_LAUNCH((k_apply_f64x2<Exact, 4>), a->n_vec);
+        else       TFM_LAUNCH((k_apply_f64x2<Fast, 4>), a->n_vec);
+        name = "k_apply_f64x2";
+    } else if (a->vec_len == 2 && aligned && a->dtype == TFM_F32) {
+        if (exact) TFM_LAUNCH((k_apply_f32x2<Exact, 4>), a->n_vec / 2 + 1);
+        else       TFM_LAUNCH((k_apply_f32x2<Fast, 4>), a->n_vec / 2 + 1);
+        name = "k_apply_f32x2";
+    } else if (a->dtype == TFM_F64) {
+        if (exact) TFM_LAUNCH((k_apply_generic<Exact, double>), a->n_vec);
+        else       TFM_LAUNCH((k_apply_generic<Fast, double>), a->n_vec);
+        name = "k_apply_generic<f64>";
+    } else {
+        if (exact) TFM_LAUNCH((k_apply_generic<Exact, float>), a->n_vec);
+        else       TFM_LAUNCH((k_apply_generic<Fast, float>), a->n_vec);
+        name = "k_apply_generic<f32>";
+    }
+#undef TFM_LAUNCH
+    count_launch();
+    set_last_kernel(name);
+    return cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
+}
+
+}  // namespace tfm

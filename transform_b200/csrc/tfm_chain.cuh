@@ -1,0 +1,232 @@
+// tfm_chain.cuh -- in-register evaluation of a flattened, direction-resolved transform chain.
+//
+// Replaces the whole-array temporaries of Composition._forward/_reverse (core.py:1551-1559),
+// Linear (basic.py:141-176), Radial (basic.py:670-711) and the linear/TAN/CAR part of WCS
+// (core.py:1719-1747): one (x,y) pair lives in two fp64 registers from pixel index to tap.
+//
+// Two arithmetic policies:
+//   Exact  every operation is an explicitly rounded intrinsic in the reference's order, so nvcc
+//          cannot contract mul+add into fma; the only fma is the gemv one NumPy itself performs
+//          (see include/tfm_b200.h, TFM_LIN_MAT_FORDER).  Affine chains are bit-identical to the
+//          reference; transcendental ops differ from glibc by <= 2 ulp (CUDA libdevice).
+//   Fast   same formulas, contraction allowed (the host has already pre-composed affine runs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tfm_b200.h"
+
+namespace tfm {
+
+struct ChainDev {
+    int32_t n;
+    int32_t pad;
+    tfm_op ops[TFM_MAX_OPS];
+};
+
+struct Exact {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static constexpr bool exact = true;
+};
+
+struct Fast {
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    static constexpr bool exact = false;
+};
+
+// np.remainder for floats (npy_divmod): result takes the sign of the divisor; a zero result is
+// copysign(0, b).  Used for `out[...,0] %= 2*np.pi` (basic.py:683-684).
+__device__ __forceinline__ double np_remainder(double a, double b)
+{
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if ((b < 0.0) != (m < 0.0)) m = __dadd_rn(m, b);
+    } else {
+        m = copysign(0.0, b);
+    }
+    return m;
+}
+
+template <class A>
+__device__ __forceinline__ void matvec2(const double *m, bool f_order, double &x, double &y)
+{
+    double ox, oy;
+    if (f_order) {          // transposed view in the reference: fma(m[i][1], y, fl(m[i][0]*x))
+        ox = A::fma(m[1], y, A::mul(m[0], x));
+        oy = A::fma(m[3], y, A::mul(m[2], x));
+    } else {                // C-contiguous: fma(m[i][0], x, fl(m[i][1]*y))
+        ox = A::fma(m[0], x, A::mul(m[1], y));
+        oy = A::fma(m[2], x, A::mul(m[3], y));
+    }
+    x = ox;
+    y = oy;
+}
+
+template <class A>
+__device__ __forceinline__ void op_linear(const tfm_op &op, double &x, double &y)
+{
+    const int f = op.flags;
+    if (op.dir == TFM_FWD) {                                   // basic.py:141-158
+        if (f & TFM_LIN_HAS_PRE) { x = A::add(x, op.p[4]); y = A::add(y, op.p[5]); }
+        if (f & TFM_LIN_HAS_MATRIX) matvec2<A>(op.p, (f & TFM_LIN_MAT_FORDER) != 0, x, y);
+        if (f & TFM_LIN_HAS_POST) { x = A::add(x, op.p[6]); y = A::add(y, op.p[7]); }
+    } else {                                                   // basic.py:160-176
+        if (f & TFM_LIN_HAS_POST) { x = A::sub(x, op.p[6]); y = A::sub(y, op.p[7]); }
+        if (f & TFM_LIN_HAS_MATRIX) matvec2<A>(op.p, (f & TFM_LIN_MAT_FORDER) != 0, x, y);
+        if (f & TFM_LIN_HAS_PRE) { x = A::sub(x, op.p[4]); y = A::sub(y, op.p[5]); }
+    }
+}
+
+template <class A>
+__device__ __forceinline__ void op_radial(const tfm_op &op, double &x, double &y)
+{
+    const int f = op.flags;
+    if (op.dir == TFM_FWD) {                                   // basic.py:670-690
+        if (f & TFM_RAD_ORIGIN_NONZERO) { x = A::sub(x, op.p[0]); y = A::sub(y, op.p[1]); }
+        double th = atan2((f & TFM_RAD_CCW) ? y : -y, x);
+        th = A::div(th, op.p[3]);
+        if (f & TFM_RAD_POS_ONLY) th = np_remainder(th, 6.283185307179586);
+        double r2 = A::add(A::mul(x, x), A::mul(y, y));
+        double r;
+        if (f & TFM_RAD_R0_TRUTHY)
+            r = A::mul(0.5, log(A::div(r2, A::mul(op.p[2], op.p[2]))));
+        else
+            r = __dsqrt_rn(r2);
+        x = th;
+        y = r;
+    } else {                                                   // basic.py:692-711
+        double d0 = A::mul(x, op.p[3]);
+        double s, c;
+        sincos(d0, &s, &c);
+        if (!(f & TFM_RAD_CCW)) s = -s;
+        double r = (f & TFM_RAD_R0_NOT_NONE) ? A::mul(op.p[2], exp(y)) : y;
+        x = A::mul(c, r);
+        y = A::mul(s, r);
+        if (f & TFM_RAD_ORIGIN_NONZERO) { x = A::add(x, op.p[0]); y = A::add(y, op.p[1]); }
+    }
+}
+
+// ---- FITS WCS (Greisen & Calabretta 2002 paper I; Calabretta & Greisen 2002 paper II) ----
+// PARITY UNPINNED beyond the linear part: the reference delegates to astropy/wcslib
+// (core.py:1727, 1742), which is absent and unpinned; restated from the papers.
+#define TFM_D2R 0.017453292519943295
+#define TFM_R2D 57.29577951308232
+
+template <class A>
+__device__ __forceinline__ void wcs_native_to_celestial(const double *R, double phi, double theta,
+                                                        double &lon, double &lat, bool to_celestial)
+{
+    // unit vector in the source frame, rotated by R (or R^T), back to angles (degrees)
+    double sp, cp, st, ct;
+    sincos(phi * TFM_D2R, &sp, &cp);
+    sincos(theta * TFM_D2R, &st, &ct);
+    double vx = ct * cp, vy = ct * sp, vz = st;
+    double wx, wy, wz;
+    if (to_celestial) {
+        wx = R[0] * vx + R[1] * vy + R[2] * vz;
+        wy = R[3] * vx + R[4] * vy + R[5] * vz;
+        wz = R[6] * vx + R[7] * vy + R[8] * vz;
+    } else {
+        wx = R[0] * vx + R[3] * vy + R[6] * vz;
+        wy = R[1] * vx + R[4] * vy + R[7] * vz;
+        wz = R[2] * vx + R[5] * vy + R[8] * vz;
+    }
+    lon = atan2(wy, wx) * TFM_R2D;
+    lat = atan2(wz, sqrt(wx * wx + wy * wy)) * TFM_R2D;
+}
+
+template <class A>
+__device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
+{
+    const int proj = op.flags & 0xff;
+    if (op.dir == TFM_FWD) {            // pixel (origin 0) -> world: all_pix2world(d, 0), core.py:1727
+        double dx = A::sub(A::add(x, 1.0), op.p[0]);       // FITS pixels are 1-based
+        double dy = A::sub(A::add(y, 1.0), op.p[1]);
+        double ix = A::add(A::mul(op.p[2], dx), A::mul(op.p[3], dy));
+        double iy = A::add(A::mul(op.p[4], dx), A::mul(op.p[5], dy));
+        if (proj == TFM_WCS_PROJ_NONE) {
+            x = A::add(ix, op.p[10]);
+            y = A::add(iy, op.p[11]);
+            return;
+        }
+        double phi, theta;
+        if (proj == TFM_WCS_PROJ_TAN) {                    // paper II eq. 14, 15, 55
+            double r = sqrt(ix * ix + iy * iy);
+            phi = (r == 0.0) ? 0.0 : atan2(ix, -iy) * TFM_R2D;
+            theta = atan2(TFM_R2D, r) * TFM_R2D;
+        } else {                                           // CAR: paper II eq. 83, 84
+            phi = ix;
+            theta = iy;
+        }
+        double lon, lat;
+        wcs_native_to_celestial<A>(op.p + 12, phi, theta, lon, lat, true);
+        // wcslib normalises the celestial longitude into [0, 360)
+        if (lon < 0.0) lon += 360.0;
+        x = lon;
+        y = lat;
+    } else {                            // world -> pixel: all_world2pix(d, 0), core.py:1742
+        double ix, iy;
+        if (proj == TFM_WCS_PROJ_NONE) {
+            ix = A::sub(x, op.p[10]);
+            iy = A::sub(y, op.p[11]);
+        } else {
+            double phi, theta;
+            wcs_native_to_celestial<A>(op.p + 12, x, y, phi, theta, false);
+            if (proj == TFM_WCS_PROJ_TAN) {                // paper II eq. 12, 13, 54
+                double sp, cp, st, ct;
+                sincos(phi * TFM_D2R, &sp, &cp);
+                sincos(theta * TFM_D2R, &st, &ct);
+                double r = (st > 0.0) ? TFM_R2D * ct / st : nan("");   // theta <= 0: not on this side of the sky
+                ix = r * sp;
+                iy = -r * cp;
+            } else {                                       // CAR
+                ix = phi;
+                iy = theta;
+            }
+        }
+        double px = A::add(A::mul(op.p[6], ix), A::mul(op.p[7], iy));
+        double py = A::add(A::mul(op.p[8], ix), A::mul(op.p[9], iy));
+        x = A::sub(A::add(px, op.p[0]), 1.0);
+        y = A::sub(A::add(py, op.p[1]), 1.0);
+    }
+}
+
+// interpND / interpND_grid take a precomputed coordinate array (helpers.pyx:379, 1293)
+__device__ __forceinline__ void op_index(const tfm_op &op, double &x, double &y)
+{
+    const double2 *idx = reinterpret_cast<const double2 *>(__double_as_longlong(op.p[0]));
+    const long long nx = (long long)op.p[1], ny = (long long)op.p[2];
+    const long long ix = (long long)x, iy = (long long)y;
+    if (ix < 0 || ix >= nx || iy < 0 || iy >= ny) {
+        x = nan("");
+        y = nan("");
+        return;
+    }
+    const double2 v = __ldg(idx + iy * nx + ix);
+    x = v.x;
+    y = v.y;
+}
+
+template <class A>
+__device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double &y)
+{
+    for (int i = 0; i < ch.n; ++i) {
+        const tfm_op &op = ch.ops[i];
+        switch (op.kind) {
+        case TFM_OP_LINEAR: op_linear<A>(op, x, y); break;
+        case TFM_OP_RADIAL: op_radial<A>(op, x, y); break;
+        case TFM_OP_WCS: op_wcs<A>(op, x, y); break;
+        case TFM_OP_INDEX: op_index(op, x, y); break;
+        default: break;                                     // identity
+        }
+    }
+}
+
+}  // namespace tfm

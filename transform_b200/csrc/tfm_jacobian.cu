@@ -1,0 +1,473 @@
+// tfm_jacobian.cu -- K2: Jacobian-adaptive (DeForest 2004) anti-aliased resampler.
+//
+// One launch replaces interpND_grid(..., antialias=True) (helpers.pyx:1293-1530):
+//   coordinates      self.invert(grid)                      -> chain_eval on a (32+4) x (8+4) halo tile
+//   simple_jacobian  helpers.pyx:896-906   [NY-1,NX-1,2,2]  -> cell differences from the smem tile
+//   jump_detect      helpers.pyx:1012-1141 (9-/6-lag sort)  -> selection network per cell, smem flags
+//   jacobian         helpers.pyx:1225-1247 (grid-centring)  -> 4-cell flagged mean per pixel
+//   interpND_jacobian helpers.pyx:1542-1803                 -> svd2x2, padding, footprint loop
+// None of the reference's [NY,NX,2], [NY,NX,2,2] float64 temporaries (1 + 2 GB at 8192^2) exists:
+// HBM sees the source pixels and the output pixels only.  The footprint loop (25..121+ taps per
+// pixel, each an exp) makes this kernel instruction-bound, not HBM-bound -- see DESIGN.md.
+//
+// Repairs relative to the shipped (non-functional) reference text are those enumerated in
+// oracle/oracle_np.py::interp_grid_jacobian (R1-R12).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "tfm_chain.cuh"
+#include "tfm_common.cuh"
+
+namespace tfm {
+
+constexpr int JTX = 32, JTY = 8;            // output tile
+constexpr int PW = JTX + 4, PH = JTY + 4;   // coordinate points (halo 2)
+constexpr int CW = JTX + 3, CH = JTY + 3;   // cells (lower-left point index), halo 2 / 1
+
+struct JacParams {
+    const void *src;
+    void *dst;
+    long long src_pitch, dst_pitch;
+    long long src_plane, dst_plane;
+    int n_planes;
+    int src_h, src_w, src_x0, src_y0, full_h, full_w;
+    int dst_h, dst_w;
+    long long dst_x0, dst_y0;
+    int grid_h, grid_w;                      // full output grid (edge rules)
+    int bound_x, bound_y;
+    int filter;
+    int src_f64, dst_f64;
+    double oblur, pad_pow, padval, jump_thresh;
+    long long max_reg;
+    int *status;
+    ChainDev chain;
+};
+
+// ---- 2x2 SVD / recompose (helpers.pyx:1845-1916) ----
+__device__ __forceinline__ void svd2x2_dev(const double *M, double *U, double *s, double *V)
+{
+    const double a = M[0], b = M[1], c = M[2], d = M[3];
+    const double au = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
+    const double bu = __dadd_rn(__dmul_rn(a, c), __dmul_rn(b, d));
+    const double du = __dadd_rn(__dmul_rn(c, c), __dmul_rn(d, d));
+    const double theta = __dmul_rn(0.5, atan2(__dmul_rn(2.0, bu), __dsub_rn(au, du)));
+    double St, Ct;
+    sincos(theta, &St, &Ct);
+    U[0] = Ct; U[1] = -St; U[2] = St; U[3] = Ct;
+    const double aw = __dadd_rn(__dmul_rn(a, a), __dmul_rn(c, c));
+    const double bw = __dadd_rn(__dmul_rn(a, b), __dmul_rn(c, d));
+    const double dw = __dadd_rn(__dmul_rn(b, b), __dmul_rn(d, d));
+    const double phi = __dmul_rn(0.5, atan2(__dmul_rn(2.0, bw), __dsub_rn(aw, dw)));
+    double Sp, Cp;
+    sincos(phi, &Sp, &Cp);
+    const double cs00 = __dadd_rn(
+        __dmul_rn(__dadd_rn(__dmul_rn(Ct, a), __dmul_rn(St, c)), Cp),
+        __dmul_rn(__dadd_rn(__dmul_rn(Ct, b), __dmul_rn(St, d)), Sp));
+    const double cs11 = __dsub_rn(
+        __dmul_rn(__dsub_rn(__dmul_rn(St, a), __dmul_rn(Ct, c)), Sp),
+        __dmul_rn(__dsub_rn(__dmul_rn(St, b), __dmul_rn(Ct, d)), Cp));
+    s[0] = fabs(cs00);
+    s[1] = fabs(cs11);
+    const double c00 = cs00 >= 0 ? 1.0 : -1.0, c11 = cs11 >= 0 ? 1.0 : -1.0;
+    V[0] = __dmul_rn(Cp, c00); V[1] = __dmul_rn(-Sp, c11);
+    V[2] = __dmul_rn(Sp, c00); V[3] = __dmul_rn(Cp, c11);
+}
+
+__device__ __forceinline__ void svc2x2_dev(const double *U, const double *s, const double *V, double *M)
+{
+    const double U00S0 = __dmul_rn(U[0], s[0]), U10S0 = __dmul_rn(U[2], s[0]);
+    const double U01S1 = __dmul_rn(U[1], s[1]), U11S1 = __dmul_rn(U[3], s[1]);
+    M[0] = __dadd_rn(__dmul_rn(U00S0, V[0]), __dmul_rn(U01S1, V[1]));
+    M[1] = __dadd_rn(__dmul_rn(U00S0, V[2]), __dmul_rn(U01S1, V[3]));
+    M[2] = __dadd_rn(__dmul_rn(U10S0, V[0]), __dmul_rn(U11S1, V[1]));
+    M[3] = __dadd_rn(__dmul_rn(U10S0, V[2]), __dmul_rn(U11S1, V[3]));
+}
+
+// ---- k-th smallest of a handful of doubles (np.sort(...)[k], helpers.pyx:1063-1064, 1109-1110) ----
+__device__ __forceinline__ void cswap(double &a, double &b)
+{
+    const double lo = fmin(a, b), hi = fmax(a, b);
+    a = lo;
+    b = hi;
+}
+
+__device__ __forceinline__ double kth3_of9(double *v)     // element 3 of the sorted 9
+{
+    // 25-exchange sorting network for 9 inputs
+    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[0], v[3]); cswap(v[3], v[6]); cswap(v[0], v[3]);
+    cswap(v[1], v[4]); cswap(v[4], v[7]); cswap(v[1], v[4]);
+    cswap(v[2], v[5]); cswap(v[5], v[8]); cswap(v[2], v[5]);
+    cswap(v[1], v[3]); cswap(v[5], v[7]);
+    cswap(v[2], v[6]); cswap(v[4], v[6]); cswap(v[2], v[4]);
+    cswap(v[2], v[3]); cswap(v[5], v[6]);
+    return v[3];
+}
+
+__device__ __forceinline__ double kth2_of6(double *v)     // element 2 of the sorted 6
+{
+    // 12-exchange sorting network for 6 inputs
+    cswap(v[0], v[5]); cswap(v[1], v[3]); cswap(v[2], v[4]);
+    cswap(v[1], v[2]); cswap(v[3], v[4]);
+    cswap(v[0], v[3]); cswap(v[2], v[5]);
+    cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]);
+    cswap(v[1], v[2]); cswap(v[3], v[4]);
+    return v[2];
+}
+
+// generic boundary on one axis; same rules as K1 / helpers.pyx:1750-1790 with R9
+__device__ __forceinline__ int jbound(long long i, int size, int mode, int &state)
+{
+    if ((unsigned long long)i < (unsigned long long)size) return (int)i;
+    switch (mode) {
+    case TFM_B_EXTEND: return i < 0 ? 0 : size - 1;
+    case TFM_B_PERIODIC: { long long r = i % (long long)size; if (r < 0) r += size; return (int)r; }
+    case TFM_B_MIRROR: {
+        long long s2 = 2LL * size, r = i % s2;
+        if (r < 0) r += s2;
+        if (r >= size) r = s2 - 1 - r;
+        return (int)r; }
+    case TFM_B_FORBID: state |= 2; return 0;
+    default: state |= 1; return 0;           // truncate
+    }
+}
+
+template <typename RegT>
+__device__ __forceinline__ RegT filt_eval(int filter, RegT xf, RegT yf);
+
+template <>
+__device__ __forceinline__ double filt_eval<double>(int filter, double xf, double yf)
+{
+    const double pi = 3.141592653589793;
+    double filt, a, b;
+    switch (filter) {
+    case TFM_FILT_TENT:                                          // helpers.pyx:1693-1695
+        filt = (xf < 1) ? __dsub_rn(1.0, xf) : 0.0;
+        filt = __dmul_rn(filt, (yf < 1) ? __dsub_rn(1.0, yf) : 0.0);
+        return filt;
+    case TFM_FILT_LANCZOS:                                       // helpers.pyx:1697-1706
+        if (xf > 3 || yf > 3) return 0.0;
+        a = __dmul_rn(pi, xf); b = __ddiv_rn(a, 3.0);
+        filt = __ddiv_rn(__dmul_rn(__ddiv_rn(sin(a), a), sin(b)), b);
+        a = __dmul_rn(pi, yf); b = __ddiv_rn(a, 3.0);
+        return __dmul_rn(filt, __ddiv_rn(__dmul_rn(__ddiv_rn(sin(a), a), sin(b)), b));
+    case TFM_FILT_HANNING:                                       // helpers.pyx:1708-1717
+        if (xf > 1 || yf > 1) return 0.0;
+        b = cos(__dmul_rn(pi, xf)); filt = __dmul_rn(b, b);
+        b = cos(__dmul_rn(pi, yf)); return __dmul_rn(filt, __dmul_rn(b, b));
+    case TFM_FILT_TUKEY:                                         // helpers.pyx:1719-1732
+        if (xf > 1 || yf > 1) return 0.0;
+        filt = 1.0;
+        if (xf > 0.5) { b = cos(__dmul_rn(__dmul_rn(pi, 2.0), __dsub_rn(xf, 0.5))); filt = __dmul_rn(b, b); }
+        if (yf > 0.5) { b = cos(__dmul_rn(__dmul_rn(pi, 2.0), __dsub_rn(yf, 0.5))); filt = __dmul_rn(filt, __dmul_rn(b, b)); }
+        return filt;
+    default:                                                     // Gaussian, helpers.pyx:1734-1735
+        return exp(-__dadd_rn(__dmul_rn(xf, xf), __dmul_rn(yf, yf)));
+    }
+}
+
+template <>
+__device__ __forceinline__ float filt_eval<float>(int filter, float xf, float yf)
+{
+    const float pi = 3.14159265358979f;
+    float filt, a, b;
+    switch (filter) {
+    case TFM_FILT_TENT:
+        return ((xf < 1) ? 1.0f - xf : 0.0f) * ((yf < 1) ? 1.0f - yf : 0.0f);
+    case TFM_FILT_LANCZOS:
+        if (xf > 3 || yf > 3) return 0.0f;
+        a = pi * xf; b = a / 3.0f; filt = sinf(a) / a * sinf(b) / b;
+        a = pi * yf; b = a / 3.0f; return filt * (sinf(a) / a * sinf(b) / b);
+    case TFM_FILT_HANNING:
+        if (xf > 1 || yf > 1) return 0.0f;
+        b = cosf(pi * xf); filt = b * b;
+        b = cosf(pi * yf); return filt * b * b;
+    case TFM_FILT_TUKEY:
+        if (xf > 1 || yf > 1) return 0.0f;
+        filt = 1.0f;
+        if (xf > 0.5f) { b = cosf(pi * 2.0f * (xf - 0.5f)); filt = b * b; }
+        if (yf > 0.5f) { b = cosf(pi * 2.0f * (yf - 0.5f)); filt *= b * b; }
+        return filt;
+    default:
+        return __expf(-(xf * xf + yf * yf));
+    }
+}
+
+// A: chain arithmetic; RegT: footprint arithmetic (double = parity mode, float = fast mode)
+template <class A, typename SrcT, typename DstT, typename RegT>
+__global__ void __launch_bounds__(JTX * JTY)
+k_jacobian(const __grid_constant__ JacParams P)
+{
+    __shared__ double s_px[PH][PW], s_py[PH][PW];     // inverse-mapped coordinates of grid points
+    __shared__ double s_m2[CH][CW];                   // Jmag2 per cell (helpers.pyx:1020)
+    __shared__ unsigned char s_flag[CH][CW];          // jump flag per cell (1 = ok)
+
+    const int tid = threadIdx.y * JTX + threadIdx.x;
+    const char *const src_base = static_cast<const char *>(P.src) + (long long)blockIdx.z * P.src_plane;
+    char *const dst_base = static_cast<char *>(P.dst) + (long long)blockIdx.z * P.dst_plane;
+    const long long GX0 = P.dst_x0 + (long long)blockIdx.x * JTX;   // global grid coords of tile origin
+    const long long GY0 = P.dst_y0 + (long long)blockIdx.y * JTY;
+    const int GW = P.grid_w, GH = P.grid_h;
+    // smem window origin: 2 points of halo; when the tile's first column (row) is the LAST grid
+    // column (row), the edge-copy clamp below reaches one further back, so slide the window by 1
+    // (such a tile has a single valid column (row), the far side of the window is unused).
+    const int shx = (GX0 == GW - 1) ? 1 : 0, shy = (GY0 == GH - 1) ? 1 : 0;
+    const long long WX0 = GX0 - 2 - shx, WY0 = GY0 - 2 - shy;
+
+    // ---- 1. coordinates of the halo tile (points outside the grid are never used) ----
+    for (int i = tid; i < PW * PH; i += JTX * JTY) {
+        const int pj = i / PW, pi = i - pj * PW;
+        const long long gx = WX0 + pi, gy = WY0 + pj;
+        double x = (double)gx, y = (double)gy;
+        if (gx >= 0 && gx < GW && gy >= 0 && gy < GH) chain_eval<A>(P.chain, x, y);
+        s_px[pj][pi] = x;
+        s_py[pj][pi] = y;
+    }
+    __syncthreads();
+
+    // ---- 2. Jmag2 per cell: cell (ci,cj) spans points (ci..ci+1, cj..cj+1) ----
+    for (int i = tid; i < CW * CH; i += JTX * JTY) {
+        const int cj = i / CW, ci = i - cj * CW;
+        const double ax = s_px[cj + 1][ci + 1], bx = s_px[cj + 1][ci], cx = s_px[cj][ci + 1], dx = s_px[cj][ci];
+        const double ay = s_py[cj + 1][ci + 1], by = s_py[cj + 1][ci], cy = s_py[cj][ci + 1], dy = s_py[cj][ci];
+        // helpers.pyx:897-906: ((a-b)+c)-d over 2 and ((a+b)-c)-d over 2
+        const double j00 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ax, bx), cx), dx), 0.5);
+        const double j10 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ay, by), cy), dy), 0.5);
+        const double j01 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ax, bx), cx), dx), 0.5);
+        const double j11 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ay, by), cy), dy), 0.5);
+        s_m2[cj][ci] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(j00, j00), __dmul_rn(j01, j01)),
+                                           __dmul_rn(j10, j10)), __dmul_rn(j11, j11));
+    }
+    __syncthreads();
+
+    // ---- 3. jump flags for the (JTX+1) x (JTY+1) cells the tile's pixels average over ----
+    const int NCX = GW - 1, NCY = GH - 1;              // cell grid extent
+    for (int i = tid; i < (JTX + 1) * (JTY + 1); i += JTX * JTY) {
+        const int fj = i / (JTX + 1), fi = i - fj * (JTX + 1);
+        const int ci = fi + 1, cj = fj + 1;            // index into s_m2 (cell halo of 1)
+        const long long gcx = WX0 + ci, gcy = WY0 + cj;               // global cell index
+        unsigned char flag = 1;
+        if (P.jump_thresh != 0.0 && gcx >= 0 && gcx < NCX && gcy >= 0 && gcy < NCY) {
+            const bool ix_in = (gcx >= 1 && gcx <= NCX - 2), iy_in = (gcy >= 1 && gcy <= NCY - 2);
+            double v[9];
+            if (ix_in && iy_in) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) v[a * 3 + b] = s_m2[cj - 1 + a][ci - 1 + b];
+                flag = s_m2[cj][ci] <= __dmul_rn(kth3_of9(v), P.jump_thresh);
+            } else if (ix_in && NCY >= 2) {            // bottom / top row of cells: 2 x 3 lags
+                const int r0 = (gcy == 0) ? cj : cj - 1;
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) v[a * 3 + b] = s_m2[r0 + a][ci - 1 + b];
+                flag = s_m2[cj][ci] <= __dmul_rn(kth2_of6(v), P.jump_thresh);
+            } else if (iy_in && NCX >= 2) {            // left / right column of cells: 3 x 2 lags
+                const int c0 = (gcx == 0) ? ci : ci - 1;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) v[a * 2 + b] = s_m2[cj - 1 + a][c0 + b];
+                flag = s_m2[cj][ci] <= __dmul_rn(kth2_of6(v), P.jump_thresh);
+            }                                           // corners stay 1 (helpers.pyx:986-989)
+        }
+        s_flag[cj][ci] = flag;
+    }
+    __syncthreads();
+
+    // ---- 4. per pixel: grid-centred Jacobian, SVD padding, footprint ----
+    const int X = blockIdx.x * JTX + threadIdx.x, Y = blockIdx.y * JTY + threadIdx.y;
+    if (X >= P.dst_w || Y >= P.dst_h) return;
+    const long long gx = P.dst_x0 + X, gy = P.dst_y0 + Y;
+    // edge rows/columns copy their inner neighbour (helpers.pyx:1244-1247): clamp to [1, G-2]
+    long long jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
+    long long jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
+    // point index of (jx,jy) inside the smem tile; the clamp moves by at most 1, halo is 2
+    const int qi = (int)(jx - WX0), qj = (int)(jy - WY0);
+
+    double Ji[4] = {0.0, 0.0, 0.0, 0.0};
+    int nvalid = 0;
+    // helpers.pyx:1227-1231: cells (y-1,x-1) + (y,x-1) + (y-1,x) + (y,x), in that order
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ci = qi - 1 + (k >> 1), cj = qj - 1 + (k & 1);
+        const bool ok = s_flag[cj][ci] != 0;
+        nvalid += ok ? 1 : 0;
+        const double ax = s_px[cj + 1][ci + 1], bx = s_px[cj + 1][ci], cx = s_px[cj][ci + 1], dx = s_px[cj][ci];
+        const double ay = s_py[cj + 1][ci + 1], by = s_py[cj + 1][ci], cy = s_py[cj][ci + 1], dy = s_py[cj][ci];
+        double j00 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ax, bx), cx), dx), 0.5);
+        double j10 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ay, by), cy), dy), 0.5);
+        double j01 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ax, bx), cx), dx), 0.5);
+        double j11 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ay, by), cy), dy), 0.5);
+        if (!ok) { j00 = 0.0; j01 = 0.0; j10 = 0.0; j11 = 0.0; }          // helpers.pyx:1207
+        if (k == 0) { Ji[0] = j00; Ji[1] = j01; Ji[2] = j10; Ji[3] = j11; }
+        else {
+            Ji[0] = __dadd_rn(Ji[0], j00); Ji[1] = __dadd_rn(Ji[1], j01);
+            Ji[2] = __dadd_rn(Ji[2], j10); Ji[3] = __dadd_rn(Ji[3], j11);
+        }
+    }
+    const double denom = (P.jump_thresh != 0.0) ? (double)(nvalid < 1 ? 1 : nvalid) : 4.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Ji[k] = __ddiv_rn(Ji[k], denom);
+
+    double U[4], V[4], s[2], J[4];
+    svd2x2_dev(Ji, U, s, V);                                                     // helpers.pyx:1659
+    s[0] = exp(__ddiv_rn(-log(__dadd_rn(P.padval, exp(__dmul_rn(log(s[0]), P.pad_pow)))), P.pad_pow));
+    s[1] = exp(__ddiv_rn(-log(__dadd_rn(P.padval, exp(__dmul_rn(log(s[1]), P.pad_pow)))), P.pad_pow));
+    svc2x2_dev(V, s, U, J);                                                      // helpers.pyx:1663
+    const double smin = fmin(s[0], s[1]);
+    const double rs = __dmul_rn(2.0, ceil(__ddiv_rn(P.oblur, smin)));            // helpers.pyx:1666
+    long long reg = (rs < 1.0e15) ? (long long)rs : 1000000000000000LL;
+    if (P.max_reg > 0 && reg > P.max_reg) reg = P.max_reg;
+    const int half = (int)(reg / 2 > 0x3fffffff ? 0x3fffffff : reg / 2);
+
+    const double px = s_px[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
+    const double py = s_py[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
+    DstT *drow = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch);
+    if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) { drow[X] = (DstT)0; return; }
+    const double fxs = floor(px), fys = floor(py);
+    const long long xs = (long long)fxs, ys = (long long)fys;
+    const RegT xf_of = (RegT)__dsub_rn(px, fxs), yf_of = (RegT)__dsub_rn(py, fys);
+    const RegT J0 = (RegT)J[0], J1 = (RegT)J[1], J2 = (RegT)J[2], J3 = (RegT)J[3];
+    const RegT ob = (RegT)P.oblur;
+
+    RegT val = 0, wgt = 0;
+    int state = 0;
+    for (int yr = -half; yr <= half; ++yr) {
+        const RegT y0 = (RegT)yr + yf_of;
+        for (int xr = -half; xr <= half; ++xr) {
+            const RegT x0 = (RegT)xr + xf_of;
+            RegT xf, yf;
+            if (sizeof(RegT) == 8) {
+                xf = fabs(__dadd_rn(__dmul_rn(J0, x0), __dmul_rn(J1, y0))) / ob;   // helpers.pyx:1689-1690
+                yf = fabs(__dadd_rn(__dmul_rn(J2, x0), __dmul_rn(J3, y0))) / ob;
+            } else {
+                xf = fabsf(J0 * x0 + J1 * y0) / ob;
+                yf = fabsf(J2 * x0 + J3 * y0) / ob;
+            }
+            const RegT filt = filt_eval<RegT>(P.filter, xf, yf);
+            wgt += filt;                                                          // helpers.pyx:1740
+            int st = 0;
+            int iy = jbound(ys + yr, P.full_h, P.bound_y, st);
+            int ix = jbound(xs + xr, P.full_w, P.bound_x, st);
+            state |= st & 2;
+            if (st == 0) {
+                ix -= P.src_x0;
+                iy -= P.src_y0;
+                if ((unsigned)ix < (unsigned)P.src_w && (unsigned)iy < (unsigned)P.src_h) {
+                    const RegT sv = (RegT)__ldg(reinterpret_cast<const SrcT *>(
+                        src_base + (long long)iy * P.src_pitch) + ix);
+                    if (sizeof(RegT) == 8) val = __dadd_rn(val, __dmul_rn(sv, filt));   // helpers.pyx:1796
+                    else val = fmaf(sv, filt, val);
+                } else {
+                    state |= 4;
+                }
+            }
+        }
+    }
+    if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
+    drow[X] = (DstT)((wgt > 0) ? val / wgt : (RegT)0);                            // helpers.pyx:1800
+}
+
+__global__ void k_svd_hook(int which, const double *in, double *out)
+{
+    if (which == 0) svd2x2_dev(in, out, out + 4, out + 6);          // M -> U, s, V
+    else svc2x2_dev(in, in + 4, in + 6, out);                       // U, s, V -> M
+}
+
+int svd_hooks(int which, const double *in0, const double *in1, const double *in2,
+              double *out0, double *out1, double *out2)
+{
+    double h_in[10] = {0}, h_out[10] = {0};
+    if (which == 0) { for (int i = 0; i < 4; ++i) h_in[i] = in0[i]; }
+    else {
+        for (int i = 0; i < 4; ++i) { h_in[i] = in0[i]; h_in[6 + i] = in2[i]; }
+        h_in[4] = in1[0]; h_in[5] = in1[1];
+    }
+    double *d = nullptr;
+    if (cudaMalloc(&d, 20 * sizeof(double)) != cudaSuccess) return TFM_ECUDA;
+    cudaError_t e = cudaMemcpy(d, h_in, 10 * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_svd_hook<<<1, 1>>>(which, d, d + 10);
+        count_launch();
+        e = cudaMemcpy(h_out, d + 10, 10 * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) return TFM_ECUDA;
+    if (which == 0) {
+        for (int i = 0; i < 4; ++i) { out0[i] = h_out[i]; out2[i] = h_out[6 + i]; }
+        out1[0] = h_out[4]; out1[1] = h_out[5];
+    } else {
+        for (int i = 0; i < 4; ++i) out0[i] = h_out[i];
+    }
+    return TFM_OK;
+}
+
+int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
+{
+    if (!a || a->abi_version != TFM_ABI_VERSION) return TFM_EVALUE;
+    if (a->n_ops < 0 || a->n_ops > TFM_MAX_OPS || (a->n_ops && !a->chain)) return TFM_EVALUE;
+    if (a->filter < TFM_FILT_TENT || a->filter > TFM_FILT_GAUSSIAN) return TFM_EVALUE;   // helpers.pyx:1505
+    if (a->bound_x < TFM_B_FORBID || a->bound_x > TFM_B_MIRROR ||
+        a->bound_y < TFM_B_FORBID || a->bound_y > TFM_B_MIRROR) return TFM_EVALUE;       // helpers.pyx:1516
+    const tfm_image &s = a->src, &d = a->dst;
+    if (s.h < 0 || s.w < 0 || d.h < 0 || d.w < 0) return TFM_EVALUE;
+    if (s.n_planes < 1 || s.n_planes != d.n_planes || s.n_planes > 65535) return TFM_EVALUE;
+    if (s.full_h < s.h || s.full_w < s.w || s.full_h > 0x3fffffff || s.full_w > 0x3fffffff) return TFM_EVALUE;
+    if (d.full_h < 3 || d.full_w < 3 || d.full_h > 0x3fffffff || d.full_w > 0x3fffffff) return TFM_EVALUE;
+    if (d.x0 < 0 || d.y0 < 0 || d.x0 + d.w > d.full_w || d.y0 + d.h > d.full_h) return TFM_EVALUE;
+    if (d.h == 0 || d.w == 0) return TFM_OK;
+    if (s.full_h == 0 || s.full_w == 0 || !s.data || !d.data) return TFM_EVALUE;
+    if (!(a->oblur > 0) || !(a->pad_pow > 0)) return TFM_EVALUE;
+    for (int i = 0; i < a->n_ops; ++i)
+        if (a->chain[i].kind < TFM_OP_IDENTITY || a->chain[i].kind > TFM_OP_INDEX) return TFM_EVALUE;
+    const bool subrect = (s.x0 != 0 || s.y0 != 0 || s.full_h != s.h || s.full_w != s.w);
+    if ((a->bound_x == TFM_B_FORBID || a->bound_y == TFM_B_FORBID || subrect) && !a->status_dev)
+        return TFM_EVALUE;
+
+    JacParams P;
+    P.src = s.data; P.dst = d.data; P.src_pitch = s.pitch; P.dst_pitch = d.pitch;
+    P.src_plane = s.plane_pitch; P.dst_plane = d.plane_pitch; P.n_planes = (int)s.n_planes;
+    P.src_h = (int)s.h; P.src_w = (int)s.w; P.src_x0 = (int)s.x0; P.src_y0 = (int)s.y0;
+    P.full_h = (int)s.full_h; P.full_w = (int)s.full_w;
+    P.dst_h = (int)d.h; P.dst_w = (int)d.w; P.dst_x0 = d.x0; P.dst_y0 = d.y0;
+    P.grid_h = (int)d.full_h; P.grid_w = (int)d.full_w;
+    P.bound_x = a->bound_x; P.bound_y = a->bound_y; P.filter = a->filter;
+    P.src_f64 = s.dtype == TFM_F64; P.dst_f64 = d.dtype == TFM_F64;
+    P.oblur = a->oblur; P.pad_pow = a->pad_pow; P.jump_thresh = a->jump_thresh;
+    // helpers.pyx:1612-1615: padval 1 for tent/Hanning/Tukey, 3 for Lanczos/Gaussian
+    P.padval = (a->filter == TFM_FILT_LANCZOS || a->filter == TFM_FILT_GAUSSIAN) ? 3.0 : 1.0;
+    P.max_reg = a->max_reg;
+    P.status = a->status_dev;
+    P.chain.n = a->n_ops; P.chain.pad = 0;
+    for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
+
+    dim3 grid((unsigned)((P.dst_w + JTX - 1) / JTX), (unsigned)((P.dst_h + JTY - 1) / JTY),
+              (unsigned)P.n_planes);
+    if (grid.y > 65535u) return TFM_EUNSUPPORTED;
+    dim3 block(JTX, JTY);
+    const char *name;
+    if (a->precision == TFM_PREC_EXACT64) {
+        if (s.dtype == TFM_F32 && d.dtype == TFM_F64)
+            k_jacobian<Exact, float, double, double><<<grid, block, 0, st>>>(P);
+        else if (s.dtype == TFM_F64 && d.dtype == TFM_F64)
+            k_jacobian<Exact, double, double, double><<<grid, block, 0, st>>>(P);
+        else return TFM_EUNSUPPORTED;
+        name = "k_jacobian<exact64>";
+    } else if (a->precision == TFM_PREC_FAST32) {
+        if (s.dtype == TFM_F32 && d.dtype == TFM_F32)
+            k_jacobian<Fast, float, float, float><<<grid, block, 0, st>>>(P);
+        else return TFM_EUNSUPPORTED;
+        name = "k_jacobian<fast32>";
+    } else {
+        return TFM_EVALUE;
+    }
+    count_launch();
+    set_last_kernel(name);
+    return cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
+}
+
+}  // namespace tfm

@@ -1,0 +1,402 @@
+// tfm_resample.cu -- K1: fused inverse-chain evaluation + nearest / linear / cubic gather.
+//
+// One launch replaces Transform.resample's three whole-array stages (core.py:573-584):
+//   grid enumeration (core.py:574-578)      -> pixel index from block/thread index, zero bytes
+//   self.invert(grid) (core.py:1556-1559)   -> tfm::chain_eval in registers
+//   interpND(...) (helpers.pyx:379-844)     -> boundary-conditioned taps + weights, fused
+// HBM traffic is the compulsory one: every source pixel read once (L1/L2 absorb the 4x/16x tap
+// reuse), every output pixel written once.  No tensor cores: nothing here is a contraction.
+//
+// Thread mapping ("direct" variant): a CTA of 256 threads covers a 32 x (8*NPX) output tile.  A warp
+// covers a WW x (32/WW) patch (WW = 32, 16 or 8, chosen per launch from the local rotation of the
+// map) so that one warp-wide tap load touches as few 128-byte lines as possible, and repeats it
+// NPX times 8 rows apart with all loads of the NPX pixels in flight together.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "tfm_chain.cuh"
+#include "tfm_common.cuh"
+
+namespace tfm {
+
+struct ResampleParams {
+    const void *src;
+    void *dst;
+    long long src_pitch, dst_pitch;          // bytes
+    long long src_plane, dst_plane;          // bytes between planes (blockIdx.z)
+    int src_h, src_w;                        // staged rows / columns at `src`
+    int src_x0, src_y0;                      // global origin of src[0][0]
+    int full_h, full_w;                      // full source extent (boundary conditions)
+    int dst_h, dst_w;
+    long long dst_x0, dst_y0;                // global grid origin of dst[0][0]
+    int bound_x, bound_y;
+    int flags;
+    int lw;                                  // log2 of warp patch width (5, 4 or 3)
+    int n_planes;
+    double fill;
+    int *status;
+    ChainDev chain;
+};
+
+// ---------------------------------------------------------------------------------------------
+// tap index helpers
+// ---------------------------------------------------------------------------------------------
+// floor value (integer-valued double, or NaN/inf) -> int64 tap base, x86-64 `.astype(int)` rule:
+// NaN / inf / |f| >= 2^63 give INT64_MIN (helpers.pyx:127; oracle_np._cast_i64).
+__device__ __forceinline__ long long cast_i64(double f)
+{
+    return (fabs(f) < 9.2e18) ? __double2ll_rz(f) : LLONG_MIN;
+}
+
+// Generic boundary on one axis (helpers.pyx:136-176).  Returns the in-range index, or -1 with
+// `trunc` set for a truncated tap; 'forbid' violations raise bit 1 in *status and read as truncated.
+__device__ __noinline__ int bound_slow(long long i, int size, int mode, bool &trunc, int *status)
+{
+    switch (mode) {
+    case TFM_B_EXTEND:
+        return i < 0 ? 0 : size - 1;
+    case TFM_B_PERIODIC: {
+        long long r = i % (long long)size;
+        if (r < 0) r += size;
+        return (int)r;
+    }
+    case TFM_B_MIRROR: {
+        long long s2 = 2LL * size;
+        long long r = i % s2;
+        if (r < 0) r += s2;
+        if (r >= size) r = s2 - 1 - r;
+        return (int)r;
+    }
+    case TFM_B_FORBID:
+        if (status) atomicOr(status, 1);
+        trunc = true;
+        return -1;
+    default:  // truncate
+        trunc = true;
+        return -1;
+    }
+}
+
+__device__ __forceinline__ int bound_index(long long i, int size, int mode, bool &trunc, int *status)
+{
+    if ((unsigned long long)i < (unsigned long long)size) return (int)i;
+    return bound_slow(i, size, mode, trunc, status);
+}
+
+template <typename T>
+__device__ __forceinline__ T ldg_px(const void *base, long long pitch, int y, int x)
+{
+    return __ldg(reinterpret_cast<const T *>(static_cast<const char *>(base) + (long long)y * pitch) + x);
+}
+
+// One tap, generic path: global index -> boundary -> staged sub-rectangle -> value.
+template <typename SrcT, typename RegT>
+__device__ __forceinline__ RegT tap_generic(const ResampleParams &P, const void *src, long long gx, long long gy)
+{
+    bool trunc = false;
+    int jx = bound_index(gx, P.full_w, P.bound_x, trunc, P.status);
+    int jy = bound_index(gy, P.full_h, P.bound_y, trunc, P.status);
+    if (trunc) return (RegT)P.fill;
+    jx -= P.src_x0;
+    jy -= P.src_y0;
+    if ((unsigned)jx >= (unsigned)P.src_w || (unsigned)jy >= (unsigned)P.src_h) {
+        if (P.status) atomicOr(P.status, 2);             // host staged too small a sub-rectangle
+        return (RegT)P.fill;
+    }
+    return (RegT)ldg_px<SrcT>(src, P.src_pitch, jy, jx);
+}
+
+// One tap, truncate-on-both-axes whole-image path (the reference default bound='t').
+template <typename SrcT, typename RegT>
+__device__ __forceinline__ RegT tap_trunc(const ResampleParams &P, const void *src, int ix, int iy)
+{
+    bool inb = ((unsigned)ix < (unsigned)P.src_w) & ((unsigned)iy < (unsigned)P.src_h);
+    RegT v = (RegT)P.fill;
+    if (inb) v = (RegT)ldg_px<SrcT>(src, P.src_pitch, iy, ix);
+    return v;
+}
+
+// Tap base for the truncate fast path: any coordinate that is NaN or absurdly large maps to an
+// index whose whole footprint is out of range (the reference's INT64_MIN is out of range too).
+__device__ __forceinline__ int base_trunc(double f)
+{
+    return (fabs(f) < 1.0e9) ? __double2int_rz(f) : -1000000;
+}
+
+// ---------------------------------------------------------------------------------------------
+// interpolation arithmetic
+// ---------------------------------------------------------------------------------------------
+// Cubic Hermite with central-difference slopes in the reference's operation order
+// (helpers.pyx:755-778).  T = float reproduces NumPy's float32 first pass (region not promoted).
+__device__ __forceinline__ double hermite_exact(double r0, double r1, double r2, double r3, double b)
+{
+    double d = __dsub_rn(r2, r1);
+    double s0 = __dmul_rn(__dsub_rn(r2, r0), 0.5);
+    double s1 = __dmul_rn(__dsub_rn(r3, r1), 0.5);
+    double c2 = __dsub_rn(__dsub_rn(__dmul_rn(3.0, d), __dmul_rn(2.0, s0)), s1);
+    double c3 = __dsub_rn(__dadd_rn(s1, s0), __dmul_rn(2.0, d));
+    double t = __dadd_rn(c2, __dmul_rn(b, c3));
+    t = __dadd_rn(s0, __dmul_rn(b, t));
+    return __dadd_rn(r1, __dmul_rn(b, t));
+}
+
+__device__ __forceinline__ double hermite_exact_f32(float r0, float r1, float r2, float r3, double b)
+{
+    float d = __fsub_rn(r2, r1);
+    float s0 = __fmul_rn(__fsub_rn(r2, r0), 0.5f);
+    float s1 = __fmul_rn(__fsub_rn(r3, r1), 0.5f);
+    float c2 = __fsub_rn(__fsub_rn(__fmul_rn(3.0f, d), __fmul_rn(2.0f, s0)), s1);
+    float c3 = __fsub_rn(__fadd_rn(s1, s0), __fmul_rn(2.0f, d));
+    double t = __dadd_rn((double)c2, __dmul_rn(b, (double)c3));
+    t = __dadd_rn((double)s0, __dmul_rn(b, t));
+    return __dadd_rn((double)r1, __dmul_rn(b, t));
+}
+
+__device__ __forceinline__ float hermite_fast(float r0, float r1, float r2, float r3, float b)
+{
+    float d = r2 - r1;
+    float s0 = (r2 - r0) * 0.5f;
+    float s1 = (r3 - r1) * 0.5f;
+    float c2 = 3.0f * d - 2.0f * s0 - s1;
+    float c3 = s1 + s0 - 2.0f * d;
+    return r1 + b * (s0 + b * (c2 + b * c3));
+}
+
+template <int METHOD> struct MethodTraits;
+template <> struct MethodTraits<TFM_NEAREST> { static constexpr int NPX = 4, NT = 1; };
+template <> struct MethodTraits<TFM_LINEAR>  { static constexpr int NPX = 4, NT = 2; };
+template <> struct MethodTraits<TFM_CUBIC>   { static constexpr int NPX = 2, NT = 4; };
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+// METHOD   tfm_method
+// SrcT     source element type; DstT output element type
+// A        chain arithmetic policy (Exact / Fast)
+// RegT     arithmetic type of the interpolation (double in exact mode, float in fast mode)
+// GENERIC  false: both axes 'truncate', source is the whole image (fast path);
+//          true : per-axis runtime boundary modes and/or staged source sub-rectangle
+template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC>
+__global__ void __launch_bounds__(256)
+k_resample(const __grid_constant__ ResampleParams P)
+{
+    constexpr int NPX = MethodTraits<METHOD>::NPX;
+    constexpr int NT = MethodTraits<METHOD>::NT;
+    constexpr int T0 = (METHOD == TFM_CUBIC) ? -1 : 0;          // first tap offset
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lw = P.lw, ww = 1 << lw;
+    const void *const src_base = static_cast<const char *>(P.src) + (long long)blockIdx.z * P.src_plane;
+    void *const dst_base = static_cast<char *>(P.dst) + (long long)blockIdx.z * P.dst_plane;
+    const int px = ((warp & ((32 >> lw) - 1)) << lw) + (lane & (ww - 1));
+    const int py = ((warp >> (5 - lw)) << (5 - lw)) + (lane >> lw);
+    const int X = blockIdx.x * 32 + px;
+    const int Y0 = blockIdx.y * (8 * NPX) + py;
+    if (X >= P.dst_w) return;
+
+    // ---- phase 1: coordinates (fp64, in registers) ----
+    double cx[NPX], cy[NPX];
+#pragma unroll
+    for (int j = 0; j < NPX; ++j) {
+        double x = (double)(P.dst_x0 + X);
+        double y = (double)(P.dst_y0 + Y0 + 8 * j);
+        chain_eval<A>(P.chain, x, y);
+        cx[j] = x;
+        cy[j] = y;
+    }
+
+    // ---- phase 2: taps (all loads of the NPX pixels issued before any is consumed) ----
+    RegT v[NPX][NT][NT];
+    double fracx[NPX], fracy[NPX];
+#pragma unroll
+    for (int j = 0; j < NPX; ++j) {
+        double fx, fy;
+        if (METHOD == TFM_NEAREST) {
+            fx = floor(__dadd_rn(cx[j], 0.5));                  // helpers.pyx:127
+            fy = floor(__dadd_rn(cy[j], 0.5));
+        } else {
+            fx = floor(cx[j]);
+            fy = floor(cy[j]);
+        }
+        fracx[j] = __dsub_rn(cx[j], fx);                        // alpha = index - floor(index)
+        fracy[j] = __dsub_rn(cy[j], fy);
+        if (Y0 + 8 * j >= P.dst_h) {                            // ragged bottom tile: not an output pixel
+#pragma unroll
+            for (int ty = 0; ty < NT; ++ty)
+#pragma unroll
+                for (int tx = 0; tx < NT; ++tx) v[j][ty][tx] = (RegT)0;
+        } else if (!GENERIC) {
+            const int ix = base_trunc(fx), iy = base_trunc(fy);
+#pragma unroll
+            for (int ty = 0; ty < NT; ++ty)
+#pragma unroll
+                for (int tx = 0; tx < NT; ++tx)
+                    v[j][ty][tx] = tap_trunc<SrcT, RegT>(P, src_base, ix + T0 + tx, iy + T0 + ty);
+        } else {
+            // |f| >= 2^51 (or NaN): the reference's float tap offsets are absorbed / invalid; every
+            // tap shares the base index ("absurd coordinates").
+            const bool okx = fabs(fx) < 2.0e15, oky = fabs(fy) < 2.0e15;
+            const long long bx = cast_i64(fx), by = cast_i64(fy);
+#pragma unroll
+            for (int ty = 0; ty < NT; ++ty)
+#pragma unroll
+                for (int tx = 0; tx < NT; ++tx)
+                    v[j][ty][tx] = tap_generic<SrcT, RegT>(P, src_base, okx ? bx + T0 + tx : bx,
+                                                           oky ? by + T0 + ty : by);
+        }
+    }
+
+    // ---- phase 3: weights, reduction, store ----
+#pragma unroll
+    for (int j = 0; j < NPX; ++j) {
+        const int Y = Y0 + 8 * j;
+        if (Y >= P.dst_h) continue;
+        RegT r;
+        if (METHOD == TFM_NEAREST) {
+            r = v[j][0][0];
+        } else if (METHOD == TFM_LINEAR) {
+            if (sizeof(RegT) == 8) {
+                // helpers.pyx:584-610: weight = prod(alpha | 1-alpha); sum(region*weight) runs
+                // sequentially over the contiguous 2x2 block (x fastest).
+                const double ax = fracx[j], ay = fracy[j];
+                const double bx = __dsub_rn(1.0, ax), by = __dsub_rn(1.0, ay);
+                double acc = __dmul_rn((double)v[j][0][0], __dmul_rn(bx, by));
+                acc = __dadd_rn(acc, __dmul_rn((double)v[j][0][1], __dmul_rn(ax, by)));
+                acc = __dadd_rn(acc, __dmul_rn((double)v[j][1][0], __dmul_rn(bx, ay)));
+                acc = __dadd_rn(acc, __dmul_rn((double)v[j][1][1], __dmul_rn(ax, ay)));
+                r = (RegT)acc;
+            } else {
+                const float ax = (float)fracx[j], ay = (float)fracy[j];
+                const float top = fmaf(ax, (float)v[j][0][1] - (float)v[j][0][0], (float)v[j][0][0]);
+                const float bot = fmaf(ax, (float)v[j][1][1] - (float)v[j][1][0], (float)v[j][1][0]);
+                r = (RegT)fmaf(ay, bot - top, top);
+            }
+        } else {
+            if (sizeof(RegT) == 8) {
+                double rows[4];
+                const bool f32pass = (sizeof(SrcT) == 4) && (P.flags & TFM_F_REGION_SRC_DTYPE);
+#pragma unroll
+                for (int ty = 0; ty < 4; ++ty) {
+                    if (f32pass)
+                        rows[ty] = hermite_exact_f32((float)v[j][ty][0], (float)v[j][ty][1],
+                                                     (float)v[j][ty][2], (float)v[j][ty][3], fracx[j]);
+                    else
+                        rows[ty] = hermite_exact((double)v[j][ty][0], (double)v[j][ty][1],
+                                                 (double)v[j][ty][2], (double)v[j][ty][3], fracx[j]);
+                }
+                r = (RegT)hermite_exact(rows[0], rows[1], rows[2], rows[3], fracy[j]);
+            } else {
+                float rows[4];
+                const float bx = (float)fracx[j];
+#pragma unroll
+                for (int ty = 0; ty < 4; ++ty)
+                    rows[ty] = hermite_fast((float)v[j][ty][0], (float)v[j][ty][1],
+                                            (float)v[j][ty][2], (float)v[j][ty][3], bx);
+                r = (RegT)hermite_fast(rows[0], rows[1], rows[2], rows[3], (float)fracy[j]);
+            }
+        }
+        DstT *row = reinterpret_cast<DstT *>(static_cast<char *>(dst_base) + (long long)Y * P.dst_pitch);
+        row[X] = (DstT)r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------
+template <int METHOD, typename SrcT, typename DstT, class A, typename RegT>
+static cudaError_t launch2(const ResampleParams &P, bool generic, cudaStream_t st, const char **name)
+{
+    constexpr int NPX = MethodTraits<METHOD>::NPX;
+    dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 8 * NPX - 1) / (8 * NPX)),
+              (unsigned)P.n_planes);
+    if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
+    if (generic) {
+        k_resample<METHOD, SrcT, DstT, A, RegT, true><<<grid, 256, 0, st>>>(P);
+        *name = "k_resample<generic>";
+    } else {
+        k_resample<METHOD, SrcT, DstT, A, RegT, false><<<grid, 256, 0, st>>>(P);
+        *name = "k_resample<trunc>";
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename SrcT, typename DstT, class A, typename RegT>
+static cudaError_t launch1(int method, const ResampleParams &P, bool generic, cudaStream_t st,
+                           const char **name)
+{
+    switch (method) {
+    case TFM_NEAREST: return launch2<TFM_NEAREST, SrcT, DstT, A, RegT>(P, generic, st, name);
+    case TFM_LINEAR:  return launch2<TFM_LINEAR, SrcT, DstT, A, RegT>(P, generic, st, name);
+    default:          return launch2<TFM_CUBIC, SrcT, DstT, A, RegT>(P, generic, st, name);
+    }
+}
+
+int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
+{
+    if (!a || a->abi_version != TFM_ABI_VERSION) return TFM_EVALUE;
+    if (a->n_ops < 0 || a->n_ops > TFM_MAX_OPS || (a->n_ops && !a->chain)) return TFM_EVALUE;
+    if (a->method < TFM_NEAREST || a->method > TFM_CUBIC) return TFM_EVALUE;           // helpers.pyx:840-844
+    if (a->bound_x < TFM_B_FORBID || a->bound_x > TFM_B_MIRROR ||
+        a->bound_y < TFM_B_FORBID || a->bound_y > TFM_B_MIRROR) return TFM_EVALUE;     // helpers.pyx:174-176
+    const tfm_image &s = a->src, &d = a->dst;
+    if (s.h < 0 || s.w < 0 || d.h < 0 || d.w < 0) return TFM_EVALUE;
+    if (s.n_planes < 1 || s.n_planes != d.n_planes || s.n_planes > 65535) return TFM_EVALUE;
+    if (s.full_h < s.h || s.full_w < s.w || s.full_h > 0x3fffffff || s.full_w > 0x3fffffff ||
+        d.h > 0x3fffffff || d.w > 0x3fffffff) return TFM_EVALUE;
+    if (d.h == 0 || d.w == 0) return TFM_OK;                                            // ragged / empty output
+    if (s.full_h == 0 || s.full_w == 0) return TFM_EVALUE;
+    if (!s.data || !d.data) return TFM_EVALUE;
+    for (int i = 0; i < a->n_ops; ++i)
+        if (a->chain[i].kind < TFM_OP_IDENTITY || a->chain[i].kind > TFM_OP_INDEX) return TFM_EVALUE;
+
+    ResampleParams P;
+    P.src = s.data; P.dst = d.data;
+    P.src_pitch = s.pitch; P.dst_pitch = d.pitch;
+    P.src_plane = s.plane_pitch; P.dst_plane = d.plane_pitch; P.n_planes = (int)s.n_planes;
+    P.src_h = (int)s.h; P.src_w = (int)s.w;
+    P.src_x0 = (int)s.x0; P.src_y0 = (int)s.y0;
+    P.full_h = (int)s.full_h; P.full_w = (int)s.full_w;
+    P.dst_h = (int)d.h; P.dst_w = (int)d.w;
+    P.dst_x0 = d.x0; P.dst_y0 = d.y0;
+    P.bound_x = a->bound_x; P.bound_y = a->bound_y;
+    P.flags = a->flags;
+    P.fill = a->fillvalue;
+    P.status = a->status_dev;
+    P.chain.n = a->n_ops; P.chain.pad = 0;
+    for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
+    int lw = 5;
+    if ((a->tuning & 3) == 2) lw = 4;
+    if ((a->tuning & 3) == 3) lw = 3;
+    P.lw = lw;
+
+    const bool subrect = (s.x0 != 0 || s.y0 != 0 || s.full_h != s.h || s.full_w != s.w);
+    const bool generic = subrect || a->bound_x != TFM_B_TRUNCATE || a->bound_y != TFM_B_TRUNCATE;
+    if ((a->bound_x == TFM_B_FORBID || a->bound_y == TFM_B_FORBID || subrect) && !a->status_dev)
+        return TFM_EVALUE;
+
+    const char *name = "";
+    cudaError_t e;
+    const bool exact = (a->precision == TFM_PREC_EXACT64);
+    if (exact) {
+        if (s.dtype == TFM_F32 && d.dtype == TFM_F64)
+            e = launch1<float, double, Exact, double>(a->method, P, generic, st, &name);
+        else if (s.dtype == TFM_F64 && d.dtype == TFM_F64)
+            e = launch1<double, double, Exact, double>(a->method, P, generic, st, &name);
+        else if (s.dtype == TFM_F32 && d.dtype == TFM_F32 && a->method == TFM_NEAREST)
+            e = launch2<TFM_NEAREST, float, float, Exact, double>(P, generic, st, &name);
+        else
+            return TFM_EUNSUPPORTED;
+    } else if (a->precision == TFM_PREC_FAST32) {
+        if (s.dtype == TFM_F32 && d.dtype == TFM_F32)
+            e = launch1<float, float, Fast, float>(a->method, P, generic, st, &name);
+        else
+            return TFM_EUNSUPPORTED;
+    } else {
+        return TFM_EVALUE;
+    }
+    set_last_kernel(name);
+    return e == cudaSuccess ? TFM_OK : TFM_ECUDA;
+}
+
+}  // namespace tfm

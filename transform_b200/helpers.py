@@ -1,0 +1,95 @@
+"""interpND / interpND_grid / svd2x2 / svc2x2: the module-level entry points of helpers.pyx.
+
+Host-side mirror of /root/reference/transform/helpers.pyx:379-385, 1293-1304, 1807-1810.  Both
+interpolators take a *precomputed* coordinate array; it is uploaded once and read by the same
+CUDA kernels through a coordinate-lookup opcode (TFM_OP_INDEX) in place of a transform chain.
+2-D sources and [NY,NX,2] (or [N,2]) index arrays are the GPU path; everything else raises.
+"""
+import struct
+
+import numpy as np
+
+from . import _device as dev
+from . import _engine
+from . import _lib as L
+
+
+def _index_op(index):
+    """Upload `index` ([..., 2] float64) -> (opcode, shape2d, keepalive tensor)."""
+    if dev.is_cuda_tensor(index):
+        t = index.double().contiguous()
+    else:
+        idx = np.asarray(index)
+        if idx.ndim < 1 or idx.shape[-1] != 2:
+            raise NotImplementedError("transform_b200: interpND on the GPU takes 2-vectors (X,Y) "
+                                      "indexing a 2-D source")
+        t = dev.to_device(idx, np.float64, slot="index")
+    lead = tuple(int(s) for s in t.shape[:-1])
+    n = 1
+    for s in lead:
+        n *= s
+    if len(lead) >= 2:
+        nx = lead[-1]
+        ny = n // nx if nx else 0            # extra leading axes fold into rows: pixels are independent
+    else:
+        ny, nx = 1, n
+    op = L.TfmOp()
+    op.kind, op.dir, op.flags = L.OP_INDEX, L.FWD, 0
+    op.p[0] = struct.unpack("d", struct.pack("q", int(t.data_ptr()) if n else 0))[0]
+    op.p[1], op.p[2] = float(nx), float(ny)
+    return op, (ny, nx), lead, t
+
+
+def interpND(source, index=None, method='n', bound='t', fillvalue=0, oblur=None, strict=False, *,
+             precision=None):
+    """helpers.pyx:379-844 for 2-D sources and methods nearest / linear / cubic."""
+    if oblur is not None:
+        if method[0] in ('n',):
+            raise ValueError("interpND: oblur is not allowed with nearest-neighbor interpolation.")
+        if method[0] == 'c':
+            raise ValueError("interpND: oblur is not allowed with cubic-spline interpolation.")
+        raise NotImplementedError("transform_b200: oblur (input-plane filter scaling) is outside the GPU path")
+    src = source if dev.is_tensor(source) else np.asarray(source)
+    if len(src.shape) != 2:
+        raise NotImplementedError("transform_b200: interpND on the GPU takes a 2-D source")
+    op, (ny, nx), lead, keep = _index_op(index)
+    out = _engine.resample([op], src, (ny, nx), method[0], bound, fillvalue=fillvalue,
+                           precision=precision)
+    del keep
+    return out.reshape(lead)
+
+
+def interpND_grid(source, index=None, method='l', bound='t', antialias=True, aa=True, fillvalue=0,
+                  oblur=1.0, iblur=1.0, pad_pow=8, sv_limit=0.25, jump_detect=4.0, strict=False, *,
+                  precision=None):
+    """helpers.pyx:1293-1530 (with the repairs that make it run)."""
+    if not (antialias and aa):
+        return interpND(source, index=index, method=method, bound=bound, fillvalue=fillvalue,
+                        strict=strict, precision=precision)
+    src = source if dev.is_tensor(source) else np.asarray(source)
+    idx_shape = tuple(index.shape)
+    if idx_shape[-1] != len(src.shape):
+        raise ValueError("interpND_grid: source shape must match index vector length")
+    if len(src.shape) != len(idx_shape) - 1:
+        raise ValueError("interpND_grid: index broadcast dims must match source dims")
+    if idx_shape[-1] != 2:
+        raise ValueError("interpND_grid: anti-aliasing is only implemented for 2-D at present.")
+    op, (ny, nx), lead, keep = _index_op(index)
+    out = _engine.resample_jacobian([op], src, (ny, nx), method, bound, fillvalue=fillvalue,
+                                    oblur=oblur, iblur=iblur, pad_pow=pad_pow, sv_limit=sv_limit,
+                                    jump_detect=jump_detect, precision=precision)
+    del keep
+    return out
+
+
+def svd2x2(M, U, s, V):
+    """helpers.pyx:1807-1808: decompose M = U diag(s) V^T into the caller's arrays."""
+    u, sv, v = _engine.svd2x2(M)
+    U[...] = u
+    s[...] = sv
+    V[...] = v
+
+
+def svc2x2(U, s, V, M):
+    """helpers.pyx:1809-1810: recompose M = U diag(s) V^T into the caller's array."""
+    M[...] = _engine.svc2x2(U, s, V)
