@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline measurement of BASELINE.json, on synthetic data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+metric   : output Mpix/s, resample linear+jacobian 8192^2 (BASELINE.json)
+one step : one 8192x8192 float32 frame resampled twice --
+             (1) method 'linear'   through Scale(1.3) o Rotation(30 deg) o Offset   (config 2 at 8192^2)
+             (2) method 'Gaussian' (Jacobian-adaptive filter) through the polar unwrap
+                 Scale o Radial(origin=centre)                                      (config 3)
+           = 2 x 67.1 Mpix of output per step.
+value    : whole-job output Mpix/s with the frame resident in HBM (CUDA events, max over ranks).
+e2e      : the same step through the public API with HOST buffers: pinned host frame -> H2D ->
+           kernels -> D2H into pinned host outputs, all inside the timed region.
+N > 1    : one process per GPU, each rank resamples its own frame (the path shards by frame / by
+           output rows with no data-path collective) -> "scaling": "weak".
+roofline : for the kernel that dominates the step, algorithmic bytes (output bytes + input bytes,
+           each once: SURVEY.md section 8d) / its CUDA-event duration, against the measured HBM copy
+           bandwidth in MEASURED_PEAKS.json.
+cpu_baseline / --impl reference : the reference's CPU path (oracle/cpu_baseline.py) on the box's
+           host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+N_IMG = 8192
+METRIC = "output Mpix/s, resample linear+jacobian 8192^2"
+UNIT = "Mpix/s"
+ALG_BYTES = 2 * N_IMG * N_IMG * 4            # fp32 out + fp32 in, each once
+
+
+def config(n_gpus, extra=None):
+    c = {"workload": "8192x8192 float32 frame per GPU; step = linear resample through "
+                     "Scale(1.3)oRotation(30deg)oOffset + Jacobian-adaptive Gaussian resample through "
+                     "ScaleoRadial (polar unwrap); bound='t'",
+         "pixels_per_step_per_gpu": 2 * N_IMG * N_IMG,
+         "precision": "fp32 fast path (coordinates fp64, interpolation fp32); parity mode in breakdown",
+         "cache": "inputs (268 MB) larger than L2 (126 MB); no explicit flush",
+         "parallelism": "frames sharded across %d GPU(s), no collective in the data path" % n_gpus}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi polled while the timed region runs)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (reference arm and cpu_baseline leg)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(rows_linear, rows_jacobian, nproc):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline as cb
+    src = cb.synthetic_image(N_IMG, 0)
+    t_lin, px_lin, kind = cb.time_sample("linear", N_IMG, rows_linear, nproc, src=src)
+    t_jac, px_jac, _ = cb.time_sample("jacobian", N_IMG, rows_jacobian, nproc, src=src)
+    # one step = N^2 pixels of each method: combine the two per-pixel rates accordingly
+    full = float(N_IMG * N_IMG)
+    t_step = full * (t_lin / px_lin) + full * (t_jac / px_jac)
+    return {"value": 2 * full / t_step / 1e6, "t_lin": t_lin, "px_lin": px_lin, "t_jac": t_jac,
+            "px_jac": px_jac, "kind": kind,
+            "linear_mpix_s": px_lin / t_lin / 1e6, "jacobian_mpix_s": px_jac / t_jac / 1e6}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nproc = os.cpu_count() or 1
+    # bounded sample per step, sized from a quick calibration so K+W steps end within minutes
+    cal = cpu_sample(nproc * 2, nproc * 1, nproc)
+    budget = 150.0 / max(1, args.steps + args.warmup)           # seconds per step
+    rl = max(nproc, int(0.5 * budget * (cal["px_lin"] / cal["t_lin"]) / N_IMG))
+    rj = max(nproc, int(0.5 * budget * (cal["px_jac"] / cal["t_jac"]) / N_IMG))
+    rl, rj = min(rl, 1024), min(rj, 256)
+    for _ in range(args.warmup):
+        cpu_sample(rl, rj, nproc)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_sample(rl, rj, nproc))
+    wall = time.perf_counter() - t0
+    value = sum(v["value"] for v in vals) / len(vals)
+    last = vals[-1]
+    sample = ("per step: %d rows of the 8192^2 linear resample (interpND = %s) + %d rows of the "
+              "Jacobian-Gaussian resample (port: the reference's own cannot run), spread over the "
+              "frame, %d forked workers; per-pixel rates combined for a full step"
+              % (rl, "reference's compiled helpers module" if last["kind"] == "reference" else "oracle port",
+                 rj, nproc))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "impl": "reference", "config": config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": last["kind"],
+                             "sample": sample, "linear_mpix_s": last["linear_mpix_s"],
+                             "jacobian_mpix_s": last["jacobian_mpix_s"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_for(kernel_key):
+    """dram bytes per launch from the committed ncu --set full capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import transform_b200 as t
+    from transform_b200 import _lib as L
+
+    n = N_IMG
+    g = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    src = torch.rand((n, n), generator=g, device="cuda", dtype=torch.float32)
+    out_lin = torch.empty((n, n), device="cuda", dtype=torch.float32)
+    out_jac = torch.empty((n, n), device="cuda", dtype=torch.float32)
+    tr_aff = t.Composition([t.Scale(1.3, dim=2), t.Rotation(30, unit="deg"), t.Offset([-n / 2.0, -n / 2.0])])
+    c = (n - 1) / 2.0
+    tr_rad = t.Composition([t.Scale([n / (2 * np.pi), n / (n / np.sqrt(2.0))]), t.Radial(origin=[c, c])])
+
+    def step(prec="fp32", ev=None):
+        if ev is not None:
+            ev[0].record()
+        tr_aff.resample(src, method="linear", precision=prec, out=out_lin)
+        if ev is not None:
+            ev[1].record()
+        tr_rad.resample(src, method="Gaussian", precision=prec, out=out_jac)
+        if ev is not None:
+            ev[2].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    launches0 = L.launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for k in range(args.steps):
+            step(ev=evs[k])
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = L.launch_count() - launches0
+    ms_lin = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / args.steps
+    ms_jac = sum(ev[1].elapsed_time(ev[2]) for ev in evs) / args.steps
+
+    # ---- end to end through the public API with host buffers ----
+    h_src = torch.empty((n, n), dtype=torch.float32).pin_memory()
+    h_src.copy_(src)
+    h_lin = torch.empty((n, n), dtype=torch.float32).pin_memory()
+    h_jac = torch.empty((n, n), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        tr_aff.resample(h_src, method="linear", precision="fp32", out=h_lin)
+        tr_rad.resample(h_src, method="Gaussian", precision="fp32", out=h_jac)
+
+    step_e2e()
+    barrier()
+    k_e2e = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        step_e2e()
+    barrier()
+    s_e2e = (time.perf_counter() - t0) / k_e2e
+    ok = bool(torch.equal(h_lin, out_lin.cpu()) and torch.equal(h_jac, out_jac.cpu()))
+
+    # ---- breakdown (untimed for `value`): parity mode and the Radial chain with 'linear' ----
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    brk = {}
+    if rank == 0:
+        o64 = torch.empty((n, n), device="cuda", dtype=torch.float64)
+        brk["linear_affine_fp32_ms"] = ms_lin
+        brk["jacobian_radial_fp32_ms"] = ms_jac
+        brk["linear_radial_fp32_ms"] = timed(lambda: tr_rad.resample(src, method="linear", precision="fp32", out=out_lin))
+        brk["nearest_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="nearest", precision="fp32", out=out_lin))
+        brk["cubic_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="cubic", precision="fp32", out=out_lin))
+        brk["linear_affine_fp64_parity_ms"] = timed(lambda: tr_aff.resample(src, method="linear", out=o64))
+        brk["jacobian_radial_fp64_parity_ms"] = timed(lambda: tr_rad.resample(src, method="Gaussian", out=o64), reps=2)
+        for k in list(brk):
+            brk[k.replace("_ms", "_mpix_s")] = n * n / (brk[k] * 1e-3) / 1e6
+        del o64
+
+    # max over ranks
+    tt = torch.tensor([ms_total, s_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, s_e2e = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        px_step = 2.0 * n * n * world
+        peak, peak_src = measured_peak()
+        dom_is_jac = ms_jac >= ms_lin
+        dom_ms = ms_jac if dom_is_jac else ms_lin
+        dom_name = "k_jacobian<fast32>" if dom_is_jac else "k_resample<trunc> linear"
+        achieved = ALG_BYTES / (dom_ms * 1e-3) / 1e9
+        lin_gbs = ALG_BYTES / (ms_lin * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": px_step / (ms_total / args.steps * 1e-3) / 1e6, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(world),
+                "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                             "traffic": traffic_for("jacobian" if dom_is_jac else "linear"),
+                             "algorithmic_bytes_per_launch": ALG_BYTES,
+                             "share_of_step": dom_ms / (ms_lin + ms_jac),
+                             "linear_kernel": {"achieved": lin_gbs, "frac": lin_gbs / peak,
+                                               "ms": ms_lin, "traffic": traffic_for("linear")}},
+                "e2e": {"value": px_step / s_e2e / 1e6, "unit": UNIT,
+                        "h2d_bytes_per_step": 2 * n * n * 4, "d2h_bytes_per_step": 2 * n * n * 4,
+                        "steps": k_e2e, "matches_resident_result": ok},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "breakdown": brk}
+        if world == 1 and not args.no_cpu:
+            nproc = os.cpu_count() or 1
+            cb = cpu_sample(nproc * 16, nproc * 2, nproc)
+            line["cpu_baseline"] = {
+                "value": cb["value"], "unit": UNIT, "cores": nproc, "kind": cb["kind"],
+                "sample": "%d rows (linear, interpND = %s) + %d rows (Jacobian-Gaussian, port) of the "
+                          "8192^2 frame on %d forked workers; per-pixel rates combined for a full step"
+                          % (cb["px_lin"] // n, "reference's compiled helpers module" if cb["kind"] == "reference"
+                             else "oracle port", cb["px_jac"] // n, nproc),
+                "linear_mpix_s": cb["linear_mpix_s"], "jacobian_mpix_s": cb["jacobian_mpix_s"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -81,6 +81,12 @@ def _src_to_device(data, want_f32):
             return t, np.dtype(np.float32), npdt, False
         return t, npdt, npdt, False
     if dev.is_tensor(data):
+        npdt = dev.np_dtype_of(data)
+        if npdt is not None and data.is_pinned() and data.is_contiguous() and \
+                (npdt == np.float32 or not want_f32):
+            # pinned host tensor: one asynchronous DMA, no staging copy
+            dev.require_cuda()
+            return data.to("cuda", non_blocking=True), npdt, npdt, True
         data = data.numpy()
     a = np.asarray(data)
     orig = a.dtype
@@ -131,9 +137,11 @@ def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None,
     else:
         ddt = np.dtype(np.float64)
         final_dt = ddt
-    if out is not None:
+    host_out = None
+    if out is not None and dev.is_cuda_tensor(out):
         dst = out
     else:
+        host_out = out
         dst = dev.empty(lead + (ny, nx), ddt)
     flags = 0
     if (m == "c" and not fast and sdt == np.float32 and not trunc_pass_applies(bound)):
@@ -161,10 +169,23 @@ def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None,
     _check_status(status)
     if not from_numpy:
         return dst
+    if host_out is not None:
+        return _into_host(dst, host_out)
     res = dev.to_host(dst)
     if res.dtype != final_dt:
         res = res.astype(final_dt)
     return res
+
+
+def _into_host(dst, host_out):
+    """Device result -> caller-provided host buffer (numpy array or CPU tensor; pinned = one DMA)."""
+    torch = dev.torch_mod()
+    tgt = host_out if dev.is_tensor(host_out) else torch.from_numpy(host_out)
+    if tuple(tgt.shape) != tuple(dst.shape) or tgt.dtype != dst.dtype:
+        raise ValueError("out= must have shape %s and dtype %s" % (tuple(dst.shape), dst.dtype))
+    tgt.copy_(dst, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host_out
 
 
 def _check_status(status):
@@ -181,7 +202,7 @@ def _check_status(status):
 def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=1.0, iblur=1.0,
                       pad_pow=8, sv_limit=0.25, jump_detect=4.0, precision=None, tuning=0,
                       dst_origin=(0, 0), grid_full=None, src_origin=(0, 0), src_full=None,
-                      max_reg=None):
+                      max_reg=None, out=None):
     """K2 driver: interpND_grid(antialias=True) semantics (helpers.pyx:1293-1530) with the
     coordinates generated in-kernel from `chain_ops`."""
     lib = L.load()
@@ -205,7 +226,12 @@ def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=
     if lead != tuple(int(s) for s in src.shape[:-2]):
         raise NotImplementedError("transform_b200: leading axes of `shape` must equal those of the data")
     ddt = np.dtype(np.float32) if fast else np.dtype(np.float64)
-    dst = dev.empty(lead + (ny, nx), ddt)
+    host_out = None
+    if out is not None and dev.is_cuda_tensor(out):
+        dst = out
+    else:
+        host_out = out
+        dst = dev.empty(lead + (ny, nx), ddt)
     subrect = src_full is not None
     need_status = subrect or bx == L.BOUND_CODE["f"] or by == L.BOUND_CODE["f"]
     status = dev.status_word() if need_status else None
@@ -239,7 +265,11 @@ def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=
     rc = lib.tfm_resample_jacobian(ctypes.byref(a), dev.stream_ptr())
     L.raise_for_status(rc, "tfm_resample_jacobian")
     _check_status(status)
-    return dev.to_host(dst) if from_numpy else dst
+    if not from_numpy:
+        return dst
+    if host_out is not None:
+        return _into_host(dst, host_out)
+    return dev.to_host(dst)
 
 
 def apply(chain_ops, data, precision=None, tuning=0):
