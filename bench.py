@@ -274,6 +274,9 @@ def gpu_arm(args):
         brk["linear_affine_fp32_ms"] = ms_lin
         brk["jacobian_radial_fp32_ms"] = ms_jac
         brk["linear_radial_fp32_ms"] = timed(lambda: tr_rad.resample(src, method="linear", precision="fp32", out=out_lin))
+        for tn, nm in ((2, "16x2"), (3, "8x4"), (4, "novm")):
+            brk["linear_affine_fp32_warp%s_ms" % nm] = timed(
+                lambda: tr_aff.resample(src, method="linear", precision="fp32", out=out_lin, tuning=tn))
         brk["nearest_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="nearest", precision="fp32", out=out_lin))
         brk["cubic_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="cubic", precision="fp32", out=out_lin))
         brk["linear_affine_fp64_parity_ms"] = timed(lambda: tr_aff.resample(src, method="linear", out=o64))

@@ -45,7 +45,15 @@ def test_affine_fast32(tfm, oracle, method):
     want = oracle.resample(to_oracle(tr), src, method=method)
     assert got.dtype == np.float32
     if method == 'nearest':
-        assert np.array_equal(got, want.astype(np.float32))
+        # The fast path pre-composes the affine chain on the host (the parity mode never does), so
+        # a coordinate may round differently in its last bit; that can only flip an index when the
+        # coordinate sits on a half-integer to within rounding.  Every mismatch must be such a tie.
+        bad = np.argwhere(got != want.astype(np.float32))
+        coords = to_oracle(tr).reverse(oracle.pixel_grid(ny, nx))
+        for (y, x) in bad:
+            t = coords[y, x] + 0.5
+            assert np.abs(t - np.round(t)).min() < 1e-9, (y, x, coords[y, x])
+        assert len(bad) < 1e-3 * got.size
     else:
         assert_close_rel(got, want, 1e-5, method)
 

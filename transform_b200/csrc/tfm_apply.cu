@@ -37,11 +37,12 @@ k_apply_f64x2(const __grid_constant__ ApplyParams P)
         double2 v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) v[u] = __ldcs(in + i + u * stride);
+        double x[UNROLL], y[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            chain_eval<A>(P.chain, v[u].x, v[u].y);
-            __stcs(out + i + u * stride, v[u]);
-        }
+        for (int u = 0; u < UNROLL; ++u) { x[u] = v[u].x; y[u] = v[u].y; }
+        chain_eval_n<A, UNROLL>(P.chain, x, y);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) __stcs(out + i + u * stride, make_double2(x[u], y[u]));
     }
     for (; i < P.n_vec; i += stride) {
         double2 v = __ldcs(in + i);
@@ -64,13 +65,16 @@ k_apply_f32x2(const __grid_constant__ ApplyParams P)
         float4 v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) v[u] = __ldcs(in + i + u * stride);
+        double x[2 * UNROLL], y[2 * UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            double x0 = v[u].x, y0 = v[u].y, x1 = v[u].z, y1 = v[u].w;
-            chain_eval<A>(P.chain, x0, y0);
-            chain_eval<A>(P.chain, x1, y1);
-            __stcs(out + i + u * stride, make_float4((float)x0, (float)y0, (float)x1, (float)y1));
+            x[2 * u] = v[u].x; y[2 * u] = v[u].y; x[2 * u + 1] = v[u].z; y[2 * u + 1] = v[u].w;
         }
+        chain_eval_n<A, 2 * UNROLL>(P.chain, x, y);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            __stcs(out + i + u * stride, make_float4((float)x[2 * u], (float)y[2 * u],
+                                                     (float)x[2 * u + 1], (float)y[2 * u + 1]));
     }
     for (; i < n_pk; i += stride) {
         float4 v = __ldcs(in + i);

@@ -229,4 +229,66 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
     }
 }
 
+// ---- N-wide evaluation: the interpreter's dispatch (constant loads, flag tests, branches) is paid
+// once per op per THREAD instead of once per op per pixel; the per-pixel work is the arithmetic only.
+template <class A, int N>
+__device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N], double (&y)[N])
+{
+    for (int i = 0; i < ch.n; ++i) {
+        const tfm_op &op = ch.ops[i];
+        const int f = op.flags;
+        switch (op.kind) {
+        case TFM_OP_LINEAR: {
+            const bool fwd = (op.dir == TFM_FWD);
+            // fwd: +pre, M, +post ; rev: -post, Minv, -pre   (basic.py:141-176)
+            // x - c == x + (-c) exactly in IEEE arithmetic, so one add form serves both directions
+            const double a0 = fwd ? op.p[4] : -op.p[6], a1 = fwd ? op.p[5] : -op.p[7];
+            const double b0 = fwd ? op.p[6] : -op.p[4], b1 = fwd ? op.p[7] : -op.p[5];
+            const bool has_a = fwd ? (f & TFM_LIN_HAS_PRE) : (f & TFM_LIN_HAS_POST);
+            const bool has_b = fwd ? (f & TFM_LIN_HAS_POST) : (f & TFM_LIN_HAS_PRE);
+            if (has_a) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) { x[k] = A::add(x[k], a0); y[k] = A::add(y[k], a1); }
+            }
+            if (f & TFM_LIN_HAS_MATRIX) {
+                const double m0 = op.p[0], m1 = op.p[1], m2 = op.p[2], m3 = op.p[3];
+                if (f & TFM_LIN_MAT_FORDER) {
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double ox = A::fma(m1, y[k], A::mul(m0, x[k]));
+                        const double oy = A::fma(m3, y[k], A::mul(m2, x[k]));
+                        x[k] = ox; y[k] = oy;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double ox = A::fma(m0, x[k], A::mul(m1, y[k]));
+                        const double oy = A::fma(m2, x[k], A::mul(m3, y[k]));
+                        x[k] = ox; y[k] = oy;
+                    }
+                }
+            }
+            if (has_b) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) { x[k] = A::add(x[k], b0); y[k] = A::add(y[k], b1); }
+            }
+            break;
+        }
+        case TFM_OP_RADIAL:
+#pragma unroll
+            for (int k = 0; k < N; ++k) op_radial<A>(op, x[k], y[k]);
+            break;
+        case TFM_OP_WCS:
+#pragma unroll
+            for (int k = 0; k < N; ++k) op_wcs<A>(op, x[k], y[k]);
+            break;
+        case TFM_OP_INDEX:
+#pragma unroll
+            for (int k = 0; k < N; ++k) op_index(op, x[k], y[k]);
+            break;
+        default: break;
+        }
+    }
+}
+
 }  // namespace tfm

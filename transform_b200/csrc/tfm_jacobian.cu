@@ -20,7 +20,7 @@
 
 namespace tfm {
 
-constexpr int JTX = 32, JTY = 8;            // output tile
+constexpr int JTX = 32, JTY = 16;           // output tile (512 threads)
 constexpr int PW = JTX + 4, PH = JTY + 4;   // coordinate points (halo 2)
 constexpr int CW = JTX + 3, CH = JTY + 3;   // cells (lower-left point index), halo 2 / 1
 
@@ -195,11 +195,48 @@ __device__ __forceinline__ float filt_eval<float>(int filter, float xf, float yf
     }
 }
 
+// ---- fast-mode (fp32) pieces -------------------------------------------------------------------
+// padded inverse Jacobian in fp32: same closed form as svd2x2_dev/svc2x2_dev, MUFU-based
+// transcendentals.  Returns the three coefficients of the quadratic form q(a,b) = A a^2 + 2B ab + C b^2
+// with q = xf^2 + yf^2, (xf,yf) = J.(a,b)/oblur, pre-multiplied by log2(e) so that the Gaussian
+// weight exp(-q) is exp2(-q'), plus J itself for the non-Gaussian filters.
+__device__ __forceinline__ float pad_inv_sv(float s, float padval, float pad_pow)
+{
+    // (padval + s^p)^(-1/p)   (helpers.pyx:1661-1662)
+    const float sp = exp2f(pad_pow * __log2f(s));            // s = 0 -> log2 = -inf -> 0
+    return exp2f(-__log2f(padval + sp) / pad_pow);
+}
+
+__device__ __forceinline__ void padded_inverse_f32(const double *Ji, float padval, float pad_pow,
+                                                   float *J, float &smin)
+{
+    const float a = (float)Ji[0], b = (float)Ji[1], c = (float)Ji[2], d = (float)Ji[3];
+    const float theta = 0.5f * atan2f(2.0f * (a * c + b * d), (a * a + b * b) - (c * c + d * d));
+    const float phi = 0.5f * atan2f(2.0f * (a * b + c * d), (a * a + c * c) - (b * b + d * d));
+    float St, Ct, Sp, Cp;
+    sincosf(theta, &St, &Ct);
+    sincosf(phi, &Sp, &Cp);
+    const float cs00 = (Ct * a + St * c) * Cp + (Ct * b + St * d) * Sp;
+    const float cs11 = (St * a - Ct * c) * Sp - (St * b - Ct * d) * Cp;
+    const float s0 = pad_inv_sv(fabsf(cs00), padval, pad_pow);
+    const float s1 = pad_inv_sv(fabsf(cs11), padval, pad_pow);
+    const float c00 = cs00 >= 0 ? 1.0f : -1.0f, c11 = cs11 >= 0 ? 1.0f : -1.0f;
+    // J = V diag(s') U^T with V = W diag(sign), U = R(theta)   (svc2x2_fast(V, s, U, J), 1663)
+    const float V00 = Cp * c00, V01 = -Sp * c11, V10 = Sp * c00, V11 = Cp * c11;
+    const float a00 = V00 * s0, a10 = V10 * s0, a01 = V01 * s1, a11 = V11 * s1;
+    J[0] = a00 * Ct + a01 * (-St);
+    J[1] = a00 * St + a01 * Ct;
+    J[2] = a10 * Ct + a11 * (-St);
+    J[3] = a10 * St + a11 * Ct;
+    smin = fminf(s0, s1);
+}
+
 // A: chain arithmetic; RegT: footprint arithmetic (double = parity mode, float = fast mode)
 template <class A, typename SrcT, typename DstT, typename RegT>
 __global__ void __launch_bounds__(JTX * JTY)
 k_jacobian(const __grid_constant__ JacParams P)
 {
+    constexpr bool FASTI = (sizeof(RegT) == 4);
     __shared__ double s_px[PH][PW], s_py[PH][PW];     // inverse-mapped coordinates of grid points
     __shared__ double s_m2[CH][CW];                   // Jmag2 per cell (helpers.pyx:1020)
     __shared__ unsigned char s_flag[CH][CW];          // jump flag per cell (1 = ok)
@@ -251,28 +288,40 @@ k_jacobian(const __grid_constant__ JacParams P)
         unsigned char flag = 1;
         if (P.jump_thresh != 0.0 && gcx >= 0 && gcx < NCX && gcy >= 0 && gcy < NCY) {
             const bool ix_in = (gcx >= 1 && gcx <= NCX - 2), iy_in = (gcy >= 1 && gcy <= NCY - 2);
+            const double me = s_m2[cj][ci];
             double v[9];
+            int nv = 0;
             if (ix_in && iy_in) {
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) v[a * 3 + b] = s_m2[cj - 1 + a][ci - 1 + b];
-                flag = s_m2[cj][ci] <= __dmul_rn(kth3_of9(v), P.jump_thresh);
+                nv = 9;
             } else if (ix_in && NCY >= 2) {            // bottom / top row of cells: 2 x 3 lags
                 const int r0 = (gcy == 0) ? cj : cj - 1;
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) v[a * 3 + b] = s_m2[r0 + a][ci - 1 + b];
-                flag = s_m2[cj][ci] <= __dmul_rn(kth2_of6(v), P.jump_thresh);
+                nv = 6;
             } else if (iy_in && NCX >= 2) {            // left / right column of cells: 3 x 2 lags
                 const int c0 = (gcx == 0) ? ci : ci - 1;
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) v[a * 2 + b] = s_m2[cj - 1 + a][c0 + b];
-                flag = s_m2[cj][ci] <= __dmul_rn(kth2_of6(v), P.jump_thresh);
+                nv = 6;
             }                                           // corners stay 1 (helpers.pyx:986-989)
+            if (nv) {
+                // quick accept: the k-th smallest is >= the minimum, and for a positive threshold
+                // me <= thresh*min implies me <= thresh*kth.  Only cells near a jump (or NaN) sort.
+                double mn = v[0];
+#pragma unroll
+                for (int k = 1; k < 9; ++k) if (k < nv) mn = fmin(mn, v[k]);
+                if (P.jump_thresh > 0.0 && me <= __dmul_rn(mn, P.jump_thresh)) flag = 1;
+                else if (nv == 9) flag = me <= __dmul_rn(kth3_of9(v), P.jump_thresh);
+                else flag = me <= __dmul_rn(kth2_of6(v), P.jump_thresh);
+            }
         }
         s_flag[cj][ci] = flag;
     }
@@ -313,63 +362,139 @@ k_jacobian(const __grid_constant__ JacParams P)
 #pragma unroll
     for (int k = 0; k < 4; ++k) Ji[k] = __ddiv_rn(Ji[k], denom);
 
-    double U[4], V[4], s[2], J[4];
-    svd2x2_dev(Ji, U, s, V);                                                     // helpers.pyx:1659
-    s[0] = exp(__ddiv_rn(-log(__dadd_rn(P.padval, exp(__dmul_rn(log(s[0]), P.pad_pow)))), P.pad_pow));
-    s[1] = exp(__ddiv_rn(-log(__dadd_rn(P.padval, exp(__dmul_rn(log(s[1]), P.pad_pow)))), P.pad_pow));
-    svc2x2_dev(V, s, U, J);                                                      // helpers.pyx:1663
-    const double smin = fmin(s[0], s[1]);
-    const double rs = __dmul_rn(2.0, ceil(__ddiv_rn(P.oblur, smin)));            // helpers.pyx:1666
-    long long reg = (rs < 1.0e15) ? (long long)rs : 1000000000000000LL;
-    if (P.max_reg > 0 && reg > P.max_reg) reg = P.max_reg;
-    const int half = (int)(reg / 2 > 0x3fffffff ? 0x3fffffff : reg / 2);
-
     const double px = s_px[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
     const double py = s_py[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
     DstT *drow = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch);
     if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) { drow[X] = (DstT)0; return; }
     const double fxs = floor(px), fys = floor(py);
     const long long xs = (long long)fxs, ys = (long long)fys;
-    const RegT xf_of = (RegT)__dsub_rn(px, fxs), yf_of = (RegT)__dsub_rn(py, fys);
-    const RegT J0 = (RegT)J[0], J1 = (RegT)J[1], J2 = (RegT)J[2], J3 = (RegT)J[3];
-    const RegT ob = (RegT)P.oblur;
-
-    RegT val = 0, wgt = 0;
     int state = 0;
-    for (int yr = -half; yr <= half; ++yr) {
-        const RegT y0 = (RegT)yr + yf_of;
-        for (int xr = -half; xr <= half; ++xr) {
-            const RegT x0 = (RegT)xr + xf_of;
-            RegT xf, yf;
-            if (sizeof(RegT) == 8) {
-                xf = fabs(__dadd_rn(__dmul_rn(J0, x0), __dmul_rn(J1, y0))) / ob;   // helpers.pyx:1689-1690
-                yf = fabs(__dadd_rn(__dmul_rn(J2, x0), __dmul_rn(J3, y0))) / ob;
-            } else {
-                xf = fabsf(J0 * x0 + J1 * y0) / ob;
-                yf = fabsf(J2 * x0 + J3 * y0) / ob;
-            }
-            const RegT filt = filt_eval<RegT>(P.filter, xf, yf);
-            wgt += filt;                                                          // helpers.pyx:1740
-            int st = 0;
-            int iy = jbound(ys + yr, P.full_h, P.bound_y, st);
-            int ix = jbound(xs + xr, P.full_w, P.bound_x, st);
-            state |= st & 2;
-            if (st == 0) {
-                ix -= P.src_x0;
-                iy -= P.src_y0;
-                if ((unsigned)ix < (unsigned)P.src_w && (unsigned)iy < (unsigned)P.src_h) {
-                    const RegT sv = (RegT)__ldg(reinterpret_cast<const SrcT *>(
-                        src_base + (long long)iy * P.src_pitch) + ix);
-                    if (sizeof(RegT) == 8) val = __dadd_rn(val, __dmul_rn(sv, filt));   // helpers.pyx:1796
-                    else val = fmaf(sv, filt, val);
-                } else {
-                    state |= 4;
+
+    if constexpr (!FASTI) {
+        // ------------------------- parity mode: the reference's loop, in its order -------------
+        double U[4], V[4], s[2], J[4];
+        svd2x2_dev(Ji, U, s, V);                                                     // helpers.pyx:1659
+        s[0] = exp(__ddiv_rn(-log(__dadd_rn(P.padval, exp(__dmul_rn(log(s[0]), P.pad_pow)))), P.pad_pow));
+        s[1] = exp(__ddiv_rn(-log(__dadd_rn(P.padval, exp(__dmul_rn(log(s[1]), P.pad_pow)))), P.pad_pow));
+        svc2x2_dev(V, s, U, J);                                                      // helpers.pyx:1663
+        const double smin = fmin(s[0], s[1]);
+        const double rs = __dmul_rn(2.0, ceil(__ddiv_rn(P.oblur, smin)));            // helpers.pyx:1666
+        long long reg = (rs < 1.0e15) ? (long long)rs : 1000000000000000LL;
+        if (P.max_reg > 0 && reg > P.max_reg) reg = P.max_reg;
+        const int half = (int)(reg / 2 > 0x3fffffff ? 0x3fffffff : reg / 2);
+        const double xf_of = __dsub_rn(px, fxs), yf_of = __dsub_rn(py, fys);
+        const double ob = P.oblur;
+        double val = 0, wgt = 0;
+        for (int yr = -half; yr <= half; ++yr) {
+            const double y0 = __dadd_rn((double)yr, yf_of);
+            for (int xr = -half; xr <= half; ++xr) {
+                const double x0 = __dadd_rn((double)xr, xf_of);
+                const double xf = __ddiv_rn(fabs(__dadd_rn(__dmul_rn(J[0], x0), __dmul_rn(J[1], y0))), ob);
+                const double yf = __ddiv_rn(fabs(__dadd_rn(__dmul_rn(J[2], x0), __dmul_rn(J[3], y0))), ob);
+                const double filt = filt_eval<double>(P.filter, xf, yf);
+                wgt = __dadd_rn(wgt, filt);                                          // helpers.pyx:1740
+                int st = 0;
+                int iy = jbound(ys + yr, P.full_h, P.bound_y, st);
+                int ix = jbound(xs + xr, P.full_w, P.bound_x, st);
+                state |= st & 2;
+                if (st == 0) {
+                    ix -= P.src_x0;
+                    iy -= P.src_y0;
+                    if ((unsigned)ix < (unsigned)P.src_w && (unsigned)iy < (unsigned)P.src_h) {
+                        const double sv = (double)__ldg(reinterpret_cast<const SrcT *>(
+                            src_base + (long long)iy * P.src_pitch) + ix);
+                        val = __dadd_rn(val, __dmul_rn(sv, filt));                   // helpers.pyx:1796
+                    } else {
+                        state |= 4;
+                    }
                 }
             }
         }
+        drow[X] = (DstT)((wgt > 0) ? val / wgt : 0.0);                               // helpers.pyx:1800
+    } else {
+        // ------------------------- fast mode (fp32) --------------------------------------------
+        float J[4], smin;
+        padded_inverse_f32(Ji, (float)P.padval, (float)P.pad_pow, J, smin);
+        const float ob = (float)P.oblur, iob = 1.0f / ob;
+        const float rsf = 2.0f * ceilf(ob / smin);
+        long long reg = (rsf < 1.0e9f) ? (long long)rsf : 1000000000LL;
+        if (P.max_reg > 0 && reg > P.max_reg) reg = P.max_reg;
+        const int half = (int)(reg / 2);
+        const float xf_of = (float)(px - fxs), yf_of = (float)(py - fys);
+        const float J0 = J[0] * iob, J1 = J[1] * iob, J2 = J[2] * iob, J3 = J[3] * iob;
+        float val = 0.0f, wgt = 0.0f;
+        const bool whole = (P.src_x0 == 0 && P.src_y0 == 0 && P.src_w == P.full_w && P.src_h == P.full_h);
+        const bool inside = whole && xs - half >= 0 && xs + half < P.full_w &&
+                            ys - half >= 0 && ys + half < P.full_h;
+        const long long pe = P.src_pitch / (long long)sizeof(SrcT);
+        if (P.filter == TFM_FILT_GAUSSIAN && half <= 24) {
+            // exp(-(xf^2+yf^2)) = exp2(-(A a^2 + 2B ab + C b^2)); along a row of the footprint the
+            // weight obeys w(a+1) = w(a) r(a), r(a+1) = r(a) c: two multiplies per tap, three exp2
+            // per row instead of one exp per tap.
+            const float L2E = 1.4426950408889634f;
+            const float Aq = (J0 * J0 + J2 * J2) * L2E, Bq = (J0 * J1 + J2 * J3) * L2E,
+                        Cq = (J1 * J1 + J3 * J3) * L2E;
+            const float cstep = exp2f(-2.0f * Aq);
+            const float a0 = (float)(-half) + xf_of;
+            for (int yr = -half; yr <= half; ++yr) {
+                const float b = (float)yr + yf_of;
+                float w = exp2f(-((Aq * a0 + 2.0f * Bq * b) * a0 + Cq * b * b));
+                float r = exp2f(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b));
+                if (inside) {
+                    const SrcT *row = reinterpret_cast<const SrcT *>(src_base) + (ys + yr) * pe + (xs - half);
+                    for (int k = 0; k <= 2 * half; ++k) {
+                        val = fmaf((float)__ldg(row + k), w, val);
+                        wgt += w;
+                        w *= r;
+                        r *= cstep;
+                    }
+                } else {
+                    int sty = 0;
+                    const int iy0 = jbound(ys + yr, P.full_h, P.bound_y, sty);
+                    for (int k = 0; k <= 2 * half; ++k) {
+                        int st = sty;
+                        int ix = jbound(xs - half + k, P.full_w, P.bound_x, st);
+                        state |= st & 2;
+                        wgt += w;
+                        if (st == 0) {
+                            ix -= P.src_x0;
+                            const int iy = iy0 - P.src_y0;
+                            if ((unsigned)ix < (unsigned)P.src_w && (unsigned)iy < (unsigned)P.src_h)
+                                val = fmaf((float)__ldg(reinterpret_cast<const SrcT *>(src_base) + iy * pe + ix), w, val);
+                            else
+                                state |= 4;
+                        }
+                        w *= r;
+                        r *= cstep;
+                    }
+                }
+            }
+        } else {
+            for (int yr = -half; yr <= half; ++yr) {
+                const float y0 = (float)yr + yf_of;
+                int sty = 0;
+                const int iy0 = jbound(ys + yr, P.full_h, P.bound_y, sty);
+                for (int xr = -half; xr <= half; ++xr) {
+                    const float x0 = (float)xr + xf_of;
+                    const float filt = filt_eval<float>(P.filter, fabsf(J0 * x0 + J1 * y0), fabsf(J2 * x0 + J3 * y0));
+                    wgt += filt;
+                    int st = sty;
+                    int ix = jbound(xs + xr, P.full_w, P.bound_x, st);
+                    state |= st & 2;
+                    if (st == 0) {
+                        ix -= P.src_x0;
+                        const int iy = iy0 - P.src_y0;
+                        if ((unsigned)ix < (unsigned)P.src_w && (unsigned)iy < (unsigned)P.src_h)
+                            val = fmaf((float)__ldg(reinterpret_cast<const SrcT *>(src_base) + iy * pe + ix), filt, val);
+                        else
+                            state |= 4;
+                    }
+                }
+            }
+        }
+        drow[X] = (DstT)((wgt > 0) ? val / wgt : 0.0f);
     }
     if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
-    drow[X] = (DstT)((wgt > 0) ? val / wgt : (RegT)0);                            // helpers.pyx:1800
 }
 
 __global__ void k_svd_hook(int which, const double *in, double *out)

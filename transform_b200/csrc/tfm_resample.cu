@@ -33,6 +33,8 @@ struct ResampleParams {
     int flags;
     int lw;                                  // log2 of warp patch width (5, 4 or 3)
     int n_planes;
+    int int_w, int_h;                        // #columns / #rows at which a whole NT x NT footprint fits
+    double aff[6];                           // pre-composed affine map a00 a01 a10 a11 b0 b1 (AFF kernels)
     double fill;
     int *status;
     ChainDev chain;
@@ -167,6 +169,20 @@ template <> struct MethodTraits<TFM_NEAREST> { static constexpr int NPX = 4, NT 
 template <> struct MethodTraits<TFM_LINEAR>  { static constexpr int NPX = 4, NT = 2; };
 template <> struct MethodTraits<TFM_CUBIC>   { static constexpr int NPX = 2, NT = 4; };
 
+// floor + fractional part without the conversion (XU) pipe: t = x + 1.5*2^52 rounds x to the nearest
+// integer in the low mantissa bits; one compare-and-correct turns round-to-nearest into floor.
+// Valid for |x| < 2^31; callers route anything else to an out-of-range index first.
+__device__ __forceinline__ void floor_frac_fast(double x, int &i, float &frac)
+{
+    const double MAGIC = 6755399441055744.0;
+    const double t = x + MAGIC;
+    double r = t - MAGIC;                 // rn(x)
+    i = __double2loint(t);
+    double fr = x - r;                    // in [-0.5, 0.5], exact
+    if (fr < 0.0) { fr += 1.0; i -= 1; }
+    frac = (float)fr;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -176,63 +192,108 @@ template <> struct MethodTraits<TFM_CUBIC>   { static constexpr int NPX = 2, NT 
 // RegT     arithmetic type of the interpolation (double in exact mode, float in fast mode)
 // GENERIC  false: both axes 'truncate', source is the whole image (fast path);
 //          true : per-axis runtime boundary modes and/or staged source sub-rectangle
-template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC>
+// AFF      the whole chain was pre-composed by the host into one affine map P.aff (fast mode only)
+template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC, bool AFF>
 __global__ void __launch_bounds__(256)
 k_resample(const __grid_constant__ ResampleParams P)
 {
     constexpr int NPX = MethodTraits<METHOD>::NPX;
     constexpr int NT = MethodTraits<METHOD>::NT;
     constexpr int T0 = (METHOD == TFM_CUBIC) ? -1 : 0;          // first tap offset
+    constexpr bool FASTI = (sizeof(RegT) == 4);                 // fp32 interpolation arithmetic
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lw = P.lw, ww = 1 << lw;
-    const void *const src_base = static_cast<const char *>(P.src) + (long long)blockIdx.z * P.src_plane;
-    void *const dst_base = static_cast<char *>(P.dst) + (long long)blockIdx.z * P.dst_plane;
+    const char *const src_base = static_cast<const char *>(P.src) + (long long)blockIdx.z * P.src_plane;
+    char *const dst_base = static_cast<char *>(P.dst) + (long long)blockIdx.z * P.dst_plane;
     const int px = ((warp & ((32 >> lw) - 1)) << lw) + (lane & (ww - 1));
     const int py = ((warp >> (5 - lw)) << (5 - lw)) + (lane >> lw);
     const int X = blockIdx.x * 32 + px;
     const int Y0 = blockIdx.y * (8 * NPX) + py;
-    if (X >= P.dst_w) return;
+    const bool xin = X < P.dst_w;
 
     // ---- phase 1: coordinates (fp64, in registers) ----
     double cx[NPX], cy[NPX];
+    if (AFF) {
+        const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y0);
+        const double bx = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
+        const double by = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
 #pragma unroll
-    for (int j = 0; j < NPX; ++j) {
-        double x = (double)(P.dst_x0 + X);
-        double y = (double)(P.dst_y0 + Y0 + 8 * j);
-        chain_eval<A>(P.chain, x, y);
-        cx[j] = x;
-        cy[j] = y;
+        for (int j = 0; j < NPX; ++j) {
+            cx[j] = fma((double)(8 * j), P.aff[1], bx);
+            cy[j] = fma((double)(8 * j), P.aff[3], by);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            cx[j] = (double)(P.dst_x0 + X);
+            cy[j] = (double)(P.dst_y0 + Y0 + 8 * j);
+        }
+        chain_eval_n<A, NPX>(P.chain, cx, cy);
     }
 
     // ---- phase 2: taps (all loads of the NPX pixels issued before any is consumed) ----
     RegT v[NPX][NT][NT];
-    double fracx[NPX], fracy[NPX];
+    double fracx[NPX], fracy[NPX];          // exact mode
+    float ffx[NPX], ffy[NPX];               // fast mode
+    bool valid[NPX];
 #pragma unroll
-    for (int j = 0; j < NPX; ++j) {
-        double fx, fy;
-        if (METHOD == TFM_NEAREST) {
-            fx = floor(__dadd_rn(cx[j], 0.5));                  // helpers.pyx:127
-            fy = floor(__dadd_rn(cy[j], 0.5));
-        } else {
-            fx = floor(cx[j]);
-            fy = floor(cy[j]);
+    for (int j = 0; j < NPX; ++j) valid[j] = xin && (Y0 + 8 * j < P.dst_h);
+
+    if (!GENERIC) {
+        int ix[NPX], iy[NPX];
+        bool interior = true;
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            double x = cx[j], y = cy[j];
+            if (METHOD == TFM_NEAREST) { x = __dadd_rn(x, 0.5); y = __dadd_rn(y, 0.5); }   // helpers.pyx:127
+            const bool sane = (fabs(x) < 1.0e9) && (fabs(y) < 1.0e9);     // false for NaN / inf / absurd
+            if (FASTI) {
+                floor_frac_fast(x, ix[j], ffx[j]);
+                floor_frac_fast(y, iy[j], ffy[j]);
+            } else {
+                const double fx = floor(x), fy = floor(y);
+                fracx[j] = __dsub_rn(x, fx);                    // alpha = index - floor(index)
+                fracy[j] = __dsub_rn(y, fy);
+                ix[j] = __double2int_rz(fx);
+                iy[j] = __double2int_rz(fy);
+            }
+            if (!sane) { ix[j] = -1000000; iy[j] = -1000000; }  // whole footprint out of range -> fill
+            if (!valid[j]) { ix[j] = -T0; iy[j] = -T0; }        // not an output pixel: harmless taps
+            interior = interior && ((unsigned)(ix[j] + T0) < (unsigned)P.int_w) &&
+                       ((unsigned)(iy[j] + T0) < (unsigned)P.int_h);
         }
-        fracx[j] = __dsub_rn(cx[j], fx);                        // alpha = index - floor(index)
-        fracy[j] = __dsub_rn(cy[j], fy);
-        if (Y0 + 8 * j >= P.dst_h) {                            // ragged bottom tile: not an output pixel
+        const long long pe = P.src_pitch / (long long)sizeof(SrcT);
+        if (__all_sync(0xffffffffu, interior)) {
+            // every tap of every pixel of this warp lies inside the image: no predicates
 #pragma unroll
-            for (int ty = 0; ty < NT; ++ty)
+            for (int j = 0; j < NPX; ++j) {
+                const SrcT *p = reinterpret_cast<const SrcT *>(src_base) + (long long)(iy[j] + T0) * pe + (ix[j] + T0);
 #pragma unroll
-                for (int tx = 0; tx < NT; ++tx) v[j][ty][tx] = (RegT)0;
-        } else if (!GENERIC) {
-            const int ix = base_trunc(fx), iy = base_trunc(fy);
+                for (int ty = 0; ty < NT; ++ty)
 #pragma unroll
-            for (int ty = 0; ty < NT; ++ty)
-#pragma unroll
-                for (int tx = 0; tx < NT; ++tx)
-                    v[j][ty][tx] = tap_trunc<SrcT, RegT>(P, src_base, ix + T0 + tx, iy + T0 + ty);
+                    for (int tx = 0; tx < NT; ++tx) v[j][ty][tx] = (RegT)__ldg(p + ty * pe + tx);
+            }
         } else {
+#pragma unroll
+            for (int j = 0; j < NPX; ++j)
+#pragma unroll
+                for (int ty = 0; ty < NT; ++ty)
+#pragma unroll
+                    for (int tx = 0; tx < NT; ++tx)
+                        v[j][ty][tx] = valid[j] ? tap_trunc<SrcT, RegT>(P, src_base, ix[j] + T0 + tx, iy[j] + T0 + ty)
+                                                : (RegT)0;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            double x = cx[j], y = cy[j];
+            if (METHOD == TFM_NEAREST) { x = __dadd_rn(x, 0.5); y = __dadd_rn(y, 0.5); }
+            const double fx = floor(x), fy = floor(y);
+            fracx[j] = __dsub_rn(x, fx);
+            fracy[j] = __dsub_rn(y, fy);
+            ffx[j] = (float)fracx[j];
+            ffy[j] = (float)fracy[j];
             // |f| >= 2^51 (or NaN): the reference's float tap offsets are absorbed / invalid; every
             // tap shares the base index ("absurd coordinates").
             const bool okx = fabs(fx) < 2.0e15, oky = fabs(fy) < 2.0e15;
@@ -241,21 +302,22 @@ k_resample(const __grid_constant__ ResampleParams P)
             for (int ty = 0; ty < NT; ++ty)
 #pragma unroll
                 for (int tx = 0; tx < NT; ++tx)
-                    v[j][ty][tx] = tap_generic<SrcT, RegT>(P, src_base, okx ? bx + T0 + tx : bx,
-                                                           oky ? by + T0 + ty : by);
+                    v[j][ty][tx] = valid[j] ? tap_generic<SrcT, RegT>(P, src_base, okx ? bx + T0 + tx : bx,
+                                                                      oky ? by + T0 + ty : by)
+                                            : (RegT)0;
         }
     }
 
     // ---- phase 3: weights, reduction, store ----
 #pragma unroll
     for (int j = 0; j < NPX; ++j) {
+        if (!valid[j]) continue;
         const int Y = Y0 + 8 * j;
-        if (Y >= P.dst_h) continue;
         RegT r;
         if (METHOD == TFM_NEAREST) {
             r = v[j][0][0];
         } else if (METHOD == TFM_LINEAR) {
-            if (sizeof(RegT) == 8) {
+            if (!FASTI) {
                 // helpers.pyx:584-610: weight = prod(alpha | 1-alpha); sum(region*weight) runs
                 // sequentially over the contiguous 2x2 block (x fastest).
                 const double ax = fracx[j], ay = fracy[j];
@@ -266,13 +328,13 @@ k_resample(const __grid_constant__ ResampleParams P)
                 acc = __dadd_rn(acc, __dmul_rn((double)v[j][1][1], __dmul_rn(ax, ay)));
                 r = (RegT)acc;
             } else {
-                const float ax = (float)fracx[j], ay = (float)fracy[j];
+                const float ax = ffx[j], ay = ffy[j];
                 const float top = fmaf(ax, (float)v[j][0][1] - (float)v[j][0][0], (float)v[j][0][0]);
                 const float bot = fmaf(ax, (float)v[j][1][1] - (float)v[j][1][0], (float)v[j][1][0]);
                 r = (RegT)fmaf(ay, bot - top, top);
             }
         } else {
-            if (sizeof(RegT) == 8) {
+            if (!FASTI) {
                 double rows[4];
                 const bool f32pass = (sizeof(SrcT) == 4) && (P.flags & TFM_F_REGION_SRC_DTYPE);
 #pragma unroll
@@ -287,15 +349,14 @@ k_resample(const __grid_constant__ ResampleParams P)
                 r = (RegT)hermite_exact(rows[0], rows[1], rows[2], rows[3], fracy[j]);
             } else {
                 float rows[4];
-                const float bx = (float)fracx[j];
 #pragma unroll
                 for (int ty = 0; ty < 4; ++ty)
                     rows[ty] = hermite_fast((float)v[j][ty][0], (float)v[j][ty][1],
-                                            (float)v[j][ty][2], (float)v[j][ty][3], bx);
-                r = (RegT)hermite_fast(rows[0], rows[1], rows[2], rows[3], (float)fracy[j]);
+                                            (float)v[j][ty][2], (float)v[j][ty][3], ffx[j]);
+                r = (RegT)hermite_fast(rows[0], rows[1], rows[2], rows[3], ffy[j]);
             }
         }
-        DstT *row = reinterpret_cast<DstT *>(static_cast<char *>(dst_base) + (long long)Y * P.dst_pitch);
+        DstT *row = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch);
         row[X] = (DstT)r;
     }
 }
@@ -304,17 +365,25 @@ k_resample(const __grid_constant__ ResampleParams P)
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 template <int METHOD, typename SrcT, typename DstT, class A, typename RegT>
-static cudaError_t launch2(const ResampleParams &P, bool generic, cudaStream_t st, const char **name)
+static cudaError_t launch2(ResampleParams &P, bool generic, bool aff, cudaStream_t st, const char **name)
 {
     constexpr int NPX = MethodTraits<METHOD>::NPX;
+    constexpr int NT = MethodTraits<METHOD>::NT;
     dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 8 * NPX - 1) / (8 * NPX)),
               (unsigned)P.n_planes);
     if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
+    P.int_w = P.src_w - NT + 1 > 0 ? P.src_w - NT + 1 : 0;
+    P.int_h = P.src_h - NT + 1 > 0 ? P.src_h - NT + 1 : 0;
     if (generic) {
-        k_resample<METHOD, SrcT, DstT, A, RegT, true><<<grid, 256, 0, st>>>(P);
+        k_resample<METHOD, SrcT, DstT, A, RegT, true, false><<<grid, 256, 0, st>>>(P);
         *name = "k_resample<generic>";
+    } else if (aff && !A::exact) {
+        if constexpr (!A::exact) {
+            k_resample<METHOD, SrcT, DstT, Fast, RegT, false, true><<<grid, 256, 0, st>>>(P);
+        }
+        *name = "k_resample<trunc,affine>";
     } else {
-        k_resample<METHOD, SrcT, DstT, A, RegT, false><<<grid, 256, 0, st>>>(P);
+        k_resample<METHOD, SrcT, DstT, A, RegT, false, false><<<grid, 256, 0, st>>>(P);
         *name = "k_resample<trunc>";
     }
     count_launch();
@@ -322,14 +391,47 @@ static cudaError_t launch2(const ResampleParams &P, bool generic, cudaStream_t s
 }
 
 template <typename SrcT, typename DstT, class A, typename RegT>
-static cudaError_t launch1(int method, const ResampleParams &P, bool generic, cudaStream_t st,
+static cudaError_t launch1(int method, ResampleParams &P, bool generic, bool aff, cudaStream_t st,
                            const char **name)
 {
     switch (method) {
-    case TFM_NEAREST: return launch2<TFM_NEAREST, SrcT, DstT, A, RegT>(P, generic, st, name);
-    case TFM_LINEAR:  return launch2<TFM_LINEAR, SrcT, DstT, A, RegT>(P, generic, st, name);
-    default:          return launch2<TFM_CUBIC, SrcT, DstT, A, RegT>(P, generic, st, name);
+    case TFM_NEAREST: return launch2<TFM_NEAREST, SrcT, DstT, A, RegT>(P, generic, aff, st, name);
+    case TFM_LINEAR:  return launch2<TFM_LINEAR, SrcT, DstT, A, RegT>(P, generic, aff, st, name);
+    default:          return launch2<TFM_CUBIC, SrcT, DstT, A, RegT>(P, generic, aff, st, name);
     }
+}
+
+// Pre-compose a chain made only of LINEAR / IDENTITY ops into one affine map (fast mode only; the
+// fp64-exact mode never pre-fuses, SURVEY.md section 7 "hard parts").  Parameter preparation on the
+// host, a handful of flops per call -- not part of the data path.
+static bool compose_affine(const tfm_op *ops, int n, double *aff)
+{
+    double a00 = 1, a01 = 0, a10 = 0, a11 = 1, b0 = 0, b1 = 0;
+    for (int i = 0; i < n; ++i) {
+        const tfm_op &op = ops[i];
+        if (op.kind == TFM_OP_IDENTITY) continue;
+        if (op.kind != TFM_OP_LINEAR) return false;
+        const bool fwd = (op.dir == TFM_FWD);
+        const int f = op.flags;
+        double m00 = 1, m01 = 0, m10 = 0, m11 = 1;
+        if (f & TFM_LIN_HAS_MATRIX) { m00 = op.p[0]; m01 = op.p[1]; m10 = op.p[2]; m11 = op.p[3]; }
+        double pa0 = 0, pa1 = 0, pb0 = 0, pb1 = 0;      // out = M.(in + pa) + pb
+        if (fwd) {
+            if (f & TFM_LIN_HAS_PRE) { pa0 = op.p[4]; pa1 = op.p[5]; }
+            if (f & TFM_LIN_HAS_POST) { pb0 = op.p[6]; pb1 = op.p[7]; }
+        } else {
+            if (f & TFM_LIN_HAS_POST) { pa0 = -op.p[6]; pa1 = -op.p[7]; }
+            if (f & TFM_LIN_HAS_PRE) { pb0 = -op.p[4]; pb1 = -op.p[5]; }
+        }
+        const double c0 = b0 + pa0, c1 = b1 + pa1;      // (A x + b) + pa
+        const double n00 = m00 * a00 + m01 * a10, n01 = m00 * a01 + m01 * a11;
+        const double n10 = m10 * a00 + m11 * a10, n11 = m10 * a01 + m11 * a11;
+        b0 = m00 * c0 + m01 * c1 + pb0;
+        b1 = m10 * c0 + m11 * c1 + pb1;
+        a00 = n00; a01 = n01; a10 = n10; a11 = n11;
+    }
+    aff[0] = a00; aff[1] = a01; aff[2] = a10; aff[3] = a11; aff[4] = b0; aff[5] = b1;
+    return true;
 }
 
 int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
@@ -375,21 +477,23 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
     if ((a->bound_x == TFM_B_FORBID || a->bound_y == TFM_B_FORBID || subrect) && !a->status_dev)
         return TFM_EVALUE;
 
+    if (s.pitch % (s.dtype == TFM_F64 ? 8 : 4) != 0) return TFM_EVALUE;
     const char *name = "";
     cudaError_t e;
     const bool exact = (a->precision == TFM_PREC_EXACT64);
+    const bool aff = !exact && !(a->tuning & 4) && compose_affine(a->chain, a->n_ops, P.aff);
     if (exact) {
         if (s.dtype == TFM_F32 && d.dtype == TFM_F64)
-            e = launch1<float, double, Exact, double>(a->method, P, generic, st, &name);
+            e = launch1<float, double, Exact, double>(a->method, P, generic, false, st, &name);
         else if (s.dtype == TFM_F64 && d.dtype == TFM_F64)
-            e = launch1<double, double, Exact, double>(a->method, P, generic, st, &name);
+            e = launch1<double, double, Exact, double>(a->method, P, generic, false, st, &name);
         else if (s.dtype == TFM_F32 && d.dtype == TFM_F32 && a->method == TFM_NEAREST)
-            e = launch2<TFM_NEAREST, float, float, Exact, double>(P, generic, st, &name);
+            e = launch2<TFM_NEAREST, float, float, Exact, double>(P, generic, false, st, &name);
         else
             return TFM_EUNSUPPORTED;
     } else if (a->precision == TFM_PREC_FAST32) {
         if (s.dtype == TFM_F32 && d.dtype == TFM_F32)
-            e = launch1<float, float, Fast, float>(a->method, P, generic, st, &name);
+            e = launch1<float, float, Fast, float>(a->method, P, generic, aff, st, &name);
         else
             return TFM_EUNSUPPORTED;
     } else {
