@@ -231,6 +231,58 @@ __device__ __forceinline__ void padded_inverse_f32(const double *Ji, float padva
     smin = fminf(s0, s1);
 }
 
+// f(lambda) = (padval + lambda^(p/2))^(-2/p): the squared padded inverse singular value as a function
+// of the squared singular value lambda (helpers.pyx:1661-1662 applied to s = sqrt(lambda)).
+__device__ __forceinline__ float pad_inv_sq(float lam, float padval, float pad_pow)
+{
+    const float sp = exp2f(0.5f * pad_pow * __log2f(lam));   // lam = 0 -> 0
+    return exp2f(-2.0f * __log2f(padval + sp) / pad_pow);
+}
+
+// Gaussian footprint weights need only Q = J^T J with J = V diag(s') U^T, i.e. Q = U diag(s'^2) U^T
+// = f(M M^T) for M = Ji = U diag(s) V^T: a function of a symmetric 2x2 matrix, which is always
+// alpha*I + beta*(M M^T).  No angles, no sincos -- eigenvalues by one sqrt.
+__device__ __forceinline__ void gaussian_quadratic_f32(const double *Ji, float padval, float pad_pow,
+                                                       float &q00, float &q01, float &q11, float &smin)
+{
+    const float a = (float)Ji[0], b = (float)Ji[1], c = (float)Ji[2], d = (float)Ji[3];
+    const float g00 = a * a + b * b, g01 = a * c + b * d, g11 = c * c + d * d;
+    const float mean = 0.5f * (g00 + g11), dif = 0.5f * (g00 - g11);
+    const float rad = sqrtf(dif * dif + g01 * g01);
+    const float lp = mean + rad, lm = fmaxf(mean - rad, 0.0f);
+    const float fp = pad_inv_sq(lp, padval, pad_pow), fm = pad_inv_sq(lm, padval, pad_pow);
+    float beta = 0.0f;
+    if (rad > 1e-6f * mean) beta = (fp - fm) / (lp - lm);
+    const float alpha = fp - beta * lp;
+    q00 = alpha + beta * g00;
+    q01 = beta * g01;
+    q11 = alpha + beta * g11;
+    smin = sqrtf(fp);                      // the larger singular value has the smaller padded inverse
+}
+
+// (2*HALF+1)^2 Gaussian taps, fully unrolled.  Weights by recurrence: along a row
+// w(a+1) = w(a) r(a), r(a+1) = r(a) cA; from row to row w0 *= rb, rb *= cC, r0 *= cB.
+template <int HALF, typename SrcT>
+__device__ __forceinline__ void gauss_taps(const SrcT *p, long long pe, float w0, float r0, float rb,
+                                           float cA, float cB, float cC, float &val, float &wgt)
+{
+#pragma unroll
+    for (int j = 0; j < 2 * HALF + 1; ++j) {
+        float w = w0, r = r0;
+#pragma unroll
+        for (int k = 0; k < 2 * HALF + 1; ++k) {
+            val = fmaf((float)__ldg(p + k), w, val);
+            wgt += w;
+            w *= r;
+            r *= cA;
+        }
+        p += pe;
+        w0 *= rb;
+        rb *= cC;
+        r0 *= cB;
+    }
+}
+
 // A: chain arithmetic; RegT: footprint arithmetic (double = parity mode, float = fast mode)
 template <class A, typename SrcT, typename DstT, typename RegT>
 __global__ void __launch_bounds__(JTX * JTY)
@@ -338,29 +390,42 @@ k_jacobian(const __grid_constant__ JacParams P)
     const int qi = (int)(jx - WX0), qj = (int)(jy - WY0);
 
     double Ji[4] = {0.0, 0.0, 0.0, 0.0};
-    int nvalid = 0;
-    // helpers.pyx:1227-1231: cells (y-1,x-1) + (y,x-1) + (y-1,x) + (y,x), in that order
+    const bool all_ok = (s_flag[qj - 1][qi - 1] & s_flag[qj][qi - 1] & s_flag[qj - 1][qi] & s_flag[qj][qi]) != 0;
+    if (FASTI && all_ok) {
+        // no flagged cell: the four cell Jacobians add up to the Sobel-like stencil
+        //   d/dx = (I[y+1][x+1]-I[y+1][x-1] + 2(I[y][x+1]-I[y][x-1]) + I[y-1][x+1]-I[y-1][x-1]) / 8
+        // (identical up to fp64 rounding of the regrouped sum)
+        const double *X0 = &s_px[qj - 1][qi - 1], *X1 = &s_px[qj][qi - 1], *X2 = &s_px[qj + 1][qi - 1];
+        const double *Y0r = &s_py[qj - 1][qi - 1], *Y1r = &s_py[qj][qi - 1], *Y2r = &s_py[qj + 1][qi - 1];
+        Ji[0] = 0.125 * ((X2[2] - X2[0]) + 2.0 * (X1[2] - X1[0]) + (X0[2] - X0[0]));
+        Ji[2] = 0.125 * ((Y2r[2] - Y2r[0]) + 2.0 * (Y1r[2] - Y1r[0]) + (Y0r[2] - Y0r[0]));
+        Ji[1] = 0.125 * ((X2[0] - X0[0]) + 2.0 * (X2[1] - X0[1]) + (X2[2] - X0[2]));
+        Ji[3] = 0.125 * ((Y2r[0] - Y0r[0]) + 2.0 * (Y2r[1] - Y0r[1]) + (Y2r[2] - Y0r[2]));
+    } else {
+        int nvalid = 0;
+        // helpers.pyx:1227-1231: cells (y-1,x-1) + (y,x-1) + (y-1,x) + (y,x), in that order
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int ci = qi - 1 + (k >> 1), cj = qj - 1 + (k & 1);
-        const bool ok = s_flag[cj][ci] != 0;
-        nvalid += ok ? 1 : 0;
-        const double ax = s_px[cj + 1][ci + 1], bx = s_px[cj + 1][ci], cx = s_px[cj][ci + 1], dx = s_px[cj][ci];
-        const double ay = s_py[cj + 1][ci + 1], by = s_py[cj + 1][ci], cy = s_py[cj][ci + 1], dy = s_py[cj][ci];
-        double j00 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ax, bx), cx), dx), 0.5);
-        double j10 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ay, by), cy), dy), 0.5);
-        double j01 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ax, bx), cx), dx), 0.5);
-        double j11 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ay, by), cy), dy), 0.5);
-        if (!ok) { j00 = 0.0; j01 = 0.0; j10 = 0.0; j11 = 0.0; }          // helpers.pyx:1207
-        if (k == 0) { Ji[0] = j00; Ji[1] = j01; Ji[2] = j10; Ji[3] = j11; }
-        else {
-            Ji[0] = __dadd_rn(Ji[0], j00); Ji[1] = __dadd_rn(Ji[1], j01);
-            Ji[2] = __dadd_rn(Ji[2], j10); Ji[3] = __dadd_rn(Ji[3], j11);
+        for (int k = 0; k < 4; ++k) {
+            const int ci = qi - 1 + (k >> 1), cj = qj - 1 + (k & 1);
+            const bool ok = s_flag[cj][ci] != 0;
+            nvalid += ok ? 1 : 0;
+            const double ax = s_px[cj + 1][ci + 1], bx = s_px[cj + 1][ci], cx = s_px[cj][ci + 1], dx = s_px[cj][ci];
+            const double ay = s_py[cj + 1][ci + 1], by = s_py[cj + 1][ci], cy = s_py[cj][ci + 1], dy = s_py[cj][ci];
+            double j00 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ax, bx), cx), dx), 0.5);
+            double j10 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ay, by), cy), dy), 0.5);
+            double j01 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ax, bx), cx), dx), 0.5);
+            double j11 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ay, by), cy), dy), 0.5);
+            if (!ok) { j00 = 0.0; j01 = 0.0; j10 = 0.0; j11 = 0.0; }          // helpers.pyx:1207
+            if (k == 0) { Ji[0] = j00; Ji[1] = j01; Ji[2] = j10; Ji[3] = j11; }
+            else {
+                Ji[0] = __dadd_rn(Ji[0], j00); Ji[1] = __dadd_rn(Ji[1], j01);
+                Ji[2] = __dadd_rn(Ji[2], j10); Ji[3] = __dadd_rn(Ji[3], j11);
+            }
         }
-    }
-    const double denom = (P.jump_thresh != 0.0) ? (double)(nvalid < 1 ? 1 : nvalid) : 4.0;
+        const double denom = (P.jump_thresh != 0.0) ? (double)(nvalid < 1 ? 1 : nvalid) : 4.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) Ji[k] = __ddiv_rn(Ji[k], denom);
+        for (int k = 0; k < 4; ++k) Ji[k] = __ddiv_rn(Ji[k], denom);
+    }
 
     const double px = s_px[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
     const double py = s_py[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
@@ -413,70 +478,68 @@ k_jacobian(const __grid_constant__ JacParams P)
         drow[X] = (DstT)((wgt > 0) ? val / wgt : 0.0);                               // helpers.pyx:1800
     } else {
         // ------------------------- fast mode (fp32) --------------------------------------------
-        float J[4], smin;
-        padded_inverse_f32(Ji, (float)P.padval, (float)P.pad_pow, J, smin);
         const float ob = (float)P.oblur, iob = 1.0f / ob;
-        const float rsf = 2.0f * ceilf(ob / smin);
+        const bool gauss = (P.filter == TFM_FILT_GAUSSIAN);
+        float J[4] = {0.f, 0.f, 0.f, 0.f}, smin, q00 = 0.f, q01 = 0.f, q11 = 0.f;
+        if (gauss) gaussian_quadratic_f32(Ji, (float)P.padval, (float)P.pad_pow, q00, q01, q11, smin);
+        else padded_inverse_f32(Ji, (float)P.padval, (float)P.pad_pow, J, smin);
+        float ratio = ob / smin;
+        if (fabsf(ratio - rintf(ratio)) < 2e-5f * ratio) {
+            // the footprint size is a ceil(): when fp32 cannot decide it, redo that one number in fp64
+            double U[4], V[4], sd[2];
+            svd2x2_dev(Ji, U, sd, V);
+            const double s0 = exp(-log(P.padval + exp(log(sd[0]) * P.pad_pow)) / P.pad_pow);
+            const double s1 = exp(-log(P.padval + exp(log(sd[1]) * P.pad_pow)) / P.pad_pow);
+            ratio = (float)ceil(P.oblur / fmin(s0, s1));
+        }
+        const float rsf = 2.0f * ceilf(ratio);
         long long reg = (rsf < 1.0e9f) ? (long long)rsf : 1000000000LL;
         if (P.max_reg > 0 && reg > P.max_reg) reg = P.max_reg;
         const int half = (int)(reg / 2);
         const float xf_of = (float)(px - fxs), yf_of = (float)(py - fys);
-        const float J0 = J[0] * iob, J1 = J[1] * iob, J2 = J[2] * iob, J3 = J[3] * iob;
         float val = 0.0f, wgt = 0.0f;
         const bool whole = (P.src_x0 == 0 && P.src_y0 == 0 && P.src_w == P.full_w && P.src_h == P.full_h);
         const bool inside = whole && xs - half >= 0 && xs + half < P.full_w &&
                             ys - half >= 0 && ys + half < P.full_h;
+        // a footprint entirely beyond a truncated edge: every tap is skipped, val stays 0 and the
+        // pixel is 0 whatever the weights are (helpers.pyx:1793-1800)
+        const bool all_out = (P.bound_x == TFM_B_TRUNCATE && (xs + half < 0 || xs - half >= P.full_w)) ||
+                             (P.bound_y == TFM_B_TRUNCATE && (ys + half < 0 || ys - half >= P.full_h));
+        if (all_out) { drow[X] = (DstT)0; return; }
         const long long pe = P.src_pitch / (long long)sizeof(SrcT);
-        if (P.filter == TFM_FILT_GAUSSIAN && half <= 24) {
-            // exp(-(xf^2+yf^2)) = exp2(-(A a^2 + 2B ab + C b^2)); along a row of the footprint the
-            // weight obeys w(a+1) = w(a) r(a), r(a+1) = r(a) c: two multiplies per tap, three exp2
-            // per row instead of one exp per tap.
-            const float L2E = 1.4426950408889634f;
-            const float Aq = (J0 * J0 + J2 * J2) * L2E, Bq = (J0 * J1 + J2 * J3) * L2E,
-                        Cq = (J1 * J1 + J3 * J3) * L2E;
-            const float cstep = exp2f(-2.0f * Aq);
-            const float a0 = (float)(-half) + xf_of;
-            for (int yr = -half; yr <= half; ++yr) {
-                const float b = (float)yr + yf_of;
-                float w = exp2f(-((Aq * a0 + 2.0f * Bq * b) * a0 + Cq * b * b));
-                float r = exp2f(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b));
-                if (inside) {
-                    const SrcT *row = reinterpret_cast<const SrcT *>(src_base) + (ys + yr) * pe + (xs - half);
-                    for (int k = 0; k <= 2 * half; ++k) {
-                        val = fmaf((float)__ldg(row + k), w, val);
-                        wgt += w;
-                        w *= r;
-                        r *= cstep;
-                    }
-                } else {
-                    int sty = 0;
-                    const int iy0 = jbound(ys + yr, P.full_h, P.bound_y, sty);
-                    for (int k = 0; k <= 2 * half; ++k) {
-                        int st = sty;
-                        int ix = jbound(xs - half + k, P.full_w, P.bound_x, st);
-                        state |= st & 2;
-                        wgt += w;
-                        if (st == 0) {
-                            ix -= P.src_x0;
-                            const int iy = iy0 - P.src_y0;
-                            if ((unsigned)ix < (unsigned)P.src_w && (unsigned)iy < (unsigned)P.src_h)
-                                val = fmaf((float)__ldg(reinterpret_cast<const SrcT *>(src_base) + iy * pe + ix), w, val);
-                            else
-                                state |= 4;
-                        }
-                        w *= r;
-                        r *= cstep;
-                    }
-                }
+        const float L2E = 1.4426950408889634f;
+        const float Aq = q00 * iob * iob * L2E, Bq = q01 * iob * iob * L2E, Cq = q11 * iob * iob * L2E;
+        const float h2 = (float)half * (float)half + 2.0f * (float)half + 1.0f;
+        const bool recur_ok = gauss && inside && half >= 1 && half <= 6 &&
+                              (Aq + 2.0f * fabsf(Bq) + Cq) * h2 < 100.0f;
+        if (recur_ok) {
+            // exp(-(xf^2+yf^2)) = exp2(-(A a^2 + 2B ab + C b^2)): three exp2 per pixel row set, two
+            // multiplies per tap
+            const float a0 = (float)(-half) + xf_of, b0 = (float)(-half) + yf_of;
+            const float w0 = exp2f(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
+            const float r0 = exp2f(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
+            const float rb = exp2f(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
+            const float cA = exp2f(-2.0f * Aq), cB = exp2f(-2.0f * Bq), cC = exp2f(-2.0f * Cq);
+            const SrcT *p0 = reinterpret_cast<const SrcT *>(src_base) + (ys - half) * pe + (xs - half);
+            switch (half) {
+            case 1: gauss_taps<1, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+            case 2: gauss_taps<2, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+            case 3: gauss_taps<3, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+            case 4: gauss_taps<4, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+            case 5: gauss_taps<5, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+            default: gauss_taps<6, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
             }
         } else {
+            const float J0 = J[0] * iob, J1 = J[1] * iob, J2 = J[2] * iob, J3 = J[3] * iob;
             for (int yr = -half; yr <= half; ++yr) {
                 const float y0 = (float)yr + yf_of;
                 int sty = 0;
                 const int iy0 = jbound(ys + yr, P.full_h, P.bound_y, sty);
                 for (int xr = -half; xr <= half; ++xr) {
                     const float x0 = (float)xr + xf_of;
-                    const float filt = filt_eval<float>(P.filter, fabsf(J0 * x0 + J1 * y0), fabsf(J2 * x0 + J3 * y0));
+                    float filt;
+                    if (gauss) filt = exp2f(-((Aq * x0 + 2.0f * Bq * y0) * x0 + Cq * y0 * y0));
+                    else filt = filt_eval<float>(P.filter, fabsf(J0 * x0 + J1 * y0), fabsf(J2 * x0 + J3 * y0));
                     wgt += filt;
                     int st = sty;
                     int ix = jbound(xs + xr, P.full_w, P.bound_x, st);

@@ -176,11 +176,10 @@ __device__ __forceinline__ void floor_frac_fast(double x, int &i, float &frac)
 {
     const double MAGIC = 6755399441055744.0;
     const double t = x + MAGIC;
-    double r = t - MAGIC;                 // rn(x)
-    i = __double2loint(t);
-    double fr = x - r;                    // in [-0.5, 0.5], exact
-    if (fr < 0.0) { fr += 1.0; i -= 1; }
-    frac = (float)fr;
+    i = __double2loint(t);                // rn(x)
+    float f = (float)(x - (t - MAGIC));   // x - rn(x) in [-0.5, 0.5], exact before the conversion
+    if (f < 0.0f) { f += 1.0f; i -= 1; }  // round-to-nearest -> floor (fp32/ALU pipes, not fp64)
+    frac = f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,12 +241,13 @@ k_resample(const __grid_constant__ ResampleParams P)
 
     if (!GENERIC) {
         int ix[NPX], iy[NPX];
+        bool sane[NPX];
         bool interior = true;
 #pragma unroll
         for (int j = 0; j < NPX; ++j) {
             double x = cx[j], y = cy[j];
             if (METHOD == TFM_NEAREST) { x = __dadd_rn(x, 0.5); y = __dadd_rn(y, 0.5); }   // helpers.pyx:127
-            const bool sane = (fabs(x) < 1.0e9) && (fabs(y) < 1.0e9);     // false for NaN / inf / absurd
+            sane[j] = (fabs(x) < 1.0e9) && (fabs(y) < 1.0e9);             // false for NaN / inf / absurd
             if (FASTI) {
                 floor_frac_fast(x, ix[j], ffx[j]);
                 floor_frac_fast(y, iy[j], ffy[j]);
@@ -258,31 +258,34 @@ k_resample(const __grid_constant__ ResampleParams P)
                 ix[j] = __double2int_rz(fx);
                 iy[j] = __double2int_rz(fy);
             }
-            if (!sane) { ix[j] = -1000000; iy[j] = -1000000; }  // whole footprint out of range -> fill
-            if (!valid[j]) { ix[j] = -T0; iy[j] = -T0; }        // not an output pixel: harmless taps
-            interior = interior && ((unsigned)(ix[j] + T0) < (unsigned)P.int_w) &&
+            interior = interior && valid[j] && sane[j] &&
+                       ((unsigned)(ix[j] + T0) < (unsigned)P.int_w) &&
                        ((unsigned)(iy[j] + T0) < (unsigned)P.int_h);
         }
-        const long long pe = P.src_pitch / (long long)sizeof(SrcT);
+        const int pe = (int)(P.src_pitch / (long long)sizeof(SrcT));       // host guarantees h*pe < 2^31
         if (__all_sync(0xffffffffu, interior)) {
-            // every tap of every pixel of this warp lies inside the image: no predicates
+            // every tap of every pixel of this warp lies inside the image: no predicates, no selects
+            const SrcT *const base = reinterpret_cast<const SrcT *>(src_base);
 #pragma unroll
             for (int j = 0; j < NPX; ++j) {
-                const SrcT *p = reinterpret_cast<const SrcT *>(src_base) + (long long)(iy[j] + T0) * pe + (ix[j] + T0);
+                const SrcT *p = base + ((iy[j] + T0) * pe + (ix[j] + T0));
 #pragma unroll
                 for (int ty = 0; ty < NT; ++ty)
 #pragma unroll
-                    for (int tx = 0; tx < NT; ++tx) v[j][ty][tx] = (RegT)__ldg(p + ty * pe + tx);
+                    for (int tx = 0; tx < NT; ++tx) v[j][ty][tx] = (RegT)__ldg(p + (ty * pe + tx));
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < NPX; ++j)
+            for (int j = 0; j < NPX; ++j) {
+                // NaN / absurd coordinate: whole footprint out of range -> fill (INT64_MIN in the reference)
+                const int bx = sane[j] ? ix[j] : -1000000, by = sane[j] ? iy[j] : -1000000;
 #pragma unroll
                 for (int ty = 0; ty < NT; ++ty)
 #pragma unroll
                     for (int tx = 0; tx < NT; ++tx)
-                        v[j][ty][tx] = valid[j] ? tap_trunc<SrcT, RegT>(P, src_base, ix[j] + T0 + tx, iy[j] + T0 + ty)
+                        v[j][ty][tx] = valid[j] ? tap_trunc<SrcT, RegT>(P, src_base, bx + T0 + tx, by + T0 + ty)
                                                 : (RegT)0;
+            }
         }
     } else {
 #pragma unroll
@@ -473,7 +476,9 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
     P.lw = lw;
 
     const bool subrect = (s.x0 != 0 || s.y0 != 0 || s.full_h != s.h || s.full_w != s.w);
-    const bool generic = subrect || a->bound_x != TFM_B_TRUNCATE || a->bound_y != TFM_B_TRUNCATE;
+    const long long src_elems = s.h * (s.pitch / (s.dtype == TFM_F64 ? 8 : 4));
+    const bool generic = subrect || a->bound_x != TFM_B_TRUNCATE || a->bound_y != TFM_B_TRUNCATE ||
+                         src_elems >= 0x7fffffffLL;      // the fast path indexes taps with 32-bit offsets
     if ((a->bound_x == TFM_B_FORBID || a->bound_y == TFM_B_FORBID || subrect) && !a->status_dev)
         return TFM_EVALUE;
 
