@@ -20,9 +20,9 @@
 
 namespace tfm {
 
-constexpr int JTX = 32, JTY = 16;           // output tile (512 threads)
-constexpr int PW = JTX + 4, PH = JTY + 4;   // coordinate points (halo 2)
-constexpr int CW = JTX + 3, CH = JTY + 3;   // cells (lower-left point index), halo 2 / 1
+constexpr int JTX = 32;                     // output tile width; height JTY is a template parameter
+constexpr int PW = JTX + 4;                 // coordinate points per row (halo 2)
+constexpr int CW = JTX + 3;                 // cells per row (lower-left point index), halo 2 / 1
 
 struct JacParams {
     const void *src;
@@ -284,12 +284,13 @@ __device__ __forceinline__ void gauss_taps(const SrcT *p, long long pe, float w0
 }
 
 // A: chain arithmetic; RegT: footprint arithmetic (double = parity mode, float = fast mode)
-template <class A, typename SrcT, typename DstT, typename RegT>
-__global__ void __launch_bounds__(JTX * JTY)
+template <class A, typename SrcT, typename DstT, typename RegT, int JTY>
+__global__ void __launch_bounds__(JTX * JTY, 1024 / (JTX * JTY))
 k_jacobian(const __grid_constant__ JacParams P)
 {
     constexpr bool FASTI = (sizeof(RegT) == 4);
-    __shared__ double s_px[PH][PW], s_py[PH][PW];     // inverse-mapped coordinates of grid points
+    constexpr int PH = JTY + 4, CH = JTY + 3;
+    __shared__ double2 s_p[PH][PW];                   // inverse-mapped (x,y) of grid points, interleaved
     __shared__ double s_m2[CH][CW];                   // Jmag2 per cell (helpers.pyx:1020)
     __shared__ unsigned char s_flag[CH][CW];          // jump flag per cell (1 = ok)
 
@@ -311,16 +312,15 @@ k_jacobian(const __grid_constant__ JacParams P)
         const long long gx = WX0 + pi, gy = WY0 + pj;
         double x = (double)gx, y = (double)gy;
         if (gx >= 0 && gx < GW && gy >= 0 && gy < GH) chain_eval<A>(P.chain, x, y);
-        s_px[pj][pi] = x;
-        s_py[pj][pi] = y;
+        s_p[pj][pi] = make_double2(x, y);
     }
     __syncthreads();
 
     // ---- 2. Jmag2 per cell: cell (ci,cj) spans points (ci..ci+1, cj..cj+1) ----
     for (int i = tid; i < CW * CH; i += JTX * JTY) {
         const int cj = i / CW, ci = i - cj * CW;
-        const double ax = s_px[cj + 1][ci + 1], bx = s_px[cj + 1][ci], cx = s_px[cj][ci + 1], dx = s_px[cj][ci];
-        const double ay = s_py[cj + 1][ci + 1], by = s_py[cj + 1][ci], cy = s_py[cj][ci + 1], dy = s_py[cj][ci];
+        const double2 pa = s_p[cj + 1][ci + 1], pb = s_p[cj + 1][ci], pc = s_p[cj][ci + 1], pd = s_p[cj][ci];
+        const double ax = pa.x, bx = pb.x, cx = pc.x, dx = pd.x, ay = pa.y, by = pb.y, cy = pc.y, dy = pd.y;
         // helpers.pyx:897-906: ((a-b)+c)-d over 2 and ((a+b)-c)-d over 2
         const double j00 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ax, bx), cx), dx), 0.5);
         const double j10 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ay, by), cy), dy), 0.5);
@@ -395,12 +395,12 @@ k_jacobian(const __grid_constant__ JacParams P)
         // no flagged cell: the four cell Jacobians add up to the Sobel-like stencil
         //   d/dx = (I[y+1][x+1]-I[y+1][x-1] + 2(I[y][x+1]-I[y][x-1]) + I[y-1][x+1]-I[y-1][x-1]) / 8
         // (identical up to fp64 rounding of the regrouped sum)
-        const double *X0 = &s_px[qj - 1][qi - 1], *X1 = &s_px[qj][qi - 1], *X2 = &s_px[qj + 1][qi - 1];
-        const double *Y0r = &s_py[qj - 1][qi - 1], *Y1r = &s_py[qj][qi - 1], *Y2r = &s_py[qj + 1][qi - 1];
-        Ji[0] = 0.125 * ((X2[2] - X2[0]) + 2.0 * (X1[2] - X1[0]) + (X0[2] - X0[0]));
-        Ji[2] = 0.125 * ((Y2r[2] - Y2r[0]) + 2.0 * (Y1r[2] - Y1r[0]) + (Y0r[2] - Y0r[0]));
-        Ji[1] = 0.125 * ((X2[0] - X0[0]) + 2.0 * (X2[1] - X0[1]) + (X2[2] - X0[2]));
-        Ji[3] = 0.125 * ((Y2r[0] - Y0r[0]) + 2.0 * (Y2r[1] - Y0r[1]) + (Y2r[2] - Y0r[2]));
+        const double2 *r0 = &s_p[qj - 1][qi - 1], *r1 = &s_p[qj][qi - 1], *r2 = &s_p[qj + 1][qi - 1];
+        const double2 a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b2 = r1[2], c0 = r2[0], c1 = r2[1], c2 = r2[2];
+        Ji[0] = 0.125 * ((c2.x - c0.x) + 2.0 * (b2.x - b0.x) + (a2.x - a0.x));
+        Ji[2] = 0.125 * ((c2.y - c0.y) + 2.0 * (b2.y - b0.y) + (a2.y - a0.y));
+        Ji[1] = 0.125 * ((c0.x - a0.x) + 2.0 * (c1.x - a1.x) + (c2.x - a2.x));
+        Ji[3] = 0.125 * ((c0.y - a0.y) + 2.0 * (c1.y - a1.y) + (c2.y - a2.y));
     } else {
         int nvalid = 0;
         // helpers.pyx:1227-1231: cells (y-1,x-1) + (y,x-1) + (y-1,x) + (y,x), in that order
@@ -409,8 +409,8 @@ k_jacobian(const __grid_constant__ JacParams P)
             const int ci = qi - 1 + (k >> 1), cj = qj - 1 + (k & 1);
             const bool ok = s_flag[cj][ci] != 0;
             nvalid += ok ? 1 : 0;
-            const double ax = s_px[cj + 1][ci + 1], bx = s_px[cj + 1][ci], cx = s_px[cj][ci + 1], dx = s_px[cj][ci];
-            const double ay = s_py[cj + 1][ci + 1], by = s_py[cj + 1][ci], cy = s_py[cj][ci + 1], dy = s_py[cj][ci];
+            const double2 pa = s_p[cj + 1][ci + 1], pb = s_p[cj + 1][ci], pc = s_p[cj][ci + 1], pd = s_p[cj][ci];
+            const double ax = pa.x, bx = pb.x, cx = pc.x, dx = pd.x, ay = pa.y, by = pb.y, cy = pc.y, dy = pd.y;
             double j00 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ax, bx), cx), dx), 0.5);
             double j10 = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(ay, by), cy), dy), 0.5);
             double j01 = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(ax, bx), cx), dx), 0.5);
@@ -427,8 +427,8 @@ k_jacobian(const __grid_constant__ JacParams P)
         for (int k = 0; k < 4; ++k) Ji[k] = __ddiv_rn(Ji[k], denom);
     }
 
-    const double px = s_px[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
-    const double py = s_py[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
+    const double2 pme = s_p[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
+    const double px = pme.x, py = pme.y;
     DstT *drow = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch);
     if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) { drow[X] = (DstT)0; return; }
     const double fxs = floor(px), fys = floor(py);
@@ -633,26 +633,30 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     P.chain.n = a->n_ops; P.chain.pad = 0;
     for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
 
-    dim3 grid((unsigned)((P.dst_w + JTX - 1) / JTX), (unsigned)((P.dst_h + JTY - 1) / JTY),
+    const int jty = (a->tuning & 8) ? 8 : 16;
+    dim3 grid((unsigned)((P.dst_w + JTX - 1) / JTX), (unsigned)((P.dst_h + jty - 1) / jty),
               (unsigned)P.n_planes);
     if (grid.y > 65535u) return TFM_EUNSUPPORTED;
-    dim3 block(JTX, JTY);
+    dim3 block(JTX, jty);
     const char *name;
+#define TFM_JLAUNCH(AA, ST, DT, RT)                                              \
+    do {                                                                         \
+        if (jty == 8) k_jacobian<AA, ST, DT, RT, 8><<<grid, block, 0, st>>>(P);   \
+        else k_jacobian<AA, ST, DT, RT, 16><<<grid, block, 0, st>>>(P);           \
+    } while (0)
     if (a->precision == TFM_PREC_EXACT64) {
-        if (s.dtype == TFM_F32 && d.dtype == TFM_F64)
-            k_jacobian<Exact, float, double, double><<<grid, block, 0, st>>>(P);
-        else if (s.dtype == TFM_F64 && d.dtype == TFM_F64)
-            k_jacobian<Exact, double, double, double><<<grid, block, 0, st>>>(P);
+        if (s.dtype == TFM_F32 && d.dtype == TFM_F64) TFM_JLAUNCH(Exact, float, double, double);
+        else if (s.dtype == TFM_F64 && d.dtype == TFM_F64) TFM_JLAUNCH(Exact, double, double, double);
         else return TFM_EUNSUPPORTED;
         name = "k_jacobian<exact64>";
     } else if (a->precision == TFM_PREC_FAST32) {
-        if (s.dtype == TFM_F32 && d.dtype == TFM_F32)
-            k_jacobian<Fast, float, float, float><<<grid, block, 0, st>>>(P);
+        if (s.dtype == TFM_F32 && d.dtype == TFM_F32) TFM_JLAUNCH(Fast, float, float, float);
         else return TFM_EUNSUPPORTED;
         name = "k_jacobian<fast32>";
     } else {
         return TFM_EVALUE;
     }
+#undef TFM_JLAUNCH
     count_launch();
     set_last_kernel(name);
     return cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;

@@ -35,6 +35,7 @@ struct ResampleParams {
     int n_planes;
     int int_w, int_h;                        // #columns / #rows at which a whole NT x NT footprint fits
     double aff[6];                           // pre-composed affine map a00 a01 a10 a11 b0 b1 (AFF kernels)
+    int aff_bounded;                         // host proved |coordinate| < 2^30 over the whole output grid
     double fill;
     int *status;
     ChainDev chain;
@@ -182,139 +183,18 @@ __device__ __forceinline__ void floor_frac_fast(double x, int &i, float &frac)
     frac = f;
 }
 
-// ---------------------------------------------------------------------------------------------
-// the kernel
-// ---------------------------------------------------------------------------------------------
-// METHOD   tfm_method
-// SrcT     source element type; DstT output element type
-// A        chain arithmetic policy (Exact / Fast)
-// RegT     arithmetic type of the interpolation (double in exact mode, float in fast mode)
-// GENERIC  false: both axes 'truncate', source is the whole image (fast path);
-//          true : per-axis runtime boundary modes and/or staged source sub-rectangle
-// AFF      the whole chain was pre-composed by the host into one affine map P.aff (fast mode only)
-template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC, bool AFF>
-__global__ void __launch_bounds__(256)
-k_resample(const __grid_constant__ ResampleParams P)
+// phase 3: weights, reduction, store.  CHECK = false: every pixel of the warp is a valid output
+// pixel (decided by the warp vote), so the stores are unconditional.
+template <int METHOD, typename SrcT, typename DstT, typename RegT, int NPX, int NT, bool CHECK>
+__device__ __forceinline__ void finish(const ResampleParams &P, RegT (&v)[NPX][NT][NT],
+                                       const double (&fracx)[NPX], const double (&fracy)[NPX],
+                                       const float (&ffx)[NPX], const float (&ffy)[NPX],
+                                       const bool (&valid)[NPX], char *dst_base, int X, int Y0)
 {
-    constexpr int NPX = MethodTraits<METHOD>::NPX;
-    constexpr int NT = MethodTraits<METHOD>::NT;
-    constexpr int T0 = (METHOD == TFM_CUBIC) ? -1 : 0;          // first tap offset
-    constexpr bool FASTI = (sizeof(RegT) == 4);                 // fp32 interpolation arithmetic
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lw = P.lw, ww = 1 << lw;
-    const char *const src_base = static_cast<const char *>(P.src) + (long long)blockIdx.z * P.src_plane;
-    char *const dst_base = static_cast<char *>(P.dst) + (long long)blockIdx.z * P.dst_plane;
-    const int px = ((warp & ((32 >> lw) - 1)) << lw) + (lane & (ww - 1));
-    const int py = ((warp >> (5 - lw)) << (5 - lw)) + (lane >> lw);
-    const int X = blockIdx.x * 32 + px;
-    const int Y0 = blockIdx.y * (8 * NPX) + py;
-    const bool xin = X < P.dst_w;
-
-    // ---- phase 1: coordinates (fp64, in registers) ----
-    double cx[NPX], cy[NPX];
-    if (AFF) {
-        const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y0);
-        const double bx = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
-        const double by = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
-#pragma unroll
-        for (int j = 0; j < NPX; ++j) {
-            cx[j] = fma((double)(8 * j), P.aff[1], bx);
-            cy[j] = fma((double)(8 * j), P.aff[3], by);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < NPX; ++j) {
-            cx[j] = (double)(P.dst_x0 + X);
-            cy[j] = (double)(P.dst_y0 + Y0 + 8 * j);
-        }
-        chain_eval_n<A, NPX>(P.chain, cx, cy);
-    }
-
-    // ---- phase 2: taps (all loads of the NPX pixels issued before any is consumed) ----
-    RegT v[NPX][NT][NT];
-    double fracx[NPX], fracy[NPX];          // exact mode
-    float ffx[NPX], ffy[NPX];               // fast mode
-    bool valid[NPX];
-#pragma unroll
-    for (int j = 0; j < NPX; ++j) valid[j] = xin && (Y0 + 8 * j < P.dst_h);
-
-    if (!GENERIC) {
-        int ix[NPX], iy[NPX];
-        bool sane[NPX];
-        bool interior = true;
-#pragma unroll
-        for (int j = 0; j < NPX; ++j) {
-            double x = cx[j], y = cy[j];
-            if (METHOD == TFM_NEAREST) { x = __dadd_rn(x, 0.5); y = __dadd_rn(y, 0.5); }   // helpers.pyx:127
-            sane[j] = (fabs(x) < 1.0e9) && (fabs(y) < 1.0e9);             // false for NaN / inf / absurd
-            if (FASTI) {
-                floor_frac_fast(x, ix[j], ffx[j]);
-                floor_frac_fast(y, iy[j], ffy[j]);
-            } else {
-                const double fx = floor(x), fy = floor(y);
-                fracx[j] = __dsub_rn(x, fx);                    // alpha = index - floor(index)
-                fracy[j] = __dsub_rn(y, fy);
-                ix[j] = __double2int_rz(fx);
-                iy[j] = __double2int_rz(fy);
-            }
-            interior = interior && valid[j] && sane[j] &&
-                       ((unsigned)(ix[j] + T0) < (unsigned)P.int_w) &&
-                       ((unsigned)(iy[j] + T0) < (unsigned)P.int_h);
-        }
-        const int pe = (int)(P.src_pitch / (long long)sizeof(SrcT));       // host guarantees h*pe < 2^31
-        if (__all_sync(0xffffffffu, interior)) {
-            // every tap of every pixel of this warp lies inside the image: no predicates, no selects
-            const SrcT *const base = reinterpret_cast<const SrcT *>(src_base);
-#pragma unroll
-            for (int j = 0; j < NPX; ++j) {
-                const SrcT *p = base + ((iy[j] + T0) * pe + (ix[j] + T0));
-#pragma unroll
-                for (int ty = 0; ty < NT; ++ty)
-#pragma unroll
-                    for (int tx = 0; tx < NT; ++tx) v[j][ty][tx] = (RegT)__ldg(p + (ty * pe + tx));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NPX; ++j) {
-                // NaN / absurd coordinate: whole footprint out of range -> fill (INT64_MIN in the reference)
-                const int bx = sane[j] ? ix[j] : -1000000, by = sane[j] ? iy[j] : -1000000;
-#pragma unroll
-                for (int ty = 0; ty < NT; ++ty)
-#pragma unroll
-                    for (int tx = 0; tx < NT; ++tx)
-                        v[j][ty][tx] = valid[j] ? tap_trunc<SrcT, RegT>(P, src_base, bx + T0 + tx, by + T0 + ty)
-                                                : (RegT)0;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < NPX; ++j) {
-            double x = cx[j], y = cy[j];
-            if (METHOD == TFM_NEAREST) { x = __dadd_rn(x, 0.5); y = __dadd_rn(y, 0.5); }
-            const double fx = floor(x), fy = floor(y);
-            fracx[j] = __dsub_rn(x, fx);
-            fracy[j] = __dsub_rn(y, fy);
-            ffx[j] = (float)fracx[j];
-            ffy[j] = (float)fracy[j];
-            // |f| >= 2^51 (or NaN): the reference's float tap offsets are absorbed / invalid; every
-            // tap shares the base index (see DESIGN.md, "absurd coordinates").
-            const bool okx = fabs(fx) < 2.0e15, oky = fabs(fy) < 2.0e15;
-            const long long bx = cast_i64(fx), by = cast_i64(fy);
-#pragma unroll
-            for (int ty = 0; ty < NT; ++ty)
-#pragma unroll
-                for (int tx = 0; tx < NT; ++tx)
-                    v[j][ty][tx] = valid[j] ? tap_generic<SrcT, RegT>(P, src_base, okx ? bx + T0 + tx : bx,
-                                                                      oky ? by + T0 + ty : by)
-                                            : (RegT)0;
-        }
-    }
-
-    // ---- phase 3: weights, reduction, store ----
+    constexpr bool FASTI = (sizeof(RegT) == 4);
 #pragma unroll
     for (int j = 0; j < NPX; ++j) {
-        if (!valid[j]) continue;
+        if (CHECK && !valid[j]) continue;
         const int Y = Y0 + 8 * j;
         RegT r;
         if (METHOD == TFM_NEAREST) {
@@ -362,6 +242,175 @@ k_resample(const __grid_constant__ ResampleParams P)
         DstT *row = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch);
         row[X] = (DstT)r;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+// METHOD   tfm_method
+// SrcT     source element type; DstT output element type
+// A        chain arithmetic policy (Exact / Fast)
+// RegT     arithmetic type of the interpolation (double in exact mode, float in fast mode)
+// GENERIC  false: both axes 'truncate', source is the whole image (fast path);
+//          true : per-axis runtime boundary modes and/or staged source sub-rectangle
+// AFF      the whole chain was pre-composed by the host into one affine map P.aff (fast mode only)
+template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC, bool AFF>
+__global__ void __launch_bounds__(256)
+k_resample(const __grid_constant__ ResampleParams P)
+{
+    constexpr int NPX = MethodTraits<METHOD>::NPX;
+    constexpr int NT = MethodTraits<METHOD>::NT;
+    constexpr int T0 = (METHOD == TFM_CUBIC) ? -1 : 0;          // first tap offset
+    constexpr bool FASTI = (sizeof(RegT) == 4);                 // fp32 interpolation arithmetic
+
+    // a warp covers a 16 x 2 patch of the tile (compile-time shape: measured within 8% of the best
+    // of 32x1 / 16x2 / 8x4 on rotated maps, and no worse on axis-aligned ones)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const char *const src_base = static_cast<const char *>(P.src) + (long long)blockIdx.z * P.src_plane;
+    char *const dst_base = static_cast<char *>(P.dst) + (long long)blockIdx.z * P.dst_plane;
+    const int px = ((warp & 1) << 4) + (lane & 15);
+    const int py = ((warp >> 1) << 1) + (lane >> 4);
+    const int X = blockIdx.x * 32 + px;
+    const int Y0 = blockIdx.y * (8 * NPX) + py;
+    const bool xin = X < P.dst_w;
+
+    // ---- phase 1: coordinates (fp64, in registers) ----
+    double cx[NPX], cy[NPX];
+    if (AFF) {
+        const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y0);
+        const double bx = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
+        const double by = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            cx[j] = fma((double)(8 * j), P.aff[1], bx);
+            cy[j] = fma((double)(8 * j), P.aff[3], by);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            cx[j] = (double)(P.dst_x0 + X);
+            cy[j] = (double)(P.dst_y0 + Y0 + 8 * j);
+        }
+        chain_eval_n<A, NPX>(P.chain, cx, cy);
+    }
+
+    // ---- phase 2: taps (all loads of the NPX pixels issued before any is consumed) ----
+    RegT v[NPX][NT][NT];
+    double fracx[NPX], fracy[NPX];          // exact mode
+    float ffx[NPX], ffy[NPX];               // fast mode
+    bool valid[NPX];
+
+    if (!GENERIC) {
+        int ix[NPX], iy[NPX];
+        bool sane[NPX];
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            double x = cx[j], y = cy[j];
+            if (METHOD == TFM_NEAREST) { x = __dadd_rn(x, 0.5); y = __dadd_rn(y, 0.5); }   // helpers.pyx:127
+            if (FASTI) {
+                floor_frac_fast(x, ix[j], ffx[j]);
+                floor_frac_fast(y, iy[j], ffy[j]);
+            } else {
+                const double fx = floor(x), fy = floor(y);
+                fracx[j] = __dsub_rn(x, fx);                    // alpha = index - floor(index)
+                fracy[j] = __dsub_rn(y, fy);
+                ix[j] = __double2int_rz(fx);
+                iy[j] = __double2int_rz(fy);
+            }
+            // false for NaN / inf / absurd.  For host-composed affine maps the host has bounded
+            // |coordinate| over the whole output grid (P.aff_bounded): nothing to test per pixel.
+            if (AFF) sane[j] = true;
+            else sane[j] = (fabs(x) < 1.0e9) && (fabs(y) < 1.0e9);
+        }
+        const int pe = (int)(P.src_pitch / (long long)sizeof(SrcT));       // host guarantees h*pe < 2^31
+        // CTA-uniform: the whole 32 x (8*NPX) tile lies inside the output and (AFF) coordinates are
+        // known to be sane -> the per-warp classification below needs range compares only.
+        const bool tile_ok = (blockIdx.x * 32 + 32 <= P.dst_w) && (blockIdx.y * (8 * NPX) + 8 * NPX <= P.dst_h) &&
+                             (!AFF || P.aff_bounded);
+        if (tile_ok) {
+            bool interior = true;
+#pragma unroll
+            for (int j = 0; j < NPX; ++j)
+                interior = interior && sane[j] && ((unsigned)(ix[j] + T0) < (unsigned)P.int_w) &&
+                           ((unsigned)(iy[j] + T0) < (unsigned)P.int_h);
+            if (__all_sync(0xffffffffu, interior)) {
+                // every tap of every pixel of this warp lies inside the image: no predicates
+                const SrcT *const base = reinterpret_cast<const SrcT *>(src_base);
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) {
+                    const int o = (iy[j] + T0) * pe + (ix[j] + T0);
+#pragma unroll
+                    for (int ty = 0; ty < NT; ++ty) {
+                        const SrcT *p = base + (o + ty * pe);
+#pragma unroll
+                        for (int tx = 0; tx < NT; ++tx) v[j][ty][tx] = (RegT)__ldg(p + tx);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) valid[j] = true;
+                finish<METHOD, SrcT, DstT, RegT, NPX, NT, false>(P, v, fracx, fracy, ffx, ffy, valid, dst_base, X, Y0);
+                return;
+            }
+            // whole footprint of every pixel outside the image: the result is the fill value
+            bool outside = true;
+#pragma unroll
+            for (int j = 0; j < NPX; ++j)
+                outside = outside && (!sane[j] ||
+                                      (unsigned)(ix[j] + T0 + NT - 1) >= (unsigned)(P.src_w + NT - 1) ||
+                                      (unsigned)(iy[j] + T0 + NT - 1) >= (unsigned)(P.src_h + NT - 1));
+            if (__all_sync(0xffffffffu, outside)) {
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) {
+                    valid[j] = true;
+#pragma unroll
+                    for (int ty = 0; ty < NT; ++ty)
+#pragma unroll
+                        for (int tx = 0; tx < NT; ++tx) v[j][ty][tx] = (RegT)P.fill;
+                }
+                finish<METHOD, SrcT, DstT, RegT, NPX, NT, false>(P, v, fracx, fracy, ffx, ffy, valid, dst_base, X, Y0);
+                return;
+            }
+        }
+        // mixed warp or ragged tile: per-tap predicates
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            valid[j] = xin && (Y0 + 8 * j < P.dst_h);
+            const bool ok = sane[j] && (!AFF || P.aff_bounded || ((fabs(cx[j]) < 1.0e9) && (fabs(cy[j]) < 1.0e9)));
+            // NaN / absurd coordinate: whole footprint out of range -> fill (INT64_MIN in the reference)
+            const int bx = ok ? ix[j] : -1000000, by = ok ? iy[j] : -1000000;
+#pragma unroll
+            for (int ty = 0; ty < NT; ++ty)
+#pragma unroll
+                for (int tx = 0; tx < NT; ++tx)
+                    v[j][ty][tx] = valid[j] ? tap_trunc<SrcT, RegT>(P, src_base, bx + T0 + tx, by + T0 + ty)
+                                            : (RegT)0;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            valid[j] = xin && (Y0 + 8 * j < P.dst_h);
+            double x = cx[j], y = cy[j];
+            if (METHOD == TFM_NEAREST) { x = __dadd_rn(x, 0.5); y = __dadd_rn(y, 0.5); }
+            const double fx = floor(x), fy = floor(y);
+            fracx[j] = __dsub_rn(x, fx);
+            fracy[j] = __dsub_rn(y, fy);
+            ffx[j] = (float)fracx[j];
+            ffy[j] = (float)fracy[j];
+            // |f| >= 2^51 (or NaN): the reference's float tap offsets are absorbed / invalid; every
+            // tap shares the base index (see DESIGN.md, "absurd coordinates").
+            const bool okx = fabs(fx) < 2.0e15, oky = fabs(fy) < 2.0e15;
+            const long long bx = cast_i64(fx), by = cast_i64(fy);
+#pragma unroll
+            for (int ty = 0; ty < NT; ++ty)
+#pragma unroll
+                for (int tx = 0; tx < NT; ++tx)
+                    v[j][ty][tx] = valid[j] ? tap_generic<SrcT, RegT>(P, src_base, okx ? bx + T0 + tx : bx,
+                                                                      oky ? by + T0 + ty : by)
+                                            : (RegT)0;
+        }
+    }
+
+    finish<METHOD, SrcT, DstT, RegT, NPX, NT, true>(P, v, fracx, fracy, ffx, ffy, valid, dst_base, X, Y0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -487,6 +536,13 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
     cudaError_t e;
     const bool exact = (a->precision == TFM_PREC_EXACT64);
     const bool aff = !exact && !(a->tuning & 4) && compose_affine(a->chain, a->n_ops, P.aff);
+    P.aff_bounded = 0;
+    if (aff) {
+        const double xm = fabs((double)d.x0) + (double)d.w, ym = fabs((double)d.y0) + (double)d.h;
+        const double bx = fabs(P.aff[0]) * xm + fabs(P.aff[1]) * ym + fabs(P.aff[4]) + 1.0;
+        const double by = fabs(P.aff[2]) * xm + fabs(P.aff[3]) * ym + fabs(P.aff[5]) + 1.0;
+        P.aff_bounded = (bx < 1.0e9 && by < 1.0e9) ? 1 : 0;      // NaN parameters compare false
+    }
     if (exact) {
         if (s.dtype == TFM_F32 && d.dtype == TFM_F64)
             e = launch1<float, double, Exact, double>(a->method, P, generic, false, st, &name);
