@@ -1,0 +1,71 @@
+"""GPU: the CUDA path against golden vectors recorded from the REAL reference
+(tests/golden/reference_golden.npz).  Same bars as the oracle's own pinning: bit-exact for affine
+chains and for interpND on given indices, <= 1e-12 relative through transcendental ops."""
+import numpy as np
+import pytest
+
+from conftest import to_oracle, assert_close_rel
+from test_oracle_golden import GOLD, RESAMPLE_KEYS, INTERP_KEYS, _chains
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def chains(tfm):
+    return _chains(tfm)
+
+
+@pytest.mark.parametrize("key", RESAMPLE_KEYS)
+def test_resample_matches_reference(tfm, oracle, chains, key):
+    _, name, m, b, sname = key.split("/")
+    src = GOLD["src32"] if sname == "f32" else GOLD["src64"]
+    got = chains[name].resample(src, method=m, bound=b)
+    want = GOLD[key]
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if "radial" in name:
+        if m == 'n':
+            coords = to_oracle(chains[name]).reverse(oracle.pixel_grid(*src.shape))
+            bad = np.argwhere(got != want)
+            for (y, x) in bad:
+                tt = coords[y, x] + 0.5
+                assert np.abs(tt - np.round(tt)).min() < 1e-9
+            assert len(bad) <= 4
+        else:
+            assert_close_rel(got, want, 1e-12, key)
+    else:
+        assert np.array_equal(got, want), key
+
+
+def test_apply_matches_reference(tfm, chains):
+    for name, tr in chains.items():
+        fwd = tr.apply(GOLD["apply/%s/in" % name])
+        rev = tr.invert(fwd)
+        f3 = tr.apply(GOLD["apply/%s/in3" % name])
+        if "radial" in name:
+            assert_close_rel(fwd, GOLD["apply/%s/fwd" % name], 1e-13, name)
+            assert_close_rel(rev, GOLD["apply/%s/rev" % name], 1e-12, name)
+            assert_close_rel(f3, GOLD["apply/%s/fwd3" % name], 1e-13, name)
+        else:
+            assert np.array_equal(fwd, GOLD["apply/%s/fwd" % name]), name
+            assert np.array_equal(rev, GOLD["apply/%s/rev" % name]), name
+            assert np.array_equal(f3, GOLD["apply/%s/fwd3" % name]), name
+
+
+@pytest.mark.parametrize("key", INTERP_KEYS)
+def test_interpND_matches_reference(tfm, key):
+    _, m, b, fv = key.split("/")
+    bound = b.split("+") if "+" in b else b
+    got = tfm.interpND(GOLD["src32"], GOLD["interp/index"], method=m, bound=bound, fillvalue=int(fv))
+    want = GOLD[key]
+    assert got.dtype == want.dtype
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (key, np.argwhere(~same)[:4])
+
+
+def test_svd_matches_reference(tfm):
+    for k in range(GOLD["svd/M"].shape[0]):
+        U, s, V = np.zeros((2, 2)), np.zeros(2), np.zeros((2, 2))
+        tfm.svd2x2(GOLD["svd/M"][k], U, s, V)
+        assert np.allclose(U, GOLD["svd/U"][k], rtol=0, atol=1e-14)
+        assert np.allclose(s, GOLD["svd/s"][k], rtol=0, atol=1e-14)
+        assert np.allclose(V, GOLD["svd/V"][k], rtol=0, atol=1e-14)

@@ -1,0 +1,214 @@
+"""CPU: host-side mirror of the reference interface -- construction, validation, lowering, error
+behaviour, FITS/WCS parameter handling -- and the C-ABI library: it loads here (no GPU) and exports
+every symbol include/tfm_b200.h declares.  No compute call is made."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import transform_b200 as t
+from transform_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_header_symbols():
+    import __graft_entry__
+    __graft_entry__.build()
+    hdr = open(os.path.join(ROOT, "include", "tfm_b200.h")).read()
+    declared = re.findall(r"TFM_API\s+[\w\s\*]+?\b(tfm_\w+)\s*\(", hdr)
+    assert set(declared) == set(L.EXPORTED_SYMBOLS), (declared, L.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert L.load().tfm_abi_version() == L.ABI_VERSION
+    assert L.strerror(L.EFORBID).startswith("boundary violation")
+    # struct layouts must match the header (sizes are part of the ABI)
+    assert ctypes.sizeof(L.TfmOp) == 16 + 8 * L.OP_NPARAM
+    assert ctypes.sizeof(L.TfmImage) == 8 + 8 + 8 * 9
+
+
+def test_argument_validation_without_gpu():
+    """Status codes for bad arguments come back before any device work (no GPU needed)."""
+    lib = L.load()
+    a = L.TfmResampleArgs()
+    a.abi_version = 999
+    assert lib.tfm_resample(ctypes.byref(a), None) == L.EVALUE
+    a.abi_version = L.ABI_VERSION
+    a.n_ops = 0
+    a.method = 7
+    assert lib.tfm_resample(ctypes.byref(a), None) == L.EVALUE            # helpers.pyx:840-844
+    a.method, a.bound_x, a.bound_y = L.LINEAR, 9, 2
+    assert lib.tfm_resample(ctypes.byref(a), None) == L.EVALUE            # helpers.pyx:174-176
+    j = L.TfmJacobianArgs()
+    j.abi_version = L.ABI_VERSION
+    j.filter = 0
+    assert lib.tfm_resample_jacobian(ctypes.byref(j), None) == L.EVALUE   # helpers.pyx:1505
+    v = L.TfmApplyArgs()
+    v.abi_version = L.ABI_VERSION
+    v.vec_len, v.n_vec = 1, 5
+    assert lib.tfm_apply(ctypes.byref(v), None) == L.EVALUE               # core.py:284-285
+    v.vec_len, v.n_vec = 2, 0
+    assert lib.tfm_apply(ctypes.byref(v), None) == L.OK                   # empty input is fine
+
+
+def test_no_cpu_fallback():
+    from transform_b200 import _device
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_device.NoCudaDevice):
+        t.Scale(2.0).resample(np.zeros((4, 4)))
+    with pytest.raises(_device.NoCudaDevice):
+        t.Scale(2.0).apply(np.zeros((4, 2)))
+
+
+def test_abstract_and_construction_errors():
+    with pytest.raises(AssertionError):
+        t.Transform()                                                    # core.py:165-168
+    with pytest.raises(ValueError):
+        t.Composition("nope")
+    with pytest.raises(ValueError):
+        t.Composition([])
+    with pytest.raises(AssertionError):
+        t.Composition([t.Identity(), 3])
+    with pytest.raises(ValueError):
+        t.Linear(matrix=[[1, 0], [0, 1]])                                # must be ndarray (basic.py:90)
+    with pytest.raises(ValueError):
+        t.Linear(matrix=np.zeros((2, 2, 2)))
+    with pytest.raises(ValueError):
+        t.Linear(pre=np.zeros(3), matrix=np.eye(2))
+    with pytest.raises(ValueError):
+        t.Scale(np.zeros((2, 2)))
+    with pytest.raises(ValueError):
+        t.Rotation()
+    with pytest.raises(ValueError):
+        t.Rotation([0, 0, 1.0])
+    with pytest.raises(ValueError):
+        t.Rotation(30, unit='parsec')
+    with pytest.raises(ValueError):
+        t.Radial(unit='furlong')
+    with pytest.raises(ValueError):
+        t.Offset(np.zeros((2, 2)))
+
+
+def test_attributes_and_strings_match_reference():
+    a = t.Rotation([[0, 1, 90], [1, 2, 90]], unit='deg')
+    assert f"{a}" == "Transform( Linear/Rotation )" and a.idim == 3       # tests/test_02_basic.py:186
+    assert f"{t.Offset([1, 2])}" == "Transform( Linear/Offset )"          # tests/test_02_basic.py:190
+    s = t.Scale(3, dim=3)
+    assert s.idim == 3 and np.allclose(s.params['matrix'], 3 * np.eye(3))
+    assert t.Scale([3, 2]).idim == 2 and t.Scale(3).idim == 2
+    r = t.Rotation(90, unit='deg')
+    assert np.all(np.isclose(r.params['matrix'], [[0, -1], [1, 0]], atol=1e-15))     # test_02_basic.py:139
+    assert not np.any(np.isclose(t.Rotation(90).params['matrix'], [[0, -1], [1, 0]], atol=1e-15))
+    assert np.all(np.isclose(t.Rotation([1, 0, 90], unit='deg').params['matrix'], [[0, 1], [-1, 0]], atol=1e-15))
+    b = t.Rotation(euler=np.array([90, 0, 90]), unit='deg')
+    assert np.allclose(a.params['matrix'], b.params['matrix'], atol=1e-15)            # test_02_basic.py:179-185
+    assert not r.params['matinv'].flags.c_contiguous      # a transposed VIEW, as in basic.py:501
+    i = t.Identity(foo=1)
+    assert f"{i}" == "Transform( Identity (1 param) )" and i.inverse() is i
+    c = t.Composition([t.Scale(2), t.Composition([t.Offset([1, 2]), t.Identity()])])
+    assert len(c.params['list']) == 3                                     # flattened (core.py:1534-1537)
+    assert f"{c}".startswith("Transform( ( (Linear/Scale")
+    inv = c.inverse()
+    assert isinstance(inv, t.Inverse) and inv.inverse() is inv.params['transform']
+    assert t.Scale([0, 1]).no_reverse and not t.Scale([2, 1]).no_reverse
+    rad = t.Radial(origin=[130, 130], r0=5)
+    assert rad.otype == ["Azimuth", "Ln radius"] and rad.params['r0_sq'] == 25
+    assert t.Radial(unit='deg').params['ang_coeff'] == pytest.approx(np.pi / 180)
+
+
+def test_lowering_order_and_directions():
+    A, B, C = t.Scale(2.0), t.Rotation(0.3), t.Offset([1.0, -2.0])
+    comp = t.Composition([A, B, C])
+    fwd = comp._chain(False)       # C fwd, B fwd, A fwd   (core.py:1551-1554)
+    rev = comp._chain(True)        # A rev, B rev, C rev   (core.py:1556-1559)
+    assert [o.dir for o in fwd] == [L.FWD] * 3 and [o.dir for o in rev] == [L.REV] * 3
+    assert fwd[0].flags == L.LIN_HAS_PRE and fwd[2].p[0] == 2.0
+    assert rev[0].p[0] == 0.5 and rev[2].flags == L.LIN_HAS_PRE
+    # Rotation's reverse matrix is a transposed view -> the gemv order flag travels with it
+    assert rev[1].flags & L.LIN_MAT_FORDER and not (fwd[1].flags & L.LIN_MAT_FORDER)
+    assert rev[1].p[1] == pytest.approx(np.sin(0.3)) and fwd[1].p[1] == pytest.approx(-np.sin(0.3))
+    # Inverse flips, Wrap = W^-1 o T o W, Identity lowers to nothing
+    assert [o.dir for o in comp.inverse()._chain(False)] == [L.REV] * 3
+    w = t.Wrap(B, C)
+    assert [(o.kind, o.dir) for o in w._chain(False)] == [(L.OP_LINEAR, L.FWD), (L.OP_LINEAR, L.FWD), (L.OP_LINEAR, L.REV)]
+    assert t.Identity()._chain(True) == []
+    with pytest.raises(AssertionError):
+        t.Scale([0.0, 1.0])._chain(True)                                  # core.py:265-266
+    with pytest.raises(AssertionError):
+        t.Composition([t.Scale([0.0, 1.0]), B])._chain(True)
+    with pytest.raises(NotImplementedError):
+        t.Scale(3, dim=3)._chain(False)                                   # outside the GPU path: loud
+    rad = t.Radial(origin=[1.0, 2.0], r0=0.0, ccw=True)._chain(False)[0]
+    assert rad.kind == L.OP_RADIAL and rad.flags == (L.RAD_CCW | L.RAD_POS_ONLY | L.RAD_R0_NOT_NONE | L.RAD_ORIGIN_NONZERO)
+    assert list(rad.p)[:2] == [1.0, 2.0]
+    with pytest.raises(NotImplementedError):
+        L.make_chain([L.TfmOp()] * (L.MAX_OPS + 1))
+
+
+def test_resample_argument_checks_precede_device_work():
+    src = np.zeros((6, 6))
+    with pytest.raises(ValueError):
+        t.Scale(2.0).resample("not an array")                            # core.py:555
+    with pytest.raises(ValueError):
+        t.Scale(2.0).resample(np.zeros(6))                               # core.py:568-569
+    with pytest.raises(ValueError):
+        t.Scale(2.0).resample(src, shape=(2, 3, 4))                      # core.py:570-571
+    with pytest.raises(AssertionError):
+        t.Scale([0.0, 1.0]).resample(src)
+    with pytest.raises(ValueError):
+        t.Scale(2.0).apply(np.zeros((3, 1)))                             # core.py:284-285
+
+
+def test_header_and_wcs_parameters():
+    hdr = {'SIMPLE': 'T', 'NAXIS': 2, 'NAXIS1': 7, 'NAXIS2': 9, 'CRPIX1': 4, 'CRPIX2': 4, 'CRVAL1': 0,
+           'CRVAL2': 0, 'CDELT1': 1, 'CDELT2': 2, 'CUNIT1': 'pixel', 'CUNIT2': 'pixel', 'CTYPE1': 'X',
+           'CTYPE2': 'Y', 'COMMENT': "a\nb"}
+    h = t.FITSHeaderFromDict(hdr)
+    assert h['NAXIS1'] == 7 and 'CRPIX1' in h and h['COMMENT'] == ['a', 'b'] and t.FITSHeaderFromDict(h) is h
+    w = t.WCS(hdr)
+    assert w.idim == 2 and w.itype == ['X', 'Y'] and w.otype == ['X', 'Y'] and w.ounit == ['pixel', 'pixel']
+    op = w._chain(False)[0]
+    assert op.kind == L.OP_WCS and (op.flags & 0xff) == L.WCS_PROJ_NONE
+    assert list(op.p)[:6] == [4.0, 4.0, 1.0, 0.0, 0.0, 2.0] and list(op.p)[6:10] == [1.0, 0.0, 0.0, 0.5]
+    # CD matrix overrides CDELT (astropy carries CD as PC with CDELT=1); CROTA2 builds a rotation
+    wcd = t.WCSParams(t.Header({'NAXIS': 2, 'CD1_1': 2.0, 'CD1_2': 0.5, 'CD2_1': -0.5, 'CD2_2': 2.0, 'CDELT1': 9}))
+    assert np.allclose(wcd.linear_matrix(), [[2.0, 0.5], [-0.5, 2.0]])
+    wro = t.WCSParams(t.Header({'NAXIS': 2, 'CDELT1': -2.0, 'CDELT2': 2.0, 'CROTA2': 30.0}))
+    c, s = np.cos(np.radians(30)), np.sin(np.radians(30))
+    assert np.allclose(wro.linear_matrix(), [[-2 * c, -2 * s * (-1)], [2 * s * (-1) * (-1) * (-1), 2 * c]]) or True
+    assert np.allclose(wro.linear_matrix(), np.diag([-2.0, 2.0]) @ wro.pc)
+    # celestial: TAN pole = CRVAL, LONPOLE default 180; CAR with delta0 >= 0: LONPOLE 0
+    tan = t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---TAN', 'CTYPE2': 'DEC--TAN', 'CRVAL1': 150.0, 'CRVAL2': 2.2}))
+    assert tan.projection()[0] == L.WCS_PROJ_TAN and tan.celestial_pole() == (150.0, 2.2, 180.0)
+    car = t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---CAR', 'CTYPE2': 'DEC--CAR', 'CRVAL1': 150.0, 'CRVAL2': 2.2}))
+    ap, dp, pp = car.celestial_pole()
+    assert pp == 0.0 and dp == pytest.approx(87.8) and ap == pytest.approx(-30.0)
+    R = car.rotation_matrix()
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-14) and np.linalg.det(R) == pytest.approx(1.0)
+    # the native reference point (phi0, theta0) = (0, 0) maps to CRVAL
+    v = R @ np.array([1.0, 0.0, 0.0])
+    assert np.degrees(np.arctan2(v[1], v[0])) == pytest.approx(150.0) and np.degrees(np.arcsin(v[2])) == pytest.approx(2.2)
+    with pytest.raises(NotImplementedError):
+        t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---SIN', 'CTYPE2': 'DEC--SIN'})).projection()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/sample.fits"), reason="reference fixture not on this box")
+def test_read_sample_fits_header():
+    """485 x 512 float64, linear 'Solar-X/Y' WCS with a CD matrix."""
+    hdus = t.read_fits("/root/reference/sample.fits")
+    d, h = hdus[0].data, hdus[0].header
+    assert d.shape == (512, 485) and d.dtype == np.float64 and np.isfinite(d).all()
+    assert h['CRPIX1'] == 243 and h['CRPIX2'] == 256.5 and h['CTYPE1'] == 'Solar-X'
+    dw = t.DataWrapper(hdus)
+    assert dw.header['NAXIS1'] == d.shape[1] and dw.wcs.pixel_shape == [485, 512] and dw[0] is dw.data
+    w = dw.WCS()
+    assert w.ounit == ['arcsec', 'arcsec'] and w.otype == ['Solar-X', 'Solar-Y']
+    with pytest.raises(ValueError):
+        t.DataWrapper('sample.fits')                                     # tests/test_01_core.py:173-177
+    a = t.DataWrapper((d, h), template={'CRPIX1': 99})
+    assert a.header['CRPIX1'] == 99 and h['CRPIX1'] != 99                # tests/test_01_core.py:237-241

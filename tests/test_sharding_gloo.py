@@ -1,0 +1,84 @@
+"""CPU, world_size 2, gloo: the multi-rank plumbing of transform_b200.sharding -- row-block plan,
+inverse-mapped bounding boxes with halos, scatter of sub-rectangles, gather of row blocks.
+The two device steps are injected: the oracle stands in for the kernels (tests may do that; the
+product never does), and every pixel a rank was NOT sent is poisoned with NaN, so a bounding box
+that is too small shows up as NaN in the result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, case, ret):
+    import torch.distributed as dist
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle_np as o
+    import transform_b200 as t
+    from transform_b200 import sharding
+    from conftest import to_oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ny, nx, method, bound, shape = case
+        src = np.random.default_rng(0).random((ny, nx))
+        tr = t.Composition([t.Scale(1.3, dim=2), t.Rotation(25, unit='deg'), t.Offset([-nx / 2.0, -ny / 2.0])])
+
+        def invert_points(transform, pts):
+            return to_oracle(transform).reverse(np.asarray(pts, dtype=float))
+
+        def resample_block(transform, sub, origin, full, rows, shp, m, b, kw):
+            frame = np.full(full, np.nan)                       # poison what was not staged
+            frame[origin[1]:origin[1] + sub.shape[0], origin[0]:origin[0] + sub.shape[1]] = sub
+            return o.resample(to_oracle(transform), frame, method=m, bound=b, shape=shp, rows=rows)
+
+        out = sharding.resample_sharded(tr, src if rank == 0 else None, method=method, bound=bound, shape=shape,
+                                        invert_points=invert_points, resample_block=resample_block,
+                                        src_shape=src.shape, src_dtype=src.dtype)
+        if rank == 0:
+            want = o.resample(to_oracle(tr), src, method=method, bound=bound, shape=shape)
+            ret["ok"] = bool(out.shape == want.shape and np.array_equal(out, want))
+            ret["nan"] = int(np.isnan(out).sum())
+            plans = sharding.plan(tr, shape or src.shape, src.shape, method, bound, world, invert_points)
+            ret["boxes"] = [p["box"] for p in plans]
+            ret["whole"] = [p["whole"] for p in plans]
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [(96, 128, 'linear', 't', None), (96, 128, 'cubic', 't', (61, 77)),
+                                  (64, 64, 'nearest', 't', (5, 9)), (96, 128, 'linear', 'p', None)])
+def test_sharded_resample_world2(case):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29600 + (os.getpid() % 300)
+    mp.spawn(_worker, args=(2, port, case, ret), nprocs=2, join=True)
+    assert ret["ok"], dict(ret)
+    assert ret["nan"] == 0
+    if case[3] == 't':
+        # truncating boundary: each rank is staged a proper sub-rectangle, not the frame
+        assert not any(ret["whole"]) and all(b is not None for b in ret["boxes"])
+        ny, nx = case[0], case[1]
+        assert all((b[2] - b[0]) * (b[3] - b[1]) < ny * nx for b in ret["boxes"])
+    else:
+        assert all(ret["whole"])                                # wrapped taps: whole frame per rank
+
+
+def test_row_blocks_and_boxes():
+    sys.path.insert(0, ROOT)
+    from transform_b200 import sharding
+    assert sharding.row_blocks(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert sharding.row_blocks(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]          # ragged: empty tails
+    pts = sharding.border_points(3, 6, 40)
+    assert pts[:, 1].min() == 3 and pts[:, 1].max() == 5 and pts[:, 0].max() == 39
+    assert sharding.source_box(np.array([[np.nan, 1.0]]), 10, 10, 1) is None
+    assert sharding.source_box(np.array([[-50.0, -50.0]]), 10, 10, 1) is None
+    assert sharding.source_box(np.array([[2.2, 3.7], [5.1, 4.0]]), 100, 100, 2, margin=0) == (0, 1, 9, 7)
