@@ -53,6 +53,7 @@ def config(n_gpus, extra=None):
 # clocks sampler (nvidia-smi polled while the timed region runs)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """One streaming `nvidia-smi -lms 20` process for the duration of the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -60,28 +61,37 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.samples = []
-        self.stop = threading.Event()
-        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.proc = None
+        self.thread = None
 
-    def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+    def _pump(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6:
+                self.samples.append(f)
 
     def __enter__(self):
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+            time.sleep(0.3)                       # let the sampler come up before the timed region
+            self.samples.clear()
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.thread.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            if self.thread is not None:
+                self.thread.join(timeout=5)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -188,6 +198,9 @@ def gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to exactly one JSON line: NCCL prints its version banner there at VERSION level
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sys.path.insert(0, ROOT)
     import numpy as np
