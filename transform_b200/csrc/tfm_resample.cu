@@ -36,6 +36,8 @@ struct ResampleParams {
     int int_w, int_h;                        // #columns / #rows at which a whole NT x NT footprint fits
     double aff[6];                           // pre-composed affine map a00 a01 a10 a11 b0 b1 (AFF kernels)
     int aff_bounded;                         // host proved |coordinate| < 2^30 over the whole output grid
+    float aff_f[8];                          // fp32 copy of aff[0..5] + (dst_x0, dst_y0) for the empty-tile test
+    float aff_margin;                        // absolute fp32 rounding allowance for that test
     double fill;
     int *status;
     ChainDev chain;
@@ -273,6 +275,34 @@ k_resample(const __grid_constant__ ResampleParams P)
     const int X = blockIdx.x * 32 + px;
     const int Y0 = blockIdx.y * (8 * NPX) + py;
     const bool xin = X < P.dst_w;
+
+    // ---- phase 0 (host-composed affine maps only): CTA-uniform rejection of empty tiles ----
+    // The tile maps to a parallelogram whose bounding box is spanned by its 4 corners.  If that box,
+    // padded by the footprint and a 2-pixel safety margin, misses a truncated image entirely, every
+    // pixel of the tile is the fill value: store it and retire the CTA before any per-pixel work.
+    if (AFF && !GENERIC && P.aff_bounded) {
+        // fp32 is plenty here: |coordinate| < 1e9 is host-proven and the test carries a margin of
+        // 2 pixels + 1e-6 relative (P.aff_margin) on top of the footprint
+        const float tx0 = (float)(int)(blockIdx.x * 32) + P.aff_f[6], tx1 = tx0 + 31.0f;
+        const float ty0 = (float)(int)(blockIdx.y * (8 * NPX)) + P.aff_f[7], ty1 = ty0 + (float)(8 * NPX - 1);
+        const float ux0 = P.aff_f[0] * tx0, ux1 = P.aff_f[0] * tx1, uy0 = P.aff_f[1] * ty0, uy1 = P.aff_f[1] * ty1;
+        const float vx0 = P.aff_f[2] * tx0, vx1 = P.aff_f[2] * tx1, vy0 = P.aff_f[3] * ty0, vy1 = P.aff_f[3] * ty1;
+        const float xmin = fminf(ux0, ux1) + fminf(uy0, uy1) + P.aff_f[4], xmax = fmaxf(ux0, ux1) + fmaxf(uy0, uy1) + P.aff_f[4];
+        const float ymin = fminf(vx0, vx1) + fminf(vy0, vy1) + P.aff_f[5], ymax = fmaxf(vx0, vx1) + fmaxf(vy0, vy1) + P.aff_f[5];
+        const float pad = (float)(NT + 2) + P.aff_margin;
+        if (xmax < -pad || ymax < -pad || xmin > (float)P.src_w + pad || ymin > (float)P.src_h + pad) {
+            const DstT f = (DstT)(RegT)P.fill;
+            if (xin) {
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) {
+                    const int Y = Y0 + 8 * j;
+                    if (Y < P.dst_h)
+                        reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch)[X] = f;
+                }
+            }
+            return;
+        }
+    }
 
     // ---- phase 1: coordinates (fp64, in registers) ----
     double cx[NPX], cy[NPX];
@@ -542,6 +572,11 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         const double bx = fabs(P.aff[0]) * xm + fabs(P.aff[1]) * ym + fabs(P.aff[4]) + 1.0;
         const double by = fabs(P.aff[2]) * xm + fabs(P.aff[3]) * ym + fabs(P.aff[5]) + 1.0;
         P.aff_bounded = (bx < 1.0e9 && by < 1.0e9) ? 1 : 0;      // NaN parameters compare false
+        for (int k = 0; k < 6; ++k) P.aff_f[k] = (float)P.aff[k];
+        P.aff_f[6] = (float)d.x0;
+        P.aff_f[7] = (float)d.y0;
+        P.aff_margin = (float)(4e-6 * (bx > by ? bx : by));      // a few fp32 ulps of the largest term
+        if (!(P.aff_margin < 64.0f)) P.aff_bounded = 0;          // huge coordinates: skip the shortcut
     }
     if (exact) {
         if (s.dtype == TFM_F32 && d.dtype == TFM_F64)
