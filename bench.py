@@ -290,7 +290,7 @@ def gpu_arm(args):
         for tn, nm in ((2, "16x2"), (3, "8x4"), (4, "novm")):
             brk["linear_affine_fp32_warp%s_ms" % nm] = timed(
                 lambda: tr_aff.resample(src, method="linear", precision="fp32", out=out_lin, tuning=tn))
-        brk["jacobian_radial_fp32_tile32x8_ms"] = timed(
+        brk["jacobian_radial_fp32_tile32x16_ms"] = timed(
             lambda: tr_rad.resample(src, method="Gaussian", precision="fp32", out=out_jac, tuning=8), reps=3)
         brk["nearest_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="nearest", precision="fp32", out=out_lin))
         brk["cubic_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="cubic", precision="fp32", out=out_lin))
