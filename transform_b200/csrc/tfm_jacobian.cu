@@ -195,6 +195,41 @@ __device__ __forceinline__ float filt_eval<float>(int filter, float xf, float yf
     }
 }
 
+// Exact jump flag of one cell (helpers.pyx:1045-1139): 3x3 lags inside the cell grid, 2x3 / 3x2 on a
+// grid edge (the edge line and the next one), corners untouched (1).  Cold path: reached only for
+// cells near a jump, on grid edges, or when the fp32 quick-accept cannot decide.
+__device__ __noinline__ unsigned char jump_flag_exact(const double *m2, int cw, int ci, int cj,
+                                                      int gcx, int gcy, int NCX, int NCY, double thresh)
+{
+    const bool ix_in = (gcx >= 1 && gcx <= NCX - 2), iy_in = (gcy >= 1 && gcy <= NCY - 2);
+    const double me = m2[cj * cw + ci];
+    double v[9];
+    if (ix_in && iy_in) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) v[a * 3 + b] = m2[(cj - 1 + a) * cw + ci - 1 + b];
+        return me <= __dmul_rn(kth3_of9(v), thresh);
+    }
+    if (ix_in && NCY >= 2) {                       // bottom / top row of cells: 2 x 3 lags
+        const int r0 = (gcy == 0) ? cj : cj - 1;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) v[a * 3 + b] = m2[(r0 + a) * cw + ci - 1 + b];
+        return me <= __dmul_rn(kth2_of6(v), thresh);
+    }
+    if (iy_in && NCX >= 2) {                       // left / right column of cells: 3 x 2 lags
+        const int c0 = (gcx == 0) ? ci : ci - 1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) v[a * 2 + b] = m2[(cj - 1 + a) * cw + c0 + b];
+        return me <= __dmul_rn(kth2_of6(v), thresh);
+    }
+    return 1;                                      // corners (helpers.pyx:986-989)
+}
+
 // ---- fast-mode (fp32) pieces -------------------------------------------------------------------
 // padded inverse Jacobian in fp32: same closed form as svd2x2_dev/svc2x2_dev, MUFU-based
 // transcendentals.  Returns the three coefficients of the quadratic form q(a,b) = A a^2 + 2B ab + C b^2
@@ -360,31 +395,19 @@ k_jacobian(const __grid_constant__ JacParams P)
         const int gcx = wx0 + ci, gcy = wy0 + cj;      // global cell index
         unsigned char flag = 1;
         if (P.jump_thresh != 0.0 && (unsigned)gcx < (unsigned)NCX && (unsigned)gcy < (unsigned)NCY) {
-            const bool ix_in = (gcx >= 1 && gcx <= NCX - 2), iy_in = (gcy >= 1 && gcy <= NCY - 2);
-            // neighbourhood window in the smem cell array: 3x3 inside, 2x3 / 3x2 on a grid edge
-            // (the edge line and the next one, helpers.pyx:1079-1139), none at corners
-            int r0 = cj - 1, nr = 3, c0 = ci - 1, nc = 3;
-            if (!iy_in) { r0 = (gcy == 0) ? cj : cj - 1; nr = 2; }
-            if (!ix_in) { c0 = (gcx == 0) ? ci : ci - 1; nc = 2; }
-            const bool has = (ix_in && iy_in) || (ix_in && NCY >= 2) || (iy_in && NCX >= 2);
-            if (has && !(nr == 2 && nc == 2)) {
-                // quick accept in fp32: the k-th smallest is >= the minimum, so for a positive
-                // threshold me <= thr*min implies me <= thr*kth; margins cover the fp32 rounding.
-                // Only cells near a jump (or non-finite ones) take the exact fp64 sort.
-                float mn = s_m2f[r0][c0];
-                for (int a = 0; a < nr; ++a)
-                    for (int b = 0; b < nc; ++b) mn = fminf(mn, s_m2f[r0 + a][c0 + b]);
-                const float mef = s_m2f[cj][ci];
-                if (!(thr_f > 0.0f && mef < 1.0e30f && mef * 1.00001f <= thr_f * mn * 0.99999f)) {
-                    double v[9];
-                    int n = 0;
-                    for (int a = 0; a < nr; ++a)
-                        for (int b = 0; b < nc; ++b) v[n++] = s_m2[r0 + a][c0 + b];
-                    const double me = s_m2[cj][ci];
-                    if (n == 9) flag = me <= __dmul_rn(kth3_of9(v), P.jump_thresh);
-                    else flag = me <= __dmul_rn(kth2_of6(v), P.jump_thresh);
-                }
-            }                                           // corners stay 1 (helpers.pyx:986-989)
+            const bool interior = (gcx >= 1 && gcx <= NCX - 2 && gcy >= 1 && gcy <= NCY - 2);
+            bool decided = false;
+            if (interior) {
+                // quick accept in fp32 (fully unrolled): the k-th smallest is >= the minimum, so for
+                // a positive threshold me <= thr*min implies me <= thr*kth; the margins cover the
+                // fp32 rounding.  Only cells near a jump (or non-finite ones) take the exact sort.
+                const float *r0 = &s_m2f[cj - 1][ci - 1], *r1 = &s_m2f[cj][ci - 1], *r2 = &s_m2f[cj + 1][ci - 1];
+                const float mn = fminf(fminf(fminf(r0[0], r0[1]), fminf(r0[2], r1[0])),
+                                       fminf(fminf(r1[1], r1[2]), fminf(fminf(r2[0], r2[1]), r2[2])));
+                const float mef = r1[1];
+                decided = (thr_f > 0.0f) && (mef < 1.0e30f) && (mef * 1.00001f <= thr_f * mn * 0.99999f);
+            }
+            if (!decided) flag = jump_flag_exact(&s_m2[0][0], CW, ci, cj, gcx, gcy, NCX, NCY, P.jump_thresh);
         }
         s_flag[cj][ci] = flag;
     }
