@@ -266,33 +266,42 @@ __device__ __forceinline__ void padded_inverse_f32(const double *Ji, float padva
     smin = fminf(s0, s1);
 }
 
+// single-instruction MUFU approximations (fast mode only; 1-2 ulp, flush-to-zero)
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // f(lambda) = (padval + lambda^(p/2))^(-2/p): the squared padded inverse singular value as a function
 // of the squared singular value lambda (helpers.pyx:1661-1662 applied to s = sqrt(lambda)).
-__device__ __forceinline__ float pad_inv_sq(float lam, float padval, float pad_pow)
+__device__ __forceinline__ float pad_inv_sq(float lam, float padval, float half_pow, float m2_over_pow)
 {
-    const float sp = exp2f(0.5f * pad_pow * __log2f(lam));   // lam = 0 -> 0
-    return exp2f(-2.0f * __log2f(padval + sp) / pad_pow);
+    const float sp = fast_ex2(half_pow * fast_lg2(lam));     // lam = 0 -> lg2 = -inf -> 0
+    return fast_ex2(m2_over_pow * fast_lg2(padval + sp));
 }
 
 // Gaussian footprint weights need only Q = J^T J with J = V diag(s') U^T, i.e. Q = U diag(s'^2) U^T
 // = f(M M^T) for M = Ji = U diag(s) V^T: a function of a symmetric 2x2 matrix, which is always
-// alpha*I + beta*(M M^T).  No angles, no sincos -- eigenvalues by one sqrt.
+// alpha*I + beta*(M M^T).  No angles, no sincos -- eigenvalues by one square root.
+// Returns 1/smin (the footprint half-width is ceil(oblur/smin)).
 __device__ __forceinline__ void gaussian_quadratic_f32(const double *Ji, float padval, float pad_pow,
-                                                       float &q00, float &q01, float &q11, float &smin)
+                                                       float &q00, float &q01, float &q11, float &inv_smin)
 {
     const float a = (float)Ji[0], b = (float)Ji[1], c = (float)Ji[2], d = (float)Ji[3];
     const float g00 = a * a + b * b, g01 = a * c + b * d, g11 = c * c + d * d;
     const float mean = 0.5f * (g00 + g11), dif = 0.5f * (g00 - g11);
-    const float rad = sqrtf(dif * dif + g01 * g01);
+    const float r2 = dif * dif + g01 * g01;
+    const float rad = (r2 > 0.0f) ? r2 * fast_rsqrt(r2) : 0.0f;
     const float lp = mean + rad, lm = fmaxf(mean - rad, 0.0f);
-    const float fp = pad_inv_sq(lp, padval, pad_pow), fm = pad_inv_sq(lm, padval, pad_pow);
+    const float half_pow = 0.5f * pad_pow, m2p = -2.0f * fast_rcp(pad_pow);
+    const float fp = pad_inv_sq(lp, padval, half_pow, m2p), fm = pad_inv_sq(lm, padval, half_pow, m2p);
     float beta = 0.0f;
-    if (rad > 1e-6f * mean) beta = (fp - fm) / (lp - lm);
+    if (rad > 1e-6f * mean) beta = (fp - fm) * fast_rcp(lp - lm);
     const float alpha = fp - beta * lp;
     q00 = alpha + beta * g00;
     q01 = beta * g01;
     q11 = alpha + beta * g11;
-    smin = sqrtf(fp);                      // the larger singular value has the smaller padded inverse
+    inv_smin = fast_rsqrt(fp);             // the larger singular value has the smaller padded inverse
 }
 
 // (2*HALF+1)^2 Gaussian taps, fully unrolled.  Weights by recurrence: along a row
@@ -512,13 +521,13 @@ k_jacobian(const __grid_constant__ JacParams P)
         drow[X] = (DstT)((wgt > 0) ? val / wgt : 0.0);                               // helpers.pyx:1800
     } else {
         // ------------------------- fast mode (fp32) --------------------------------------------
-        const float ob = (float)P.oblur, iob = 1.0f / ob;
+        const float ob = (float)P.oblur, iob = fast_rcp(ob);
         const bool gauss = (P.filter == TFM_FILT_GAUSSIAN);
-        float J[4] = {0.f, 0.f, 0.f, 0.f}, smin, q00 = 0.f, q01 = 0.f, q11 = 0.f;
-        if (gauss) gaussian_quadratic_f32(Ji, (float)P.padval, (float)P.pad_pow, q00, q01, q11, smin);
-        else padded_inverse_f32(Ji, (float)P.padval, (float)P.pad_pow, J, smin);
-        float ratio = ob / smin;
-        if (fabsf(ratio - rintf(ratio)) < 2e-5f * ratio) {
+        float J[4] = {0.f, 0.f, 0.f, 0.f}, smin, inv_smin, q00 = 0.f, q01 = 0.f, q11 = 0.f;
+        if (gauss) gaussian_quadratic_f32(Ji, (float)P.padval, (float)P.pad_pow, q00, q01, q11, inv_smin);
+        else { padded_inverse_f32(Ji, (float)P.padval, (float)P.pad_pow, J, smin); inv_smin = fast_rcp(smin); }
+        float ratio = ob * inv_smin;
+        if (fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) {
             // the footprint size is a ceil(): when fp32 cannot decide it, redo that one number in fp64
             double U[4], V[4], sd[2];
             svd2x2_dev(Ji, U, sd, V);
@@ -550,10 +559,10 @@ k_jacobian(const __grid_constant__ JacParams P)
             // exp(-(xf^2+yf^2)) = exp2(-(A a^2 + 2B ab + C b^2)): three exp2 per pixel row set, two
             // multiplies per tap
             const float a0 = (float)(-half) + xf_of, b0 = (float)(-half) + yf_of;
-            const float w0 = exp2f(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
-            const float r0 = exp2f(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
-            const float rb = exp2f(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
-            const float cA = exp2f(-2.0f * Aq), cB = exp2f(-2.0f * Bq), cC = exp2f(-2.0f * Cq);
+            const float w0 = fast_ex2(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
+            const float r0 = fast_ex2(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
+            const float rb = fast_ex2(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
+            const float cA = fast_ex2(-2.0f * Aq), cB = fast_ex2(-2.0f * Bq), cC = fast_ex2(-2.0f * Cq);
             const SrcT *p0 = reinterpret_cast<const SrcT *>(src_base) + (ys - half) * pe + (xs - half);
             switch (half) {
             case 1: gauss_taps<1, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
@@ -572,7 +581,7 @@ k_jacobian(const __grid_constant__ JacParams P)
                 for (int xr = -half; xr <= half; ++xr) {
                     const float x0 = (float)xr + xf_of;
                     float filt;
-                    if (gauss) filt = exp2f(-((Aq * x0 + 2.0f * Bq * y0) * x0 + Cq * y0 * y0));
+                    if (gauss) filt = fast_ex2(-((Aq * x0 + 2.0f * Bq * y0) * x0 + Cq * y0 * y0));
                     else filt = filt_eval<float>(P.filter, fabsf(J0 * x0 + J1 * y0), fabsf(J2 * x0 + J3 * y0));
                     wgt += filt;
                     int st = sty;
@@ -589,7 +598,7 @@ k_jacobian(const __grid_constant__ JacParams P)
                 }
             }
         }
-        drow[X] = (DstT)((wgt > 0) ? val / wgt : 0.0f);
+        drow[X] = (DstT)((wgt > 0) ? val * fast_rcp(wgt) : 0.0f);
     }
     if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
 }
