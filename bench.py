@@ -188,6 +188,61 @@ def traffic_for(kernel_key):
         return None
 
 
+def extra_configs(t, torch, np, timed):
+    """BASELINE configs 2, 4 and 5 at full size (untimed for `value`; reported in `breakdown`)."""
+    out = {}
+    peak, _ = measured_peak()
+    # config 2: 4096^2 float32, Scale o Rotation o Offset, nearest and linear
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(7)
+    src = torch.rand((n, n), generator=g, device="cuda", dtype=torch.float32)
+    dst = torch.empty_like(src)
+    tr = t.Composition([t.Scale(1.3, dim=2), t.Rotation(30, unit="deg"), t.Offset([-n / 2.0, -n / 2.0])])
+    for m in ("nearest", "linear"):
+        ms = timed(lambda: tr.resample(src, method=m, precision="fp32", out=dst), reps=20)
+        out["config2_4096_%s_fp32_ms" % m] = ms
+        out["config2_4096_%s_fp32_mpix_s" % m] = n * n / (ms * 1e-3) / 1e6
+        out["config2_4096_%s_fp32_roofline_frac" % m] = 2 * n * n * 4 / (ms * 1e-3) / 1e9 / peak
+    # other affine maps at 8192^2 (the 60 % target should not hinge on one angle)
+    n8 = N_IMG
+    src8 = torch.rand((n8, n8), generator=g, device="cuda", dtype=torch.float32)
+    dst8 = torch.empty_like(src8)
+    for name, trx in (("rot45", t.Wrap(t.Rotation(45, unit="deg"), t.Offset([-n8 / 2.0, -n8 / 2.0]))),
+                      ("rot5", t.Wrap(t.Rotation(5, unit="deg"), t.Offset([-n8 / 2.0, -n8 / 2.0]))),
+                      ("scale0p8", t.Scale(0.8, dim=2)), ("shift", t.Offset([3.25, -7.5]))):
+        ms = timed(lambda: trx.resample(src8, method="linear", precision="fp32", out=dst8), reps=10)
+        out["linear_%s_8192_fp32_ms" % name] = ms
+        out["linear_%s_8192_fp32_roofline_frac" % name] = ALG_BYTES / (ms * 1e-3) / 1e9 / peak
+    del src8, dst8
+    # config 4: batch of 64 4096^2 frames, TAN -> CAR, linear (one launch, frames as planes)
+    hdr = {'NAXIS': 2, 'NAXIS1': n, 'NAXIS2': n, 'CTYPE1': 'RA---TAN', 'CTYPE2': 'DEC--TAN', 'CUNIT1': 'deg',
+           'CUNIT2': 'deg', 'CRPIX1': n / 2 + 0.5, 'CRPIX2': n / 2 + 0.5, 'CRVAL1': 150.0, 'CRVAL2': 20.0,
+           'CDELT1': -1.5 / n, 'CDELT2': 1.5 / n}
+    car = dict(hdr, CTYPE1='RA---CAR', CTYPE2='DEC--CAR')
+    total = t.Composition([t.WCS(car).inverse(), t.WCS(hdr)])
+    nb = 64
+    frames = torch.rand((nb, n, n), generator=g, device="cuda", dtype=torch.float32)
+    outb = torch.empty_like(frames)
+    ms = timed(lambda: total.resample(frames, method="linear", precision="fp32", out=outb, shape=(nb, n, n)), reps=2)
+    out["config4_64x4096_tan2car_linear_fp32_ms"] = ms
+    out["config4_64x4096_tan2car_linear_fp32_mpix_s"] = nb * n * n / (ms * 1e-3) / 1e6
+    out["config4_64x4096_tan2car_linear_fp32_roofline_frac"] = 2 * nb * n * n * 4 / (ms * 1e-3) / 1e9 / peak
+    del frames, outb
+    # config 5: Transform.apply on 1e9 2-vectors through an inverted composed chain (fp64: 32 GB of traffic)
+    nv = 10 ** 9
+    v = (torch.rand((nv, 2), generator=g, device="cuda", dtype=torch.float64) - 0.5) * 8192
+    aff = t.Composition([t.Scale([1.5, 2]), t.Rotation(30, unit="deg"), t.Offset([3, 4])]).inverse()
+    rad = t.Composition([t.Scale([1.5, 2]), t.Radial(origin=[0.1, 0.2]), t.Offset([3, 4])]).inverse()
+    for name, trx in (("affine", aff), ("radial", rad)):
+        ms = timed(lambda: trx.apply(v), reps=2)
+        out["config5_apply_1e9_%s_fp64_ms" % name] = ms
+        out["config5_apply_1e9_%s_fp64_mvec_s" % name] = nv / (ms * 1e-3) / 1e6
+        out["config5_apply_1e9_%s_fp64_roofline_frac" % name] = nv * 2 * 2 * 8 / (ms * 1e-3) / 1e9 / peak
+    del v
+    torch.cuda.empty_cache()
+    return out
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -287,8 +342,8 @@ def gpu_arm(args):
         brk["linear_affine_fp32_ms"] = ms_lin
         brk["jacobian_radial_fp32_ms"] = ms_jac
         brk["linear_radial_fp32_ms"] = timed(lambda: tr_rad.resample(src, method="linear", precision="fp32", out=out_lin))
-        for tn, nm in ((2, "16x2"), (3, "8x4"), (4, "novm")):
-            brk["linear_affine_fp32_warp%s_ms" % nm] = timed(
+        for tn, nm in ((16, "ldg_gather"), (4 | 16, "ldg_gather_interpreted_chain")):
+            brk["linear_affine_fp32_%s_ms" % nm] = timed(
                 lambda: tr_aff.resample(src, method="linear", precision="fp32", out=out_lin, tuning=tn))
         brk["jacobian_radial_fp32_tile32x16_ms"] = timed(
             lambda: tr_rad.resample(src, method="Gaussian", precision="fp32", out=out_jac, tuning=8), reps=3)
@@ -299,6 +354,8 @@ def gpu_arm(args):
         for k in list(brk):
             brk[k.replace("_ms", "_mpix_s")] = n * n / (brk[k] * 1e-3) / 1e6
         del o64
+        if not args.no_extra:
+            brk.update(extra_configs(t, torch, np, timed))
 
     # max over ranks
     tt = torch.tensor([ms_total, s_e2e], device="cuda", dtype=torch.float64)
@@ -352,6 +409,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs 2/4/5 breakdown (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
+#include <mutex>
 #include "tfm_chain.cuh"
 #include "tfm_common.cuh"
 
@@ -444,6 +446,140 @@ k_resample(const __grid_constant__ ResampleParams P)
 }
 
 // ---------------------------------------------------------------------------------------------
+// texture-gather variant (fp32 fast path, linear, bound = truncate with fill 0, whole image)
+// ---------------------------------------------------------------------------------------------
+// The texture unit does what the ALU pipe was saturated with in k_resample: address generation,
+// the out-of-range test of every tap (border mode returns 0 = the reference's truncate boundary with
+// its default fillvalue) and the fetch of the whole 2x2 footprint in ONE instruction (TLD4).  What is
+// left per pixel: 2 DFMA (coordinates), the XU-free floor/fraction, 6 fp32 ops of interpolation in
+// the same order as k_resample, one store.  No interior/outside classification at all.
+template <class A, bool AFF>
+__global__ void __launch_bounds__(256)
+k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex)
+{
+    constexpr int NPX = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    char *const dst_base = static_cast<char *>(P.dst);
+    const int px = ((warp & 1) << 4) + (lane & 15);
+    const int py = ((warp >> 1) << 1) + (lane >> 4);
+    const int X = blockIdx.x * 32 + px;
+    const int Y0 = blockIdx.y * (8 * NPX) + py;
+    const bool xin = X < P.dst_w;
+
+    if (AFF && P.aff_bounded) {            // CTA-uniform rejection of empty tiles (see k_resample)
+        const float tx0 = (float)(int)(blockIdx.x * 32) + P.aff_f[6], tx1 = tx0 + 31.0f;
+        const float ty0 = (float)(int)(blockIdx.y * (8 * NPX)) + P.aff_f[7], ty1 = ty0 + (float)(8 * NPX - 1);
+        const float ux0 = P.aff_f[0] * tx0, ux1 = P.aff_f[0] * tx1, uy0 = P.aff_f[1] * ty0, uy1 = P.aff_f[1] * ty1;
+        const float vx0 = P.aff_f[2] * tx0, vx1 = P.aff_f[2] * tx1, vy0 = P.aff_f[3] * ty0, vy1 = P.aff_f[3] * ty1;
+        const float xmin = fminf(ux0, ux1) + fminf(uy0, uy1) + P.aff_f[4], xmax = fmaxf(ux0, ux1) + fmaxf(uy0, uy1) + P.aff_f[4];
+        const float ymin = fminf(vx0, vx1) + fminf(vy0, vy1) + P.aff_f[5], ymax = fmaxf(vx0, vx1) + fmaxf(vy0, vy1) + P.aff_f[5];
+        const float pad = 4.0f + P.aff_margin;
+        if (xmax < -pad || ymax < -pad || xmin > (float)P.src_w + pad || ymin > (float)P.src_h + pad) {
+            if (xin) {
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) {
+                    const int Y = Y0 + 8 * j;
+                    if (Y < P.dst_h) reinterpret_cast<float *>(dst_base + (long long)Y * P.dst_pitch)[X] = 0.0f;
+                }
+            }
+            return;
+        }
+    }
+
+    double cx[NPX], cy[NPX];
+    if (AFF) {
+        const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y0);
+        const double bx = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
+        const double by = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            cx[j] = fma((double)(8 * j), P.aff[1], bx);
+            cy[j] = fma((double)(8 * j), P.aff[3], by);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            cx[j] = (double)(P.dst_x0 + X);
+            cy[j] = (double)(P.dst_y0 + Y0 + 8 * j);
+        }
+        chain_eval_n<A, NPX>(P.chain, cx, cy);
+    }
+
+    float4 g[NPX];
+    float fx[NPX], fy[NPX];
+#pragma unroll
+    for (int j = 0; j < NPX; ++j) {
+        int ix, iy;
+        floor_frac_fast(cx[j], ix, fx[j]);
+        floor_frac_fast(cy[j], iy, fy[j]);
+        // NaN / inf / absurd coordinate -> far outside the texture (border = 0); the compare is only
+        // needed when the host could not bound the coordinates
+        if (!(AFF && P.aff_bounded)) {
+            if (!((fabs(cx[j]) < 1.0e9) && (fabs(cy[j]) < 1.0e9))) { ix = -100000; iy = -100000; fx[j] = 0.f; fy[j] = 0.f; }
+        }
+        // unnormalised coordinates: the bilinear footprint of (u,v) is texels floor(u-0.5)+{0,1},
+        // so (ix+1, iy+1) selects columns ix, ix+1 and rows iy, iy+1
+        g[j] = tex2Dgather<float4>(tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < NPX; ++j) {
+        const int Y = Y0 + 8 * j;
+        if (!xin || Y >= P.dst_h) continue;
+        // gather order: x = (i0,j1), y = (i1,j1), z = (i1,j0), w = (i0,j0)
+        const float v00 = g[j].w, v01 = g[j].z, v10 = g[j].x, v11 = g[j].y;
+        const float top = fmaf(fx[j], v01 - v00, v00);
+        const float bot = fmaf(fx[j], v11 - v10, v10);
+        reinterpret_cast<float *>(dst_base + (long long)Y * P.dst_pitch)[X] = fmaf(fy[j], bot - top, top);
+    }
+}
+
+// Texture objects over caller memory are cached per (device, pointer, geometry): creating one costs
+// microseconds, a resample launch ~100.  A texture object refers to an address range, not to its
+// contents, so reuse after the caller rewrote (or re-allocated) the buffer is safe.
+struct TexKey {
+    int dev; const void *ptr; int w, h; long long pitch;
+    bool operator==(const TexKey &o) const { return dev == o.dev && ptr == o.ptr && w == o.w && h == o.h && pitch == o.pitch; }
+};
+static std::mutex g_tex_mu;
+static TexKey g_tex_keys[16];
+static cudaTextureObject_t g_tex_objs[16];
+static int g_tex_n = 0, g_tex_next = 0;
+
+static bool get_texture(const void *ptr, int w, int h, long long pitch, cudaTextureObject_t *out)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    TexKey key{dev, ptr, w, h, pitch};
+    std::lock_guard<std::mutex> lock(g_tex_mu);
+    for (int i = 0; i < g_tex_n; ++i)
+        if (g_tex_keys[i] == key) { *out = g_tex_objs[i]; return true; }
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypePitch2D;
+    rd.res.pitch2D.devPtr = const_cast<void *>(ptr);
+    rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+    rd.res.pitch2D.width = (size_t)w;
+    rd.res.pitch2D.height = (size_t)h;
+    rd.res.pitch2D.pitchInBytes = (size_t)pitch;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeBorder;
+    td.addressMode[1] = cudaAddressModeBorder;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    cudaTextureObject_t t = 0;
+    if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    int slot;
+    if (g_tex_n < 16) slot = g_tex_n++;
+    else { slot = g_tex_next; g_tex_next = (g_tex_next + 1) & 15; cudaDestroyTextureObject(g_tex_objs[slot]); }
+    g_tex_keys[slot] = key;
+    g_tex_objs[slot] = t;
+    *out = t;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 template <int METHOD, typename SrcT, typename DstT, class A, typename RegT>
@@ -588,7 +724,23 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         else
             return TFM_EUNSUPPORTED;
     } else if (a->precision == TFM_PREC_FAST32) {
-        if (s.dtype == TFM_F32 && d.dtype == TFM_F32)
+        // texture-gather variant: linear, truncate on both axes with the default fill 0, one plane,
+        // geometry within the limits of pitch-linear 2-D textures
+        cudaTextureObject_t tex = 0;
+        const bool tex_ok = !generic && a->method == TFM_LINEAR && s.dtype == TFM_F32 && d.dtype == TFM_F32 &&
+                            a->fillvalue == 0.0 && s.n_planes == 1 && !(a->tuning & 16) &&
+                            s.w <= 131072 && s.h <= 65000 && (s.pitch % 32) == 0 &&
+                            (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 &&
+                            get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &tex);
+        if (tex_ok) {
+            dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 31) / 32), 1);
+            if (grid.y > 65535u) return TFM_EUNSUPPORTED;
+            if (aff) k_resample_tex<Fast, true><<<grid, 256, 0, st>>>(P, tex);
+            else k_resample_tex<Fast, false><<<grid, 256, 0, st>>>(P, tex);
+            count_launch();
+            name = aff ? "k_resample_tex<affine>" : "k_resample_tex";
+            e = cudaGetLastError();
+        } else if (s.dtype == TFM_F32 && d.dtype == TFM_F32)
             e = launch1<float, float, Fast, float>(a->method, P, generic, aff, st, &name);
         else
             return TFM_EUNSUPPORTED;
