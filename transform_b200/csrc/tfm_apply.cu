@@ -25,7 +25,7 @@ struct ApplyParams {
     ChainDev chain;
 };
 
-template <class A, int UNROLL>
+template <class A, int UNROLL, bool SPH>
 __global__ void __launch_bounds__(256)
 k_apply_f64x2(const __grid_constant__ ApplyParams P)
 {
@@ -40,19 +40,19 @@ k_apply_f64x2(const __grid_constant__ ApplyParams P)
         double x[UNROLL], y[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) { x[u] = v[u].x; y[u] = v[u].y; }
-        chain_eval_n<A, UNROLL>(P.chain, x, y);
+        chain_eval_n<A, SPH, UNROLL>(P.chain, x, y);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) __stcs(out + i + u * stride, make_double2(x[u], y[u]));
     }
     for (; i < P.n_vec; i += stride) {
         double2 v = __ldcs(in + i);
-        chain_eval<A>(P.chain, v.x, v.y);
+        chain_eval<A, SPH>(P.chain, v.x, v.y);
         __stcs(out + i, v);
     }
 }
 
 // two fp32 vectors per 16-byte packet
-template <class A, int UNROLL>
+template <class A, int UNROLL, bool SPH>
 __global__ void __launch_bounds__(256)
 k_apply_f32x2(const __grid_constant__ ApplyParams P)
 {
@@ -70,7 +70,7 @@ k_apply_f32x2(const __grid_constant__ ApplyParams P)
         for (int u = 0; u < UNROLL; ++u) {
             x[2 * u] = v[u].x; y[2 * u] = v[u].y; x[2 * u + 1] = v[u].z; y[2 * u + 1] = v[u].w;
         }
-        chain_eval_n<A, 2 * UNROLL>(P.chain, x, y);
+        chain_eval_n<A, SPH, 2 * UNROLL>(P.chain, x, y);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
             __stcs(out + i + u * stride, make_float4((float)x[2 * u], (float)y[2 * u],
@@ -79,22 +79,22 @@ k_apply_f32x2(const __grid_constant__ ApplyParams P)
     for (; i < n_pk; i += stride) {
         float4 v = __ldcs(in + i);
         double x0 = v.x, y0 = v.y, x1 = v.z, y1 = v.w;
-        chain_eval<A>(P.chain, x0, y0);
-        chain_eval<A>(P.chain, x1, y1);
+        chain_eval<A, SPH>(P.chain, x0, y0);
+        chain_eval<A, SPH>(P.chain, x1, y1);
         __stcs(out + i, make_float4((float)x0, (float)y0, (float)x1, (float)y1));
     }
     if ((P.n_vec & 1) && blockIdx.x == 0 && threadIdx.x == 0) {       // odd tail vector
         const float *fi = static_cast<const float *>(P.in) + 2 * (P.n_vec - 1);
         float *fo = static_cast<float *>(P.out) + 2 * (P.n_vec - 1);
         double x = fi[0], y = fi[1];
-        chain_eval<A>(P.chain, x, y);
+        chain_eval<A, SPH>(P.chain, x, y);
         fo[0] = (float)x;
         fo[1] = (float)y;
     }
 }
 
 // general vec_len (>= 2): one thread per vector, extras copied through
-template <class A, typename T>
+template <class A, typename T, bool SPH>
 __global__ void __launch_bounds__(256)
 k_apply_generic(const __grid_constant__ ApplyParams P)
 {
@@ -106,7 +106,7 @@ k_apply_generic(const __grid_constant__ ApplyParams P)
         const T *vi = in + i * L;
         T *vo = out + i * L;
         double x = (double)vi[0], y = (double)vi[1];
-        chain_eval<A>(P.chain, x, y);
+        chain_eval<A, SPH>(P.chain, x, y);
         for (int k = 2; k < L; ++k) vo[k] = vi[k];
         vo[0] = (T)x;
         vo[1] = (T)y;
@@ -139,8 +139,13 @@ int apply_dispatch(const tfm_apply_args *a, cudaStream_t st)
 
     ApplyParams P;
     P.in = a->in; P.out = a->out; P.n_vec = a->n_vec; P.vec_len = a->vec_len;
-    P.chain.n = a->n_ops; P.chain.pad = 0;
-    for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
+    P.chain.pad = 0;
+    if (a->precision == TFM_PREC_FAST32) {
+        P.chain.n = fuse_chain_fast(a->chain, a->n_ops, P.chain.ops);       // fast mode: peephole fusion
+    } else {
+        P.chain.n = a->n_ops;
+        for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
+    }
 
     const bool exact = (a->precision == TFM_PREC_EXACT64);
     const bool aligned = ((reinterpret_cast<uintptr_t>(a->in) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0;
@@ -150,23 +155,30 @@ int apply_dispatch(const tfm_apply_args *a, cudaStream_t st)
         int grid = resident_grid((const void *)KERNEL, (ITEMS));                        \
         KERNEL<<<grid, 256, 0, st>>>(P);                                                \
     } while (0)
+    const bool sph = chain_has_sph(P.chain);
+#define TFM_L2(KERNEL_E_T, KERNEL_E_F, KERNEL_F_T, KERNEL_F_F, ITEMS)            \
+    do {                                                                         \
+        if (exact) { if (sph) TFM_LAUNCH(KERNEL_E_T, ITEMS); else TFM_LAUNCH(KERNEL_E_F, ITEMS); } \
+        else { if (sph) TFM_LAUNCH(KERNEL_F_T, ITEMS); else TFM_LAUNCH(KERNEL_F_F, ITEMS); }       \
+    } while (0)
     if (a->vec_len == 2 && aligned && a->dtype == TFM_F64) {
-        if (exact) TFM_LAUNCH((k_apply_f64x2<Exact, 4>), a->n_vec);
-        else       TFM_LAUNCH((k_apply_f64x2<Fast, 4>), a->n_vec);
+        TFM_L2((k_apply_f64x2<Exact, 4, true>), (k_apply_f64x2<Exact, 4, false>),
+               (k_apply_f64x2<Fast, 4, true>), (k_apply_f64x2<Fast, 4, false>), a->n_vec);
         name = "k_apply_f64x2";
     } else if (a->vec_len == 2 && aligned && a->dtype == TFM_F32) {
-        if (exact) TFM_LAUNCH((k_apply_f32x2<Exact, 4>), a->n_vec / 2 + 1);
-        else       TFM_LAUNCH((k_apply_f32x2<Fast, 4>), a->n_vec / 2 + 1);
+        TFM_L2((k_apply_f32x2<Exact, 4, true>), (k_apply_f32x2<Exact, 4, false>),
+               (k_apply_f32x2<Fast, 4, true>), (k_apply_f32x2<Fast, 4, false>), a->n_vec / 2 + 1);
         name = "k_apply_f32x2";
     } else if (a->dtype == TFM_F64) {
-        if (exact) TFM_LAUNCH((k_apply_generic<Exact, double>), a->n_vec);
-        else       TFM_LAUNCH((k_apply_generic<Fast, double>), a->n_vec);
+        TFM_L2((k_apply_generic<Exact, double, true>), (k_apply_generic<Exact, double, false>),
+               (k_apply_generic<Fast, double, true>), (k_apply_generic<Fast, double, false>), a->n_vec);
         name = "k_apply_generic<f64>";
     } else {
-        if (exact) TFM_LAUNCH((k_apply_generic<Exact, float>), a->n_vec);
-        else       TFM_LAUNCH((k_apply_generic<Fast, float>), a->n_vec);
+        TFM_L2((k_apply_generic<Exact, float, true>), (k_apply_generic<Exact, float, false>),
+               (k_apply_generic<Fast, float, true>), (k_apply_generic<Fast, float, false>), a->n_vec);
         name = "k_apply_generic<f32>";
     }
+#undef TFM_L2
 #undef TFM_LAUNCH
     count_launch();
     set_last_kernel(name);

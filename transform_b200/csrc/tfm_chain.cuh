@@ -119,33 +119,16 @@ __device__ __forceinline__ void op_radial(const tfm_op &op, double &x, double &y
 #define TFM_D2R 0.017453292519943295
 #define TFM_R2D 57.29577951308232
 
-template <class A>
-__device__ __forceinline__ void wcs_native_to_celestial(const double *R, double phi, double theta,
-                                                        double &lon, double &lat, bool to_celestial)
-{
-    // unit vector in the source frame, rotated by R (or R^T), back to angles (degrees)
-    double sp, cp, st, ct;
-    sincos(phi * TFM_D2R, &sp, &cp);
-    sincos(theta * TFM_D2R, &st, &ct);
-    double vx = ct * cp, vy = ct * sp, vz = st;
-    double wx, wy, wz;
-    if (to_celestial) {
-        wx = R[0] * vx + R[1] * vy + R[2] * vz;
-        wy = R[3] * vx + R[4] * vy + R[5] * vz;
-        wz = R[6] * vx + R[7] * vy + R[8] * vz;
-    } else {
-        wx = R[0] * vx + R[3] * vy + R[6] * vz;
-        wy = R[1] * vx + R[4] * vy + R[7] * vz;
-        wz = R[2] * vx + R[5] * vy + R[8] * vz;
-    }
-    lon = atan2(wy, wx) * TFM_R2D;
-    lat = atan2(wz, sqrt(wx * wx + wy * wy)) * TFM_R2D;
-}
-
+// Spherical part in unit-vector form.  m = (cos t cos p, cos t sin p, sin t) for native (p, t);
+// l = R m is the celestial unit vector (R built on the host from CRVAL / LONPOLE / LATPOLE).
+//   TAN (gnomonic): intermediate (x, y) = R2D (m_y, -m_x) / m_z  <=>  m ~ (-y, x, R2D)   [eq. 54-55]
+//   CAR           : (x, y) = (p, t) in degrees                                          [eq. 83-84]
+// so TAN needs no trigonometry at all and CAR needs one sincos pair or one atan2 pair.
 template <class A>
 __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
 {
     const int proj = op.flags & 0xff;
+    const double *R = op.p + 12;
     if (op.dir == TFM_FWD) {            // pixel (origin 0) -> world: all_pix2world(d, 0), core.py:1727
         double dx = A::sub(A::add(x, 1.0), op.p[0]);       // FITS pixels are 1-based
         double dy = A::sub(A::add(y, 1.0), op.p[1]);
@@ -156,19 +139,21 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             y = A::add(iy, op.p[11]);
             return;
         }
-        double phi, theta;
-        if (proj == TFM_WCS_PROJ_TAN) {                    // paper II eq. 14, 15, 55
-            double r = sqrt(ix * ix + iy * iy);
-            phi = (r == 0.0) ? 0.0 : atan2(ix, -iy) * TFM_R2D;
-            theta = atan2(TFM_R2D, r) * TFM_R2D;
-        } else {                                           // CAR: paper II eq. 83, 84
-            phi = ix;
-            theta = iy;
+        double mx, my, mz;
+        if (proj == TFM_WCS_PROJ_TAN) {
+            mx = -iy; my = ix; mz = TFM_R2D;               // un-normalised: only angles are taken below
+        } else {
+            double sp, cp, st, ct;
+            sincos(ix * TFM_D2R, &sp, &cp);
+            sincos(iy * TFM_D2R, &st, &ct);
+            mx = ct * cp; my = ct * sp; mz = st;
         }
-        double lon, lat;
-        wcs_native_to_celestial<A>(op.p + 12, phi, theta, lon, lat, true);
-        // wcslib normalises the celestial longitude into [0, 360)
-        if (lon < 0.0) lon += 360.0;
+        const double lx = R[0] * mx + R[1] * my + R[2] * mz;
+        const double ly = R[3] * mx + R[4] * my + R[5] * mz;
+        const double lz = R[6] * mx + R[7] * my + R[8] * mz;
+        double lon = atan2(ly, lx) * TFM_R2D;
+        const double lat = atan2(lz, sqrt(lx * lx + ly * ly)) * TFM_R2D;
+        if (lon < 0.0) lon += 360.0;                       // wcslib normalises into [0, 360)
         x = lon;
         y = lat;
     } else {                            // world -> pixel: all_world2pix(d, 0), core.py:1742
@@ -177,18 +162,25 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             ix = A::sub(x, op.p[10]);
             iy = A::sub(y, op.p[11]);
         } else {
-            double phi, theta;
-            wcs_native_to_celestial<A>(op.p + 12, x, y, phi, theta, false);
-            if (proj == TFM_WCS_PROJ_TAN) {                // paper II eq. 12, 13, 54
-                double sp, cp, st, ct;
-                sincos(phi * TFM_D2R, &sp, &cp);
-                sincos(theta * TFM_D2R, &st, &ct);
-                double r = (st > 0.0) ? TFM_R2D * ct / st : nan("");   // theta <= 0: not on this side of the sky
-                ix = r * sp;
-                iy = -r * cp;
-            } else {                                       // CAR
-                ix = phi;
-                iy = theta;
+            double sl, cl, sb, cb;
+            sincos(x * TFM_D2R, &sl, &cl);
+            sincos(y * TFM_D2R, &sb, &cb);
+            const double lx = cb * cl, ly = cb * sl, lz = sb;
+            const double mx = R[0] * lx + R[3] * ly + R[6] * lz;       // R^T l
+            const double my = R[1] * lx + R[4] * ly + R[7] * lz;
+            const double mz = R[2] * lx + R[5] * ly + R[8] * lz;
+            if (proj == TFM_WCS_PROJ_TAN) {
+                if (mz > 0.0) {
+                    const double s = TFM_R2D / mz;
+                    ix = my * s;
+                    iy = -mx * s;
+                } else {                                   // theta <= 0: the far side of the sky
+                    ix = nan("");
+                    iy = nan("");
+                }
+            } else {
+                ix = atan2(my, mx) * TFM_R2D;
+                iy = atan2(mz, sqrt(mx * mx + my * my)) * TFM_R2D;
             }
         }
         double px = A::add(A::mul(op.p[6], ix), A::mul(op.p[7], iy));
@@ -196,6 +188,85 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
         x = A::sub(A::add(px, op.p[0]), 1.0);
         y = A::sub(A::add(py, op.p[1]), 1.0);
     }
+}
+
+// Internal opcode (never crosses the C ABI): a WCS pixel->world op directly followed by a WCS
+// world->pixel op, both with a spherical projection -- what remap() builds for a WCS-to-WCS
+// resampling (core.py:920-923).  The fast-mode host pass (fuse_chain_fast) replaces the pair by one
+// op that keeps the celestial direction as a unit vector: no angles, no atan2 -> sincos round trip.
+//   p[0..1] CRPIX_A  p[2..5] CD_A  p[6..14] R = R_B^T R_A  p[15..18] CDinv_B  p[19..20] CRPIX_B
+//   flags = projA | projB << 8
+#define TFM_OP_WCS_PAIR 100
+
+__device__ __forceinline__ void op_wcs_pair(const tfm_op &op, double &x, double &y)
+{
+    const int pa = op.flags & 0xff, pb = (op.flags >> 8) & 0xff;
+    const double dx = (x + 1.0) - op.p[0], dy = (y + 1.0) - op.p[1];
+    const double ix = op.p[2] * dx + op.p[3] * dy, iy = op.p[4] * dx + op.p[5] * dy;
+    double mx, my, mz;
+    if (pa == TFM_WCS_PROJ_TAN) {
+        const double inv = rsqrt(ix * ix + iy * iy + TFM_R2D * TFM_R2D);
+        mx = -iy * inv; my = ix * inv; mz = TFM_R2D * inv;
+    } else {
+        double sp, cp, st, ct;
+        sincos(ix * TFM_D2R, &sp, &cp);
+        sincos(iy * TFM_D2R, &st, &ct);
+        mx = ct * cp; my = ct * sp; mz = st;
+    }
+    const double *R = op.p + 6;
+    const double nx = R[0] * mx + R[1] * my + R[2] * mz;
+    const double ny = R[3] * mx + R[4] * my + R[5] * mz;
+    const double nz = R[6] * mx + R[7] * my + R[8] * mz;
+    double ox, oy;
+    if (pb == TFM_WCS_PROJ_TAN) {
+        if (nz > 0.0) { const double sc = TFM_R2D / nz; ox = ny * sc; oy = -nx * sc; }
+        else { ox = nan(""); oy = nan(""); }
+    } else {
+        ox = atan2(ny, nx) * TFM_R2D;
+        oy = atan2(nz, sqrt(nx * nx + ny * ny)) * TFM_R2D;
+    }
+    x = (op.p[15] * ox + op.p[16] * oy + op.p[19]) - 1.0;
+    y = (op.p[17] * ox + op.p[18] * oy + op.p[20]) - 1.0;
+}
+
+static inline bool chain_has_sph(const ChainDev &ch)
+{
+    for (int i = 0; i < ch.n; ++i)
+        if (ch.ops[i].kind == TFM_OP_WCS || ch.ops[i].kind == TFM_OP_WCS_PAIR) return true;
+    return false;
+}
+
+// Host-side fast-mode peephole pass: copy `ops` into `out`, fusing adjacent spherical WCS pairs.
+static inline int fuse_chain_fast(const tfm_op *ops, int n, tfm_op *out)
+{
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        const tfm_op &a = ops[i];
+        if (i + 1 < n && a.kind == TFM_OP_WCS && a.dir == TFM_FWD && (a.flags & 0xff) != TFM_WCS_PROJ_NONE &&
+            ops[i + 1].kind == TFM_OP_WCS && ops[i + 1].dir == TFM_REV &&
+            (ops[i + 1].flags & 0xff) != TFM_WCS_PROJ_NONE) {
+            const tfm_op &b = ops[i + 1];
+            tfm_op f;
+            f.kind = TFM_OP_WCS_PAIR; f.dir = TFM_FWD; f.reserved = 0;
+            f.flags = (a.flags & 0xff) | ((b.flags & 0xff) << 8);
+            for (int k = 0; k < TFM_OP_NPARAM; ++k) f.p[k] = 0.0;
+            f.p[0] = a.p[0]; f.p[1] = a.p[1];
+            for (int k = 0; k < 4; ++k) { f.p[2 + k] = a.p[2 + k]; f.p[15 + k] = b.p[6 + k]; }
+            const double *RA = a.p + 12, *RB = b.p + 12;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    double acc = 0.0;
+                    for (int k = 0; k < 3; ++k) acc += RB[k * 3 + r] * RA[k * 3 + c];   // (R_B^T R_A)[r][c]
+                    f.p[6 + r * 3 + c] = acc;
+                }
+            f.p[19] = b.p[0]; f.p[20] = b.p[1];
+            out[m++] = f;
+            ++i;
+        } else {
+            out[m++] = a;
+        }
+    }
+    return m;
 }
 
 // interpND / interpND_grid take a precomputed coordinate array (helpers.pyx:379, 1293)
@@ -214,7 +285,11 @@ __device__ __forceinline__ void op_index(const tfm_op &op, double &x, double &y)
     y = v.y;
 }
 
-template <class A>
+// SPH: the chain contains spherical WCS ops.  Their code (sincos/atan2 in fp64) is compiled only into
+// the kernel instantiations that the host selects for such chains -- inlined into every kernel it
+// costs the others registers (measured +7% on the Jacobian kernel), out of line it spills the
+// interpreter's state to the stack (measured 2x on the parity-mode linear kernel).
+template <class A, bool SPH>
 __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double &y)
 {
     for (int i = 0; i < ch.n; ++i) {
@@ -222,7 +297,8 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
         switch (op.kind) {
         case TFM_OP_LINEAR: op_linear<A>(op, x, y); break;
         case TFM_OP_RADIAL: op_radial<A>(op, x, y); break;
-        case TFM_OP_WCS: op_wcs<A>(op, x, y); break;
+        case TFM_OP_WCS: if constexpr (SPH) op_wcs<A>(op, x, y); break;
+        case TFM_OP_WCS_PAIR: if constexpr (SPH) op_wcs_pair(op, x, y); break;
         case TFM_OP_INDEX: op_index(op, x, y); break;
         default: break;                                     // identity
         }
@@ -231,7 +307,7 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
 
 // ---- N-wide evaluation: the interpreter's dispatch (constant loads, flag tests, branches) is paid
 // once per op per THREAD instead of once per op per pixel; the per-pixel work is the arithmetic only.
-template <class A, int N>
+template <class A, bool SPH, int N>
 __device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N], double (&y)[N])
 {
     for (int i = 0; i < ch.n; ++i) {
@@ -279,8 +355,16 @@ __device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N],
             for (int k = 0; k < N; ++k) op_radial<A>(op, x[k], y[k]);
             break;
         case TFM_OP_WCS:
+            if constexpr (SPH) {
 #pragma unroll
-            for (int k = 0; k < N; ++k) op_wcs<A>(op, x[k], y[k]);
+                for (int k = 0; k < N; ++k) op_wcs<A>(op, x[k], y[k]);
+            }
+            break;
+        case TFM_OP_WCS_PAIR:
+            if constexpr (SPH) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) op_wcs_pair(op, x[k], y[k]);
+            }
             break;
         case TFM_OP_INDEX:
 #pragma unroll

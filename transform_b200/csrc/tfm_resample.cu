@@ -258,7 +258,7 @@ __device__ __forceinline__ void finish(const ResampleParams &P, RegT (&v)[NPX][N
 // GENERIC  false: both axes 'truncate', source is the whole image (fast path);
 //          true : per-axis runtime boundary modes and/or staged source sub-rectangle
 // AFF      the whole chain was pre-composed by the host into one affine map P.aff (fast mode only)
-template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC, bool AFF>
+template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC, bool AFF, bool SPH>
 __global__ void __launch_bounds__(256)
 k_resample(const __grid_constant__ ResampleParams P)
 {
@@ -323,7 +323,7 @@ k_resample(const __grid_constant__ ResampleParams P)
             cx[j] = (double)(P.dst_x0 + X);
             cy[j] = (double)(P.dst_y0 + Y0 + 8 * j);
         }
-        chain_eval_n<A, NPX>(P.chain, cx, cy);
+        chain_eval_n<A, SPH, NPX>(P.chain, cx, cy);
     }
 
     // ---- phase 2: taps (all loads of the NPX pixels issued before any is consumed) ----
@@ -453,7 +453,7 @@ k_resample(const __grid_constant__ ResampleParams P)
 // its default fillvalue) and the fetch of the whole 2x2 footprint in ONE instruction (TLD4).  What is
 // left per pixel: 2 DFMA (coordinates), the XU-free floor/fraction, 6 fp32 ops of interpolation in
 // the same order as k_resample, one store.  No interior/outside classification at all.
-template <class A, bool AFF>
+template <class A, bool AFF, bool SPH>
 __global__ void __launch_bounds__(256)
 k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex)
 {
@@ -502,7 +502,7 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
             cx[j] = (double)(P.dst_x0 + X);
             cy[j] = (double)(P.dst_y0 + Y0 + 8 * j);
         }
-        chain_eval_n<A, NPX>(P.chain, cx, cy);
+        chain_eval_n<A, SPH, NPX>(P.chain, cx, cy);
     }
 
     float4 g[NPX];
@@ -592,16 +592,19 @@ static cudaError_t launch2(ResampleParams &P, bool generic, bool aff, cudaStream
     if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
     P.int_w = P.src_w - NT + 1 > 0 ? P.src_w - NT + 1 : 0;
     P.int_h = P.src_h - NT + 1 > 0 ? P.src_h - NT + 1 : 0;
+    const bool sph = chain_has_sph(P.chain);
     if (generic) {
-        k_resample<METHOD, SrcT, DstT, A, RegT, true, false><<<grid, 256, 0, st>>>(P);
+        if (sph) k_resample<METHOD, SrcT, DstT, A, RegT, true, false, true><<<grid, 256, 0, st>>>(P);
+        else k_resample<METHOD, SrcT, DstT, A, RegT, true, false, false><<<grid, 256, 0, st>>>(P);
         *name = "k_resample<generic>";
     } else if (aff && !A::exact) {
         if constexpr (!A::exact) {
-            k_resample<METHOD, SrcT, DstT, Fast, RegT, false, true><<<grid, 256, 0, st>>>(P);
+            k_resample<METHOD, SrcT, DstT, Fast, RegT, false, true, false><<<grid, 256, 0, st>>>(P);
         }
         *name = "k_resample<trunc,affine>";
     } else {
-        k_resample<METHOD, SrcT, DstT, A, RegT, false, false><<<grid, 256, 0, st>>>(P);
+        if (sph) k_resample<METHOD, SrcT, DstT, A, RegT, false, false, true><<<grid, 256, 0, st>>>(P);
+        else k_resample<METHOD, SrcT, DstT, A, RegT, false, false, false><<<grid, 256, 0, st>>>(P);
         *name = "k_resample<trunc>";
     }
     count_launch();
@@ -683,8 +686,13 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
     P.flags = a->flags;
     P.fill = a->fillvalue;
     P.status = a->status_dev;
-    P.chain.n = a->n_ops; P.chain.pad = 0;
-    for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
+    P.chain.pad = 0;
+    if (a->precision == TFM_PREC_FAST32) {
+        P.chain.n = fuse_chain_fast(a->chain, a->n_ops, P.chain.ops);       // fast mode: peephole fusion
+    } else {
+        P.chain.n = a->n_ops;
+        for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
+    }
     int lw = 5;
     if ((a->tuning & 3) == 2) lw = 4;
     if ((a->tuning & 3) == 3) lw = 3;
@@ -735,8 +743,9 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         if (tex_ok) {
             dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 31) / 32), 1);
             if (grid.y > 65535u) return TFM_EUNSUPPORTED;
-            if (aff) k_resample_tex<Fast, true><<<grid, 256, 0, st>>>(P, tex);
-            else k_resample_tex<Fast, false><<<grid, 256, 0, st>>>(P, tex);
+            if (aff) k_resample_tex<Fast, true, false><<<grid, 256, 0, st>>>(P, tex);
+            else if (chain_has_sph(P.chain)) k_resample_tex<Fast, false, true><<<grid, 256, 0, st>>>(P, tex);
+            else k_resample_tex<Fast, false, false><<<grid, 256, 0, st>>>(P, tex);
             count_launch();
             name = aff ? "k_resample_tex<affine>" : "k_resample_tex";
             e = cudaGetLastError();
