@@ -345,8 +345,9 @@ def gpu_arm(args):
         for tn, nm in ((16, "ldg_gather"), (4 | 16, "ldg_gather_interpreted_chain")):
             brk["linear_affine_fp32_%s_ms" % nm] = timed(
                 lambda: tr_aff.resample(src, method="linear", precision="fp32", out=out_lin, tuning=tn))
-        brk["jacobian_radial_fp32_tile32x16_ms"] = timed(
-            lambda: tr_rad.resample(src, method="Gaussian", precision="fp32", out=out_jac, tuning=8), reps=3)
+        for tn, nm in ((8, "32x16"), (32, "32x8")):
+            brk["jacobian_radial_fp32_tile%s_ms" % nm] = timed(
+                lambda: tr_rad.resample(src, method="Gaussian", precision="fp32", out=out_jac, tuning=tn), reps=3)
         brk["nearest_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="nearest", precision="fp32", out=out_lin))
         brk["cubic_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="cubic", precision="fp32", out=out_lin))
         brk["linear_affine_fp64_parity_ms"] = timed(lambda: tr_aff.resample(src, method="linear", out=o64))

@@ -329,10 +329,14 @@ __device__ __forceinline__ void gauss_taps(const SrcT *p, long long pe, float w0
 
 // A: chain arithmetic; RegT: footprint arithmetic (double = parity mode, float = fast mode)
 template <class A, typename SrcT, typename DstT, typename RegT, int JTY, bool SPH>
-__global__ void __launch_bounds__(JTX * JTY, 1024 / (JTX * JTY))
+__global__ void __launch_bounds__(JTX * 8, 4)
 k_jacobian(const __grid_constant__ JacParams P)
 {
+    // 256 threads (32 x 8) cover a 32 x JTY tile, JTY in {8, 16, 32}: thread (tx,ty) owns pixels
+    // (tx, ty + 8j).  Taller tiles amortise the 2-point coordinate halo: evaluations per pixel are
+    // (36 x 12)/256 = 1.69 at JTY = 8, 1.41 at 16, 1.27 at 32.
     constexpr bool FASTI = (sizeof(RegT) == 4);
+    constexpr int NTH = JTX * 8;
     constexpr int PH = JTY + 4, CH = JTY + 3;
     __shared__ double2 s_p[PH][PW];                   // inverse-mapped (x,y) of grid points, interleaved
     __shared__ double s_m2[CH][CW];                   // Jmag2 per cell (helpers.pyx:1020)
@@ -354,7 +358,6 @@ k_jacobian(const __grid_constant__ JacParams P)
     // ---- 1. coordinates of the halo tile (points outside the grid are never used) ----
     // two points per interpreter dispatch (chain_eval_n): i and i + nthreads
     {
-        constexpr int NTH = JTX * JTY;
         for (int i = tid; i < PW * PH; i += 2 * NTH) {
             double x[2], y[2];
             int pi[2], pj[2];
@@ -378,7 +381,7 @@ k_jacobian(const __grid_constant__ JacParams P)
     __syncthreads();
 
     // ---- 2. Jmag2 per cell: cell (ci,cj) spans points (ci..ci+1, cj..cj+1) ----
-    for (int i = tid; i < CW * CH; i += JTX * JTY) {
+    for (int i = tid; i < CW * CH; i += NTH) {
         const int cj = i / CW, ci = i - cj * CW;
         const double2 pa = s_p[cj + 1][ci + 1], pb = s_p[cj + 1][ci], pc = s_p[cj][ci + 1], pd = s_p[cj][ci];
         const double ax = pa.x, bx = pb.x, cx = pc.x, dx = pd.x, ay = pa.y, by = pb.y, cy = pc.y, dy = pd.y;
@@ -398,7 +401,7 @@ k_jacobian(const __grid_constant__ JacParams P)
     const int NCX = GW - 1, NCY = GH - 1;              // cell grid extent
     const int wx0 = (int)WX0, wy0 = (int)WY0;
     const float thr_f = (float)P.jump_thresh;
-    for (int i = tid; i < (JTX + 1) * (JTY + 1); i += JTX * JTY) {
+    for (int i = tid; i < (JTX + 1) * (JTY + 1); i += NTH) {
         const int fj = i / (JTX + 1), fi = i - fj * (JTX + 1);
         const int ci = fi + 1, cj = fj + 1;            // index into s_m2 (cell halo of 1)
         const int gcx = wx0 + ci, gcy = wy0 + cj;      // global cell index
@@ -423,8 +426,13 @@ k_jacobian(const __grid_constant__ JacParams P)
     __syncthreads();
 
     // ---- 4. per pixel: grid-centred Jacobian, SVD padding, footprint ----
-    const int X = blockIdx.x * JTX + threadIdx.x, Y = blockIdx.y * JTY + threadIdx.y;
-    if (X >= P.dst_w || Y >= P.dst_h) return;
+    int state = 0;
+    const int X = blockIdx.x * JTX + threadIdx.x;
+#pragma unroll 1
+    for (int jrow = 0; jrow < JTY / 8; ++jrow) {
+    const int ly = threadIdx.y + 8 * jrow;              // row inside the tile
+    const int Y = blockIdx.y * JTY + ly;
+    if (X >= P.dst_w || Y >= P.dst_h) continue;
     const long long gx = P.dst_x0 + X, gy = P.dst_y0 + Y;
     // edge rows/columns copy their inner neighbour (helpers.pyx:1244-1247): clamp to [1, G-2]
     long long jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
@@ -470,13 +478,12 @@ k_jacobian(const __grid_constant__ JacParams P)
         for (int k = 0; k < 4; ++k) Ji[k] = __ddiv_rn(Ji[k], denom);
     }
 
-    const double2 pme = s_p[threadIdx.y + 2 + shy][threadIdx.x + 2 + shx];
+    const double2 pme = s_p[ly + 2 + shy][threadIdx.x + 2 + shx];
     const double px = pme.x, py = pme.y;
     DstT *drow = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch);
-    if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) { drow[X] = (DstT)0; return; }
+    if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) { drow[X] = (DstT)0; continue; }
     const double fxs = floor(px), fys = floor(py);
     const long long xs = (long long)fxs, ys = (long long)fys;
-    int state = 0;
 
     if constexpr (!FASTI) {
         // ------------------------- parity mode: the reference's loop, in its order -------------
@@ -548,7 +555,7 @@ k_jacobian(const __grid_constant__ JacParams P)
         // pixel is 0 whatever the weights are (helpers.pyx:1793-1800)
         const bool all_out = (P.bound_x == TFM_B_TRUNCATE && (xs + half < 0 || xs - half >= P.full_w)) ||
                              (P.bound_y == TFM_B_TRUNCATE && (ys + half < 0 || ys - half >= P.full_h));
-        if (all_out) { drow[X] = (DstT)0; return; }
+        if (all_out) { drow[X] = (DstT)0; continue; }
         const long long pe = P.src_pitch / (long long)sizeof(SrcT);
         const float L2E = 1.4426950408889634f;
         const float Aq = q00 * iob * iob * L2E, Bq = q01 * iob * iob * L2E, Cq = q11 * iob * iob * L2E;
@@ -600,6 +607,7 @@ k_jacobian(const __grid_constant__ JacParams P)
         }
         drow[X] = (DstT)((wgt > 0) ? val * fast_rcp(wgt) : 0.0f);
     }
+    }   // jrow
     if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
 }
 
@@ -682,17 +690,19 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     }
 
     const bool sph = chain_has_sph(P.chain);
-    const int jty = (!sph && (a->tuning & 8)) ? 16 : 8;       // 32x8 tiles (4 CTAs/SM) measured 7% faster than 32x16
+    // tile height: 32 by default (4 pixels per thread); tuning bits 8 / 32 select 16 / 8 for A/B runs
+    const int jty = sph ? 8 : ((a->tuning & 32) ? 8 : ((a->tuning & 8) ? 16 : 32));
     dim3 grid((unsigned)((P.dst_w + JTX - 1) / JTX), (unsigned)((P.dst_h + jty - 1) / jty),
               (unsigned)P.n_planes);
     if (grid.y > 65535u) return TFM_EUNSUPPORTED;
-    dim3 block(JTX, jty);
+    dim3 block(JTX, 8);
     const char *name;
-#define TFM_JLAUNCH(AA, ST, DT, RT)                                              \
-    do {                                                                         \
-        if (sph) k_jacobian<AA, ST, DT, RT, 8, true><<<grid, block, 0, st>>>(P);          \
-        else if (jty == 8) k_jacobian<AA, ST, DT, RT, 8, false><<<grid, block, 0, st>>>(P); \
-        else k_jacobian<AA, ST, DT, RT, 16, false><<<grid, block, 0, st>>>(P);              \
+#define TFM_JLAUNCH(AA, ST, DT, RT)                                                          \
+    do {                                                                                     \
+        if (sph) k_jacobian<AA, ST, DT, RT, 8, true><<<grid, block, 0, st>>>(P);              \
+        else if (jty == 8) k_jacobian<AA, ST, DT, RT, 8, false><<<grid, block, 0, st>>>(P);   \
+        else if (jty == 16) k_jacobian<AA, ST, DT, RT, 16, false><<<grid, block, 0, st>>>(P); \
+        else k_jacobian<AA, ST, DT, RT, 32, false><<<grid, block, 0, st>>>(P);                \
     } while (0)
     if (a->precision == TFM_PREC_EXACT64) {
         if (s.dtype == TFM_F32 && d.dtype == TFM_F64) TFM_JLAUNCH(Exact, float, double, double);
