@@ -24,6 +24,10 @@ cpu_baseline / --impl reference : the reference's CPU path (oracle/cpu_baseline.
 import argparse
 import json
 import os
+
+# keep stdout to exactly one JSON line: NCCL prints its version banner there at VERSION level
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 import subprocess
 import sys
 import threading
@@ -252,6 +256,10 @@ def gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    # NCCL writes its version banner to stdout; park stdout on stderr until the JSON line is due
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         # keep stdout to exactly one JSON line: NCCL prints its version banner there at VERSION level
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -397,7 +405,10 @@ def gpu_arm(args):
                           % (cb["px_lin"] // n, "reference's compiled helpers module" if cb["kind"] == "reference"
                              else "oracle port", cb["px_jac"] // n, nproc),
                 "linear_mpix_s": cb["linear_mpix_s"], "jacobian_mpix_s": cb["jacobian_mpix_s"]}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -428,6 +428,13 @@ k_resample(const __grid_constant__ ResampleParams P)
             fracy[j] = __dsub_rn(y, fy);
             ffx[j] = (float)fracx[j];
             ffy[j] = (float)fracy[j];
+            if (FASTI && fabs(x) < 1.0e9 && fabs(y) < 1.0e9) {
+                // every fast-mode variant (LDG gather, texture gather, this generic one) must round the
+                // fp32 fraction identically, so that a sharded run reproduces the unsharded one bit for bit
+                int iu;
+                floor_frac_fast(x, iu, ffx[j]);
+                floor_frac_fast(y, iu, ffy[j]);
+            }
             // |f| >= 2^51 (or NaN): the reference's float tap offsets are absorbed / invalid; every
             // tap shares the base index ("absurd coordinates").
             const bool okx = fabs(fx) < 2.0e15, oky = fabs(fy) < 2.0e15;
@@ -594,7 +601,13 @@ static cudaError_t launch2(ResampleParams &P, bool generic, bool aff, cudaStream
     P.int_h = P.src_h - NT + 1 > 0 ? P.src_h - NT + 1 : 0;
     const bool sph = chain_has_sph(P.chain);
     if (generic) {
-        if (sph) k_resample<METHOD, SrcT, DstT, A, RegT, true, false, true><<<grid, 256, 0, st>>>(P);
+        if (aff && !A::exact) {
+            // same host-composed coordinates as the non-generic fast kernels: a staged shard must
+            // reproduce the unsharded fast-mode result bit for bit
+            if constexpr (!A::exact) {
+                k_resample<METHOD, SrcT, DstT, Fast, RegT, true, true, false><<<grid, 256, 0, st>>>(P);
+            }
+        } else if (sph) k_resample<METHOD, SrcT, DstT, A, RegT, true, false, true><<<grid, 256, 0, st>>>(P);
         else k_resample<METHOD, SrcT, DstT, A, RegT, true, false, false><<<grid, 256, 0, st>>>(P);
         *name = "k_resample<generic>";
     } else if (aff && !A::exact) {
