@@ -230,6 +230,22 @@ typedef struct tfm_apply_args {
 
 TFM_API int tfm_apply(const tfm_apply_args *args, void *stream);
 
+/* ---- the Jacobian helpers the reference exposes as module functions (2-D case) ----
+ * All pointers are device pointers, arrays dense and row-major, float64 (flags int64 like NumPy's int).
+ * tfm_simple_jacobian  replaces simple_jacobian(index)            helpers.pyx:846-958 (2-D: 896-906)
+ *     index[ny][nx][2] -> Js[ny-1][nx-1][2][2],  Js[...,i,j] = d coord_i / d pix_j
+ * tfm_jump_detect      replaces jump_detect(Js, jump_thresh)      helpers.pyx:960-1141 (N-D branch, N=2)
+ *     Js[ncy][ncx][2][2] -> flags[ncy][ncx] (1 = ok, 0 = jump); scratch: ncy*ncx doubles.
+ *     Repair R12: upper-edge results land on the true upper edge.
+ * tfm_jacobian_grid    replaces the 2-D branch of jacobian(index) helpers.pyx:1225-1247, with the
+ *     repairs that make it return (R1, R2, R11): cells Js[ny-1][nx-1][2][2] and flags (or NULL for
+ *     no jump detection) -> grid-centred J[ny][nx][2][2]; edge rows/columns copy their neighbour. */
+TFM_API int tfm_simple_jacobian(const double *index, int64_t ny, int64_t nx, double *Js, void *stream);
+TFM_API int tfm_jump_detect(const double *Js, int64_t ncy, int64_t ncx, double jump_thresh, int64_t *flags,
+                    double *scratch, void *stream);
+TFM_API int tfm_jacobian_grid(const double *Js, const int64_t *flags, int64_t ny, int64_t nx, double *J,
+                      void *stream);
+
 /* ---- host-side test hooks mirroring helpers.pyx:1807-1810 (svd2x2 / svc2x2) ----
  * M, U, V: 4 doubles row-major; s: 2 doubles.  Run the device routines on one matrix on the
  * current device and copy the result back (used by parity tests only). */

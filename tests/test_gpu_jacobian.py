@@ -131,3 +131,32 @@ def test_svd_hooks(tfm, oracle):
     tfm.svd2x2(M, U, s, V)
     tfm.svc2x2(V, 1.0 / s, U, M2)
     assert np.all(np.isclose(np.matmul(M, M2), np.eye(2), 1e-8))
+
+
+def test_jacobian_helper_entry_points(tfm, oracle):
+    """simple_jacobian / jump_detect / jacobian as callable GPU entry points (helpers.pyx:846-1290):
+    bit-exact against the oracle, and against the reference's golden vectors on the square fixture."""
+    from test_oracle_golden import GOLD
+    sq = GOLD["jac/coords_sq"]
+    Js = tfm.simple_jacobian(sq)
+    assert np.array_equal(Js, oracle.simple_jacobian(sq))
+    assert np.array_equal(tfm.jump_detect(Js, 4.0), GOLD["jac/jump4_sq"])
+    assert np.array_equal(tfm.jump_detect(Js, 1.2), GOLD["jac/jump1p2_sq"])
+    ns = GOLD["jac/coords"]                                   # non-square: oracle (with repair R12)
+    Jn = tfm.simple_jacobian(ns)
+    assert np.array_equal(Jn, GOLD["jac/simple"])
+    for thr in (10, 4.0, 1.2):
+        assert np.array_equal(tfm.jump_detect(Jn, thr), oracle.jump_detect(Jn, thr))
+    for kw, okw in ((dict(), dict(jump_thresh=10.)), (dict(jump_thresh=1.2), dict(jump_thresh=1.2)),
+                    (dict(jump_detect=False), dict(jump_thresh=0))):
+        assert np.array_equal(tfm.jacobian(ns, **kw), oracle.jacobian(ns, **okw)), kw
+    # reference KATs (tests/test_03_helpers.py:380-402, 632-645)
+    grid = np.zeros([5, 5, 2])
+    grid[1, 2, 0] = 1
+    grid[2, 2, 1] = 0.5
+    jf = tfm.jump_detect(tfm.simple_jacobian(grid))
+    assert np.all(jf == [[1, 1, 1, 1], [1, 1, 1, 1], [1, 0, 0, 1], [1, 1, 1, 1]])
+    with pytest.raises(ValueError):
+        tfm.simple_jacobian(np.zeros((1, 10, 2)))
+    with pytest.raises(NotImplementedError):
+        tfm.simple_jacobian(np.zeros((4, 4, 4, 3)))

@@ -51,6 +51,23 @@ int tfm_apply(const tfm_apply_args *args, void *stream)
     return tfm::apply_dispatch(args, static_cast<cudaStream_t>(stream));
 }
 
+int tfm_simple_jacobian(const double *index, int64_t ny, int64_t nx, double *Js, void *stream)
+{
+    return tfm::jacobian_helpers(0, index, nullptr, ny, nx, 0.0, Js, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int tfm_jump_detect(const double *Js, int64_t ncy, int64_t ncx, double jump_thresh, int64_t *flags,
+                    double *scratch, void *stream)
+{
+    return tfm::jacobian_helpers(1, Js, nullptr, ncy, ncx, jump_thresh, flags, scratch,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int tfm_jacobian_grid(const double *Js, const int64_t *flags, int64_t ny, int64_t nx, double *J, void *stream)
+{
+    return tfm::jacobian_helpers(2, Js, flags, ny, nx, 0.0, J, nullptr, static_cast<cudaStream_t>(stream));
+}
+
 int tfm_svd2x2(const double *M, double *U, double *s, double *V)
 {
     if (!M || !U || !s || !V) return TFM_EVALUE;

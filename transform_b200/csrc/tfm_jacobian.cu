@@ -611,6 +611,96 @@ k_jacobian(const __grid_constant__ JacParams P)
     if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stand-alone entry points for the three Jacobian helpers the reference exposes as module functions
+// (helpers.pyx:846-958 simple_jacobian, 960-1141 jump_detect, 1145-1290 jacobian), 2-D case.  They
+// share the arithmetic of the fused kernel above (same differences, same selection networks, same
+// summation order) but work on arrays in global memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_simple_jacobian(const double2 *idx, int ny, int nx, double *Js)
+{
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (cx >= nx - 1 || cy >= ny - 1) return;
+    const double2 pa = idx[(long long)(cy + 1) * nx + cx + 1], pb = idx[(long long)(cy + 1) * nx + cx];
+    const double2 pc = idx[(long long)cy * nx + cx + 1], pd = idx[(long long)cy * nx + cx];
+    double *o = Js + ((long long)cy * (nx - 1) + cx) * 4;
+    o[0] = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(pa.x, pb.x), pc.x), pd.x), 0.5);    // d x / d pix_x
+    o[1] = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(pa.x, pb.x), pc.x), pd.x), 0.5);    // d x / d pix_y
+    o[2] = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(pa.y, pb.y), pc.y), pd.y), 0.5);    // d y / d pix_x
+    o[3] = __dmul_rn(__dsub_rn(__dsub_rn(__dadd_rn(pa.y, pb.y), pc.y), pd.y), 0.5);    // d y / d pix_y
+}
+
+__global__ void k_jmag2(const double *Js, long long n, double *m2)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *j = Js + i * 4;
+    m2[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(j[0], j[0]), __dmul_rn(j[1], j[1])),
+                                __dmul_rn(j[2], j[2])), __dmul_rn(j[3], j[3]));
+}
+
+__global__ void k_jump_detect(const double *m2, int ncy, int ncx, double thresh, long long *flags)
+{
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (cx >= ncx || cy >= ncy) return;
+    flags[(long long)cy * ncx + cx] = jump_flag_exact(m2, ncx, cx, cy, cx, cy, ncx, ncy, thresh);
+}
+
+__global__ void k_jacobian_grid(const double *Js, const long long *flags, int ny, int nx, double *J)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    // edge rows / columns copy their inner neighbour (helpers.pyx:1244-1247)
+    const int jx = x < 1 ? 1 : (x > nx - 2 ? nx - 2 : x), jy = y < 1 ? 1 : (y > ny - 2 ? ny - 2 : y);
+    const int ncx = nx - 1;
+    double acc[4] = {0, 0, 0, 0};
+    int nvalid = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {          // cells (y-1,x-1) + (y,x-1) + (y-1,x) + (y,x), helpers.pyx:1227-1231
+        const int cx = jx - 1 + (k >> 1), cy = jy - 1 + (k & 1);
+        const long long c = (long long)cy * ncx + cx;
+        const bool ok = flags ? (flags[c] != 0) : true;
+        nvalid += ok ? 1 : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double v = ok ? Js[c * 4 + q] : 0.0;
+            acc[q] = (k == 0) ? v : __dadd_rn(acc[q], v);
+        }
+    }
+    const double denom = flags ? (double)(nvalid < 1 ? 1 : nvalid) : 4.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) J[((long long)y * nx + x) * 4 + q] = __ddiv_rn(acc[q], denom);
+}
+
+int jacobian_helpers(int which, const void *in0, const void *in1, long long ny, long long nx, double thresh,
+                     void *out, void *scratch, cudaStream_t st)
+{
+    if (ny < 2 || nx < 2 || ny > 0x3fffffff || nx > 0x3fffffff || !in0 || !out) return TFM_EVALUE;
+    dim3 block(32, 8);
+    if (which == 0) {                       // simple_jacobian: index[ny][nx][2] -> Js[ny-1][nx-1][2][2]
+        dim3 grid((unsigned)((nx - 1 + 31) / 32), (unsigned)((ny - 1 + 7) / 8));
+        k_simple_jacobian<<<grid, block, 0, st>>>(static_cast<const double2 *>(in0), (int)ny, (int)nx,
+                                                  static_cast<double *>(out));
+    } else if (which == 1) {                // jump_detect: Js[ny][nx][2][2] (cell grid) -> flags[ny][nx] (int64)
+        if (!scratch) return TFM_EVALUE;
+        const long long n = ny * nx;
+        k_jmag2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const double *>(in0), n,
+                                                              static_cast<double *>(scratch));
+        count_launch();
+        dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + 7) / 8));
+        k_jump_detect<<<grid, block, 0, st>>>(static_cast<const double *>(scratch), (int)ny, (int)nx, thresh,
+                                              static_cast<long long *>(out));
+    } else {                                // jacobian: Js (cells), flags|NULL -> J[ny][nx][2][2] (grid points)
+        if (ny < 3 || nx < 3) return TFM_EVALUE;
+        dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + 7) / 8));
+        k_jacobian_grid<<<grid, block, 0, st>>>(static_cast<const double *>(in0), static_cast<const long long *>(in1),
+                                                (int)ny, (int)nx, static_cast<double *>(out));
+    }
+    count_launch();
+    set_last_kernel(which == 0 ? "k_simple_jacobian" : (which == 1 ? "k_jump_detect" : "k_jacobian_grid"));
+    return cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
+}
+
 __global__ void k_svd_hook(int which, const double *in, double *out)
 {
     if (which == 0) svd2x2_dev(in, out, out + 4, out + 6);          // M -> U, s, V
