@@ -236,11 +236,139 @@ static inline bool chain_has_sph(const ChainDev &ch)
     return false;
 }
 
-// Host-side fast-mode peephole pass: copy `ops` into `out`, fusing adjacent spherical WCS pairs.
+// Internal opcode (never crosses the C ABI): [affine..., Radial reverse, affine...] at the START of a
+// chain, i.e. a polar / log-polar unwrap seen from the output pixel grid.  Angle and radius argument
+// are affine in the pixel indices, theta = tX X + tY Y + t0, rho = a10 X + a11 Y + b1, so inside a
+// tile cos/sin(theta) follow from two small tables by the angle-addition formulas (and exp(rho)
+// from two tables by exp(a+b) = exp(a) exp(b)): the resample kernels evaluate 2 x (tile edge)
+// sincos per TILE instead of one per grid point.  op_polar is the direct form used elsewhere.
+//   p[0..3] A1  p[4..5] b1  p[6] ang_coeff  p[7] r0  p[8..9] origin  p[10..13] A2  p[14..15] b2
+//   flags: TFM_RAD_CCW, TFM_RAD_R0_NOT_NONE, TFM_POLAR_HAS_A2
+#define TFM_OP_POLAR 101
+#define TFM_POLAR_HAS_A2 32
+
+__device__ __forceinline__ void polar_finish(const tfm_op &op, double c, double s, double r, double &x, double &y)
+{
+    if (!(op.flags & TFM_RAD_CCW)) s = -s;
+    const double x1 = c * r + op.p[8], y1 = s * r + op.p[9];
+    if (op.flags & TFM_POLAR_HAS_A2) {
+        x = fma(op.p[10], x1, fma(op.p[11], y1, op.p[14]));
+        y = fma(op.p[12], x1, fma(op.p[13], y1, op.p[15]));
+    } else {
+        x = x1;
+        y = y1;
+    }
+}
+
+__device__ __forceinline__ void op_polar(const tfm_op &op, double &x, double &y)
+{
+    const double u = fma(op.p[0], x, fma(op.p[1], y, op.p[4]));
+    const double v = fma(op.p[2], x, fma(op.p[3], y, op.p[5]));
+    double s, c;
+    sincos(u * op.p[6], &s, &c);
+    const double r = (op.flags & TFM_RAD_R0_NOT_NONE) ? op.p[7] * exp(v) : v;
+    polar_finish(op, c, s, r, x, y);
+}
+
+// Per-tile tables for TFM_OP_POLAR.  ta[i] = (cos, sin)(i tX), tb[j] = (cos, sin)(theta(X0,Y0) + j tY);
+// ea[i] = exp(i a10), eb[j] = r0 exp(rho(X0,Y0) + j a11) for the log-polar form.  Call with all
+// threads of the CTA, then __syncthreads().
+__device__ __forceinline__ void polar_tables(const tfm_op &op, double X0, double Y0, int ni, int nj,
+                                             double2 *ta, double2 *tb, double *ea, double *eb,
+                                             int tid, int nthreads)
+{
+    const double coeff = op.p[6];
+    const double tX = op.p[0] * coeff, tY = op.p[1] * coeff;
+    const double t0 = fma(op.p[0], X0, fma(op.p[1], Y0, op.p[4])) * coeff;
+    const bool lg = (op.flags & TFM_RAD_R0_NOT_NONE) != 0;
+    const double rho0 = fma(op.p[2], X0, fma(op.p[3], Y0, op.p[5]));
+    for (int k = tid; k < ni + nj; k += nthreads) {
+        double s, c;
+        if (k < ni) {
+            sincos((double)k * tX, &s, &c);
+            ta[k] = make_double2(c, s);
+            if (lg) ea[k] = exp((double)k * op.p[2]);
+        } else {
+            const int j = k - ni;
+            sincos(fma((double)j, tY, t0), &s, &c);
+            tb[j] = make_double2(c, s);
+            if (lg) eb[j] = op.p[7] * exp(fma((double)j, op.p[3], rho0));
+        }
+    }
+}
+
+// coordinates of local grid point (i, j) of the tile whose tables were built for origin (X0, Y0)
+__device__ __forceinline__ void polar_from_tables(const tfm_op &op, double X0, double Y0, int i, int j,
+                                                  const double2 *ta, const double2 *tb, const double *ea,
+                                                  const double *eb, double &x, double &y)
+{
+    const double2 a = ta[i], b = tb[j];
+    const double c = a.x * b.x - a.y * b.y, s = a.y * b.x + a.x * b.y;
+    double r;
+    if (op.flags & TFM_RAD_R0_NOT_NONE) r = ea[i] * eb[j];
+    else r = fma(op.p[2], X0 + (double)i, fma(op.p[3], Y0 + (double)j, op.p[5]));
+    polar_finish(op, c, s, r, x, y);
+}
+
+// Compose LINEAR / IDENTITY ops [i0, i1) into out = A.in + b (fp64, host).  Parameter preparation,
+// a handful of flops per call -- not part of the data path.  The fp64-exact mode never pre-fuses.
+static inline void compose_linear_run(const tfm_op *ops, int i0, int i1, double *A4, double *b2)
+{
+    double a00 = 1, a01 = 0, a10 = 0, a11 = 1, b0 = 0, b1 = 0;
+    for (int i = i0; i < i1; ++i) {
+        const tfm_op &op = ops[i];
+        if (op.kind != TFM_OP_LINEAR) continue;
+        const bool fwd = (op.dir == TFM_FWD);
+        const int f = op.flags;
+        double m00 = 1, m01 = 0, m10 = 0, m11 = 1;
+        if (f & TFM_LIN_HAS_MATRIX) { m00 = op.p[0]; m01 = op.p[1]; m10 = op.p[2]; m11 = op.p[3]; }
+        double pa0 = 0, pa1 = 0, pb0 = 0, pb1 = 0;      // out = M.(in + pa) + pb
+        if (fwd) {
+            if (f & TFM_LIN_HAS_PRE) { pa0 = op.p[4]; pa1 = op.p[5]; }
+            if (f & TFM_LIN_HAS_POST) { pb0 = op.p[6]; pb1 = op.p[7]; }
+        } else {
+            if (f & TFM_LIN_HAS_POST) { pa0 = -op.p[6]; pa1 = -op.p[7]; }
+            if (f & TFM_LIN_HAS_PRE) { pb0 = -op.p[4]; pb1 = -op.p[5]; }
+        }
+        const double c0 = b0 + pa0, c1 = b1 + pa1;
+        const double n00 = m00 * a00 + m01 * a10, n01 = m00 * a01 + m01 * a11;
+        const double n10 = m10 * a00 + m11 * a10, n11 = m10 * a01 + m11 * a11;
+        b0 = m00 * c0 + m01 * c1 + pb0;
+        b1 = m10 * c0 + m11 * c1 + pb1;
+        a00 = n00; a01 = n01; a10 = n10; a11 = n11;
+    }
+    A4[0] = a00; A4[1] = a01; A4[2] = a10; A4[3] = a11; b2[0] = b0; b2[1] = b1;
+}
+
+static inline bool is_linear_like(const tfm_op &op) { return op.kind == TFM_OP_LINEAR || op.kind == TFM_OP_IDENTITY; }
+
+// Host-side fast-mode peephole pass: copy `ops` into `out`, fusing (a) a leading
+// [affine..., Radial reverse, affine...] run into one TFM_OP_POLAR and (b) adjacent spherical WCS pairs.
 static inline int fuse_chain_fast(const tfm_op *ops, int n, tfm_op *out)
 {
-    int m = 0;
-    for (int i = 0; i < n; ++i) {
+    int m = 0, i = 0;
+    {   // (a) polar prefix
+        int k = 0;
+        while (k < n && is_linear_like(ops[k])) ++k;
+        if (k < n && ops[k].kind == TFM_OP_RADIAL && ops[k].dir == TFM_REV) {
+            int e = k + 1;
+            while (e < n && is_linear_like(ops[e])) ++e;
+            tfm_op f;
+            f.kind = TFM_OP_POLAR; f.dir = TFM_FWD; f.reserved = 0;
+            for (int q = 0; q < TFM_OP_NPARAM; ++q) f.p[q] = 0.0;
+            compose_linear_run(ops, 0, k, f.p + 0, f.p + 4);
+            const tfm_op &r = ops[k];
+            f.p[6] = r.p[3]; f.p[7] = r.p[2]; f.p[8] = r.p[0]; f.p[9] = r.p[1];
+            f.flags = r.flags & (TFM_RAD_CCW | TFM_RAD_R0_NOT_NONE);
+            if (e > k + 1) {
+                compose_linear_run(ops, k + 1, e, f.p + 10, f.p + 14);
+                f.flags |= TFM_POLAR_HAS_A2;
+            }
+            out[m++] = f;
+            i = e;
+        }
+    }
+    for (; i < n; ++i) {
         const tfm_op &a = ops[i];
         if (i + 1 < n && a.kind == TFM_OP_WCS && a.dir == TFM_FWD && (a.flags & 0xff) != TFM_WCS_PROJ_NONE &&
             ops[i + 1].kind == TFM_OP_WCS && ops[i + 1].dir == TFM_REV &&
@@ -290,15 +418,16 @@ __device__ __forceinline__ void op_index(const tfm_op &op, double &x, double &y)
 // costs the others registers (measured +7% on the Jacobian kernel), out of line it spills the
 // interpreter's state to the stack (measured 2x on the parity-mode linear kernel).
 template <class A, bool SPH>
-__device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double &y)
+__device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double &y, int first = 0)
 {
-    for (int i = 0; i < ch.n; ++i) {
+    for (int i = first; i < ch.n; ++i) {
         const tfm_op &op = ch.ops[i];
         switch (op.kind) {
         case TFM_OP_LINEAR: op_linear<A>(op, x, y); break;
         case TFM_OP_RADIAL: op_radial<A>(op, x, y); break;
         case TFM_OP_WCS: if constexpr (SPH) op_wcs<A>(op, x, y); break;
         case TFM_OP_WCS_PAIR: if constexpr (SPH) op_wcs_pair(op, x, y); break;
+        case TFM_OP_POLAR: op_polar(op, x, y); break;
         case TFM_OP_INDEX: op_index(op, x, y); break;
         default: break;                                     // identity
         }
@@ -308,9 +437,9 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
 // ---- N-wide evaluation: the interpreter's dispatch (constant loads, flag tests, branches) is paid
 // once per op per THREAD instead of once per op per pixel; the per-pixel work is the arithmetic only.
 template <class A, bool SPH, int N>
-__device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N], double (&y)[N])
+__device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N], double (&y)[N], int first = 0)
 {
-    for (int i = 0; i < ch.n; ++i) {
+    for (int i = first; i < ch.n; ++i) {
         const tfm_op &op = ch.ops[i];
         const int f = op.flags;
         switch (op.kind) {
@@ -365,6 +494,10 @@ __device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N],
 #pragma unroll
                 for (int k = 0; k < N; ++k) op_wcs_pair(op, x[k], y[k]);
             }
+            break;
+        case TFM_OP_POLAR:
+#pragma unroll
+            for (int k = 0; k < N; ++k) op_polar(op, x[k], y[k]);
             break;
         case TFM_OP_INDEX:
 #pragma unroll

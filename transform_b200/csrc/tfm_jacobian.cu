@@ -356,8 +356,24 @@ k_jacobian(const __grid_constant__ JacParams P)
     const long long WX0 = GX0 - 2 - shx, WY0 = GY0 - 2 - shy;
 
     // ---- 1. coordinates of the halo tile (points outside the grid are never used) ----
-    // two points per interpreter dispatch (chain_eval_n): i and i + nthreads
-    {
+    __shared__ double2 s_ta[PW], s_tb[PH];            // polar chains: per-tile angle tables
+    __shared__ double s_ea[PW], s_eb[PH];             //               and radius (log-polar) tables
+    const bool polar = FASTI && P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_POLAR;
+    if (polar) {
+        // [affine, Radial reverse, affine] prefix: angle and radius are affine in the grid indices, so
+        // PW + PH sincos per tile (angle addition) replace PW x PH of them
+        const tfm_op &op0 = P.chain.ops[0];
+        polar_tables(op0, (double)WX0, (double)WY0, PW, PH, s_ta, s_tb, s_ea, s_eb, tid, NTH);
+        __syncthreads();
+        for (int i = tid; i < PW * PH; i += NTH) {
+            const int pj = i / PW, pi = i - pj * PW;
+            double x, y;
+            polar_from_tables(op0, (double)WX0, (double)WY0, pi, pj, s_ta, s_tb, s_ea, s_eb, x, y);
+            chain_eval<A, SPH>(P.chain, x, y, 1);
+            s_p[pj][pi] = make_double2(x, y);
+        }
+    } else {
+        // two points per interpreter dispatch (chain_eval_n): i and i + nthreads
         for (int i = tid; i < PW * PH; i += 2 * NTH) {
             double x[2], y[2];
             int pi[2], pj[2];

@@ -503,6 +503,19 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
             cx[j] = fma((double)(8 * j), P.aff[1], bx);
             cy[j] = fma((double)(8 * j), P.aff[3], by);
         }
+    } else if (P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_POLAR) {
+        // polar prefix: 32 + 32 sincos per tile through the angle-addition tables (tfm_chain.cuh)
+        __shared__ double2 s_ta[32], s_tb[32];
+        __shared__ double s_ea[32], s_eb[32];
+        const tfm_op &op0 = P.chain.ops[0];
+        const double TX0 = (double)(P.dst_x0 + (long long)blockIdx.x * 32);
+        const double TY0 = (double)(P.dst_y0 + (long long)blockIdx.y * 32);
+        polar_tables(op0, TX0, TY0, 32, 32, s_ta, s_tb, s_ea, s_eb, threadIdx.x, 256);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NPX; ++j)
+            polar_from_tables(op0, TX0, TY0, px, py + 8 * j, s_ta, s_tb, s_ea, s_eb, cx[j], cy[j]);
+        chain_eval_n<A, SPH, NPX>(P.chain, cx, cy, 1);
     } else {
 #pragma unroll
         for (int j = 0; j < NPX; ++j) {
@@ -640,31 +653,9 @@ static cudaError_t launch1(int method, ResampleParams &P, bool generic, bool aff
 // host, a handful of flops per call -- not part of the data path.
 static bool compose_affine(const tfm_op *ops, int n, double *aff)
 {
-    double a00 = 1, a01 = 0, a10 = 0, a11 = 1, b0 = 0, b1 = 0;
-    for (int i = 0; i < n; ++i) {
-        const tfm_op &op = ops[i];
-        if (op.kind == TFM_OP_IDENTITY) continue;
-        if (op.kind != TFM_OP_LINEAR) return false;
-        const bool fwd = (op.dir == TFM_FWD);
-        const int f = op.flags;
-        double m00 = 1, m01 = 0, m10 = 0, m11 = 1;
-        if (f & TFM_LIN_HAS_MATRIX) { m00 = op.p[0]; m01 = op.p[1]; m10 = op.p[2]; m11 = op.p[3]; }
-        double pa0 = 0, pa1 = 0, pb0 = 0, pb1 = 0;      // out = M.(in + pa) + pb
-        if (fwd) {
-            if (f & TFM_LIN_HAS_PRE) { pa0 = op.p[4]; pa1 = op.p[5]; }
-            if (f & TFM_LIN_HAS_POST) { pb0 = op.p[6]; pb1 = op.p[7]; }
-        } else {
-            if (f & TFM_LIN_HAS_POST) { pa0 = -op.p[6]; pa1 = -op.p[7]; }
-            if (f & TFM_LIN_HAS_PRE) { pb0 = -op.p[4]; pb1 = -op.p[5]; }
-        }
-        const double c0 = b0 + pa0, c1 = b1 + pa1;      // (A x + b) + pa
-        const double n00 = m00 * a00 + m01 * a10, n01 = m00 * a01 + m01 * a11;
-        const double n10 = m10 * a00 + m11 * a10, n11 = m10 * a01 + m11 * a11;
-        b0 = m00 * c0 + m01 * c1 + pb0;
-        b1 = m10 * c0 + m11 * c1 + pb1;
-        a00 = n00; a01 = n01; a10 = n10; a11 = n11;
-    }
-    aff[0] = a00; aff[1] = a01; aff[2] = a10; aff[3] = a11; aff[4] = b0; aff[5] = b1;
+    for (int i = 0; i < n; ++i)
+        if (!is_linear_like(ops[i])) return false;
+    compose_linear_run(ops, 0, n, aff, aff + 4);
     return true;
 }
 
