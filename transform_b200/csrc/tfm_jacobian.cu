@@ -310,7 +310,7 @@ template <int HALF, typename SrcT>
 __device__ __forceinline__ void gauss_taps(const SrcT *p, long long pe, float w0, float r0, float rb,
                                            float cA, float cB, float cC, float &val, float &wgt)
 {
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 2 * HALF + 1; ++j) {
         float w = w0, r = r0;
 #pragma unroll
