@@ -143,7 +143,7 @@ def reference_arm(args):
     budget = 150.0 / max(1, args.steps + args.warmup)           # seconds per step
     rl = max(nproc, int(0.5 * budget * (cal["px_lin"] / cal["t_lin"]) / N_IMG))
     rj = max(nproc, int(0.5 * budget * (cal["px_jac"] / cal["t_jac"]) / N_IMG))
-    rl, rj = min(rl, 1024), min(rj, 256)
+    rl, rj = min(rl, 4096), min(rj, 1024)
     for _ in range(args.warmup):
         cpu_sample(rl, rj, nproc)
     vals, t0 = [], time.perf_counter()
@@ -397,7 +397,8 @@ def gpu_arm(args):
                 "gpu_launches": int(launches), "clocks": clk.summary(), "breakdown": brk}
         if world == 1 and not args.no_cpu:
             nproc = os.cpu_count() or 1
-            cb = cpu_sample(nproc * 16, nproc * 2, nproc)
+            # ~10-30 core-seconds per leg: big enough that forking the workers does not dominate
+            cb = cpu_sample(nproc * 256, nproc * 64, nproc)
             line["cpu_baseline"] = {
                 "value": cb["value"], "unit": UNIT, "cores": nproc, "kind": cb["kind"],
                 "sample": "%d rows (linear, interpND = %s) + %d rows (Jacobian-Gaussian, port) of the "

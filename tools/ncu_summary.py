@@ -73,7 +73,11 @@ def main():
             rd = to_bytes(r[h.index("dram__bytes_read.sum")], units[h.index("dram__bytes_read.sum")])
             wr = to_bytes(r[h.index("dram__bytes_write.sum")], units[h.index("dram__bytes_write.sum")])
             f.write("\nDRAM traffic per launch: %.1f MB read + %.1f MB write = %.1f MB\n\n" % (rd / 1e6, wr / 1e6, (rd + wr) / 1e6))
-            key = "jacobian" if "k_jacobian" in name else ("linear" if "k_resample<(int)1" in name or "k_resample<1" in name else None)
+            key = None
+            if "k_jacobian" in name:
+                key = "jacobian"
+            elif "k_resample_tex" in name or "k_resample<(int)1" in name or "k_resample<1" in name:
+                key = "linear"
             if key:
                 traffic[key] = rd + wr
     with open(os.path.join(os.path.dirname(prefix), "traffic.json"), "w") as f:
