@@ -190,3 +190,41 @@ def test_full_size_properties(tfm):
     b = tr.resample(2 * src, method='linear', precision='fp32')
     assert torch.allclose(b, 2 * a, rtol=1e-6, atol=1e-6)
     assert a.dtype == torch.float32 and a.shape == (n, n)
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.uint8, np.int64, np.uint16])
+def test_integer_sources_follow_reference_dtype_rules(tfm, oracle, dtype):
+    """FITS images are often integers.  Reference rules (helpers.pyx:373-374, 598-611): nearest keeps
+    the source dtype unless the truncation pass promotes it with the int64 fill; linear and cubic
+    return float64.  Integer sources are carried as float64 on the device (exact below 2^53)."""
+    info = np.iinfo(dtype)
+    src = np.random.default_rng(3).integers(max(info.min, -30000), min(info.max, 30000), size=(41, 57)).astype(dtype)
+    # cubic: the reference forms 3*(r2-r1) in the SOURCE integer dtype (helpers.pyx:774), which wraps
+    # around for large int16 values; the device carries integers as float64 (documented deviation), so
+    # the cubic comparison uses a range where the reference does not overflow
+    src_small = (src // 16).astype(dtype)
+    tr = tfm.Composition([tfm.Scale(1.2, dim=2), tfm.Rotation(0.3), tfm.Offset([-20.0, -15.0])])
+    for m in ('nearest', 'linear', 'cubic'):
+        for b in ('t', 'e', 'm'):
+            if m == 'cubic' and dtype in (np.uint8, np.uint16):
+                continue        # the reference's first Hermite pass wraps around in unsigned arithmetic
+            data = src_small if m == 'cubic' else src
+            got = tr.resample(data, method=m, bound=b)
+            want = oracle.resample(to_oracle(tr), data, method=m, bound=b)
+            assert got.dtype == want.dtype, (m, b, got.dtype, want.dtype)
+            assert np.array_equal(got, want), (m, b)
+
+
+def test_noncontiguous_and_odd_pitch_inputs(tfm, oracle):
+    """Views with strides and widths that break the texture path's alignment rules must still work
+    (the engine stages a contiguous copy; 485 float32 columns are not a multiple of 32 bytes)."""
+    base = np.random.default_rng(4).random((64, 970)).astype(np.float32)
+    view = base[:, ::2]                                     # 64 x 485, strided
+    tr = tfm.Composition([tfm.Rotation(10, unit='deg'), tfm.Offset([-200.0, -30.0])])
+    for prec, tol in (('fp64', 0.0), ('fp32', 1e-5)):
+        got = tr.resample(view, method='linear', precision=prec)
+        want = oracle.resample(to_oracle(tr), np.ascontiguousarray(view), method='linear')
+        if tol == 0.0:
+            assert np.array_equal(got, want)
+        else:
+            assert_close_rel(got, want, tol, prec)
