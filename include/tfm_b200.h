@@ -29,7 +29,7 @@ extern "C" {
 #define TFM_API
 #endif
 
-#define TFM_ABI_VERSION 1
+#define TFM_ABI_VERSION 2
 #define TFM_MAX_OPS 16          /* flattened chain length (Composition flattening, core.py:1534-1537) */
 #define TFM_OP_NPARAM 24
 
@@ -108,8 +108,15 @@ typedef struct tfm_op {
 /* ---- enumerations shared by the resamplers ---- */
 typedef enum tfm_dtype { TFM_F32 = 0, TFM_F64 = 1 } tfm_dtype;
 
-/* interpND methods (helpers.pyx:541-611, 703-787); first letter in the reference */
-typedef enum tfm_method { TFM_NEAREST = 0, TFM_LINEAR = 1, TFM_CUBIC = 2 } tfm_method;
+/* interpND methods (helpers.pyx:541-611, 703-835); first letter in the reference.  The last six are
+ * the "collapsible filters" (helpers.pyx:792-835): a size x size region around floor(v) weighted by
+ * a separable window, size = 16 / 6 / 8 / 2 / 2 / 2 scaled by oblur (helpers.pyx:708-711).
+ * TFM_TENT is the reference's method 'l' WITH oblur (without, 'l' is TFM_LINEAR). */
+typedef enum tfm_method {
+    TFM_NEAREST = 0, TFM_LINEAR = 1, TFM_CUBIC = 2,
+    TFM_SINC = 3, TFM_LANCZOS = 4, TFM_GAUSSIAN = 5, TFM_HANN = 6, TFM_TUKEY = 7, TFM_TENT = 8
+} tfm_method;
+#define TFM_FILTER_MAX_SIZE 112  /* region edge limit of the filter kernel (shared-memory weights) */
 
 /* boundary codes: the reference's own table (helpers.pyx:1511) */
 typedef enum tfm_bound {
@@ -152,7 +159,7 @@ typedef struct tfm_image {
     int64_t plane_pitch;   /* bytes between planes */
 } tfm_image;
 
-/* ---- K1: fused inverse-chain evaluation + nearest / linear / cubic gather ----
+/* ---- K1: fused inverse-chain evaluation + nearest / linear / cubic / windowed-filter gather ----
  * Replaces, for one call of Transform.resample (core.py:573-584):
  *   output-grid enumeration  np.mgrid[...].transpose()        core.py:574-578   (zero bytes here)
  *   icoords = self.invert(grid)                               core.py:574, 1556-1559
@@ -173,6 +180,7 @@ typedef struct tfm_resample_args {
     int32_t flags;
     int32_t tuning;        /* 0 = auto; otherwise a kernel-variant selector (bench / ncu only) */
     double fillvalue;      /* helpers.pyx:373-374 */
+    double oblur;          /* helpers.pyx:509-516; 0 = None.  Only with the filter methods */
     int32_t *status_dev;
 } tfm_resample_args;
 

@@ -419,16 +419,109 @@ def interp_cubic(source, index, bound="t", fillvalue=0):
     return _hermite(rows[0], rows[1], rows[2], rows[3], b_y)
 
 
-def interpND(source, index, method="n", bound="t", fillvalue=0):
-    """2-D subset of helpers.pyx:379-844 (nearest, linear, cubic)."""
+FILTER_SIZE = {"l": 2, "s": 16, "z": 6, "g": 8, "h": 2, "t": 2}       # helpers.pyx:708
+
+
+def filter_window(m, of):
+    """Window value at offset `of` (in units of oblur-scaled input pixels), helpers.pyx:809-826."""
+    if m == "s":
+        return np.sinc(of)
+    if m == "z":
+        bb = np.clip(of, -3, 3)
+        return 3 * np.sinc(bb) * np.sinc(bb / 3)
+    if m == "g":
+        return np.exp(-of * of / 0.5 / 0.5)
+    if m == "h":
+        return 1 + np.cos(np.pi * np.clip(of, -1, 1))
+    if m == "t":
+        return 1 + np.cos(np.pi * np.clip(np.abs(of) * 2 - 0.5, 0, 1))
+    if m == "l":
+        return 1 - np.clip(np.abs(of), 0, 1)
+    raise AssertionError("This can't happen")
+
+
+def interp_filter(source, index, method, bound="t", fillvalue=0, oblur=None):
+    """The collapsible input-plane filters of interpND (helpers.pyx:703-735, 792-835): sinc, Lanczos,
+    Gaussian, Hann, Tukey and the tent with oblur.  A size x size region at floor(v) - (size/2 - 1) is
+    gathered with per-tap boundary conditions, then collapsed one axis at a time, X first:
+        region <- sum(k * region, axis) / sum(k, axis),   k = window((tap - sample)/oblur)."""
+    bx, by = _bound_chars(bound)
+    m = method[0]
+    index = np.asarray(index, dtype=np.float64)
+    size = FILTER_SIZE[m]
+    if oblur is not None:
+        size = int(2 * np.ceil(size / 2 * oblur))                          # helpers.pyx:711
+    else:
+        oblur = 1.0
+    offset = int(size / 2) - 1
+    with np.errstate(invalid="ignore"):
+        fx, fy = np.floor(index[..., 0]), np.floor(index[..., 1])
+        b_x, b_y = index[..., 0] - fx, index[..., 1] - fy
+    tp = _trunc_pass_applies(bound)
+    ixs = [_tap_index(fx - offset, k) for k in range(size)]
+    # of = ((1 - b) - (offset + 1) + i) / oblur    (helpers.pyx:800-802)
+    kx = [filter_window(m, ((1 - b_x) - (offset + 1) + i) / oblur) for i in range(size)]
+    ky = [filter_window(m, ((1 - b_y) - (offset + 1) + i) / oblur) for i in range(size)]
+    # Summation orders, pinned bit-for-bit against the compiled reference: the first-axis kernel `k`
+    # inherits the transposed-mgrid memory order, so its normaliser k.sum(axis=-1) runs along a
+    # strided axis (sequential adds); the other three reductions run along a contiguous axis
+    # (NumPy's 8-accumulator pairwise order, see _npsum).
+    kxs = _seqsum(kx)
+    rows = []
+    with np.errstate(invalid="ignore"):
+        for j in range(size):
+            iy = _tap_index(fy - offset, j)
+            taps = [_tap(source, ix, iy, bx, by, fillvalue, tp) for ix in ixs]
+            rows.append(_npsum([k * t for k, t in zip(kx, taps)]) / kxs)
+        return _npsum([k * r for k, r in zip(ky, rows)]) / _npsum(ky)
+
+
+def _seqsum(terms):
+    acc = terms[0]
+    for t in terms[1:]:
+        acc = acc + t
+    return acc
+
+
+def _npsum(terms):
+    """Sum of a list of arrays in the order NumPy's reduction over a contiguous last axis uses
+    (pairwise_sum in umath: sequential below 8 terms; 8 interleaved accumulators, combined as
+    ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the remainder sequentially, up to 128 terms)."""
+    n = len(terms)
+    if n < 8:
+        acc = terms[0]
+        for t in terms[1:]:
+            acc = acc + t
+        return acc
+    r = list(terms[0:8])
+    i = 8
+    while i + 8 <= n:
+        for k in range(8):
+            r[k] = r[k] + terms[i + k]
+        i += 8
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+    for t in terms[i:]:
+        res = res + t
+    return res
+
+
+def interpND(source, index, method="n", bound="t", fillvalue=0, oblur=None):
+    """2-D subset of helpers.pyx:379-844: nearest, linear, cubic and the collapsible filters
+    (everything but the Fourier method)."""
     m = method[0]
     source = np.asarray(source)
     if m == "n":
+        if oblur is not None:
+            raise ValueError("interpND: oblur is not allowed with nearest-neighbor interpolation.")
         return interp_nearest(source, index, bound, fillvalue)
-    if m == "l":
+    if m == "l" and oblur is None:
         return interp_linear(source, index, bound, fillvalue)
     if m == "c":
+        if oblur is not None:
+            raise ValueError("interpND: oblur is not allowed with cubic-spline interpolation.")
         return interp_cubic(source, index, bound, fillvalue)
+    if m in FILTER_SIZE:
+        return interp_filter(source, index, m, bound, fillvalue, oblur)
     raise ValueError("interpND: valid methods are ('n','l','c','f','s','z','g','h','t')")
 
 
@@ -445,7 +538,7 @@ def pixel_grid(ny, nx, y0=0, y1=None):
     return g
 
 
-def resample(t, data, method="n", bound="t", shape=None, fillvalue=0, rows=None, tile=256):
+def resample(t, data, method="n", bound="t", shape=None, fillvalue=0, rows=None, tile=256, oblur=None):
     """Transform.resample (core.py:422-586) for 2-D data.  `rows=(y0,y1)` restricts the output to
     a row block (used for row-tiled / multi-process CPU baselines)."""
     data = np.asarray(data)
@@ -458,7 +551,7 @@ def resample(t, data, method="n", bound="t", shape=None, fillvalue=0, rows=None,
     for ya in range(y0, y1, tile):
         yb = min(y1, ya + tile)
         coords = t.reverse(pixel_grid(ny, nx, ya, yb))
-        blk = interpND(data, coords, method=m, bound=bound, fillvalue=fillvalue)
+        blk = interpND(data, coords, method=m, bound=bound, fillvalue=fillvalue, oblur=oblur)
         if out is None:
             out = np.empty((y1 - y0, nx), dtype=blk.dtype)
         out[ya - y0:yb - y0] = blk

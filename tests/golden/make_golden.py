@@ -75,6 +75,20 @@ def main():
             for fv in (0, -9):
                 key = "interp/%s/%s/%s" % (m, b if isinstance(b, str) else "+".join(b), fv)
                 out[key] = t.interpND(src32, idx, method=m, bound=b, fillvalue=fv)
+    # the collapsible input-plane filters (helpers.pyx:703-735, 792-835), with and without oblur
+    for m in 'szghtl':
+        for b in ('t', 'e', 'p', 'm', ['p', 'e']):
+            for ob in (None, 1.7, 0.6):
+                if m == 'l' and ob is None:
+                    continue
+                if ob == 0.6 and b != 't':
+                    continue
+                key = "filt/%s/%s/%s" % (m, b if isinstance(b, str) else "+".join(b), ob)
+                out[key] = t.interpND(src32, idx, method=m, bound=b, fillvalue=-9, oblur=ob)
+        out["filt64/%s" % m] = t.interpND(src64, idx, method=m, bound='m', oblur=1.3)
+    for m in ('sinc', 'zlanczos', 'gaussian', 'hann', 'tukey'):
+        out["fresample/affine/%s/t/f32" % m[0]] = ch["affine"].resample(src32, method=m, bound='t')
+        out["fresample/radial/%s/p/f64" % m[0]] = ch["radial"].resample(src64, method=m, bound='p', shape=(20, 37))
     # Jacobian pieces that the reference can run (helpers.pyx:846-958, 960-1141, 1807-1810)
     # forward through the polar transform: atan2 wraps at the branch cut, which is what jump_detect
     # exists for (the inverse direction, cos/sin, is continuous)

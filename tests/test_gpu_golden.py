@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import to_oracle, assert_close_rel
-from test_oracle_golden import GOLD, RESAMPLE_KEYS, INTERP_KEYS, _chains
+from test_oracle_golden import GOLD, RESAMPLE_KEYS, INTERP_KEYS, FILT_KEYS, _chains
 
 pytestmark = pytest.mark.gpu
 
@@ -60,6 +60,36 @@ def test_interpND_matches_reference(tfm, key):
     assert got.dtype == want.dtype
     same = (got == want) | (np.isnan(got) & np.isnan(want))
     assert same.all(), (key, np.argwhere(~same)[:4])
+
+
+@pytest.mark.parametrize("key", FILT_KEYS)
+def test_interpND_filters_match_reference(tfm, key):
+    """Collapsible filters (helpers.pyx:703-735, 792-835) against the real reference: the tent has no
+    transcendental and is bit-exact; the others go through sin / cos / exp, whose last-ulp
+    differences between CUDA's and the host's libm leave <= 1e-12."""
+    _, m, b, ob = key.split("/")
+    bound = b.split("+") if "+" in b else b
+    ob = None if ob == "None" else float(ob)
+    got = tfm.interpND(GOLD["src32"], GOLD["interp/index"], method=m, bound=bound, fillvalue=-9, oblur=ob)
+    want = GOLD[key]
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if m == 'l':
+        assert ((got == want) | (np.isnan(got) & np.isnan(want))).all(), key
+    else:
+        assert_close_rel(got, want, 1e-12, key)
+
+
+def test_filters_through_resample_match_reference(tfm, chains):
+    for m in "szghtl":
+        got = tfm.interpND(GOLD["src64"], GOLD["interp/index"], method=m, bound='m', oblur=1.3)
+        assert_close_rel(got, GOLD["filt64/%s" % m], 1e-12, m)
+    for m, name in (("s", "sinc"), ("z", "zlanczos"), ("g", "gaussian"), ("h", "hann"), ("t", "tukey")):
+        got = chains["affine"].resample(GOLD["src32"], method=name, bound='t')
+        want = GOLD["fresample/affine/%s/t/f32" % m]
+        assert got.dtype == want.dtype
+        assert_close_rel(got, want, 1e-12, m)
+        got = chains["radial"].resample(GOLD["src64"], method=name, bound='p', shape=(20, 37))
+        assert_close_rel(got, GOLD["fresample/radial/%s/p/f64" % m], 1e-11, m)
 
 
 def test_svd_matches_reference(tfm):

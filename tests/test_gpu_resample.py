@@ -141,7 +141,7 @@ def test_errors_match_reference(tfm):
     with pytest.raises(AssertionError):
         tfm.Scale([0.0, 1.0]).resample(src)             # not invertible (basic.py:321)
     with pytest.raises(NotImplementedError):
-        tfm.Scale(2.0).resample(src, method='sinc')      # outside the GPU path: loud, no fallback
+        tfm.Scale(2.0).resample(src, method='fourier')   # outside the GPU path: loud, no fallback
 
 
 def test_nan_and_absurd_coordinates(tfm, oracle):
@@ -228,3 +228,62 @@ def test_noncontiguous_and_odd_pitch_inputs(tfm, oracle):
             assert np.array_equal(got, want)
         else:
             assert_close_rel(got, want, tol, prec)
+
+
+# ---------------------------------------------------------------------------------------------
+# windowed input-plane filters (helpers.pyx:703-735, 792-835)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m", list("szghtl"))
+@pytest.mark.parametrize("bound", ['t', 'e', 'p', 'm', ['m', 'p']])
+def test_filters_match_oracle(tfm, oracle, m, bound):
+    rng = np.random.default_rng(77)
+    src = rng.random((61, 83)).astype(np.float32)
+    tr = tfm.Composition([tfm.Scale(1.7, dim=2), tfm.Rotation(25, unit='deg'), tfm.Offset([-20.0, -35.0])])
+    for ob in (None, 2.2):
+        if m == 'l' and ob is None:
+            continue
+        got = tr.resample(src, method=m, bound=bound, shape=(70, 90), oblur=ob, fillvalue=3)
+        want = oracle.resample(to_oracle(tr), src, method=m, bound=bound, shape=(70, 90), oblur=ob, fillvalue=3)
+        assert got.dtype == want.dtype == np.float64
+        if m == 'l':
+            assert np.array_equal(got, want)
+        else:
+            assert_close_rel(got, want, 1e-12, (m, bound, ob))
+
+
+def test_filters_fast_mode_and_limits(tfm, oracle):
+    rng = np.random.default_rng(78)
+    src = rng.random((96, 128)).astype(np.float32)
+    tr = tfm.Composition([tfm.Scale(0.8, dim=2), tfm.Rotation(-12, unit='deg'), tfm.Offset([-10.0, 5.0])])
+    for m in "szghtl":
+        ob = 1.5
+        got = tr.resample(src, method=m, bound='t', oblur=ob, precision='fp32')
+        want = oracle.resample(to_oracle(tr), src, method=m, bound='t', oblur=ob)
+        assert got.dtype == np.float32
+        assert_close_rel(got, want, 2e-5, m)
+    # a constant image stays constant under every normalised window
+    flat = np.full((40, 50), 2.5, dtype=np.float32)
+    for m in "szght":
+        got = tr.resample(flat, method=m, bound='e')
+        assert np.allclose(got, 2.5, rtol=1e-13, atol=0)
+    # oblur is rejected where the reference rejects it (helpers.pyx:543-544, 748-749)
+    with pytest.raises(ValueError):
+        tr.resample(src, method='n', oblur=2.0)
+    with pytest.raises(ValueError):
+        tr.resample(src, method='c', oblur=2.0)
+    # the largest region the kernel holds (sinc, 16*7 = 112), and one beyond it
+    big = tr.resample(src, method='s', bound='m', oblur=7.0, shape=(24, 24))
+    want = oracle.resample(to_oracle(tr), src, method='s', bound='m', oblur=7.0, shape=(24, 24))
+    assert_close_rel(big, want, 1e-11, "sinc oblur 7")
+    with pytest.raises(NotImplementedError):
+        tr.resample(src, method='s', oblur=7.5)
+
+
+def test_filters_batched_and_f64(tfm, oracle):
+    rng = np.random.default_rng(79)
+    src = rng.random((3, 33, 47))
+    tr = tfm.Wrap(tfm.Rotation(0.3), tfm.Offset([20.0, 15.0]))
+    got = tr.resample(src, method='g', bound='p')
+    for k in range(3):
+        want = oracle.resample(to_oracle(tr), src[k], method='g', bound='p')
+        assert_close_rel(got[k], want, 1e-12, k)

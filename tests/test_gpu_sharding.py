@@ -44,7 +44,8 @@ def _worker(rank, world, port, case, ret):
 
 @pytest.mark.parametrize("case", [("linear", "t", {}), ("cubic", "t", {}), ("nearest", "e", {}),
                                   ("linear", "t", {"precision": "fp32"}), ("G", "t", {}),
-                                  ("G", "t", {"precision": "fp32"})])
+                                  ("G", "t", {"precision": "fp32"}), ("hann", "t", {}),
+                                  ("gaussian", "t", {"oblur": 1.5}), ("zlanczos", "t", {"precision": "fp32"})])
 def test_sharded_equals_unsharded(case):
     mgr = mp.Manager()
     ret = mgr.dict()

@@ -97,6 +97,39 @@ def test_interpND_matches_reference(oracle, key):
     assert same.all(), (key, np.argwhere(~same)[:4])
 
 
+FILT_KEYS = [k for k in GOLD.files if k.startswith("filt/")]
+
+
+@pytest.mark.parametrize("key", FILT_KEYS)
+def test_interpND_filters_match_reference(oracle, key):
+    """sinc / Lanczos / Gaussian / Hann / Tukey / tent-with-oblur (helpers.pyx:703-735, 792-835):
+    bit-exact, including NumPy's reduction orders."""
+    _, m, b, ob = key.split("/")
+    bound = b.split("+") if "+" in b else b
+    ob = None if ob == "None" else float(ob)
+    got = oracle.interpND(GOLD["src32"], GOLD["interp/index"], method=m, bound=bound, fillvalue=-9, oblur=ob)
+    want = GOLD[key]
+    assert got.dtype == want.dtype
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (key, np.argwhere(~same)[:4])
+
+
+def test_filters_through_resample_match_reference(oracle, chains):
+    for m in "szghtl":
+        got = oracle.interpND(GOLD["src64"], GOLD["interp/index"], method=m, bound='m', oblur=1.3)
+        want = GOLD["filt64/%s" % m]
+        assert ((got == want) | (np.isnan(got) & np.isnan(want))).all(), m
+    for m in "szght":
+        got = oracle.resample(to_oracle(chains["affine"]), GOLD["src32"], method=m, bound='t')
+        assert np.array_equal(got, GOLD["fresample/affine/%s/t/f32" % m], equal_nan=True), m
+        got = oracle.resample(to_oracle(chains["radial"]), GOLD["src64"], method=m, bound='p', shape=(20, 37))
+        assert_close_rel(got, GOLD["fresample/radial/%s/p/f64" % m], 1e-11, m)
+    with pytest.raises(ValueError):
+        oracle.interpND(GOLD["src32"], GOLD["interp/index"], method='n', oblur=2.0)
+    with pytest.raises(ValueError):
+        oracle.interpND(GOLD["src32"], GOLD["interp/index"], method='c', oblur=2.0)
+
+
 def test_jacobian_pieces_match_reference(oracle):
     # square grid: simple_jacobian and jump_detect bit-identical to the reference
     sq = GOLD["jac/coords_sq"]

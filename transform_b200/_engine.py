@@ -17,7 +17,18 @@ from . import _lib as L
 _METHODS = {"n": L.NEAREST, "l": L.LINEAR, "c": L.CUBIC}
 # capital-letter methods of Transform.resample (core.py:495-508) -> interpND_grid filter letters
 _AA_METHODS = {"G": "g", "H": "h", "R": "t", "Z": "z", "L": "l"}
-_UNSUPPORTED_INTERP = ("f", "s", "z", "g", "h", "t")
+# the collapsible input-plane filters of interpND (helpers.pyx:703-735, 792-835) and their region size
+_FILTERS = {"s": (L.SINC, 16), "z": (L.LANCZOS, 6), "g": (L.GAUSSIAN, 8), "h": (L.HANN, 2),
+            "t": (L.TUKEY, 2), "l": (L.TENT, 2)}
+_UNSUPPORTED_INTERP = ("f",)
+
+
+def filter_size(m, oblur):
+    """Edge of the sampled region (helpers.pyx:708-711)."""
+    size = _FILTERS[m][1]
+    if oblur is not None:
+        size = int(2 * np.ceil(size / 2 * oblur))
+    return size
 
 
 def parse_precision(precision):
@@ -101,18 +112,30 @@ def _src_to_device(data, want_f32):
 
 
 def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None, tuning=0,
-             dst_origin=(0, 0), src_origin=(0, 0), src_full=None, out=None):
+             dst_origin=(0, 0), src_origin=(0, 0), src_full=None, out=None, oblur=None):
     """K1 driver.  `chain_ops` is the inverse chain in execution order (list of TfmOp)."""
     lib = L.load()
     prec = parse_precision(precision)
     m = method[0]
-    if m not in _METHODS:
+    if m not in _METHODS and m not in _FILTERS:
         if m in _UNSUPPORTED_INTERP:
             raise NotImplementedError(
-                "transform_b200: interpND method '%s' (input-plane filter) is outside the GPU hot "
-                "path (nearest/linear/cubic and the Jacobian-adaptive 'G','H','R','Z'); there is "
-                "no CPU fallback" % m)
+                "transform_b200: interpND method '%s' (Fourier interpolation) is outside the GPU "
+                "hot path; there is no CPU fallback" % m)
         raise ValueError("interpND: valid methods are ('n','l','c','f','s','z','g','h','t')")
+    # helpers.pyx:543-544, 748-749
+    if oblur is not None:
+        if m == "n":
+            raise ValueError("interpND: oblur is not allowed with nearest-neighbor interpolation.")
+        if m == "c":
+            raise ValueError("interpND: oblur is not allowed with cubic-spline interpolation.")
+        oblur = float(oblur)
+        if not oblur > 0:
+            raise ValueError("interpND: oblur must be positive")
+    is_filter = m in _FILTERS and (m != "l" or oblur is not None)
+    if is_filter and filter_size(m, oblur) > L.FILTER_MAX_SIZE:
+        raise NotImplementedError("transform_b200: filter region of %d pixels exceeds the kernel "
+                                  "limit of %d" % (filter_size(m, oblur), L.FILTER_MAX_SIZE))
     bx, by = bound_pair(bound)
     fast = prec == L.PREC_FAST32
     src, sdt, orig_dt, from_numpy = _src_to_device(data, fast)
@@ -157,12 +180,13 @@ def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None,
     a.chain = ctypes.cast(arr, ctypes.POINTER(L.TfmOp))
     a.src = _image(src, sdt, src_origin[0], src_origin[1], src_full)
     a.dst = _image(dst, ddt, dst_origin[0], dst_origin[1])
-    a.method = _METHODS[m]
+    a.method = _FILTERS[m][0] if is_filter else _METHODS[m]
     a.bound_x, a.bound_y = bx, by
     a.precision = prec
     a.flags = flags
     a.tuning = int(tuning)
     a.fillvalue = float(fillvalue)
+    a.oblur = float(oblur) if (is_filter and oblur is not None) else 0.0
     a.status_dev = status.data_ptr() if status is not None else None
     rc = lib.tfm_resample(ctypes.byref(a), dev.stream_ptr())
     L.raise_for_status(rc, "tfm_resample")

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtfm_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_OPS = 16
 OP_NPARAM = 24
 
@@ -24,6 +24,8 @@ RAD_CCW, RAD_POS_ONLY, RAD_R0_NOT_NONE, RAD_R0_TRUTHY, RAD_ORIGIN_NONZERO = 1, 2
 WCS_PROJ_NONE, WCS_PROJ_TAN, WCS_PROJ_CAR = 0, 1, 2
 F32, F64 = 0, 1
 NEAREST, LINEAR, CUBIC = 0, 1, 2
+SINC, LANCZOS, GAUSSIAN, HANN, TUKEY, TENT = 3, 4, 5, 6, 7, 8
+FILTER_MAX_SIZE = 112
 BOUND_CODE = {"f": 1, "t": 2, "e": 3, "p": 4, "m": 5}            # helpers.pyx:1511
 FILTER_CODE = {"l": 1, "z": 2, "h": 3, "t": 4, "g": 5}           # helpers.pyx:1501
 PREC_EXACT64, PREC_FAST32 = 0, 1
@@ -49,7 +51,7 @@ class TfmResampleArgs(ctypes.Structure):
                 ("src", TfmImage), ("dst", TfmImage),
                 ("method", ctypes.c_int32), ("bound_x", ctypes.c_int32), ("bound_y", ctypes.c_int32),
                 ("precision", ctypes.c_int32), ("flags", ctypes.c_int32), ("tuning", ctypes.c_int32),
-                ("fillvalue", ctypes.c_double), ("status_dev", ctypes.c_void_p)]
+                ("fillvalue", ctypes.c_double), ("oblur", ctypes.c_double), ("status_dev", ctypes.c_void_p)]
 
 
 class TfmJacobianArgs(ctypes.Structure):

@@ -98,7 +98,8 @@ class Transform:
 
         The output grid is enumerated implicitly, mapped back through the inverse chain in
         registers and interpolated in ONE CUDA kernel.  `method` (first character):
-        'n'earest, 'l'inear, 'c'ubic use interpND semantics (helpers.pyx:541-611, 703-787);
+        'n'earest, 'l'inear, 'c'ubic and the input-plane filters 's'inc, 'z' (Lanczos),
+        'g'aussian, 'h'ann, 't'ukey use interpND semantics (helpers.pyx:541-611, 703-835);
         the capital letters the reference advertises but never dispatches (core.py:495-508,
         581-584) -- 'G'aussian, 'H'anning, 'R'ounded (Tukey), 'Z'Lanczos -- run the
         Jacobian-adaptive anti-aliasing kernel with interpND_grid's keyword arguments
@@ -137,10 +138,11 @@ class Transform:
                 return _engine.resample_jacobian(ops, data0, shape, _engine._AA_METHODS[m], bound,
                                                  fillvalue=fillvalue, precision=precision,
                                                  tuning=tuning, out=out, **aa)
+        oblur = aa.pop('oblur', None)           # interpND's keyword (helpers.pyx:509-516)
         if aa:
             raise TypeError("resample() got unexpected keyword arguments %s" % sorted(aa))
         return _engine.resample(ops, data0, shape, m, bound, fillvalue=fillvalue,
-                                precision=precision, tuning=tuning, out=out)
+                                precision=precision, tuning=tuning, out=out, oblur=oblur)
 
     def remap(self, data, /, method='n', bound='t', phot='radiance', shape=None, template=None,
               input_range=None, output_range=None, justify=False, rectify=True, wcs=None, **kw):

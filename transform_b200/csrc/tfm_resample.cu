@@ -600,6 +600,220 @@ static bool get_texture(const void *ptr, int w, int h, long long pitch, cudaText
 }
 
 // ---------------------------------------------------------------------------------------------
+// windowed ("collapsible") filters: sinc, Lanczos, Gaussian, Hann, Tukey, tent-with-oblur
+// ---------------------------------------------------------------------------------------------
+// helpers.pyx:703-735, 792-835.  A size x size region at floor(v) - (size/2 - 1) is weighted by a
+// separable window of the sub-pixel offset and collapsed one axis at a time, X first:
+//     row_j  = sum_i(kx_i * tap_ji) / sum_i(kx_i)          out = sum_j(ky_j * row_j) / sum_j(ky_j)
+// One thread per output pixel.  The S x-weights of a pixel are evaluated once and parked in shared
+// memory ([i][thread] layout, conflict-free), the y-weight of a row is evaluated when the row is
+// consumed: 2S window evaluations for S^2 taps.
+//
+// Exact mode reproduces NumPy's reduction ORDER (pinned against the compiled reference, see
+// oracle_np.interp_filter): the x normaliser is a sequential sum (strided axis), the other three
+// reductions use NumPy's pairwise scheme -- 8 interleaved partial sums over the first 8*floor(S/8)
+// terms, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the remainder sequentially.
+struct FilterParams {
+    int method;                              // TFM_SINC .. TFM_TENT
+    int size;                                // region edge S
+    int offset;                              // S/2 - 1
+    double oblur;                            // 1.0 when None
+};
+
+__device__ __forceinline__ double clip_keepnan(double x, double lo, double hi)
+{
+    return x < lo ? lo : (x > hi ? hi : x);             // NaN falls through, like np.clip
+}
+
+__device__ __forceinline__ double np_sinc(double x)
+{
+    const double y = __dmul_rn(3.141592653589793, x == 0.0 ? 1.0e-20 : x);     // numpy.sinc
+    return __ddiv_rn(sin(y), y);
+}
+
+// window value at offset `of`, operation order of helpers.pyx:809-826
+__device__ __forceinline__ double window_exact(int m, double of)
+{
+    switch (m) {
+    case TFM_SINC: return np_sinc(of);
+    case TFM_LANCZOS: {
+        const double bb = clip_keepnan(of, -3.0, 3.0);
+        return __dmul_rn(__dmul_rn(3.0, np_sinc(bb)), np_sinc(__ddiv_rn(bb, 3.0)));
+    }
+    case TFM_GAUSSIAN: return exp(__dmul_rn(__dmul_rn(__dmul_rn(-of, of), 2.0), 2.0));   // -bb*bb/0.5/0.5
+    case TFM_HANN: return __dadd_rn(1.0, cos(__dmul_rn(3.141592653589793, clip_keepnan(of, -1.0, 1.0))));
+    case TFM_TUKEY:
+        return __dadd_rn(1.0, cos(__dmul_rn(3.141592653589793,
+                                            clip_keepnan(__dsub_rn(__dmul_rn(fabs(of), 2.0), 0.5), 0.0, 1.0))));
+    default: return __dsub_rn(1.0, clip_keepnan(fabs(of), 0.0, 1.0));
+    }
+}
+
+__device__ __forceinline__ float window_fast(int m, float of)
+{
+    // sinpif / cospif reduce the argument exactly (the sinc and Lanczos weights alternate in sign, so
+    // absolute errors of the plain fast intrinsics would not cancel); 2S evaluations per pixel only
+    const float PI = 3.14159265358979f;
+    switch (m) {
+    case TFM_SINC: {
+        const float y = PI * of;
+        return fabsf(of) < 1e-4f ? 1.0f : __fdividef(sinpif(of), y);
+    }
+    case TFM_LANCZOS: {
+        const float bb = fminf(fmaxf(of, -3.0f), 3.0f);
+        const float b3 = bb * (1.0f / 3.0f);
+        return fabsf(bb) < 1e-3f ? 3.0f : __fdividef(3.0f * sinpif(bb) * sinpif(b3), (PI * PI) * bb * b3);
+    }
+    case TFM_GAUSSIAN: return exp2f(-5.770780163555854f * of * of);              // exp(-4 of^2)
+    case TFM_HANN: return 1.0f + cospif(fminf(fmaxf(of, -1.0f), 1.0f));
+    case TFM_TUKEY: return 1.0f + cospif(fminf(fmaxf(fabsf(of) * 2.0f - 0.5f, 0.0f), 1.0f));
+    default: return 1.0f - fminf(fabsf(of), 1.0f);
+    }
+}
+
+// of_i = ((1 - b) - (offset + 1) + i) / oblur      (helpers.pyx:800-802)
+__device__ __forceinline__ double filt_of(double one_minus_b, const FilterParams &F, int i)
+{
+    return __ddiv_rn(__dadd_rn(__dsub_rn(one_minus_b, (double)(F.offset + 1)), (double)i), F.oblur);
+}
+
+// NumPy's pairwise reduction over n streamed terms; term(i) is called exactly once per i, in order.
+template <class TermFn>
+__device__ __forceinline__ double np_pairwise_sum(int n, TermFn term)
+{
+    const int nb = n >> 3;
+    double res;
+    int i = 0;
+    if (nb == 0) {
+        res = term(0);
+        i = 1;
+    } else {
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = term(k);
+        for (int b = 1; b < nb; ++b) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], term(b * 8 + k));
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        i = nb * 8;
+    }
+    for (; i < n; ++i) res = __dadd_rn(res, term(i));
+    return res;
+}
+
+// one collapsed row (exact mode): sum_i kx_i * tap(i), pairwise order.  Kept out of line: the y
+// reduction instantiates it once per unrolled slot.
+template <typename SrcT, bool GENERIC>
+__device__ __noinline__ double filt_row_exact(const ResampleParams &P, const char *src_base, const double *kx,
+                                              int S, long long gx0, long long gy, bool okx, bool interior)
+{
+    if (interior) {
+        const SrcT *row = reinterpret_cast<const SrcT *>(src_base + (gy - P.src_y0) * P.src_pitch) + (gx0 - P.src_x0);
+        return np_pairwise_sum(S, [&](int i) { return __dmul_rn(kx[i * 256], (double)__ldg(row + i)); });
+    }
+    return np_pairwise_sum(S, [&](int i) {
+        return __dmul_rn(kx[i * 256], tap_generic<SrcT, double>(P, src_base, okx ? gx0 + i : gx0, gy));
+    });
+}
+
+template <typename SrcT, typename DstT, class A, typename RegT, bool SPH>
+__global__ void __launch_bounds__(256)
+k_resample_filter(const __grid_constant__ ResampleParams P, const __grid_constant__ FilterParams F)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool FASTI = (sizeof(RegT) == 4);
+    RegT *const kx = reinterpret_cast<RegT *>(smem_raw) + threadIdx.x;          // kx[i * 256]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const char *const src_base = static_cast<const char *>(P.src) + (long long)blockIdx.z * P.src_plane;
+    char *const dst_base = static_cast<char *>(P.dst) + (long long)blockIdx.z * P.dst_plane;
+    const int X = blockIdx.x * 32 + ((warp & 1) << 4) + (lane & 15);
+    const int Y = blockIdx.y * 8 + ((warp >> 1) << 1) + (lane >> 4);
+    if (X >= P.dst_w || Y >= P.dst_h) return;
+
+    double cx[1] = {(double)(P.dst_x0 + X)}, cy[1] = {(double)(P.dst_y0 + Y)};
+    chain_eval_n<A, SPH, 1>(P.chain, cx, cy);
+    const double x = cx[0], y = cy[0];
+    const double fx = floor(x), fy = floor(y);
+    const int S = F.size;
+    // tap bases; |f| >= 2^51 or NaN: all taps share the (invalid) base index, as in k_resample
+    const bool okx = fabs(fx) < 2.0e15, oky = fabs(fy) < 2.0e15;
+    const long long gx0 = okx ? cast_i64(fx) - F.offset : cast_i64(fx);
+    const long long gy0 = oky ? cast_i64(fy) - F.offset : cast_i64(fy);
+    // whole region inside the staged data: plain loads, no boundary logic
+    const bool interior = okx && oky && gx0 >= P.src_x0 && gy0 >= P.src_y0 &&
+                          gx0 + S <= (long long)P.src_x0 + P.src_w && gy0 + S <= (long long)P.src_y0 + P.src_h;
+    DstT *const out = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch) + X;
+
+    if (!FASTI) {
+        const double bx1 = __dsub_rn(1.0, __dsub_rn(x, fx)), by1 = __dsub_rn(1.0, __dsub_rn(y, fy));
+        double kxs = 0.0;                                                        // sequential (strided axis)
+        for (int i = 0; i < S; ++i) {
+            const double k = window_exact(F.method, filt_of(bx1, F, i));
+            kx[i * 256] = (RegT)k;
+            kxs = (i == 0) ? k : __dadd_rn(kxs, k);
+        }
+        const double *kxd = reinterpret_cast<const double *>(kx);
+        const double kys = np_pairwise_sum(S, [&](int j) { return window_exact(F.method, filt_of(by1, F, j)); });
+        const double acc = np_pairwise_sum(S, [&](int j) {
+            const double ky = window_exact(F.method, filt_of(by1, F, j));
+            const double row = filt_row_exact<SrcT, true>(P, src_base, kxd, S, gx0, oky ? gy0 + j : gy0, okx, interior);
+            return __dmul_rn(ky, __ddiv_rn(row, kxs));
+        });
+        *out = (DstT)__ddiv_rn(acc, kys);
+    } else {
+        const float bx1 = 1.0f - (float)(x - fx), by1 = 1.0f - (float)(y - fy);
+        const float iob = 1.0f / (float)F.oblur, o1 = (float)(F.offset + 1);
+        float kxs = 0.0f;
+        for (int i = 0; i < S; ++i) {
+            const float k = window_fast(F.method, (bx1 - o1 + (float)i) * iob);
+            kx[i * 256] = (RegT)k;
+            kxs += k;
+        }
+        const float *kxf = reinterpret_cast<const float *>(kx);
+        float acc = 0.0f, kys = 0.0f;
+        for (int j = 0; j < S; ++j) {
+            const float ky = window_fast(F.method, (by1 - o1 + (float)j) * iob);
+            kys += ky;
+            float row = 0.0f;
+            if (interior) {
+                const SrcT *r = reinterpret_cast<const SrcT *>(src_base + (gy0 + j - P.src_y0) * P.src_pitch) + (gx0 - P.src_x0);
+                for (int i = 0; i < S; ++i) row = fmaf(kxf[i * 256], (float)__ldg(r + i), row);
+            } else {
+                for (int i = 0; i < S; ++i)
+                    row = fmaf(kxf[i * 256], tap_generic<SrcT, float>(P, src_base, okx ? gx0 + i : gx0, oky ? gy0 + j : gy0), row);
+            }
+            acc = fmaf(ky, row, acc);
+        }
+        *out = (DstT)(acc / (kxs * kys));
+    }
+}
+
+template <typename SrcT, typename DstT, class A, typename RegT>
+static cudaError_t launch_filter(const ResampleParams &P, const FilterParams &F, cudaStream_t st, const char **name)
+{
+    dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 7) / 8), (unsigned)P.n_planes);
+    if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
+    const size_t smem = (size_t)256 * (size_t)F.size * sizeof(RegT);
+    const bool sph = chain_has_sph(P.chain);
+    auto go = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, 256, smem, st>>>(P, F);
+        return cudaGetLastError();
+    };
+    cudaError_t e = sph ? go(k_resample_filter<SrcT, DstT, A, RegT, true>)
+                        : go(k_resample_filter<SrcT, DstT, A, RegT, false>);
+    count_launch();
+    *name = "k_resample_filter";
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 template <int METHOD, typename SrcT, typename DstT, class A, typename RegT>
@@ -663,7 +877,12 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
 {
     if (!a || a->abi_version != TFM_ABI_VERSION) return TFM_EVALUE;
     if (a->n_ops < 0 || a->n_ops > TFM_MAX_OPS || (a->n_ops && !a->chain)) return TFM_EVALUE;
-    if (a->method < TFM_NEAREST || a->method > TFM_CUBIC) return TFM_EVALUE;           // helpers.pyx:840-844
+    if (a->method < TFM_NEAREST || a->method > TFM_TENT) return TFM_EVALUE;            // helpers.pyx:840-844
+    const bool is_filter = a->method >= TFM_SINC;
+    // helpers.pyx:543-544, 748-749: oblur is rejected by nearest and cubic; 'l' with oblur is TFM_TENT
+    if (!is_filter && a->oblur != 0.0) return TFM_EVALUE;
+    if (a->method == TFM_TENT && !(a->oblur != 0.0)) return TFM_EVALUE;
+    if (is_filter && !(a->oblur >= 0.0)) return TFM_EVALUE;
     if (a->bound_x < TFM_B_FORBID || a->bound_x > TFM_B_MIRROR ||
         a->bound_y < TFM_B_FORBID || a->bound_y > TFM_B_MIRROR) return TFM_EVALUE;     // helpers.pyx:174-176
     const tfm_image &s = a->src, &d = a->dst;
@@ -726,7 +945,26 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         P.aff_margin = (float)(4e-6 * (bx > by ? bx : by));      // a few fp32 ulps of the largest term
         if (!(P.aff_margin < 64.0f)) P.aff_bounded = 0;          // huge coordinates: skip the shortcut
     }
-    if (exact) {
+    if (is_filter) {
+        static const int base_size[] = {16, 6, 8, 2, 2, 2};                           // helpers.pyx:708
+        FilterParams F;
+        F.method = a->method;
+        F.oblur = a->oblur != 0.0 ? a->oblur : 1.0;
+        double sz = base_size[a->method - TFM_SINC];
+        if (a->oblur != 0.0) sz = 2.0 * ceil(sz / 2.0 * a->oblur);                      // helpers.pyx:711
+        if (!(sz >= 2.0)) return TFM_EVALUE;
+        if (sz > (double)TFM_FILTER_MAX_SIZE) return TFM_EUNSUPPORTED;
+        F.size = (int)sz;
+        F.offset = F.size / 2 - 1;
+        if (exact && s.dtype == TFM_F32 && d.dtype == TFM_F64)
+            e = launch_filter<float, double, Exact, double>(P, F, st, &name);
+        else if (exact && s.dtype == TFM_F64 && d.dtype == TFM_F64)
+            e = launch_filter<double, double, Exact, double>(P, F, st, &name);
+        else if (!exact && s.dtype == TFM_F32 && d.dtype == TFM_F32)
+            e = launch_filter<float, float, Fast, float>(P, F, st, &name);
+        else
+            return TFM_EUNSUPPORTED;
+    } else if (exact) {
         if (s.dtype == TFM_F32 && d.dtype == TFM_F64)
             e = launch1<float, double, Exact, double>(a->method, P, generic, false, st, &name);
         else if (s.dtype == TFM_F64 && d.dtype == TFM_F64)

@@ -42,19 +42,14 @@ def _index_op(index):
 
 def interpND(source, index=None, method='n', bound='t', fillvalue=0, oblur=None, strict=False, *,
              precision=None):
-    """helpers.pyx:379-844 for 2-D sources and methods nearest / linear / cubic."""
-    if oblur is not None:
-        if method[0] in ('n',):
-            raise ValueError("interpND: oblur is not allowed with nearest-neighbor interpolation.")
-        if method[0] == 'c':
-            raise ValueError("interpND: oblur is not allowed with cubic-spline interpolation.")
-        raise NotImplementedError("transform_b200: oblur (input-plane filter scaling) is outside the GPU path")
+    """helpers.pyx:379-844 for 2-D sources: nearest / linear / cubic and the collapsible filters
+    sinc / Lanczos ('z') / Gaussian / Hann / Tukey, with interpND's `oblur` scaling."""
     src = source if dev.is_tensor(source) else np.asarray(source)
     if len(src.shape) != 2:
         raise NotImplementedError("transform_b200: interpND on the GPU takes a 2-D source")
     op, (ny, nx), lead, keep = _index_op(index)
     out = _engine.resample([op], src, (ny, nx), method[0], bound, fillvalue=fillvalue,
-                           precision=precision)
+                           precision=precision, oblur=oblur)
     del keep
     return out.reshape(lead)
 

@@ -20,6 +20,15 @@ import numpy as np
 HALO = {"n": 1, "l": 2, "c": 3}          # taps reach floor-1 .. floor+2 (cubic); +1 of slack
 
 
+def halo_of(method, oblur=None):
+    """Reach of the interpolation footprint around floor(v), in pixels (None: whole frame needed)."""
+    from . import _engine
+    m = method[0]
+    if m in _engine._FILTERS and (m != "l" or oblur is not None):
+        return _engine.filter_size(m, oblur) // 2 + 1
+    return HALO.get(m)
+
+
 def row_blocks(height, world):
     """Contiguous row blocks [y0, y1) per rank, equal size except the tail (possibly empty)."""
     per = -(-int(height) // int(world))
@@ -69,13 +78,12 @@ def source_box(coords, src_h, src_w, halo, margin=2):
     return (x0, y0, x1, y1)
 
 
-def plan(transform, shape, src_shape, method, bound, world, invert_points, smooth_margin=8):
+def plan(transform, shape, src_shape, method, bound, world, invert_points, smooth_margin=8, oblur=None):
     """Per-rank plan: list of dicts {rows, box | None, whole}.  `whole` = stage the entire frame
     (non-truncating boundary modes act in global coordinates; or the box is most of the frame)."""
     ny, nx = int(shape[-2]), int(shape[-1])
     sh, sw = int(src_shape[-2]), int(src_shape[-1])
-    m = method[0]
-    halo = HALO.get(m)
+    halo = halo_of(method, oblur)
     bl = bound if isinstance(bound, (list, tuple)) else [bound]
     wrapping = any(b[0] != 't' for b in bl)
     out = []
@@ -142,7 +150,7 @@ def resample_sharded(transform, data, method='n', bound='t', shape=None, *, grou
         shape = src_shape
     full = (int(src_shape[-2]), int(src_shape[-1]))
     # every rank derives the SAME plan (deterministic host logic + identical kernels)
-    plans = plan(transform, shape, src_shape, method, bound, world, invert_points)
+    plans = plan(transform, shape, src_shape, method, bound, world, invert_points, oblur=kw.get("oblur"))
     mine = plans[rank]
 
     # ---- scatter: root -> rank r : its sub-rectangle ----
