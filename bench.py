@@ -217,6 +217,12 @@ def extra_configs(t, torch, np, timed):
         ms = timed(lambda: trx.resample(src8, method="linear", precision="fp32", out=dst8), reps=10)
         out["linear_%s_8192_fp32_ms" % name] = ms
         out["linear_%s_8192_fp32_roofline_frac" % name] = ALG_BYTES / (ms * 1e-3) / 1e9 / peak
+    # the reference's windowed input-plane filters on the named chain (Hann: 2x2 region inside K1;
+    # Lanczos: 6x6 region, general filter kernel)
+    trn = t.Composition([t.Scale(1.3, dim=2), t.Rotation(30, unit="deg"), t.Offset([-n8 / 2.0, -n8 / 2.0])])
+    for m in ("hann", "zlanczos"):
+        ms = timed(lambda: trn.resample(src8, method=m, precision="fp32", out=dst8), reps=5)
+        out["%s_named_8192_fp32_ms" % m] = ms
     del src8, dst8
     # config 4: batch of 64 4096^2 frames, TAN -> CAR, linear (one launch, frames as planes)
     hdr = {'NAXIS': 2, 'NAXIS1': n, 'NAXIS2': n, 'CTYPE1': 'RA---TAN', 'CTYPE2': 'DEC--TAN', 'CUNIT1': 'deg',

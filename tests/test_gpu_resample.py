@@ -287,3 +287,19 @@ def test_filters_batched_and_f64(tfm, oracle):
     for k in range(3):
         want = oracle.resample(to_oracle(tr), src[k], method='g', bound='p')
         assert_close_rel(got[k], want, 1e-12, k)
+
+
+def test_filter_2x2_route_equals_general_kernel(tfm):
+    """Hann / Tukey / tent regions of 2 x 2 run inside k_resample; tuning bit 64 forces the general
+    filter kernel.  Same arithmetic, same order: identical bits in parity mode."""
+    rng = np.random.default_rng(80)
+    src = rng.random((50, 70)).astype(np.float32)
+    tr = tfm.Composition([tfm.Scale(1.4, dim=2), tfm.Rotation(33, unit='deg'), tfm.Offset([-30.0, -20.0])])
+    for m, ob in (("h", None), ("t", None), ("l", 0.7), ("h", 1.0)):
+        for bound in ('t', 'p'):
+            a = tr.resample(src, method=m, bound=bound, oblur=ob, shape=(64, 96))
+            b = tr.resample(src, method=m, bound=bound, oblur=ob, shape=(64, 96), tuning=64)
+            assert np.array_equal(a, b, equal_nan=True), (m, ob, bound)
+        a = tr.resample(src, method=m, oblur=ob, precision='fp32')
+        b = tr.resample(src, method=m, oblur=ob, precision='fp32', tuning=64)
+        assert np.allclose(a, b, rtol=0, atol=2e-6), (m, ob)

@@ -42,6 +42,8 @@ struct ResampleParams {
     float aff_margin;                        // absolute fp32 rounding allowance for that test
     double fill;
     int *status;
+    int win_method;                          // TFM_WIN2 kernels: which window (TFM_HANN / TFM_TUKEY / TFM_TENT ...)
+    double win_oblur;
     ChainDev chain;
 };
 
@@ -169,10 +171,80 @@ __device__ __forceinline__ float hermite_fast(float r0, float r1, float r2, floa
     return r1 + b * (s0 + b * (c2 + b * c3));
 }
 
+// ---------------------------------------------------------------------------------------------
+// window functions of the collapsible filters (helpers.pyx:792-835; see k_resample_filter below)
+// ---------------------------------------------------------------------------------------------
+struct FilterParams {
+    int method;                              // TFM_SINC .. TFM_TENT
+    int size;                                // region edge S
+    int offset;                              // S/2 - 1
+    double oblur;                            // 1.0 when None
+};
+
+__device__ __forceinline__ double clip_keepnan(double x, double lo, double hi)
+{
+    return x < lo ? lo : (x > hi ? hi : x);             // NaN falls through, like np.clip
+}
+
+__device__ __forceinline__ double np_sinc(double x)
+{
+    const double y = __dmul_rn(3.141592653589793, x == 0.0 ? 1.0e-20 : x);     // numpy.sinc
+    return __ddiv_rn(sin(y), y);
+}
+
+// window value at offset `of`, operation order of helpers.pyx:809-826
+__device__ __forceinline__ double window_exact(int m, double of)
+{
+    switch (m) {
+    case TFM_SINC: return np_sinc(of);
+    case TFM_LANCZOS: {
+        const double bb = clip_keepnan(of, -3.0, 3.0);
+        return __dmul_rn(__dmul_rn(3.0, np_sinc(bb)), np_sinc(__ddiv_rn(bb, 3.0)));
+    }
+    case TFM_GAUSSIAN: return exp(__dmul_rn(__dmul_rn(__dmul_rn(-of, of), 2.0), 2.0));   // -bb*bb/0.5/0.5
+    case TFM_HANN: return __dadd_rn(1.0, cos(__dmul_rn(3.141592653589793, clip_keepnan(of, -1.0, 1.0))));
+    case TFM_TUKEY:
+        return __dadd_rn(1.0, cos(__dmul_rn(3.141592653589793,
+                                            clip_keepnan(__dsub_rn(__dmul_rn(fabs(of), 2.0), 0.5), 0.0, 1.0))));
+    default: return __dsub_rn(1.0, clip_keepnan(fabs(of), 0.0, 1.0));
+    }
+}
+
+__device__ __forceinline__ float window_fast(int m, float of)
+{
+    // sinpif / cospif reduce the argument exactly (the sinc and Lanczos weights alternate in sign, so
+    // absolute errors of the plain fast intrinsics would not cancel); 2S evaluations per pixel only
+    const float PI = 3.14159265358979f;
+    switch (m) {
+    case TFM_SINC: {
+        const float y = PI * of;
+        return fabsf(of) < 1e-4f ? 1.0f : __fdividef(sinpif(of), y);
+    }
+    case TFM_LANCZOS: {
+        const float bb = fminf(fmaxf(of, -3.0f), 3.0f);
+        const float b3 = bb * (1.0f / 3.0f);
+        return fabsf(bb) < 1e-3f ? 3.0f : __fdividef(3.0f * sinpif(bb) * sinpif(b3), (PI * PI) * bb * b3);
+    }
+    case TFM_GAUSSIAN: return exp2f(-5.770780163555854f * of * of);              // exp(-4 of^2)
+    case TFM_HANN: return 1.0f + cospif(fminf(fmaxf(of, -1.0f), 1.0f));
+    case TFM_TUKEY: return 1.0f + cospif(fminf(fmaxf(fabsf(of) * 2.0f - 0.5f, 0.0f), 1.0f));
+    default: return 1.0f - fminf(fabsf(of), 1.0f);
+    }
+}
+
+// of_i = ((1 - b) - (offset + 1) + i) / oblur      (helpers.pyx:800-802)
+__device__ __forceinline__ double filt_of(double one_minus_b, const FilterParams &F, int i)
+{
+    return __ddiv_rn(__dadd_rn(__dsub_rn(one_minus_b, (double)(F.offset + 1)), (double)i), F.oblur);
+}
+
+#define TFM_WIN2 9   // internal METHOD: any filter whose region is 2 x 2 (Hann, Tukey, tent with oblur <= 1)
+
 template <int METHOD> struct MethodTraits;
 template <> struct MethodTraits<TFM_NEAREST> { static constexpr int NPX = 4, NT = 1; };
 template <> struct MethodTraits<TFM_LINEAR>  { static constexpr int NPX = 4, NT = 2; };
 template <> struct MethodTraits<TFM_CUBIC>   { static constexpr int NPX = 2, NT = 4; };
+template <> struct MethodTraits<TFM_WIN2>    { static constexpr int NPX = 4, NT = 2; };
 
 // floor + fractional part without the conversion (XU) pipe: t = x + 1.5*2^52 rounds x to the nearest
 // integer in the low mantissa bits; one compare-and-correct turns round-to-nearest into floor.
@@ -219,6 +291,29 @@ __device__ __forceinline__ void finish(const ResampleParams &P, RegT (&v)[NPX][N
                 const float top = fmaf(ax, (float)v[j][0][1] - (float)v[j][0][0], (float)v[j][0][0]);
                 const float bot = fmaf(ax, (float)v[j][1][1] - (float)v[j][1][0], (float)v[j][1][0]);
                 r = (RegT)fmaf(ay, bot - top, top);
+            }
+        } else if (METHOD == TFM_WIN2) {
+            // 2 x 2 region of a collapsible filter (helpers.pyx:792-835), offset = 0:
+            //   of_i = ((1 - b) - 1 + i) / oblur;  row_j = (kx0 v_j0 + kx1 v_j1) / (kx0 + kx1);
+            //   out = (ky0 row_0 + ky1 row_1) / (ky0 + ky1)
+            if (!FASTI) {
+                FilterParams F;
+                F.method = P.win_method; F.size = 2; F.offset = 0; F.oblur = P.win_oblur;
+                const double bx1 = __dsub_rn(1.0, fracx[j]), by1 = __dsub_rn(1.0, fracy[j]);
+                const double kx0 = window_exact(F.method, filt_of(bx1, F, 0)), kx1 = window_exact(F.method, filt_of(bx1, F, 1));
+                const double ky0 = window_exact(F.method, filt_of(by1, F, 0)), ky1 = window_exact(F.method, filt_of(by1, F, 1));
+                const double kxs = __dadd_rn(kx0, kx1), kys = __dadd_rn(ky0, ky1);
+                const double r0 = __ddiv_rn(__dadd_rn(__dmul_rn(kx0, (double)v[j][0][0]), __dmul_rn(kx1, (double)v[j][0][1])), kxs);
+                const double r1 = __ddiv_rn(__dadd_rn(__dmul_rn(kx0, (double)v[j][1][0]), __dmul_rn(kx1, (double)v[j][1][1])), kxs);
+                r = (RegT)__ddiv_rn(__dadd_rn(__dmul_rn(ky0, r0), __dmul_rn(ky1, r1)), kys);
+            } else {
+                const float iob = 1.0f / (float)P.win_oblur;
+                const float bx1 = 1.0f - ffx[j], by1 = 1.0f - ffy[j];
+                const float kx0 = window_fast(P.win_method, (bx1 - 1.0f) * iob), kx1 = window_fast(P.win_method, bx1 * iob);
+                const float ky0 = window_fast(P.win_method, (by1 - 1.0f) * iob), ky1 = window_fast(P.win_method, by1 * iob);
+                const float r0 = fmaf(kx1, (float)v[j][0][1], kx0 * (float)v[j][0][0]);
+                const float r1 = fmaf(kx1, (float)v[j][1][1], kx0 * (float)v[j][1][0]);
+                r = (RegT)__fdividef(fmaf(ky1, r1, ky0 * r0), (kx0 + kx1) * (ky0 + ky1));
             }
         } else {
             if (!FASTI) {
@@ -613,70 +708,6 @@ static bool get_texture(const void *ptr, int w, int h, long long pitch, cudaText
 // oracle_np.interp_filter): the x normaliser is a sequential sum (strided axis), the other three
 // reductions use NumPy's pairwise scheme -- 8 interleaved partial sums over the first 8*floor(S/8)
 // terms, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the remainder sequentially.
-struct FilterParams {
-    int method;                              // TFM_SINC .. TFM_TENT
-    int size;                                // region edge S
-    int offset;                              // S/2 - 1
-    double oblur;                            // 1.0 when None
-};
-
-__device__ __forceinline__ double clip_keepnan(double x, double lo, double hi)
-{
-    return x < lo ? lo : (x > hi ? hi : x);             // NaN falls through, like np.clip
-}
-
-__device__ __forceinline__ double np_sinc(double x)
-{
-    const double y = __dmul_rn(3.141592653589793, x == 0.0 ? 1.0e-20 : x);     // numpy.sinc
-    return __ddiv_rn(sin(y), y);
-}
-
-// window value at offset `of`, operation order of helpers.pyx:809-826
-__device__ __forceinline__ double window_exact(int m, double of)
-{
-    switch (m) {
-    case TFM_SINC: return np_sinc(of);
-    case TFM_LANCZOS: {
-        const double bb = clip_keepnan(of, -3.0, 3.0);
-        return __dmul_rn(__dmul_rn(3.0, np_sinc(bb)), np_sinc(__ddiv_rn(bb, 3.0)));
-    }
-    case TFM_GAUSSIAN: return exp(__dmul_rn(__dmul_rn(__dmul_rn(-of, of), 2.0), 2.0));   // -bb*bb/0.5/0.5
-    case TFM_HANN: return __dadd_rn(1.0, cos(__dmul_rn(3.141592653589793, clip_keepnan(of, -1.0, 1.0))));
-    case TFM_TUKEY:
-        return __dadd_rn(1.0, cos(__dmul_rn(3.141592653589793,
-                                            clip_keepnan(__dsub_rn(__dmul_rn(fabs(of), 2.0), 0.5), 0.0, 1.0))));
-    default: return __dsub_rn(1.0, clip_keepnan(fabs(of), 0.0, 1.0));
-    }
-}
-
-__device__ __forceinline__ float window_fast(int m, float of)
-{
-    // sinpif / cospif reduce the argument exactly (the sinc and Lanczos weights alternate in sign, so
-    // absolute errors of the plain fast intrinsics would not cancel); 2S evaluations per pixel only
-    const float PI = 3.14159265358979f;
-    switch (m) {
-    case TFM_SINC: {
-        const float y = PI * of;
-        return fabsf(of) < 1e-4f ? 1.0f : __fdividef(sinpif(of), y);
-    }
-    case TFM_LANCZOS: {
-        const float bb = fminf(fmaxf(of, -3.0f), 3.0f);
-        const float b3 = bb * (1.0f / 3.0f);
-        return fabsf(bb) < 1e-3f ? 3.0f : __fdividef(3.0f * sinpif(bb) * sinpif(b3), (PI * PI) * bb * b3);
-    }
-    case TFM_GAUSSIAN: return exp2f(-5.770780163555854f * of * of);              // exp(-4 of^2)
-    case TFM_HANN: return 1.0f + cospif(fminf(fmaxf(of, -1.0f), 1.0f));
-    case TFM_TUKEY: return 1.0f + cospif(fminf(fmaxf(fabsf(of) * 2.0f - 0.5f, 0.0f), 1.0f));
-    default: return 1.0f - fminf(fabsf(of), 1.0f);
-    }
-}
-
-// of_i = ((1 - b) - (offset + 1) + i) / oblur      (helpers.pyx:800-802)
-__device__ __forceinline__ double filt_of(double one_minus_b, const FilterParams &F, int i)
-{
-    return __ddiv_rn(__dadd_rn(__dsub_rn(one_minus_b, (double)(F.offset + 1)), (double)i), F.oblur);
-}
-
 // NumPy's pairwise reduction over n streamed terms; term(i) is called exactly once per i, in order.
 template <class TermFn>
 __device__ __forceinline__ double np_pairwise_sum(int n, TermFn term)
@@ -701,6 +732,42 @@ __device__ __forceinline__ double np_pairwise_sum(int n, TermFn term)
     }
     for (; i < n; ++i) res = __dadd_rn(res, term(i));
     return res;
+}
+
+// two reductions of the same length in one pass (term(i, a, b) yields both addends)
+template <class TermFn>
+__device__ __forceinline__ void np_pairwise_sum2(int n, TermFn term, double &sa, double &sb)
+{
+    const int nb = n >> 3;
+    int i = 0;
+    if (nb == 0) {
+        term(0, sa, sb);
+        i = 1;
+    } else {
+        double r[8], q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) term(k, r[k], q[k]);
+        for (int b = 1; b < nb; ++b) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                double ta, tb;
+                term(b * 8 + k, ta, tb);
+                r[k] = __dadd_rn(r[k], ta);
+                q[k] = __dadd_rn(q[k], tb);
+            }
+        }
+        sa = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                       __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        sb = __dadd_rn(__dadd_rn(__dadd_rn(q[0], q[1]), __dadd_rn(q[2], q[3])),
+                       __dadd_rn(__dadd_rn(q[4], q[5]), __dadd_rn(q[6], q[7])));
+        i = nb * 8;
+    }
+    for (; i < n; ++i) {
+        double ta, tb;
+        term(i, ta, tb);
+        sa = __dadd_rn(sa, ta);
+        sb = __dadd_rn(sb, tb);
+    }
 }
 
 // one collapsed row (exact mode): sum_i kx_i * tap(i), pairwise order.  Kept out of line: the y
@@ -746,6 +813,11 @@ k_resample_filter(const __grid_constant__ ResampleParams P, const __grid_constan
     const bool interior = okx && oky && gx0 >= P.src_x0 && gy0 >= P.src_y0 &&
                           gx0 + S <= (long long)P.src_x0 + P.src_w && gy0 + S <= (long long)P.src_y0 + P.src_h;
     DstT *const out = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch) + X;
+    // truncated axis with the whole region out of range (or an invalid coordinate): every tap is
+    // the fill value -- one collapsed row serves all S rows, and nothing is loaded
+    const bool allfill =
+        (P.bound_x == TFM_B_TRUNCATE && (!okx || gx0 >= (long long)P.full_w || gx0 + S <= 0)) ||
+        (P.bound_y == TFM_B_TRUNCATE && (!oky || gy0 >= (long long)P.full_h || gy0 + S <= 0));
 
     if (!FASTI) {
         const double bx1 = __dsub_rn(1.0, __dsub_rn(x, fx)), by1 = __dsub_rn(1.0, __dsub_rn(y, fy));
@@ -756,14 +828,22 @@ k_resample_filter(const __grid_constant__ ResampleParams P, const __grid_constan
             kxs = (i == 0) ? k : __dadd_rn(kxs, k);
         }
         const double *kxd = reinterpret_cast<const double *>(kx);
-        const double kys = np_pairwise_sum(S, [&](int j) { return window_exact(F.method, filt_of(by1, F, j)); });
-        const double acc = np_pairwise_sum(S, [&](int j) {
+        double row_fill = 0.0;
+        if (allfill) row_fill = np_pairwise_sum(S, [&](int i) { return __dmul_rn(kxd[i * 256], P.fill); });
+        double acc, kys;
+        np_pairwise_sum2(S, [&](int j, double &ta, double &tb) {
             const double ky = window_exact(F.method, filt_of(by1, F, j));
-            const double row = filt_row_exact<SrcT, true>(P, src_base, kxd, S, gx0, oky ? gy0 + j : gy0, okx, interior);
-            return __dmul_rn(ky, __ddiv_rn(row, kxs));
-        });
+            const double row = allfill ? row_fill
+                                       : filt_row_exact<SrcT, true>(P, src_base, kxd, S, gx0, oky ? gy0 + j : gy0, okx, interior);
+            ta = __dmul_rn(ky, __ddiv_rn(row, kxs));
+            tb = ky;
+        }, acc, kys);
         *out = (DstT)__ddiv_rn(acc, kys);
     } else {
+        if (allfill) {
+            *out = (DstT)((float)P.fill + (float)((x - x) + (y - y)));          // NaN / inf coordinates stay NaN
+            return;
+        }
         const float bx1 = 1.0f - (float)(x - fx), by1 = 1.0f - (float)(y - fy);
         const float iob = 1.0f / (float)F.oblur, o1 = (float)(F.offset + 1);
         float kxs = 0.0f;
@@ -779,8 +859,15 @@ k_resample_filter(const __grid_constant__ ResampleParams P, const __grid_constan
             kys += ky;
             float row = 0.0f;
             if (interior) {
+                // S is even: two independent chains, several taps in flight per iteration
                 const SrcT *r = reinterpret_cast<const SrcT *>(src_base + (gy0 + j - P.src_y0) * P.src_pitch) + (gx0 - P.src_x0);
-                for (int i = 0; i < S; ++i) row = fmaf(kxf[i * 256], (float)__ldg(r + i), row);
+                float ra = 0.0f, rb = 0.0f;
+#pragma unroll 4
+                for (int i = 0; i < S; i += 2) {
+                    ra = fmaf(kxf[i * 256], (float)__ldg(r + i), ra);
+                    rb = fmaf(kxf[(i + 1) * 256], (float)__ldg(r + i + 1), rb);
+                }
+                row = ra + rb;
             } else {
                 for (int i = 0; i < S; ++i)
                     row = fmaf(kxf[i * 256], tap_generic<SrcT, float>(P, src_base, okx ? gx0 + i : gx0, oky ? gy0 + j : gy0), row);
@@ -858,6 +945,7 @@ static cudaError_t launch1(int method, ResampleParams &P, bool generic, bool aff
     switch (method) {
     case TFM_NEAREST: return launch2<TFM_NEAREST, SrcT, DstT, A, RegT>(P, generic, aff, st, name);
     case TFM_LINEAR:  return launch2<TFM_LINEAR, SrcT, DstT, A, RegT>(P, generic, aff, st, name);
+    case TFM_WIN2:    return launch2<TFM_WIN2, SrcT, DstT, A, RegT>(P, generic, aff, st, name);
     default:          return launch2<TFM_CUBIC, SrcT, DstT, A, RegT>(P, generic, aff, st, name);
     }
 }
@@ -956,7 +1044,19 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         if (sz > (double)TFM_FILTER_MAX_SIZE) return TFM_EUNSUPPORTED;
         F.size = (int)sz;
         F.offset = F.size / 2 - 1;
-        if (exact && s.dtype == TFM_F32 && d.dtype == TFM_F64)
+        P.win_method = F.method;
+        P.win_oblur = F.oblur;
+        if (F.size == 2 && !(a->tuning & 64)) {
+            // 2 x 2 regions share k_resample's tiling, warp classification and tap code
+            if (exact && s.dtype == TFM_F32 && d.dtype == TFM_F64)
+                e = launch1<float, double, Exact, double>(TFM_WIN2, P, generic, false, st, &name);
+            else if (exact && s.dtype == TFM_F64 && d.dtype == TFM_F64)
+                e = launch1<double, double, Exact, double>(TFM_WIN2, P, generic, false, st, &name);
+            else if (!exact && s.dtype == TFM_F32 && d.dtype == TFM_F32)
+                e = launch1<float, float, Fast, float>(TFM_WIN2, P, generic, aff, st, &name);
+            else
+                return TFM_EUNSUPPORTED;
+        } else if (exact && s.dtype == TFM_F32 && d.dtype == TFM_F64)
             e = launch_filter<float, double, Exact, double>(P, F, st, &name);
         else if (exact && s.dtype == TFM_F64 && d.dtype == TFM_F64)
             e = launch_filter<double, double, Exact, double>(P, F, st, &name);
