@@ -55,10 +55,12 @@ typedef enum tfm_op_kind {
     TFM_OP_LINEAR = 1,     /* basic.py:12-218 (+Scale 224-336, Rotation 338-506, Offset 508-551) */
     TFM_OP_RADIAL = 2,     /* basic.py:553-716 */
     TFM_OP_WCS = 3,        /* core.py:1650-1747 (astropy.wcs all_pix2world/all_world2pix, origin 0) */
-    TFM_OP_INDEX = 4       /* coordinate lookup: (x,y) = index[y][x][0..1].  Not a Transform of the
+    TFM_OP_INDEX = 4,      /* coordinate lookup: (x,y) = index[y][x][0..1].  Not a Transform of the
                               reference: it is how interpND(source, index, ...) / interpND_grid
                               (helpers.pyx:379, 1293), which take a precomputed coordinate array,
                               run through the same kernels.  Must be the first element of a chain. */
+    TFM_OP_PIN = 5         /* per-axis pincushion family: Quadpin (basic.py:846-1017), Cubicpin
+                              (1020-1175), Poly / Quarticpin (1178-1462, forward only) */
 } tfm_op_kind;
 
 typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
@@ -96,6 +98,37 @@ typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
 /* TFM_OP_INDEX
  *   p[0] the BIT PATTERN of a device pointer to float64 index[ny][nx][2] (dense, (X,Y) last axis)
  *   p[1] nx   p[2] ny   (grid points outside [0,nx) x [0,ny) yield NaN coordinates) */
+
+/* TFM_OP_PIN  -- elementwise per axis a (0 = X, 1 = Y); parameter block of axis a at p[12a ..]:
+ *   [0] origin   [1..4] c0..c3   [5..11] length^(k-1) for k = 2..8 (Poly only)
+ * The constants are the reference's own Python-scalar sub-expressions, evaluated by the host shim
+ * exactly as the reference evaluates them (d = input component, o = origin):
+ *   Quadpin  fwd (basic.py:932-967):  u=d-o; u = u + ((c0*(u*|u|))/c1); u = u/c2; +o
+ *            c0 = strength, c1 = length, c2 = |strength|+1
+ *   Quadpin  rev (970-1010): u = -1 + sqrt(1 + ((c0*|d-o|)*c1)); u = (u*c2)/c3; u *= (d<o ? -1 : 1); +o
+ *            c0 = 4*strength/length, c1 = 1+|strength|, c2 = length, c3 = 2*strength
+ *   Cubicpin fwd (1097-1128): u=d-o; q=u/c1; u = u + (((c0*u)*q)*q); u = u/c2; +o
+ *            c0 = strength, c1 = length, c2 = strength^2+1
+ *   Cubicpin rev (1130-1170), A = strength/length/length: u=(d-o)*c0; al = c1*(-u);
+ *            in = sqrt(al*al + c2); root(x) = sign(x)*|x|^(1/3);
+ *            u = c3*(root(0.5*(al+in)) + root(0.5*(al-in))); +o
+ *            c0 = strength+1, c1 = 27*A*A, c2 = 4*(3A)^3, c3 = -1/(3A)
+ *   Poly     fwd (1318-1358): u=d-o; a=u; for k=2..degree: a = a + ((c0*u^k)/length^(k-1)); u = c1*a; +o
+ *            c0 = strength, c1 = 1/(|strength|^(degree-1)+1) (den=1) or 1/(|strength|+1);
+ *            degree in tfm_op.reserved (2..8)
+ * flags: bits 0-1 TFM_PIN_QUAD / CUBIC / POLY; TFM_PIN_SHIFTED: origin is not all-zero (the
+ * subtraction and re-addition happen only then); TFM_PIN_DIM1: only the X component (dim=1). */
+#define TFM_PIN_QUAD 0
+#define TFM_PIN_CUBIC 1
+#define TFM_PIN_POLY 2
+#define TFM_PIN_SHIFTED 4
+#define TFM_PIN_DIM1 8
+#define TFM_PIN_TRUNC 16   /* cast the result to int64 (C truncation; NaN/inf -> INT64_MIN): what the
+                              reference does when a pincushion op constructed with `dim=` is the first
+                              op applied to INTEGER data -- e.g. the np.mgrid pixel grid of resample()
+                              (core.py:574-578) -- because it writes its result back into the copy of
+                              its input (basic.py:962-965, 1005-1008, 1123-1126, 1165-1168, 1353-1356) */
+#define TFM_PIN_MAX_DEGREE 8
 
 typedef struct tfm_op {
     int32_t kind;          /* tfm_op_kind */
@@ -141,6 +174,8 @@ typedef enum tfm_precision {
 #define TFM_F_REGION_SRC_DTYPE 1 /* cubic, exact mode: first Hermite pass in the SOURCE dtype (float32)
                                     because the reference's region was not promoted by the truncation
                                     pass (helpers.pyx:373-374, 755-762) */
+#define TFM_F_FLUX 2 /* K2 only: phot='flux' (core.py:521-533, documented but not implemented there;
+                        SVD.pyx:285-286 has it): scale each output by |det J| of the unpadded Jacobian */
 
 /* One 2-D image plane in device memory.  (x0,y0) is the position of element [0][0] in the
  * coordinate system of the FULL image of size full_w x full_h: a whole image has x0=y0=0 and

@@ -210,6 +210,150 @@ class Radial(Op):
         return out
 
 
+class _Pin(Op):
+    """Shared parameter handling of Quadpin / Cubicpin / Poly (basic.py:899-929, 1064-1094,
+    1281-1315): origin, length and strength are scalars or per-axis vectors; `dim` limits the
+    transform to the first `dim` components (idim = odim = dim)."""
+
+    def __init__(self, origin=0, length=1, strength=0.0, dim=None, idim=0):
+        self.origin, self.length, self.strength, self.dim = origin, length, strength, dim
+        self.idim = self.odim = int(idim) if dim is None else int(dim)          # basic.py:912-914
+
+    def _split(self, data):
+        data = np.array(data)                                  # `data = data.copy()`: dtype kept
+        out = data[..., :self.dim].copy() if self.dim is not None else data.copy()
+        return data, out
+
+    def _join(self, data, out):
+        # Quirk kept (basic.py:962-965 and twins): with `dim` given the result is written back INTO
+        # the copy of the input, so integer input -- the np.mgrid pixel grid that resample() feeds the
+        # first reverse op (core.py:574-578) -- truncates the transformed coordinates to int64.
+        # Without `dim` (e.g. idim=2, odim=2) the float result is returned as is.
+        if self.dim is not None:
+            with np.errstate(invalid="ignore"):
+                data[..., :self.dim] = out
+            return data
+        return out
+
+
+class Quadpin(_Pin):
+    """Quadratic pincushion, per axis (basic.py:846-1017)."""
+
+    def __init__(self, origin=0, length=1, strength=0.1, dim=None, idim=0):
+        super().__init__(origin, length, strength, dim, idim)
+
+    def forward(self, v):                                      # basic.py:932-967
+        data, out = self._split(v)
+        origin, strength, length = self.origin, self.strength, self.length
+        shifted = not np.all(origin == 0)
+        if shifted:
+            origin = np.array([origin])
+            out = out - origin
+        out = out + strength * (out * np.abs(out)) / length
+        out = out / (np.abs(strength) + 1)
+        if shifted:
+            out = out + origin
+        return self._join(data, out)
+
+    def reverse(self, v):                                      # basic.py:970-1010
+        data, out = self._split(v)
+        origin, strength, length = self.origin, self.strength, self.length
+        od = out.copy()
+        shifted = not np.all(origin == 0)
+        if shifted:
+            origin = np.array([origin])
+            od = out - origin
+        cmp = (data[..., :self.dim] if self.dim is not None else data) < origin   # `data < origin`, unshifted
+        with np.errstate(invalid="ignore"):
+            out = -1.0 + np.sqrt(1.0 + 4.0 * strength / length * np.abs(od) * (1.0 + np.abs(strength)))
+            out = out * length / (2.0 * strength)
+            out = out * (1.0 - 2.0 * cmp)
+        if shifted:
+            out = out + origin
+        return self._join(data, out)
+
+
+class Cubicpin(_Pin):
+    """Cubic pincushion, per axis (basic.py:1020-1175).  As coded: the forward divides by
+    strength^2 + 1 where the reverse multiplies by strength + 1, and the reverse evaluates BOTH
+    Cardano roots (the first `try` dies on an unbound name after computing the negative branch;
+    the bare `except` computes the positive one) -- reproduced, not repaired."""
+
+    def __init__(self, origin=0, length=1, strength=0.0, dim=None, idim=0):
+        super().__init__(origin, length, strength, dim, idim)
+
+    def forward(self, v):                                      # basic.py:1097-1128
+        data, out = self._split(v)
+        origin, strength, length = self.origin, self.strength, self.length
+        shifted = not np.all(origin == 0)
+        if shifted:
+            origin = np.array([origin])
+            out = out - origin
+        dl0 = out / length
+        out = out + strength * out * dl0 * dl0
+        out = out / ((strength * strength) + 1)
+        if shifted:
+            out = out + origin
+        return self._join(data, out)
+
+    def reverse(self, v):                                      # basic.py:1130-1170
+        data, out = self._split(v)
+        origin, strength, length = self.origin, self.strength, self.length
+        shifted = not np.all(origin == 0)
+        if shifted:
+            origin = np.array([origin])
+            out = out - origin
+        out = out * (strength + 1)
+        A = strength / length / length
+        D = -out
+        alpha = 27 * A * A * D
+        beta = 3 * A * 1
+        with np.errstate(all="ignore"):
+            inner = np.sqrt(alpha * alpha + 4.0 * beta * beta * beta)
+            an = 0.5 * (alpha - inner)
+            cn = (1 - 2 * (an < 0)) * (abs(an) ** (1 / 3))
+            ap = 0.5 * (alpha + inner)
+            cp = (1 - 2 * (ap < 0)) * (abs(ap) ** (1 / 3))
+            cuberoot = cp + cn
+            try:
+                out = (-1 / (3 * A)) * cuberoot
+            except ZeroDivisionError:
+                out = (-1 / (3 * np.nan)) * cuberoot
+        if shifted:
+            out = out + origin
+        return self._join(data, out)
+
+
+class Poly(_Pin):
+    """Forward-only polynomial pincushion (basic.py:1178-1362); Quarticpin = Poly(degree=4, strength=0.1)."""
+
+    def __init__(self, origin=0, length=1, strength=0.0, degree=2, dim=None, den=1, idim=0):
+        super().__init__(origin, length, strength, dim, idim)
+        self.degree, self.den = degree, den
+
+    def forward(self, v):                                      # basic.py:1318-1358
+        data, out = self._split(v)
+        origin, strength, length = self.origin, self.strength, self.length
+        shifted = not np.all(origin == 0)
+        if shifted:
+            origin = np.array([origin])
+            out = out - origin
+        a = out
+        if self.den != 1:
+            sc = 1.0 / (np.abs(strength) + 1)
+        else:
+            sc = 1.0 / (np.abs(strength) ** (self.degree - 1) + 1)
+        for k in range(2, self.degree + 1):
+            a = a + strength * (out ** k) / (length ** (k - 1))
+        out = sc * a
+        if shifted:
+            out = out + origin
+        return self._join(data, out)
+
+    def reverse(self, v):
+        raise AssertionError("Poly is invalid in the reverse direction")
+
+
 class Identity(Op):
     idim = 0
     odim = 0
@@ -255,15 +399,32 @@ class Composition(Op):
         return v
 
 
+def _first_leaf_is_dim_pin(t, invert):
+    """Is the first leaf op that `t` applies (in the given direction) a pincushion op with `dim`?"""
+    while True:
+        if isinstance(t, Inverse):
+            t, invert = t.t, not invert
+        elif isinstance(t, Composition):
+            t = t.ops[0] if invert else t.ops[-1]
+        else:
+            return isinstance(t, _Pin) and t.dim is not None
+
+
 def apply(t, data, invert=False):
     """Transform.apply for 2-D transforms (core.py:218-294): extra trailing components are
     passed through unchanged (core.py:271-276, 287-292)."""
     data = np.asarray(data)
     d = data.astype(np.float64)
+    if data.dtype.kind in "iu" and _first_leaf_is_dim_pin(t, invert):
+        d = data                                 # integer input reaches a pincushion op with `dim`: see _Pin._join
     fn = t.reverse if invert else t.forward
     n = 2
     if isinstance(t, Identity):
         return d
+    if isinstance(t, _Pin):                      # idim = dim, or 0 = every component (core.py:271-292)
+        n = t.idim
+        if n == 0:
+            return fn(d)
     if d.shape[-1] < n:
         raise ValueError("requires %d dimensions; data have %d" % (n, d.shape[-1]))
     if d.shape[-1] > n:
@@ -538,6 +699,13 @@ def pixel_grid(ny, nx, y0=0, y1=None):
     return g
 
 
+def _grid_for(t, ny, nx, y0=0, y1=None):
+    """The grid as the first reverse op sees it: np.mgrid is int64 (core.py:574-578), which matters
+    only to a pincushion op with `dim` (it writes its result back into the integer array)."""
+    g = pixel_grid(ny, nx, y0, y1)
+    return g.astype(np.int64) if _first_leaf_is_dim_pin(t, True) else g
+
+
 def resample(t, data, method="n", bound="t", shape=None, fillvalue=0, rows=None, tile=256, oblur=None):
     """Transform.resample (core.py:422-586) for 2-D data.  `rows=(y0,y1)` restricts the output to
     a row block (used for row-tiled / multi-process CPU baselines)."""
@@ -550,7 +718,7 @@ def resample(t, data, method="n", bound="t", shape=None, fillvalue=0, rows=None,
     out = None
     for ya in range(y0, y1, tile):
         yb = min(y1, ya + tile)
-        coords = t.reverse(pixel_grid(ny, nx, ya, yb))
+        coords = t.reverse(_grid_for(t, ny, nx, ya, yb))
         blk = interpND(data, coords, method=m, bound=bound, fillvalue=fillvalue, oblur=oblur)
         if out is None:
             out = np.empty((y1 - y0, nx), dtype=blk.dtype)
@@ -676,8 +844,10 @@ _BOUND_CODE = {"f": 1, "t": 2, "e": 3, "p": 4, "m": 5}           # helpers.pyx:1
 
 
 def interp_jacobian(source, index, J, method="g", bound="t", fillvalue=0, oblur=1.0, iblur=1.0,
-                    pad_pow=8, max_reg=0):
-    """interpND_jacobian (helpers.pyx:1542-1803) via oracle_c.orc_interp_jacobian."""
+                    pad_pow=8, max_reg=0, phot="radiance"):
+    """interpND_jacobian (helpers.pyx:1542-1803) via oracle_c.orc_interp_jacobian.
+    phot='flux' (documented at core.py:521-533, not implemented there): scale by |det J| of the
+    unpadded Jacobian, the rule of the reference's other anti-aliaser (SVD.pyx:285-286)."""
     try:
         mcode = _METHOD_CODE[method[0]]
     except KeyError:
@@ -698,11 +868,13 @@ def interp_jacobian(source, index, J, method="g", bound="t", fillvalue=0, oblur=
         raise ValueError("value out of bounds with Forbid boundary in effect")
     if rc != 0:
         raise ValueError("interpND_jacobian: invalid interpolation method")
+    if phot[0].lower() in ("f", "e"):
+        dest = dest * np.abs(Jc[..., 0, 0] * Jc[..., 1, 1] - Jc[..., 0, 1] * Jc[..., 1, 0])
     return dest
 
 
 def interp_grid_jacobian(source, index, method="g", bound="t", fillvalue=0, oblur=1.0, iblur=1.0,
-                         pad_pow=8, jump_detect=4.0, max_reg=0):
+                         pad_pow=8, jump_detect=4.0, max_reg=0, phot="radiance"):
     """interpND_grid with antialias=True (helpers.pyx:1480-1530), 2-D only.
 
     The shipped code cannot run.  Repairs applied, each a named
@@ -733,7 +905,7 @@ def interp_grid_jacobian(source, index, method="g", bound="t", fillvalue=0, oblu
         raise ValueError("interpND_grid: anti-aliasing is only implemented for 2-D at present.")
     J = jacobian(index, jump_thresh=jump_detect)
     return interp_jacobian(source, index, J, method, bound, fillvalue, oblur, iblur, pad_pow,
-                           max_reg)
+                           max_reg, phot)
 
 
 def resample_jacobian(t, data, method="g", bound="t", shape=None, rows=None, **kw):

@@ -54,6 +54,15 @@ def to_oracle(tr):
     if name == "Radial":
         return o.Radial(origin=np.asarray(p["origin"], dtype=float)[0:2].reshape(-1)[0:2],
                         r0=p["r0"], ang_coeff=p["ang_coeff"], ccw=p["ccw"], pos_only=p["pos"])
+    if name == "Quadpin":
+        return o.Quadpin(origin=p["origin"], length=p["length"], strength=p["strength"],
+                         dim=p["dim"], idim=tr.idim)
+    if name == "Cubicpin":
+        return o.Cubicpin(origin=p["origin"], length=p["length"], strength=p["strength"],
+                          dim=p["dim"], idim=tr.idim)
+    if name in ("Poly", "Quarticpin"):
+        return o.Poly(origin=p["origin"], length=p["length"], strength=p["strength"], degree=p["degree"],
+                      dim=p["dim"], idim=tr.idim, den=p["den"])
     if name == "Identity":
         return o.Identity()
     if name == "Inverse":

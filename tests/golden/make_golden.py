@@ -35,6 +35,31 @@ def chains(t):
     }
 
 
+def pin_chains(t):
+    """Per-axis pincushion family (basic.py:846-1462); the forward-only Poly is used inverted, which
+    is how it serves resample()."""
+    return {
+        # `dim=` given: the reference writes the result back into its copy of the INTEGER pixel grid,
+        # so resample() sees truncated coordinates (quirk reproduced, see oracle_np._Pin._join)
+        "quad": t.Quadpin(dim=2, strength=-0.3, length=40.0, origin=np.array([30.0, 20.0])),
+        "cubic": t.Cubicpin(dim=2, strength=0.4, length=60.0, origin=np.array([31.5, 23.5])),
+        "poly_inv": t.Poly(dim=2, length=50.0, strength=0.2, degree=4, origin=np.array([31.5, 23.5])).inverse(),
+        "quad_dim1": t.Quadpin(dim=1, strength=0.5, length=25.0),
+        # idim/odim given instead: float coordinates all the way (the usable spelling)
+        "quad_f": t.Quadpin(idim=2, odim=2, strength=-0.3, length=40.0, origin=np.array([30.0, 20.0])),
+        "quad_vec": t.Quadpin(idim=2, odim=2, strength=np.array([0.2, -0.1]), length=np.array([30., 50.])),
+        "cubic_f": t.Cubicpin(idim=2, odim=2, strength=0.4, length=60.0, origin=np.array([31.5, 23.5])),
+        "cubic_neg": t.Cubicpin(idim=2, odim=2, strength=-0.2, length=80.0),
+        "poly_f": t.Poly(idim=2, odim=2, length=50.0, strength=0.2, degree=4,
+                         origin=np.array([31.5, 23.5])).inverse(),
+        "quartic_inv": t.Quarticpin(idim=2, odim=2, length=60.0).inverse(),
+        "quad_chain": t.Composition([t.Offset([2.0, -1.0]), t.Quadpin(dim=2, strength=0.15, length=35.0,
+                                                                      origin=np.array([31.5, 23.5])),
+                                     t.Scale(1.1, dim=2)]),
+        "poly_den0": t.Poly(idim=2, odim=2, length=45.0, strength=-0.2, degree=5, den=0).inverse(),
+    }
+
+
 def main():
     warnings.simplefilter("ignore")
     t = ref_import.load_reference()
@@ -89,6 +114,17 @@ def main():
     for m in ('sinc', 'zlanczos', 'gaussian', 'hann', 'tukey'):
         out["fresample/affine/%s/t/f32" % m[0]] = ch["affine"].resample(src32, method=m, bound='t')
         out["fresample/radial/%s/p/f64" % m[0]] = ch["radial"].resample(src64, method=m, bound='p', shape=(20, 37))
+    # per-axis pincushion transforms
+    vp = rng.random((301, 2)) * 160 - 60
+    out["pin/in"] = vp
+    for name, tr in pin_chains(t).items():
+        if not tr.no_forward:
+            out["pin/%s/fwd" % name] = tr.apply(vp.copy())
+        if not tr.no_reverse:
+            out["pin/%s/rev" % name] = tr.invert(vp.copy())
+            if name != "quad_dim1":
+                out["pin/%s/lin" % name] = tr.resample(src32, method='linear')
+                out["pin/%s/near" % name] = tr.resample(src64, method='nearest', bound='m')
     # Jacobian pieces that the reference can run (helpers.pyx:846-958, 960-1141, 1807-1810)
     # forward through the polar transform: atan2 wraps at the branch cut, which is what jump_detect
     # exists for (the inverse direction, cos/sin, is continuous)

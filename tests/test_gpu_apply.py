@@ -130,3 +130,53 @@ def test_wcs_projections(tfm, oracle, proj, crval):
     back = a.invert(w)
     assert np.abs(back - p).max() < 1e-8
     assert np.abs(a.invert(ow) - oracle.apply(to_oracle(a), ow, invert=True)).max() < 1e-8
+
+
+def test_pincushion_kats_and_modes(tfm, oracle):
+    """The reference's own tables (tests/test_02_basic.py:331-419) through the CUDA path -- idim = 0
+    transforms act on every component of a 3x3 array -- plus fp32 mode and error behaviour."""
+    x = np.arange(9.).reshape(3, 3)
+    a = tfm.Quadpin()
+    d1 = a.apply(x)
+    assert np.allclose(d1, [[0, 1, 2.1818182], [3.5454545, 5.0909091, 6.8181818],
+                            [8.7272727, 10.818182, 13.090909]], atol=1e-2)
+    assert np.allclose(a.invert(d1), x, atol=1e-2)
+    a = tfm.Quadpin(origin=5.0)
+    d8 = a.apply(x)
+    assert np.allclose(d8, [[-1.8181818, -0.090909091, 1.4545455], [2.8181818, 4, 5],
+                            [6, 7.1818182, 8.5454545]], atol=1e-2)
+    assert np.allclose(a.invert(d8), x, atol=1e-2)
+    a = tfm.Cubicpin(strength=2)
+    d1 = a.apply(x)
+    assert np.allclose(d1, [[0, 0.6, 3.6], [11.4, 26.4, 51], [87.6, 138.6, 206.4]], atol=1e-2)
+    assert np.allclose(a.invert(d1), [[0, 0.79501675, 1.6595098], [2.5116355, 3.3596201, 4.2058325],
+                                      [5.0511344, 5.8959087, 6.7403507]], atol=1e-2)
+    a = tfm.Cubicpin(length=2.0)
+    assert np.allclose(a.apply(x), x, atol=1e-2)
+    assert np.isnan(a.invert(x)).all()
+    assert np.allclose(tfm.Poly().apply(x), x, atol=1e-2)
+    a = tfm.Poly(length=3.0, strength=2.0)
+    assert np.allclose(a.apply(x), [[0., 0.55555556, 1.55555556], [3., 4.88888889, 7.22222222],
+                                    [10., 13.22222222, 16.88888889]], atol=1e-2)
+    with pytest.raises(AssertionError):
+        a.invert(x)                                          # Poly has no inverse (basic.py:1296)
+    assert str(tfm.Quarticpin()) == "Transform( Poly/Quarticpin )"
+    # large random batch, both precisions, against the oracle
+    rng = np.random.default_rng(4)
+    v = rng.random((100003, 2)) * 300 - 150
+    for tr in (tfm.Quadpin(idim=2, odim=2, strength=0.2, length=80.0, origin=np.array([5.0, -3.0])),
+               tfm.Cubicpin(idim=2, odim=2, strength=0.3, length=90.0),
+               tfm.Quarticpin(idim=2, odim=2, length=120.0)):
+        otr = to_oracle(tr)
+        got = tr.apply(v)
+        assert_close_rel(got, oracle.apply(otr, v), 1e-12, str(tr))
+        f32 = tr.apply(v.astype(np.float32), precision='fp32')
+        assert f32.dtype == np.float32
+        assert_close_rel(f32, oracle.apply(otr, v), 2e-6 * 300, str(tr))
+        if not tr.no_reverse:
+            assert_close_rel(tr.invert(v), oracle.apply(otr, v, invert=True), 1e-12, str(tr))
+    # integer input + dim=: the reference's write-back truncation, reproduced
+    iv = np.arange(40).reshape(20, 2)
+    q = tfm.Quadpin(dim=2, strength=0.3, length=10.0)
+    assert np.array_equal(q.apply(iv), oracle.apply(to_oracle(q), iv))
+    assert np.array_equal(q.apply(iv), np.trunc(q.apply(iv.astype(float))))

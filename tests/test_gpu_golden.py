@@ -99,3 +99,43 @@ def test_svd_matches_reference(tfm):
         assert np.allclose(U, GOLD["svd/U"][k], rtol=0, atol=1e-14)
         assert np.allclose(s, GOLD["svd/s"][k], rtol=0, atol=1e-14)
         assert np.allclose(V, GOLD["svd/V"][k], rtol=0, atol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-axis pincushion family (basic.py:846-1462)
+# ---------------------------------------------------------------------------------------------
+from test_oracle_golden import PIN_NAMES, _pin_chains  # noqa: E402
+
+
+@pytest.mark.parametrize("name", PIN_NAMES)
+def test_pincushion_matches_reference(tfm, name):
+    """Quadpin is add/mul/div/sqrt only -> bit-exact; Cubicpin and Poly go through pow(), whose last
+    bit differs between CUDA and glibc -> 1e-12 (resampled values: bilinear weights inherit it)."""
+    tr = _pin_chains(tfm)[name]
+    exact = name.startswith("quad")
+    v = GOLD["pin/in"]
+
+    def check(got, want, what):
+        assert got.shape == want.shape and got.dtype == want.dtype, (what, got.dtype, want.dtype)
+        if exact:
+            assert np.array_equal(got, want, equal_nan=True), what
+        else:
+            assert_close_rel(got, want, 1e-12, what)
+
+    if "pin/%s/fwd" % name in GOLD.files:
+        check(tr.apply(v), GOLD["pin/%s/fwd" % name], name + " fwd")
+    if "pin/%s/rev" % name in GOLD.files:
+        check(tr.invert(v), GOLD["pin/%s/rev" % name], name + " rev")
+    if "pin/%s/lin" % name in GOLD.files:
+        got = tr.resample(GOLD["src32"], method='linear')
+        want = GOLD["pin/%s/lin" % name]
+        if exact:
+            assert np.array_equal(got, want, equal_nan=True), name
+        else:
+            # a 1-ulp coordinate difference moves a bilinear value by ~1e-13; at an exact integer
+            # coordinate it can flip floor(), which leaves the value continuous all the same
+            assert_close_rel(got, want, 1e-11, name + " lin")
+        got = tr.resample(GOLD["src64"], method='nearest', bound='m')
+        want = GOLD["pin/%s/near" % name]
+        assert got.dtype == want.dtype
+        assert (got != want).sum() <= (0 if exact else 3), name

@@ -160,3 +160,34 @@ def test_jacobian_helper_entry_points(tfm, oracle):
         tfm.simple_jacobian(np.zeros((1, 10, 2)))
     with pytest.raises(NotImplementedError):
         tfm.simple_jacobian(np.zeros((4, 4, 4, 3)))
+
+
+def test_flux_photometry(tfm, oracle):
+    """phot='flux' (core.py:521-533 documents it, SVD.pyx:285-286 implements it): output scaled by
+    |det J|.  Parity against the oracle, and the defining property: the summed value of a compact
+    source is preserved under a 2.5 x 2 downsample (the intensive result sums to 1/5 of it)."""
+    rng = np.random.default_rng(11)
+    src = np.zeros((120, 160))
+    src[30:90, 40:120] = rng.random((60, 80)) + 1.0
+    # Anisotropic on purpose.  For an exactly isotropic Jacobian (rotation x uniform scale) the
+    # reference's closed-form svd2x2_fast (helpers.pyx:1845-1894) takes both half-angles from
+    # atan2(noise, noise), independently, and its "singular values" become |s cos(random)|: parity
+    # mode reproduces that bit for bit (same rounding noise), the fp32 mode's eigenvalue form does not
+    # -- it returns the true values -- so the two legitimately differ there (see DESIGN.md, K2).
+    tr = tfm.Composition([tfm.Offset([60.3, 50.7]), tfm.Scale([0.4, 0.5]), tfm.Rotation(20, unit='deg'),
+                          tfm.Offset([-80.0, -60.0])])
+    shape = (100, 120)
+    flux = tr.resample(src, method='G', phot='flux', shape=shape)
+    rad = tr.resample(src, method='G', shape=shape)
+    want = oracle.resample_jacobian(to_oracle(tr), src, method='g', shape=shape, phot='flux')
+    assert_close_rel(flux, want, 1e-11, "flux parity")
+    assert abs(flux.sum() / src.sum() - 1.0) < 2e-3
+    assert abs(rad.sum() * 5.0 / src.sum() - 1.0) < 2e-3
+    ext = tr.resample(src, method='G', phot='extensive', shape=shape)
+    assert np.array_equal(ext, flux)
+    f32 = tr.resample(src.astype(np.float32), method='G', phot='flux', shape=shape, precision='fp32')
+    assert_close_rel(f32, want, 1e-4, "flux fp32")
+    with pytest.raises(ValueError):
+        tr.resample(src, method='G', phot='bogus')
+    # the plain interpolators ignore phot, like the reference (core.py:531-533)
+    assert np.array_equal(tr.resample(src, method='l', phot='flux'), tr.resample(src, method='l'))

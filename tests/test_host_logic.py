@@ -212,3 +212,43 @@ def test_read_sample_fits_header():
         t.DataWrapper('sample.fits')                                     # tests/test_01_core.py:173-177
     a = t.DataWrapper((d, h), template={'CRPIX1': 99})
     assert a.header['CRPIX1'] == 99 and h['CRPIX1'] != 99                # tests/test_01_core.py:237-241
+
+
+def test_pincushion_lowering():
+    """Quadpin / Cubicpin / Poly lower to one TFM_OP_PIN whose constants are the reference's own
+    scalar sub-expressions (basic.py:957-958, 994-996, 1117-1119, 1148-1173, 1341-1347)."""
+    import transform_b200 as t
+    from transform_b200 import _lib as L
+    q = t.Quadpin(dim=2, strength=-0.3, length=40.0, origin=np.array([30.0, 20.0]))
+    (op,) = q._chain(False)
+    assert op.kind == L.OP_PIN and op.dir == L.FWD and (op.flags & 3) == L.PIN_QUAD
+    assert op.flags & L.PIN_SHIFTED and not (op.flags & L.PIN_DIM1) and not (op.flags & L.PIN_TRUNC)
+    assert (op.p[0], op.p[12]) == (30.0, 20.0)
+    assert list(op.p[1:4]) == [-0.3, 40.0, abs(-0.3) + 1]
+    (op,) = q._chain(True)
+    assert op.dir == L.REV
+    assert list(op.p[13:17]) == [4.0 * -0.3 / 40.0, 1.0 + 0.3, 40.0, 2.0 * -0.3]
+    # first op on the integer pixel grid and built with dim=: write-back truncation flag
+    assert q._int_chain(True)[0].flags & L.PIN_TRUNC
+    assert not t.Quadpin(idim=2, odim=2)._int_chain(True)[0].flags & L.PIN_TRUNC
+    comp = t.Composition([t.Offset([1.0, 2.0]), q])
+    assert not comp._int_chain(True)[0].flags & L.PIN_TRUNC          # Offset runs first in reverse
+    assert comp._int_chain(False)[0].flags & L.PIN_TRUNC             # the Quadpin runs first forward
+    c = t.Cubicpin(strength=np.array([0.3, 0.1]), length=50.0, dim=2)
+    (op,) = c._chain(True)
+    A0, A1 = 0.3 / 50.0 / 50.0, 0.1 / 50.0 / 50.0
+    assert (op.flags & 3) == L.PIN_CUBIC and not (op.flags & L.PIN_SHIFTED)
+    assert list(op.p[1:5]) == [0.3 + 1, 27 * A0 * A0, 4.0 * (3 * A0) * (3 * A0) * (3 * A0), -1 / (3 * A0)]
+    assert op.p[16] == -1 / (3 * A1)
+    assert np.isnan(t.Cubicpin(dim=2)._chain(True)[0].p[4])          # strength 0: -1/(3*nan)
+    p = t.Poly(dim=1, length=3.0, strength=2.0, degree=4)
+    (op,) = p._chain(False)
+    assert (op.flags & 3) == L.PIN_POLY and op.flags & L.PIN_DIM1 and op.reserved == 4
+    assert op.p[2] == 1.0 / (2.0 ** 3 + 1) and list(op.p[5:8]) == [3.0, 9.0, 27.0]
+    assert p.no_reverse and p.inverse().no_forward
+    with pytest.raises(AssertionError):
+        p._chain(True)
+    with pytest.raises(NotImplementedError):
+        t.Poly(degree=9)._chain(False)
+    qp = t.Quarticpin(dim=2)
+    assert qp.params['degree'] == 4 and qp.params['strength'] == 0.1 and qp.idim == 2

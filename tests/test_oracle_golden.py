@@ -130,6 +130,32 @@ def test_filters_through_resample_match_reference(oracle, chains):
         oracle.interpND(GOLD["src32"], GOLD["interp/index"], method='c', oblur=2.0)
 
 
+def _pin_chains(module):
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.pin_chains(module)
+
+
+PIN_NAMES = sorted({k.split("/")[1] for k in GOLD.files if k.startswith("pin/") and k != "pin/in"})
+
+
+@pytest.mark.parametrize("name", PIN_NAMES)
+def test_pincushion_matches_reference(oracle, tfm, name):
+    """Quadpin / Cubicpin / Poly / Quarticpin (basic.py:846-1462), quirks included: bit-exact."""
+    tr = _pin_chains(tfm)[name]
+    otr = to_oracle(tr)
+    v = GOLD["pin/in"]
+    if "pin/%s/fwd" % name in GOLD.files:
+        assert np.array_equal(oracle.apply(otr, v), GOLD["pin/%s/fwd" % name], equal_nan=True)
+    if "pin/%s/rev" % name in GOLD.files:
+        assert np.array_equal(oracle.apply(otr, v, invert=True), GOLD["pin/%s/rev" % name], equal_nan=True)
+    if "pin/%s/lin" % name in GOLD.files:
+        assert np.array_equal(oracle.resample(otr, GOLD["src32"], method='l'), GOLD["pin/%s/lin" % name], equal_nan=True)
+        assert np.array_equal(oracle.resample(otr, GOLD["src64"], method='n', bound='m'), GOLD["pin/%s/near" % name],
+                              equal_nan=True)
+
+
 def test_jacobian_pieces_match_reference(oracle):
     # square grid: simple_jacobian and jump_detect bit-identical to the reference
     sq = GOLD["jac/coords_sq"]

@@ -180,3 +180,42 @@ def test_wcs_linear_pin_and_identity_gaussian():
     s = (3 + 1) ** (-1 / 8.0)
     w0 = 1.0 / sum(np.exp(-(s * a) ** 2 - (s * b) ** 2) for a in range(-2, 3) for b in range(-2, 3))
     assert np.isclose(out[4, 4], w0, rtol=1e-12)
+
+
+def test_pincushion_kats(oracle):
+    """tests/test_02_basic.py:331-419 (test_009_Quadpin, test_010_Cubicpin, test_011_Poly), same
+    inputs, expected tables and tolerances."""
+    x = np.arange(9.).reshape(3, 3)
+    a = oracle.Quadpin()
+    d1 = oracle.apply(a, x)
+    assert np.allclose(d1, [[0, 1, 2.1818182], [3.5454545, 5.0909091, 6.8181818],
+                            [8.7272727, 10.818182, 13.090909]], atol=1e-2)
+    assert np.allclose(oracle.apply(a, d1, invert=True), x, atol=1e-2)
+    a = oracle.Quadpin(length=5.0)
+    d6 = np.array([[0, 0.92727273, 1.8909091], [2.8909091, 3.9272727, 5], [6.1090909, 7.2545455, 8.4363636]])
+    assert np.allclose(oracle.apply(a, x), d6, atol=1e-2)
+    assert np.allclose(oracle.apply(a, d6, invert=True), x, atol=1e-2)
+    a = oracle.Quadpin(origin=5.0)
+    d8 = oracle.apply(a, x)
+    assert np.allclose(d8, [[-1.8181818, -0.090909091, 1.4545455], [2.8181818, 4, 5],
+                            [6, 7.1818182, 8.5454545]], atol=1e-2)
+    assert np.allclose(oracle.apply(a, d8, invert=True), x, atol=1e-2)
+    a = oracle.Quadpin(strength=6.0)
+    d12 = np.array([[0, 1, 3.7142857], [8.1428571, 14.285714, 22.142857], [31.714286, 43, 56]])
+    assert np.allclose(oracle.apply(a, x), d12, atol=1e-2)
+    assert np.allclose(oracle.apply(a, d12, invert=True), x, atol=1e-2)
+
+    a = oracle.Cubicpin(strength=2)
+    d1 = oracle.apply(a, x)
+    assert np.allclose(d1, [[0, 0.6, 3.6], [11.4, 26.4, 51], [87.6, 138.6, 206.4]], atol=1e-2)
+    assert np.allclose(oracle.apply(a, d1, invert=True),
+                       [[0, 0.79501675, 1.6595098], [2.5116355, 3.3596201, 4.2058325],
+                        [5.0511344, 5.8959087, 6.7403507]], atol=1e-2)
+    a = oracle.Cubicpin(length=2.0)                         # strength 0: forward identity, reverse all-NaN
+    assert np.allclose(oracle.apply(a, x), x, atol=1e-2)
+    assert np.isnan(oracle.apply(a, x, invert=True)).all()
+
+    assert np.allclose(oracle.apply(oracle.Poly(), x), x, atol=1e-2)
+    a = oracle.Poly(length=3.0, strength=2.0)
+    assert np.allclose(oracle.apply(a, x), [[0., 0.55555556, 1.55555556], [3., 4.88888889, 7.22222222],
+                                            [10., 13.22222222, 16.88888889]], atol=1e-2)

@@ -7,7 +7,8 @@ runs in libtfm_b200.so (hand-written CUDA for sm_100a); importing the package ne
 nor the library, calling into the path does -- and fails loudly otherwise.
 """
 from .core import Transform, Identity, PlusOne_, Inverse, Composition, Wrap       # noqa: F401
-from .basic import Linear, Scale, Rotation, Offset, Radial                        # noqa: F401
+from .basic import (Linear, Scale, Rotation, Offset, Radial, Quadpin, Cubicpin,   # noqa: F401
+                    Poly, Quarticpin)
 from .helpers import (interpND, interpND_grid, svd2x2, svc2x2, simple_jacobian,   # noqa: F401
                       jump_detect, jacobian)
 from .fitswcs import Header, WCSParams, read_fits, FITSHeaderFromDict            # noqa: F401

@@ -223,10 +223,23 @@ def _check_status(status):
                            "(sharding bounding box too small)")
 
 
+def flux_requested(phot):
+    """core.py:521-533: 'flux' / 'extensive' ask for summed-value preservation; 'radiance' /
+    'intensive' (default) for local-value preservation.  Only the first character is tested."""
+    if not isinstance(phot, str) or not phot:
+        raise ValueError("phot must be 'radiance'/'intensive' or 'flux'/'extensive'")
+    c = phot[0].lower()
+    if c in ("f", "e"):
+        return True
+    if c in ("r", "i"):
+        return False
+    raise ValueError("phot must be 'radiance'/'intensive' or 'flux'/'extensive'")
+
+
 def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=1.0, iblur=1.0,
                       pad_pow=8, sv_limit=0.25, jump_detect=4.0, precision=None, tuning=0,
                       dst_origin=(0, 0), grid_full=None, src_origin=(0, 0), src_full=None,
-                      max_reg=None, out=None):
+                      max_reg=None, out=None, phot='radiance'):
     """K2 driver: interpND_grid(antialias=True) semantics (helpers.pyx:1293-1530) with the
     coordinates generated in-kernel from `chain_ops`."""
     lib = L.load()
@@ -279,7 +292,7 @@ def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=
     a.filter = filt
     a.bound_x, a.bound_y = bx, by
     a.precision = prec
-    a.flags = 0
+    a.flags = L.F_FLUX if flux_requested(phot) else 0
     a.tuning = int(tuning)
     a.fillvalue = float(fillvalue)
     a.oblur, a.iblur, a.pad_pow = float(oblur), float(iblur), float(pad_pow)

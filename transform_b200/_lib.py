@@ -16,7 +16,8 @@ OP_NPARAM = 24
 # status codes
 OK, EVALUE, EDIRECTION, EFORBID, ECUDA, EUNSUPPORTED, ESTAGED = range(7)
 # op kinds / directions
-OP_IDENTITY, OP_LINEAR, OP_RADIAL, OP_WCS, OP_INDEX = range(5)
+OP_IDENTITY, OP_LINEAR, OP_RADIAL, OP_WCS, OP_INDEX, OP_PIN = range(6)
+PIN_QUAD, PIN_CUBIC, PIN_POLY, PIN_SHIFTED, PIN_DIM1, PIN_TRUNC, PIN_MAX_DEGREE = 0, 1, 2, 4, 8, 16, 8
 FWD, REV = 0, 1
 # flags
 LIN_HAS_PRE, LIN_HAS_POST, LIN_HAS_MATRIX, LIN_MAT_FORDER = 1, 2, 4, 8
@@ -30,6 +31,7 @@ BOUND_CODE = {"f": 1, "t": 2, "e": 3, "p": 4, "m": 5}            # helpers.pyx:1
 FILTER_CODE = {"l": 1, "z": 2, "h": 3, "t": 4, "g": 5}           # helpers.pyx:1501
 PREC_EXACT64, PREC_FAST32 = 0, 1
 F_REGION_SRC_DTYPE = 1
+F_FLUX = 2
 
 
 class TfmOp(ctypes.Structure):

@@ -286,3 +286,140 @@ class Radial(Transform):
         if not hasattr(self, '_strtmp'):
             self._strtmp = 'Radial'
         return super().__str__()
+
+
+# ---------------------------------------------------------------------------------------------
+# per-axis pincushion family (basic.py:846-1462)
+# ---------------------------------------------------------------------------------------------
+def _axis_value(v, a):
+    """Component `a` of a scalar-or-vector parameter, keeping its Python / NumPy scalar type so that
+    the constant folding below rounds exactly as the reference's own expressions do."""
+    if np.ndim(v) == 0:
+        return v
+    flat = np.asarray(v).reshape(-1)
+    return flat[a] if flat.size > 1 else flat[0]
+
+
+class _Pincushion(Transform):
+    """Shared constructor and lowering of Quadpin / Cubicpin / Poly.  The reference's `_forward`
+    mutates idim/odim on first use (`self.idim, self.odim = data.shape`, basic.py:936-937), which
+    only works for 2-D arrays and is not reproduced: idim = 0 means "every component"."""
+    _elementwise = True
+    _name = "Pincushion"
+    _kind = None
+
+    def _init(self, iunit, ounit, itype, otype, idim, odim, dim, no_reverse, params):
+        if dim is not None:                                   # basic.py:912-914
+            idim = dim
+            odim = dim
+        self.idim, self.odim = idim, odim
+        self.no_forward = False
+        self.no_reverse = no_reverse
+        self.iunit, self.ounit, self.itype, self.otype = iunit, ounit, itype, otype
+        self.params = params
+
+    def _consts(self, direction, strength, length):
+        raise NotImplementedError
+
+    def _lower(self, direction):
+        p = self.params
+        ncomp = self.idim if self.idim else 2
+        if ncomp > 2:
+            raise NotImplementedError("transform_b200: only 1-D and 2-D transforms are on the GPU path")
+        op = L.TfmOp()
+        op.kind, op.dir = L.OP_PIN, direction
+        flags = self._kind
+        origin = p['origin']
+        if not np.all(origin == 0):                           # basic.py:949, 987: shift only then
+            flags |= L.PIN_SHIFTED
+        if ncomp == 1:
+            flags |= L.PIN_DIM1
+        op.flags = flags
+        op.reserved = int(p.get('degree', 0))
+        op._writes_back = p['dim'] is not None                # see Transform._grid_chain
+        with np.errstate(all="ignore"):
+            for a in range(2):
+                base = 12 * a
+                op.p[base] = float(_axis_value(origin, a))
+                consts = self._consts(direction, _axis_value(p['strength'], a), _axis_value(p['length'], a))
+                for k, c in enumerate(consts):
+                    op.p[base + 1 + k] = float(c)
+        return [op]
+
+    def __str__(self):
+        if not hasattr(self, '_strtmp'):
+            self._strtmp = self._name
+        return super().__str__()
+
+
+class Quadpin(_Pincushion):
+    """Quadratic pincushion scaling per axis, with inverse (basic.py:846-1017)."""
+    _name = "Quadpin"
+    _kind = L.PIN_QUAD
+
+    def __init__(self, *, iunit=None, ounit=None, itype=None, otype=None, idim=0, odim=0,
+                 origin=0, length=1, strength=0.1, dim=None):
+        self._init(iunit, ounit, itype, otype, idim, odim, dim, False,
+                   {'origin': origin, 'length': length, 'strength': strength, 'dim': dim})
+
+    def _consts(self, direction, strength, length):
+        if direction == L.FWD:                                # basic.py:957-958
+            return (strength, length, np.abs(strength) + 1)
+        # basic.py:994-996
+        return (4.0 * strength / length, 1.0 + np.abs(strength), length, 2.0 * strength)
+
+
+class Cubicpin(_Pincushion):
+    """Cubic pincushion scaling per axis (basic.py:1020-1175), as coded: the two directions use
+    different normalisations (strength^2+1 vs strength+1) and are not exact inverses."""
+    _name = "Cubicpin"
+    _kind = L.PIN_CUBIC
+
+    def __init__(self, *, iunit=None, ounit=None, itype=None, otype=None, idim=0, odim=0,
+                 origin=0, length=1, strength=0.0, dim=None):
+        self._init(iunit, ounit, itype, otype, idim, odim, dim, False,
+                   {'origin': origin, 'length': length, 'strength': strength, 'dim': dim})
+
+    def _consts(self, direction, strength, length):
+        if direction == L.FWD:                                # basic.py:1117-1119
+            return (strength, length, (strength * strength) + 1)
+        Avar = strength / length / length                     # basic.py:1148-1153
+        Betavar = 3 * Avar * 1
+        try:
+            coef = -1 / (3 * Avar)                            # basic.py:1170-1173
+        except ZeroDivisionError:
+            coef = -1 / (3 * np.nan)
+        return (strength + 1, 27 * Avar * Avar, 4.0 * Betavar * Betavar * Betavar, coef)
+
+
+class Poly(_Pincushion):
+    """Forward-only polynomial pincushion (basic.py:1178-1362)."""
+    _name = "Poly"
+    _kind = L.PIN_POLY
+
+    def __init__(self, *, iunit=None, ounit=None, itype=None, otype=None, idim=0, odim=0,
+                 origin=0, length=1, strength=0.0, degree=2, dim=None, den=1):
+        self._init(iunit, ounit, itype, otype, idim, odim, dim, True,
+                   {'origin': origin, 'length': length, 'strength': strength, 'degree': degree,
+                    'dim': dim, 'den': den})
+
+    def _consts(self, direction, strength, length):
+        degree = int(self.params['degree'])
+        if degree > L.PIN_MAX_DEGREE:
+            raise NotImplementedError("transform_b200: Poly degree > %d" % L.PIN_MAX_DEGREE)
+        if self.params['den'] != 1:                           # basic.py:1341-1344
+            sc = 1.0 / (np.abs(strength) + 1)
+        else:
+            sc = 1.0 / (np.abs(strength) ** (degree - 1) + 1)
+        lk = [length ** (k - 1) for k in range(2, degree + 1)]                # basic.py:1347
+        return (strength, sc, 0.0, 0.0) + tuple(lk)
+
+
+class Quarticpin(Poly):
+    """Poly with degree 4, den 1, strength 0.1 preselected (basic.py:1365-1452)."""
+    _name = "Poly/Quarticpin"
+
+    def __init__(self, *, iunit=None, ounit=None, itype=None, otype=None, idim=0, odim=0,
+                 origin=0, length=1, strength=0.1, degree=4, dim=None, den=1):
+        super().__init__(iunit=iunit, ounit=ounit, itype=itype, otype=otype, idim=idim, odim=odim,
+                         origin=origin, length=length, strength=strength, degree=degree, dim=dim, den=den)

@@ -51,6 +51,16 @@ class Transform:
             raise AssertionError("This Transform (%s) is invalid in the forward direction" % self.__str__())
         return self._lower(L.FWD)
 
+    def _int_chain(self, invert):
+        """Chain as INTEGER input sees it -- the np.mgrid pixel grid of resample() (core.py:574-578)
+        or an integer array given to apply().  Only one thing differs from `_chain`: a pincushion op
+        constructed with `dim=` that comes first writes its result back into the integer copy of its
+        input (basic.py:962-965 and twins), i.e. truncates it to int64; reproduced by an opcode flag."""
+        ops = self._chain(invert)
+        if ops and ops[0].kind == L.OP_PIN and getattr(ops[0], "_writes_back", False):
+            ops[0].flags |= L.PIN_TRUNC
+        return ops
+
     # -- vector path (core.py:218-315) --
     def apply(self, data, invert=False, *, precision=None):
         """Apply the transform to [..., N] vectors (K3 streaming kernel).
@@ -61,7 +71,8 @@ class Transform:
         is_dev = _engine.dev.is_cuda_tensor(data)
         if not is_dev and not isinstance(data, np.ndarray):
             data = np.array(data)
-        ops = self._chain(invert)
+        int_input = (not is_dev) and data.dtype.kind in "iu"
+        ops = self._int_chain(invert) if int_input else self._chain(invert)
         dim = self.odim if invert else self.idim
         nlast = int(data.shape[-1]) if len(data.shape) else 0
         if len(data.shape) == 0 or nlast < dim:
@@ -70,6 +81,19 @@ class Transform:
             raise NotImplementedError("transform_b200: only 1-D and 2-D transforms are on the GPU path")
         if not ops:
             return data                         # Identity._forward returns its argument (core.py:1381-1385)
+        if dim == 0 and getattr(self, "_elementwise", False) and nlast != 2:
+            # idim = 0: the transform acts on every component (core.py:274-276, 290-292); an
+            # elementwise op with per-axis-identical parameters runs on the flattened data as pairs
+            if is_dev:
+                raise NotImplementedError("transform_b200: idim=0 transforms on device tensors")
+            if any(np.ndim(self.params[k]) != 0 for k in ('origin', 'length', 'strength')):
+                raise ValueError("vector parameters need vectors of matching length (2 on the GPU path)")
+            arr = np.asarray(data, dtype=np.float64)
+            flat = arr.reshape(-1)
+            if flat.size % 2:
+                flat = np.concatenate([flat, np.zeros(1)])
+            res = _engine.apply(ops, flat.reshape(-1, 2), precision=precision)
+            return res.reshape(-1)[:arr.size].reshape(arr.shape)
         if nlast == 1:                          # 1-D transform on 1-vectors: pad a dummy component
             if is_dev:
                 raise NotImplementedError("transform_b200: 1-vectors on device tensors")
@@ -105,6 +129,11 @@ class Transform:
         Jacobian-adaptive anti-aliasing kernel with interpND_grid's keyword arguments
         (oblur, iblur, pad_pow, sv_limit, jump_detect) taken from **aa.
 
+        `phot` ('radiance' default / 'flux'): the reference documents but never implements it
+        (core.py:521-533) and silently resamples intensively.  Here the anti-aliased methods honour
+        'flux' by scaling each output pixel by |det J| (as SVD.pyx:285-286 does); the plain
+        interpolators ignore it like the reference.
+
         Extra keyword-only arguments (not in the reference): precision ('fp64' parity mode,
         default; 'fp32' fast path), fillvalue (interpND's, default 0), out (a CUDA tensor to
         write into, or a host array / pinned CPU tensor that receives the result)."""
@@ -131,13 +160,13 @@ class Transform:
         if len(shape) < 2:
             raise NotImplementedError("transform_b200: the GPU path resamples 2-D planes "
                                       "(optionally batched over leading axes)")
-        ops = self._chain(True)                 # self.invert(grid), core.py:574
+        ops = self._int_chain(True)             # self.invert(grid), core.py:574 (the grid is int64)
         m = method[0]
         if m in _engine._AA_METHODS:
             if aa.pop('antialias', True) and aa.pop('aa', True):
                 return _engine.resample_jacobian(ops, data0, shape, _engine._AA_METHODS[m], bound,
                                                  fillvalue=fillvalue, precision=precision,
-                                                 tuning=tuning, out=out, **aa)
+                                                 tuning=tuning, out=out, phot=phot, **aa)
         oblur = aa.pop('oblur', None)           # interpND's keyword (helpers.pyx:509-516)
         if aa:
             raise TypeError("resample() got unexpected keyword arguments %s" % sorted(aa))

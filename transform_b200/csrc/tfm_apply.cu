@@ -134,8 +134,7 @@ int apply_dispatch(const tfm_apply_args *a, cudaStream_t st)
     if (a->dtype != TFM_F32 && a->dtype != TFM_F64) return TFM_EVALUE;
     if (a->n_vec == 0) return TFM_OK;
     if (!a->in || !a->out) return TFM_EVALUE;
-    for (int i = 0; i < a->n_ops; ++i)
-        if (a->chain[i].kind < TFM_OP_IDENTITY || a->chain[i].kind > TFM_OP_INDEX) return TFM_EVALUE;
+    if (!chain_ops_valid(a->chain, a->n_ops)) return TFM_EVALUE;
 
     ApplyParams P;
     P.in = a->in; P.out = a->out; P.n_vec = a->n_vec; P.vec_len = a->vec_len;

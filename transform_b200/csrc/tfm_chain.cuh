@@ -113,6 +113,67 @@ __device__ __forceinline__ void op_radial(const tfm_op &op, double &x, double &y
     }
 }
 
+// ---- per-axis pincushion family (basic.py:846-1462); formulas and constants: include/tfm_b200.h ----
+template <class A>
+__device__ __forceinline__ double pin_root3(double x)          // (1 - 2*(x<0)) * abs(x)**(1/3)
+{
+    const double r = pow(fabs(x), 1.0 / 3.0);
+    return (x < 0.0) ? -r : r;
+}
+
+template <class A>
+__device__ __forceinline__ double pin_axis(const tfm_op &op, const double *c, double d)
+{
+    const int kind = op.flags & 3;
+    const bool shifted = (op.flags & TFM_PIN_SHIFTED) != 0;
+    const double o = c[0];
+    double u = shifted ? A::sub(d, o) : d;
+    if (kind == TFM_PIN_QUAD) {
+        if (op.dir == TFM_FWD) {
+            u = A::add(u, A::div(A::mul(c[1], A::mul(u, fabs(u))), c[2]));
+            u = A::div(u, c[3]);
+        } else {
+            double t = __dsqrt_rn(A::add(1.0, A::mul(A::mul(c[1], fabs(u)), c[2])));
+            t = A::add(-1.0, t);
+            t = A::div(A::mul(t, c[3]), c[4]);
+            u = (d < (shifted ? o : 0.0)) ? -t : t;
+        }
+    } else if (kind == TFM_PIN_CUBIC) {
+        if (op.dir == TFM_FWD) {
+            const double q = A::div(u, c[2]);
+            u = A::add(u, A::mul(A::mul(A::mul(c[1], u), q), q));
+            u = A::div(u, c[3]);
+        } else {
+            u = A::mul(u, c[1]);
+            const double al = A::mul(c[2], -u);
+            const double in = __dsqrt_rn(A::add(A::mul(al, al), c[3]));
+            const double rn = pin_root3<A>(A::mul(0.5, A::sub(al, in)));
+            const double rp = pin_root3<A>(A::mul(0.5, A::add(al, in)));
+            u = A::mul(c[4], A::add(rp, rn));
+        }
+    } else {
+        double a = u;
+        const int degree = op.reserved;
+        for (int k = 2; k <= degree; ++k) {
+            const double pk = (k == 2) ? A::mul(u, u) : pow(u, (double)k);
+            a = A::add(a, A::div(A::mul(c[1], pk), c[5 + (k - 2)]));
+        }
+        u = A::mul(c[2], a);
+    }
+    return shifted ? A::add(u, o) : u;
+}
+
+template <class A>
+__device__ __forceinline__ void op_pin(const tfm_op &op, double &x, double &y)
+{
+    x = pin_axis<A>(op, op.p, x);
+    if (!(op.flags & TFM_PIN_DIM1)) y = pin_axis<A>(op, op.p + 12, y);
+    if (op.flags & TFM_PIN_TRUNC) {                             // float64 -> int64 write-back of the reference
+        x = (fabs(x) < 9.2e18) ? trunc(x) : -9223372036854775808.0;
+        if (!(op.flags & TFM_PIN_DIM1)) y = (fabs(y) < 9.2e18) ? trunc(y) : -9223372036854775808.0;
+    }
+}
+
 // ---- FITS WCS (Greisen & Calabretta 2002 paper I; Calabretta & Greisen 2002 paper II) ----
 // PARITY UNPINNED beyond the linear part: the reference delegates to astropy/wcslib
 // (core.py:1727, 1742), which is absent and unpinned; restated from the papers.
@@ -229,10 +290,13 @@ __device__ __forceinline__ void op_wcs_pair(const tfm_op &op, double &x, double 
     y = (op.p[17] * ox + op.p[18] * oy + op.p[20]) - 1.0;
 }
 
+// "heavy" ops (spherical WCS, the pow()-based pincushion family) are compiled only into the SPH kernel
+// instantiations, see chain_eval below
 static inline bool chain_has_sph(const ChainDev &ch)
 {
     for (int i = 0; i < ch.n; ++i)
-        if (ch.ops[i].kind == TFM_OP_WCS || ch.ops[i].kind == TFM_OP_WCS_PAIR) return true;
+        if (ch.ops[i].kind == TFM_OP_WCS || ch.ops[i].kind == TFM_OP_WCS_PAIR || ch.ops[i].kind == TFM_OP_PIN)
+            return true;
     return false;
 }
 
@@ -397,6 +461,23 @@ static inline int fuse_chain_fast(const tfm_op *ops, int n, tfm_op *out)
     return m;
 }
 
+// Host-side validation of the opcodes that cross the C ABI.
+static inline bool chain_ops_valid(const tfm_op *ops, int n)
+{
+    for (int i = 0; i < n; ++i) {
+        const tfm_op &op = ops[i];
+        if (op.kind < TFM_OP_IDENTITY || op.kind > TFM_OP_PIN) return false;
+        if (op.dir != TFM_FWD && op.dir != TFM_REV) return false;
+        if (op.kind == TFM_OP_PIN) {
+            const int k = op.flags & 3;
+            if (k > TFM_PIN_POLY) return false;
+            if (k == TFM_PIN_POLY && (op.dir != TFM_FWD || op.reserved < 0 || op.reserved > TFM_PIN_MAX_DEGREE))
+                return false;                               // Poly has no inverse (basic.py:1296)
+        }
+    }
+    return true;
+}
+
 // interpND / interpND_grid take a precomputed coordinate array (helpers.pyx:379, 1293)
 __device__ __forceinline__ void op_index(const tfm_op &op, double &x, double &y)
 {
@@ -427,6 +508,7 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
         case TFM_OP_RADIAL: op_radial<A>(op, x, y); break;
         case TFM_OP_WCS: if constexpr (SPH) op_wcs<A>(op, x, y); break;
         case TFM_OP_WCS_PAIR: if constexpr (SPH) op_wcs_pair(op, x, y); break;
+        case TFM_OP_PIN: if constexpr (SPH) op_pin<A>(op, x, y); break;
         case TFM_OP_POLAR: op_polar(op, x, y); break;
         case TFM_OP_INDEX: op_index(op, x, y); break;
         default: break;                                     // identity
@@ -493,6 +575,12 @@ __device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N],
             if constexpr (SPH) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) op_wcs_pair(op, x[k], y[k]);
+            }
+            break;
+        case TFM_OP_PIN:
+            if constexpr (SPH) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) op_pin<A>(op, x[k], y[k]);
             }
             break;
         case TFM_OP_POLAR:

@@ -36,6 +36,7 @@ struct JacParams {
     int grid_h, grid_w;                      // full output grid (edge rules)
     int bound_x, bound_y;
     int filter;
+    int flags;
     int src_f64, dst_f64;
     double oblur, pad_pow, padval, jump_thresh;
     long long max_reg;
@@ -295,12 +296,15 @@ __device__ __forceinline__ void gaussian_quadratic_f32(const double *Ji, float p
     const float lp = mean + rad, lm = fmaxf(mean - rad, 0.0f);
     const float half_pow = 0.5f * pad_pow, m2p = -2.0f * fast_rcp(pad_pow);
     const float fp = pad_inv_sq(lp, padval, half_pow, m2p), fm = pad_inv_sq(lm, padval, half_pow, m2p);
-    float beta = 0.0f;
-    if (rad > 1e-6f * mean) beta = (fp - fm) * fast_rcp(lp - lm);
-    const float alpha = fp - beta * lp;
-    q00 = alpha + beta * g00;
+    // f(G) = fp I + beta (G - lp I), beta the divided difference of f over the two eigenvalues.  For a
+    // nearly isotropic Jacobian beta is ill-conditioned (error ~ eps f / (lp - lm)), but it multiplies
+    // G - lp I, whose entries are O(lp - lm) when formed from rad and dif directly: the error of Q
+    // stays ~ eps f.  (alpha + beta g with alpha = fp - beta lp cancels catastrophically there.)
+    const float dl = lp - lm;
+    const float beta = (dl > 0.0f) ? (fp - fm) * fast_rcp(dl) : 0.0f;
+    q00 = fp - beta * (rad - dif);         // lp - g00 = rad - dif
     q01 = beta * g01;
-    q11 = alpha + beta * g11;
+    q11 = fp - beta * (rad + dif);         // lp - g11 = rad + dif
     inv_smin = fast_rsqrt(fp);             // the larger singular value has the smaller padded inverse
 }
 
@@ -541,7 +545,10 @@ k_jacobian(const __grid_constant__ JacParams P)
                 }
             }
         }
-        drow[X] = (DstT)((wgt > 0) ? val / wgt : 0.0);                               // helpers.pyx:1800
+        double res = (wgt > 0) ? val / wgt : 0.0;                                    // helpers.pyx:1800
+        if (P.flags & TFM_F_FLUX)                                                    // SVD.pyx:285-286
+            res = __dmul_rn(res, fabs(__dsub_rn(__dmul_rn(Ji[0], Ji[3]), __dmul_rn(Ji[1], Ji[2]))));
+        drow[X] = (DstT)res;
     } else {
         // ------------------------- fast mode (fp32) --------------------------------------------
         const float ob = (float)P.oblur, iob = fast_rcp(ob);
@@ -621,7 +628,9 @@ k_jacobian(const __grid_constant__ JacParams P)
                 }
             }
         }
-        drow[X] = (DstT)((wgt > 0) ? val * fast_rcp(wgt) : 0.0f);
+        float res = (wgt > 0) ? val * fast_rcp(wgt) : 0.0f;
+        if (P.flags & TFM_F_FLUX) res *= fabsf((float)Ji[0] * (float)Ji[3] - (float)Ji[1] * (float)Ji[2]);
+        drow[X] = (DstT)res;
     }
     }   // jrow
     if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
@@ -767,8 +776,7 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     if (d.h == 0 || d.w == 0) return TFM_OK;
     if (s.full_h == 0 || s.full_w == 0 || !s.data || !d.data) return TFM_EVALUE;
     if (!(a->oblur > 0) || !(a->pad_pow > 0)) return TFM_EVALUE;
-    for (int i = 0; i < a->n_ops; ++i)
-        if (a->chain[i].kind < TFM_OP_IDENTITY || a->chain[i].kind > TFM_OP_INDEX) return TFM_EVALUE;
+    if (!chain_ops_valid(a->chain, a->n_ops)) return TFM_EVALUE;
     const bool subrect = (s.x0 != 0 || s.y0 != 0 || s.full_h != s.h || s.full_w != s.w);
     if ((a->bound_x == TFM_B_FORBID || a->bound_y == TFM_B_FORBID || subrect) && !a->status_dev)
         return TFM_EVALUE;
@@ -781,6 +789,7 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     P.dst_h = (int)d.h; P.dst_w = (int)d.w; P.dst_x0 = d.x0; P.dst_y0 = d.y0;
     P.grid_h = (int)d.full_h; P.grid_w = (int)d.full_w;
     P.bound_x = a->bound_x; P.bound_y = a->bound_y; P.filter = a->filter;
+    P.flags = a->flags;
     P.src_f64 = s.dtype == TFM_F64; P.dst_f64 = d.dtype == TFM_F64;
     P.oblur = a->oblur; P.pad_pow = a->pad_pow; P.jump_thresh = a->jump_thresh;
     // helpers.pyx:1612-1615: padval 1 for tent/Hanning/Tukey, 3 for Lanczos/Gaussian

@@ -981,8 +981,7 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
     if (d.h == 0 || d.w == 0) return TFM_OK;                                            // ragged / empty output
     if (s.full_h == 0 || s.full_w == 0) return TFM_EVALUE;
     if (!s.data || !d.data) return TFM_EVALUE;
-    for (int i = 0; i < a->n_ops; ++i)
-        if (a->chain[i].kind < TFM_OP_IDENTITY || a->chain[i].kind > TFM_OP_INDEX) return TFM_EVALUE;
+    if (!chain_ops_valid(a->chain, a->n_ops)) return TFM_EVALUE;
 
     ResampleParams P;
     P.src = s.data; P.dst = d.data;

@@ -113,7 +113,7 @@ def _default_resample(transform, sub, origin, full, rows, shape, method, bound, 
     from . import _engine
     y0, y1 = rows
     blk_shape = (y1 - y0, int(shape[-1]))
-    ops = transform._chain(True)
+    ops = transform._int_chain(True)
     m = method[0]
     whole = (origin == (0, 0) and tuple(full) == tuple(sub.shape[-2:]))
     if m in _engine._AA_METHODS:
