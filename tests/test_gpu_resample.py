@@ -303,3 +303,29 @@ def test_filter_2x2_route_equals_general_kernel(tfm):
         a = tr.resample(src, method=m, oblur=ob, precision='fp32')
         b = tr.resample(src, method=m, oblur=ob, precision='fp32', tuning=64)
         assert np.allclose(a, b, rtol=0, atol=2e-6), (m, ob)
+
+
+def test_async_pipeline_matches_synchronous_calls(tfm):
+    """transform_b200.AsyncResampler: same kernels on round-robin streams, copies left in flight;
+    results must equal the synchronous API bit for bit, in any completion order."""
+    import torch
+    rng = np.random.default_rng(90)
+    tr = tfm.Composition([tfm.Scale(1.2, dim=2), tfm.Rotation(15, unit='deg'), tfm.Offset([-300.0, -200.0])])
+    frames = [torch.from_numpy(rng.random((512, 640)).astype(np.float32)).pin_memory() for _ in range(6)]
+    outs = [torch.empty((512, 640), dtype=torch.float32).pin_memory() for _ in range(6)]
+    pipe = tfm.AsyncResampler(depth=3)
+    tickets = []
+    for k, (f, o) in enumerate(zip(frames, outs)):
+        m = ("linear", "Gaussian", "cubic")[k % 3]
+        tickets.append((m, pipe.submit(tr, f, o, method=m, precision="fp32")))
+    for k in (5, 0, 3, 1, 4, 2):
+        m, tk = tickets[k]
+        got = tk.result()
+        want = tr.resample(frames[k], method=m, precision="fp32", out=torch.empty_like(outs[k]).pin_memory())
+        assert torch.equal(got, want), (k, m)
+        assert tk.done()
+    pipe.drain()
+    with pytest.raises(ValueError):
+        pipe.submit(tr, torch.zeros((4, 4)), outs[0])        # pageable input
+    with pytest.raises(ValueError):
+        tr.resample(frames[0], method="linear", precision="fp32", out=torch.empty((512, 640)), sync=False)

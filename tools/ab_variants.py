@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""A/B timing of kernel build variants (run on the GPU box).
+
+    python tools/ab_variants.py k2 name1=path1.so name2=path2.so ...
+
+Each variant is timed in its own process (the library is loaded once per process)."""
+import json
+import os
+import subprocess
+import sys
+
+CHILD = r'''
+import sys, json
+import numpy as np, torch
+sys.path.insert(0, ".")
+import transform_b200 as t
+n = 8192
+g = torch.Generator(device="cuda").manual_seed(7)
+src = torch.rand((n, n), generator=g, device="cuda", dtype=torch.float32)
+dst = torch.empty_like(src)
+c = (n - 1) / 2.0
+tr_rad = t.Composition([t.Scale([n / (2 * np.pi), n / (n / np.sqrt(2.0))]), t.Radial(origin=[c, c])])
+tr_aff = t.Composition([t.Scale(1.3, dim=2), t.Rotation(30, unit="deg"), t.Offset([-n / 2.0, -n / 2.0])])
+def timed(fn, reps):
+    fn(); fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+what = sys.argv[1]
+out = {}
+if what == "k2":
+    out["jacobian_radial_fp32_ms"] = timed(lambda: tr_rad.resample(src, method="G", precision="fp32", out=dst), 10)
+    out["jacobian_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="G", precision="fp32", out=dst), 10)
+else:
+    out["linear_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="linear", precision="fp32", out=dst), 30)
+    out["linear_affine_fp64_ms"] = timed(lambda: tr_aff.resample(src, method="linear"), 10)
+print(json.dumps(out))
+'''
+
+what = sys.argv[1]
+res = {}
+for spec in sys.argv[2:]:
+    name, path = spec.split("=", 1)
+    env = dict(os.environ)
+    if path != "default":
+        env["TFM_B200_LIB"] = os.path.abspath(path)
+    r = subprocess.run([sys.executable, "-c", CHILD, what], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
+    print(name, line, flush=True)
+    try:
+        res[name] = json.loads(line)
+    except Exception:
+        res[name] = {"error": line}
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/ab_%s.json" % what, "w"), indent=1)

@@ -13,5 +13,6 @@ from .helpers import (interpND, interpND_grid, svd2x2, svc2x2, simple_jacobian, 
                       jump_detect, jacobian)
 from .fitswcs import Header, WCSParams, read_fits, FITSHeaderFromDict            # noqa: F401
 from .remap import DataWrapper, WCS                                               # noqa: F401
+from .pipeline import AsyncResampler                                              # noqa: F401
 
 __version__ = "0.1.0"

@@ -112,7 +112,7 @@ def _src_to_device(data, want_f32):
 
 
 def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None, tuning=0,
-             dst_origin=(0, 0), src_origin=(0, 0), src_full=None, out=None, oblur=None):
+             dst_origin=(0, 0), src_origin=(0, 0), src_full=None, out=None, oblur=None, sync=True):
     """K1 driver.  `chain_ops` is the inverse chain in execution order (list of TfmOp)."""
     lib = L.load()
     prec = parse_precision(precision)
@@ -194,21 +194,26 @@ def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None,
     if not from_numpy:
         return dst
     if host_out is not None:
-        return _into_host(dst, host_out)
+        return _into_host(dst, host_out, sync)
     res = dev.to_host(dst)
     if res.dtype != final_dt:
         res = res.astype(final_dt)
     return res
 
 
-def _into_host(dst, host_out):
-    """Device result -> caller-provided host buffer (numpy array or CPU tensor; pinned = one DMA)."""
+def _into_host(dst, host_out, sync=True):
+    """Device result -> caller-provided host buffer (numpy array or CPU tensor; pinned = one DMA).
+    sync=False (pipeline.AsyncResampler): the copy is left in flight on the current stream -- only
+    valid for pinned targets, and the caller owns the synchronisation."""
     torch = dev.torch_mod()
     tgt = host_out if dev.is_tensor(host_out) else torch.from_numpy(host_out)
     if tuple(tgt.shape) != tuple(dst.shape) or tgt.dtype != dst.dtype:
         raise ValueError("out= must have shape %s and dtype %s" % (tuple(dst.shape), dst.dtype))
+    if not sync and not tgt.is_pinned():
+        raise ValueError("asynchronous results need a pinned host buffer")
     tgt.copy_(dst, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    if sync:
+        torch.cuda.current_stream().synchronize()
     return host_out
 
 
@@ -239,7 +244,7 @@ def flux_requested(phot):
 def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=1.0, iblur=1.0,
                       pad_pow=8, sv_limit=0.25, jump_detect=4.0, precision=None, tuning=0,
                       dst_origin=(0, 0), grid_full=None, src_origin=(0, 0), src_full=None,
-                      max_reg=None, out=None, phot='radiance'):
+                      max_reg=None, out=None, phot='radiance', sync=True):
     """K2 driver: interpND_grid(antialias=True) semantics (helpers.pyx:1293-1530) with the
     coordinates generated in-kernel from `chain_ops`."""
     lib = L.load()
@@ -305,7 +310,7 @@ def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=
     if not from_numpy:
         return dst
     if host_out is not None:
-        return _into_host(dst, host_out)
+        return _into_host(dst, host_out, sync)
     return dev.to_host(dst)
 
 

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtfm_b200.so")
+# TFM_B200_LIB selects another build of the SAME library (A/B kernel experiments, tools/ab_variants.py)
+LIB_PATH = os.environ.get("TFM_B200_LIB") or os.path.join(_HERE, "lib", "libtfm_b200.so")
 
 ABI_VERSION = 2
 MAX_OPS = 16

@@ -117,7 +117,7 @@ class Transform:
 
     # -- image path (core.py:422-586) --
     def resample(self, data, /, method='n', bound='t', phot='radiance', shape=None, *,
-                 precision=None, fillvalue=0, tuning=0, out=None, **aa):
+                 precision=None, fillvalue=0, tuning=0, out=None, sync=True, **aa):
         """Resample gridded data through the transform (reference: core.py:422-586).
 
         The output grid is enumerated implicitly, mapped back through the inverse chain in
@@ -136,7 +136,8 @@ class Transform:
 
         Extra keyword-only arguments (not in the reference): precision ('fp64' parity mode,
         default; 'fp32' fast path), fillvalue (interpND's, default 0), out (a CUDA tensor to
-        write into, or a host array / pinned CPU tensor that receives the result)."""
+        write into, or a host array / pinned CPU tensor that receives the result), sync (False
+        leaves the copy into a pinned `out` in flight; used by pipeline.AsyncResampler)."""
         if isinstance(data, np.ndarray) or _engine.dev.is_tensor(data):
             data0 = data
         elif hasattr(data, 'data') and isinstance(data.data, np.ndarray):
@@ -166,12 +167,12 @@ class Transform:
             if aa.pop('antialias', True) and aa.pop('aa', True):
                 return _engine.resample_jacobian(ops, data0, shape, _engine._AA_METHODS[m], bound,
                                                  fillvalue=fillvalue, precision=precision,
-                                                 tuning=tuning, out=out, phot=phot, **aa)
+                                                 tuning=tuning, out=out, phot=phot, sync=sync, **aa)
         oblur = aa.pop('oblur', None)           # interpND's keyword (helpers.pyx:509-516)
         if aa:
             raise TypeError("resample() got unexpected keyword arguments %s" % sorted(aa))
         return _engine.resample(ops, data0, shape, m, bound, fillvalue=fillvalue,
-                                precision=precision, tuning=tuning, out=out, oblur=oblur)
+                                precision=precision, tuning=tuning, out=out, oblur=oblur, sync=sync)
 
     def remap(self, data, /, method='n', bound='t', phot='radiance', shape=None, template=None,
               input_range=None, output_range=None, justify=False, rectify=True, wcs=None, **kw):

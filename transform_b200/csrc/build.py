@@ -27,6 +27,33 @@ def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
+def build_variant(name, defines):
+    """A/B builds for kernel experiments: lib/variants/libtfm_b200_<name>.so compiled with extra -D
+    flags; select it at run time with TFM_B200_LIB=<path> (tools/ab_variants.py)."""
+    vdir = os.path.join(OUT_DIR, "variants")
+    odir = os.path.join(OBJ_DIR, "variant_" + name)
+    os.makedirs(vdir, exist_ok=True)
+    os.makedirs(odir, exist_ok=True)
+    out = os.path.join(vdir, "libtfm_b200_%s.so" % name)
+
+    def one(src):
+        obj = os.path.join(odir, src + ".o")
+        cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(HERE, src), "-o", obj]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stdout))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(one, SOURCES))
+    cmd = [NVCC, "-shared", "-o", out] + objs + ["-Xlinker", "--exclude-libs,ALL", "-lcudart_static",
+                                                  "-lpthread", "-ldl", "-lrt"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s" % r.stdout)
+    return out
+
+
 def build(force=False, verbose=False):
     srcs = [os.path.join(HERE, s) for s in SOURCES]
     deps = srcs + [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]

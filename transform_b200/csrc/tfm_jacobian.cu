@@ -308,32 +308,60 @@ __device__ __forceinline__ void gaussian_quadratic_f32(const double *Ji, float p
     inv_smin = fast_rsqrt(fp);             // the larger singular value has the smaller padded inverse
 }
 
-// (2*HALF+1)^2 Gaussian taps, fully unrolled.  Weights by recurrence: along a row
-// w(a+1) = w(a) r(a), r(a+1) = r(a) cA; from row to row w0 *= rb, rb *= cC, r0 *= cB.
+// (2*HALF+1)^2 Gaussian taps.  Weights by recurrence: along a row w(a+1) = w(a) r(a),
+// r(a+1) = r(a) cA; from row to row w0 *= rb, rb *= cC, r0 *= cB.  Rows are processed in PAIRS with
+// Blackwell's packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100+): lane .x carries row j, lane
+// .y row j+1, so a pair of taps costs 2 loads + 4 packed instructions instead of 2 + 8.  The odd last
+// row runs in scalar form.
 template <int HALF, typename SrcT>
 __device__ __forceinline__ void gauss_taps(const SrcT *p, long long pe, float w0, float r0, float rb,
                                            float cA, float cB, float cC, float &val, float &wgt)
 {
+    constexpr int N = 2 * HALF + 1;
+    const float2 cA2 = make_float2(cA, cA);
+    const float cB2s = cB * cB;                        // two-row steps of the row-to-row recurrences
+    const float cC2s = cC * cC;
+    float2 val2 = make_float2(0.0f, 0.0f), wgt2 = make_float2(0.0f, 0.0f);
 #pragma unroll 1
-    for (int j = 0; j < 2 * HALF + 1; ++j) {
+    for (int j = 0; j + 1 < N; j += 2) {
+        // rows j and j+1: first weights w0, w0*rb; first ratios r0, r0*cB
+        float2 w = make_float2(w0, w0 * rb);
+        float2 r = make_float2(r0, r0 * cB);
+        const SrcT *q = p + pe;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const float2 v = make_float2((float)__ldg(p + k), (float)__ldg(q + k));
+            val2 = __ffma2_rn(v, w, val2);
+            wgt2 = __fadd2_rn(wgt2, w);
+            w = __fmul2_rn(w, r);
+            r = __fmul2_rn(r, cA2);
+        }
+        p += 2 * pe;
+        // advance two rows: w0 <- w0 rb (rb cC) ; rb <- rb cC^2 ; r0 <- r0 cB^2
+        w0 *= rb * (rb * cC);
+        rb *= cC2s;
+        r0 *= cB2s;
+    }
+    {   // last (odd) row
         float w = w0, r = r0;
 #pragma unroll
-        for (int k = 0; k < 2 * HALF + 1; ++k) {
+        for (int k = 0; k < N; ++k) {
             val = fmaf((float)__ldg(p + k), w, val);
             wgt += w;
             w *= r;
             r *= cA;
         }
-        p += pe;
-        w0 *= rb;
-        rb *= cC;
-        r0 *= cB;
     }
+    val += val2.x + val2.y;
+    wgt += wgt2.x + wgt2.y;
 }
 
+#ifndef TFM_K2_MINBLOCKS
+#define TFM_K2_MINBLOCKS 4
+#endif
 // A: chain arithmetic; RegT: footprint arithmetic (double = parity mode, float = fast mode)
 template <class A, typename SrcT, typename DstT, typename RegT, int JTY, bool SPH>
-__global__ void __launch_bounds__(JTX * 8, 4)
+__global__ void __launch_bounds__(JTX * 8, TFM_K2_MINBLOCKS)
 k_jacobian(const __grid_constant__ JacParams P)
 {
     // 256 threads (32 x 8) cover a 32 x JTY tile, JTY in {8, 16, 32}: thread (tx,ty) owns pixels
@@ -401,6 +429,14 @@ k_jacobian(const __grid_constant__ JacParams P)
     __syncthreads();
 
     // ---- 2. Jmag2 per cell: cell (ci,cj) spans points (ci..ci+1, cj..cj+1) ----
+    // Alongside: min and max of Jmag2 over the tile's in-grid cells.  If max <= thresh * min no cell
+    // of the tile can be flagged (its k-th smallest neighbour is >= min), and phase 3 is skipped.
+    // Non-negative floats order like their bit patterns, so the warp reduction is one REDUX each.
+    __shared__ unsigned int s_mm[2];
+    if (tid == 0) { s_mm[0] = 0xffffffffu; s_mm[1] = 0u; }      // ordered by the barrier after phase 1
+    unsigned int mn_bits = 0xffffffffu, mx_bits = 0u;
+    const int NCX = GW - 1, NCY = GH - 1;              // cell grid extent
+    const int wx0 = (int)WX0, wy0 = (int)WY0;
     for (int i = tid; i < CW * CH; i += NTH) {
         const int cj = i / CW, ci = i - cj * CW;
         const double2 pa = s_p[cj + 1][ci + 1], pb = s_p[cj + 1][ci], pc = s_p[cj][ci + 1], pd = s_p[cj][ci];
@@ -413,14 +449,26 @@ k_jacobian(const __grid_constant__ JacParams P)
         const double m2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(j00, j00), __dmul_rn(j01, j01)),
                                               __dmul_rn(j10, j10)), __dmul_rn(j11, j11));
         s_m2[cj][ci] = m2;
-        s_m2f[cj][ci] = (float)m2;
+        const float m2f = (float)m2;
+        s_m2f[cj][ci] = m2f;
+        if ((unsigned)(wx0 + ci) < (unsigned)NCX && (unsigned)(wy0 + cj) < (unsigned)NCY) {
+            const unsigned int b = __float_as_uint(m2f);         // NaN sorts above inf: fails the test below
+            mn_bits = min(mn_bits, b);
+            mx_bits = max(mx_bits, b);
+        }
     }
+    mn_bits = __reduce_min_sync(0xffffffffu, mn_bits);
+    mx_bits = __reduce_max_sync(0xffffffffu, mx_bits);
+    if ((tid & 31) == 0) { atomicMin(&s_mm[0], mn_bits); atomicMax(&s_mm[1], mx_bits); }
     __syncthreads();
 
     // ---- 3. jump flags for the (JTX+1) x (JTY+1) cells the tile's pixels average over ----
-    const int NCX = GW - 1, NCY = GH - 1;              // cell grid extent
-    const int wx0 = (int)WX0, wy0 = (int)WY0;
     const float thr_f = (float)P.jump_thresh;
+    const float tile_mn = __uint_as_float(s_mm[0]), tile_mx = __uint_as_float(s_mm[1]);
+    // CTA-uniform: every cell of the tile passes (or detection is off): no flags to compute or read
+    const bool tile_clean = (P.jump_thresh == 0.0) ||
+                            (thr_f > 0.0f && tile_mx < 1.0e30f && tile_mx * 1.00001f <= thr_f * tile_mn * 0.99999f);
+    if (!tile_clean)
     for (int i = tid; i < (JTX + 1) * (JTY + 1); i += NTH) {
         const int fj = i / (JTX + 1), fi = i - fj * (JTX + 1);
         const int ci = fi + 1, cj = fj + 1;            // index into s_m2 (cell halo of 1)
@@ -443,7 +491,7 @@ k_jacobian(const __grid_constant__ JacParams P)
         }
         s_flag[cj][ci] = flag;
     }
-    __syncthreads();
+    if (!tile_clean) __syncthreads();
 
     // ---- 4. per pixel: grid-centred Jacobian, SVD padding, footprint ----
     int state = 0;
@@ -461,7 +509,8 @@ k_jacobian(const __grid_constant__ JacParams P)
     const int qi = (int)(jx - WX0), qj = (int)(jy - WY0);
 
     double Ji[4] = {0.0, 0.0, 0.0, 0.0};
-    const bool all_ok = (s_flag[qj - 1][qi - 1] & s_flag[qj][qi - 1] & s_flag[qj - 1][qi] & s_flag[qj][qi]) != 0;
+    const bool all_ok = tile_clean ||
+                        (s_flag[qj - 1][qi - 1] & s_flag[qj][qi - 1] & s_flag[qj - 1][qi] & s_flag[qj][qi]) != 0;
     if (FASTI && all_ok) {
         // no flagged cell: the four cell Jacobians add up to the Sobel-like stencil
         //   d/dx = (I[y+1][x+1]-I[y+1][x-1] + 2(I[y][x+1]-I[y][x-1]) + I[y-1][x+1]-I[y-1][x-1]) / 8
@@ -478,7 +527,7 @@ k_jacobian(const __grid_constant__ JacParams P)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int ci = qi - 1 + (k >> 1), cj = qj - 1 + (k & 1);
-            const bool ok = s_flag[cj][ci] != 0;
+            const bool ok = tile_clean || s_flag[cj][ci] != 0;
             nvalid += ok ? 1 : 0;
             const double2 pa = s_p[cj + 1][ci + 1], pb = s_p[cj + 1][ci], pc = s_p[cj][ci + 1], pd = s_p[cj][ci];
             const double ax = pa.x, bx = pb.x, cx = pc.x, dx = pd.x, ay = pa.y, by = pb.y, cy = pc.y, dy = pd.y;

@@ -1,0 +1,73 @@
+"""Stream-pipelined resampling of host frames: upload, kernel and download of consecutive calls overlap.
+
+A synchronous `Transform.resample(host_frame, out=host_buffer)` is a serial chain -- H2D copy, kernel,
+D2H copy -- and for the bandwidth-bound methods the two PCIe copies take 50x longer than the kernel.
+`AsyncResampler` gives each submitted call its own CUDA stream (round-robin over `depth` streams):
+the H2D copy of call k+1, the kernel of call k and the D2H copy of call k-1 run concurrently, and the
+link is used in both directions at once.  Same kernels, same results; only the scheduling differs.
+
+    pipe = AsyncResampler(depth=4)
+    tickets = [pipe.submit(tr, frame, out=buf, method='linear', precision='fp32')
+               for frame, buf in zip(pinned_frames, pinned_outputs)]
+    for t in tickets:
+        result = t.result()          # blocks until that call's D2H copy has landed in `buf`
+    pipe.drain()
+
+Inputs and outputs must be pinned CPU tensors (`torch.empty(...).pin_memory()`): pageable memory
+would turn every copy into a synchronous staged one.
+"""
+from . import _device as dev
+
+
+class Ticket:
+    """Handle of one submitted call: `.result()` waits for its output buffer to be complete."""
+
+    def __init__(self, event, out):
+        self._event = event
+        self._out = out
+
+    def done(self):
+        return self._event.query()
+
+    def result(self):
+        self._event.synchronize()
+        return self._out
+
+
+class AsyncResampler:
+    def __init__(self, depth=4, device=None):
+        torch = dev.require_cuda()
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self._torch = torch
+        self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._streams = [torch.cuda.Stream(device=self._device) for _ in range(depth)]
+        self._events = [None] * depth
+        self._next = 0
+
+    def submit(self, transform, data, out, method='n', bound='t', **kw):
+        """Enqueue transform.resample(data, method, bound, out=out, **kw); returns a Ticket."""
+        torch = self._torch
+        if not (dev.is_tensor(data) and not data.is_cuda and data.is_pinned()):
+            raise ValueError("AsyncResampler.submit: `data` must be a pinned CPU tensor")
+        if not (dev.is_tensor(out) and not out.is_cuda and out.is_pinned()):
+            raise ValueError("AsyncResampler.submit: `out` must be a pinned CPU tensor")
+        slot = self._next
+        self._next = (slot + 1) % len(self._streams)
+        stream = self._streams[slot]
+        prev = self._events[slot]
+        if prev is not None:
+            prev.synchronize()               # bound the queue: at most `depth` calls in flight
+        # work submitted by the caller on the current stream (e.g. filling `data`) comes first
+        stream.wait_stream(torch.cuda.current_stream(self._device))
+        with torch.cuda.stream(stream):
+            transform.resample(data, method=method, bound=bound, out=out, sync=False, **kw)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._events[slot] = ev
+        return Ticket(ev, out)
+
+    def drain(self):
+        for ev in self._events:
+            if ev is not None:
+                ev.synchronize()
