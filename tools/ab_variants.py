@@ -34,8 +34,12 @@ if what == "k2":
     out["jacobian_radial_fp32_ms"] = timed(lambda: tr_rad.resample(src, method="G", precision="fp32", out=dst), 10)
     out["jacobian_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="G", precision="fp32", out=dst), 10)
 else:
-    out["linear_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="linear", precision="fp32", out=dst), 30)
-    out["linear_affine_fp64_ms"] = timed(lambda: tr_aff.resample(src, method="linear"), 10)
+    maps = {"named": tr_aff, "shift": t.Offset([3.25, -7.5]), "scale0p8": t.Scale(0.8, dim=2),
+            "rot5": t.Wrap(t.Rotation(5, unit="deg"), t.Offset([-n / 2.0, -n / 2.0])),
+            "rot45": t.Wrap(t.Rotation(45, unit="deg"), t.Offset([-n / 2.0, -n / 2.0])),
+            "polar": tr_rad}
+    for name, tr in maps.items():
+        out["linear_%s_fp32_ms" % name] = round(timed(lambda: tr.resample(src, method="linear", precision="fp32", out=dst), 30), 4)
 print(json.dumps(out))
 '''
 
