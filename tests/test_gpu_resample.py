@@ -329,3 +329,19 @@ def test_async_pipeline_matches_synchronous_calls(tfm):
         pipe.submit(tr, torch.zeros((4, 4)), outs[0])        # pageable input
     with pytest.raises(ValueError):
         tr.resample(frames[0], method="linear", precision="fp32", out=torch.empty((512, 640)), sync=False)
+
+
+def test_tma_staged_variant_is_bit_identical(tfm):
+    """tuning bit 256: the TMA-staged shared-memory variant of the fp32 linear kernel (affine maps).
+    Zero-filled out-of-range box parts are the truncate boundary; results equal the texture variant."""
+    import torch
+    rng = np.random.default_rng(91)
+    src = torch.from_numpy(rng.random((700, 896)).astype(np.float32)).cuda()   # pitch % 32 == 0
+    for tr in (tfm.Offset([3.25, -7.5]), tfm.Scale(0.45, dim=2),
+               tfm.Composition([tfm.Scale(1.3, dim=2), tfm.Rotation(30, unit='deg'), tfm.Offset([-450.0, -350.0])]),
+               tfm.Wrap(tfm.Rotation(45, unit='deg'), tfm.Offset([-450.0, -350.0]))):
+        for shape in ((700, 896), (333, 517)):
+            a = tr.resample(src, method='linear', precision='fp32', shape=shape)
+            b = tr.resample(src, method='linear', precision='fp32', shape=shape, tuning=256)
+            assert torch.equal(a, b), (str(tr), shape)
+    assert tfm._lib.load().tfm_last_kernel().decode().startswith("k_resample_tma")

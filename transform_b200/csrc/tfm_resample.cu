@@ -11,6 +11,7 @@
 // covers a WW x (32/WW) patch (WW = 32, 16 or 8, chosen per launch from the local rotation of the
 // map) so that one warp-wide tap load touches as few 128-byte lines as possible, and repeats it
 // NPX times 8 rows apart with all loads of the NPX pixels in flight together.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -695,6 +696,194 @@ static bool get_texture(const void *ptr, int w, int h, long long pitch, cudaText
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA-staged variant (fp32 fast path, linear, affine map, bound = truncate with fill 0, whole image)
+// ---------------------------------------------------------------------------------------------
+// An affine map sends a 32 x 32 output tile to a parallelogram whose bounding box has a size the host
+// knows in advance.  One elected thread asks the Tensor Memory Accelerator for exactly that box
+// (cp.async.bulk.tensor.2d, completion on an mbarrier); out-of-range parts of the box are zero-filled
+// by the TMA unit, which IS the reference's truncate boundary with its default fillvalue -- no
+// per-tap classification anywhere.  While the box is in flight all threads evaluate their
+// coordinates; then every tap is a shared-memory load.  HBM sees each source line once per tile
+// (halo overlaps are L2 hits), registers are not staged through, and neither the LSU address path
+// nor the texture write-back (the two limits of the other variants) is on the critical path.
+// Status: correct (bit-identical to the other variants, tests), but measured slower than the texture
+// gather in this one-box-per-CTA form (see the dispatch below); kept behind a tuning bit.
+struct TmaBox {
+    int bw, bh;                              // box columns / rows (bw * 4 bytes is a multiple of 16)
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256)
+k_resample_tma(const __grid_constant__ ResampleParams P, const __grid_constant__ CUtensorMap tmap,
+               const __grid_constant__ TmaBox B)
+{
+    constexpr int NPX = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // the box first (TMA needs a 128-byte aligned destination: no static shared memory in this kernel,
+    // so the dynamic window starts at offset 0), the mbarrier behind it
+    float *const tile = reinterpret_cast<float *>(smem_raw);
+    unsigned long long *const s_mbar_p = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)B.bw * B.bh * 4);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    char *const dst_base = static_cast<char *>(P.dst);
+    const int px = ((warp & 1) << 4) + (lane & 15);
+    const int py = ((warp >> 1) << 1) + (lane >> 4);
+    const int X = blockIdx.x * 32 + px;
+    const int Y0 = blockIdx.y * (8 * NPX) + py;
+    const bool xin = X < P.dst_w;
+
+    // CTA-uniform rejection of empty tiles (see k_resample)
+    {
+        const float tx0 = (float)(int)(blockIdx.x * 32) + P.aff_f[6], tx1 = tx0 + 31.0f;
+        const float ty0 = (float)(int)(blockIdx.y * 32) + P.aff_f[7], ty1 = ty0 + 31.0f;
+        const float ux0 = P.aff_f[0] * tx0, ux1 = P.aff_f[0] * tx1, uy0 = P.aff_f[1] * ty0, uy1 = P.aff_f[1] * ty1;
+        const float vx0 = P.aff_f[2] * tx0, vx1 = P.aff_f[2] * tx1, vy0 = P.aff_f[3] * ty0, vy1 = P.aff_f[3] * ty1;
+        const float xmin = fminf(ux0, ux1) + fminf(uy0, uy1) + P.aff_f[4], xmax = fmaxf(ux0, ux1) + fmaxf(uy0, uy1) + P.aff_f[4];
+        const float ymin = fminf(vx0, vx1) + fminf(vy0, vy1) + P.aff_f[5], ymax = fmaxf(vx0, vx1) + fmaxf(vy0, vy1) + P.aff_f[5];
+        const float pad = 4.0f + P.aff_margin;
+        if (xmax < -pad || ymax < -pad || xmin > (float)P.src_w + pad || ymin > (float)P.src_h + pad) {
+            if (xin) {
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) {
+                    const int Y = Y0 + 8 * j;
+                    if (Y < P.dst_h) reinterpret_cast<float *>(dst_base + (long long)Y * P.dst_pitch)[X] = 0.0f;
+                }
+            }
+            return;
+        }
+    }
+
+    // source box of this tile: the map is affine, so the extremes are at the tile corners; one pixel
+    // of margin on the low side, the host-chosen box size covers the high side
+    const double TX = (double)(P.dst_x0 + (long long)blockIdx.x * 32), TY = (double)(P.dst_y0 + (long long)blockIdx.y * 32);
+    const double cx0 = fma(P.aff[0], TX, fma(P.aff[1], TY, P.aff[4]));
+    const double cy0 = fma(P.aff[2], TX, fma(P.aff[3], TY, P.aff[5]));
+    const double xlo = cx0 + fmin(31.0 * P.aff[0], 0.0) + fmin(31.0 * P.aff[1], 0.0);
+    const double ylo = cy0 + fmin(31.0 * P.aff[2], 0.0) + fmin(31.0 * P.aff[3], 0.0);
+    // the box must start on a 16-byte boundary of the innermost axis (measured: an unaligned start
+    // coordinate raises an illegal-instruction fault), hence the round-down to a multiple of 4 pixels
+    const int bx0 = ((int)floor(xlo) - 1) & ~3, by0 = (int)floor(ylo) - 1;     // |coordinate| < 1e9: host-proven
+
+    const uint32_t mbar = smem_addr(s_mbar_p);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = (uint32_t)(B.bw * B.bh * 4);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(smem_addr(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(bx0), "r"(by0), "r"(mbar)
+            : "memory");
+    }
+
+    // coordinates while the box is in flight
+    float fx[NPX], fy[NPX];
+    int lx[NPX], ly[NPX];
+    {
+        const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y0);
+        const double bx = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
+        const double by = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            int ix, iy;
+            floor_frac_fast(fma((double)(8 * j), P.aff[1], bx), ix, fx[j]);
+            floor_frac_fast(fma((double)(8 * j), P.aff[3], by), iy, fy[j]);
+            lx[j] = ix - bx0;
+            ly[j] = iy - by0;
+        }
+    }
+    __syncthreads();                                   // the barrier's initialisation is visible to all
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar), "r"(0u) : "memory");
+        }
+    }
+
+    const int bw = B.bw;
+#pragma unroll
+    for (int j = 0; j < NPX; ++j) {
+        const int Y = Y0 + 8 * j;
+        if (!xin || Y >= P.dst_h) continue;
+        float v00, v01, v10, v11;
+        if ((unsigned)lx[j] < (unsigned)(bw - 1) && (unsigned)ly[j] < (unsigned)(B.bh - 1)) {
+            const float *t = tile + ly[j] * bw + lx[j];
+            v00 = t[0]; v01 = t[1]; v10 = t[bw]; v11 = t[bw + 1];
+        } else {
+            // cannot happen for in-range arithmetic; kept so that a rounding surprise reads the right
+            // texel from global memory instead of a wrong one from the box
+            const int ix = lx[j] + bx0, iy = ly[j] + by0;
+            v00 = tap_trunc<float, float>(P, P.src, ix, iy);
+            v01 = tap_trunc<float, float>(P, P.src, ix + 1, iy);
+            v10 = tap_trunc<float, float>(P, P.src, ix, iy + 1);
+            v11 = tap_trunc<float, float>(P, P.src, ix + 1, iy + 1);
+        }
+        const float top = fmaf(fx[j], v01 - v00, v00);
+        const float bot = fmaf(fx[j], v11 - v10, v10);
+        reinterpret_cast<float *>(dst_base + (long long)Y * P.dst_pitch)[X] = fmaf(fy[j], bot - top, top);
+    }
+}
+
+// Tensor maps over caller memory, cached like the texture objects (the map describes an address range
+// and a box shape, not contents).  cuTensorMapEncodeTiled comes from the driver through the runtime's
+// entry-point query: no link-time dependency on libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmapKey {
+    int dev; const void *ptr; int w, h; long long pitch; int bw, bh;
+    bool operator==(const TmapKey &o) const
+    { return dev == o.dev && ptr == o.ptr && w == o.w && h == o.h && pitch == o.pitch && bw == o.bw && bh == o.bh; }
+};
+static std::mutex g_tmap_mu;
+static TmapKey g_tmap_keys[16];
+static CUtensorMap g_tmap_maps[16];
+static int g_tmap_n = 0, g_tmap_next = 0;
+
+static bool get_tensor_map(const void *ptr, int w, int h, long long pitch, int bw, int bh, CUtensorMap *out)
+{
+    static EncodeTiledFn encode = nullptr;
+    static bool looked_up = false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    TmapKey key{dev, ptr, w, h, pitch, bw, bh};
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    if (!looked_up) {
+        looked_up = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeTiledFn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode) return false;
+    for (int i = 0; i < g_tmap_n; ++i)
+        if (g_tmap_keys[i] == key) { *out = g_tmap_maps[i]; return true; }
+    CUtensorMap m;
+    const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    int slot;
+    if (g_tmap_n < 16) slot = g_tmap_n++;
+    else { slot = g_tmap_next; g_tmap_next = (g_tmap_next + 1) & 15; }
+    g_tmap_keys[slot] = key;
+    g_tmap_maps[slot] = m;
+    *out = m;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // windowed ("collapsible") filters: sinc, Lanczos, Gaussian, Hann, Tukey, tent-with-oblur
 // ---------------------------------------------------------------------------------------------
 // helpers.pyx:703-735, 792-835.  A size x size region at floor(v) - (size/2 - 1) is weighted by a
@@ -1081,7 +1270,39 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
                             s.w <= 131072 && s.h <= 65000 && (s.pitch % 32) == 0 &&
                             (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 &&
                             get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &tex);
-        if (tex_ok) {
+        // TMA-staged variant: same conditions, host-composed affine map with a bounded source box
+        bool tma_done = false;
+        // Opt-in (tuning bit 256): measured SLOWER than the texture gather on B200 (8192^2: named chain
+        // 0.138 vs 0.090 ms, pure shift 0.227 vs 0.141 ms) -- per-CTA load latency is exposed in this
+        // one-box-per-CTA form and the shared-memory taps cost more issue slots than one TLD4.
+        if (tex_ok && aff && P.aff_bounded && (a->tuning & 256) && (s.pitch % 16) == 0) {
+            const double ex = 31.0 * (fabs(P.aff[0]) + fabs(P.aff[1])), ey = 31.0 * (fabs(P.aff[2]) + fabs(P.aff[3]));
+            if (ex < 200.0 && ey < 200.0) {
+                TmaBox B;
+                // +1 low margin, +2 for floor/+1 tap, +1 slack, +3 for the aligned start; multiple of 4
+                B.bw = (((int)ceil(ex) + 7) + 3) & ~3;
+                B.bh = (int)ceil(ey) + 4;
+                const size_t smem = (size_t)B.bw * B.bh * 4 + 16;          // box + mbarrier
+                CUtensorMap tm;
+                if (B.bw <= 256 && B.bh <= 256 && smem <= 96 * 1024 &&
+                    get_tensor_map(s.data, (int)s.w, (int)s.h, s.pitch, B.bw, B.bh, &tm)) {
+                    dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 31) / 32), 1);
+                    if (grid.y > 65535u) return TFM_EUNSUPPORTED;
+                    cudaError_t ea = cudaSuccess;
+                    if (smem > 48 * 1024)
+                        ea = cudaFuncSetAttribute(k_resample_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (ea == cudaSuccess) {
+                        k_resample_tma<0><<<grid, 256, smem, st>>>(P, tm, B);
+                        count_launch();
+                        name = "k_resample_tma<affine>";
+                        e = cudaGetLastError();
+                        tma_done = true;
+                    }
+                }
+            }
+        }
+        if (tma_done) {
+        } else if (tex_ok) {
             dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 31) / 32), 1);
             if (grid.y > 65535u) return TFM_EUNSUPPORTED;
             if (aff) k_resample_tex<Fast, true, false><<<grid, 256, 0, st>>>(P, tex);
