@@ -381,7 +381,7 @@ def gpu_arm(args):
         brk["linear_affine_fp32_ms"] = ms_lin
         brk["jacobian_radial_fp32_ms"] = ms_jac
         brk["linear_radial_fp32_ms"] = timed(lambda: tr_rad.resample(src, method="linear", precision="fp32", out=out_lin))
-        for tn, nm in ((16, "ldg_gather"), (4 | 16, "ldg_gather_interpreted_chain")):
+        for tn, nm in ((16, "ldg_gather"), (4 | 16, "ldg_gather_interpreted_chain"), (256, "tma_staged")):
             brk["linear_affine_fp32_%s_ms" % nm] = timed(
                 lambda: tr_aff.resample(src, method="linear", precision="fp32", out=out_lin, tuning=tn))
         for tn, nm in ((8, "32x16"), (32, "32x8")):
