@@ -273,6 +273,16 @@ typedef struct tfm_apply_args {
 
 TFM_API int tfm_apply(const tfm_apply_args *args, void *stream);
 
+/* ---- K0: FITS pixel decode (the step before the path: file -> device image) ----
+ * Replaces what astropy.io.fits does for the reference when it opens the file (core.py:991-1023,
+ * DataWrapper on a file name / HDU): big-endian BITPIX samples -> native floating point, with
+ * physical = BZERO + BSCALE * stored when either keyword is non-trivial.
+ * raw: device pointer to the data unit as it sits in the file (16-byte aligned), n samples.
+ * out: TFM_F32 for BITPIX = -32 (a byte swap; scaling in float32), TFM_F64 for every BITPIX
+ *      (integers convert exactly; scaling is one rounded multiply and one rounded add). */
+TFM_API int tfm_fits_decode(const void *raw, int32_t bitpix, int64_t n, double bscale, double bzero,
+                            int32_t out_dtype, void *out, void *stream);
+
 /* ---- the Jacobian helpers the reference exposes as module functions (2-D case) ----
  * All pointers are device pointers, arrays dense and row-major, float64 (flags int64 like NumPy's int).
  * tfm_simple_jacobian  replaces simple_jacobian(index)            helpers.pyx:846-958 (2-D: 896-906)

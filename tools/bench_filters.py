@@ -34,3 +34,22 @@ for prec in ("fp32", "fp64"):
             print(prec, name, m, ob, "%.3f ms" % ms, "%.0f Mpix/s" % (n * n / ms / 1e3), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/filters.json", "w"), indent=1)
+
+# K0: FITS decode throughput (8192^2 samples)
+import transform_b200 as t2  # noqa: E402
+peak = 6547.5
+nn = n * n
+for bitpix, out_b in ((-32, 4), (16, 8), (-64, 8)):
+    raw = torch.randint(0, 255, (nn * abs(bitpix) // 8,), device="cuda", dtype=torch.uint8)
+    t2.decode_fits_data(raw, bitpix, (n, n))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        t2.decode_fits_data(raw, bitpix, (n, n))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gbs = nn * (abs(bitpix) // 8 + out_b) / (ms * 1e-3) / 1e9
+    print("fits decode BITPIX %d: %.3f ms  %.0f GB/s (%.0f%% of %.0f)" % (bitpix, ms, gbs, 100 * gbs / peak, peak), flush=True)
+    del raw

@@ -11,7 +11,8 @@ from .basic import (Linear, Scale, Rotation, Offset, Radial, Quadpin, Cubicpin, 
                     Poly, Quarticpin)
 from .helpers import (interpND, interpND_grid, svd2x2, svc2x2, simple_jacobian,   # noqa: F401
                       jump_detect, jacobian)
-from .fitswcs import Header, WCSParams, read_fits, FITSHeaderFromDict            # noqa: F401
+from .fitswcs import (Header, WCSParams, read_fits, FITSHeaderFromDict,           # noqa: F401
+                      decode_fits_data)
 from .remap import DataWrapper, WCS                                               # noqa: F401
 from .pipeline import AsyncResampler                                              # noqa: F401
 

@@ -77,7 +77,7 @@ class TfmApplyArgs(ctypes.Structure):
 
 
 EXPORTED_SYMBOLS = ("tfm_resample", "tfm_resample_jacobian", "tfm_apply", "tfm_svd2x2", "tfm_svc2x2",
-                    "tfm_simple_jacobian", "tfm_jump_detect", "tfm_jacobian_grid",
+                    "tfm_simple_jacobian", "tfm_jump_detect", "tfm_jacobian_grid", "tfm_fits_decode",
                     "tfm_abi_version", "tfm_strerror", "tfm_launch_count", "tfm_last_kernel")
 
 _lib = None
@@ -110,6 +110,8 @@ def load():
     lib.tfm_apply.restype = ctypes.c_int
     lib.tfm_apply.argtypes = [ctypes.POINTER(TfmApplyArgs), ctypes.c_void_p]
     vp, i64 = ctypes.c_void_p, ctypes.c_int64
+    lib.tfm_fits_decode.restype = ctypes.c_int
+    lib.tfm_fits_decode.argtypes = [vp, ctypes.c_int32, i64, ctypes.c_double, ctypes.c_double, ctypes.c_int32, vp, vp]
     lib.tfm_simple_jacobian.restype = ctypes.c_int
     lib.tfm_simple_jacobian.argtypes = [vp, i64, i64, vp, vp]
     lib.tfm_jump_detect.restype = ctypes.c_int

@@ -68,6 +68,13 @@ int tfm_jacobian_grid(const double *Js, const int64_t *flags, int64_t ny, int64_
     return tfm::jacobian_helpers(2, Js, flags, ny, nx, 0.0, J, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int tfm_fits_decode(const void *raw, int32_t bitpix, int64_t n, double bscale, double bzero,
+                    int32_t out_dtype, void *out, void *stream)
+{
+    return tfm::fits_decode_dispatch(raw, bitpix, n, bscale, bzero, out_dtype, out,
+                                     static_cast<cudaStream_t>(stream));
+}
+
 int tfm_svd2x2(const double *M, double *U, double *s, double *V)
 {
     if (!M || !U || !s || !V) return TFM_EVALUE;

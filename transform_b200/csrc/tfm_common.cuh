@@ -14,6 +14,8 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st);
 int apply_dispatch(const tfm_apply_args *a, cudaStream_t st);
 int jacobian_helpers(int which, const void *in0, const void *in1, long long ny, long long nx, double thresh,
                      void *out, void *scratch, cudaStream_t st);
+int fits_decode_dispatch(const void *raw, int bitpix, long long n, double bscale, double bzero,
+                         int out_dtype, void *out, cudaStream_t st);
 int svd_hooks(int which, const double *in0, const double *in1, const double *in2,
               double *out0, double *out1, double *out2);
 

@@ -163,8 +163,37 @@ def _parse_card_value(text):
         return text
 
 
-def read_fits(path):
-    """Read the primary HDU of a FITS file -> HDUList([PrimaryHDU(data, header)])."""
+def decode_fits_data(raw_dev, bitpix, shape, bscale=1, bzero=0):
+    """FITS data unit on the device -> CUDA tensor of `shape` (K0, csrc/tfm_fits.cu).
+
+    raw_dev: 1-D uint8 CUDA tensor holding the big-endian samples as they sit in the file.
+    Returns float32 for BITPIX = -32 (a byte swap; scaling, if any, in float32 as NumPy does for a
+    float32 array and Python scalars), float64 otherwise -- integer samples convert exactly (the
+    resamplers carry integer images as float64 anyway) and scaling is `stored * BSCALE + BZERO`
+    with NumPy's two roundings."""
+    from . import _device as dev
+    torch = dev.require_cuda()
+    lib = L.load()
+    n = 1
+    for s_ in shape:
+        n *= int(s_)
+    nbytes = n * (abs(int(bitpix)) // 8)
+    if raw_dev.dtype != torch.uint8 or not raw_dev.is_cuda or raw_dev.numel() < nbytes:
+        raise ValueError("decode_fits_data: raw_dev must be a uint8 CUDA tensor of at least %d bytes" % nbytes)
+    f32 = int(bitpix) == -32
+    out = torch.empty(tuple(int(s_) for s_ in shape), dtype=torch.float32 if f32 else torch.float64,
+                      device=raw_dev.device)
+    rc = lib.tfm_fits_decode(raw_dev.data_ptr(), int(bitpix), n, float(bscale), float(bzero),
+                             L.F32 if f32 else L.F64, out.data_ptr(), dev.stream_ptr())
+    L.raise_for_status(rc, "tfm_fits_decode")
+    return out
+
+
+def read_fits(path, device=False):
+    """Read the primary HDU of a FITS file -> HDUList([PrimaryHDU(data, header)]).
+
+    device=True: the data unit is uploaded as raw bytes and decoded on the GPU (`decode_fits_data`);
+    `data` is then a CUDA tensor that resample()/remap() take without another copy."""
     with open(path, "rb") as f:
         raw = f.read()
     hdr = Header()
@@ -192,6 +221,18 @@ def read_fits(path):
         bitpix = int(hdr["BITPIX"])
         dt = {8: ">u1", 16: ">i2", 32: ">i4", 64: ">i8", -32: ">f4", -64: ">f8"}[bitpix]
         n = int(np.prod(shape, dtype=np.int64))
+        if device:
+            from . import _device as dev
+            torch = dev.require_cuda()
+            nbytes = n * (abs(bitpix) // 8)
+            if len(raw) < pos + nbytes:
+                raise ValueError("read_fits: truncated data unit in %s" % path)
+            stage = dev._pinned(nbytes, "fits")
+            stage[:nbytes].numpy()[:] = np.frombuffer(raw, dtype=np.uint8, count=nbytes, offset=pos)
+            raw_dev = stage[:nbytes].to("cuda", non_blocking=True)
+            data = decode_fits_data(raw_dev, bitpix, shape, hdr.get("BSCALE", 1), hdr.get("BZERO", 0))
+            torch.cuda.current_stream().synchronize()        # the staging buffer is reused
+            return HDUList([PrimaryHDU(data, hdr)])
         arr = np.frombuffer(raw, dtype=dt, count=n, offset=pos).reshape(shape)
         data = arr.astype(arr.dtype.newbyteorder("="))
         bscale, bzero = hdr.get("BSCALE", 1), hdr.get("BZERO", 0)
