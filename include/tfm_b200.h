@@ -94,6 +94,16 @@ typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
 #define TFM_WCS_PROJ_NONE 0
 #define TFM_WCS_PROJ_TAN 1
 #define TFM_WCS_PROJ_CAR 2
+/* further projections of paper II (Calabretta & Greisen 2002), default projection parameters only */
+#define TFM_WCS_PROJ_STG 3   /* stereographic            eq. 56-57 */
+#define TFM_WCS_PROJ_SIN 4   /* orthographic (xi=eta=0)  eq. 59-60 */
+#define TFM_WCS_PROJ_ARC 5   /* zenithal equidistant     eq. 67-68 */
+#define TFM_WCS_PROJ_ZEA 6   /* zenithal equal-area      eq. 69-70 */
+#define TFM_WCS_PROJ_CEA 7   /* cylindrical equal-area (lambda=1) eq. 80-81 */
+#define TFM_WCS_PROJ_MER 8   /* Mercator                 eq. 85-86 */
+#define TFM_WCS_PROJ_SFL 9   /* Sanson-Flamsteed         eq. 87-88 */
+#define TFM_WCS_PROJ_AIT 10  /* Hammer-Aitoff            eq. 108-110 */
+#define TFM_WCS_PROJ_MAX 10
 
 /* TFM_OP_INDEX
  *   p[0] the BIT PATTERN of a device pointer to float64 index[ny][nx][2] (dense, (X,Y) last axis)

@@ -944,6 +944,78 @@ def _jacobian_rows(coords, ya, yb, ny, jump_thresh):
 # --------------------------------------------------------------------------------------
 # FITS WCS (core.py:1719-1747 -> astropy.wcs.WCS.all_pix2world / all_world2pix, origin 0)
 # --------------------------------------------------------------------------------------
+_R0 = 180.0 / np.pi
+
+
+def _deproject(proj, x, y):
+    """Projection-plane (x, y) [deg] -> native (phi, theta) [deg]; Calabretta & Greisen 2002, in the
+    paper's own angle form (the CUDA path works on unit vectors: the two derivations cross-check)."""
+    with np.errstate(all="ignore"):
+        if proj in ("TAN", "STG", "SIN", "ARC", "ZEA"):                      # zenithal, eq. 14-15
+            R = np.hypot(x, y)
+            phi = np.where(R == 0, 0.0, np.degrees(np.arctan2(x, -y)))
+            if proj == "TAN":
+                theta = np.degrees(np.arctan2(_R0, R))                       # eq. 55
+            elif proj == "STG":
+                theta = 90.0 - 2.0 * np.degrees(np.arctan(R / (2.0 * _R0)))  # eq. 57
+            elif proj == "SIN":
+                theta = np.degrees(np.arccos(R / _R0))                       # eq. 60 (NaN beyond the limb)
+            elif proj == "ARC":
+                theta = np.where(R <= 180.0, 90.0 - R, np.nan)               # eq. 68
+            else:
+                theta = 90.0 - 2.0 * np.degrees(np.arcsin(R / (2.0 * _R0)))  # eq. 70
+            return phi, theta
+        if proj == "CAR":
+            return x, y                                                      # eq. 83-84
+        if proj == "CEA":
+            return x, np.degrees(np.arcsin(y / _R0))                         # eq. 81, lambda = 1
+        if proj == "MER":
+            return x, 2.0 * np.degrees(np.arctan(np.exp(y / _R0))) - 90.0    # eq. 86
+        if proj == "SFL":
+            c = np.cos(np.radians(y))
+            phi = np.where(c > 0, x / np.where(c > 0, c, 1.0), np.where(x == 0, 0.0, np.nan))   # eq. 88
+            phi = np.where((np.abs(y) <= 90.0) & (np.abs(phi) <= 180.0 * (1 + 1e-12)), phi, np.nan)
+            return phi, y
+        if proj == "AIT":
+            z2 = 1.0 - (x / (4.0 * _R0)) ** 2 - (y / (2.0 * _R0)) ** 2       # eq. 109-110
+            z2 = np.where(z2 >= 0.5 * (1 - 1e-12), z2, np.nan)
+            Z = np.sqrt(z2)
+            phi = 2.0 * np.degrees(np.arctan2((x / (2.0 * _R0)) * Z, 2.0 * z2 - 1.0))
+            theta = np.degrees(np.arcsin((y / _R0) * Z))
+            return phi, theta
+    raise ValueError(proj)
+
+
+def _project(proj, phi, theta):
+    """Native (phi, theta) [deg] -> projection-plane (x, y) [deg]."""
+    ph, th = np.radians(phi), np.radians(theta)
+    with np.errstate(all="ignore"):
+        if proj in ("TAN", "STG", "SIN", "ARC", "ZEA"):
+            if proj == "TAN":
+                R = np.where(theta > 0, _R0 / np.tan(th), np.nan)            # eq. 54
+            elif proj == "STG":
+                R = np.where(theta > -90, 2.0 * _R0 * np.tan(np.radians(90.0 - theta) / 2.0), np.nan)
+            elif proj == "SIN":
+                R = np.where(theta >= 0, _R0 * np.cos(th), np.nan)           # eq. 59
+            elif proj == "ARC":
+                R = 90.0 - theta                                             # eq. 67
+            else:
+                R = np.where(theta > -90, 2.0 * _R0 * np.sin(np.radians(90.0 - theta) / 2.0), np.nan)
+            return R * np.sin(ph), -R * np.cos(ph)                           # eq. 12-13
+        if proj == "CAR":
+            return phi, theta
+        if proj == "CEA":
+            return phi, _R0 * np.sin(th)
+        if proj == "MER":
+            return phi, np.where(np.abs(theta) < 90, _R0 * np.log(np.tan(np.radians(90.0 + theta) / 2.0)), np.nan)
+        if proj == "SFL":
+            return phi * np.cos(th), theta
+        if proj == "AIT":
+            g = np.sqrt(2.0 / (1.0 + np.cos(th) * np.cos(ph / 2.0)))         # eq. 108
+            return 2.0 * _R0 * g * np.cos(th) * np.sin(ph / 2.0), _R0 * g * np.sin(th)
+    raise ValueError(proj)
+
+
 class WCS(Op):
     """pixel (origin 0) <-> world for two axes.
 
@@ -955,7 +1027,8 @@ class WCS(Op):
       * TAN / CAR:   PARITY UNPINNED (nothing in the reference's tests exercises them).
     Deliberately written with the explicit Euler-angle formulas per point -- not with the 3x3
     rotation matrix the CUDA path uses -- so that the two derivations check each other.
-    proj: None (linear axes), 'TAN' or 'CAR'.  cd = CDELT_i * PC_ij."""
+    proj: None (linear axes), 'TAN', 'CAR', or one of STG SIN ARC ZEA CEA MER SFL AIT (default
+    projection parameters).  cd = CDELT_i * PC_ij."""
 
     def __init__(self, crpix, cd, crval, proj=None, lonpole=None, latpole=None):
         self.crpix = np.asarray(crpix, dtype=np.float64)
@@ -964,7 +1037,7 @@ class WCS(Op):
         self.crval = np.asarray(crval, dtype=np.float64)
         self.proj = proj
         if proj is not None:
-            phi0, theta0 = {"TAN": (0.0, 90.0), "CAR": (0.0, 0.0)}[proj]
+            phi0, theta0 = (0.0, 90.0) if proj in ("TAN", "STG", "SIN", "ARC", "ZEA") else (0.0, 0.0)
             a0, d0 = self.crval
             self.phi_p = lonpole if lonpole is not None else phi0 + (0.0 if d0 >= theta0 else 180.0)
             theta_p = 90.0 if latpole is None else latpole
@@ -1000,12 +1073,7 @@ class WCS(Op):
             out[..., 0] = ix + self.crval[0]
             out[..., 1] = iy + self.crval[1]
             return out
-        if self.proj == "TAN":
-            r = np.sqrt(ix * ix + iy * iy)
-            phi = np.where(r == 0, 0.0, np.degrees(np.arctan2(ix, -iy)))
-            theta = np.degrees(np.arctan2(180.0 / np.pi, r))
-        else:
-            phi, theta = ix, iy
+        phi, theta = _deproject(self.proj, ix, iy)
         ph, th, dp = np.radians(phi - self.phi_p), np.radians(theta), np.radians(self.delta_p)
         # eq. (2); the latitude is taken with atan2(z, hypot(x, y)) instead of asin(z) -- the
         # well-conditioned form wcslib switches to near the poles (sphx2s)
@@ -1034,13 +1102,7 @@ class WCS(Op):
             theta = np.degrees(np.arctan2(zz, np.hypot(xx, yy)))
             phi = np.where(phi > 180.0, phi - 360.0, phi)
             phi = np.where(phi <= -180.0, phi + 360.0, phi)
-            if self.proj == "TAN":
-                with np.errstate(divide="ignore", invalid="ignore"):
-                    r = np.where(zz > 0, (180.0 / np.pi) * np.hypot(xx, yy) / zz, np.nan)   # r0 cot(theta)
-                ix = r * np.sin(np.radians(phi))
-                iy = -r * np.cos(np.radians(phi))
-            else:
-                ix, iy = phi, theta
+            ix, iy = _project(self.proj, phi, theta)
         px = self.cdinv[0, 0] * ix + self.cdinv[0, 1] * iy
         py = self.cdinv[1, 0] * ix + self.cdinv[1, 1] * iy
         out = np.empty(v.shape, dtype=np.float64)

@@ -72,7 +72,8 @@ def to_oracle(tr):
     if name == "WCS":
         w = p["wcs"]
         proj = w.projection()
-        code = None if proj is None else {1: "TAN", 2: "CAR"}[proj[0]]
+        from transform_b200.fitswcs import _PROJ_NAME
+        code = None if proj is None else _PROJ_NAME[proj[0]]
         return o.WCS(w.crpix, w.linear_matrix(), w.crval, code, w.lonpole, w.latpole)
     raise NotImplementedError(name)
 

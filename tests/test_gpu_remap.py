@@ -102,3 +102,25 @@ def test_config4_tan_to_car_batch(tfm, oracle):
         assert_close_rel(batch[k], want, 1e-10, "frame %d" % k)
     assert_close_rel(out0.data, batch[0], 1e-15, "remap == composed chain")
     assert np.count_nonzero(batch[0]) > 0.8 * n * n                           # >= 80 % overlap
+
+
+@pytest.mark.parametrize("src_proj,dst_proj", [("ARC", "CEA"), ("STG", "AIT"), ("SIN", "ZEA"), ("MER", "SFL")])
+def test_remap_between_added_projections(tfm, oracle, src_proj, dst_proj):
+    """the other projections of paper II through the same remap path
+    (parity and fp32 mode; the fused TAN/CAR pair op must not be applied to these)."""
+    n = 80
+    a = {'NAXIS': 2, 'NAXIS1': n, 'NAXIS2': n, 'CTYPE1': 'HPLN-' + src_proj, 'CTYPE2': 'HPLT-' + src_proj,
+         'CUNIT1': 'deg', 'CUNIT2': 'deg', 'CRPIX1': n / 2 + 0.5, 'CRPIX2': n / 2 + 0.5, 'CRVAL1': 20.0,
+         'CRVAL2': 10.0, 'CDELT1': 0.05, 'CDELT2': 0.05}
+    b = dict(a, CTYPE1='HPLN-' + dst_proj, CTYPE2='HPLT-' + dst_proj)
+    frame = np.random.default_rng(13).random((n, n)).astype(np.float32)
+    out = tfm.Identity().remap((frame, a), template=b, method='linear')
+    assert out.header['CTYPE1'] == 'HPLN-' + dst_proj
+    total = tfm.Composition([tfm.WCS(b).inverse(), tfm.WCS(a)])
+    want = oracle.resample(to_oracle(total), frame, method='linear', shape=(n, n))
+    assert_close_rel(out.data, want, 1e-9, "parity")
+    fast = total.resample(frame, method='linear', shape=(n, n), precision='fp32')
+    assert_close_rel(fast, want, 2e-5, "fp32")
+    assert np.count_nonzero(out.data) > 0.7 * n * n
+    with pytest.raises(NotImplementedError):
+        tfm.WCS(dict(a, PV2_1=0.5))                               # non-default projection parameter

@@ -219,3 +219,32 @@ def test_pincushion_kats(oracle):
     a = oracle.Poly(length=3.0, strength=2.0)
     assert np.allclose(oracle.apply(a, x), [[0., 0.55555556, 1.55555556], [3., 4.88888889, 7.22222222],
                                             [10., 13.22222222, 16.88888889]], atol=1e-2)
+
+
+def test_projection_closed_forms(oracle):
+    """Calabretta & Greisen 2002: radii / ordinates of the added projections at angles where the
+    formulas have closed-form values, and project(deproject()) round trips."""
+    r0 = 180.0 / np.pi
+    z = np.zeros(1)
+    for proj, R in (("STG", 2 * r0), ("SIN", r0), ("ARC", 90.0), ("ZEA", r0 * np.sqrt(2.0))):
+        x, y = oracle._project(proj, z + 90.0, z)              # phi = 90, theta = 0: on the +x axis
+        assert np.allclose([x[0], y[0]], [R, 0.0], atol=1e-12), proj
+        x, y = oracle._project(proj, z, z + 90.0)              # the native pole maps to the origin
+        assert np.allclose([x[0], y[0]], [0.0, 0.0], atol=1e-12), proj
+    x, y = oracle._project("TAN", z + 180.0, z + 45.0)         # R = r0 cot(45) = r0, phi = 180: +y
+    assert np.allclose([x[0], y[0]], [0.0, r0], atol=1e-12)
+    assert np.allclose(oracle._project("CEA", z + 30.0, z + 90.0), [[30.0], [r0]])
+    assert np.allclose(oracle._project("MER", z + 30.0, z + 45.0)[1], r0 * np.log(np.tan(np.radians(67.5))))
+    assert np.allclose(oracle._project("SFL", z + 60.0, z + 60.0), [[30.0], [60.0]])
+    x, y = oracle._project("AIT", z + 180.0, z)                # end of the equator: x = 2 sqrt(2) r0
+    assert np.allclose([x[0], y[0]], [2 * np.sqrt(2.0) * r0, 0.0])
+    x, y = oracle._project("AIT", z, z + 90.0)                 # pole: y = sqrt(2) r0
+    assert np.allclose([x[0], y[0]], [0.0, np.sqrt(2.0) * r0])
+    rng = np.random.default_rng(8)
+    phi = rng.random(500) * 340 - 170
+    theta = rng.random(500) * 160 - 80
+    for proj in ("TAN", "STG", "SIN", "ARC", "ZEA", "CAR", "CEA", "MER", "SFL", "AIT"):
+        th = np.abs(theta) + 5 if proj in ("TAN", "SIN") else theta       # visible hemisphere only
+        x, y = oracle._project(proj, phi, th)
+        p2, t2 = oracle._deproject(proj, x, y)
+        assert np.allclose(p2, phi, atol=1e-9) and np.allclose(t2, th, atol=1e-9), proj

@@ -24,6 +24,8 @@ FWD, REV = 0, 1
 LIN_HAS_PRE, LIN_HAS_POST, LIN_HAS_MATRIX, LIN_MAT_FORDER = 1, 2, 4, 8
 RAD_CCW, RAD_POS_ONLY, RAD_R0_NOT_NONE, RAD_R0_TRUTHY, RAD_ORIGIN_NONZERO = 1, 2, 4, 8, 16
 WCS_PROJ_NONE, WCS_PROJ_TAN, WCS_PROJ_CAR = 0, 1, 2
+(WCS_PROJ_STG, WCS_PROJ_SIN, WCS_PROJ_ARC, WCS_PROJ_ZEA, WCS_PROJ_CEA, WCS_PROJ_MER, WCS_PROJ_SFL,
+ WCS_PROJ_AIT) = range(3, 11)
 F32, F64 = 0, 1
 NEAREST, LINEAR, CUBIC = 0, 1, 2
 SINC, LANCZOS, GAUSSIAN, HANN, TUKEY, TENT = 3, 4, 5, 6, 7, 8

@@ -185,6 +185,102 @@ __device__ __forceinline__ void op_pin(const tfm_op &op, double &x, double &y)
 //   TAN (gnomonic): intermediate (x, y) = R2D (m_y, -m_x) / m_z  <=>  m ~ (-y, x, R2D)   [eq. 54-55]
 //   CAR           : (x, y) = (p, t) in degrees                                          [eq. 83-84]
 // so TAN needs no trigonometry at all and CAR needs one sincos pair or one atan2 pair.
+// intermediate world coordinates (degrees) -> native direction m (any positive scale); NaN when the
+// point is outside the projection's image of the sphere
+__device__ __forceinline__ void wcs_deproject(int proj, double ix, double iy, double &mx, double &my, double &mz)
+{
+    const double R0 = TFM_R2D;
+    switch (proj) {
+    case TFM_WCS_PROJ_TAN: mx = -iy; my = ix; mz = R0; return;
+    case TFM_WCS_PROJ_STG: {                    // R = 2 r0 tan((90-theta)/2)
+        const double t2 = (ix * ix + iy * iy) / (4.0 * R0 * R0);
+        mx = -iy / R0; my = ix / R0; mz = 1.0 - t2;          // scaled by (1 + t^2)
+        return;
+    }
+    case TFM_WCS_PROJ_SIN: {                    // R = r0 cos(theta)
+        const double u = ix / R0, v = iy / R0, r2 = u * u + v * v;
+        mx = -v; my = u; mz = (r2 <= 1.0) ? sqrt(1.0 - r2) : nan("");
+        return;
+    }
+    case TFM_WCS_PROJ_ARC: {                    // R = 90 - theta
+        const double R = sqrt(ix * ix + iy * iy), g = R * TFM_D2R;
+        double sg, cg;
+        sincos(g, &sg, &cg);
+        const double k = (R > 0.0) ? sg / R : TFM_D2R;
+        mx = -iy * k; my = ix * k; mz = (R <= 180.0) ? cg : nan("");
+        return;
+    }
+    case TFM_WCS_PROJ_ZEA: {                    // R = 2 r0 sin((90-theta)/2)
+        const double r2 = (ix * ix + iy * iy) / (R0 * R0);
+        mz = (r2 <= 4.0) ? 1.0 - 0.5 * r2 : nan("");
+        const double q = sqrt(fmax(0.5 * (1.0 + mz), 0.0)) / R0;
+        mx = -iy * q; my = ix * q;
+        return;
+    }
+    default: break;
+    }
+    // cylindrical and pseudo-cylindrical: native (phi, theta) first
+    double phi = ix * TFM_D2R, st, ct;
+    switch (proj) {
+    case TFM_WCS_PROJ_CEA: st = iy / R0; ct = (fabs(st) <= 1.0) ? sqrt(1.0 - st * st) : nan(""); break;
+    case TFM_WCS_PROJ_MER: { const double u = iy / R0; st = tanh(u); ct = 1.0 / cosh(u); break; }
+    case TFM_WCS_PROJ_SFL:
+        sincos(iy * TFM_D2R, &st, &ct);
+        phi = (ct > 0.0) ? phi / ct : ((ix == 0.0) ? 0.0 : nan(""));
+        if (!(fabs(iy) <= 90.0) || !(fabs(phi) <= 3.141592653589793 * (1.0 + 1e-12))) phi = nan("");
+        break;
+    case TFM_WCS_PROJ_AIT: {
+        const double u = ix / (4.0 * R0), v = iy / (2.0 * R0), z2 = 1.0 - u * u - v * v;
+        if (!(z2 >= 0.5 * (1.0 - 1e-12))) { phi = nan(""); st = nan(""); ct = nan(""); break; }
+        const double Z = sqrt(z2);
+        phi = 2.0 * atan2(2.0 * u * Z, 2.0 * z2 - 1.0);
+        st = 2.0 * v * Z;                       // (y / r0) Z
+        ct = sqrt(fmax(1.0 - st * st, 0.0));
+        break;
+    }
+    default: sincos(iy * TFM_D2R, &st, &ct); break;              // CAR
+    }
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    mx = ct * cp; my = ct * sp; mz = st;
+}
+
+// native UNIT vector m -> intermediate world coordinates (degrees); NaN where the projection diverges
+// or the point is on the hidden side
+__device__ __forceinline__ void wcs_project(int proj, double mx, double my, double mz, double &ix, double &iy)
+{
+    const double R0 = TFM_R2D;
+    double k;
+    switch (proj) {
+    case TFM_WCS_PROJ_TAN: k = (mz > 0.0) ? R0 / mz : nan(""); ix = my * k; iy = -mx * k; return;
+    case TFM_WCS_PROJ_STG: k = (mz > -1.0) ? 2.0 * R0 / (1.0 + mz) : nan(""); ix = my * k; iy = -mx * k; return;
+    case TFM_WCS_PROJ_SIN: k = (mz >= 0.0) ? R0 : nan(""); ix = my * k; iy = -mx * k; return;
+    case TFM_WCS_PROJ_ARC: {
+        const double rho = sqrt(mx * mx + my * my);
+        k = (rho > 0.0) ? R0 * atan2(rho, mz) / rho : R0;
+        ix = my * k; iy = -mx * k;
+        return;
+    }
+    case TFM_WCS_PROJ_ZEA: k = (mz > -1.0) ? R0 * sqrt(2.0 / (1.0 + mz)) : nan(""); ix = my * k; iy = -mx * k; return;
+    default: break;
+    }
+    const double rho = sqrt(mx * mx + my * my);
+    const double phi = atan2(my, mx);                              // radians, (-pi, pi]
+    switch (proj) {
+    case TFM_WCS_PROJ_CEA: ix = phi * R0; iy = R0 * mz; return;
+    case TFM_WCS_PROJ_MER: ix = phi * R0; iy = (fabs(mz) < 1.0) ? R0 * atanh(mz) : nan(""); return;
+    case TFM_WCS_PROJ_SFL: ix = phi * R0 * rho; iy = atan2(mz, rho) * R0; return;
+    case TFM_WCS_PROJ_AIT: {
+        double sh, ch;
+        sincos(0.5 * phi, &sh, &ch);
+        const double g = sqrt(2.0 / (1.0 + rho * ch));
+        ix = 2.0 * R0 * g * rho * sh; iy = R0 * g * mz;
+        return;
+    }
+    default: ix = phi * R0; iy = atan2(mz, rho) * R0; return;      // CAR
+    }
+}
+
 template <class A>
 __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
 {
@@ -201,14 +297,7 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             return;
         }
         double mx, my, mz;
-        if (proj == TFM_WCS_PROJ_TAN) {
-            mx = -iy; my = ix; mz = TFM_R2D;               // un-normalised: only angles are taken below
-        } else {
-            double sp, cp, st, ct;
-            sincos(ix * TFM_D2R, &sp, &cp);
-            sincos(iy * TFM_D2R, &st, &ct);
-            mx = ct * cp; my = ct * sp; mz = st;
-        }
+        wcs_deproject(proj, ix, iy, mx, my, mz);           // un-normalised: only angles are taken below
         const double lx = R[0] * mx + R[1] * my + R[2] * mz;
         const double ly = R[3] * mx + R[4] * my + R[5] * mz;
         const double lz = R[6] * mx + R[7] * my + R[8] * mz;
@@ -230,19 +319,7 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             const double mx = R[0] * lx + R[3] * ly + R[6] * lz;       // R^T l
             const double my = R[1] * lx + R[4] * ly + R[7] * lz;
             const double mz = R[2] * lx + R[5] * ly + R[8] * lz;
-            if (proj == TFM_WCS_PROJ_TAN) {
-                if (mz > 0.0) {
-                    const double s = TFM_R2D / mz;
-                    ix = my * s;
-                    iy = -mx * s;
-                } else {                                   // theta <= 0: the far side of the sky
-                    ix = nan("");
-                    iy = nan("");
-                }
-            } else {
-                ix = atan2(my, mx) * TFM_R2D;
-                iy = atan2(mz, sqrt(mx * mx + my * my)) * TFM_R2D;
-            }
+            wcs_project(proj, mx, my, mz, ix, iy);         // NaN on the far side of the sky (TAN, SIN)
         }
         double px = A::add(A::mul(op.p[6], ix), A::mul(op.p[7], iy));
         double py = A::add(A::mul(op.p[8], ix), A::mul(op.p[9], iy));
@@ -434,9 +511,9 @@ static inline int fuse_chain_fast(const tfm_op *ops, int n, tfm_op *out)
     }
     for (; i < n; ++i) {
         const tfm_op &a = ops[i];
-        if (i + 1 < n && a.kind == TFM_OP_WCS && a.dir == TFM_FWD && (a.flags & 0xff) != TFM_WCS_PROJ_NONE &&
-            ops[i + 1].kind == TFM_OP_WCS && ops[i + 1].dir == TFM_REV &&
-            (ops[i + 1].flags & 0xff) != TFM_WCS_PROJ_NONE) {
+        const auto pairable = [](int f) { return (f & 0xff) == TFM_WCS_PROJ_TAN || (f & 0xff) == TFM_WCS_PROJ_CAR; };
+        if (i + 1 < n && a.kind == TFM_OP_WCS && a.dir == TFM_FWD && pairable(a.flags) &&
+            ops[i + 1].kind == TFM_OP_WCS && ops[i + 1].dir == TFM_REV && pairable(ops[i + 1].flags)) {
             const tfm_op &b = ops[i + 1];
             tfm_op f;
             f.kind = TFM_OP_WCS_PAIR; f.dir = TFM_FWD; f.reserved = 0;
@@ -468,6 +545,7 @@ static inline bool chain_ops_valid(const tfm_op *ops, int n)
         const tfm_op &op = ops[i];
         if (op.kind < TFM_OP_IDENTITY || op.kind > TFM_OP_PIN) return false;
         if (op.dir != TFM_FWD && op.dir != TFM_REV) return false;
+        if (op.kind == TFM_OP_WCS && ((op.flags & 0xff) < 0 || (op.flags & 0xff) > TFM_WCS_PROJ_MAX)) return false;
         if (op.kind == TFM_OP_PIN) {
             const int k = op.flags & 3;
             if (k > TFM_PIN_POLY) return false;

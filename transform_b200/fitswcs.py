@@ -246,7 +246,14 @@ def read_fits(path, device=False):
 # ------------------------------------------------------------------------------------------
 _LNG_PREFIX = ("RA--", "GLON", "ELON", "SLON", "HLON", "HPLN", "HGLN", "CRLN", "SOLX")
 _LAT_PREFIX = ("DEC-", "GLAT", "ELAT", "SLAT", "HLAT", "HPLT", "HGLT", "CRLT", "SOLY")
-_PROJ = {"TAN": (L.WCS_PROJ_TAN, 0.0, 90.0), "CAR": (L.WCS_PROJ_CAR, 0.0, 0.0)}   # code, phi0, theta0
+# code, phi0, theta0 (paper II table 13: zenithal projections have their reference point at the
+# native pole, the cylindrical / pseudo-cylindrical / Hammer-Aitoff ones at (0, 0))
+_PROJ = {"TAN": (L.WCS_PROJ_TAN, 0.0, 90.0), "CAR": (L.WCS_PROJ_CAR, 0.0, 0.0),
+         "STG": (L.WCS_PROJ_STG, 0.0, 90.0), "SIN": (L.WCS_PROJ_SIN, 0.0, 90.0),
+         "ARC": (L.WCS_PROJ_ARC, 0.0, 90.0), "ZEA": (L.WCS_PROJ_ZEA, 0.0, 90.0),
+         "CEA": (L.WCS_PROJ_CEA, 0.0, 0.0), "MER": (L.WCS_PROJ_MER, 0.0, 0.0),
+         "SFL": (L.WCS_PROJ_SFL, 0.0, 0.0), "AIT": (L.WCS_PROJ_AIT, 0.0, 0.0)}
+_PROJ_NAME = {v[0]: k for k, v in _PROJ.items()}
 
 
 def _sph_to_vec(lon_deg, lat_deg):
@@ -310,6 +317,13 @@ class WCSParams:
             self.cdelt[i] = float(get('CDELT%d' % a, 1.0))
             self.ctype[i] = str(get('CTYPE%d' % a, '')).strip()
             self.cunit[i] = str(get('CUNIT%d' % a, '')).strip()
+        # projection parameters: only the defaults are on the GPU path (PV2_1 = 1 is CEA's default lambda)
+        for k in h.keys():
+            if isinstance(k, str) and k.startswith('PV') and '_' in k and k[2:].replace('_', '').isdigit():
+                val = float(h[k])
+                if val != 0.0 and not (k == 'PV2_1' and val == 1.0):
+                    raise NotImplementedError("transform_b200: projection parameter %s = %r "
+                                              "(only default PVi_m values are on the GPU path)" % (k, h[k]))
         has_cd = any(('CD%d_%d' % (i + 1, j + 1)) in h for i in range(naxis) for j in range(naxis))
         has_pc = any(('PC%d_%d' % (i + 1, j + 1)) in h for i in range(naxis) for j in range(naxis))
         if has_cd:
@@ -364,7 +378,7 @@ class WCSParams:
             raise ValueError("WCS: CTYPE1/CTYPE2 name different projections (%s, %s)" % (c0, c1))
         if j0 not in _PROJ:
             raise NotImplementedError("transform_b200: WCS projection '%s' is not on the GPU path "
-                                      "(TAN and CAR are)" % j0)
+                                      "(%s are)" % (j0, ", ".join(sorted(_PROJ))))
         is_lng0 = p0 in _LNG_PREFIX or p0.endswith("LN") or p0.endswith("LON")
         is_lat1 = p1 in _LAT_PREFIX or p1.endswith("LT") or p1.endswith("LAT")
         if not (is_lng0 and is_lat1):
