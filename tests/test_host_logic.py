@@ -193,8 +193,14 @@ def test_header_and_wcs_parameters():
     # the native reference point (phi0, theta0) = (0, 0) maps to CRVAL
     v = R @ np.array([1.0, 0.0, 0.0])
     assert np.degrees(np.arctan2(v[1], v[0])) == pytest.approx(150.0) and np.degrees(np.arcsin(v[2])) == pytest.approx(2.2)
+    sin = t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---SIN', 'CTYPE2': 'DEC--SIN', 'CRVAL1': 10.0, 'CRVAL2': -30.0}))
+    assert sin.projection()[0] == L.WCS_PROJ_SIN and sin.celestial_pole() == (10.0, -30.0, 180.0)   # zenithal
+    cea = t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'CRLN-CEA', 'CTYPE2': 'CRLT-CEA', 'PV2_1': 1.0}))
+    assert cea.projection()[0] == L.WCS_PROJ_CEA and cea.projection()[3:] == (0.0, 0.0)
     with pytest.raises(NotImplementedError):
-        t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---SIN', 'CTYPE2': 'DEC--SIN'})).projection()
+        t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---ZPN', 'CTYPE2': 'DEC--ZPN'})).projection()
+    with pytest.raises(NotImplementedError):
+        t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---SIN', 'CTYPE2': 'DEC--SIN', 'PV2_1': 0.1}))
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/sample.fits"), reason="reference fixture not on this box")
