@@ -25,7 +25,7 @@ struct ApplyParams {
     ChainDev chain;
 };
 
-template <class A, int UNROLL, bool SPH>
+template <class A, int UNROLL, int SPH>
 __global__ void __launch_bounds__(256)
 k_apply_f64x2(const __grid_constant__ ApplyParams P)
 {
@@ -52,7 +52,7 @@ k_apply_f64x2(const __grid_constant__ ApplyParams P)
 }
 
 // two fp32 vectors per 16-byte packet
-template <class A, int UNROLL, bool SPH>
+template <class A, int UNROLL, int SPH>
 __global__ void __launch_bounds__(256)
 k_apply_f32x2(const __grid_constant__ ApplyParams P)
 {
@@ -94,7 +94,7 @@ k_apply_f32x2(const __grid_constant__ ApplyParams P)
 }
 
 // general vec_len (>= 2): one thread per vector, extras copied through
-template <class A, typename T, bool SPH>
+template <class A, typename T, int SPH>
 __global__ void __launch_bounds__(256)
 k_apply_generic(const __grid_constant__ ApplyParams P)
 {
@@ -154,27 +154,31 @@ int apply_dispatch(const tfm_apply_args *a, cudaStream_t st)
         int grid = resident_grid((const void *)KERNEL, (ITEMS));                        \
         KERNEL<<<grid, 256, 0, st>>>(P);                                                \
     } while (0)
-    const bool sph = chain_has_sph(P.chain);
-#define TFM_L2(KERNEL_E_T, KERNEL_E_F, KERNEL_F_T, KERNEL_F_F, ITEMS)            \
-    do {                                                                         \
-        if (exact) { if (sph) TFM_LAUNCH(KERNEL_E_T, ITEMS); else TFM_LAUNCH(KERNEL_E_F, ITEMS); } \
-        else { if (sph) TFM_LAUNCH(KERNEL_F_T, ITEMS); else TFM_LAUNCH(KERNEL_F_F, ITEMS); }       \
+    const int sph = chain_sph_level(P.chain);
+    // K<A, ..., SPH>: one instantiation per arithmetic policy and "heavy op" level (tfm_chain.cuh)
+#define TFM_L2(K, PRE, ITEMS)                                                                       \
+    do {                                                                                             \
+        if (exact) {                                                                                 \
+            if (sph == 2) TFM_LAUNCH((K<Exact, PRE, 2>), ITEMS);                                     \
+            else if (sph == 1) TFM_LAUNCH((K<Exact, PRE, 1>), ITEMS);                                \
+            else TFM_LAUNCH((K<Exact, PRE, 0>), ITEMS);                                              \
+        } else {                                                                                     \
+            if (sph == 2) TFM_LAUNCH((K<Fast, PRE, 2>), ITEMS);                                      \
+            else if (sph == 1) TFM_LAUNCH((K<Fast, PRE, 1>), ITEMS);                                 \
+            else TFM_LAUNCH((K<Fast, PRE, 0>), ITEMS);                                               \
+        }                                                                                            \
     } while (0)
     if (a->vec_len == 2 && aligned && a->dtype == TFM_F64) {
-        TFM_L2((k_apply_f64x2<Exact, 4, true>), (k_apply_f64x2<Exact, 4, false>),
-               (k_apply_f64x2<Fast, 4, true>), (k_apply_f64x2<Fast, 4, false>), a->n_vec);
+        TFM_L2(k_apply_f64x2, 4, a->n_vec);
         name = "k_apply_f64x2";
     } else if (a->vec_len == 2 && aligned && a->dtype == TFM_F32) {
-        TFM_L2((k_apply_f32x2<Exact, 4, true>), (k_apply_f32x2<Exact, 4, false>),
-               (k_apply_f32x2<Fast, 4, true>), (k_apply_f32x2<Fast, 4, false>), a->n_vec / 2 + 1);
+        TFM_L2(k_apply_f32x2, 4, a->n_vec / 2 + 1);
         name = "k_apply_f32x2";
     } else if (a->dtype == TFM_F64) {
-        TFM_L2((k_apply_generic<Exact, double, true>), (k_apply_generic<Exact, double, false>),
-               (k_apply_generic<Fast, double, true>), (k_apply_generic<Fast, double, false>), a->n_vec);
+        TFM_L2(k_apply_generic, double, a->n_vec);
         name = "k_apply_generic<f64>";
     } else {
-        TFM_L2((k_apply_generic<Exact, float, true>), (k_apply_generic<Exact, float, false>),
-               (k_apply_generic<Fast, float, true>), (k_apply_generic<Fast, float, false>), a->n_vec);
+        TFM_L2(k_apply_generic, float, a->n_vec);
         name = "k_apply_generic<f32>";
     }
 #undef TFM_L2

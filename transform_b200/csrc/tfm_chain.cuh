@@ -187,7 +187,37 @@ __device__ __forceinline__ void op_pin(const tfm_op &op, double &x, double &y)
 // so TAN needs no trigonometry at all and CAR needs one sincos pair or one atan2 pair.
 // intermediate world coordinates (degrees) -> native direction m (any positive scale); NaN when the
 // point is outside the projection's image of the sphere
+// LVL 1 kernels know TAN and CAR only (the projections of the benchmark configurations); the full
+// table is compiled into the LVL 2 instantiations -- inlined everywhere it cost the spherical kernel
+// variants 16 registers and the TAN -> CAR batch 11 %; out of line it cost stack traffic instead.
+__device__ __forceinline__ void wcs_deproject_all(int proj, double ix, double iy, double &mx, double &my, double &mz);
+__device__ __forceinline__ void wcs_project_all(int proj, double mx, double my, double mz, double &ix, double &iy);
+
+template <int LVL>
 __device__ __forceinline__ void wcs_deproject(int proj, double ix, double iy, double &mx, double &my, double &mz)
+{
+    if (LVL >= 2) { wcs_deproject_all(proj, ix, iy, mx, my, mz); return; }
+    if (proj == TFM_WCS_PROJ_TAN) { mx = -iy; my = ix; mz = TFM_R2D; return; }
+    double sp, cp, st, ct;
+    sincos(ix * TFM_D2R, &sp, &cp);
+    sincos(iy * TFM_D2R, &st, &ct);
+    mx = ct * cp; my = ct * sp; mz = st;
+}
+
+template <int LVL>
+__device__ __forceinline__ void wcs_project(int proj, double mx, double my, double mz, double &ix, double &iy)
+{
+    if (LVL >= 2) { wcs_project_all(proj, mx, my, mz, ix, iy); return; }
+    if (proj == TFM_WCS_PROJ_TAN) {
+        const double k = (mz > 0.0) ? TFM_R2D / mz : nan("");      // theta <= 0: the far side of the sky
+        ix = my * k; iy = -mx * k;
+        return;
+    }
+    ix = atan2(my, mx) * TFM_R2D;
+    iy = atan2(mz, sqrt(mx * mx + my * my)) * TFM_R2D;
+}
+
+__device__ __forceinline__ void wcs_deproject_all(int proj, double ix, double iy, double &mx, double &my, double &mz)
 {
     const double R0 = TFM_R2D;
     switch (proj) {
@@ -247,7 +277,7 @@ __device__ __forceinline__ void wcs_deproject(int proj, double ix, double iy, do
 
 // native UNIT vector m -> intermediate world coordinates (degrees); NaN where the projection diverges
 // or the point is on the hidden side
-__device__ __forceinline__ void wcs_project(int proj, double mx, double my, double mz, double &ix, double &iy)
+__device__ __forceinline__ void wcs_project_all(int proj, double mx, double my, double mz, double &ix, double &iy)
 {
     const double R0 = TFM_R2D;
     double k;
@@ -281,7 +311,7 @@ __device__ __forceinline__ void wcs_project(int proj, double mx, double my, doub
     }
 }
 
-template <class A>
+template <class A, int LVL>
 __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
 {
     const int proj = op.flags & 0xff;
@@ -297,7 +327,7 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             return;
         }
         double mx, my, mz;
-        wcs_deproject(proj, ix, iy, mx, my, mz);           // un-normalised: only angles are taken below
+        wcs_deproject<LVL>(proj, ix, iy, mx, my, mz);      // un-normalised: only angles are taken below
         const double lx = R[0] * mx + R[1] * my + R[2] * mz;
         const double ly = R[3] * mx + R[4] * my + R[5] * mz;
         const double lz = R[6] * mx + R[7] * my + R[8] * mz;
@@ -319,7 +349,7 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             const double mx = R[0] * lx + R[3] * ly + R[6] * lz;       // R^T l
             const double my = R[1] * lx + R[4] * ly + R[7] * lz;
             const double mz = R[2] * lx + R[5] * ly + R[8] * lz;
-            wcs_project(proj, mx, my, mz, ix, iy);         // NaN on the far side of the sky (TAN, SIN)
+            wcs_project<LVL>(proj, mx, my, mz, ix, iy);    // NaN on the far side of the sky (TAN, SIN)
         }
         double px = A::add(A::mul(op.p[6], ix), A::mul(op.p[7], iy));
         double py = A::add(A::mul(op.p[8], ix), A::mul(op.p[9], iy));
@@ -367,14 +397,22 @@ __device__ __forceinline__ void op_wcs_pair(const tfm_op &op, double &x, double 
     y = (op.p[17] * ox + op.p[18] * oy + op.p[20]) - 1.0;
 }
 
-// "heavy" ops (spherical WCS, the pow()-based pincushion family) are compiled only into the SPH kernel
-// instantiations, see chain_eval below
-static inline bool chain_has_sph(const ChainDev &ch)
+// "Heavy" ops are compiled only into dedicated kernel instantiations (template parameter SPH):
+//   0  none of them        1  WCS with linear axes, TAN or CAR (+ the fused WCS pair)
+//   2  every WCS projection and the pow()-based pincushion family
+static inline int chain_sph_level(const ChainDev &ch)
 {
-    for (int i = 0; i < ch.n; ++i)
-        if (ch.ops[i].kind == TFM_OP_WCS || ch.ops[i].kind == TFM_OP_WCS_PAIR || ch.ops[i].kind == TFM_OP_PIN)
-            return true;
-    return false;
+    int lvl = 0;
+    for (int i = 0; i < ch.n; ++i) {
+        const tfm_op &op = ch.ops[i];
+        if (op.kind == TFM_OP_PIN) lvl = 2;
+        else if (op.kind == TFM_OP_WCS_PAIR) lvl = lvl < 1 ? 1 : lvl;
+        else if (op.kind == TFM_OP_WCS) {
+            const int need = ((op.flags & 0xff) > TFM_WCS_PROJ_CAR) ? 2 : 1;
+            lvl = lvl < need ? need : lvl;
+        }
+    }
+    return lvl;
 }
 
 // Internal opcode (never crosses the C ABI): [affine..., Radial reverse, affine...] at the START of a
@@ -576,7 +614,7 @@ __device__ __forceinline__ void op_index(const tfm_op &op, double &x, double &y)
 // the kernel instantiations that the host selects for such chains -- inlined into every kernel it
 // costs the others registers (measured +7% on the Jacobian kernel), out of line it spills the
 // interpreter's state to the stack (measured 2x on the parity-mode linear kernel).
-template <class A, bool SPH>
+template <class A, int SPH>
 __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double &y, int first = 0)
 {
     for (int i = first; i < ch.n; ++i) {
@@ -584,9 +622,9 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
         switch (op.kind) {
         case TFM_OP_LINEAR: op_linear<A>(op, x, y); break;
         case TFM_OP_RADIAL: op_radial<A>(op, x, y); break;
-        case TFM_OP_WCS: if constexpr (SPH) op_wcs<A>(op, x, y); break;
-        case TFM_OP_WCS_PAIR: if constexpr (SPH) op_wcs_pair(op, x, y); break;
-        case TFM_OP_PIN: if constexpr (SPH) op_pin<A>(op, x, y); break;
+        case TFM_OP_WCS: if constexpr (SPH >= 1) op_wcs<A, SPH>(op, x, y); break;
+        case TFM_OP_WCS_PAIR: if constexpr (SPH >= 1) op_wcs_pair(op, x, y); break;
+        case TFM_OP_PIN: if constexpr (SPH >= 2) op_pin<A>(op, x, y); break;
         case TFM_OP_POLAR: op_polar(op, x, y); break;
         case TFM_OP_INDEX: op_index(op, x, y); break;
         default: break;                                     // identity
@@ -596,7 +634,7 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
 
 // ---- N-wide evaluation: the interpreter's dispatch (constant loads, flag tests, branches) is paid
 // once per op per THREAD instead of once per op per pixel; the per-pixel work is the arithmetic only.
-template <class A, bool SPH, int N>
+template <class A, int SPH, int N>
 __device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N], double (&y)[N], int first = 0)
 {
     for (int i = first; i < ch.n; ++i) {
@@ -644,19 +682,19 @@ __device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N],
             for (int k = 0; k < N; ++k) op_radial<A>(op, x[k], y[k]);
             break;
         case TFM_OP_WCS:
-            if constexpr (SPH) {
+            if constexpr (SPH >= 1) {
 #pragma unroll
-                for (int k = 0; k < N; ++k) op_wcs<A>(op, x[k], y[k]);
+                for (int k = 0; k < N; ++k) op_wcs<A, SPH>(op, x[k], y[k]);
             }
             break;
         case TFM_OP_WCS_PAIR:
-            if constexpr (SPH) {
+            if constexpr (SPH >= 1) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) op_wcs_pair(op, x[k], y[k]);
             }
             break;
         case TFM_OP_PIN:
-            if constexpr (SPH) {
+            if constexpr (SPH >= 2) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) op_pin<A>(op, x[k], y[k]);
             }

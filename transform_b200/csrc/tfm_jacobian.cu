@@ -360,7 +360,7 @@ __device__ __forceinline__ void gauss_taps(const SrcT *p, long long pe, float w0
 #define TFM_K2_MINBLOCKS 4
 #endif
 // A: chain arithmetic; RegT: footprint arithmetic (double = parity mode, float = fast mode)
-template <class A, typename SrcT, typename DstT, typename RegT, int JTY, bool SPH>
+template <class A, typename SrcT, typename DstT, typename RegT, int JTY, int SPH>
 __global__ void __launch_bounds__(JTX * 8, TFM_K2_MINBLOCKS)
 k_jacobian(const __grid_constant__ JacParams P)
 {
@@ -853,7 +853,7 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
         for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
     }
 
-    const bool sph = chain_has_sph(P.chain);
+    const int sph = chain_sph_level(P.chain);
     // tile height: 32 by default (4 pixels per thread); tuning bits 8 / 32 select 16 / 8 for A/B runs
     const int jty = sph ? 8 : ((a->tuning & 32) ? 8 : ((a->tuning & 8) ? 16 : 32));
     dim3 grid((unsigned)((P.dst_w + JTX - 1) / JTX), (unsigned)((P.dst_h + jty - 1) / jty),
@@ -863,10 +863,11 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     const char *name;
 #define TFM_JLAUNCH(AA, ST, DT, RT)                                                          \
     do {                                                                                     \
-        if (sph) k_jacobian<AA, ST, DT, RT, 8, true><<<grid, block, 0, st>>>(P);              \
-        else if (jty == 8) k_jacobian<AA, ST, DT, RT, 8, false><<<grid, block, 0, st>>>(P);   \
-        else if (jty == 16) k_jacobian<AA, ST, DT, RT, 16, false><<<grid, block, 0, st>>>(P); \
-        else k_jacobian<AA, ST, DT, RT, 32, false><<<grid, block, 0, st>>>(P);                \
+        if (sph == 2) k_jacobian<AA, ST, DT, RT, 8, 2><<<grid, block, 0, st>>>(P);            \
+        else if (sph == 1) k_jacobian<AA, ST, DT, RT, 8, 1><<<grid, block, 0, st>>>(P);       \
+        else if (jty == 8) k_jacobian<AA, ST, DT, RT, 8, 0><<<grid, block, 0, st>>>(P);   \
+        else if (jty == 16) k_jacobian<AA, ST, DT, RT, 16, 0><<<grid, block, 0, st>>>(P); \
+        else k_jacobian<AA, ST, DT, RT, 32, 0><<<grid, block, 0, st>>>(P);                \
     } while (0)
     if (a->precision == TFM_PREC_EXACT64) {
         if (s.dtype == TFM_F32 && d.dtype == TFM_F64) TFM_JLAUNCH(Exact, float, double, double);

@@ -354,7 +354,7 @@ __device__ __forceinline__ void finish(const ResampleParams &P, RegT (&v)[NPX][N
 // GENERIC  false: both axes 'truncate', source is the whole image (fast path);
 //          true : per-axis runtime boundary modes and/or staged source sub-rectangle
 // AFF      the whole chain was pre-composed by the host into one affine map P.aff (fast mode only)
-template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC, bool AFF, bool SPH>
+template <int METHOD, typename SrcT, typename DstT, class A, typename RegT, bool GENERIC, bool AFF, int SPH>
 __global__ void __launch_bounds__(256)
 k_resample(const __grid_constant__ ResampleParams P)
 {
@@ -556,7 +556,7 @@ k_resample(const __grid_constant__ ResampleParams P)
 // its default fillvalue) and the fetch of the whole 2x2 footprint in ONE instruction (TLD4).  What is
 // left per pixel: 2 DFMA (coordinates), the XU-free floor/fraction, 6 fp32 ops of interpolation in
 // the same order as k_resample, one store.  No interior/outside classification at all.
-template <class A, bool AFF, bool SPH>
+template <class A, bool AFF, int SPH>
 __global__ void __launch_bounds__(256)
 k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex)
 {
@@ -974,7 +974,7 @@ __device__ __noinline__ double filt_row_exact(const ResampleParams &P, const cha
     });
 }
 
-template <typename SrcT, typename DstT, class A, typename RegT, bool SPH>
+template <typename SrcT, typename DstT, class A, typename RegT, int SPH>
 __global__ void __launch_bounds__(256)
 k_resample_filter(const __grid_constant__ ResampleParams P, const __grid_constant__ FilterParams F)
 {
@@ -1073,7 +1073,7 @@ static cudaError_t launch_filter(const ResampleParams &P, const FilterParams &F,
     dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 7) / 8), (unsigned)P.n_planes);
     if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
     const size_t smem = (size_t)256 * (size_t)F.size * sizeof(RegT);
-    const bool sph = chain_has_sph(P.chain);
+    const int sph = chain_sph_level(P.chain);
     auto go = [&](auto kern) -> cudaError_t {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1082,8 +1082,9 @@ static cudaError_t launch_filter(const ResampleParams &P, const FilterParams &F,
         kern<<<grid, 256, smem, st>>>(P, F);
         return cudaGetLastError();
     };
-    cudaError_t e = sph ? go(k_resample_filter<SrcT, DstT, A, RegT, true>)
-                        : go(k_resample_filter<SrcT, DstT, A, RegT, false>);
+    cudaError_t e = sph == 2 ? go(k_resample_filter<SrcT, DstT, A, RegT, 2>)
+                    : sph == 1 ? go(k_resample_filter<SrcT, DstT, A, RegT, 1>)
+                               : go(k_resample_filter<SrcT, DstT, A, RegT, 0>);
     count_launch();
     *name = "k_resample_filter";
     return e;
@@ -1102,25 +1103,27 @@ static cudaError_t launch2(ResampleParams &P, bool generic, bool aff, cudaStream
     if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
     P.int_w = P.src_w - NT + 1 > 0 ? P.src_w - NT + 1 : 0;
     P.int_h = P.src_h - NT + 1 > 0 ? P.src_h - NT + 1 : 0;
-    const bool sph = chain_has_sph(P.chain);
+    const int sph = chain_sph_level(P.chain);
     if (generic) {
         if (aff && !A::exact) {
             // same host-composed coordinates as the non-generic fast kernels: a staged shard must
             // reproduce the unsharded fast-mode result bit for bit
             if constexpr (!A::exact) {
-                k_resample<METHOD, SrcT, DstT, Fast, RegT, true, true, false><<<grid, 256, 0, st>>>(P);
+                k_resample<METHOD, SrcT, DstT, Fast, RegT, true, true, 0><<<grid, 256, 0, st>>>(P);
             }
-        } else if (sph) k_resample<METHOD, SrcT, DstT, A, RegT, true, false, true><<<grid, 256, 0, st>>>(P);
-        else k_resample<METHOD, SrcT, DstT, A, RegT, true, false, false><<<grid, 256, 0, st>>>(P);
+        } else if (sph == 2) k_resample<METHOD, SrcT, DstT, A, RegT, true, false, 2><<<grid, 256, 0, st>>>(P);
+        else if (sph == 1) k_resample<METHOD, SrcT, DstT, A, RegT, true, false, 1><<<grid, 256, 0, st>>>(P);
+        else k_resample<METHOD, SrcT, DstT, A, RegT, true, false, 0><<<grid, 256, 0, st>>>(P);
         *name = "k_resample<generic>";
     } else if (aff && !A::exact) {
         if constexpr (!A::exact) {
-            k_resample<METHOD, SrcT, DstT, Fast, RegT, false, true, false><<<grid, 256, 0, st>>>(P);
+            k_resample<METHOD, SrcT, DstT, Fast, RegT, false, true, 0><<<grid, 256, 0, st>>>(P);
         }
         *name = "k_resample<trunc,affine>";
     } else {
-        if (sph) k_resample<METHOD, SrcT, DstT, A, RegT, false, false, true><<<grid, 256, 0, st>>>(P);
-        else k_resample<METHOD, SrcT, DstT, A, RegT, false, false, false><<<grid, 256, 0, st>>>(P);
+        if (sph == 2) k_resample<METHOD, SrcT, DstT, A, RegT, false, false, 2><<<grid, 256, 0, st>>>(P);
+        else if (sph == 1) k_resample<METHOD, SrcT, DstT, A, RegT, false, false, 1><<<grid, 256, 0, st>>>(P);
+        else k_resample<METHOD, SrcT, DstT, A, RegT, false, false, 0><<<grid, 256, 0, st>>>(P);
         *name = "k_resample<trunc>";
     }
     count_launch();
@@ -1305,9 +1308,11 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         } else if (tex_ok) {
             dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 31) / 32), 1);
             if (grid.y > 65535u) return TFM_EUNSUPPORTED;
-            if (aff) k_resample_tex<Fast, true, false><<<grid, 256, 0, st>>>(P, tex);
-            else if (chain_has_sph(P.chain)) k_resample_tex<Fast, false, true><<<grid, 256, 0, st>>>(P, tex);
-            else k_resample_tex<Fast, false, false><<<grid, 256, 0, st>>>(P, tex);
+            const int sph = chain_sph_level(P.chain);
+            if (aff) k_resample_tex<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
+            else if (sph == 2) k_resample_tex<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
+            else if (sph == 1) k_resample_tex<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
+            else k_resample_tex<Fast, false, 0><<<grid, 256, 0, st>>>(P, tex);
             count_launch();
             name = aff ? "k_resample_tex<affine>" : "k_resample_tex";
             e = cudaGetLastError();
