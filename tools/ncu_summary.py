@@ -53,12 +53,15 @@ def main():
     total = sum(sum(v) for v in agg.values())
     with open(prefix + "_launches.md", "w") as f:
         f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none)\n\n")
-        f.write("Command: `python bench.py --steps 3 --warmup 3 --no-cpu` (first 120 launches).  Per-launch "
+        f.write("Command: `python bench.py --steps 3 --warmup 3 --no-cpu` (first 160 launches).  Per-launch "
                 "times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
         f.write("| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write("| `%s` | %d | %.1f | %.1f | %.1f%% |\n" % (k[:110], len(v), sum(v), sum(v) / len(v), 100 * sum(v) / total))
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):      # `ncu -i X.ncu-rep --page raw --csv` already run on the GPU box (big reports do not travel)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     h, units = rr[0], rr[1]
     traffic = {}
