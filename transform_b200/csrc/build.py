@@ -16,8 +16,9 @@ PKG = os.path.dirname(HERE)
 OUT_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(HERE, "_obj")
 OUT = os.path.join(OUT_DIR, "libtfm_b200.so")
-SOURCES = ["tfm_capi.cu", "tfm_resample.cu", "tfm_apply.cu", "tfm_jacobian.cu", "tfm_fits.cu"]
-HEADERS = ["tfm_chain.cuh", "tfm_common.cuh", os.path.join("..", "..", "include", "tfm_b200.h")]
+SOURCES = ["tfm_capi.cu", "tfm_resample.cu", "tfm_resample_exact_f32.cu", "tfm_resample_exact_f64.cu",
+           "tfm_resample_fast.cu", "tfm_apply.cu", "tfm_jacobian.cu", "tfm_fits.cu"]
+HEADERS = ["tfm_chain.cuh", "tfm_common.cuh", "tfm_resample.cuh", os.path.join("..", "..", "include", "tfm_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -44,7 +45,7 @@ def build_variant(name, defines):
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stdout))
         return obj
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(one, SOURCES))
     cmd = [NVCC, "-shared", "-o", out] + objs + ["-Xlinker", "--exclude-libs,ALL", "-lcudart_static",
                                                   "-lpthread", "-ldl", "-lrt"]
@@ -76,7 +77,7 @@ def build(force=False, verbose=False):
             print(r.stdout)
         return obj
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, srcs))
     tmp = OUT + ".tmp%d" % os.getpid()
     cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-Xlinker", "--exclude-libs,ALL", "-lcudart_static",
