@@ -191,3 +191,41 @@ def test_flux_photometry(tfm, oracle):
         tr.resample(src, method='G', phot='bogus')
     # the plain interpolators ignore phot, like the reference (core.py:531-533)
     assert np.array_equal(tr.resample(src, method='l', phot='flux'), tr.resample(src, method='l'))
+
+
+def test_analytic_polar_path(tfm, oracle):
+    """Fast mode, a chain that fuses into one polar op, small angular step: coordinates and Jacobian in
+    closed form (no cell differences).  Against the oracle, and against the difference path of the
+    same kernel (tuning bit 512)."""
+    n = 768                                                   # angular step^2 = 6.7e-5 < the 1e-4 gate
+    cap = 2 * int(np.ceil(0.25 * n))                          # the engine's sv_limit footprint cap
+    src = np.random.default_rng(21).random((n, n)).astype(np.float32)
+    # origin off the pixel lattice: with (n-1)/2 the 45-degree rays land on exact integer source
+    # coordinates, where the last bit of the coordinate decides floor() and with it the (abruptly
+    # truncated) footprint window -- the two code paths then legitimately differ on those pixels
+    c = (n - 1) / 2.0 + 0.123
+    chains = (
+        tfm.Composition([tfm.Scale([n / (2 * np.pi), np.sqrt(2.0)]), tfm.Radial(origin=[c, c - 0.34])]),
+        # with a trailing affine map (A2 of the fused op) and counter-clockwise angles
+        tfm.Composition([tfm.Scale([n / (2 * np.pi), 1.3]), tfm.Radial(origin=[c, c - 0.34], ccw=True),
+                         tfm.Scale([0.9, 1.1]), tfm.Offset([5.0, -3.0])]))
+    for tr in chains:
+        got = tr.resample(src, method='G', precision='fp32')
+        fd = tr.resample(src, method='G', precision='fp32', tuning=512)
+        want = oracle.resample_jacobian(to_oracle(tr), src, method='g', max_reg=cap)
+        # rows where the polar Jacobian is (nearly) isotropic are excluded from the comparison with
+        # the oracle: the reference's closed-form SVD is noise-driven there (DESIGN.md, "Degenerate SVD")
+        err = np.abs(got - want).max(axis=1)
+        assert (err > 3e-4).sum() <= 6 and np.median(err) < 2e-5, (np.nonzero(err > 3e-4)[0], np.median(err))
+        # the footprint size is a ceil() of a function of J: a few isolated pixels sit within the
+        # 1e-5 relative difference between the analytic and the central-difference Jacobian of an
+        # integer boundary and take the next window size
+        diff = np.abs(got - fd)
+        assert (diff > 2e-5).sum() <= 16 and np.median(diff) < 1e-6, ((diff > 2e-5).sum(), np.median(diff))
+        assert not np.array_equal(got, fd)                       # the two paths really are different code
+    # log-polar
+    tr = tfm.Composition([tfm.Scale([n / (2 * np.pi), n / 6.0]), tfm.Radial(origin=[c, c - 0.34], r0=1.0)])
+    got = tr.resample(src, method='G', precision='fp32')
+    fd = tr.resample(src, method='G', precision='fp32', tuning=512)
+    assert_close_rel(got, fd, 2e-5, "log-polar analytic vs difference path")
+    assert not np.array_equal(got, fd)

@@ -391,6 +391,52 @@ k_jacobian(const __grid_constant__ JacParams P)
     __shared__ double2 s_ta[PW], s_tb[PH];            // polar chains: per-tile angle tables
     __shared__ double s_ea[PW], s_eb[PH];             //               and radius (log-polar) tables
     const bool polar = FASTI && P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_POLAR;
+    // Analytic path (fast mode, the chain is ONE fused polar op): coordinates AND Jacobian of a pixel
+    // follow in closed form from the per-tile angle / radius tables -- no halo tile, no cell
+    // differences, no flag pass, one barrier.  The reference's Jacobian is a +-1-pixel central
+    // difference; against the derivative it is off by O(step^2) of the angle (and log-radius) step,
+    // so the path is taken only when those steps are < 1e-2 (relative error < 1e-4 / 6), and only when
+    // the closed form of |J|^2 = g2 + r^2 t2 (x r^2 for log-polar) proves that no cell of the tile can
+    // be flagged as a jump: max / min over the tile (corners; r = 0 inside counts as min) times the
+    // squared condition number of the trailing affine map stays below the threshold.
+    bool analytic = false;
+    if (polar && P.chain.n == 1 && !(P.flags & 0x100)) {          // 0x100: tuning bit 512, force the difference path
+        const tfm_op &op0 = P.chain.ops[0];
+        const double coeff = op0.p[6];
+        const double t2 = (op0.p[0] * op0.p[0] + op0.p[1] * op0.p[1]) * coeff * coeff;
+        const double g2 = op0.p[2] * op0.p[2] + op0.p[3] * op0.p[3];
+        const bool lg = (op0.flags & TFM_RAD_R0_NOT_NONE) != 0;
+        analytic = (t2 < 1.0e-4) && (!lg || g2 < 1.0e-4);
+        if (analytic && P.jump_thresh != 0.0) {
+            const double xa = (double)(GX0 - 2), xb = (double)(GX0 + JTX + 1);
+            const double ya = (double)(GY0 - 2), yb = (double)(GY0 + JTY + 1);
+            const double v0 = fma(op0.p[2], xa, fma(op0.p[3], ya, op0.p[5])), v1 = fma(op0.p[2], xb, fma(op0.p[3], ya, op0.p[5]));
+            const double v2 = fma(op0.p[2], xa, fma(op0.p[3], yb, op0.p[5])), v3 = fma(op0.p[2], xb, fma(op0.p[3], yb, op0.p[5]));
+            const double vmin = fmin(fmin(v0, v1), fmin(v2, v3)), vmax = fmax(fmax(v0, v1), fmax(v2, v3));
+            double ratio;
+            if (lg) {
+                ratio = exp(2.0 * (vmax - vmin));
+            } else {
+                const double hi = fmax(vmin * vmin, vmax * vmax);
+                const double lo = (vmin <= 0.0 && vmax >= 0.0) ? 0.0 : fmin(vmin * vmin, vmax * vmax);
+                ratio = (g2 + t2 * hi) / (g2 + t2 * lo);
+            }
+            if (op0.flags & TFM_POLAR_HAS_A2) {
+                const double E = op0.p[10] * op0.p[10] + op0.p[11] * op0.p[11] + op0.p[12] * op0.p[12] + op0.p[13] * op0.p[13];
+                const double det = op0.p[10] * op0.p[13] - op0.p[11] * op0.p[12];
+                const double q = sqrt(fmax(E * E - 4.0 * det * det, 0.0));
+                ratio *= (E + q) / (E - q);
+            }
+            analytic = (P.jump_thresh > 0.0) && (ratio * 1.01 <= P.jump_thresh);      // NaN compares false
+        }
+    }
+    bool tile_clean = true;
+    if (analytic) {
+        // tables for grid points (GX0-1 .. GX0+JTX) x (GY0-1 .. GY0+JTY): the tile plus the one-point
+        // reach of the edge-copy clamp
+        polar_tables(P.chain.ops[0], (double)(GX0 - 1), (double)(GY0 - 1), JTX + 2, JTY + 2, s_ta, s_tb, s_ea, s_eb, tid, NTH);
+        __syncthreads();
+    } else {
     if (polar) {
         // [affine, Radial reverse, affine] prefix: angle and radius are affine in the grid indices, so
         // PW + PH sincos per tile (angle addition) replace PW x PH of them
@@ -466,8 +512,8 @@ k_jacobian(const __grid_constant__ JacParams P)
     const float thr_f = (float)P.jump_thresh;
     const float tile_mn = __uint_as_float(s_mm[0]), tile_mx = __uint_as_float(s_mm[1]);
     // CTA-uniform: every cell of the tile passes (or detection is off): no flags to compute or read
-    const bool tile_clean = (P.jump_thresh == 0.0) ||
-                            (thr_f > 0.0f && tile_mx < 1.0e30f && tile_mx * 1.00001f <= thr_f * tile_mn * 0.99999f);
+    tile_clean = (P.jump_thresh == 0.0) ||
+                 (thr_f > 0.0f && tile_mx < 1.0e30f && tile_mx * 1.00001f <= thr_f * tile_mn * 0.99999f);
     if (!tile_clean)
     for (int i = tid; i < (JTX + 1) * (JTY + 1); i += NTH) {
         const int fj = i / (JTX + 1), fi = i - fj * (JTX + 1);
@@ -492,6 +538,7 @@ k_jacobian(const __grid_constant__ JacParams P)
         s_flag[cj][ci] = flag;
     }
     if (!tile_clean) __syncthreads();
+    }   // !analytic
 
     // ---- 4. per pixel: grid-centred Jacobian, SVD padding, footprint ----
     int state = 0;
@@ -509,6 +556,33 @@ k_jacobian(const __grid_constant__ JacParams P)
     const int qi = (int)(jx - WX0), qj = (int)(jy - WY0);
 
     double Ji[4] = {0.0, 0.0, 0.0, 0.0};
+    double px, py;
+    if (analytic) {
+        const tfm_op &op0 = P.chain.ops[0];
+        const double TX0 = (double)(GX0 - 1), TY0 = (double)(GY0 - 1);
+        polar_from_tables(op0, TX0, TY0, (int)threadIdx.x + 1, ly + 1, s_ta, s_tb, s_ea, s_eb, px, py);
+        // closed-form Jacobian at the (edge-clamped) grid point (jx, jy)
+        const int ti = (int)(jx - (GX0 - 1)), tj = (int)(jy - (GY0 - 1));
+        const double2 ca = s_ta[ti], cb = s_tb[tj];
+        const bool lg = (op0.flags & TFM_RAD_R0_NOT_NONE) != 0;
+        const float sgn = (op0.flags & TFM_RAD_CCW) ? 1.0f : -1.0f;
+        const float c = (float)(ca.x * cb.x - ca.y * cb.y), sn = (float)(ca.y * cb.x + ca.x * cb.y);    // cos, sin(theta)
+        const float r = lg ? (float)(s_ea[ti] * s_eb[tj])
+                           : (float)fma(op0.p[2], TX0 + (double)ti, fma(op0.p[3], TY0 + (double)tj, op0.p[5]));
+        const float cf = (float)op0.p[6];
+        const float tX = (float)op0.p[0] * cf, tY = (float)op0.p[1] * cf;
+        const float drX = lg ? r * (float)op0.p[2] : (float)op0.p[2], drY = lg ? r * (float)op0.p[3] : (float)op0.p[3];
+        // x1 = r cos + ox, y1 = sgn r sin + oy
+        float j00 = c * drX - r * sn * tX, j01 = c * drY - r * sn * tY;
+        float j10 = sgn * (sn * drX + r * c * tX), j11 = sgn * (sn * drY + r * c * tY);
+        if (op0.flags & TFM_POLAR_HAS_A2) {
+            const float a = (float)op0.p[10], b = (float)op0.p[11], cc = (float)op0.p[12], d = (float)op0.p[13];
+            const float k00 = a * j00 + b * j10, k01 = a * j01 + b * j11;
+            const float k10 = cc * j00 + d * j10, k11 = cc * j01 + d * j11;
+            j00 = k00; j01 = k01; j10 = k10; j11 = k11;
+        }
+        Ji[0] = j00; Ji[1] = j01; Ji[2] = j10; Ji[3] = j11;
+    } else {
     const bool all_ok = tile_clean ||
                         (s_flag[qj - 1][qi - 1] & s_flag[qj][qi - 1] & s_flag[qj - 1][qi] & s_flag[qj][qi]) != 0;
     if (FASTI && all_ok) {
@@ -548,7 +622,9 @@ k_jacobian(const __grid_constant__ JacParams P)
     }
 
     const double2 pme = s_p[ly + 2 + shy][threadIdx.x + 2 + shx];
-    const double px = pme.x, py = pme.y;
+    px = pme.x;
+    py = pme.y;
+    }   // !analytic
     DstT *drow = reinterpret_cast<DstT *>(dst_base + (long long)Y * P.dst_pitch);
     if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) { drow[X] = (DstT)0; continue; }
     const double fxs = floor(px), fys = floor(py);
@@ -838,7 +914,7 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     P.dst_h = (int)d.h; P.dst_w = (int)d.w; P.dst_x0 = d.x0; P.dst_y0 = d.y0;
     P.grid_h = (int)d.full_h; P.grid_w = (int)d.full_w;
     P.bound_x = a->bound_x; P.bound_y = a->bound_y; P.filter = a->filter;
-    P.flags = a->flags;
+    P.flags = (a->flags & 0xff) | ((a->tuning & 512) ? 0x100 : 0);
     P.src_f64 = s.dtype == TFM_F64; P.dst_f64 = d.dtype == TFM_F64;
     P.oblur = a->oblur; P.pad_pow = a->pad_pow; P.jump_thresh = a->jump_thresh;
     // helpers.pyx:1612-1615: padval 1 for tent/Hanning/Tukey, 3 for Lanczos/Gaussian
