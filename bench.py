@@ -262,6 +262,10 @@ def gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    # host buffers of this rank on the NUMA node of its GPU (matters for the end-to-end number at N > 1)
+    from transform_b200 import _device as tdev
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = tdev.bind_to_gpu_numa(local)
     # NCCL writes its version banner to stdout; park stdout on stderr until the JSON line is due
     sys.stdout.flush()
     saved_stdout = os.dup(1)
@@ -427,9 +431,12 @@ def gpu_arm(args):
                         "steps": k_e2e, "matches_resident_result": ok,
                         "mode": "transform_b200.AsyncResampler, 4 streams: H2D / kernel / D2H of "
                                 "consecutive calls overlap; pinned host buffers",
-                        "synchronous_calls_value": px_step / s_e2e_sync / 1e6},
+                        "synchronous_calls_value": px_step / s_e2e_sync / 1e6,
+                        "host_affinity": "NVML ideal CPU set of the rank's GPU (%d cores)" % len(numa_cpus)
+                                         if numa_cpus else "unchanged"},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "breakdown": brk}
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)          # the CPU baseline uses every host core again
             nproc = os.cpu_count() or 1
             # ~10-30 core-seconds per leg: big enough that forking the workers does not dominate
             cb = cpu_sample(nproc * 256, nproc * 64, nproc)

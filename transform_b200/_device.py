@@ -102,3 +102,25 @@ def status_word():
 def np_dtype_of(t):
     torch = torch_mod()
     return {torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64)}.get(t.dtype)
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPU cores closest to a GPU (NVML's ideal affinity mask), so that
+    pinned host buffers allocated afterwards land on that GPU's NUMA node.  With one process per GPU
+    all streaming host<->device copies otherwise funnel through whichever node the allocator picked.
+    Best effort: returns the CPU set, or None when NVML / the syscall is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
