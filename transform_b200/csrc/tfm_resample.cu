@@ -164,7 +164,14 @@ static bool get_texture(const void *ptr, int w, int h, long long pitch, cudaText
     if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return false; }
     int slot;
     if (g_tex_n < 16) slot = g_tex_n++;
-    else { slot = g_tex_next; g_tex_next = (g_tex_next + 1) & 15; cudaDestroyTextureObject(g_tex_objs[slot]); }
+    else {
+        // eviction (more than 16 live source geometries): a kernel on some stream may still be reading
+        // through the victim, so drain the device before destroying it -- a rare, slow path
+        slot = g_tex_next;
+        g_tex_next = (g_tex_next + 1) & 15;
+        cudaDeviceSynchronize();
+        cudaDestroyTextureObject(g_tex_objs[slot]);
+    }
     g_tex_keys[slot] = key;
     g_tex_objs[slot] = t;
     *out = t;
