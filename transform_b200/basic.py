@@ -12,6 +12,19 @@ from .core import Transform
 from .units import angular_coefficient
 
 
+def _fingerprint(*vals):
+    """Cheap identity-and-content token of a few small parameters: lowering is memoised per instance
+    and direction, and redone whenever a parameter was replaced OR edited in place (the reference
+    reads `params` at call time, so in-place edits must keep working)."""
+    out = []
+    for v in vals:
+        if isinstance(v, np.ndarray):
+            out.append((id(v), v.strides, v.tobytes()))
+        else:
+            out.append(v)
+    return tuple(out)
+
+
 def _vec2(v, fill):
     """1- or 2-vector -> (x, y) with the missing component neutral."""
     a = np.asarray(v, dtype=np.float64).reshape(-1)
@@ -80,10 +93,20 @@ class Linear(Transform):
             raise NotImplementedError("transform_b200: Linear transforms of dimension > 2 (or "
                                       "non-square) are outside the GPU hot path")
         p = self.params
+        m = p['matrix'] if direction == L.FWD else p['matinv']
+        fp = _fingerprint(m, p['pre'], p['post'])
+        memo = self.__dict__.setdefault('_lower_memo', {})
+        hit = memo.get(direction)
+        if hit is not None and hit[0] == fp:
+            return hit[1]
+        memo[direction] = (fp, self._lower_uncached(direction, p, m))
+        return memo[direction][1]
+
+    @staticmethod
+    def _lower_uncached(direction, p, m):
         op = L.TfmOp()
         op.kind, op.dir = L.OP_LINEAR, direction
         flags = 0
-        m = p['matrix'] if direction == L.FWD else p['matinv']
         if m is not None:
             m = np.asarray(m)
             flags |= L.LIN_HAS_MATRIX
