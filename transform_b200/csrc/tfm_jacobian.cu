@@ -378,14 +378,15 @@ k_jacobian(const __grid_constant__ JacParams P)
     const int tid = threadIdx.y * JTX + threadIdx.x;
     const char *const src_base = static_cast<const char *>(P.src) + (long long)blockIdx.z * P.src_plane;
     char *const dst_base = static_cast<char *>(P.dst) + (long long)blockIdx.z * P.dst_plane;
-    const long long GX0 = P.dst_x0 + (long long)blockIdx.x * JTX;   // global grid coords of tile origin
-    const long long GY0 = P.dst_y0 + (long long)blockIdx.y * JTY;
+    // global grid coordinates of the tile origin; the host guarantees |origin| + extent < 2^31
+    const int GX0 = (int)P.dst_x0 + (int)blockIdx.x * JTX;
+    const int GY0 = (int)P.dst_y0 + (int)blockIdx.y * JTY;
     const int GW = P.grid_w, GH = P.grid_h;
     // smem window origin: 2 points of halo; when the tile's first column (row) is the LAST grid
     // column (row), the edge-copy clamp below reaches one further back, so slide the window by 1
     // (such a tile has a single valid column (row), the far side of the window is unused).
     const int shx = (GX0 == GW - 1) ? 1 : 0, shy = (GY0 == GH - 1) ? 1 : 0;
-    const long long WX0 = GX0 - 2 - shx, WY0 = GY0 - 2 - shy;
+    const int WX0 = GX0 - 2 - shx, WY0 = GY0 - 2 - shy;
 
     // ---- 1. coordinates of the halo tile (points outside the grid are never used) ----
     __shared__ double2 s_ta[PW], s_tb[PH];            // polar chains: per-tile angle tables
@@ -461,7 +462,7 @@ k_jacobian(const __grid_constant__ JacParams P)
                 const int ii = i + k * NTH;
                 pj[k] = ii / PW;
                 pi[k] = ii - pj[k] * PW;
-                const long long gx = WX0 + pi[k], gy = WY0 + pj[k];
+                const int gx = WX0 + pi[k], gy = WY0 + pj[k];
                 x[k] = (double)gx;
                 y[k] = (double)gy;
                 in[k] = ii < PW * PH;
@@ -482,7 +483,7 @@ k_jacobian(const __grid_constant__ JacParams P)
     if (tid == 0) { s_mm[0] = 0xffffffffu; s_mm[1] = 0u; }      // ordered by the barrier after phase 1
     unsigned int mn_bits = 0xffffffffu, mx_bits = 0u;
     const int NCX = GW - 1, NCY = GH - 1;              // cell grid extent
-    const int wx0 = (int)WX0, wy0 = (int)WY0;
+    const int wx0 = WX0, wy0 = WY0;
     for (int i = tid; i < CW * CH; i += NTH) {
         const int cj = i / CW, ci = i - cj * CW;
         const double2 pa = s_p[cj + 1][ci + 1], pb = s_p[cj + 1][ci], pc = s_p[cj][ci + 1], pd = s_p[cj][ci];
@@ -548,12 +549,12 @@ k_jacobian(const __grid_constant__ JacParams P)
     const int ly = threadIdx.y + 8 * jrow;              // row inside the tile
     const int Y = blockIdx.y * JTY + ly;
     if (X >= P.dst_w || Y >= P.dst_h) continue;
-    const long long gx = P.dst_x0 + X, gy = P.dst_y0 + Y;
+    const int gx = (int)P.dst_x0 + X, gy = (int)P.dst_y0 + Y;
     // edge rows/columns copy their inner neighbour (helpers.pyx:1244-1247): clamp to [1, G-2]
-    long long jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
-    long long jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
+    const int jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
+    const int jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
     // point index of (jx,jy) inside the smem tile; the clamp moves by at most 1, halo is 2
-    const int qi = (int)(jx - WX0), qj = (int)(jy - WY0);
+    const int qi = jx - WX0, qj = jy - WY0;
 
     double Ji[4] = {0.0, 0.0, 0.0, 0.0};
     double px, py;
@@ -562,7 +563,7 @@ k_jacobian(const __grid_constant__ JacParams P)
         const double TX0 = (double)(GX0 - 1), TY0 = (double)(GY0 - 1);
         polar_from_tables(op0, TX0, TY0, (int)threadIdx.x + 1, ly + 1, s_ta, s_tb, s_ea, s_eb, px, py);
         // closed-form Jacobian at the (edge-clamped) grid point (jx, jy)
-        const int ti = (int)(jx - (GX0 - 1)), tj = (int)(jy - (GY0 - 1));
+        const int ti = jx - (GX0 - 1), tj = jy - (GY0 - 1);
         const double2 ca = s_ta[ti], cb = s_tb[tj];
         const bool lg = (op0.flags & TFM_RAD_R0_NOT_NONE) != 0;
         const float sgn = (op0.flags & TFM_RAD_CCW) ? 1.0f : -1.0f;
@@ -691,18 +692,25 @@ k_jacobian(const __grid_constant__ JacParams P)
             ratio = (float)ceil(P.oblur / fmin(s0, s1));
         }
         const float rsf = 2.0f * ceilf(ratio);
-        long long reg = (rsf < 1.0e9f) ? (long long)rsf : 1000000000LL;
-        if (P.max_reg > 0 && reg > P.max_reg) reg = P.max_reg;
-        const int half = (int)(reg / 2);
+        int reg = (rsf < 1.0e9f) ? (int)rsf : 1000000000;
+        if (P.max_reg > 0 && (long long)reg > P.max_reg) reg = (int)P.max_reg;
+        const int half = reg / 2;
         const float xf_of = (float)(px - fxs), yf_of = (float)(py - fys);
         float val = 0.0f, wgt = 0.0f;
         const bool whole = (P.src_x0 == 0 && P.src_y0 == 0 && P.src_w == P.full_w && P.src_h == P.full_h);
-        const bool inside = whole && xs - half >= 0 && xs + half < P.full_w &&
-                            ys - half >= 0 && ys + half < P.full_h;
+        // 32-bit tap origin for every coordinate an image can actually contain; absurd ones keep the
+        // 64-bit tests (and can never be `inside`)
+        const bool sane32 = (fabs(px) < 1.0e9) && (fabs(py) < 1.0e9);
+        const int xi = sane32 ? (int)fxs : 0, yi = sane32 ? (int)fys : 0;
+        const bool inside = whole && sane32 && xi - half >= 0 && xi + half < P.full_w &&
+                            yi - half >= 0 && yi + half < P.full_h;
         // a footprint entirely beyond a truncated edge: every tap is skipped, val stays 0 and the
         // pixel is 0 whatever the weights are (helpers.pyx:1793-1800)
-        const bool all_out = (P.bound_x == TFM_B_TRUNCATE && (xs + half < 0 || xs - half >= P.full_w)) ||
-                             (P.bound_y == TFM_B_TRUNCATE && (ys + half < 0 || ys - half >= P.full_h));
+        const bool all_out = sane32
+            ? ((P.bound_x == TFM_B_TRUNCATE && (xi + half < 0 || xi - half >= P.full_w)) ||
+               (P.bound_y == TFM_B_TRUNCATE && (yi + half < 0 || yi - half >= P.full_h)))
+            : ((P.bound_x == TFM_B_TRUNCATE && (xs + half < 0 || xs - half >= P.full_w)) ||
+               (P.bound_y == TFM_B_TRUNCATE && (ys + half < 0 || ys - half >= P.full_h)));
         if (all_out) { drow[X] = (DstT)0; continue; }
         const long long pe = P.src_pitch / (long long)sizeof(SrcT);
         const float L2E = 1.4426950408889634f;
@@ -718,7 +726,7 @@ k_jacobian(const __grid_constant__ JacParams P)
             const float r0 = fast_ex2(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
             const float rb = fast_ex2(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
             const float cA = fast_ex2(-2.0f * Aq), cB = fast_ex2(-2.0f * Bq), cC = fast_ex2(-2.0f * Cq);
-            const SrcT *p0 = reinterpret_cast<const SrcT *>(src_base) + (ys - half) * pe + (xs - half);
+            const SrcT *p0 = reinterpret_cast<const SrcT *>(src_base) + (long long)(yi - half) * pe + (xi - half);
             switch (half) {
             case 1: gauss_taps<1, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
             case 2: gauss_taps<2, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
@@ -905,6 +913,8 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     const bool subrect = (s.x0 != 0 || s.y0 != 0 || s.full_h != s.h || s.full_w != s.w);
     if ((a->bound_x == TFM_B_FORBID || a->bound_y == TFM_B_FORBID || subrect) && !a->status_dev)
         return TFM_EVALUE;
+    // the kernel indexes the output grid with 32-bit integers
+    if (d.x0 < -0x3fffffff || d.x0 > 0x3fffffff || d.y0 < -0x3fffffff || d.y0 > 0x3fffffff) return TFM_EUNSUPPORTED;
 
     JacParams P;
     P.src = s.data; P.dst = d.data; P.src_pitch = s.pitch; P.dst_pitch = d.pitch;
