@@ -26,7 +26,8 @@ def _worker(rank, world, port, case, ret):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        ny, nx, method, bound, shape = case
+        ny, nx, method, bound, shape = case[:5]
+        extra = {"oblur": case[5]} if len(case) > 5 else {}
         src = np.random.default_rng(0).random((ny, nx))
         tr = t.Composition([t.Scale(1.3, dim=2), t.Rotation(25, unit='deg'), t.Offset([-nx / 2.0, -ny / 2.0])])
 
@@ -36,16 +37,17 @@ def _worker(rank, world, port, case, ret):
         def resample_block(transform, sub, origin, full, rows, shp, m, b, kw):
             frame = np.full(full, np.nan)                       # poison what was not staged
             frame[origin[1]:origin[1] + sub.shape[0], origin[0]:origin[0] + sub.shape[1]] = sub
-            return o.resample(to_oracle(transform), frame, method=m, bound=b, shape=shp, rows=rows)
+            return o.resample(to_oracle(transform), frame, method=m, bound=b, shape=shp, rows=rows,
+                              oblur=kw.get("oblur"))
 
         out = sharding.resample_sharded(tr, src if rank == 0 else None, method=method, bound=bound, shape=shape,
                                         invert_points=invert_points, resample_block=resample_block,
-                                        src_shape=src.shape, src_dtype=src.dtype)
+                                        src_shape=src.shape, src_dtype=src.dtype, **extra)
         if rank == 0:
-            want = o.resample(to_oracle(tr), src, method=method, bound=bound, shape=shape)
+            want = o.resample(to_oracle(tr), src, method=method, bound=bound, shape=shape, **extra)
             ret["ok"] = bool(out.shape == want.shape and np.array_equal(out, want))
             ret["nan"] = int(np.isnan(out).sum())
-            plans = sharding.plan(tr, shape or src.shape, src.shape, method, bound, world, invert_points)
+            plans = sharding.plan(tr, shape or src.shape, src.shape, method, bound, world, invert_points, **extra)
             ret["boxes"] = [p["box"] for p in plans]
             ret["whole"] = [p["whole"] for p in plans]
         else:
@@ -55,7 +57,9 @@ def _worker(rank, world, port, case, ret):
 
 
 @pytest.mark.parametrize("case", [(96, 128, 'linear', 't', None), (96, 128, 'cubic', 't', (61, 77)),
-                                  (64, 64, 'nearest', 't', (5, 9)), (96, 128, 'linear', 'p', None)])
+                                  (64, 64, 'nearest', 't', (5, 9)), (96, 128, 'linear', 'p', None),
+                                  # windowed filters: the halo follows the region size (8 and 2*ceil(3*2.5))
+                                  (96, 128, 'gaussian', 't', None), (96, 128, 'zlanczos', 't', (61, 77), 2.5)])
 def test_sharded_resample_world2(case):
     mgr = mp.Manager()
     ret = mgr.dict()
