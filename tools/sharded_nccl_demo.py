@@ -27,5 +27,15 @@ for method in ("linear", "Gaussian"):
         dist.barrier(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
     if rank == 0:
         want = tr.resample(src, method=method, precision="fp32")
-        print("%s world=%d sharded %.1f ms equal=%s" % (method, world, dt * 1e3, np.array_equal(out, want)))
+        print("%s world=%d sharded (host frame in/out) %.1f ms equal=%s" % (method, world, dt * 1e3, np.array_equal(out, want)))
+    # resident frame: device tensor in, device tensor out
+    dsrc = torch.from_numpy(src).cuda() if rank == 0 else None
+    for rep in range(3):
+        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        dout = sharding.resample_sharded(tr, dsrc, method=method, bound="t", precision="fp32",
+                                         src_shape=(n, n), src_dtype=np.float32)
+        dist.barrier(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    if rank == 0:
+        print("%s world=%d sharded (resident frame) %.1f ms equal=%s" % (method, world, dt * 1e3,
+                                                                        np.array_equal(dout.cpu().numpy(), want)))
 dist.destroy_process_group()
