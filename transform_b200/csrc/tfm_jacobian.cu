@@ -181,15 +181,16 @@ __device__ __forceinline__ float filt_eval<float>(int filter, float xf, float yf
         if (xf > 3 || yf > 3) return 0.0f;
         a = pi * xf; b = a / 3.0f; filt = sinf(a) / a * sinf(b) / b;
         a = pi * yf; b = a / 3.0f; return filt * (sinf(a) / a * sinf(b) / b);
+    // arguments of the cosines are within [0, pi]: the MUFU approximation (abs. error 2^-21) is enough
     case TFM_FILT_HANNING:
         if (xf > 1 || yf > 1) return 0.0f;
-        b = cosf(pi * xf); filt = b * b;
-        b = cosf(pi * yf); return filt * b * b;
+        b = __cosf(pi * xf); filt = b * b;
+        b = __cosf(pi * yf); return filt * b * b;
     case TFM_FILT_TUKEY:
         if (xf > 1 || yf > 1) return 0.0f;
         filt = 1.0f;
-        if (xf > 0.5f) { b = cosf(pi * 2.0f * (xf - 0.5f)); filt = b * b; }
-        if (yf > 0.5f) { b = cosf(pi * 2.0f * (yf - 0.5f)); filt *= b * b; }
+        if (xf > 0.5f) { b = __cosf(pi * 2.0f * (xf - 0.5f)); filt = b * b; }
+        if (yf > 0.5f) { b = __cosf(pi * 2.0f * (yf - 0.5f)); filt *= b * b; }
         return filt;
     default:
         return __expf(-(xf * xf + yf * yf));
@@ -734,6 +735,23 @@ k_jacobian(const __grid_constant__ JacParams P)
             case 4: gauss_taps<4, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
             case 5: gauss_taps<5, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
             default: gauss_taps<6, SrcT>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+            }
+        } else if (!gauss && inside) {
+            // tent / Lanczos / "Hanning" / Tukey with the whole footprint inside the image: plain loads
+            const float J0 = J[0] * iob, J1 = J[1] * iob, J2 = J[2] * iob, J3 = J[3] * iob;
+            const SrcT *prow = reinterpret_cast<const SrcT *>(src_base) + (long long)(yi - half) * pe + (xi - half);
+            const int nt = 2 * half + 1;
+            for (int j = 0; j < nt; ++j) {
+                const float y0 = (float)(j - half) + yf_of;
+                const float ux = J1 * y0, uy = J3 * y0;
+#pragma unroll 4
+                for (int k = 0; k < nt; ++k) {
+                    const float x0 = (float)(k - half) + xf_of;
+                    const float filt = filt_eval<float>(P.filter, fabsf(fmaf(J0, x0, ux)), fabsf(fmaf(J2, x0, uy)));
+                    wgt += filt;
+                    val = fmaf((float)__ldg(prow + k), filt, val);
+                }
+                prow += pe;
             }
         } else {
             const float J0 = J[0] * iob, J1 = J[1] * iob, J2 = J[2] * iob, J3 = J[3] * iob;
