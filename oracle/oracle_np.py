@@ -14,8 +14,12 @@ Pinning (see tests/test_oracle_golden.py and tests/golden/make_golden.py):
     imported in the authoring container (golden .npz fixtures committed) and against the
     reference's own known-answer tests (tests/test_0[123]_*.py vectors restated in
     tests/test_oracle_kat.py).
+  * the windowed filters of interpND (sinc, Lanczos, Gaussian, Hann, Tukey, tent with oblur) and
+    the pincushion family (Quadpin, Cubicpin, Poly, Quarticpin): pinned bit-for-bit the same way,
+    including NumPy's reduction orders and the integer write-back quirk of `dim=` pincushions.
   * linear WCS: pinned by tests/test_01_core.py:160-169 (sample.fits value).
-  * TAN / CAR projections and the anti-aliased (Jacobian) resampler: PARITY UNPINNED by the
+  * the spherical projections (TAN, CAR, STG, SIN, ARC, ZEA, CEA, MER, SFL, AIT), phot='flux' and
+    the anti-aliased (Jacobian) resampler: PARITY UNPINNED by the
     reference -- astropy/wcslib is absent and unpinned (setup.py:27-32), and the shipped
     interpND_grid/interpND_jacobian cannot run.  The Jacobian
     path here follows helpers.pyx with the repair list R1-R12 enumerated in
