@@ -261,6 +261,11 @@ def test_filters_fast_mode_and_limits(tfm, oracle):
         want = oracle.resample(to_oracle(tr), src, method=m, bound='t', oblur=ob)
         assert got.dtype == np.float32
         assert_close_rel(got, want, 2e-5, m)
+    # oblur = None: sinc and Lanczos weights by recurrence (one sinpi per axis) in fp32 mode
+    for m in "sz":
+        got = tr.resample(src, method=m, bound='m', precision='fp32')
+        want = oracle.resample(to_oracle(tr), src, method=m, bound='m')
+        assert_close_rel(got, want, 2e-5, m + " recurrence")
     # a constant image stays constant under every normalised window
     flat = np.full((40, 50), 2.5, dtype=np.float32)
     for m in "szght":
