@@ -350,3 +350,19 @@ def test_tma_staged_variant_is_bit_identical(tfm):
             b = tr.resample(src, method='linear', precision='fp32', shape=shape, tuning=256)
             assert torch.equal(a, b), (str(tr), shape)
     assert tfm._lib.load().tfm_last_kernel().decode().startswith("k_resample_tma")
+
+
+def test_c_example_matches_python_path(tfm, tmp_path):
+    """examples/c_abi_example.c drives tfm_resample from plain C; same chain through the Python
+    shim must give the same float64 value."""
+    import subprocess
+    from test_host_logic import _build_c_example
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout
+    val = float(r.stdout.strip().split("=")[-1])
+    h, w = 96, 128
+    src = ((np.arange(h * w) % 251) / np.float32(251.0)).astype(np.float32).reshape(h, w)
+    tr = tfm.Composition([tfm.Scale(1.3, dim=2), tfm.Rotation(30, unit='deg'), tfm.Offset([-w / 2.0, -h / 2.0])])
+    out = tr.resample(src, method='linear')
+    assert abs(out[h // 2, w // 2] - val) <= 1e-12 * max(1.0, abs(val)), (val, out[h // 2, w // 2], r.stdout)

@@ -259,3 +259,24 @@ def test_pincushion_lowering():
         t.Poly(degree=9)._chain(False)
     qp = t.Quarticpin(dim=2)
     assert qp.params['degree'] == 4 and qp.params['strength'] == 0.1 and qp.idim == 2
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_abi_example")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_example.c"), "-L" + os.path.dirname(L.LIB_PATH), "-ltfm_b200",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + os.path.dirname(L.LIB_PATH),
+           "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    return exe
+
+
+@pytest.mark.timeout(3600)
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/tfm_b200.h from C99 (-pedantic -Werror), linked against the shared library: the drop-in
+    boundary has no C++ or torch types in it."""
+    import __graft_entry__
+    __graft_entry__.build()
+    assert os.path.exists(_build_c_example(tmp_path))
