@@ -229,3 +229,21 @@ def test_analytic_polar_path(tfm, oracle):
     fd = tr.resample(src, method='G', precision='fp32', tuning=512)
     assert_close_rel(got, fd, 2e-5, "log-polar analytic vs difference path")
     assert not np.array_equal(got, fd)
+
+
+def test_analytic_path_row_blocks_equal_full_frame(tfm):
+    """The analytic polar path under sharding: a row block computed with its global grid origin (and
+    the global grid extent for the edge rules) equals the same rows of the full-frame call, bit for
+    bit -- tiles of the block are aligned differently, the closed forms must not care."""
+    import torch
+    from transform_b200 import _engine
+    n = 768
+    src = torch.rand((n, n), device="cuda", dtype=torch.float32, generator=torch.Generator(device="cuda").manual_seed(3))
+    c = (n - 1) / 2.0 + 0.123
+    tr = tfm.Composition([tfm.Scale([n / (2 * np.pi), np.sqrt(2.0)]), tfm.Radial(origin=[c, c - 0.34])])
+    full = tr.resample(src, method='G', precision='fp32')
+    ops = tr._int_chain(True)
+    for (y0, y1) in ((0, 5), (5, 400), (400, 768), (767, 768)):
+        blk = _engine.resample_jacobian(ops, src, (y1 - y0, n), 'g', 't', precision='fp32',
+                                        dst_origin=(0, y0), grid_full=(n, n))
+        assert torch.equal(blk, full[y0:y1]), (y0, y1)
