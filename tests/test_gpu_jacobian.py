@@ -247,3 +247,35 @@ def test_analytic_path_row_blocks_equal_full_frame(tfm):
         blk = _engine.resample_jacobian(ops, src, (y1 - y0, n), 'g', 't', precision='fp32',
                                         dst_origin=(0, y0), grid_full=(n, n))
         assert torch.equal(blk, full[y0:y1]), (y0, y1)
+
+
+def test_constant_jacobian_path(tfm, oracle):
+    """Fast mode, Gaussian, an all-affine chain: J, the quadratic form and the footprint size are
+    host-computed constants.  Against the oracle, against the difference path (tuning bit 512), and
+    under row-block sharding (bit-exact)."""
+    import torch
+    from transform_b200 import _engine
+    rng = np.random.default_rng(31)
+    ny, nx = 300, 420
+    src = rng.random((ny, nx)).astype(np.float32)
+    tr = tfm.Composition([tfm.Offset([200.3, 150.7]), tfm.Scale([0.45, 0.6]), tfm.Rotation(-25, unit='deg'),
+                          tfm.Offset([-210.0, -150.0])])
+    cap = max(2, 2 * int(np.ceil(0.25 * max(ny, nx))))
+    for bound in ('t', 'm'):
+        got = tr.resample(src, method='G', bound=bound, precision='fp32')
+        fd = tr.resample(src, method='G', bound=bound, precision='fp32', tuning=512)
+        want = oracle.resample_jacobian(to_oracle(tr), src, method='g', bound=bound, max_reg=cap)
+        assert_close_rel(got, want, 2e-5, "constant-J vs oracle " + bound)
+        assert_close_rel(got, fd, 2e-5, "constant-J vs difference path " + bound)
+        assert not np.array_equal(got, fd)
+    dsrc = torch.from_numpy(src).cuda()
+    full = tr.resample(dsrc, method='G', precision='fp32')
+    ops = tr._int_chain(True)
+    for (y0, y1) in ((0, 7), (7, 200), (200, 300)):
+        blk = _engine.resample_jacobian(ops, dsrc, (y1 - y0, nx), 'g', 't', precision='fp32',
+                                        dst_origin=(0, y0), grid_full=(ny, nx))
+        assert torch.equal(blk, full[y0:y1]), (y0, y1)
+    # flux: |det A| is a constant too
+    fl = tr.resample(src, method='G', phot='flux', precision='fp32')
+    rd = tr.resample(src, method='G', precision='fp32')
+    assert_close_rel(fl, rd / (0.45 * 0.6), 1e-5, "flux")

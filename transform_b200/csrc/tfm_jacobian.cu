@@ -41,6 +41,12 @@ struct JacParams {
     double oblur, pad_pow, padval, jump_thresh;
     long long max_reg;
     int *status;
+    // constant-Jacobian path (fast mode, Gaussian, the whole chain is affine): everything that depends
+    // on J alone is computed once on the host, in fp64
+    int aff_const;
+    int aff_half;                            // footprint half-width
+    double aff[6];                           // source = A . grid + b
+    float aff_q[3];                          // Gaussian quadratic form (q00, q01, q11)
     ChainDev chain;
 };
 
@@ -432,8 +438,11 @@ k_jacobian(const __grid_constant__ JacParams P)
             analytic = (P.jump_thresh > 0.0) && (ratio * 1.01 <= P.jump_thresh);      // NaN compares false
         }
     }
+    const bool affc = FASTI && P.aff_const;
     bool tile_clean = true;
-    if (analytic) {
+    if (affc) {
+        // nothing to prepare: coordinates are affine in the grid indices, the Jacobian is a constant
+    } else if (analytic) {
         // tables for grid points (GX0-1 .. GX0+JTX) x (GY0-1 .. GY0+JTY): the tile plus the one-point
         // reach of the edge-copy clamp
         polar_tables(P.chain.ops[0], (double)(GX0 - 1), (double)(GY0 - 1), JTX + 2, JTY + 2, s_ta, s_tb, s_ea, s_eb, tid, NTH);
@@ -559,7 +568,11 @@ k_jacobian(const __grid_constant__ JacParams P)
 
     double Ji[4] = {0.0, 0.0, 0.0, 0.0};
     double px, py;
-    if (analytic) {
+    if (affc) {
+        px = fma(P.aff[0], (double)gx, fma(P.aff[1], (double)gy, P.aff[4]));
+        py = fma(P.aff[2], (double)gx, fma(P.aff[3], (double)gy, P.aff[5]));
+        Ji[0] = P.aff[0]; Ji[1] = P.aff[1]; Ji[2] = P.aff[2]; Ji[3] = P.aff[3];
+    } else if (analytic) {
         const tfm_op &op0 = P.chain.ops[0];
         const double TX0 = (double)(GX0 - 1), TY0 = (double)(GY0 - 1);
         polar_from_tables(op0, TX0, TY0, (int)threadIdx.x + 1, ly + 1, s_ta, s_tb, s_ea, s_eb, px, py);
@@ -684,10 +697,12 @@ k_jacobian(const __grid_constant__ JacParams P)
         const float ob = (float)P.oblur, iob = fast_rcp(ob);
         const bool gauss = (P.filter == TFM_FILT_GAUSSIAN);
         float J[4] = {0.f, 0.f, 0.f, 0.f}, smin, inv_smin, q00 = 0.f, q01 = 0.f, q11 = 0.f;
-        if (gauss) gaussian_quadratic_f32(Ji, (float)P.padval, (float)P.pad_pow, q00, q01, q11, inv_smin);
+        int half_const = -1;
+        if (affc) { q00 = P.aff_q[0]; q01 = P.aff_q[1]; q11 = P.aff_q[2]; inv_smin = 1.0f; half_const = P.aff_half; }
+        else if (gauss) gaussian_quadratic_f32(Ji, (float)P.padval, (float)P.pad_pow, q00, q01, q11, inv_smin);
         else { padded_inverse_f32(Ji, (float)P.padval, (float)P.pad_pow, J, smin); inv_smin = fast_rcp(smin); }
         float ratio = ob * inv_smin;
-        if (fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) {
+        if (half_const < 0 && fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) {
             // the footprint size is a ceil(): when fp32 cannot decide it, redo that one number in fp64
             double U[4], V[4], sd[2];
             svd2x2_dev(Ji, U, sd, V);
@@ -698,7 +713,7 @@ k_jacobian(const __grid_constant__ JacParams P)
         const float rsf = 2.0f * ceilf(ratio);
         int reg = (rsf < 1.0e9f) ? (int)rsf : 1000000000;
         if (P.max_reg > 0 && (long long)reg > P.max_reg) reg = (int)P.max_reg;
-        const int half = reg / 2;
+        const int half = (half_const >= 0) ? half_const : reg / 2;
         const float xf_of = (float)(px - fxs), yf_of = (float)(py - fys);
         float val = 0.0f, wgt = 0.0f;
         const bool whole = (P.src_x0 == 0 && P.src_y0 == 0 && P.src_w == P.full_w && P.src_h == P.full_h);
@@ -958,6 +973,38 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     } else {
         P.chain.n = a->n_ops;
         for (int i = 0; i < a->n_ops; ++i) P.chain.ops[i] = a->chain[i];
+    }
+
+    // constant-Jacobian path: fast mode, Gaussian, an all-affine chain, and a jump threshold under
+    // which a constant |J|^2 can never be flagged (ratio of neighbouring cells is 1 up to rounding)
+    P.aff_const = 0;
+    P.aff_half = 0;
+    if (a->precision == TFM_PREC_FAST32 && a->filter == TFM_FILT_GAUSSIAN && !(a->tuning & 512) &&
+        (a->jump_thresh == 0.0 || a->jump_thresh >= 1.001)) {
+        bool lin = true;
+        for (int i = 0; i < a->n_ops; ++i) lin = lin && is_linear_like(a->chain[i]);
+        if (lin) {
+            compose_linear_run(a->chain, 0, a->n_ops, P.aff, P.aff + 4);
+            const double ja = P.aff[0], jb = P.aff[1], jc = P.aff[2], jd = P.aff[3];
+            // Q = f(J J^T), f(lambda) = (padval + lambda^(p/2))^(-2/p): the fp64 twin of gaussian_quadratic_f32
+            const double g00 = ja * ja + jb * jb, g01 = ja * jc + jb * jd, g11 = jc * jc + jd * jd;
+            const double mean = 0.5 * (g00 + g11), dif = 0.5 * (g00 - g11);
+            const double rad = sqrt(dif * dif + g01 * g01);
+            const double lp = mean + rad, lm = fmax(mean - rad, 0.0);
+            auto f = [&](double lam) { return pow(P.padval + pow(lam, 0.5 * P.pad_pow), -2.0 / P.pad_pow); };
+            const double fp = f(lp), fm = f(lm);
+            const double beta = (lp - lm > 0.0) ? (fp - fm) / (lp - lm) : 0.0;
+            const double q00 = fp - beta * (rad - dif), q01 = beta * g01, q11 = fp - beta * (rad + dif);
+            const double smin = sqrt(fp);                       // the smaller padded inverse singular value
+            double reg = 2.0 * ceil(P.oblur / smin);            // helpers.pyx:1666
+            if (P.max_reg > 0 && reg > (double)P.max_reg) reg = (double)P.max_reg;
+            if (isfinite(q00) && isfinite(q01) && isfinite(q11) && isfinite(reg) && reg >= 0.0 && reg < 2.0e9 &&
+                isfinite(P.aff[4]) && isfinite(P.aff[5])) {
+                P.aff_const = 1;
+                P.aff_half = (int)(reg / 2.0);
+                P.aff_q[0] = (float)q00; P.aff_q[1] = (float)q01; P.aff_q[2] = (float)q11;
+            }
+        }
     }
 
     const int sph = chain_sph_level(P.chain);
