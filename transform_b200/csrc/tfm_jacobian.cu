@@ -43,6 +43,7 @@ struct JacParams {
     int *status;
     // constant-Jacobian path (fast mode, Gaussian, the whole chain is affine): everything that depends
     // on J alone is computed once on the host, in fp64
+    int lw;                                  // log2 of the warp patch width in the footprint phase
     int aff_const;
     int aff_half;                            // footprint half-width
     double aff[6];                           // source = A . grid + b
@@ -553,10 +554,20 @@ k_jacobian(const __grid_constant__ JacParams P)
 
     // ---- 4. per pixel: grid-centred Jacobian, SVD padding, footprint ----
     int state = 0;
-    const int X = blockIdx.x * JTX + threadIdx.x;
+    // Thread -> pixel map of the footprint phase: a warp covers a K2_WX x (32 / K2_WX) patch of the
+    // tile instead of one 32-pixel row, so that the 32 footprints a tap load gathers from sit in a
+    // compact source patch (an arc of 32 pixels of a polar unwrap spans up to 140 source pixels: one
+    // tap load then touches ~8 cache lines, and the L1 tag stage, one line per clock, was the limit).
+    // Measured at 8192^2 (polar unwrap / rotated affine down-scale): 32x1 2.70 / 0.70 ms, 16x2 2.20 /
+    // 0.69, 8x4 2.00 / 0.72, 4x8 1.98 / 0.82 -- the host picks log2(width) per launch (P.lw).
+    const int lw = P.lw;                               // 5, 4, 3 or 2: patch is (1 << lw) x (32 >> lw)
+    const int lane = tid & 31, wrp = tid >> 5;
+    const int tx = ((wrp & ((32 >> lw) - 1)) << lw) + (lane & ((1 << lw) - 1));
+    const int ty = (wrp >> (5 - lw)) * (32 >> lw) + (lane >> lw);
+    const int X = blockIdx.x * JTX + tx;
 #pragma unroll 1
     for (int jrow = 0; jrow < JTY / 8; ++jrow) {
-    const int ly = threadIdx.y + 8 * jrow;              // row inside the tile
+    const int ly = ty + 8 * jrow;                       // row inside the tile
     const int Y = blockIdx.y * JTY + ly;
     if (X >= P.dst_w || Y >= P.dst_h) continue;
     const int gx = (int)P.dst_x0 + X, gy = (int)P.dst_y0 + Y;
@@ -575,7 +586,7 @@ k_jacobian(const __grid_constant__ JacParams P)
     } else if (analytic) {
         const tfm_op &op0 = P.chain.ops[0];
         const double TX0 = (double)(GX0 - 1), TY0 = (double)(GY0 - 1);
-        polar_from_tables(op0, TX0, TY0, (int)threadIdx.x + 1, ly + 1, s_ta, s_tb, s_ea, s_eb, px, py);
+        polar_from_tables(op0, TX0, TY0, tx + 1, ly + 1, s_ta, s_tb, s_ea, s_eb, px, py);
         // closed-form Jacobian at the (edge-clamped) grid point (jx, jy)
         const int ti = jx - (GX0 - 1), tj = jy - (GY0 - 1);
         const double2 ca = s_ta[ti], cb = s_tb[tj];
@@ -636,7 +647,7 @@ k_jacobian(const __grid_constant__ JacParams P)
         for (int k = 0; k < 4; ++k) Ji[k] = __ddiv_rn(Ji[k], denom);
     }
 
-    const double2 pme = s_p[ly + 2 + shy][threadIdx.x + 2 + shx];
+    const double2 pme = s_p[ly + 2 + shy][tx + 2 + shx];
     px = pme.x;
     py = pme.y;
     }   // !analytic
@@ -1006,6 +1017,12 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
             }
         }
     }
+
+    // warp patch of the footprint phase: 8 x 4 unless the map is affine (16 x 2); tuning bits 1024 /
+    // 2048 force 32 x 1 / 4 x 8 for A/B runs
+    P.lw = P.aff_const ? 4 : 3;
+    if (a->tuning & 1024) P.lw = 5;
+    if (a->tuning & 2048) P.lw = 2;
 
     const int sph = chain_sph_level(P.chain);
     // tile height: 32 by default (4 pixels per thread); tuning bits 8 / 32 select 16 / 8 for A/B runs
