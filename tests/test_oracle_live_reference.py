@@ -1,0 +1,98 @@
+"""CPU: the oracle against the LIVE reference (imported from /root/reference through
+oracle/ref_import.py) on seeded random cases -- beyond the committed golden vectors.  Runs only where
+the reference tree is mounted (the authoring container); skipped on the GPU box."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/transform"),
+                                reason="the reference tree is not mounted on this machine")
+
+BOUNDS = ['t', 'e', 'p', 'm']
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import ref_import
+    warnings.simplefilter("ignore")
+    return ref_import.load_reference()
+
+
+def _pair(ref, o, rng, ny, nx, kind):
+    """The same random transform as a reference object and as an oracle object."""
+    if kind == "affine":
+        sc = rng.uniform(0.5, 2.0, size=2)
+        ang = rng.uniform(-180, 180)
+        off = rng.uniform(-0.6, 0.1, size=2) * np.array([nx, ny])
+        r = ref.Composition([ref.Scale(sc), ref.Rotation(ang, unit='deg'), ref.Offset(off)])
+        q = o.Composition([o.Scale(sc), o.Rotation(ang, unit='deg'), o.Offset(off)])
+        return r, q
+    if kind == "radial":
+        org = [rng.uniform(0.2, 0.8) * nx, rng.uniform(0.2, 0.8) * ny]
+        ccw, pos = bool(rng.random() < 0.5), bool(rng.random() < 0.5)
+        r0 = None if rng.random() < 0.6 else rng.uniform(0.5, 3.0)
+        pre = [nx / (2 * np.pi), ny / (3.0 if r0 else 0.7 * max(nx, ny))]
+        r = ref.Composition([ref.Scale(pre), ref.Radial(origin=np.array(org), ccw=ccw, pos_only=pos, r0=r0)])
+        q = o.Composition([o.Scale(pre), o.Radial(origin=org, ccw=ccw, pos_only=pos, r0=r0)])
+        return r, q
+    st, ln = rng.uniform(-0.4, 0.4), rng.uniform(20, 80)
+    org = rng.uniform(0.3, 0.7, size=2) * np.array([nx, ny])
+    if rng.random() < 0.5:
+        return (ref.Quadpin(idim=2, odim=2, strength=st, length=ln, origin=org),
+                o.Quadpin(idim=2, strength=st, length=ln, origin=org))
+    deg = int(rng.integers(2, 5))
+    return (ref.Poly(idim=2, odim=2, strength=st / 2, length=ln, degree=deg, origin=org).inverse(),
+            o.Inverse(o.Poly(idim=2, strength=st / 2, length=ln, degree=deg, origin=org)))
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_resample_random_cases(ref, oracle, seed):
+    rng = np.random.default_rng(7000 + seed)
+    ny, nx = int(rng.integers(3, 60)), int(rng.integers(3, 80))
+    kind = ("affine", "radial", "pin")[seed % 3]
+    r, q = _pair(ref, oracle, rng, ny, nx, kind)
+    dt = (np.float32, np.float64, np.int16)[int(rng.integers(0, 3))]
+    src = (rng.random((ny, nx)) * 100).astype(dt)
+    shape = None if rng.random() < 0.5 else (int(rng.integers(1, 70)), int(rng.integers(1, 90)))
+    bound = BOUNDS[int(rng.integers(0, 4))]
+    if rng.random() < 0.3:
+        bound = [BOUNDS[int(rng.integers(0, 4))], BOUNDS[int(rng.integers(0, 4))]]
+    for m in ('nearest', 'linear', 'cubic', 'hann', 'gaussian', 'zlanczos'):
+        if m == 'cubic' and np.dtype(dt).kind in 'iu':
+            continue
+        want = r.resample(src, method=m, bound=bound, shape=shape)
+        got = oracle.resample(q, src, method=m, bound=bound, shape=shape)
+        what = (seed, kind, m, bound, shape, np.dtype(dt).name)
+        assert got.shape == want.shape and got.dtype == want.dtype, what
+        if kind == "radial":
+            if m == 'nearest':
+                assert (got != want).sum() <= max(2, got.size // 500), what
+            else:
+                ok = np.isclose(got, want, rtol=0, atol=1e-10 * max(1.0, float(np.nanmax(np.abs(want)))), equal_nan=True)
+                assert ok.all(), what
+        else:
+            assert np.array_equal(got, want, equal_nan=True), what
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_apply_random_cases(ref, oracle, seed):
+    rng = np.random.default_rng(8000 + seed)
+    kind = ("affine", "radial", "pin")[seed % 3]
+    r, q = _pair(ref, oracle, rng, 64, 80, kind)
+    v = rng.uniform(1.0, 60.0, size=(int(rng.integers(1, 400)), int(rng.integers(2, 5))))
+    for invert in (False, True):
+        if (invert and r.no_reverse) or (not invert and r.no_forward):
+            continue
+        want = r.apply(v.copy(), invert=invert)
+        got = oracle.apply(q, v.copy(), invert=invert)
+        if kind == "radial":
+            assert np.allclose(got, want, rtol=1e-13, atol=1e-12), (seed, invert)
+        else:
+            assert np.array_equal(got, want, equal_nan=True), (seed, kind, invert)
