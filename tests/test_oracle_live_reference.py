@@ -96,3 +96,28 @@ def test_apply_random_cases(ref, oracle, seed):
             assert np.allclose(got, want, rtol=1e-13, atol=1e-12), (seed, invert)
         else:
             assert np.array_equal(got, want, equal_nan=True), (seed, kind, invert)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_jacobian_pieces_random_cases(ref, oracle, seed):
+    """simple_jacobian / jump_detect (square grids: no R12 ambiguity) / svd2x2 against the live
+    reference's compiled helpers."""
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.integers(5, 40))
+    # a smooth map with a branch cut now and then: forward polar coordinates of a shifted grid
+    g = np.mgrid[range(n), range(n)].transpose().astype(float)
+    org = rng.uniform(0.2, 0.8, size=2) * n
+    d = g - org
+    coords = np.stack([np.arctan2(d[..., 1], d[..., 0]) * rng.uniform(1, 20), np.hypot(d[..., 0], d[..., 1])], -1)
+    coords += rng.normal(0, 1e-3, coords.shape)
+    Js_ref = ref.simple_jacobian(coords)
+    Js = oracle.simple_jacobian(coords)
+    assert np.array_equal(Js, Js_ref)
+    for thr in (1.2, 4.0, 10.0):
+        assert np.array_equal(oracle.jump_detect(Js, thr), ref.jump_detect(Js_ref, thr)), (seed, thr)
+    for _ in range(10):
+        M = rng.uniform(-3, 3, size=(2, 2))
+        U, s, V = np.zeros((2, 2)), np.zeros(2), np.zeros((2, 2))
+        ref.svd2x2(M, U, s, V)
+        U2, s2, V2 = oracle.svd2x2(M)
+        assert np.allclose(U2, U, atol=1e-14) and np.allclose(s2, s, atol=1e-14) and np.allclose(V2, V, atol=1e-14)
