@@ -18,13 +18,17 @@ Pinning (see tests/test_oracle_golden.py and tests/golden/make_golden.py):
     the pincushion family (Quadpin, Cubicpin, Poly, Quarticpin): pinned bit-for-bit the same way,
     including NumPy's reduction orders and the integer write-back quirk of `dim=` pincushions.
   * linear WCS: pinned by tests/test_01_core.py:160-169 (sample.fits value).
-  * the spherical projections (TAN, CAR, STG, SIN, ARC, ZEA, CEA, MER, SFL, AIT), phot='flux' and
-    the anti-aliased (Jacobian) resampler: PARITY UNPINNED by the
-    reference -- astropy/wcslib is absent and unpinned (setup.py:27-32), and the shipped
-    interpND_grid/interpND_jacobian cannot run.  The Jacobian
-    path here follows helpers.pyx with the repair list R1-R12 enumerated in
-    `interp_grid_jacobian` below; it is cross-checked against the reference's *working*
-    independent implementation SVD.pyx::map_coordinates on affine maps.
+  * the anti-aliased (Jacobian) resampler: the shipped interpND_grid / jacobian / interpND_jacobian
+    cannot run, so the restatement here follows helpers.pyx with the
+    repair list R1-R12 enumerated in `interp_grid_jacobian` below -- and is PINNED BIT FOR BIT against
+    the reference's OWN code compiled with the minimal repairs R1-R6, R11
+    (oracle/build_ref_repaired.py -> oracle/_ref/helpers_repaired*.so): all four usable filter shapes
+    x boundaries t/e/p x jump detection on/off x oblur, golden fixtures `aa/*` and live random sweeps.
+    R9 (mirror boundary) and R12 (non-square jump_detect) are the two deliberate departures and are
+    outside that pin; it is also cross-checked against SVD.pyx::map_coordinates on affine maps.
+  * PARITY UNPINNED: the spherical projections (TAN, CAR, STG, SIN, ARC, ZEA, CEA, MER, SFL, AIT) --
+    astropy/wcslib is absent and unpinned (setup.py:27-32) -- and phot='flux' (documented at
+    core.py:521-533 but not implemented by the reference).
 
 Arithmetic conventions that the CUDA path reproduces bit-for-bit in its fp64-exact mode:
   * a 2x2 matrix-vector product is fma(m00, x, fl(m01*y)) -- what np.matmul on [...,2,1] stacks

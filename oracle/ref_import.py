@@ -48,6 +48,19 @@ def load_ref_helpers():
     return _load_ext("helpers", "tfm_ref_helpers")
 
 
+def load_ref_helpers_repaired():
+    """The reference's helpers module built with the named repairs of oracle/build_ref_repaired.py:
+    its anti-aliased path (interpND_grid -> jacobian -> interpND_jacobian) runs."""
+    if "tfm_ref_helpers_repaired" in sys.modules:
+        return sys.modules["tfm_ref_helpers_repaired"]
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    if not os.path.exists(os.path.join(_REFDIR, "helpers_repaired" + suffix)):
+        import build_ref_repaired
+        if not build_ref_repaired.build():
+            raise ImportError("oracle/_ref/helpers_repaired%s not built and the reference is absent" % suffix)
+    return _load_ext("helpers_repaired", "tfm_ref_helpers_repaired")
+
+
 def load_ref_svd():
     if "tfm_ref_SVD" in sys.modules:
         return sys.modules["tfm_ref_SVD"]

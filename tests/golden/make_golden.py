@@ -149,6 +149,23 @@ def main():
     tgt = np.zeros((24, 32))
     svd.map_coordinates(src64, tgt, lambda c: t.Scale([2.0, 2.0]).apply(c))
     out["svdpyx/target"] = tgt
+    # the reference's OWN anti-aliased path, built with the named repairs (oracle/build_ref_repaired.py):
+    # square output grids (R12 is not applied there), no mirror boundary (R9 is not applied there)
+    hr = ref_import.load_ref_helpers_repaired()
+    grid48 = np.mgrid[range(48), range(48)].transpose()
+    aa_maps = {"affine": t.Composition([t.Offset([30.0, 22.0]), t.Scale([0.55, 0.8]), t.Rotation(25, unit='deg'),
+                                        t.Offset([-24.0, -24.0])]),
+               "polar": t.Composition([t.Scale([48 / (2 * np.pi), 48 / 30.0]), t.Radial(origin=[31.5, 23.5])])}
+    for name, tr in aa_maps.items():
+        coords = tr.invert(grid48)
+        out["aa/%s/coords" % name] = coords
+        for m in "glht":
+            for b in ("t", "e", "p"):
+                out["aa/%s/%s/%s" % (name, m, b)] = np.asarray(hr.interpND_grid(src64, coords.copy(), method=m, bound=b, strict=True))
+        out["aa/%s/g/t/nojump" % name] = np.asarray(hr.interpND_grid(src64, coords.copy(), method='g', bound='t',
+                                                                      jump_detect=0, strict=True))
+        out["aa/%s/g/e/oblur2" % name] = np.asarray(hr.interpND_grid(src64, coords.copy(), method='g', bound='e',
+                                                                      oblur=2.0, strict=True))
     np.savez_compressed(os.path.join(HERE, "reference_golden.npz"), **out)
     print("wrote %d arrays, %d bytes" % (len(out), os.path.getsize(os.path.join(HERE, "reference_golden.npz"))))
 

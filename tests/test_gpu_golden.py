@@ -139,3 +139,27 @@ def test_pincushion_matches_reference(tfm, name):
         want = GOLD["pin/%s/near" % name]
         assert got.dtype == want.dtype
         assert (got != want).sum() <= (0 if exact else 3), name
+
+
+# ---------------------------------------------------------------------------------------------
+# the anti-aliased path against the reference's own code built with the named repairs
+# ---------------------------------------------------------------------------------------------
+from test_oracle_golden import AA_KEYS, _aa_kwargs  # noqa: E402
+
+
+@pytest.mark.parametrize("key", AA_KEYS)
+def test_antialiased_path_matches_repaired_reference(tfm, key):
+    """K2 (through interpND_grid on the recorded coordinate arrays) against outputs of the reference's
+    own interpND_grid -> jacobian -> interpND_jacobian compiled with repairs R1-R6, R11
+    (oracle/build_ref_repaired.py, fixtures by tests/golden/make_golden.py).  Parity mode: same
+    summation order, libm last bits only; fp32 mode: tolerance, isolated footprint-size flips."""
+    name, kw = _aa_kwargs(key)
+    coords = GOLD["aa/%s/coords" % name]
+    want = GOLD[key]
+    got = tfm.interpND_grid(GOLD["src64"], coords, sv_limit=100.0, **kw)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    assert_close_rel(got, want, 1e-11, key)
+    if kw["method"] == "g":
+        fast = tfm.interpND_grid(GOLD["src64"].astype(np.float32), coords, sv_limit=100.0, precision='fp32', **kw)
+        err = np.abs(fast - want)
+        assert np.median(err) < 2e-5 and (err > 5e-4).sum() <= max(3, err.size // 100), (key, err.max())

@@ -206,3 +206,26 @@ def test_jacobian_filter_vs_reference_svdpyx(oracle):
     # and on a constant image both reproduce the constant
     const = oracle.resample_jacobian(otr, np.full_like(src, 2.5), method='g', bound='e', shape=want.shape)
     assert np.allclose(const, 2.5, atol=1e-12)
+
+
+AA_KEYS = [k for k in GOLD.files if k.startswith("aa/") and not k.endswith("/coords")]
+
+
+def _aa_kwargs(key):
+    parts = key.split("/")
+    kw = {"method": parts[2], "bound": parts[3]}
+    if len(parts) > 4 and parts[4] == "nojump":
+        kw["jump_detect"] = 0
+    if len(parts) > 4 and parts[4] == "oblur2":
+        kw["oblur"] = 2.0
+    return parts[1], kw
+
+
+@pytest.mark.parametrize("key", AA_KEYS)
+def test_antialiased_path_matches_repaired_reference(oracle, key):
+    """The anti-aliased resampler against the reference's OWN code built with the named repairs
+    R1-R6, R11 (oracle/build_ref_repaired.py): identical bits, for every filter shape, boundary,
+    with and without jump detection."""
+    name, kw = _aa_kwargs(key)
+    got = oracle.interp_grid_jacobian(GOLD["src64"], GOLD["aa/%s/coords" % name], **kw)
+    assert np.array_equal(got, GOLD[key], equal_nan=True), key

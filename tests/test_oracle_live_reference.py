@@ -121,3 +121,25 @@ def test_jacobian_pieces_random_cases(ref, oracle, seed):
         ref.svd2x2(M, U, s, V)
         U2, s2, V2 = oracle.svd2x2(M)
         assert np.allclose(U2, U, atol=1e-14) and np.allclose(s2, s, atol=1e-14) and np.allclose(V2, V, atol=1e-14)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_antialiased_path_random_cases(oracle, seed):
+    """oracle.interp_grid_jacobian against the repaired build of the reference's own interpND_grid
+    (oracle/build_ref_repaired.py) on random smooth maps; square grids, no mirror boundary (R9 and R12
+    are the oracle's two deliberate departures)."""
+    import ref_import
+    hr = ref_import.load_ref_helpers_repaired()
+    rng = np.random.default_rng(9500 + seed)
+    n = int(rng.integers(12, 40))
+    src = rng.random((int(rng.integers(10, 50)), int(rng.integers(10, 50))))
+    g = np.mgrid[range(n), range(n)].transpose().astype(float)
+    A = rng.uniform(-1.5, 1.5, size=(2, 2)) + np.eye(2)
+    idx = (g - n / 2) @ A.T + np.array(src.shape[::-1]) / 2 + 0.05 * np.sin(g[..., ::-1] / 3.0)
+    for m in "glht":
+        for b in ("t", "e", "p"):
+            jd = (4.0, 0, 1.5)[int(rng.integers(0, 3))]
+            ob = (1.0, 1.7)[int(rng.integers(0, 2))]
+            want = np.asarray(hr.interpND_grid(src, idx.copy(), method=m, bound=b, jump_detect=jd, oblur=ob, strict=True))
+            got = oracle.interp_grid_jacobian(src, idx.copy(), method=m, bound=b, jump_detect=jd, oblur=ob)
+            assert np.array_equal(got, want, equal_nan=True), (seed, m, b, jd, ob)
