@@ -136,7 +136,7 @@ def test_antialiased_path_random_cases(oracle, seed):
     g = np.mgrid[range(n), range(n)].transpose().astype(float)
     A = rng.uniform(-1.5, 1.5, size=(2, 2)) + np.eye(2)
     idx = (g - n / 2) @ A.T + np.array(src.shape[::-1]) / 2 + 0.05 * np.sin(g[..., ::-1] / 3.0)
-    for m in "glht":
+    for m in "glhtz":
         for b in ("t", "e", "p"):
             jd = (4.0, 0, 1.5)[int(rng.integers(0, 3))]
             ob = (1.0, 1.7)[int(rng.integers(0, 2))]
