@@ -280,3 +280,43 @@ def test_header_is_plain_c_and_links(tmp_path):
     import __graft_entry__
     __graft_entry__.build()
     assert os.path.exists(_build_c_example(tmp_path))
+
+
+def test_product_never_touches_the_oracle_or_a_cpu_fallback():
+    """The product package may not import, execute or link anything under oracle/, and it has no CPU
+    compute path: every compute entry point goes through libtfm_b200.so (and raises without it)."""
+    import ast
+    pkg = os.path.join(ROOT, "transform_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith(".py"):
+                continue
+            src = open(os.path.join(dirpath, fn)).read()
+            tree = ast.parse(src)
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                for n in names:
+                    assert not n.split(".")[0].startswith("oracle") and "ref_import" not in n and "build_ref" not in n, (fn, n)
+            assert "oracle/_ref" not in src and "liboracle" not in src, fn
+    # the CUDA sources mention the oracle in comments only (never an #include or a symbol)
+    for fn in os.listdir(os.path.join(pkg, "csrc")):
+        if fn.endswith((".cu", ".cuh")):
+            for line in open(os.path.join(pkg, "csrc", fn)):
+                if "oracle" in line.lower():
+                    assert line.lstrip().startswith("//") or "//" in line.split("oracle")[0].split("Oracle")[0], (fn, line)
+                assert "#include" not in line or "oracle" not in line.lower(), (fn, line)
+    # no library -> loud failure, not a fallback
+    saved = L.LIB_PATH
+    try:
+        L.LIB_PATH = saved + ".does-not-exist"
+        L._lib = None
+        with pytest.raises(L.LibraryMissing):
+            L.load()
+    finally:
+        L.LIB_PATH = saved
+        L._lib = None
+        L.load()
