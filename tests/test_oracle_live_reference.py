@@ -143,3 +143,31 @@ def test_antialiased_path_random_cases(oracle, seed):
             want = np.asarray(hr.interpND_grid(src, idx.copy(), method=m, bound=b, jump_detect=jd, oblur=ob, strict=True))
             got = oracle.interp_grid_jacobian(src, idx.copy(), method=m, bound=b, jump_detect=jd, oblur=ob)
             assert np.array_equal(got, want, equal_nan=True), (seed, m, b, jd, ob)
+
+
+def test_mirror_boundary_departure_R9(oracle):
+    """R9: under the mirror boundary the reference's footprint loop reflects with `s-1-i` after the
+    mod-2s step (helpers.pyx:1768-1769, 1789-1790) where its own apply_boundary uses `2s-1-i`
+    (helpers.pyx:172).  The oracle (and K2) follow apply_boundary.  The two agree wherever no tap
+    leaves the image and differ where one does -- and there the reference's rule can index out of the
+    array's lower end (negative index), which is why it is not reproduced."""
+    import ref_import
+    hr = ref_import.load_ref_helpers_repaired()
+    rng = np.random.default_rng(77)
+    src = rng.random((40, 40))
+    n = 16
+    g = np.mgrid[range(n), range(n)].transpose().astype(float)
+    inner = g * 0.9 + 12.3                                   # footprints stay inside the image
+    a = np.asarray(hr.interpND_grid(src, inner.copy(), method='g', bound='m', strict=True))
+    b = oracle.interp_grid_jacobian(src, inner.copy(), method='g', bound='m')
+    assert np.array_equal(a, b)
+    edge = g * 0.9 + 30.2                                    # footprints cross the upper edges
+    a = np.asarray(hr.interpND_grid(src, edge.copy(), method='g', bound='m', strict=True))
+    b = oracle.interp_grid_jacobian(src, edge.copy(), method='g', bound='m')
+    crossing = (edge.max(axis=-1) + 3 >= 40)
+    assert np.array_equal(a[~crossing], b[~crossing])
+    assert not np.array_equal(a[crossing], b[crossing])
+    # the oracle's rule is apply_boundary's: same result as mirroring the image explicitly
+    big = np.pad(src, 40, mode='symmetric')
+    c = oracle.interp_grid_jacobian(big, edge + 40.0, method='g', bound='t')
+    assert np.allclose(b, c, rtol=0, atol=1e-12)          # shifted coordinates round their fractions differently
