@@ -1,0 +1,268 @@
+"""The kernel variants behind the headline numbers, pinned against the oracle AT the BASELINE sizes.
+
+bench.py's step is two calls on an 8192^2 float32 frame (linear through Scale o Rotation o Offset,
+Jacobian-Gaussian through the polar unwrap); BASELINE config 2 is the same affine chain at 4096^2,
+config 5 is Transform.apply on a long vector array.  Each test here
+  (a) issues exactly the call the bench issues (same transform, size, precision, device-resident data),
+  (b) asserts WHICH kernel variant the dispatcher chose (tfm_last_kernel), so that a silent change of
+      the dispatch rules cannot leave the headline variant untested, and
+  (c) compares >= 128 full output rows spread over the frame plus the four borders with the oracle
+      (oracle.resample(rows=...) / oracle.resample_jacobian(rows=...), helpers.pyx:559-611,
+      1542-1803 restated) under a tolerance whose outliers are capped in MAGNITUDE, not only counted.
+"""
+import numpy as np
+import pytest
+
+from conftest import to_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def sample_rows(n, k=128):
+    rows = set(int(r) for r in np.linspace(0, n - 1, k))
+    rows.update((0, 1, 2, n - 3, n - 2, n - 1))           # bottom and top borders (left/right: every row is full width)
+    return sorted(rows)
+
+
+def named_chain(tfm, n):
+    return tfm.Composition([tfm.Scale(1.3, dim=2), tfm.Rotation(30, unit='deg'), tfm.Offset([-n / 2.0, -n / 2.0])])
+
+
+def polar_chain(tfm, n):
+    c = (n - 1) / 2.0
+    return tfm.Composition([tfm.Scale([n / (2 * np.pi), n / (n / np.sqrt(2.0))]), tfm.Radial(origin=[c, c])])
+
+
+def frame(n, seed):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.rand((n, n), generator=g, device="cuda", dtype=torch.float32)
+
+
+def oracle_rows(oracle, otr, src, rows, **kw):
+    return np.stack([oracle.resample(otr, src, rows=(y, y + 1), **kw)[0] for y in rows])
+
+
+def err_stats(got, want):
+    err = np.abs(np.asarray(got, dtype=np.float64) - np.asarray(want, dtype=np.float64))
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    err = np.nan_to_num(err)
+    return err, float(err.max()), float(np.median(err))
+
+
+# --------------------------------------------------------------------------------------------------
+# K1 linear, fp32 fast path
+# --------------------------------------------------------------------------------------------------
+K1_VARIANTS = [  # (tuning, expected kernel name, None = whatever the default dispatch picks)
+    (0, None),
+    (16, "k_resample<trunc,affine>"),
+    (256, "k_resample_tma<affine>"),
+    (128, "k_resample_tex<affine>"),
+]
+
+
+@pytest.mark.parametrize("n", [8192, 4096])
+def test_linear_fp32_named_chain_all_variants(tfm, oracle, n):
+    """bench step call 1 (8192^2) and BASELINE config 2 (4096^2): every fp32 linear kernel variant
+    against the oracle, 1e-5 (north_star's fp32 tolerance), no outliers allowed."""
+    from transform_b200 import _lib
+    src = frame(n, 1000)
+    tr = named_chain(tfm, n)
+    rows = sample_rows(n)
+    want = oracle_rows(oracle, to_oracle(tr), src.cpu().numpy(), rows, method='linear')
+    default_name = None
+    results = {}
+    for tuning, name in K1_VARIANTS:
+        out = tr.resample(src, method='linear', precision='fp32', tuning=tuning)
+        k = _lib.last_kernel()
+        if name is None:
+            default_name = k
+            # the default must be one of the fast affine variants, never the generic interpreter
+            assert k in ("k_resample_tex<affine>", "k_resample_pipe<affine>", "k_resample_rows<axis>"), k
+        else:
+            assert k == name, (tuning, k)
+        got = out[rows].cpu().numpy()
+        err, emax, emed = err_stats(got, want)
+        assert emax <= 1e-5, (n, tuning, k, emax, emed)
+        results[tuning] = out
+    # all variants round the fp32 fraction identically: bit-equal outputs (what sharding relies on)
+    import torch
+    for tuning, out in results.items():
+        assert torch.equal(out, results[0]), (tuning, default_name)
+
+
+@pytest.mark.parametrize("case", ["shift", "rot5", "rot45", "scale0p8", "scale2"])
+def test_linear_fp32_full_coverage_maps(tfm, oracle, case):
+    """The maps of bench.py's roofline breakdown (every source pixel is touched), 8192^2, default
+    dispatch and every opt-in variant, against the oracle on sampled rows."""
+    from transform_b200 import _lib
+    import torch
+    n = 8192
+    src = frame(n, 7)
+    tr = {"shift": tfm.Offset([3.25, -7.5]),
+          "rot5": tfm.Wrap(tfm.Rotation(5, unit='deg'), tfm.Offset([-n / 2.0, -n / 2.0])),
+          "rot45": tfm.Wrap(tfm.Rotation(45, unit='deg'), tfm.Offset([-n / 2.0, -n / 2.0])),
+          "scale0p8": tfm.Scale(0.8, dim=2), "scale2": tfm.Scale(2.0, dim=2)}[case]
+    rows = sample_rows(n, 64)
+    want = oracle_rows(oracle, to_oracle(tr), src.cpu().numpy(), rows, method='linear')
+    ref = None
+    for tuning in (0, 16, 128, 256):
+        out = tr.resample(src, method='linear', precision='fp32', tuning=tuning)
+        k = _lib.last_kernel()
+        err, emax, emed = err_stats(out[rows].cpu().numpy(), want)
+        assert emax <= 1e-5, (case, tuning, k, emax)
+        if ref is None:
+            ref = out
+        else:
+            assert torch.equal(out, ref), (case, tuning, k)
+
+
+def test_nearest_fp32_config2(tfm, oracle):
+    """BASELINE config 2, nearest: indices bit-exact.  In the fast path the host pre-composes the
+    affine chain, which can move a coordinate by an ulp: a mismatch is legal only where the
+    reference's coordinate sits within 1e-9 of a half-integer tie."""
+    n = 4096
+    src = frame(n, 7)
+    tr = named_chain(tfm, n)
+    rows = sample_rows(n)
+    otr = to_oracle(tr)
+    srcn = src.cpu().numpy()
+    want = oracle_rows(oracle, otr, srcn, rows, method='nearest')
+    got = tr.resample(src, method='nearest', precision='fp32')[rows].cpu().numpy()
+    bad = np.argwhere(got != want)
+    for (ri, x) in bad[:50]:
+        c = otr.reverse(np.array([[float(x), float(rows[ri])]]))[0]
+        frac = np.abs((c + 0.5) - np.round(c + 0.5))
+        assert frac.min() < 1e-9, (rows[ri], x, c)
+    assert len(bad) <= 4, len(bad)
+    # parity mode: bit-exact everywhere
+    exact = tr.resample(src, method='nearest')[rows].cpu().numpy()
+    assert np.array_equal(exact, want)
+
+
+# --------------------------------------------------------------------------------------------------
+# parity mode (fp64) at full size
+# --------------------------------------------------------------------------------------------------
+def test_parity_mode_8192(tfm, oracle):
+    """precision='fp64' at 8192^2: linear through the affine chain is bit-exact; linear through the
+    polar chain holds 1e-12 relative (libm last bits); the Jacobian-Gaussian holds 1e-11."""
+    from transform_b200 import _lib
+    n = 8192
+    src = frame(n, 1000)
+    srcn = src.cpu().numpy()
+    rows = sample_rows(n, 128)
+    tr = named_chain(tfm, n)
+    got = tr.resample(src, method='linear')
+    assert _lib.last_kernel() == "k_resample<trunc>"
+    want = oracle_rows(oracle, to_oracle(tr), srcn, rows, method='linear')
+    assert np.array_equal(got[rows].cpu().numpy(), want)
+    del got
+    rad = polar_chain(tfm, n)
+    got = rad.resample(src, method='linear')[rows].cpu().numpy()
+    want = oracle_rows(oracle, to_oracle(rad), srcn, rows, method='linear')
+    err, emax, emed = err_stats(got, want)
+    assert emax <= 1e-9, emax            # |coordinate| ~ 8e3 x 2 ulp of libm sincos = 4e-12 px x gradient <= 1
+    src64 = srcn.astype(np.float64)
+    rows_j = sample_rows(n, 24)
+    got = rad.resample(src, method='Gaussian')
+    assert _lib.last_kernel() == "k_jacobian<exact64>"
+    got = got[rows_j].cpu().numpy()
+    cap = 2 * int(np.ceil(0.25 * n))
+    want = np.stack([oracle.resample_jacobian(to_oracle(rad), src64, method='g', rows=(y, y + 1), max_reg=cap)[0]
+                     for y in rows_j])
+    err, emax, emed = err_stats(got, want)
+    # a handful of pixels sit on a ceil() boundary of the footprint size, where 2 ulp of sincos flip
+    # the window; everything else is 1e-11.  Magnitude cap: a flipped window changes a mean of
+    # uniform [0,1) samples by at most the weight of its outer ring (< 0.1)
+    assert emed <= 1e-13 and (err > 1e-10).sum() <= 8 and emax < 0.1, (emax, emed, (err > 1e-10).sum())
+
+
+# --------------------------------------------------------------------------------------------------
+# K2 Jacobian-Gaussian, fp32 fast path
+# --------------------------------------------------------------------------------------------------
+K2_TOL = 3e-4          # stated tolerance of the fp32 Jacobian method
+K2_CAP = 5e-2          # no sampled pixel may be off by more than this, whatever the reason
+
+
+def test_jacobian_fp32_polar_8192(tfm, oracle):
+    """bench step call 2: the analytic-polar variant of k_jacobian<fast32> at 8192^2 against the
+    oracle on sampled rows.  Stated tolerance 3e-4 absolute on uniform [0,1) data; pixels whose
+    footprint size (a ceil() of a function of J) lands on the other side of an integer boundary than
+    the oracle's are the only ones allowed above it: at most 0.05 % of the sampled pixels, and none
+    above K2_CAP."""
+    from transform_b200 import _lib
+    n = 8192
+    src = frame(n, 1000)
+    rad = polar_chain(tfm, n)
+    out = rad.resample(src, method='Gaussian', precision='fp32')
+    assert _lib.last_kernel() == "k_jacobian<fast32,analytic-polar>", _lib.last_kernel()
+    rows = sample_rows(n, 128)
+    src64 = src.cpu().numpy().astype(np.float64)
+    cap = 2 * int(np.ceil(0.25 * n))
+    otr = to_oracle(rad)
+    want = np.stack([oracle.resample_jacobian(otr, src64, method='g', rows=(y, y + 1), max_reg=cap)[0] for y in rows])
+    got = out[rows].cpu().numpy()
+    err, emax, emed = err_stats(got, want)
+    nbad = int((err > K2_TOL).sum())
+    assert emed < 2e-5 and nbad <= err.size // 2000 and emax <= K2_CAP, (emax, emed, nbad, err.size)
+    # the difference path of the same kernel (tuning bit 512) obeys the same bounds
+    fd = rad.resample(src, method='Gaussian', precision='fp32', tuning=512)
+    assert _lib.last_kernel() == "k_jacobian<fast32>", _lib.last_kernel()
+    err, emax, emed = err_stats(fd[rows].cpu().numpy(), want)
+    nbad = int((err > K2_TOL).sum())
+    assert emed < 2e-5 and nbad <= err.size // 2000 and emax <= K2_CAP, (emax, emed, nbad)
+
+
+def test_jacobian_fp32_affine_8192(tfm, oracle):
+    """The constant-Jacobian variant (anti-aliased down-scaling + rotation) at 8192^2, every staging
+    variant of it, against the oracle: 2e-5 everywhere (J is exact, no footprint-size flips)."""
+    from transform_b200 import _lib
+    import torch
+    n = 8192
+    src = frame(n, 5)
+    tr = tfm.Composition([tfm.Offset([n / 2.0 + 0.3, n / 2.0 - 0.2]), tfm.Scale([0.6, 0.7]),
+                          tfm.Rotation(25, unit='deg'), tfm.Offset([-n / 2.0, -n / 2.0])])
+    rows = sample_rows(n, 96)
+    src64 = src.cpu().numpy().astype(np.float64)
+    cap = 2 * int(np.ceil(0.25 * n))
+    otr = to_oracle(tr)
+    want = np.stack([oracle.resample_jacobian(otr, src64, method='g', rows=(y, y + 1), max_reg=cap)[0] for y in rows])
+    ref = None
+    for tuning in (0, 4096):
+        out = tr.resample(src, method='Gaussian', precision='fp32', tuning=tuning)
+        k = _lib.last_kernel()
+        assert k.startswith("k_jacobian<fast32,const-J"), k
+        err, emax, emed = err_stats(out[rows].cpu().numpy(), want)
+        assert emax <= 2e-5, (tuning, k, emax, emed)
+        if ref is None:
+            ref = out
+        else:
+            assert float((out - ref).abs().max()) <= 2e-6, (tuning, k)
+
+
+# --------------------------------------------------------------------------------------------------
+# K3 apply (config 5) on a slice of the full job
+# --------------------------------------------------------------------------------------------------
+def test_apply_config5_slices(tfm, oracle):
+    """BASELINE config 5's chains on 1e8 vectors (the 1e9 job is the same kernel looping longer):
+    three 1e6-vector slices -- head, middle, ragged tail -- bit-exact (affine) / 1e-11 (Radial)."""
+    import torch
+    from transform_b200 import _lib
+    nv = 10 ** 8 + 3
+    g = torch.Generator(device="cuda").manual_seed(2)
+    v = (torch.rand((nv, 2), generator=g, device="cuda", dtype=torch.float64) - 0.5) * 8192
+    aff = tfm.Composition([tfm.Scale([1.5, 2]), tfm.Rotation(30, unit='deg'), tfm.Offset([3, 4])]).inverse()
+    rad = tfm.Composition([tfm.Scale([1.5, 2]), tfm.Radial(origin=[0.1, 0.2]), tfm.Offset([3, 4])]).inverse()
+    sl = [slice(0, 10 ** 6), slice(nv // 2, nv // 2 + 10 ** 6), slice(nv - 10 ** 6 - 3, nv)]
+    for tr, exact in ((aff, True), (rad, False)):
+        out = tr.apply(v)
+        assert _lib.last_kernel().startswith("k_apply"), _lib.last_kernel()
+        for s in sl:
+            want = oracle.apply(to_oracle(tr), v[s].cpu().numpy())
+            got = out[s].cpu().numpy()
+            if exact:
+                assert np.array_equal(got, want)
+            else:
+                err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
+                assert float(err.max()) <= 1e-11, float(err.max())
+        del out

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Linear resampling at 8192^2 float32 through several affine maps, per kernel variant (GPU box).
-tuning 0 = auto (texture gather), 256 = TMA-staged shared-memory taps, 16 = plain LDG gather."""
+tuning 0 = auto, 128 = first texture-gather form, 256 = TMA-staged shared-memory taps (one box per CTA),
+16 = plain LDG gather."""
 import json
 import os
 import sys
@@ -25,7 +26,7 @@ peak = 6547.5
 res = {}
 for name, tr in maps.items():
     row = {}
-    for tun in (0, 256, 16):
+    for tun in (0, 128, 256, 16):
         f = lambda: tr.resample(src, method="linear", precision="fp32", out=dst, tuning=tun)
         f(); f(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -17,8 +17,8 @@ OUT_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(HERE, "_obj")
 OUT = os.path.join(OUT_DIR, "libtfm_b200.so")
 SOURCES = ["tfm_capi.cu", "tfm_resample.cu", "tfm_resample_exact_f32.cu", "tfm_resample_exact_f64.cu",
-           "tfm_resample_fast.cu", "tfm_apply.cu", "tfm_jacobian.cu", "tfm_fits.cu"]
-HEADERS = ["tfm_chain.cuh", "tfm_common.cuh", "tfm_resample.cuh", os.path.join("..", "..", "include", "tfm_b200.h")]
+           "tfm_resample_fast.cu", "tfm_apply.cu", "tfm_jacobian.cu", "tfm_jacobian_fast.cu", "tfm_fits.cu"]
+HEADERS = ["tfm_chain.cuh", "tfm_common.cuh", "tfm_resample.cuh", "tfm_jacobian_common.cuh", os.path.join("..", "..", "include", "tfm_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

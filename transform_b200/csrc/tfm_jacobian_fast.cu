@@ -1,0 +1,544 @@
+// tfm_jacobian_fast.cu -- K2, fast mode (fp32), Gaussian filter: the two lean kernels.
+//
+// Same algorithm as tfm_jacobian.cu (interpND_grid(..., antialias=True), helpers.pyx:1293-1530:
+// jacobian() + interpND_jacobian() with the Gaussian of helpers.pyx:1734-1735), for the two map
+// families whose Jacobian has a closed form, so that nothing of the reference's finite-difference
+// machinery (coordinate halo tile, cell differences, jump flags) has to exist:
+//   k_jac_gauss_const<HALF>   the whole chain is affine: J, the quadratic form of the Gaussian, the
+//                             footprint size and the recurrence constants are launch constants
+//   k_jac_gauss_polar         the chain is one fused polar op [affine, Radial^-1, affine] (the polar /
+//                             log-polar unwrap): coordinates and J per pixel from per-tile angle tables
+// Both are chosen by the HOST (jacobian_fast_dispatch): the conditions under which the closed form
+// stands for the reference's +-1-pixel central difference and under which jump_detect cannot flag a
+// cell are properties of the map and the output grid, not of a tile.
+//
+// Why a second translation unit: ncu on k_jacobian<Fast> (8192^2 polar unwrap, profiles/r2_k2.md)
+// showed 646 instructions per pixel at 61 % issue utilisation, of which only ~200 were footprint taps;
+// ~350 were per-pixel prologue (fp64 <-> fp32 conversions on the XU pipe, 64-bit index arithmetic,
+// paths for every filter / boundary / precision sharing one register allocation) and ~60 per-tile
+// tests executed by every thread.  Here every constant arrives as the type it is used in, indices
+// are 32-bit, floor/fraction is fixed point (floor_frac_fast), and pixels whose footprint is not
+// wholly inside the staged source take one out-of-line slow path.
+#include "tfm_jacobian_common.cuh"
+
+namespace tfm {
+
+constexpr int FT = 32;                      // output tile edge (256 threads, 4 pixels per thread)
+
+struct JacFastParams {
+    const float *src;
+    float *dst;
+    long long src_plane, dst_plane;          // elements between planes
+    int src_pe, dst_pe;                      // row pitch in elements
+    int src_h, src_w, src_x0, src_y0, full_h, full_w;
+    int dst_h, dst_w, dst_x0, dst_y0;
+    int grid_h, grid_w;                      // full output grid (edge rule of helpers.pyx:1244-1247)
+    int bound_x, bound_y;
+    int flux;                                // phot='flux': scale by |det J| (SVD.pyx:285-286)
+    int lw;                                  // log2 of the warp patch width
+    int max_half;                            // cap on the footprint half-width (max_reg / 2)
+    int *status;
+    float qscale;                            // log2(e) / oblur^2: exp(-q/oblur^2) = exp2(-q * qscale)
+    float ob;                                // oblur
+    float padval, half_pow, m2_over_pow;     // padding (helpers.pyx:1661-1662): pad_pow / 2, -2 / pad_pow
+    double oblur_d, padval_d, pad_pow_d;     // for the exact footprint-size decision
+    // ---- constant-Jacobian kernel ----
+    double aff[6];                           // source = A . grid + b
+    float Aq, Bq, Cq;                        // quadratic form, already times qscale
+    float cA, cB, cC;                        // exp2(-2 Aq), exp2(-2 Bq), exp2(-2 Cq)
+    float det;                               // |det A|
+    int half;
+    // ---- polar kernel ----
+    double pa[6];                            // A1 (row-major), b1: (theta arg, rho) = A1 . grid + b1
+    double coeff, r0, ox, oy;                // ang_coeff, r0 (log-polar), origin
+    double a2[6];                            // trailing affine map A2, b2
+    int ccw, lg, has_a2;
+    float tXf, tYf, p2f, p3f, a2f[4];
+};
+
+// ---------------------------------------------------------------------------------------------
+// footprint accumulation
+// ---------------------------------------------------------------------------------------------
+// (2*HALF+1)^2 Gaussian taps of a footprint wholly inside the staged source.  Weights by recurrence:
+// along a row w(a+1) = w(a) r(a), r(a+1) = r(a) cA; from row to row w0 *= rb, rb *= cC, r0 *= cB.
+// Rows are processed in PAIRS with Blackwell's packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2): lane
+// .x carries row j, lane .y row j+1, and the row-to-row state (first weights W, first ratios R, and the
+// two-row weight step RB2) is packed the same way -- a pair of taps costs 2 loads + 4 packed
+// instructions, a pair of rows 3 packed instructions of bookkeeping.  The odd last row is scalar.
+template <int HALF>
+__device__ __forceinline__ void gauss_taps2(const float *__restrict__ p0, int pe, float w0, float r0, float rb,
+                                            float cA, float cB, float cC, float &val, float &wgt)
+{
+    constexpr int N = 2 * HALF + 1;
+    const float2 cA2 = make_float2(cA, cA);
+    const float cC2 = cC * cC, cB2 = cB * cB;
+    const float2 CB2 = make_float2(cB2, cB2), C4 = make_float2(cC2 * cC2, cC2 * cC2);
+    const float rb1 = rb * cC;
+    float2 W = make_float2(w0, w0 * rb);                     // first weights of rows j, j+1
+    float2 R = make_float2(r0, r0 * cB);                     // first ratios of rows j, j+1
+    float2 RB2 = make_float2(rb * rb * cC, rb1 * rb1 * cC);  // w0(j+2) / w0(j), w0(j+3) / w0(j+1)
+    float2 val2 = make_float2(0.0f, 0.0f), wgt2 = make_float2(0.0f, 0.0f);
+#pragma unroll(HALF <= 2 ? HALF : 1)
+    for (int j = 0; j < HALF; ++j) {
+        const float *p = p0 + (2 * j) * pe, *q = p + pe;
+        float2 w = W, r = R;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const float2 v = make_float2(__ldg(p + k), __ldg(q + k));
+            val2 = __ffma2_rn(v, w, val2);
+            wgt2 = __fadd2_rn(wgt2, w);
+            w = __fmul2_rn(w, r);
+            r = __fmul2_rn(r, cA2);
+        }
+        W = __fmul2_rn(W, RB2);
+        RB2 = __fmul2_rn(RB2, C4);
+        R = __fmul2_rn(R, CB2);
+    }
+    {   // last (odd) row: its first weight and ratio are lane .x of the advanced state
+        const float *p = p0 + (2 * HALF) * pe;
+        float w = W.x, r = R.x;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            val = fmaf(__ldg(p + k), w, val);
+            wgt += w;
+            w *= r;
+            r *= cA;
+        }
+    }
+    val += val2.x + val2.y;
+    wgt += wgt2.x + wgt2.y;
+}
+
+__device__ __forceinline__ void gauss_taps_any(int half, const float *p0, int pe, float w0, float r0, float rb,
+                                               float cA, float cB, float cC, float &val, float &wgt)
+{
+    switch (half) {
+    case 1: gauss_taps2<1>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+    case 2: gauss_taps2<2>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+    case 3: gauss_taps2<3>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+    case 4: gauss_taps2<4>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+    case 5: gauss_taps2<5>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+    default: gauss_taps2<6>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+    }
+}
+
+// Out-of-line path for the pixels the recurrence cannot serve: footprint crossing an image (or staged
+// rectangle) edge, half-width 0 or > 6, weights too small for the recurrence, absurd coordinates.
+// The reference's loop as coded (helpers.pyx:1678-1800, repairs R7/R9): a truncated tap adds its
+// weight but not its value; 'forbid' raises.  One exp2 per tap.
+__device__ __noinline__ void gauss_slow(const JacFastParams &P, const float *src_base, double px, double py,
+                                        float Aq, float Bq, float Cq, int half, float &val, float &wgt, int &state)
+{
+    const double fxs = floor(px), fys = floor(py);
+    const long long xs = (long long)fxs, ys = (long long)fys;
+    const float xf_of = (float)(px - fxs), yf_of = (float)(py - fys);
+    val = 0.0f;
+    wgt = 0.0f;
+    for (int yr = -half; yr <= half; ++yr) {
+        const float y0 = (float)yr + yf_of;
+        int sty = 0;
+        const int iy0 = jbound(ys + yr, P.full_h, P.bound_y, sty);
+        for (int xr = -half; xr <= half; ++xr) {
+            const float x0 = (float)xr + xf_of;
+            const float filt = fast_ex2(-((Aq * x0 + 2.0f * Bq * y0) * x0 + Cq * y0 * y0));
+            wgt += filt;
+            int st = sty;
+            int ix = jbound(xs + xr, P.full_w, P.bound_x, st);
+            state |= st & 2;
+            if (st == 0) {
+                ix -= P.src_x0;
+                const int iy = iy0 - P.src_y0;
+                if ((unsigned)ix < (unsigned)P.src_w && (unsigned)iy < (unsigned)P.src_h)
+                    val = fmaf(__ldg(src_base + (long long)iy * P.src_pe + ix), filt, val);
+                else
+                    state |= 4;
+            }
+        }
+    }
+}
+
+// The footprint half-width is ceil(oblur / smin'): when fp32 cannot decide the ceil(), that one number
+// is redone in fp64 from the same Jacobian with the reference's own SVD and padding formulas.
+__device__ __noinline__ float exact_half_ratio(const JacFastParams &P, float j00, float j01, float j10, float j11)
+{
+    const double Ji[4] = {(double)j00, (double)j01, (double)j10, (double)j11};
+    double U[4], V[4], sd[2];
+    svd2x2_dev(Ji, U, sd, V);
+    const double s0 = exp(-log(P.padval_d + exp(log(sd[0]) * P.pad_pow_d)) / P.pad_pow_d);
+    const double s1 = exp(-log(P.padval_d + exp(log(sd[1]) * P.pad_pow_d)) / P.pad_pow_d);
+    return (float)ceil(P.oblur_d / fmin(s0, s1));
+}
+
+// fp32 twin of gaussian_quadratic_f32 (tfm_jacobian_common.cuh) taking the Jacobian as floats
+__device__ __forceinline__ void gaussian_quadratic(float a, float b, float c, float d, float padval, float half_pow,
+                                                   float m2p, float &q00, float &q01, float &q11, float &inv_smin)
+{
+    const float g00 = a * a + b * b, g01 = a * c + b * d, g11 = c * c + d * d;
+    const float mean = 0.5f * (g00 + g11), dif = 0.5f * (g00 - g11);
+    const float r2 = dif * dif + g01 * g01;
+    const float rad = (r2 > 0.0f) ? r2 * fast_rsqrt(r2) : 0.0f;
+    const float lp = mean + rad, lm = fmaxf(mean - rad, 0.0f);
+    const float fp = pad_inv_sq(lp, padval, half_pow, m2p), fm = pad_inv_sq(lm, padval, half_pow, m2p);
+    const float dl = lp - lm;
+    const float beta = (dl > 0.0f) ? (fp - fm) * fast_rcp(dl) : 0.0f;
+    q00 = fp - beta * (rad - dif);
+    q01 = beta * g01;
+    q11 = fp - beta * (rad + dif);
+    inv_smin = fast_rsqrt(fp);
+}
+
+// One pixel, given its source position, the (scaled) quadratic form and the footprint half-width.
+// Returns val / wgt (0 when the footprint carries no weight or lies wholly beyond a truncated edge).
+template <int HALF_CT>     // > 0: compile-time half-width (constant-Jacobian kernel); 0: run time
+__device__ __forceinline__ float gauss_pixel(const JacFastParams &P, const float *__restrict__ src_base, double px, double py,
+                                             float Aq, float Bq, float Cq, float cA, float cB, float cC, int half_rt,
+                                             int &state)
+{
+    const int half = HALF_CT > 0 ? HALF_CT : half_rt;
+    float val = 0.0f, wgt = 0.0f;
+    const bool sane = (fabs(px) < TFM_SANE_COORD) && (fabs(py) < TFM_SANE_COORD);
+    if (!sane) {
+        if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) return 0.0f;      // NaN / inf (as tfm_jacobian.cu)
+        gauss_slow(P, src_base, px, py, Aq, Bq, Cq, half, val, wgt, state);
+        return (wgt > 0.0f) ? val * fast_rcp(wgt) : 0.0f;
+    }
+    int xi, yi;
+    float xf, yf;
+    floor_frac_fast(px, xi, xf);
+    floor_frac_fast(py, yi, yf);
+    // a footprint entirely beyond a truncated edge: every tap is skipped, the pixel is 0 whatever the
+    // weights are (helpers.pyx:1793-1800)
+    if ((P.bound_x == TFM_B_TRUNCATE && (xi + half < 0 || xi - half >= P.full_w)) ||
+        (P.bound_y == TFM_B_TRUNCATE && (yi + half < 0 || yi - half >= P.full_h)))
+        return 0.0f;
+    const int limx = P.src_w - 2 * half, limy = P.src_h - 2 * half;
+    const int ox = xi - half - P.src_x0, oy = yi - half - P.src_y0;
+    const bool inside = limx > 0 && limy > 0 && (unsigned)ox < (unsigned)limx && (unsigned)oy < (unsigned)limy;
+    const float hf = (float)half;
+    const float h2 = (hf + 1.0f) * (hf + 1.0f);
+    if (inside && half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * h2 < 100.0f) {
+        const float a0 = xf - hf, b0 = yf - hf;
+        const float w0 = fast_ex2(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
+        const float r0 = fast_ex2(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
+        const float rb = fast_ex2(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
+        const float *p0 = src_base + (oy * P.src_pe + ox);
+        if (HALF_CT > 0) gauss_taps2<(HALF_CT > 0 ? HALF_CT : 1)>(p0, P.src_pe, w0, r0, rb, cA, cB, cC, val, wgt);
+        else gauss_taps_any(half, p0, P.src_pe, w0, r0, rb, cA, cB, cC, val, wgt);
+    } else {
+        gauss_slow(P, src_base, px, py, Aq, Bq, Cq, half, val, wgt, state);
+    }
+    return (wgt > 0.0f) ? val * fast_rcp(wgt) : 0.0f;
+}
+
+// thread -> pixel map of a 32 x 32 tile: a warp covers a (1 << lw) x (32 >> lw) patch, repeated 4 times
+// 8 rows apart, so that the 32 footprints one tap load gathers from sit in a compact source patch
+__device__ __forceinline__ void patch_xy(int lw, int tid, int &tx, int &ty)
+{
+    const int lane = tid & 31, wrp = tid >> 5;
+    tx = ((wrp & ((32 >> lw) - 1)) << lw) + (lane & ((1 << lw) - 1));
+    ty = (wrp >> (5 - lw)) * (32 >> lw) + (lane >> lw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// constant-Jacobian kernel
+// ---------------------------------------------------------------------------------------------
+template <int HALF>
+__global__ void __launch_bounds__(256, 4)
+k_jac_gauss_const(const __grid_constant__ JacFastParams P)
+{
+    const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
+    float *const dst_base = P.dst + (long long)blockIdx.z * P.dst_plane;
+    int tx, ty;
+    patch_xy(P.lw, threadIdx.x, tx, ty);
+    const int X = blockIdx.x * FT + tx;
+    if (X >= P.dst_w) return;
+    const int Y0 = blockIdx.y * FT + ty;
+    const double gxd = (double)(P.dst_x0 + X);
+    double gyd = (double)(P.dst_y0 + Y0);
+    int state = 0;
+    float *drow = dst_base + (long long)Y0 * P.dst_pe + X;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        if (Y0 + 8 * j >= P.dst_h) break;
+        const double px = fma(P.aff[0], gxd, fma(P.aff[1], gyd, P.aff[4]));
+        const double py = fma(P.aff[2], gxd, fma(P.aff[3], gyd, P.aff[5]));
+        float res = gauss_pixel<HALF>(P, src_base, px, py, P.Aq, P.Bq, P.Cq, P.cA, P.cB, P.cC, P.half, state);
+        if (P.flux) res *= P.det;
+        *drow = res;
+        drow += 8 * P.dst_pe;
+        gyd += 8.0;
+    }
+    if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// analytic polar kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4)
+k_jac_gauss_polar(const __grid_constant__ JacFastParams P)
+{
+    constexpr int TN = FT + 2;              // table entries: grid points G0-1 .. G0+FT (edge-copy clamp reach)
+    __shared__ double2 s_ta[TN], s_tb[TN];  // (cos, sin)(i tX), (cos, sin)(theta(X0, Y0) + j tY)
+    __shared__ double s_ea[TN], s_eb[TN];   // log-polar: exp(i a10), r0 exp(rho(X0, Y0) + j a11)
+    __shared__ float2 s_taf[TN], s_tbf[TN]; // fp32 copies for the Jacobian
+    __shared__ float s_eaf[TN], s_ebf[TN];
+
+    const int tid = threadIdx.x;
+    const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
+    float *const dst_base = P.dst + (long long)blockIdx.z * P.dst_plane;
+    const int GX0 = P.dst_x0 + (int)blockIdx.x * FT, GY0 = P.dst_y0 + (int)blockIdx.y * FT;
+    const double X0 = (double)(GX0 - 1), Y0d = (double)(GY0 - 1);
+    const bool lg = P.lg != 0;
+    if (tid < 2 * TN) {
+        // same formulas as polar_tables (tfm_chain.cuh)
+        const double tX = P.pa[0] * P.coeff, tY = P.pa[1] * P.coeff;
+        double s, c;
+        if (tid < TN) {
+            sincos((double)tid * tX, &s, &c);
+            s_ta[tid] = make_double2(c, s);
+            s_taf[tid] = make_float2((float)c, (float)s);
+            if (lg) { const double e = exp((double)tid * P.pa[2]); s_ea[tid] = e; s_eaf[tid] = (float)e; }
+        } else {
+            const int j = tid - TN;
+            const double t0 = fma(P.pa[0], X0, fma(P.pa[1], Y0d, P.pa[4])) * P.coeff;
+            sincos(fma((double)j, tY, t0), &s, &c);
+            s_tb[j] = make_double2(c, s);
+            s_tbf[j] = make_float2((float)c, (float)s);
+            if (lg) {
+                const double rho0 = fma(P.pa[2], X0, fma(P.pa[3], Y0d, P.pa[5]));
+                const double e = P.r0 * exp(fma((double)j, P.pa[3], rho0));
+                s_eb[j] = e; s_ebf[j] = (float)e;
+            }
+        }
+    }
+    __syncthreads();
+
+    int tx, ty;
+    patch_xy(P.lw, tid, tx, ty);
+    const int X = blockIdx.x * FT + tx;
+    if (X >= P.dst_w) return;
+    const int Yt = blockIdx.y * FT + ty;
+    const int gx = P.dst_x0 + X;
+    const int GW = P.grid_w, GH = P.grid_h;
+    // Jacobian column of this thread: edge columns copy their inner neighbour (helpers.pyx:1244-1247)
+    const int jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
+    const int cti = jx - (GX0 - 1);
+    const double2 ta = s_ta[tx + 1];
+    const float2 taf = s_taf[cti];
+    const double gxd = (double)gx;
+    double gyd = (double)(P.dst_y0 + Yt);
+    const float sgn = P.ccw ? 1.0f : -1.0f;
+    // radius (linear form) at the table origin, fp32, for the Jacobian
+    const float rb32 = (float)fma(P.pa[2], X0, fma(P.pa[3], Y0d, P.pa[5]));
+    const float rcol32 = fmaf(P.p2f, (float)cti, rb32);
+    int state = 0;
+    float *drow = dst_base + (long long)Yt * P.dst_pe + X;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int ly = ty + 8 * j;
+        if (Yt + 8 * j >= P.dst_h) break;
+        const int gy = P.dst_y0 + Yt + 8 * j;
+        // ---- source position (fp64): cos/sin by angle addition from the tables ----
+        const double2 tb = s_tb[ly + 1];
+        const double c = ta.x * tb.x - ta.y * tb.y, s = ta.y * tb.x + ta.x * tb.y;
+        const double r = lg ? s_ea[tx + 1] * s_eb[ly + 1] : fma(P.pa[2], gxd, fma(P.pa[3], gyd, P.pa[5]));
+        const double x1 = fma(c, r, P.ox), y1 = fma(P.ccw ? s : -s, r, P.oy);
+        double px = x1, py = y1;
+        if (P.has_a2) {
+            px = fma(P.a2[0], x1, fma(P.a2[1], y1, P.a2[4]));
+            py = fma(P.a2[2], x1, fma(P.a2[3], y1, P.a2[5]));
+        }
+        // ---- closed-form Jacobian at the (edge-clamped) grid point, fp32 ----
+        const int jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
+        const int ctj = jy - (GY0 - 1);
+        const float2 tbf = s_tbf[ctj];
+        const float cf = taf.x * tbf.x - taf.y * tbf.y, sf = taf.y * tbf.x + taf.x * tbf.y;
+        const float rf = lg ? s_eaf[cti] * s_ebf[ctj] : fmaf(P.p3f, (float)ctj, rcol32);
+        const float drX = lg ? rf * P.p2f : P.p2f, drY = lg ? rf * P.p3f : P.p3f;
+        const float rs = rf * sf, rc = rf * cf;
+        // x1 = r cos + ox, y1 = sgn r sin + oy
+        float j00 = fmaf(cf, drX, -rs * P.tXf), j01 = fmaf(cf, drY, -rs * P.tYf);
+        float j10 = sgn * fmaf(sf, drX, rc * P.tXf), j11 = sgn * fmaf(sf, drY, rc * P.tYf);
+        if (P.has_a2) {
+            const float k00 = P.a2f[0] * j00 + P.a2f[1] * j10, k01 = P.a2f[0] * j01 + P.a2f[1] * j11;
+            const float k10 = P.a2f[2] * j00 + P.a2f[3] * j10, k11 = P.a2f[2] * j01 + P.a2f[3] * j11;
+            j00 = k00; j01 = k01; j10 = k10; j11 = k11;
+        }
+        // ---- padded quadratic form and footprint size ----
+        float q00, q01, q11, inv_smin;
+        gaussian_quadratic(j00, j01, j10, j11, P.padval, P.half_pow, P.m2_over_pow, q00, q01, q11, inv_smin);
+        float ratio = P.ob * inv_smin;
+        if (fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) ratio = exact_half_ratio(P, j00, j01, j10, j11);
+        int half = (ratio < 1.0e9f) ? __float2int_ru(ratio) : 1000000000;
+        half = min(half, P.max_half);
+        const float Aq = q00 * P.qscale, Bq = q01 * P.qscale, Cq = q11 * P.qscale;
+        const float cA = fast_ex2(-2.0f * Aq), cB = fast_ex2(-2.0f * Bq), cC = fast_ex2(-2.0f * Cq);
+        float res = gauss_pixel<0>(P, src_base, px, py, Aq, Bq, Cq, cA, cB, cC, half, state);
+        if (P.flux) res *= fabsf(j00 * j11 - j01 * j10);
+        *drow = res;
+        drow += 8 * P.dst_pe;
+        gyd += 8.0;
+    }
+    if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+// Largest ratio max|J|^2 / min|J|^2 any (FT+4)^2 neighbourhood of grid points can show for the polar
+// map, from the closed form |J|^2 = g2 + t2 v^2 (x v^2-free exp form for log-polar), v = radius
+// argument, affine in the grid indices: f(w) = (g2 + t2 (w + D)^2) / (g2 + t2 w^2) over the |v| the
+// output region contains, D = the span of v across one neighbourhood.  f rises to
+// w* = (-D + sqrt(D^2 + 4 g2 / t2)) / 2 and falls after it.
+static double polar_jump_ratio_bound(const tfm_op &op, const tfm_image &d)
+{
+    const double coeff = op.p[6];
+    const double t2 = (op.p[0] * op.p[0] + op.p[1] * op.p[1]) * coeff * coeff;
+    const double g2 = op.p[2] * op.p[2] + op.p[3] * op.p[3];
+    const bool lg = (op.flags & TFM_RAD_R0_NOT_NONE) != 0;
+    const double D = (FT + 3) * (fabs(op.p[2]) + fabs(op.p[3]));
+    double ratio;
+    if (lg) {
+        ratio = exp(2.0 * D);
+    } else {
+        const double xa = (double)d.x0 - 2.0, xb = (double)(d.x0 + d.w) + 1.0;
+        const double ya = (double)d.y0 - 2.0, yb = (double)(d.y0 + d.h) + 1.0;
+        const double v[4] = {op.p[2] * xa + op.p[3] * ya + op.p[5], op.p[2] * xb + op.p[3] * ya + op.p[5],
+                             op.p[2] * xa + op.p[3] * yb + op.p[5], op.p[2] * xb + op.p[3] * yb + op.p[5]};
+        double vmin = v[0], vmax = v[0];
+        for (int k = 1; k < 4; ++k) { vmin = fmin(vmin, v[k]); vmax = fmax(vmax, v[k]); }
+        const double wmax = fmax(fabs(vmin), fabs(vmax));
+        const double wmin = (vmin <= 0.0 && vmax >= 0.0) ? 0.0 : fmin(fabs(vmin), fabs(vmax));
+        if (!(g2 > 0.0)) return INFINITY;
+        if (!(t2 > 0.0)) ratio = 1.0;
+        else {
+            double w = 0.5 * (-D + sqrt(D * D + 4.0 * g2 / t2));
+            w = fmin(fmax(w, wmin), wmax);
+            ratio = (g2 + t2 * (w + D) * (w + D)) / (g2 + t2 * w * w);
+        }
+    }
+    if (op.flags & TFM_POLAR_HAS_A2) {
+        const double E = op.p[10] * op.p[10] + op.p[11] * op.p[11] + op.p[12] * op.p[12] + op.p[13] * op.p[13];
+        const double det = op.p[10] * op.p[13] - op.p[11] * op.p[12];
+        const double q = sqrt(fmax(E * E - 4.0 * det * det, 0.0));
+        ratio *= (E + q) / (E - q);
+    }
+    return ratio;
+}
+
+// Returns 1 when one of the lean kernels was launched (status in *rc), 0 when the call is outside
+// their scope and the general kernel must take it.
+int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
+{
+    const tfm_image &s = a->src, &d = a->dst;
+    if (a->precision != TFM_PREC_FAST32 || a->filter != TFM_FILT_GAUSSIAN) return 0;
+    if (s.dtype != TFM_F32 || d.dtype != TFM_F32) return 0;
+    if (a->tuning & (512 | 8 | 32 | 8192)) return 0;              // A/B switches of the general kernel
+    if ((s.pitch % 4) || (d.pitch % 4) || (s.plane_pitch % 4) || (d.plane_pitch % 4)) return 0;
+    if (s.pitch / 4 > 0x3fffffff || d.pitch / 4 > 0x3fffffff || s.h * (s.pitch / 4) >= 0x7fffffffLL) return 0;
+
+    JacFastParams P;
+    memset(&P, 0, sizeof(P));
+    P.src = static_cast<const float *>(s.data); P.dst = static_cast<float *>(d.data);
+    P.src_plane = s.plane_pitch / 4; P.dst_plane = d.plane_pitch / 4;
+    P.src_pe = (int)(s.pitch / 4); P.dst_pe = (int)(d.pitch / 4);
+    P.src_h = (int)s.h; P.src_w = (int)s.w; P.src_x0 = (int)s.x0; P.src_y0 = (int)s.y0;
+    P.full_h = (int)s.full_h; P.full_w = (int)s.full_w;
+    P.dst_h = (int)d.h; P.dst_w = (int)d.w; P.dst_x0 = (int)d.x0; P.dst_y0 = (int)d.y0;
+    P.grid_h = (int)d.full_h; P.grid_w = (int)d.full_w;
+    P.bound_x = a->bound_x; P.bound_y = a->bound_y;
+    P.flux = (a->flags & TFM_F_FLUX) ? 1 : 0;
+    P.status = a->status_dev;
+    P.max_half = (a->max_reg > 0 && a->max_reg / 2 < 0x3fffffff) ? (int)(a->max_reg / 2) : 0x3fffffff;
+    const double padval = 3.0;                                  // Gaussian (helpers.pyx:1612-1615)
+    P.qscale = (float)(1.4426950408889634 / (a->oblur * a->oblur));
+    P.ob = (float)a->oblur;
+    P.padval = (float)padval; P.half_pow = (float)(0.5 * a->pad_pow); P.m2_over_pow = (float)(-2.0 / a->pad_pow);
+    P.oblur_d = a->oblur; P.padval_d = padval; P.pad_pow_d = a->pad_pow;
+
+    dim3 grid((unsigned)((P.dst_w + FT - 1) / FT), (unsigned)((P.dst_h + FT - 1) / FT), (unsigned)s.n_planes);
+    if (grid.y > 65535u) return 0;
+
+    bool lin = true;
+    for (int i = 0; i < a->n_ops; ++i) lin = lin && is_linear_like(a->chain[i]);
+    if (lin) {
+        // constant-Jacobian kernel: a constant |J|^2 cannot be flagged by jump_detect when the threshold
+        // exceeds 1 (ratio of neighbouring cells is 1 up to rounding)
+        if (!(a->jump_thresh == 0.0 || a->jump_thresh >= 1.001)) return 0;
+        compose_linear_run(a->chain, 0, a->n_ops, P.aff, P.aff + 4);
+        const double ja = P.aff[0], jb = P.aff[1], jc = P.aff[2], jd = P.aff[3];
+        // Q = f(J J^T), f(lambda) = (padval + lambda^(p/2))^(-2/p): the fp64 twin of gaussian_quadratic
+        const double g00 = ja * ja + jb * jb, g01 = ja * jc + jb * jd, g11 = jc * jc + jd * jd;
+        const double mean = 0.5 * (g00 + g11), dif = 0.5 * (g00 - g11);
+        const double rad = sqrt(dif * dif + g01 * g01);
+        const double lp = mean + rad, lm = fmax(mean - rad, 0.0);
+        auto f = [&](double lam) { return pow(padval + pow(lam, 0.5 * a->pad_pow), -2.0 / a->pad_pow); };
+        const double fp = f(lp), fm = f(lm);
+        const double beta = (lp - lm > 0.0) ? (fp - fm) / (lp - lm) : 0.0;
+        const double q00 = fp - beta * (rad - dif), q01 = beta * g01, q11 = fp - beta * (rad + dif);
+        double reg = 2.0 * ceil(a->oblur / sqrt(fp));            // helpers.pyx:1666
+        if (a->max_reg > 0 && reg > (double)a->max_reg) reg = (double)a->max_reg;
+        if (!(isfinite(q00) && isfinite(q01) && isfinite(q11) && isfinite(reg) && reg >= 0.0 && reg < 2.0e9 &&
+              isfinite(P.aff[4]) && isfinite(P.aff[5])))
+            return 0;
+        const double sc = 1.4426950408889634 / (a->oblur * a->oblur);
+        P.half = (int)(reg / 2.0);
+        P.Aq = (float)(q00 * sc); P.Bq = (float)(q01 * sc); P.Cq = (float)(q11 * sc);
+        P.cA = (float)exp2(-2.0 * q00 * sc); P.cB = (float)exp2(-2.0 * q01 * sc); P.cC = (float)exp2(-2.0 * q11 * sc);
+        P.det = (float)fabs(ja * jd - jb * jc);
+        P.lw = 4;
+        if (a->tuning & 1024) P.lw = 5;
+        if (a->tuning & 2048) P.lw = 3;
+        switch (P.half) {
+        case 1: k_jac_gauss_const<1><<<grid, 256, 0, st>>>(P); break;
+        case 2: k_jac_gauss_const<2><<<grid, 256, 0, st>>>(P); break;
+        case 3: k_jac_gauss_const<3><<<grid, 256, 0, st>>>(P); break;
+        case 4: k_jac_gauss_const<4><<<grid, 256, 0, st>>>(P); break;
+        case 5: k_jac_gauss_const<5><<<grid, 256, 0, st>>>(P); break;
+        case 6: k_jac_gauss_const<6><<<grid, 256, 0, st>>>(P); break;
+        default: k_jac_gauss_const<0><<<grid, 256, 0, st>>>(P); break;   // every pixel takes the slow path
+        }
+        count_launch();
+        set_last_kernel("k_jacobian<fast32,const-J>");
+        *rc = cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
+        return 1;
+    }
+
+    tfm_op fused[TFM_MAX_OPS];
+    const int nf = fuse_chain_fast(a->chain, a->n_ops, fused);
+    if (nf != 1 || fused[0].kind != TFM_OP_POLAR) return 0;
+    const tfm_op &op = fused[0];
+    {
+        // The reference's Jacobian is a +-1-pixel central difference; against the derivative it is off by
+        // O(step^2) of the angle (and log-radius) step: closed form only when those are < 1e-2
+        const double coeff = op.p[6];
+        const double t2 = (op.p[0] * op.p[0] + op.p[1] * op.p[1]) * coeff * coeff;
+        const double g2 = op.p[2] * op.p[2] + op.p[3] * op.p[3];
+        const bool lg = (op.flags & TFM_RAD_R0_NOT_NONE) != 0;
+        if (!(t2 < 1.0e-4) || (lg && !(g2 < 1.0e-4))) return 0;
+        if (a->jump_thresh != 0.0) {
+            const double ratio = polar_jump_ratio_bound(op, d);
+            if (!(a->jump_thresh > 0.0) || !(ratio * 1.01 <= a->jump_thresh)) return 0;   // NaN compares false
+        }
+    }
+    for (int k = 0; k < 6; ++k) P.pa[k] = op.p[k];
+    P.coeff = op.p[6]; P.r0 = op.p[7]; P.ox = op.p[8]; P.oy = op.p[9];
+    P.a2[0] = op.p[10]; P.a2[1] = op.p[11]; P.a2[2] = op.p[12]; P.a2[3] = op.p[13]; P.a2[4] = op.p[14]; P.a2[5] = op.p[15];
+    P.ccw = (op.flags & TFM_RAD_CCW) ? 1 : 0;
+    P.lg = (op.flags & TFM_RAD_R0_NOT_NONE) ? 1 : 0;
+    P.has_a2 = (op.flags & TFM_POLAR_HAS_A2) ? 1 : 0;
+    P.tXf = (float)(op.p[0] * op.p[6]); P.tYf = (float)(op.p[1] * op.p[6]);
+    P.p2f = (float)op.p[2]; P.p3f = (float)op.p[3];
+    for (int k = 0; k < 4; ++k) P.a2f[k] = (float)op.p[10 + k];
+    P.lw = 3;
+    if (a->tuning & 1024) P.lw = 5;
+    if (a->tuning & 2048) P.lw = 2;
+    if (a->tuning & 16384) P.lw = 4;
+    k_jac_gauss_polar<<<grid, 256, 0, st>>>(P);
+    count_launch();
+    set_last_kernel("k_jacobian<fast32,analytic-polar>");
+    *rc = cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
+    return 1;
+}
+
+}  // namespace tfm

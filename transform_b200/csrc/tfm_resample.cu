@@ -107,7 +107,7 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
         // NaN / inf / absurd coordinate -> far outside the texture (border = 0); the compare is only
         // needed when the host could not bound the coordinates
         if (!(AFF && P.aff_bounded)) {
-            if (!((fabs(cx[j]) < 1.0e9) && (fabs(cy[j]) < 1.0e9))) { ix = -100000; iy = -100000; fx[j] = 0.f; fy[j] = 0.f; }
+            if (!((fabs(cx[j]) < TFM_SANE_COORD) && (fabs(cy[j]) < TFM_SANE_COORD))) { ix = -100000; iy = -100000; fx[j] = 0.f; fy[j] = 0.f; }
         }
         // unnormalised coordinates: the bilinear footprint of (u,v) is texels floor(u-0.5)+{0,1},
         // so (ix+1, iy+1) selects columns ix, ix+1 and rows iy, iy+1
@@ -122,6 +122,108 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
         const float top = fmaf(fx[j], v01 - v00, v00);
         const float bot = fmaf(fx[j], v11 - v10, v10);
         reinterpret_cast<float *>(dst_base + (long long)Y * P.dst_pitch)[X] = fmaf(fy[j], bot - top, top);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// texture-gather variant, second form: 4 CONSECUTIVE output pixels per thread, one 16-byte store
+// ---------------------------------------------------------------------------------------------
+// ncu on k_resample_tex (8192^2, pure shift, profiles/r2_k1.md): 60.8 instructions per pixel at 83 %
+// issue utilisation -- the kernel was issue-bound before it was texture-bound.  Of the 60.8, 16 were
+// the per-thread share of the empty-tile test, 14 the four scalar stores with their bounds checks and
+// 64-bit address arithmetic, 20 the two floor/fraction extractions.  Here:
+//   * a thread owns pixels (X .. X+3, Y): coordinates advance by one DFMA per axis, the four results
+//     leave in ONE st.global.v4 (a warp writes four full 128-byte rows segments);
+//   * a warp covers a 32 x 4 patch (8 lanes x 4 pixels wide), so the footprints of one TLD4 stay as
+//     compact as with the 16 x 2 patch of the first form;
+//   * the empty-tile test works from the tile centre and a host-computed half-extent (10 instructions);
+//   * floor/fraction in fixed point (floor_frac_fast).
+template <class A, bool AFF, int SPH>
+__global__ void __launch_bounds__(256)
+k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = (lane & 7) << 2;
+    const int py = (warp << 2) + (lane >> 3);
+    const int X = blockIdx.x * 32 + px;
+    const int Y = blockIdx.y * 32 + py;
+    float *const drow = reinterpret_cast<float *>(static_cast<char *>(P.dst) + (long long)Y * P.dst_pitch) + X;
+    const bool row_in = Y < P.dst_h;
+    const bool vec = row_in && (X + 3 < P.dst_w) && P.dst_vec4;
+
+    // AFF instantiations are launched only when the host has bounded the coordinates (P.aff_bounded)
+    if (AFF) {                             // CTA-uniform rejection of empty tiles: centre +- half-extent
+        const float xc = (float)(int)(blockIdx.x * 32) + P.aff_f[6], yc = (float)(int)(blockIdx.y * 32) + P.aff_f[7];
+        const float cxc = fmaf(P.aff_f[0], xc, fmaf(P.aff_f[1], yc, P.aff_c[0]));
+        const float cyc = fmaf(P.aff_f[2], xc, fmaf(P.aff_f[3], yc, P.aff_c[1]));
+        if (cxc < -P.aff_c[2] || cxc > P.aff_lim[0] || cyc < -P.aff_c[3] || cyc > P.aff_lim[1]) {
+            if (vec) *reinterpret_cast<float4 *>(drow) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else if (row_in) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (X + j < P.dst_w) drow[j] = 0.0f;
+            }
+            return;
+        }
+    }
+
+    double cx[4], cy[4];
+    if (AFF) {
+        const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y);
+        cx[0] = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
+        cy[0] = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            cx[j] = fma((double)j, P.aff[0], cx[0]);
+            cy[j] = fma((double)j, P.aff[2], cy[0]);
+        }
+    } else if (P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_POLAR) {
+        __shared__ double2 s_ta[32], s_tb[32];
+        __shared__ double s_ea[32], s_eb[32];
+        const tfm_op &op0 = P.chain.ops[0];
+        const double TX0 = (double)(P.dst_x0 + (long long)blockIdx.x * 32);
+        const double TY0 = (double)(P.dst_y0 + (long long)blockIdx.y * 32);
+        polar_tables(op0, TX0, TY0, 32, 32, s_ta, s_tb, s_ea, s_eb, threadIdx.x, 256);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            polar_from_tables(op0, TX0, TY0, px + j, py, s_ta, s_tb, s_ea, s_eb, cx[j], cy[j]);
+        chain_eval_n<A, SPH, 4>(P.chain, cx, cy, 1);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cx[j] = (double)(P.dst_x0 + X + j);
+            cy[j] = (double)(P.dst_y0 + Y);
+        }
+        chain_eval_n<A, SPH, 4>(P.chain, cx, cy);
+    }
+
+    float4 g[4];
+    float fx[4], fy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int ix, iy;
+        floor_frac_fast(cx[j], ix, fx[j]);
+        floor_frac_fast(cy[j], iy, fy[j]);
+        if (!AFF) {                          // NaN / inf / absurd coordinate -> far outside the texture (border = 0)
+            if (!((fabs(cx[j]) < TFM_SANE_COORD) && (fabs(cy[j]) < TFM_SANE_COORD))) { ix = -100000; iy = -100000; fx[j] = 0.f; fy[j] = 0.f; }
+        }
+        g[j] = tex2Dgather<float4>(tex, (float)(ix + 1), (float)(iy + 1), 0);
+    }
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // gather order: x = (i0,j1), y = (i1,j1), z = (i1,j0), w = (i0,j0)
+        const float v00 = g[j].w, v01 = g[j].z, v10 = g[j].x, v11 = g[j].y;
+        const float top = fmaf(fx[j], v01 - v00, v00);
+        const float bot = fmaf(fx[j], v11 - v10, v10);
+        r[j] = fmaf(fy[j], bot - top, top);
+    }
+    if (vec) *reinterpret_cast<float4 *>(drow) = make_float4(r[0], r[1], r[2], r[3]);
+    else if (row_in) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (X + j < P.dst_w) drow[j] = r[j];
     }
 }
 
@@ -247,7 +349,7 @@ k_resample_tma(const __grid_constant__ ResampleParams P, const __grid_constant__
     const double ylo = cy0 + fmin(31.0 * P.aff[2], 0.0) + fmin(31.0 * P.aff[3], 0.0);
     // the box must start on a 16-byte boundary of the innermost axis (measured: an unaligned start
     // coordinate raises an illegal-instruction fault), hence the round-down to a multiple of 4 pixels
-    const int bx0 = ((int)floor(xlo) - 1) & ~3, by0 = (int)floor(ylo) - 1;     // |coordinate| < 1e9: host-proven
+    const int bx0 = ((int)floor(xlo) - 1) & ~3, by0 = (int)floor(ylo) - 1;     // |coordinate| < 2.5e8: host-proven
 
     const uint32_t mbar = smem_addr(s_mbar_p);
     if (threadIdx.x == 0) {
@@ -441,13 +543,20 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         const double xm = fabs((double)d.x0) + (double)d.w, ym = fabs((double)d.y0) + (double)d.h;
         const double bx = fabs(P.aff[0]) * xm + fabs(P.aff[1]) * ym + fabs(P.aff[4]) + 1.0;
         const double by = fabs(P.aff[2]) * xm + fabs(P.aff[3]) * ym + fabs(P.aff[5]) + 1.0;
-        P.aff_bounded = (bx < 1.0e9 && by < 1.0e9) ? 1 : 0;      // NaN parameters compare false
+        P.aff_bounded = (bx < TFM_SANE_COORD && by < TFM_SANE_COORD) ? 1 : 0;      // NaN parameters compare false
         for (int k = 0; k < 6; ++k) P.aff_f[k] = (float)P.aff[k];
         P.aff_f[6] = (float)d.x0;
         P.aff_f[7] = (float)d.y0;
         P.aff_margin = (float)(4e-6 * (bx > by ? bx : by));      // a few fp32 ulps of the largest term
         if (!(P.aff_margin < 64.0f)) P.aff_bounded = 0;          // huge coordinates: skip the shortcut
+        P.aff_c[0] = (float)(P.aff[4] + 15.5 * (P.aff[0] + P.aff[1]));
+        P.aff_c[1] = (float)(P.aff[5] + 15.5 * (P.aff[2] + P.aff[3]));
+        P.aff_c[2] = (float)(15.5 * (fabs(P.aff[0]) + fabs(P.aff[1])) + 3.0) + P.aff_margin;
+        P.aff_c[3] = (float)(15.5 * (fabs(P.aff[2]) + fabs(P.aff[3])) + 3.0) + P.aff_margin;
+        P.aff_lim[0] = (float)s.w + P.aff_c[2];
+        P.aff_lim[1] = (float)s.h + P.aff_c[3];
     }
+    P.dst_vec4 = ((d.pitch % 16) == 0 && (reinterpret_cast<uintptr_t>(d.data) % 16) == 0) ? 1 : 0;
     if (is_filter) {
         static const int base_size[] = {16, 6, 8, 2, 2, 2};                           // helpers.pyx:708
         FilterParams F;
@@ -533,12 +642,21 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
             dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 31) / 32), 1);
             if (grid.y > 65535u) return TFM_EUNSUPPORTED;
             const int sph = chain_sph_level(P.chain);
-            if (aff) k_resample_tex<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
-            else if (sph == 2) k_resample_tex<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
-            else if (sph == 1) k_resample_tex<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
-            else k_resample_tex<Fast, false, 0><<<grid, 256, 0, st>>>(P, tex);
+            if (a->tuning & 128) {           // first form (4 pixels 8 rows apart, scalar stores): A/B runs only
+                if (aff) k_resample_tex<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
+                else if (sph == 2) k_resample_tex<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
+                else if (sph == 1) k_resample_tex<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
+                else k_resample_tex<Fast, false, 0><<<grid, 256, 0, st>>>(P, tex);
+                name = aff ? "k_resample_tex<affine>" : "k_resample_tex";
+            } else {
+                const bool aff4 = aff && P.aff_bounded;
+                if (aff4) k_resample_tex4<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
+                else if (sph == 2) k_resample_tex4<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
+                else if (sph == 1) k_resample_tex4<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
+                else k_resample_tex4<Fast, false, 0><<<grid, 256, 0, st>>>(P, tex);
+                name = aff4 ? "k_resample_tex4<affine>" : "k_resample_tex4";
+            }
             count_launch();
-            name = aff ? "k_resample_tex<affine>" : "k_resample_tex";
             e = cudaGetLastError();
         } else if (s.dtype == TFM_F32 && d.dtype == TFM_F32)
             e = launch1<float, float, Fast, float>(a->method, P, generic, aff, st, &name);

@@ -33,6 +33,11 @@ struct ResampleParams {
     int aff_bounded;                         // host proved |coordinate| < 2^30 over the whole output grid
     float aff_f[8];                          // fp32 copy of aff[0..5] + (dst_x0, dst_y0) for the empty-tile test
     float aff_margin;                        // absolute fp32 rounding allowance for that test
+    float aff_c[4];                          // tile-centre form of the same test (32 x 32 tiles): source coordinate of
+                                             // the centre of tile (0,0) relative to the output origin, and the
+                                             // half-extents (footprint, safety margin and rounding allowance included)
+    float aff_lim[2];                        // src_w + aff_c[2], src_h + aff_c[3]
+    int dst_vec4;                            // dst rows are 16-byte aligned: four pixels leave in one store
     double fill;
     int *status;
     int win_method;                          // TFM_WIN2 kernels: which window (TFM_HANN / TFM_TUKEY / TFM_TENT ...)
@@ -122,7 +127,7 @@ __device__ __forceinline__ RegT tap_trunc(const ResampleParams &P, const void *s
 // index whose whole footprint is out of range (the reference's INT64_MIN is out of range too).
 __device__ __forceinline__ int base_trunc(double f)
 {
-    return (fabs(f) < 1.0e9) ? __double2int_rz(f) : -1000000;
+    return (fabs(f) < TFM_SANE_COORD) ? __double2int_rz(f) : -1000000;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -279,19 +284,6 @@ template <> struct MethodTraits<TFM_LINEAR>  { static constexpr int NPX = 4, NT 
 template <> struct MethodTraits<TFM_CUBIC>   { static constexpr int NPX = 2, NT = 4; };
 template <> struct MethodTraits<TFM_WIN2>    { static constexpr int NPX = 4, NT = 2; };
 
-// floor + fractional part without the conversion (XU) pipe: t = x + 1.5*2^52 rounds x to the nearest
-// integer in the low mantissa bits; one compare-and-correct turns round-to-nearest into floor.
-// Valid for |x| < 2^31; callers route anything else to an out-of-range index first.
-__device__ __forceinline__ void floor_frac_fast(double x, int &i, float &frac)
-{
-    const double MAGIC = 6755399441055744.0;
-    const double t = x + MAGIC;
-    i = __double2loint(t);                // rn(x)
-    float f = (float)(x - (t - MAGIC));   // x - rn(x) in [-0.5, 0.5], exact before the conversion
-    if (f < 0.0f) { f += 1.0f; i -= 1; }  // round-to-nearest -> floor (fp32/ALU pipes, not fp64)
-    frac = f;
-}
-
 // phase 3: weights, reduction, store.  CHECK = false: every pixel of the warp is a valid output
 // pixel (decided by the warp vote), so the stores are unconditional.
 template <int METHOD, typename SrcT, typename DstT, typename RegT, int NPX, int NT, bool CHECK>
@@ -411,7 +403,7 @@ k_resample(const __grid_constant__ ResampleParams P)
     // padded by the footprint and a 2-pixel safety margin, misses a truncated image entirely, every
     // pixel of the tile is the fill value: store it and retire the CTA before any per-pixel work.
     if (AFF && !GENERIC && P.aff_bounded) {
-        // fp32 is plenty here: |coordinate| < 1e9 is host-proven and the test carries a margin of
+        // fp32 is plenty here: |coordinate| < 2.5e8 is host-proven and the test carries a margin of
         // 2 pixels + 1e-6 relative (P.aff_margin) on top of the footprint
         const float tx0 = (float)(int)(blockIdx.x * 32) + P.aff_f[6], tx1 = tx0 + 31.0f;
         const float ty0 = (float)(int)(blockIdx.y * (8 * NPX)) + P.aff_f[7], ty1 = ty0 + (float)(8 * NPX - 1);
@@ -480,7 +472,7 @@ k_resample(const __grid_constant__ ResampleParams P)
             // false for NaN / inf / absurd.  For host-composed affine maps the host has bounded
             // |coordinate| over the whole output grid (P.aff_bounded): nothing to test per pixel.
             if (AFF) sane[j] = true;
-            else sane[j] = (fabs(x) < 1.0e9) && (fabs(y) < 1.0e9);
+            else sane[j] = (fabs(x) < TFM_SANE_COORD) && (fabs(y) < TFM_SANE_COORD);
         }
         const int pe = (int)(P.src_pitch / (long long)sizeof(SrcT));       // host guarantees h*pe < 2^31
         // CTA-uniform: the whole 32 x (8*NPX) tile lies inside the output and (AFF) coordinates are
@@ -535,7 +527,7 @@ k_resample(const __grid_constant__ ResampleParams P)
 #pragma unroll
         for (int j = 0; j < NPX; ++j) {
             valid[j] = xin && (Y0 + 8 * j < P.dst_h);
-            const bool ok = sane[j] && (!AFF || P.aff_bounded || ((fabs(cx[j]) < 1.0e9) && (fabs(cy[j]) < 1.0e9)));
+            const bool ok = sane[j] && (!AFF || P.aff_bounded || ((fabs(cx[j]) < TFM_SANE_COORD) && (fabs(cy[j]) < TFM_SANE_COORD)));
             // NaN / absurd coordinate: whole footprint out of range -> fill (INT64_MIN in the reference)
             const int bx = ok ? ix[j] : -1000000, by = ok ? iy[j] : -1000000;
 #pragma unroll
@@ -556,7 +548,7 @@ k_resample(const __grid_constant__ ResampleParams P)
             fracy[j] = __dsub_rn(y, fy);
             ffx[j] = (float)fracx[j];
             ffy[j] = (float)fracy[j];
-            if (FASTI && fabs(x) < 1.0e9 && fabs(y) < 1.0e9) {
+            if (FASTI && fabs(x) < TFM_SANE_COORD && fabs(y) < TFM_SANE_COORD) {
                 // every fast-mode variant (LDG gather, texture gather, this generic one) must round the
                 // fp32 fraction identically, so that a sharded run reproduces the unsharded one bit for bit
                 int iu;
