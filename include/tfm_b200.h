@@ -169,7 +169,11 @@ typedef enum tfm_bound {
 /* Jacobian-filter shapes: the reference's own table (helpers.pyx:1501) */
 typedef enum tfm_filter {
     TFM_FILT_TENT = 1, TFM_FILT_LANCZOS = 2, TFM_FILT_HANNING = 3, TFM_FILT_TUKEY = 4,
-    TFM_FILT_GAUSSIAN = 5
+    TFM_FILT_GAUSSIAN = 5,
+    /* not in helpers.pyx's table: the Hann window (cos(pi x) + 1)/2 per axis that the reference's other,
+     * working anti-aliaser uses (SVD.pyx:110-111).  TFM_FILT_HANNING is helpers.pyx:1708-1717 as
+     * coded -- cos^2(pi x), which has weight 1 at the EDGE of its support. */
+    TFM_FILT_HANN_WINDOW = 6
 } tfm_filter;
 
 typedef enum tfm_precision {

@@ -114,7 +114,7 @@ static int orc_bound1(int64_t *pi, int64_t size, int bound)
 }
 
 /* source[sh][sw] f64, index[ny][nx][2], jac[ny][nx][2][2] -> dest[ny][nx]
- * method: l=1 z=2 h=3 t=4 g=5 (helpers.pyx:1501); bound: f=1 t=2 e=3 p=4 m=5 (helpers.pyx:1511).
+ * method: l=1 z=2 h=3 t=4 g=5 (helpers.pyx:1501), w=6 (Hann window of SVD.pyx:110-111); bound: f=1 t=2 e=3 p=4 m=5 (helpers.pyx:1511).
  * max_reg: 0 = unlimited (reference behaviour); >0 caps reg_size (the documented-but-unused
  *          sv_limit guard, helpers.pyx:1441-1445, made explicit; the CUDA path takes the same cap). */
 int orc_interp_jacobian(const double *source, int64_t sh, int64_t sw,
@@ -126,7 +126,7 @@ int orc_interp_jacobian(const double *source, int64_t sh, int64_t sw,
     (void)fillvalue; (void)iblur;                       /* unused by the reference too (R7) */
     double padval;
     const double pi = 3.141592653589793;
-    if (method == 1 || method == 3 || method == 4) padval = 1;       /* helpers.pyx:1612-1615 */
+    if (method == 1 || method == 3 || method == 4 || method == 6) padval = 1; /* helpers.pyx:1612-1615; 6 as 3 */
     else if (method == 2 || method == 5) padval = 3;
     else return ORC_EVALUE;
     if (bound_x < 1 || bound_x > 5 || bound_y < 1 || bound_y > 5) return ORC_EVALUE;
@@ -189,6 +189,12 @@ int orc_interp_jacobian(const double *source, int64_t sh, int64_t sw,
                             if (xf > 0.5) { b = cos(pi * 2 * (xf - 0.5)); filt = b * b; }
                             if (yf > 0.5) { b = cos(pi * 2 * (yf - 0.5)); filt *= b * b; }
                         }
+                        break;
+                    case 6:
+                        /* the Hann window the reference's OTHER anti-aliaser uses (SVD.pyx:110-111):
+                         * (cos(pi min(|x|,1)) + 1)(cos(pi min(|y|,1)) + 1) / 2 -- helpers.pyx:1708-1717
+                         * (case 3) squares cos(pi x) instead, which is not a window */
+                        filt = (cos((xf < 1 ? xf : 1) * pi) + 1.0) * (cos((yf < 1 ? yf : 1) * pi) + 1.0) / 2.0;
                         break;
                     default:
                         filt = exp(-(xf * xf + yf * yf));                        /* 1735 */

@@ -847,7 +847,8 @@ def svc2x2(U, s, V):
 # Anti-aliased (Jacobian-adaptive) resampling: interpND_grid (helpers.pyx:1293-1530) driving
 # interpND_jacobian (helpers.pyx:1542-1803, C restatement in oracle_c.c)
 # --------------------------------------------------------------------------------------
-_METHOD_CODE = {"l": 1, "z": 2, "h": 3, "t": 4, "g": 5}          # helpers.pyx:1501
+_METHOD_CODE = {"l": 1, "z": 2, "h": 3, "t": 4, "g": 5,          # helpers.pyx:1501
+                "w": 6}                                          # the Hann window of SVD.pyx:110-111
 _BOUND_CODE = {"f": 1, "t": 2, "e": 3, "p": 4, "m": 5}           # helpers.pyx:1511
 
 

@@ -279,3 +279,22 @@ def test_constant_jacobian_path(tfm, oracle):
     fl = tr.resample(src, method='G', phot='flux', precision='fp32')
     rd = tr.resample(src, method='G', precision='fp32')
     assert_close_rel(fl, rd / (0.45 * 0.6), 1e-5, "flux")
+
+
+def test_hann_window_and_flux_match_reference_svdpyx(tfm, oracle):
+    """K2 with the Hann-window filter ('W') and phot='flux' against golden vectors of the reference's
+    working anti-aliaser SVD.pyx::map_coordinates (tests/golden/svdpyx_golden.npz; see the CPU twin of
+    this test for when the two algorithms coincide).  Parity mode 1e-12, fp32 mode 1e-5."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "svdpyx_golden.npz"))
+    src = G["src64"]
+    for case in sorted(k.split("/")[0] for k in G.files if k.endswith("/params")):
+        sx, sy, ox, oy = G[case + "/params"]
+        tr = tfm.Scale([1 / sx, 1 / sy], pre=np.array([-ox, -oy]))
+        for phot in ("radiance", "flux"):
+            want = G[case + "/" + phot]
+            got = tr.resample(src, method='W', bound='e', shape=want.shape, pad_pow=64, jump_detect=0, phot=phot)
+            assert float(np.abs(got - want).max()) <= 1e-12 * max(1.0, float(np.abs(want).max())), (case, phot)
+            fast = tr.resample(src.astype(np.float32), method='W', bound='e', shape=want.shape, pad_pow=64,
+                               jump_detect=0, phot=phot, precision='fp32')
+            assert float(np.abs(fast - want).max()) <= 1e-5 * max(1.0, float(np.abs(want).max())), (case, phot)

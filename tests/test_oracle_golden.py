@@ -189,23 +189,29 @@ def test_svd_matches_reference(oracle):
         assert s[0] >= s[1] >= 0
 
 
-def test_jacobian_filter_vs_reference_svdpyx(oracle):
-    """Cross-check of the repaired interpND_grid restatement against the reference's WORKING but
-    independent DeForest-2004 implementation (SVD.pyx::map_coordinates, Hanning window, different
-    padding and footprint rules): on a 2x affine downsample of random data both are local weighted
-    means of the same ~4x4 neighbourhoods, so they must correlate strongly and agree on the mean."""
-    src = GOLD["src64"]
-    want = GOLD["svdpyx/target"]
-    otr = oracle.Scale([0.5, 0.5])            # Ci(out) = 2*out  <=>  forward transform scales by 0.5
-    got = oracle.resample_jacobian(otr, src, method='g', bound='e', shape=want.shape)
-    assert got.shape == want.shape
-    inner = (slice(2, -2), slice(2, -2))
-    r = np.corrcoef(got[inner].ravel(), want[inner].ravel())[0, 1]
-    assert r > 0.8, r          # measured 0.85: same neighbourhoods, different window (Hanning vs Gaussian) and padding
-    assert abs(got[inner].mean() - want[inner].mean()) < 0.02
-    # and on a constant image both reproduce the constant
-    const = oracle.resample_jacobian(otr, np.full_like(src, 2.5), method='g', bound='e', shape=want.shape)
-    assert np.allclose(const, 2.5, atol=1e-12)
+SVDPYX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "svdpyx_golden.npz"))
+SVDPYX_CASES = sorted(k.split("/")[0] for k in SVDPYX.files if k.endswith("/params"))
+
+
+@pytest.mark.parametrize("case", SVDPYX_CASES)
+@pytest.mark.parametrize("phot", ["radiance", "flux"])
+def test_hann_window_and_flux_match_reference_svdpyx(oracle, case, phot):
+    """The Hann-window filter ('w') and phot='flux' against the reference's WORKING DeForest-2004
+    implementation, SVD.pyx::map_coordinates (SVD.pyx:193-292; window 110-111, flux rule 285-286), on
+    the maps where the two algorithms coincide tap for tap (tests/golden/make_svdpyx_golden.py:
+    integer source positions, diagonal Jacobian with scales >= 2, 'extend' boundary, pad_pow large so
+    that interpND_grid's padded inverse singular values equal map_coordinates' plain 1/s).
+    Tolerance 1e-14 absolute on values of order 1 (measured 3e-16 / 2e-15)."""
+    sx, sy, ox, oy = SVDPYX[case + "/params"]
+    want = SVDPYX[case + "/" + phot]
+    otr = oracle.Linear(matrix=np.diag([1 / sx, 1 / sy]), matinv=np.diag([sx, sy]), pre=[-ox, -oy])
+    got = oracle.resample_jacobian(otr, SVDPYX["src64"], method='w', bound='e', shape=want.shape,
+                                   pad_pow=64, jump_detect=0, phot=phot)
+    assert float(np.abs(got - want).max()) <= 1e-14 * max(1.0, float(np.abs(want).max()))
+    # the window as coded in helpers.pyx:1708-1717 ('h', cos^2) is a different function: it must NOT agree
+    other = oracle.resample_jacobian(otr, SVDPYX["src64"], method='h', bound='e', shape=want.shape,
+                                     pad_pow=64, jump_detect=0, phot=phot)
+    assert float(np.abs(other - want).max()) > 1e-3
 
 
 AA_KEYS = [k for k in GOLD.files if k.startswith("aa/") and not k.endswith("/coords")]

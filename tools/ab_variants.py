@@ -31,8 +31,13 @@ def timed(fn, reps):
 what = sys.argv[1]
 out = {}
 if what == "k2":
-    out["jacobian_radial_fp32_ms"] = timed(lambda: tr_rad.resample(src, method="G", precision="fp32", out=dst), 10)
-    out["jacobian_affine_fp32_ms"] = timed(lambda: tr_aff.resample(src, method="G", precision="fp32", out=dst), 10)
+    from transform_b200 import _lib
+    tr_dn = t.Composition([t.Offset([n / 2.0 + 0.3, n / 2.0 - 0.2]), t.Scale([0.6, 0.7]), t.Rotation(25, unit="deg"), t.Offset([-n / 2.0, -n / 2.0])])
+    for tun in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0").split(",")]:
+        out["radial_t%d_ms" % tun] = round(timed(lambda: tr_rad.resample(src, method="G", precision="fp32", out=dst, tuning=tun), 10), 4)
+        out["radial_t%d_k" % tun] = _lib.last_kernel()
+        out["named_t%d_ms" % tun] = round(timed(lambda: tr_aff.resample(src, method="G", precision="fp32", out=dst, tuning=tun), 10), 4)
+        out["down_t%d_ms" % tun] = round(timed(lambda: tr_dn.resample(src, method="G", precision="fp32", out=dst, tuning=tun), 10), 4)
 else:
     maps = {"named": tr_aff, "shift": t.Offset([3.25, -7.5]), "scale0p8": t.Scale(0.8, dim=2),
             "rot5": t.Wrap(t.Rotation(5, unit="deg"), t.Offset([-n / 2.0, -n / 2.0])),
@@ -44,13 +49,18 @@ print(json.dumps(out))
 '''
 
 what = sys.argv[1]
+tunings = "0"
+specs = sys.argv[2:]
+if specs and specs[0].startswith("tunings="):
+    tunings = specs[0].split("=", 1)[1]
+    specs = specs[1:]
 res = {}
-for spec in sys.argv[2:]:
+for spec in specs:
     name, path = spec.split("=", 1)
     env = dict(os.environ)
     if path != "default":
         env["TFM_B200_LIB"] = os.path.abspath(path)
-    r = subprocess.run([sys.executable, "-c", CHILD, what], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    r = subprocess.run([sys.executable, "-c", CHILD, what, tunings], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
     print(name, line, flush=True)
     try:

@@ -16,7 +16,7 @@ from . import _lib as L
 
 _METHODS = {"n": L.NEAREST, "l": L.LINEAR, "c": L.CUBIC}
 # capital-letter methods of Transform.resample (core.py:495-508) -> interpND_grid filter letters
-_AA_METHODS = {"G": "g", "H": "h", "R": "t", "Z": "z", "L": "l"}
+_AA_METHODS = {"G": "g", "H": "h", "R": "t", "Z": "z", "L": "l", "W": "w"}
 # the collapsible input-plane filters of interpND (helpers.pyx:703-735, 792-835) and their region size
 _FILTERS = {"s": (L.SINC, 16), "z": (L.LANCZOS, 6), "g": (L.GAUSSIAN, 8), "h": (L.HANN, 2),
             "t": (L.TUKEY, 2), "l": (L.TENT, 2)}
@@ -80,6 +80,22 @@ def _image(t, np_dtype, x0=0, y0=0, full=None):
     return img
 
 
+def _device_out(out, shape, ddt, src):
+    """A caller-supplied CUDA tensor as the kernel destination: it must be exactly what the kernel is
+    about to write -- same leading axes and grid, the output dtype of this call, dense rows, same
+    device.  (The kernel takes pitch and element size from the EXPECTED layout: anything else would
+    be written with the wrong stride, or past its end.)"""
+    if tuple(int(v) for v in out.shape) != tuple(int(v) for v in shape):
+        raise ValueError("out= must have shape %s, not %s" % (tuple(shape), tuple(out.shape)))
+    if dev.np_dtype_of(out) != np.dtype(ddt):
+        raise ValueError("out= must have dtype %s for this call, not %s" % (np.dtype(ddt).name, out.dtype))
+    if not out.is_contiguous():
+        raise ValueError("out= must be a contiguous CUDA tensor")
+    if out.device != src.device:
+        raise ValueError("out= is on %s but the data is on %s" % (out.device, src.device))
+    return out
+
+
 def _src_to_device(data, want_f32):
     """-> (cuda tensor, numpy dtype on device, original numpy dtype, came_from_numpy)."""
     if dev.is_cuda_tensor(data):
@@ -112,7 +128,8 @@ def _src_to_device(data, want_f32):
 
 
 def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None, tuning=0,
-             dst_origin=(0, 0), src_origin=(0, 0), src_full=None, out=None, oblur=None, sync=True):
+             dst_origin=(0, 0), src_origin=(0, 0), src_full=None, out=None, oblur=None, sync=True,
+             status_host=None):
     """K1 driver.  `chain_ops` is the inverse chain in execution order (list of TfmOp)."""
     lib = L.load()
     prec = parse_precision(precision)
@@ -162,7 +179,7 @@ def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None,
         final_dt = ddt
     host_out = None
     if out is not None and dev.is_cuda_tensor(out):
-        dst = out
+        dst = _device_out(out, lead + (ny, nx), ddt, src)
     else:
         host_out = out
         dst = dev.empty(lead + (ny, nx), ddt)
@@ -190,11 +207,11 @@ def resample(chain_ops, data, shape, method, bound, fillvalue=0, precision=None,
     a.status_dev = status.data_ptr() if status is not None else None
     rc = lib.tfm_resample(ctypes.byref(a), dev.stream_ptr())
     L.raise_for_status(rc, "tfm_resample")
-    _check_status(status)
-    if not from_numpy:
-        return dst
+    _check_status(status, sync, status_host)
     if host_out is not None:
         return _into_host(dst, host_out, sync)
+    if not from_numpy:
+        return dst
     res = dev.to_host(dst)
     if res.dtype != final_dt:
         res = res.astype(final_dt)
@@ -217,15 +234,25 @@ def _into_host(dst, host_out, sync=True):
     return host_out
 
 
-def _check_status(status):
-    if status is None:
-        return
-    bits = int(status.item())
+def raise_for_status_bits(bits):
+    """Status word of a kernel (include/tfm_b200.h, tfm_resample_args.status_dev) -> exception."""
     if bits & 1:
         raise ValueError("apply_boundary: boundary violation with 'forbid' condition")
     if bits & 2:
         raise RuntimeError("transform_b200: a tap fell outside the staged source sub-rectangle "
                            "(sharding bounding box too small)")
+
+
+def _check_status(status, sync=True, status_host=None):
+    """Read the device status word.  Blocking by default (`.item()` is a device sync).  With sync=False
+    and a pinned int32 `status_host` the word is copied asynchronously on the current stream instead,
+    and whoever waits for the call (pipeline.Ticket.result) passes it to raise_for_status_bits."""
+    if status is None:
+        return
+    if not sync and status_host is not None:
+        status_host.copy_(status, non_blocking=True)
+        return
+    raise_for_status_bits(int(status.item()))
 
 
 def flux_requested(phot):
@@ -244,7 +271,7 @@ def flux_requested(phot):
 def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=1.0, iblur=1.0,
                       pad_pow=8, sv_limit=0.25, jump_detect=4.0, precision=None, tuning=0,
                       dst_origin=(0, 0), grid_full=None, src_origin=(0, 0), src_full=None,
-                      max_reg=None, out=None, phot='radiance', sync=True):
+                      max_reg=None, out=None, phot='radiance', sync=True, status_host=None):
     """K2 driver: interpND_grid(antialias=True) semantics (helpers.pyx:1293-1530) with the
     coordinates generated in-kernel from `chain_ops`."""
     lib = L.load()
@@ -252,7 +279,7 @@ def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=
     try:
         filt = L.FILTER_CODE[method[0]]
     except (KeyError, IndexError, TypeError):
-        raise ValueError("interpND_grid: method must be 'l','z','h','t', or 'g'")
+        raise ValueError("interpND_grid: method must be 'l','z','h','t', or 'g' (or 'w', the Hann window)")
     try:
         bx, by = bound_pair(bound)
     except ValueError:
@@ -270,7 +297,7 @@ def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=
     ddt = np.dtype(np.float32) if fast else np.dtype(np.float64)
     host_out = None
     if out is not None and dev.is_cuda_tensor(out):
-        dst = out
+        dst = _device_out(out, lead + (ny, nx), ddt, src)
     else:
         host_out = out
         dst = dev.empty(lead + (ny, nx), ddt)
@@ -306,11 +333,11 @@ def resample_jacobian(chain_ops, data, shape, method, bound, fillvalue=0, oblur=
     a.status_dev = status.data_ptr() if status is not None else None
     rc = lib.tfm_resample_jacobian(ctypes.byref(a), dev.stream_ptr())
     L.raise_for_status(rc, "tfm_resample_jacobian")
-    _check_status(status)
-    if not from_numpy:
-        return dst
+    _check_status(status, sync, status_host)
     if host_out is not None:
         return _into_host(dst, host_out, sync)
+    if not from_numpy:
+        return dst
     return dev.to_host(dst)
 
 

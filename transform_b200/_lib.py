@@ -31,7 +31,8 @@ NEAREST, LINEAR, CUBIC = 0, 1, 2
 SINC, LANCZOS, GAUSSIAN, HANN, TUKEY, TENT = 3, 4, 5, 6, 7, 8
 FILTER_MAX_SIZE = 112
 BOUND_CODE = {"f": 1, "t": 2, "e": 3, "p": 4, "m": 5}            # helpers.pyx:1511
-FILTER_CODE = {"l": 1, "z": 2, "h": 3, "t": 4, "g": 5}           # helpers.pyx:1501
+FILTER_CODE = {"l": 1, "z": 2, "h": 3, "t": 4, "g": 5,           # helpers.pyx:1501
+               "w": 6}                                           # Hann window of SVD.pyx:110-111 (TFM_FILT_HANN_WINDOW)
 PREC_EXACT64, PREC_FAST32 = 0, 1
 F_REGION_SRC_DTYPE = 1
 F_FLUX = 2

@@ -163,16 +163,27 @@ class Transform:
                                       "(optionally batched over leading axes)")
         ops = self._int_chain(True)             # self.invert(grid), core.py:574 (the grid is int64)
         m = method[0]
+        status_host = aa.pop('status_host', None)
+        # interpND_grid's two spellings of the anti-aliasing switch (helpers.pyx:1297-1298); both are
+        # consumed whatever their values
+        antialias = bool(aa.pop('antialias', True)) & bool(aa.pop('aa', True))
         if m in _engine._AA_METHODS:
-            if aa.pop('antialias', True) and aa.pop('aa', True):
+            if antialias:
                 return _engine.resample_jacobian(ops, data0, shape, _engine._AA_METHODS[m], bound,
                                                  fillvalue=fillvalue, precision=precision,
-                                                 tuning=tuning, out=out, phot=phot, sync=sync, **aa)
+                                                 tuning=tuning, out=out, phot=phot, sync=sync,
+                                                 status_host=status_host, **aa)
+            # anti-aliasing switched off: the capital letter falls back to its input-plane filter, as
+            # interpND_grid(antialias=False) does (helpers.pyx:1524-1530); only oblur carries over
+            m = _engine._AA_METHODS[m]
+            for k in ('iblur', 'pad_pow', 'sv_limit', 'jump_detect', 'max_reg'):
+                aa.pop(k, None)
         oblur = aa.pop('oblur', None)           # interpND's keyword (helpers.pyx:509-516)
         if aa:
             raise TypeError("resample() got unexpected keyword arguments %s" % sorted(aa))
         return _engine.resample(ops, data0, shape, m, bound, fillvalue=fillvalue,
-                                precision=precision, tuning=tuning, out=out, oblur=oblur, sync=sync)
+                                precision=precision, tuning=tuning, out=out, oblur=oblur, sync=sync,
+                                status_host=status_host)
 
     def remap(self, data, /, method='n', bound='t', phot='radiance', shape=None, template=None,
               input_range=None, output_range=None, justify=False, rectify=True, wcs=None, **kw):

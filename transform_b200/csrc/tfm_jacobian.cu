@@ -113,6 +113,10 @@ __device__ __forceinline__ double filt_eval<double>(int filter, double xf, doubl
         if (xf > 0.5) { b = cos(__dmul_rn(__dmul_rn(pi, 2.0), __dsub_rn(xf, 0.5))); filt = __dmul_rn(b, b); }
         if (yf > 0.5) { b = cos(__dmul_rn(__dmul_rn(pi, 2.0), __dsub_rn(yf, 0.5))); filt = __dmul_rn(filt, __dmul_rn(b, b)); }
         return filt;
+    case TFM_FILT_HANN_WINDOW:                                   // SVD.pyx:110-111
+        a = __dadd_rn(cos(__dmul_rn(xf < 1 ? xf : 1.0, pi)), 1.0);
+        b = __dadd_rn(cos(__dmul_rn(yf < 1 ? yf : 1.0, pi)), 1.0);
+        return __ddiv_rn(__dmul_rn(a, b), 2.0);
     default:                                                     // Gaussian, helpers.pyx:1734-1735
         return exp(-__dadd_rn(__dmul_rn(xf, xf), __dmul_rn(yf, yf)));
     }
@@ -141,6 +145,8 @@ __device__ __forceinline__ float filt_eval<float>(int filter, float xf, float yf
         if (xf > 0.5f) { b = __cosf(pi * 2.0f * (xf - 0.5f)); filt = b * b; }
         if (yf > 0.5f) { b = __cosf(pi * 2.0f * (yf - 0.5f)); filt *= b * b; }
         return filt;
+    case TFM_FILT_HANN_WINDOW:
+        return 0.5f * (__cosf(pi * fminf(xf, 1.0f)) + 1.0f) * (__cosf(pi * fminf(yf, 1.0f)) + 1.0f);
     default:
         return __expf(-(xf * xf + yf * yf));
     }
@@ -189,8 +195,10 @@ __device__ __noinline__ unsigned char jump_flag_exact(const double *m2, int cw, 
 __device__ __forceinline__ float pad_inv_sv(float s, float padval, float pad_pow)
 {
     // (padval + s^p)^(-1/p)   (helpers.pyx:1661-1662)
-    const float sp = exp2f(pad_pow * __log2f(s));            // s = 0 -> log2 = -inf -> 0
-    return exp2f(-__log2f(padval + sp) / pad_pow);
+    // s = 0 -> log2 = -inf -> 0; above 2^60 the sum IS the power (and the power may overflow fp32)
+    const float e = pad_pow * __log2f(s);
+    const float lg = (e > 60.0f) ? e : __log2f(padval + exp2f(e));
+    return exp2f(-lg / pad_pow);
 }
 
 __device__ __forceinline__ void padded_inverse_f32(const double *Ji, float padval, float pad_pow,
@@ -845,7 +853,7 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
 {
     if (!a || a->abi_version != TFM_ABI_VERSION) return TFM_EVALUE;
     if (a->n_ops < 0 || a->n_ops > TFM_MAX_OPS || (a->n_ops && !a->chain)) return TFM_EVALUE;
-    if (a->filter < TFM_FILT_TENT || a->filter > TFM_FILT_GAUSSIAN) return TFM_EVALUE;   // helpers.pyx:1505
+    if (a->filter < TFM_FILT_TENT || a->filter > TFM_FILT_HANN_WINDOW) return TFM_EVALUE;   // helpers.pyx:1505
     if (a->bound_x < TFM_B_FORBID || a->bound_x > TFM_B_MIRROR ||
         a->bound_y < TFM_B_FORBID || a->bound_y > TFM_B_MIRROR) return TFM_EVALUE;       // helpers.pyx:1516
     const tfm_image &s = a->src, &d = a->dst;

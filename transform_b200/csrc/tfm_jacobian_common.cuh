@@ -76,8 +76,11 @@ __device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.appro
 // of the squared singular value lambda (helpers.pyx:1661-1662 applied to s = sqrt(lambda)).
 __device__ __forceinline__ float pad_inv_sq(float lam, float padval, float half_pow, float m2_over_pow)
 {
-    const float sp = fast_ex2(half_pow * fast_lg2(lam));     // lam = 0 -> lg2 = -inf -> 0
-    return fast_ex2(m2_over_pow * fast_lg2(padval + sp));
+    // lam = 0 -> lg2 = -inf -> 0.  Above 2^60 the padding constant is below fp32 resolution and the
+    // power may overflow fp32 (pad_pow = 64 with s >= 4): the logarithm of the sum is the exponent itself
+    const float e = half_pow * fast_lg2(lam);
+    const float lg = (e > 60.0f) ? e : fast_lg2(padval + fast_ex2(e));
+    return fast_ex2(m2_over_pow * lg);
 }
 
 // Gaussian footprint weights need only Q = J^T J with J = V diag(s') U^T, i.e. Q = U diag(s'^2) U^T

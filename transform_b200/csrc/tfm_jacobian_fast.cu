@@ -38,6 +38,9 @@ struct JacFastParams {
     int lw;                                  // log2 of the warp patch width
     int max_half;                            // cap on the footprint half-width (max_reg / 2)
     int *status;
+    cudaTextureObject_t tex;                 // point-sampled, border = 0 (tap mode 2)
+    int tex_edges;                           // both bounds truncate and the whole image is staged: the texture's
+                                             // border IS the reference's truncated tap -- no edge classification
     float qscale;                            // log2(e) / oblur^2: exp(-q/oblur^2) = exp2(-q * qscale)
     float ob;                                // oblur
     float padval, half_pow, m2_over_pow;     // padding (helpers.pyx:1661-1662): pad_pow / 2, -2 / pad_pow
@@ -109,31 +112,174 @@ __device__ __forceinline__ void gauss_taps2(const float *__restrict__ p0, int pe
     wgt += wgt2.x + wgt2.y;
 }
 
-__device__ __forceinline__ void gauss_taps_any(int half, const float *p0, int pe, float w0, float r0, float rb,
+// The same footprint with 8-byte loads.  ncu on the row-pair form (profiles/r2_k2.md): the kernel is
+// bound by the L1TEX sector stage, not by instruction issue -- one 4-byte tap load of a warp touches
+// ~13 sectors (32 footprints spread along an arc), and there are (2*HALF+1)^2 of them per pixel.  An
+// 8-byte load of two horizontally adjacent taps touches the SAME sectors, so loading column PAIRS
+// nearly halves the sector traffic.  8-byte alignment: the window starts on the even column at or
+// below the footprint's first column and spans N+1 columns; the one column outside the reference's
+// square (the first when the start was odd, else the last) is selected away (value AND weight: a NaN
+// there must not leak).  Packed lanes are the two columns of a pair: w(c+2) = w(c) r(c) r(c+1), so
+// with R2 = (r(c)^2 cA, r(c+1)^2 cA) the pair state advances as W2 *= R2, R2 *= cA^4.
+template <int HALF>
+__device__ __forceinline__ void gauss_taps_cp(const float *__restrict__ p0, int pe, bool first_out, float w0, float r0,
+                                              float rb, float cA, float cB, float cC, float &val, float &wgt)
+{
+    constexpr int N = 2 * HALF + 1, NP = HALF + 1;
+    const float cA2 = cA * cA, cA4s = cA2 * cA2;
+    const float2 CA4 = make_float2(cA4s, cA4s);
+    const float2 CA13 = make_float2(cA, cA * cA2);           // R2 = r0^2 * (cA, cA^3)
+    float2 WR = make_float2(w0, r0);                         // (first weight, first ratio) of the row
+    float2 STEP = make_float2(rb, cB);                       // row-to-row: w0 *= rb, r0 *= cB; rb *= cC
+    const float2 CC1 = make_float2(cC, 1.0f);
+    float2 val2 = make_float2(0.0f, 0.0f), wgt2 = make_float2(0.0f, 0.0f);
+#pragma unroll(HALF <= 2 ? N : 2)
+    for (int j = 0; j < N; ++j) {
+        const float2 *p = reinterpret_cast<const float2 *>(p0 + j * pe);
+        const float2 t = __fmul2_rn(WR, make_float2(WR.y, WR.y));        // (w0 r0, r0^2)
+        float2 W2 = make_float2(WR.x, t.x);
+        float2 R2 = __fmul2_rn(make_float2(t.y, t.y), CA13);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            float2 v = __ldg(p + i);
+            float2 W = W2;
+            if (i == 0) { v.x = first_out ? 0.0f : v.x; W.x = first_out ? 0.0f : W.x; }
+            if (i == NP - 1) { v.y = first_out ? v.y : 0.0f; W.y = first_out ? W.y : 0.0f; }
+            val2 = __ffma2_rn(v, W, val2);
+            wgt2 = __fadd2_rn(wgt2, W);
+            if (i + 1 < NP) {
+                W2 = __fmul2_rn(W2, R2);
+                R2 = __fmul2_rn(R2, CA4);
+            }
+        }
+        WR = __fmul2_rn(WR, STEP);
+        STEP = __fmul2_rn(STEP, CC1);
+    }
+    val += val2.x + val2.y;
+    wgt += wgt2.x + wgt2.y;
+}
+
+// The same footprint through the texture unit (tap mode 2).  One TLD4 returns the 2 x 2 block
+// (c, c+1) x (r, r+1) of every lane with no alignment rule, so the window starts exactly on the
+// footprint; it spans (N+1) x (N+1) texels in (HALF+1)^2 fetches, and the column and row beyond the
+// reference's square (always the LAST ones) are simply not accumulated -- no selects.  Out-of-range
+// texels read 0 (border mode), which is the reference's truncated tap (weight counted, value skipped,
+// helpers.pyx:1740 vs 1793-1796): with truncate boundaries NO pixel needs the slow path.
+// ncu, 8192^2 polar unwrap (profiles/r2_k2.md): the 8-byte LDG form is bound by the LSU data pipe --
+// 3.5 wavefronts per request (one per cache line the 32 footprints of a warp touch), 2 taps per lane;
+// the texture path returns 4 taps per lane per request through its own filter/write-back stage.
+// one row pair (r, r+1) of the texture form; BOTH = false: row r+1 lies outside the square
+template <int HALF, bool BOTH>
+__device__ __forceinline__ void tex_row_pair(cudaTextureObject_t tex, float fx0, float fy, float2 &WR, float2 &STEP,
+                                             const float2 CC1, const float2 CA13, const float2 CA4,
+                                             float2 &val2, float2 &wgt2, float &val, float &wgt)
+{
+    constexpr int NP = HALF + 1;
+    const float2 ta = __fmul2_rn(WR, make_float2(WR.y, WR.y));       // (w0 r0, r0^2) of row r
+    float2 Wa = make_float2(WR.x, ta.x);
+    float2 Ra = __fmul2_rn(make_float2(ta.y, ta.y), CA13);
+    WR = __fmul2_rn(WR, STEP);
+    STEP = __fmul2_rn(STEP, CC1);
+    float2 Wb = make_float2(0.f, 0.f), Rb = make_float2(0.f, 0.f);
+    if (BOTH) {
+        const float2 tb = __fmul2_rn(WR, make_float2(WR.y, WR.y));
+        Wb = make_float2(WR.x, tb.x);
+        Rb = __fmul2_rn(make_float2(tb.y, tb.y), CA13);
+        WR = __fmul2_rn(WR, STEP);
+        STEP = __fmul2_rn(STEP, CC1);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        // gather order: x = (c, r+1), y = (c+1, r+1), z = (c+1, r), w = (c, r)
+        const float4 g = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
+        if (i < HALF) {
+            val2 = __ffma2_rn(make_float2(g.w, g.z), Wa, val2);
+            wgt2 = __fadd2_rn(wgt2, Wa);
+            Wa = __fmul2_rn(Wa, Ra);
+            Ra = __fmul2_rn(Ra, CA4);
+            if (BOTH) {
+                val2 = __ffma2_rn(make_float2(g.x, g.y), Wb, val2);
+                wgt2 = __fadd2_rn(wgt2, Wb);
+                Wb = __fmul2_rn(Wb, Rb);
+                Rb = __fmul2_rn(Rb, CA4);
+            }
+        } else {                                             // last pair: column N is outside the square
+            val = fmaf(g.w, Wa.x, val);
+            wgt += Wa.x;
+            if (BOTH) {
+                val = fmaf(g.x, Wb.x, val);
+                wgt += Wb.x;
+            }
+        }
+    }
+}
+
+template <int HALF>
+__device__ __forceinline__ void gauss_taps_tex(cudaTextureObject_t tex, int xs, int ys, float w0, float r0, float rb,
                                                float cA, float cB, float cC, float &val, float &wgt)
 {
+    const float cA2 = cA * cA, cA4s = cA2 * cA2;
+    const float2 CA4 = make_float2(cA4s, cA4s);
+    const float2 CA13 = make_float2(cA, cA * cA2);           // R2 = r0^2 * (cA, cA^3)
+    float2 WR = make_float2(w0, r0);                         // (first weight, first ratio) of the row
+    float2 STEP = make_float2(rb, cB);                       // row-to-row: w0 *= rb, r0 *= cB; rb *= cC
+    const float2 CC1 = make_float2(cC, 1.0f);
+    float2 val2 = make_float2(0.0f, 0.0f), wgt2 = make_float2(0.0f, 0.0f);
+    const float fx0 = (float)(xs + 1);
+    float fy = (float)(ys + 1);
+#pragma unroll(HALF <= 2 ? HALF : 1)
+    for (int j = 0; j < HALF; ++j, fy += 2.0f)
+        tex_row_pair<HALF, true>(tex, fx0, fy, WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
+    tex_row_pair<HALF, false>(tex, fx0, fy, WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
+    val += val2.x + val2.y;
+    wgt += wgt2.x + wgt2.y;
+}
+
+template <int TM>
+__device__ __forceinline__ void gauss_taps_any(cudaTextureObject_t tex, int xs, int ys, int half, const float *p0, int pe, bool first_out,
+                                               float w0, float r0, float rb, float cA, float cB, float cC,
+                                               float &val, float &wgt)
+{
+#define TFM_TAPS(H)                                                                           \
+    if (TM == 2) gauss_taps_tex<H>(tex, xs, ys, w0, r0, rb, cA, cB, cC, val, wgt);             \
+    else if (TM == 1) gauss_taps_cp<H>(p0, pe, first_out, w0, r0, rb, cA, cB, cC, val, wgt);   \
+    else gauss_taps2<H>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt)
     switch (half) {
-    case 1: gauss_taps2<1>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
-    case 2: gauss_taps2<2>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
-    case 3: gauss_taps2<3>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
-    case 4: gauss_taps2<4>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
-    case 5: gauss_taps2<5>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
-    default: gauss_taps2<6>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt); break;
+    case 1: TFM_TAPS(1); break;
+    case 2: TFM_TAPS(2); break;
+    case 3: TFM_TAPS(3); break;
+    case 4: TFM_TAPS(4); break;
+    case 5: TFM_TAPS(5); break;
+    default: TFM_TAPS(6); break;
     }
+#undef TFM_TAPS
 }
 
 // Out-of-line path for the pixels the recurrence cannot serve: footprint crossing an image (or staged
 // rectangle) edge, half-width 0 or > 6, weights too small for the recurrence, absurd coordinates.
 // The reference's loop as coded (helpers.pyx:1678-1800, repairs R7/R9): a truncated tap adds its
 // weight but not its value; 'forbid' raises.  One exp2 per tap.
-__device__ __noinline__ void gauss_slow(const JacFastParams &P, const float *src_base, double px, double py,
-                                        float Aq, float Bq, float Cq, int half, float &val, float &wgt, int &state)
+struct SlowResult { float res; int state; };       // by value: reference arguments would live on the stack
+
+__device__ __noinline__ SlowResult gauss_slow(const JacFastParams &P, const float *src_base, double px, double py,
+                                              float Aq, float Bq, float Cq, int half)
 {
-    const double fxs = floor(px), fys = floor(py);
-    const long long xs = (long long)fxs, ys = (long long)fys;
-    const float xf_of = (float)(px - fxs), yf_of = (float)(py - fys);
-    val = 0.0f;
-    wgt = 0.0f;
+    long long xs, ys;
+    float xf_of, yf_of;
+    if ((fabs(px) < TFM_SANE_COORD) && (fabs(py) < TFM_SANE_COORD)) {
+        // the same (2^-23-quantised) floor and fraction as the recurrence path: which pixels take this
+        // path must not move a footprint window
+        int xi, yi;
+        floor_frac_fast(px, xi, xf_of);
+        floor_frac_fast(py, yi, yf_of);
+        xs = xi; ys = yi;
+    } else {
+        const double fxs = floor(px), fys = floor(py);
+        xs = (long long)fxs; ys = (long long)fys;
+        xf_of = (float)(px - fxs); yf_of = (float)(py - fys);
+    }
+    float val = 0.0f, wgt = 0.0f;
+    int state = 0;
     for (int yr = -half; yr <= half; ++yr) {
         const float y0 = (float)yr + yf_of;
         int sty = 0;
@@ -155,6 +301,10 @@ __device__ __noinline__ void gauss_slow(const JacFastParams &P, const float *src
             }
         }
     }
+    SlowResult out;
+    out.res = (wgt > 0.0f) ? val * fast_rcp(wgt) : 0.0f;
+    out.state = state;
+    return out;
 }
 
 // The footprint half-width is ceil(oblur / smin'): when fp32 cannot decide the ceil(), that one number
@@ -187,45 +337,85 @@ __device__ __forceinline__ void gaussian_quadratic(float a, float b, float c, fl
     inv_smin = fast_rsqrt(fp);
 }
 
-// One pixel, given its source position, the (scaled) quadratic form and the footprint half-width.
-// Returns val / wgt (0 when the footprint carries no weight or lies wholly beyond a truncated edge).
-template <int HALF_CT>     // > 0: compile-time half-width (constant-Jacobian kernel); 0: run time
-__device__ __forceinline__ float gauss_pixel(const JacFastParams &P, const float *__restrict__ src_base, double px, double py,
-                                             float Aq, float Bq, float Cq, float cA, float cB, float cC, int half_rt,
-                                             int &state)
+// Footprint set-up of one pixel: what the tap loop needs, 9 words.  off < 0: nothing left to do (the
+// pixel was all-out, or went through the slow path; `res` holds its value).
+struct TapRec {
+    int off;               // element offset of the window's first (aligned) tap inside the plane; tap mode 2:
+                           // x of the window's first texel + 2^20 (kept non-negative: < 0 means "no taps")
+    int ys;                // tap mode 2: y of the window's first texel
+    int half;              // half-width | first_out << 8
+    float w0, r0, rb;      // weight at the window's first tap, its ratio along the row, and to the next row
+    float res;             // value of a pixel that needs no taps
+};
+
+// Classifies the pixel (all-out / slow path / recurrence) and prepares the recurrence.  Pixels the
+// recurrence cannot serve are finished here, out of line.
+template <int TM>
+__device__ __forceinline__ TapRec gauss_setup(const JacFastParams &P, const float *__restrict__ src_base, double px, double py,
+                                              float Aq, float Bq, float Cq, int half, int &state)
 {
-    const int half = HALF_CT > 0 ? HALF_CT : half_rt;
-    float val = 0.0f, wgt = 0.0f;
+    TapRec rec;
+    constexpr bool CP = (TM == 1);
+    rec.off = -1; rec.ys = 0; rec.half = half; rec.w0 = 0.0f; rec.r0 = 0.0f; rec.rb = 0.0f; rec.res = 0.0f;
     const bool sane = (fabs(px) < TFM_SANE_COORD) && (fabs(py) < TFM_SANE_COORD);
-    if (!sane) {
-        if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) return 0.0f;      // NaN / inf (as tfm_jacobian.cu)
-        gauss_slow(P, src_base, px, py, Aq, Bq, Cq, half, val, wgt, state);
-        return (wgt > 0.0f) ? val * fast_rcp(wgt) : 0.0f;
+    bool fast = false;
+    int xi = 0, yi = 0, ox = 0, oy = 0;
+    float xf = 0.0f, yf = 0.0f;
+    if (sane) {
+        floor_frac_fast(px, xi, xf);
+        floor_frac_fast(py, yi, yf);
+        // a footprint entirely beyond a truncated edge: every tap is skipped, the pixel is 0 whatever the
+        // weights are (helpers.pyx:1793-1800)
+        if ((P.bound_x == TFM_B_TRUNCATE && (xi + half < 0 || xi - half >= P.full_w)) ||
+            (P.bound_y == TFM_B_TRUNCATE && (yi + half < 0 || yi - half >= P.full_h)))
+            return rec;
+        // whole footprint (plus the alignment column of the 8-byte form) inside the staged source
+        const int limx = P.src_w - 2 * half - (CP ? 1 : 0), limy = P.src_h - 2 * half;
+        ox = xi - half - P.src_x0;
+        oy = yi - half - P.src_y0;
+        const float hf1 = (float)(half + 1);
+        const bool inside = limx > 0 && limy > 0 && (unsigned)ox < (unsigned)limx && (unsigned)oy < (unsigned)limy;
+        fast = (inside || (TM == 2 && P.tex_edges)) &&
+               half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * (hf1 * hf1) < 100.0f;
+    } else if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) {
+        return rec;                                              // NaN / inf (as tfm_jacobian.cu)
     }
-    int xi, yi;
-    float xf, yf;
-    floor_frac_fast(px, xi, xf);
-    floor_frac_fast(py, yi, yf);
-    // a footprint entirely beyond a truncated edge: every tap is skipped, the pixel is 0 whatever the
-    // weights are (helpers.pyx:1793-1800)
-    if ((P.bound_x == TFM_B_TRUNCATE && (xi + half < 0 || xi - half >= P.full_w)) ||
-        (P.bound_y == TFM_B_TRUNCATE && (yi + half < 0 || yi - half >= P.full_h)))
-        return 0.0f;
-    const int limx = P.src_w - 2 * half, limy = P.src_h - 2 * half;
-    const int ox = xi - half - P.src_x0, oy = yi - half - P.src_y0;
-    const bool inside = limx > 0 && limy > 0 && (unsigned)ox < (unsigned)limx && (unsigned)oy < (unsigned)limy;
+    if (!fast) {
+        const SlowResult sr = gauss_slow(P, src_base, px, py, Aq, Bq, Cq, half);
+        state |= sr.state;
+        rec.res = sr.res;
+        return rec;
+    }
+    const bool first_out = CP && (ox & 1);
     const float hf = (float)half;
-    const float h2 = (hf + 1.0f) * (hf + 1.0f);
-    if (inside && half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * h2 < 100.0f) {
-        const float a0 = xf - hf, b0 = yf - hf;
-        const float w0 = fast_ex2(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
-        const float r0 = fast_ex2(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
-        const float rb = fast_ex2(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
-        const float *p0 = src_base + (oy * P.src_pe + ox);
-        if (HALF_CT > 0) gauss_taps2<(HALF_CT > 0 ? HALF_CT : 1)>(p0, P.src_pe, w0, r0, rb, cA, cB, cC, val, wgt);
-        else gauss_taps_any(half, p0, P.src_pe, w0, r0, rb, cA, cB, cC, val, wgt);
+    const float a0 = xf - hf - (first_out ? 1.0f : 0.0f), b0 = yf - hf;
+    rec.w0 = fast_ex2(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
+    rec.r0 = fast_ex2(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
+    rec.rb = fast_ex2(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
+    if (TM == 2) { rec.off = ox + (1 << 20); rec.ys = oy; }
+    else rec.off = oy * P.src_pe + (CP ? (ox & ~1) : ox);
+    rec.half = half | (first_out ? 256 : 0);
+    return rec;
+}
+
+// HALF_CT > 0: compile-time half-width (constant-Jacobian kernel); 0: run time.
+// TM: tap mode -- 0 four-byte loads (row pairs), 1 eight-byte loads (column pairs), 2 texture gather.
+template <int HALF_CT, int TM>
+__device__ __forceinline__ float gauss_run(const JacFastParams &P, const float *__restrict__ src_base, int off, int ys,
+                                           int half_fo, float w0, float r0, float rb, float cA, float cB, float cC)
+{
+    constexpr int H = (HALF_CT > 0 ? HALF_CT : 1);
+    const float *p0 = src_base + (TM == 2 ? 0 : off);
+    const int xs = off - (1 << 20);
+    const int pe = P.src_pe;
+    const bool first_out = (half_fo & 256) != 0;
+    float val = 0.0f, wgt = 0.0f;
+    if (HALF_CT > 0) {
+        if (TM == 2) gauss_taps_tex<H>(P.tex, xs, ys, w0, r0, rb, cA, cB, cC, val, wgt);
+        else if (TM == 1) gauss_taps_cp<H>(p0, pe, first_out, w0, r0, rb, cA, cB, cC, val, wgt);
+        else gauss_taps2<H>(p0, pe, w0, r0, rb, cA, cB, cC, val, wgt);
     } else {
-        gauss_slow(P, src_base, px, py, Aq, Bq, Cq, half, val, wgt, state);
+        gauss_taps_any<TM>(P.tex, xs, ys, half_fo & 255, p0, pe, first_out, w0, r0, rb, cA, cB, cC, val, wgt);
     }
     return (wgt > 0.0f) ? val * fast_rcp(wgt) : 0.0f;
 }
@@ -242,8 +432,14 @@ __device__ __forceinline__ void patch_xy(int lw, int tid, int &tx, int &ty)
 // ---------------------------------------------------------------------------------------------
 // constant-Jacobian kernel
 // ---------------------------------------------------------------------------------------------
-template <int HALF>
-__global__ void __launch_bounds__(256, 4)
+#ifndef TFM_K2F_MINBLOCKS
+#define TFM_K2F_MINBLOCKS 4
+#endif
+#ifndef TFM_K2F_TWOPHASE
+#define TFM_K2F_TWOPHASE 0
+#endif
+template <int HALF, int TM>
+__global__ void __launch_bounds__(256, TFM_K2F_MINBLOCKS)
 k_jac_gauss_const(const __grid_constant__ JacFastParams P)
 {
     const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
@@ -262,7 +458,10 @@ k_jac_gauss_const(const __grid_constant__ JacFastParams P)
         if (Y0 + 8 * j >= P.dst_h) break;
         const double px = fma(P.aff[0], gxd, fma(P.aff[1], gyd, P.aff[4]));
         const double py = fma(P.aff[2], gxd, fma(P.aff[3], gyd, P.aff[5]));
-        float res = gauss_pixel<HALF>(P, src_base, px, py, P.Aq, P.Bq, P.Cq, P.cA, P.cB, P.cC, P.half, state);
+        const TapRec rec = gauss_setup<TM>(P, src_base, px, py, P.Aq, P.Bq, P.Cq, HALF > 0 ? HALF : P.half, state);
+        float res = rec.res;
+        if (rec.off >= 0)
+            res = gauss_run<HALF, TM>(P, src_base, rec.off, rec.ys, rec.half, rec.w0, rec.r0, rec.rb, P.cA, P.cB, P.cC);
         if (P.flux) res *= P.det;
         *drow = res;
         drow += 8 * P.dst_pe;
@@ -274,18 +473,28 @@ k_jac_gauss_const(const __grid_constant__ JacFastParams P)
 // ---------------------------------------------------------------------------------------------
 // analytic polar kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4)
+// Two phases per thread, joined by a 9-word record per pixel in shared memory (written and read by
+// the same thread: no barrier):
+//   A  source position, closed-form Jacobian, padded quadratic form, footprint size, recurrence set-up
+//   B  the tap loops
+// In one loop the two halves compete for 64 registers: ncu showed ~25 % of the L1 wavefronts of the
+// one-phase form to be spill traffic and every launch constant re-fetched per pixel.  Apart, phase A
+// keeps its constants in registers and phase B holds nothing but tap state.
+template <int TM>
+__global__ void __launch_bounds__(256, TFM_K2F_MINBLOCKS)
 k_jac_gauss_polar(const __grid_constant__ JacFastParams P)
 {
     constexpr int TN = FT + 2;              // table entries: grid points G0-1 .. G0+FT (edge-copy clamp reach)
     __shared__ double2 s_ta[TN], s_tb[TN];  // (cos, sin)(i tX), (cos, sin)(theta(X0, Y0) + j tY)
     __shared__ double s_ea[TN], s_eb[TN];   // log-polar: exp(i a10), r0 exp(rho(X0, Y0) + j a11)
-    __shared__ float2 s_taf[TN], s_tbf[TN]; // fp32 copies for the Jacobian
-    __shared__ float s_eaf[TN], s_ebf[TN];
+#if TFM_K2F_TWOPHASE
+    __shared__ float4 s_r0[4][256];         // w0, r0, rb, cA
+    __shared__ float4 s_r1[4][256];         // cB, cC, res / flux factor, bits of off
+    __shared__ int2 s_r2[4][256];           // half | first_out << 8 (-1: row beyond the output), window row (tap mode 2)
+#endif
 
     const int tid = threadIdx.x;
     const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
-    float *const dst_base = P.dst + (long long)blockIdx.z * P.dst_plane;
     const int GX0 = P.dst_x0 + (int)blockIdx.x * FT, GY0 = P.dst_y0 + (int)blockIdx.y * FT;
     const double X0 = (double)(GX0 - 1), Y0d = (double)(GY0 - 1);
     const bool lg = P.lg != 0;
@@ -296,18 +505,15 @@ k_jac_gauss_polar(const __grid_constant__ JacFastParams P)
         if (tid < TN) {
             sincos((double)tid * tX, &s, &c);
             s_ta[tid] = make_double2(c, s);
-            s_taf[tid] = make_float2((float)c, (float)s);
-            if (lg) { const double e = exp((double)tid * P.pa[2]); s_ea[tid] = e; s_eaf[tid] = (float)e; }
+            if (lg) s_ea[tid] = exp((double)tid * P.pa[2]);
         } else {
             const int j = tid - TN;
             const double t0 = fma(P.pa[0], X0, fma(P.pa[1], Y0d, P.pa[4])) * P.coeff;
             sincos(fma((double)j, tY, t0), &s, &c);
             s_tb[j] = make_double2(c, s);
-            s_tbf[j] = make_float2((float)c, (float)s);
             if (lg) {
                 const double rho0 = fma(P.pa[2], X0, fma(P.pa[3], Y0d, P.pa[5]));
-                const double e = P.r0 * exp(fma((double)j, P.pa[3], rho0));
-                s_eb[j] = e; s_ebf[j] = (float)e;
+                s_eb[j] = P.r0 * exp(fma((double)j, P.pa[3], rho0));
             }
         }
     }
@@ -318,67 +524,102 @@ k_jac_gauss_polar(const __grid_constant__ JacFastParams P)
     const int X = blockIdx.x * FT + tx;
     if (X >= P.dst_w) return;
     const int Yt = blockIdx.y * FT + ty;
-    const int gx = P.dst_x0 + X;
-    const int GW = P.grid_w, GH = P.grid_h;
-    // Jacobian column of this thread: edge columns copy their inner neighbour (helpers.pyx:1244-1247)
-    const int jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
-    const int cti = jx - (GX0 - 1);
-    const double2 ta = s_ta[tx + 1];
-    const float2 taf = s_taf[cti];
-    const double gxd = (double)gx;
-    double gyd = (double)(P.dst_y0 + Yt);
-    const float sgn = P.ccw ? 1.0f : -1.0f;
-    // radius (linear form) at the table origin, fp32, for the Jacobian
-    const float rb32 = (float)fma(P.pa[2], X0, fma(P.pa[3], Y0d, P.pa[5]));
-    const float rcol32 = fmaf(P.p2f, (float)cti, rb32);
     int state = 0;
-    float *drow = dst_base + (long long)Yt * P.dst_pe + X;
+
+    // ------------------------------- phase A -------------------------------
+    {
+        const int gx = P.dst_x0 + X;
+        const int GW = P.grid_w, GH = P.grid_h;
+        const double2 ta = s_ta[tx + 1];
+        const double gxd = (double)gx;
+        double gyd = (double)(P.dst_y0 + Yt);
+        const float sgn = P.ccw ? 1.0f : -1.0f;
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        const int ly = ty + 8 * j;
-        if (Yt + 8 * j >= P.dst_h) break;
-        const int gy = P.dst_y0 + Yt + 8 * j;
-        // ---- source position (fp64): cos/sin by angle addition from the tables ----
-        const double2 tb = s_tb[ly + 1];
-        const double c = ta.x * tb.x - ta.y * tb.y, s = ta.y * tb.x + ta.x * tb.y;
-        const double r = lg ? s_ea[tx + 1] * s_eb[ly + 1] : fma(P.pa[2], gxd, fma(P.pa[3], gyd, P.pa[5]));
-        const double x1 = fma(c, r, P.ox), y1 = fma(P.ccw ? s : -s, r, P.oy);
-        double px = x1, py = y1;
-        if (P.has_a2) {
-            px = fma(P.a2[0], x1, fma(P.a2[1], y1, P.a2[4]));
-            py = fma(P.a2[2], x1, fma(P.a2[3], y1, P.a2[5]));
+        for (int j = 0; j < 4; ++j, gyd += 8.0) {
+            const int ly = ty + 8 * j;
+#if TFM_K2F_TWOPHASE
+            if (Yt + 8 * j >= P.dst_h) { s_r2[j][tid] = make_int2(-1, 0); continue; }
+#else
+            if (Yt + 8 * j >= P.dst_h) break;
+#endif
+            const int gy = P.dst_y0 + Yt + 8 * j;
+            // ---- source position (fp64): cos/sin by angle addition from the tables ----
+            const double2 tb = s_tb[ly + 1];
+            double c = ta.x * tb.x - ta.y * tb.y, s = ta.y * tb.x + ta.x * tb.y;
+            double r = lg ? s_ea[tx + 1] * s_eb[ly + 1] : fma(P.pa[2], gxd, fma(P.pa[3], gyd, P.pa[5]));
+            const double x1 = fma(c, r, P.ox), y1 = fma(P.ccw ? s : -s, r, P.oy);
+            double px = x1, py = y1;
+            if (P.has_a2) {
+                px = fma(P.a2[0], x1, fma(P.a2[1], y1, P.a2[4]));
+                py = fma(P.a2[2], x1, fma(P.a2[3], y1, P.a2[5]));
+            }
+            // ---- closed-form Jacobian, fp32.  Grid-edge pixels copy their inner neighbour
+            // (helpers.pyx:1244-1247): there (only) cos, sin and radius are re-derived at the clamped point.
+            // Inputs are rounded from the fp64 values of the pixel, which do not depend on how the grid
+            // is tiled: row-block shards reproduce the full frame.
+            const int jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
+            const int jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
+            if (jx != gx || jy != gy) {
+                const double2 ca = s_ta[jx - (GX0 - 1)], cb = s_tb[jy - (GY0 - 1)];
+                c = ca.x * cb.x - ca.y * cb.y;
+                s = ca.y * cb.x + ca.x * cb.y;
+                r = lg ? s_ea[jx - (GX0 - 1)] * s_eb[jy - (GY0 - 1)]
+                       : fma(P.pa[2], (double)jx, fma(P.pa[3], (double)jy, P.pa[5]));
+            }
+            const float cf = (float)c, sf = (float)s, rf = (float)r;
+            const float drX = lg ? rf * P.p2f : P.p2f, drY = lg ? rf * P.p3f : P.p3f;
+            const float rs = rf * sf, rc = rf * cf;
+            // x1 = r cos + ox, y1 = sgn r sin + oy
+            float j00 = fmaf(cf, drX, -rs * P.tXf), j01 = fmaf(cf, drY, -rs * P.tYf);
+            float j10 = sgn * fmaf(sf, drX, rc * P.tXf), j11 = sgn * fmaf(sf, drY, rc * P.tYf);
+            if (P.has_a2) {
+                const float k00 = P.a2f[0] * j00 + P.a2f[1] * j10, k01 = P.a2f[0] * j01 + P.a2f[1] * j11;
+                const float k10 = P.a2f[2] * j00 + P.a2f[3] * j10, k11 = P.a2f[2] * j01 + P.a2f[3] * j11;
+                j00 = k00; j01 = k01; j10 = k10; j11 = k11;
+            }
+            // ---- padded quadratic form and footprint size ----
+            float q00, q01, q11, inv_smin;
+            gaussian_quadratic(j00, j01, j10, j11, P.padval, P.half_pow, P.m2_over_pow, q00, q01, q11, inv_smin);
+            float ratio = P.ob * inv_smin;
+            if (fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) ratio = exact_half_ratio(P, j00, j01, j10, j11);
+            int half = (ratio < 1.0e9f) ? __float2int_ru(ratio) : 1000000000;
+            half = min(half, P.max_half);
+            const float Aq = q00 * P.qscale, Bq = q01 * P.qscale, Cq = q11 * P.qscale;
+            const TapRec rec = gauss_setup<TM>(P, src_base, px, py, Aq, Bq, Cq, half, state);
+            const float fl = P.flux ? fabsf(j00 * j11 - j01 * j10) : 1.0f;
+#if TFM_K2F_TWOPHASE
+            s_r0[j][tid] = make_float4(rec.w0, rec.r0, rec.rb, fast_ex2(-2.0f * Aq));
+            s_r1[j][tid] = make_float4(fast_ex2(-2.0f * Bq), fast_ex2(-2.0f * Cq), rec.off >= 0 ? fl : rec.res * fl,
+                                       __int_as_float(rec.off));
+            s_r2[j][tid] = make_int2(rec.half, rec.ys);
+#else
+            float res = rec.res * fl;
+            if (rec.off >= 0)
+                res = fl * gauss_run<0, TM>(P, src_base, rec.off, rec.ys, rec.half, rec.w0, rec.r0, rec.rb,
+                                            fast_ex2(-2.0f * Aq), fast_ex2(-2.0f * Bq), fast_ex2(-2.0f * Cq));
+            P.dst[(long long)blockIdx.z * P.dst_plane + (long long)(Yt + 8 * j) * P.dst_pe + X] = res;
+#endif
         }
-        // ---- closed-form Jacobian at the (edge-clamped) grid point, fp32 ----
-        const int jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
-        const int ctj = jy - (GY0 - 1);
-        const float2 tbf = s_tbf[ctj];
-        const float cf = taf.x * tbf.x - taf.y * tbf.y, sf = taf.y * tbf.x + taf.x * tbf.y;
-        const float rf = lg ? s_eaf[cti] * s_ebf[ctj] : fmaf(P.p3f, (float)ctj, rcol32);
-        const float drX = lg ? rf * P.p2f : P.p2f, drY = lg ? rf * P.p3f : P.p3f;
-        const float rs = rf * sf, rc = rf * cf;
-        // x1 = r cos + ox, y1 = sgn r sin + oy
-        float j00 = fmaf(cf, drX, -rs * P.tXf), j01 = fmaf(cf, drY, -rs * P.tYf);
-        float j10 = sgn * fmaf(sf, drX, rc * P.tXf), j11 = sgn * fmaf(sf, drY, rc * P.tYf);
-        if (P.has_a2) {
-            const float k00 = P.a2f[0] * j00 + P.a2f[1] * j10, k01 = P.a2f[0] * j01 + P.a2f[1] * j11;
-            const float k10 = P.a2f[2] * j00 + P.a2f[3] * j10, k11 = P.a2f[2] * j01 + P.a2f[3] * j11;
-            j00 = k00; j01 = k01; j10 = k10; j11 = k11;
-        }
-        // ---- padded quadratic form and footprint size ----
-        float q00, q01, q11, inv_smin;
-        gaussian_quadratic(j00, j01, j10, j11, P.padval, P.half_pow, P.m2_over_pow, q00, q01, q11, inv_smin);
-        float ratio = P.ob * inv_smin;
-        if (fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) ratio = exact_half_ratio(P, j00, j01, j10, j11);
-        int half = (ratio < 1.0e9f) ? __float2int_ru(ratio) : 1000000000;
-        half = min(half, P.max_half);
-        const float Aq = q00 * P.qscale, Bq = q01 * P.qscale, Cq = q11 * P.qscale;
-        const float cA = fast_ex2(-2.0f * Aq), cB = fast_ex2(-2.0f * Bq), cC = fast_ex2(-2.0f * Cq);
-        float res = gauss_pixel<0>(P, src_base, px, py, Aq, Bq, Cq, cA, cB, cC, half, state);
-        if (P.flux) res *= fabsf(j00 * j11 - j01 * j10);
-        *drow = res;
-        drow += 8 * P.dst_pe;
-        gyd += 8.0;
     }
+
+#if TFM_K2F_TWOPHASE
+    // ------------------------------- phase B -------------------------------
+    float *drow = P.dst + (long long)blockIdx.z * P.dst_plane + (long long)Yt * P.dst_pe + X;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j, drow += 8 * P.dst_pe) {
+        const int2 hy = s_r2[j][tid];
+        const int hf = hy.x;
+        if (hf < 0) break;                                       // rows beyond the output
+        const float4 b = s_r1[j][tid];
+        const int off = __float_as_int(b.w);
+        float res = b.z;
+        if (off >= 0) {
+            const float4 a = s_r0[j][tid];
+            res *= gauss_run<0, TM>(P, src_base, off, hy.y, hf, a.x, a.y, a.z, a.w, b.x, b.y);
+        }
+        *drow = res;
+    }
+#endif
     if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
 }
 
@@ -458,6 +699,18 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
 
     dim3 grid((unsigned)((P.dst_w + FT - 1) / FT), (unsigned)((P.dst_h + FT - 1) / FT), (unsigned)s.n_planes);
     if (grid.y > 65535u) return 0;
+    // tap mode: texture gather where a pitch-linear texture can be laid over the source (one plane,
+    // geometry within the 2-D texture limits), else 8-byte loads where rows are 8-byte aligned, else
+    // 4-byte loads.  Tuning bits 4096 / 32768 force the 4-byte / 8-byte form for A/B runs.
+    int tm = 0;
+    if (!(a->tuning & 4096) && (reinterpret_cast<uintptr_t>(s.data) % 8) == 0 && (s.pitch % 8) == 0 &&
+        (s.plane_pitch % 8) == 0)
+        tm = 1;
+    if (!(a->tuning & (4096 | 32768)) && s.n_planes == 1 && s.w <= 131072 && s.h <= 65000 && (s.pitch % 32) == 0 &&
+        (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 && get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &P.tex))
+        tm = 2;
+    const bool whole = (s.x0 == 0 && s.y0 == 0 && s.full_h == s.h && s.full_w == s.w);
+    P.tex_edges = (tm == 2 && whole && a->bound_x == TFM_B_TRUNCATE && a->bound_y == TFM_B_TRUNCATE) ? 1 : 0;
 
     bool lin = true;
     for (int i = 0; i < a->n_ops; ++i) lin = lin && is_linear_like(a->chain[i]);
@@ -489,17 +742,23 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
         P.lw = 4;
         if (a->tuning & 1024) P.lw = 5;
         if (a->tuning & 2048) P.lw = 3;
+#define TFM_CJ(H)                                                              \
+        if (tm == 2) k_jac_gauss_const<H, 2><<<grid, 256, 0, st>>>(P);          \
+        else if (tm == 1) k_jac_gauss_const<H, 1><<<grid, 256, 0, st>>>(P);     \
+        else k_jac_gauss_const<H, 0><<<grid, 256, 0, st>>>(P)
         switch (P.half) {
-        case 1: k_jac_gauss_const<1><<<grid, 256, 0, st>>>(P); break;
-        case 2: k_jac_gauss_const<2><<<grid, 256, 0, st>>>(P); break;
-        case 3: k_jac_gauss_const<3><<<grid, 256, 0, st>>>(P); break;
-        case 4: k_jac_gauss_const<4><<<grid, 256, 0, st>>>(P); break;
-        case 5: k_jac_gauss_const<5><<<grid, 256, 0, st>>>(P); break;
-        case 6: k_jac_gauss_const<6><<<grid, 256, 0, st>>>(P); break;
-        default: k_jac_gauss_const<0><<<grid, 256, 0, st>>>(P); break;   // every pixel takes the slow path
+        case 1: TFM_CJ(1); break;
+        case 2: TFM_CJ(2); break;
+        case 3: TFM_CJ(3); break;
+        case 4: TFM_CJ(4); break;
+        case 5: TFM_CJ(5); break;
+        case 6: TFM_CJ(6); break;
+        default: TFM_CJ(0); break;                               // every pixel takes the slow path
         }
+#undef TFM_CJ
         count_launch();
-        set_last_kernel("k_jacobian<fast32,const-J>");
+        set_last_kernel(tm == 2 ? "k_jacobian<fast32,const-J,tex>"
+                                : (tm == 1 ? "k_jacobian<fast32,const-J,ld64>" : "k_jacobian<fast32,const-J,ld32>"));
         *rc = cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
         return 1;
     }
@@ -534,9 +793,12 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
     if (a->tuning & 1024) P.lw = 5;
     if (a->tuning & 2048) P.lw = 2;
     if (a->tuning & 16384) P.lw = 4;
-    k_jac_gauss_polar<<<grid, 256, 0, st>>>(P);
+    if (tm == 2) k_jac_gauss_polar<2><<<grid, 256, 0, st>>>(P);
+    else if (tm == 1) k_jac_gauss_polar<1><<<grid, 256, 0, st>>>(P);
+    else k_jac_gauss_polar<0><<<grid, 256, 0, st>>>(P);
     count_launch();
-    set_last_kernel("k_jacobian<fast32,analytic-polar>");
+    set_last_kernel(tm == 2 ? "k_jacobian<fast32,analytic-polar,tex>"
+                            : (tm == 1 ? "k_jacobian<fast32,analytic-polar,ld64>" : "k_jacobian<fast32,analytic-polar,ld32>"));
     *rc = cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
     return 1;
 }

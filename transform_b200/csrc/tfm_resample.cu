@@ -67,13 +67,13 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
 
     double cx[NPX], cy[NPX];
     if (AFF) {
+        // canonical form of every fast-mode kernel: c = fma(a0, X, fma(a1, Y, b)) on exact doubles X, Y
         const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y0);
-        const double bx = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
-        const double by = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
 #pragma unroll
         for (int j = 0; j < NPX; ++j) {
-            cx[j] = fma((double)(8 * j), P.aff[1], bx);
-            cy[j] = fma((double)(8 * j), P.aff[3], by);
+            const double Yj = Yd + (double)(8 * j);
+            cx[j] = fma(P.aff[0], Xd, fma(P.aff[1], Yj, P.aff[4]));
+            cy[j] = fma(P.aff[2], Xd, fma(P.aff[3], Yj, P.aff[5]));
         }
     } else if (P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_POLAR) {
         // polar prefix: 32 + 32 sincos per tile through the angle-addition tables (tfm_chain.cuh)
@@ -107,7 +107,12 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
         // NaN / inf / absurd coordinate -> far outside the texture (border = 0); the compare is only
         // needed when the host could not bound the coordinates
         if (!(AFF && P.aff_bounded)) {
-            if (!((fabs(cx[j]) < TFM_SANE_COORD) && (fabs(cy[j]) < TFM_SANE_COORD))) { ix = -100000; iy = -100000; fx[j] = 0.f; fy[j] = 0.f; }
+            if (!((fabs(cx[j]) < TFM_SANE_COORD) && (fabs(cy[j]) < TFM_SANE_COORD))) {
+                // far outside the texture (border = 0); a non-finite coordinate makes the weights NaN, as in the
+                // reference (alpha = v - floor(v)), an absurd finite one leaves them 0
+                ix = -100000; iy = -100000;
+                fx[j] = (float)(cx[j] - cx[j]); fy[j] = (float)(cy[j] - cy[j]);
+            }
         }
         // unnormalised coordinates: the bilinear footprint of (u,v) is texels floor(u-0.5)+{0,1},
         // so (ix+1, iy+1) selects columns ix, ix+1 and rows iy, iy+1
@@ -126,30 +131,33 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
 }
 
 // ---------------------------------------------------------------------------------------------
-// texture-gather variant, second form: 4 CONSECUTIVE output pixels per thread, one 16-byte store
+// texture-gather variant, second form: 4 pixels of ONE output row per thread
 // ---------------------------------------------------------------------------------------------
 // ncu on k_resample_tex (8192^2, pure shift, profiles/r2_k1.md): 60.8 instructions per pixel at 83 %
 // issue utilisation -- the kernel was issue-bound before it was texture-bound.  Of the 60.8, 16 were
-// the per-thread share of the empty-tile test, 14 the four scalar stores with their bounds checks and
-// 64-bit address arithmetic, 20 the two floor/fraction extractions.  Here:
-//   * a thread owns pixels (X .. X+3, Y): coordinates advance by one DFMA per axis, the four results
-//     leave in ONE st.global.v4 (a warp writes four full 128-byte rows segments);
-//   * a warp covers a 32 x 4 patch (8 lanes x 4 pixels wide), so the footprints of one TLD4 stay as
-//     compact as with the 16 x 2 patch of the first form;
-//   * the empty-tile test works from the tile centre and a host-computed half-extent (10 instructions);
+// the per-thread share of the empty-tile test, 14 the four stores (each with its own bounds check and
+// 64-bit row address), 20 the two floor/fraction extractions.  Here:
+//   * a thread owns pixels (X, X+8, X+16, X+24) of row Y: one row pointer, four stores at immediate
+//     offsets, the row part fma(a1, Y, b) of the coordinates shared by the four pixels;
+//   * a warp covers an 8 x 4 patch per TLD4, so the 32 footprints of one instruction stay compact.
+//     (Four CONSECUTIVE pixels per thread and one st.global.v4 were built first: 35.8 instructions
+//     per pixel, but 0.192 ms instead of 0.143 -- lanes 4 pixels apart make every TLD4 touch 2.7x the
+//     sectors and the L1TEX sector stage saturates at 92 %.  Scalar stores of 8 consecutive pixels
+//     x 4 rows fill whole 32-byte sectors anyway.)
+//   * the empty-tile test works from the tile centre and a host-computed half-extent;
 //   * floor/fraction in fixed point (floor_frac_fast).
 template <class A, bool AFF, int SPH>
 __global__ void __launch_bounds__(256)
 k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = (lane & 7) << 2;
+    const int px = lane & 7;
     const int py = (warp << 2) + (lane >> 3);
     const int X = blockIdx.x * 32 + px;
     const int Y = blockIdx.y * 32 + py;
     float *const drow = reinterpret_cast<float *>(static_cast<char *>(P.dst) + (long long)Y * P.dst_pitch) + X;
     const bool row_in = Y < P.dst_h;
-    const bool vec = row_in && (X + 3 < P.dst_w) && P.dst_vec4;
+    const bool full = row_in && (blockIdx.x * 32 + 32 <= (unsigned)P.dst_w);
 
     // AFF instantiations are launched only when the host has bounded the coordinates (P.aff_bounded)
     if (AFF) {                             // CTA-uniform rejection of empty tiles: centre +- half-extent
@@ -157,11 +165,11 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
         const float cxc = fmaf(P.aff_f[0], xc, fmaf(P.aff_f[1], yc, P.aff_c[0]));
         const float cyc = fmaf(P.aff_f[2], xc, fmaf(P.aff_f[3], yc, P.aff_c[1]));
         if (cxc < -P.aff_c[2] || cxc > P.aff_lim[0] || cyc < -P.aff_c[3] || cyc > P.aff_lim[1]) {
-            if (vec) *reinterpret_cast<float4 *>(drow) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (full) { drow[0] = 0.f; drow[8] = 0.f; drow[16] = 0.f; drow[24] = 0.f; }
             else if (row_in) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (X + j < P.dst_w) drow[j] = 0.0f;
+                    if (X + 8 * j < P.dst_w) drow[8 * j] = 0.0f;
             }
             return;
         }
@@ -169,13 +177,14 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
 
     double cx[4], cy[4];
     if (AFF) {
+        // canonical form of every fast-mode kernel: c = fma(a0, X, fma(a1, Y, b)) on exact doubles X, Y
         const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y);
-        cx[0] = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
-        cy[0] = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
+        const double rx = fma(P.aff[1], Yd, P.aff[4]), ry = fma(P.aff[3], Yd, P.aff[5]);
 #pragma unroll
-        for (int j = 1; j < 4; ++j) {
-            cx[j] = fma((double)j, P.aff[0], cx[0]);
-            cy[j] = fma((double)j, P.aff[2], cy[0]);
+        for (int j = 0; j < 4; ++j) {
+            const double Xj = Xd + (double)(8 * j);
+            cx[j] = fma(P.aff[0], Xj, rx);
+            cy[j] = fma(P.aff[2], Xj, ry);
         }
     } else if (P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_POLAR) {
         __shared__ double2 s_ta[32], s_tb[32];
@@ -187,12 +196,12 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            polar_from_tables(op0, TX0, TY0, px + j, py, s_ta, s_tb, s_ea, s_eb, cx[j], cy[j]);
+            polar_from_tables(op0, TX0, TY0, px + 8 * j, py, s_ta, s_tb, s_ea, s_eb, cx[j], cy[j]);
         chain_eval_n<A, SPH, 4>(P.chain, cx, cy, 1);
     } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            cx[j] = (double)(P.dst_x0 + X + j);
+            cx[j] = (double)(P.dst_x0 + X + 8 * j);
             cy[j] = (double)(P.dst_y0 + Y);
         }
         chain_eval_n<A, SPH, 4>(P.chain, cx, cy);
@@ -206,7 +215,12 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
         floor_frac_fast(cx[j], ix, fx[j]);
         floor_frac_fast(cy[j], iy, fy[j]);
         if (!AFF) {                          // NaN / inf / absurd coordinate -> far outside the texture (border = 0)
-            if (!((fabs(cx[j]) < TFM_SANE_COORD) && (fabs(cy[j]) < TFM_SANE_COORD))) { ix = -100000; iy = -100000; fx[j] = 0.f; fy[j] = 0.f; }
+            if (!((fabs(cx[j]) < TFM_SANE_COORD) && (fabs(cy[j]) < TFM_SANE_COORD))) {
+                // far outside the texture (border = 0); a non-finite coordinate makes the weights NaN, as in the
+                // reference (alpha = v - floor(v)), an absurd finite one leaves them 0
+                ix = -100000; iy = -100000;
+                fx[j] = (float)(cx[j] - cx[j]); fy[j] = (float)(cy[j] - cy[j]);
+            }
         }
         g[j] = tex2Dgather<float4>(tex, (float)(ix + 1), (float)(iy + 1), 0);
     }
@@ -219,11 +233,11 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
         const float bot = fmaf(fx[j], v11 - v10, v10);
         r[j] = fmaf(fy[j], bot - top, top);
     }
-    if (vec) *reinterpret_cast<float4 *>(drow) = make_float4(r[0], r[1], r[2], r[3]);
+    if (full) { drow[0] = r[0]; drow[8] = r[1]; drow[16] = r[2]; drow[24] = r[3]; }
     else if (row_in) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (X + j < P.dst_w) drow[j] = r[j];
+            if (X + 8 * j < P.dst_w) drow[8 * j] = r[j];
     }
 }
 
@@ -239,7 +253,7 @@ static TexKey g_tex_keys[16];
 static cudaTextureObject_t g_tex_objs[16];
 static int g_tex_n = 0, g_tex_next = 0;
 
-static bool get_texture(const void *ptr, int w, int h, long long pitch, cudaTextureObject_t *out)
+bool get_texture(const void *ptr, int w, int h, long long pitch, cudaTextureObject_t *out)
 {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -368,13 +382,12 @@ k_resample_tma(const __grid_constant__ ResampleParams P, const __grid_constant__
     int lx[NPX], ly[NPX];
     {
         const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y0);
-        const double bx = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
-        const double by = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
 #pragma unroll
         for (int j = 0; j < NPX; ++j) {
             int ix, iy;
-            floor_frac_fast(fma((double)(8 * j), P.aff[1], bx), ix, fx[j]);
-            floor_frac_fast(fma((double)(8 * j), P.aff[3], by), iy, fy[j]);
+            const double Yj = Yd + (double)(8 * j);
+            floor_frac_fast(fma(P.aff[0], Xd, fma(P.aff[1], Yj, P.aff[4])), ix, fx[j]);
+            floor_frac_fast(fma(P.aff[2], Xd, fma(P.aff[3], Yj, P.aff[5])), iy, fy[j]);
             lx[j] = ix - bx0;
             ly[j] = iy - by0;
         }
@@ -556,7 +569,6 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         P.aff_lim[0] = (float)s.w + P.aff_c[2];
         P.aff_lim[1] = (float)s.h + P.aff_c[3];
     }
-    P.dst_vec4 = ((d.pitch % 16) == 0 && (reinterpret_cast<uintptr_t>(d.data) % 16) == 0) ? 1 : 0;
     if (is_filter) {
         static const int base_size[] = {16, 6, 8, 2, 2, 2};                           // helpers.pyx:708
         FilterParams F;

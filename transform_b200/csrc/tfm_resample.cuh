@@ -37,7 +37,6 @@ struct ResampleParams {
                                              // the centre of tile (0,0) relative to the output origin, and the
                                              // half-extents (footprint, safety margin and rounding allowance included)
     float aff_lim[2];                        // src_w + aff_c[2], src_h + aff_c[3]
-    int dst_vec4;                            // dst rows are 16-byte aligned: four pixels leave in one store
     double fill;
     int *status;
     int win_method;                          // TFM_WIN2 kernels: which window (TFM_HANN / TFM_TUKEY / TFM_TENT ...)
@@ -429,13 +428,13 @@ k_resample(const __grid_constant__ ResampleParams P)
     // ---- phase 1: coordinates (fp64, in registers) ----
     double cx[NPX], cy[NPX];
     if (AFF) {
+        // canonical form of every fast-mode kernel: c = fma(a0, X, fma(a1, Y, b)) on exact doubles X, Y
         const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y0);
-        const double bx = fma(P.aff[0], Xd, fma(P.aff[1], Yd, P.aff[4]));
-        const double by = fma(P.aff[2], Xd, fma(P.aff[3], Yd, P.aff[5]));
 #pragma unroll
         for (int j = 0; j < NPX; ++j) {
-            cx[j] = fma((double)(8 * j), P.aff[1], bx);
-            cy[j] = fma((double)(8 * j), P.aff[3], by);
+            const double Yj = Yd + (double)(8 * j);
+            cx[j] = fma(P.aff[0], Xd, fma(P.aff[1], Yj, P.aff[4]));
+            cy[j] = fma(P.aff[2], Xd, fma(P.aff[3], Yj, P.aff[5]));
         }
     } else {
 #pragma unroll
@@ -472,7 +471,12 @@ k_resample(const __grid_constant__ ResampleParams P)
             // false for NaN / inf / absurd.  For host-composed affine maps the host has bounded
             // |coordinate| over the whole output grid (P.aff_bounded): nothing to test per pixel.
             if (AFF) sane[j] = true;
-            else sane[j] = (fabs(x) < TFM_SANE_COORD) && (fabs(y) < TFM_SANE_COORD);
+            else {
+                sane[j] = (fabs(x) < TFM_SANE_COORD) && (fabs(y) < TFM_SANE_COORD);
+                // the fixed-point fraction is meaningless out there: NaN for a non-finite coordinate (the
+                // reference's alpha = v - floor(v)), 0 for an absurd finite one
+                if (FASTI && !sane[j]) { ffx[j] = (float)(x - x); ffy[j] = (float)(y - y); }
+            }
         }
         const int pe = (int)(P.src_pitch / (long long)sizeof(SrcT));       // host guarantees h*pe < 2^31
         // CTA-uniform: the whole 32 x (8*NPX) tile lies inside the output and (AFF) coordinates are

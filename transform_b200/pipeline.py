@@ -22,15 +22,21 @@ from . import _device as dev
 class Ticket:
     """Handle of one submitted call: `.result()` waits for its output buffer to be complete."""
 
-    def __init__(self, event, out):
+    def __init__(self, event, out, status_host=None):
         self._event = event
         self._out = out
+        self._status = status_host
 
     def done(self):
         return self._event.query()
 
     def result(self):
+        """Wait for the call; raises what the synchronous call would have raised ('forbid' boundary
+        violated -> ValueError), read from the status word that travelled back with the result."""
         self._event.synchronize()
+        if self._status is not None:
+            from . import _engine
+            _engine.raise_for_status_bits(int(self._status[0]))
         return self._out
 
 
@@ -43,6 +49,8 @@ class AsyncResampler:
         self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._streams = [torch.cuda.Stream(device=self._device) for _ in range(depth)]
         self._events = [None] * depth
+        # one pinned status word per slot: a 'forbid' boundary does not serialise the pipeline
+        self._status = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(depth)]
         self._next = 0
 
     def submit(self, transform, data, out, method='n', bound='t', **kw):
@@ -60,12 +68,15 @@ class AsyncResampler:
             prev.synchronize()               # bound the queue: at most `depth` calls in flight
         # work submitted by the caller on the current stream (e.g. filling `data`) comes first
         stream.wait_stream(torch.cuda.current_stream(self._device))
+        status_host = self._status[slot]
+        status_host.zero_()
         with torch.cuda.stream(stream):
-            transform.resample(data, method=method, bound=bound, out=out, sync=False, **kw)
+            transform.resample(data, method=method, bound=bound, out=out, sync=False,
+                               status_host=status_host, **kw)
             ev = torch.cuda.Event()
             ev.record(stream)
         self._events[slot] = ev
-        return Ticket(ev, out)
+        return Ticket(ev, out, status_host)
 
     def drain(self):
         for ev in self._events:
