@@ -108,6 +108,9 @@ def _setup(kind, n, src):
         return _linear_rows, impl
     if kind == "jacobian":
         _G["jchain"] = radial_chain(n)
+        # interpND_grid converts the frame to float64 once per call (helpers.pyx:1520); row blocks of ONE
+        # call share that copy
+        _G["src64"] = np.ascontiguousarray(src, dtype=np.float64)
         o.clib()                      # build/load the C restatement before forking
         return _jacobian_rows, impl
     raise ValueError(kind)

@@ -366,3 +366,74 @@ def test_c_example_matches_python_path(tfm, tmp_path):
     tr = tfm.Composition([tfm.Scale(1.3, dim=2), tfm.Rotation(30, unit='deg'), tfm.Offset([-w / 2.0, -h / 2.0])])
     out = tr.resample(src, method='linear')
     assert abs(out[h // 2, w // 2] - val) <= 1e-12 * max(1.0, abs(val)), (val, out[h // 2, w // 2], r.stdout)
+
+
+def test_device_out_is_validated(tfm):
+    """A CUDA tensor passed as out= must be exactly what the kernel is about to write: the kernel takes
+    pitch and element size from the EXPECTED layout, so a float32 buffer in parity mode (float64 output),
+    a sliced view, a wrong shape or another leading axis would be written past its end or with the wrong
+    stride.  Each is rejected with ValueError, for K1 and K2."""
+    import torch
+    src = torch.rand((40, 56), device="cuda", dtype=torch.float32)
+    tr = tfm.Composition([tfm.Rotation(0.2), tfm.Offset([-20.0, -10.0])])
+    for method in ("linear", "Gaussian"):
+        good64 = torch.empty((40, 56), device="cuda", dtype=torch.float64)
+        assert tr.resample(src, method=method, out=good64) is good64
+        good32 = torch.empty((40, 56), device="cuda", dtype=torch.float32)
+        assert tr.resample(src, method=method, precision="fp32", out=good32) is good32
+        with pytest.raises(ValueError):                          # dtype: parity mode writes float64
+            tr.resample(src, method=method, out=torch.empty((40, 56), device="cuda", dtype=torch.float32))
+        with pytest.raises(ValueError):                          # dtype: fast mode writes float32
+            tr.resample(src, method=method, precision="fp32", out=good64)
+        with pytest.raises(ValueError):                          # shape differs from the output grid
+            tr.resample(src, method=method, precision="fp32", out=torch.empty((40, 60), device="cuda"))
+        with pytest.raises(ValueError):                          # non-contiguous view
+            tr.resample(src, method=method, precision="fp32",
+                        out=torch.empty((40, 112), device="cuda", dtype=torch.float32)[:, ::2])
+        with pytest.raises(ValueError):                          # leading axis mismatch
+            tr.resample(src, method=method, precision="fp32", out=torch.empty((2, 40, 56), device="cuda"))
+
+
+def test_host_out_with_device_input_and_submit_many(tfm):
+    """A CUDA frame with a host out= buffer fills the buffer (it used to be left untouched), and
+    AsyncResampler.submit_many uploads a pinned frame once for several resamplings."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.rand((300, 420), generator=g, device="cuda", dtype=torch.float32)
+    tr = tfm.Composition([tfm.Scale(1.2, dim=2), tfm.Rotation(0.3), tfm.Offset([-200.0, -150.0])])
+    rad = tfm.Composition([tfm.Scale([420 / (2 * np.pi), 1.5]), tfm.Radial(origin=[209.5, 149.5])])
+    want_l = tr.resample(src, method="linear", precision="fp32")
+    want_g = rad.resample(src, method="Gaussian", precision="fp32")
+    host = np.zeros((300, 420), dtype=np.float32)
+    ret = tr.resample(src, method="linear", precision="fp32", out=host)
+    assert ret is host and np.array_equal(host, want_l.cpu().numpy())
+    pipe = tfm.AsyncResampler(depth=2)
+    h_src = torch.empty((300, 420), dtype=torch.float32).pin_memory()
+    h_src.copy_(src)
+    outs = [torch.zeros((300, 420), dtype=torch.float32).pin_memory() for _ in range(2)]
+    tk = pipe.submit_many(h_src, [(tr, outs[0], "linear", {"precision": "fp32"}),
+                                  (rad, outs[1], "Gaussian", {"precision": "fp32"})])
+    res = tk.result()
+    assert res[0] is outs[0] and torch.equal(outs[0], want_l.cpu()) and torch.equal(outs[1], want_g.cpu())
+    # a 'forbid' boundary violated inside the pipeline surfaces at result(), not at submit
+    far = tfm.Offset([1000.0, 0.0])
+    tk = pipe.submit(far, h_src, outs[0], method="linear", bound="f", precision="fp32")
+    with pytest.raises(ValueError):
+        tk.result()
+    pipe.drain()
+
+
+def test_antialias_switch_through_resample(tfm, oracle):
+    """resample(method='Gaussian', antialias=False) (or aa=False) falls back to the input-plane filter
+    of the same letter, like interpND_grid(antialias=False) (helpers.pyx:1524-1530); both keywords are
+    consumed whatever their values (the second used to survive and raise TypeError)."""
+    src = np.random.default_rng(8).random((48, 64))
+    tr = tfm.Composition([tfm.Scale(1.1, dim=2), tfm.Rotation(0.25), tfm.Offset([-30.0, -20.0])])
+    want = oracle.resample(to_oracle(tr), src, method='g')
+    for kw in ({"antialias": False}, {"aa": False}, {"antialias": False, "aa": True}, {"antialias": True, "aa": False}):
+        got = tr.resample(src, method='Gaussian', jump_detect=4.0, **kw)
+        assert_close_rel(got, want, 1e-12, str(kw))
+    on = tr.resample(src, method='Gaussian', antialias=True, aa=True)
+    assert not np.allclose(on, want)
+    with pytest.raises(TypeError):
+        tr.resample(src, method='Gaussian', antialias=False, bogus=1)

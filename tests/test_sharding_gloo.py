@@ -86,3 +86,82 @@ def test_row_blocks_and_boxes():
     assert sharding.source_box(np.array([[np.nan, 1.0]]), 10, 10, 1) is None
     assert sharding.source_box(np.array([[-50.0, -50.0]]), 10, 10, 1) is None
     assert sharding.source_box(np.array([[2.2, 3.7], [5.1, 4.0]]), 100, 100, 2, margin=0) == (0, 1, 9, 7)
+
+
+# --------------------------------------------------------------------------------------------------
+# ShardedResampler: cached plan, row / column split, strips gathered while the next one is computed
+# --------------------------------------------------------------------------------------------------
+def _worker_sr(rank, world, port, case, ret):
+    import torch
+    import torch.distributed as dist
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle_np as o
+    import transform_b200 as t
+    from transform_b200 import sharding
+    from conftest import to_oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        kind, method, split, nsub, shape = case
+        ny, nx = 96, 128
+        src = np.random.default_rng(0).random((ny, nx)).astype(np.float32)
+        if kind == "polar":
+            tr = t.Composition([t.Scale([nx / (2 * np.pi), ny / 70.0]), t.Radial(origin=[63.5, 47.5])])
+        else:
+            tr = t.Composition([t.Scale(1.3, dim=2), t.Rotation(25, unit='deg'), t.Offset([-nx / 2.0, -ny / 2.0])])
+        aa = method[0].isupper()
+
+        def invert_points(transform, pts):
+            return to_oracle(transform).reverse(np.asarray(pts, dtype=float))
+
+        def resample_rect(transform, sub, origin, full, rect, shp, m, b, kw, out=None):
+            frame = np.full(full, np.nan)                       # poison what was not staged
+            frame[origin[1]:origin[1] + sub.shape[0], origin[0]:origin[0] + sub.shape[1]] = sub
+            x0, y0, x1, y1 = rect
+            if aa:
+                blk = o.resample_jacobian(to_oracle(transform), frame, method=m[0].lower(), bound=b, shape=shp,
+                                          rows=(y0, y1), max_reg=24)
+            else:
+                blk = o.resample(to_oracle(transform), frame, method=m, bound=b, shape=shp, rows=(y0, y1))
+            return np.ascontiguousarray(blk[:, x0:x1])
+
+        sr = sharding.ShardedResampler(tr, src.shape, shape=shape, method=method, bound='t', nsub=nsub, split=split,
+                                       invert_points=invert_points, resample_rect=resample_rect,
+                                       **({"max_half": 12} if aa else {}))
+        for rep in range(2):                                     # second call: cached plan and buffers
+            out = sr(src if rank == 0 else None)
+        shp = shape or src.shape
+        if aa:
+            want = o.resample_jacobian(to_oracle(tr), src, method=method[0].lower(), bound='t', shape=shp, max_reg=24)
+        else:
+            want = o.resample(to_oracle(tr), src, method=method, bound='t', shape=shp)
+        got = out.numpy()
+        ret["ok%d" % rank] = bool(got.shape == want.shape and np.array_equal(got, want, equal_nan=False))
+        ret["nan%d" % rank] = int(np.isnan(got).sum())
+        if rank == 0:
+            ret["split"] = sr.split
+            ret["staged"] = int(sr.staged_pixels)
+            ret["whole"] = [p["whole"] for p in sr.plans]
+            ret["bytes"] = (int(sr.bytes_scatter), int(sr.bytes_gather))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [("affine", "linear", "rows", 1, None), ("affine", "linear", "cols", 3, None),
+                                  ("affine", "cubic", "auto", 2, (61, 77)), ("polar", "linear", "auto", 2, None),
+                                  ("polar", "Gaussian", "auto", 2, None), ("affine", "Gaussian", "rows", 3, (50, 70))])
+def test_sharded_resampler_world2(case):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_worker_sr, args=(2, port, case, ret), nprocs=2, join=True)
+    r = dict(ret)
+    assert r["ok0"] and r["ok1"], r                               # every rank holds the full, exact result
+    assert r["nan0"] == 0 and r["nan1"] == 0, r                   # no tap fell on a pixel that was not staged
+    assert r["staged"] < 2 * 96 * 128, r                          # less than two whole frames were sent
+    assert r["bytes"][1] > 0
+    if case[0] == "polar":
+        assert r["split"] == "cols", r                            # wedges beat annuli

@@ -26,7 +26,7 @@ peak = 6547.5
 res = {}
 for name, tr in maps.items():
     row = {}
-    for tun in (0, 128, 256, 16):
+    for tun in (0, 8192, 128, 256, 16):
         f = lambda: tr.resample(src, method="linear", precision="fp32", out=dst, tuning=tun)
         f(); f(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

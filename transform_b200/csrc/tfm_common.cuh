@@ -43,6 +43,17 @@ __device__ __forceinline__ unsigned lop3_and_or(unsigned a, unsigned b, unsigned
     return d;
 }
 
+// the same, with the index left as (floor(x) - TFM_FLOOR_RAW_BIAS) mod 2^32: a caller that subtracts an origin
+// anyway folds the bias into it
+#define TFM_FLOOR_RAW_BIAS 0x70000000u
+__device__ __forceinline__ void floor_frac_raw(double x, unsigned &i_raw, float &frac)
+{
+    const double t = x + 805306368.0;
+    const unsigned lo = (unsigned)__double2loint(t), hi = (unsigned)__double2hiint(t);
+    i_raw = __funnelshift_r(lo, hi, 23);
+    frac = __uint_as_float(lop3_and_or(lo, 0x007fffffu, 0x3f800000u)) - 1.0f;
+}
+
 __device__ __forceinline__ void floor_frac_fast(double x, int &i, float &frac)
 {
     const double t = x + 805306368.0;                          // 1.5 * 2^29 = 0x41C8000000000000

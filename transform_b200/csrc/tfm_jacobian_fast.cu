@@ -168,9 +168,10 @@ __device__ __forceinline__ void gauss_taps_cp(const float *__restrict__ p0, int 
 // ncu, 8192^2 polar unwrap (profiles/r2_k2.md): the 8-byte LDG form is bound by the LSU data pipe --
 // 3.5 wavefronts per request (one per cache line the 32 footprints of a warp touch), 2 taps per lane;
 // the texture path returns 4 taps per lane per request through its own filter/write-back stage.
-// one row pair (r, r+1) of the texture form; BOTH = false: row r+1 lies outside the square
+// one row pair (r, r+1) of the texture form, texels already fetched; BOTH = false: row r+1 lies outside
+// the square
 template <int HALF, bool BOTH>
-__device__ __forceinline__ void tex_row_pair(cudaTextureObject_t tex, float fx0, float fy, float2 &WR, float2 &STEP,
+__device__ __forceinline__ void tex_row_pair(const float4 (&g)[HALF + 1], float2 &WR, float2 &STEP,
                                              const float2 CC1, const float2 CA13, const float2 CA4,
                                              float2 &val2, float2 &wgt2, float &val, float &wgt)
 {
@@ -191,46 +192,74 @@ __device__ __forceinline__ void tex_row_pair(cudaTextureObject_t tex, float fx0,
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         // gather order: x = (c, r+1), y = (c+1, r+1), z = (c+1, r), w = (c, r)
-        const float4 g = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
         if (i < HALF) {
-            val2 = __ffma2_rn(make_float2(g.w, g.z), Wa, val2);
+            val2 = __ffma2_rn(make_float2(g[i].w, g[i].z), Wa, val2);
             wgt2 = __fadd2_rn(wgt2, Wa);
             Wa = __fmul2_rn(Wa, Ra);
             Ra = __fmul2_rn(Ra, CA4);
             if (BOTH) {
-                val2 = __ffma2_rn(make_float2(g.x, g.y), Wb, val2);
+                val2 = __ffma2_rn(make_float2(g[i].x, g[i].y), Wb, val2);
                 wgt2 = __fadd2_rn(wgt2, Wb);
                 Wb = __fmul2_rn(Wb, Rb);
                 Rb = __fmul2_rn(Rb, CA4);
             }
         } else {                                             // last pair: column N is outside the square
-            val = fmaf(g.w, Wa.x, val);
+            val = fmaf(g[i].w, Wa.x, val);
             wgt += Wa.x;
             if (BOTH) {
-                val = fmaf(g.x, Wb.x, val);
+                val = fmaf(g[i].x, Wb.x, val);
                 wgt += Wb.x;
             }
         }
     }
 }
 
+// The texture unit answers after several hundred cycles and a warp consumes its texels in order: what
+// hides the latency is the number of fetches in flight.  ncu on the first form (fetch, use, fetch, ...,
+// 2-3 in flight): 56 % of the stall samples on the first FFMA2 after a fetch.  Here the fetches of the
+// WHOLE footprint (HALF <= 2: 4 or 9 TLD4, 16 or 36 registers) or of a whole row pair (HALF + 1 TLD4) are
+// issued before the first weight is formed.
 template <int HALF>
 __device__ __forceinline__ void gauss_taps_tex(cudaTextureObject_t tex, int xs, int ys, float w0, float r0, float rb,
                                                float cA, float cB, float cC, float &val, float &wgt)
 {
-    const float cA2 = cA * cA, cA4s = cA2 * cA2;
-    const float2 CA4 = make_float2(cA4s, cA4s);
-    const float2 CA13 = make_float2(cA, cA * cA2);           // R2 = r0^2 * (cA, cA^3)
-    float2 WR = make_float2(w0, r0);                         // (first weight, first ratio) of the row
-    float2 STEP = make_float2(rb, cB);                       // row-to-row: w0 *= rb, r0 *= cB; rb *= cC
-    const float2 CC1 = make_float2(cC, 1.0f);
-    float2 val2 = make_float2(0.0f, 0.0f), wgt2 = make_float2(0.0f, 0.0f);
+    constexpr int NP = HALF + 1;
     const float fx0 = (float)(xs + 1);
     float fy = (float)(ys + 1);
-#pragma unroll(HALF <= 2 ? HALF : 1)
-    for (int j = 0; j < HALF; ++j, fy += 2.0f)
-        tex_row_pair<HALF, true>(tex, fx0, fy, WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
-    tex_row_pair<HALF, false>(tex, fx0, fy, WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
+    float2 val2 = make_float2(0.0f, 0.0f), wgt2 = make_float2(0.0f, 0.0f);
+    if constexpr (HALF <= 2) {
+        float4 g[NP][NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+                g[j][i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy + (float)(2 * j), 0);
+        const float cA2 = cA * cA, cA4s = cA2 * cA2;
+        const float2 CA4 = make_float2(cA4s, cA4s);
+        const float2 CA13 = make_float2(cA, cA * cA2);       // R2 = r0^2 * (cA, cA^3)
+        float2 WR = make_float2(w0, r0);                     // (first weight, first ratio) of the row
+        float2 STEP = make_float2(rb, cB);                   // row-to-row: w0 *= rb, r0 *= cB; rb *= cC
+        const float2 CC1 = make_float2(cC, 1.0f);
+#pragma unroll
+        for (int j = 0; j < HALF; ++j)
+            tex_row_pair<HALF, true>(g[j], WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
+        tex_row_pair<HALF, false>(g[HALF], WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
+    } else {
+        const float cA2 = cA * cA, cA4s = cA2 * cA2;
+        const float2 CA4 = make_float2(cA4s, cA4s);
+        const float2 CA13 = make_float2(cA, cA * cA2);
+        float2 WR = make_float2(w0, r0);
+        float2 STEP = make_float2(rb, cB);
+        const float2 CC1 = make_float2(cC, 1.0f);
+#pragma unroll 1
+        for (int j = 0; j < NP; ++j, fy += 2.0f) {
+            float4 g[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
+            if (j < HALF) tex_row_pair<HALF, true>(g, WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
+            else tex_row_pair<HALF, false>(g, WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
+        }
+    }
     val += val2.x + val2.y;
     wgt += wgt2.x + wgt2.y;
 }

@@ -13,6 +13,15 @@
 // NPX times 8 rows apart with all loads of the NPX pixels in flight together.
 #include "tfm_resample.cuh"
 
+// Which of the two fast affine kernels runs is a performance choice only (bit-identical results): the
+// persistent TMA pipeline where most of the output maps inside the source (measured 8192^2, ms: shift
+// 0.114 vs 0.137, rot 5 0.114 vs 0.141, rot 45 0.114 vs 0.132, scale 2 0.112 vs 0.127, scale 0.8 [64 %
+// coverage] 0.097 vs 0.114), the texture gather where most output tiles are empty (named chain, 42 %
+// coverage: 0.082 vs 0.104 -- its CTAs retire on a 10-instruction test, the pipeline's consumers still
+// walk every tile).
+// Tuning bit 8192 forces the pipeline, 128 / 16 / 256 force the other variants.
+#define TFM_PIPE_COVERAGE 0.55
+
 namespace tfm {
 
 // the kernel families are compiled in their own translation units
@@ -481,6 +490,204 @@ static bool get_tensor_map(const void *ptr, int w, int h, long long pitch, int b
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// persistent, multi-stage TMA pipeline (fp32 fast path, linear, affine map, truncate / fill 0)
+// ---------------------------------------------------------------------------------------------
+// The texture-gather kernels stop at the texture unit's write-back (88 % busy at 0.135 ms for a pure
+// shift, profiles/r2_k1.md): every source pixel crosses it four times.  Here HBM -> shared memory is one
+// bulk tensor copy per tile -- the source bounding box of a 32 x 32 output tile under an affine map has
+// a size the host knows -- and the four taps are LDS.  What made the one-box-per-CTA form of round 1
+// slow (exposed TMA latency, per-CTA set-up, mbarrier polling) is removed by making the CTAs persistent:
+//   * grid = resident CTAs only; CTA b walks tiles b, b + G, b + 2G, ...
+//   * STAGES boxes in flight per CTA: while tile i is being interpolated, the boxes of tiles i+1 ..
+//     i+STAGES-1 are already on their way (one elected thread issues cp.async.bulk.tensor.2d and arms
+//     the stage's mbarrier with the byte count; everybody waits on the barrier's phase parity);
+//   * one __syncthreads per tile (1024 pixels) releases the stage for the next box;
+//   * boxes that miss the image entirely are never fetched: the producer arrives on the barrier without
+//     a transaction and flags the stage, the consumers store zeros.
+// Out-of-range parts of a box are zero-filled by the TMA unit = the reference's truncate boundary with
+// fill 0.  Coordinates, floor/fraction and interpolation order are those of every other fast-mode
+// kernel (bit-identical results, tests/test_gpu_headline.py).
+struct PipeParams {
+    int bw, bh;                              // box columns / rows (bw * 4 bytes is a multiple of 16)
+    int stage_bytes;                         // box bytes rounded up to 128
+    int tiles_x, tiles_y;
+    int step_x, step_y;                      // gridDim.x % tiles_x, gridDim.x / tiles_x: the tile walk without divisions
+};
+
+constexpr int PIPE_STAGES = 4;
+constexpr int PIPE_TW = 64, PIPE_TH = 32;   // output tile: 8 consumer warps x 4 rows, 8 pixels per thread
+constexpr int PIPE_THREADS = 288;           // 8 consumer warps + 1 producer warp
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+// out-of-line: the 8 pixels of one consumer thread straight from global memory (never taken unless the
+// box arithmetic of host and device disagree)
+static __device__ __noinline__ void pipe_redo_row(const ResampleParams &P, double Xd, double rx, double ry, float *drow, int X)
+{
+    for (int k = 0; k < 8; ++k) {
+        if (X + 8 * k >= P.dst_w) break;
+        const double Xj = Xd + (double)(8 * k);
+        int ix, iy;
+        float fx, fy;
+        floor_frac_fast(fma(P.aff[0], Xj, rx), ix, fx);
+        floor_frac_fast(fma(P.aff[2], Xj, ry), iy, fy);
+        const float v00 = tap_trunc<float, float>(P, P.src, ix, iy), v01 = tap_trunc<float, float>(P, P.src, ix + 1, iy);
+        const float v10 = tap_trunc<float, float>(P, P.src, ix, iy + 1), v11 = tap_trunc<float, float>(P, P.src, ix + 1, iy + 1);
+        const float top = fmaf(fx, v01 - v00, v00);
+        const float bot = fmaf(fx, v11 - v10, v10);
+        drow[8 * k] = fmaf(fy, bot - top, top);
+    }
+}
+
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
+
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(PIPE_THREADS)
+k_resample_pipe(const __grid_constant__ ResampleParams P, const __grid_constant__ CUtensorMap tmap,
+                const __grid_constant__ PipeParams B)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [STAGES boxes][STAGES x int4 box info][STAGES full barriers][STAGES empty barriers]
+    int4 *const s_info = reinterpret_cast<int4 *>(smem_raw + (size_t)PIPE_STAGES * B.stage_bytes);   // (bx0, by0, empty, -)
+    unsigned long long *const s_full = reinterpret_cast<unsigned long long *>(s_info + PIPE_STAGES);
+    unsigned long long *const s_empty = s_full + PIPE_STAGES;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = gridDim.x;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < PIPE_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_addr(&s_empty[s])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();                                   // barrier initialisation visible to all
+
+    // tile walk of this CTA: t = blockIdx.x, + G, + 2G, ... as (tx, ty) without divisions in the loop
+    int tx = blockIdx.x % B.tiles_x, ty = blockIdx.x / B.tiles_x;
+
+    if (warp == 8) {
+        // ------------------------------ producer warp (one lane) ------------------------------
+        if (lane != 0) return;
+        for (int it = 0; ty < B.tiles_y; ++it) {
+            const int s = it % PIPE_STAGES;
+            // the producer runs ahead and then waits most of the time: back off between polls instead of
+            // spinning (ncu: its try_wait loop was 12 % of all issued instructions)
+            if (it >= PIPE_STAGES) mbar_wait_sleep(smem_addr(&s_empty[s]), (uint32_t)(((it / PIPE_STAGES) - 1) & 1));
+            // source box of the tile: the map is affine, so the extremes are at the tile corners; one pixel
+            // of margin on the low side, the host-chosen box size covers the high side
+            const double TX = (double)(P.dst_x0 + (long long)tx * PIPE_TW), TY = (double)(P.dst_y0 + (long long)ty * PIPE_TH);
+            const double cx0 = fma(P.aff[0], TX, fma(P.aff[1], TY, P.aff[4]));
+            const double cy0 = fma(P.aff[2], TX, fma(P.aff[3], TY, P.aff[5]));
+            const double xlo = cx0 + fmin((PIPE_TW - 1.0) * P.aff[0], 0.0) + fmin((PIPE_TH - 1.0) * P.aff[1], 0.0);
+            const double ylo = cy0 + fmin((PIPE_TW - 1.0) * P.aff[2], 0.0) + fmin((PIPE_TH - 1.0) * P.aff[3], 0.0);
+            // the box must start on a 16-byte boundary of the innermost axis: round down to a multiple of 4
+            const int bx0 = ((int)floor(xlo) - 1) & ~3, by0 = (int)floor(ylo) - 1;     // |coordinate| < 2.5e8: host-proven
+            const bool empty = bx0 >= P.src_w || by0 >= P.src_h || bx0 + B.bw <= 0 || by0 + B.bh <= 0;
+            s_info[s] = make_int4(bx0, by0, empty ? 1 : 0, 0);
+            const uint32_t bar = smem_addr(&s_full[s]);
+            if (empty) {
+                // nothing to fetch: the consumers store zeros
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            } else {
+                const uint32_t bytes = (uint32_t)(B.bw * B.bh * 4);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                    ::"r"(smem_addr(smem_raw + (size_t)s * B.stage_bytes)), "l"(reinterpret_cast<uint64_t>(&tmap)),
+                      "r"(bx0), "r"(by0), "r"(bar)
+                    : "memory");
+            }
+            tx += B.step_x; ty += B.step_y;
+            if (tx >= B.tiles_x) { tx -= B.tiles_x; ++ty; }
+        }
+        return;
+    }
+
+    // ---------------------------------- consumer warps ----------------------------------
+    const int px = lane & 7;
+    const int py = (warp << 2) + (lane >> 3);
+    const int bw = B.bw;
+    for (int it = 0; ty < B.tiles_y; ++it) {
+        const int s = it % PIPE_STAGES;
+        const int X = tx * PIPE_TW + px, Y = ty * PIPE_TH + py;
+        // row part of the coordinates while the box may still be in flight (canonical form of every
+        // fast-mode kernel: c = fma(a0, X, fma(a1, Y, b)) on exact doubles)
+        const double Xd = (double)(P.dst_x0 + X), Yd = (double)(P.dst_y0 + Y);
+        const double rx = fma(P.aff[1], Yd, P.aff[4]), ry = fma(P.aff[3], Yd, P.aff[5]);
+        mbar_wait(smem_addr(&s_full[s]), (uint32_t)((it / PIPE_STAGES) & 1));
+        const int4 info = s_info[s];
+        const float *const tile = reinterpret_cast<const float *>(smem_raw + (size_t)s * B.stage_bytes);
+        float *const drow = reinterpret_cast<float *>(static_cast<char *>(P.dst) + (long long)Y * P.dst_pitch) + X;
+        const bool row_in = Y < P.dst_h;
+        const bool full = row_in && (tx * PIPE_TW + PIPE_TW <= P.dst_w);
+        // local tap index = floor(c) - box origin; the bias of the raw floor is folded into the origin
+        const unsigned ox = (unsigned)info.x - TFM_FLOOR_RAW_BIAS, oy = (unsigned)info.y - TFM_FLOOR_RAW_BIAS;
+        bool bad = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float r[4];
+            if (info.z) {
+                r[0] = r[1] = r[2] = r[3] = 0.0f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double Xj = Xd + (double)(8 * (4 * h + j));
+                    unsigned ixr, iyr;
+                    float fx, fy;
+                    floor_frac_raw(fma(P.aff[0], Xj, rx), ixr, fx);
+                    floor_frac_raw(fma(P.aff[2], Xj, ry), iyr, fy);
+                    const unsigned lx = ixr - ox, ly = iyr - oy;
+                    // the host sized the box so that every tap of the tile lies inside it; should rounding ever
+                    // disagree, the tap index is neutralised here and the thread redoes its pixels from global
+                    // memory below
+                    const bool out = lx >= (unsigned)(bw - 1) || ly >= (unsigned)(B.bh - 1);
+                    bad = bad || out;
+                    const float *tp = tile + (out ? 0 : (int)(ly * (unsigned)bw + lx));
+                    const float v00 = tp[0], v01 = tp[1], v10 = tp[bw], v11 = tp[bw + 1];
+                    const float top = fmaf(fx, v01 - v00, v00);
+                    const float bot = fmaf(fx, v11 - v10, v10);
+                    r[j] = fmaf(fy, bot - top, top);
+                }
+            }
+            float *const d = drow + 32 * h;
+            if (full) { d[0] = r[0]; d[8] = r[1]; d[16] = r[2]; d[24] = r[3]; }
+            else if (row_in) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (X + 32 * h + 8 * j < P.dst_w) d[8 * j] = r[j];
+            }
+        }
+        if (bad && row_in) pipe_redo_row(P, Xd, rx, ry, drow, X);
+        // this warp is done with stage s: one arrival per consumer warp releases it to the producer
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_empty[s])) : "memory");
+        tx += B.step_x; ty += B.step_y;
+        if (tx >= B.tiles_x) { tx -= B.tiles_x; ++ty; }
+    }
+}
+
 // Pre-compose a chain made only of LINEAR / IDENTITY ops into one affine map (fast mode only; the
 // fp64-exact mode never pre-fuses, SURVEY.md section 7 "hard parts").  Parameter preparation on the
 // host, a handful of flops per call -- not part of the data path.
@@ -490,6 +697,19 @@ static bool compose_affine(const tfm_op *ops, int n, double *aff)
         if (!is_linear_like(ops[i])) return false;
     compose_linear_run(ops, 0, n, aff, aff + 4);
     return true;
+}
+
+// Fraction of a 16 x 16 lattice of output grid points that an affine map sends inside the source.
+static double affine_coverage(const double *aff, const tfm_image &d, const tfm_image &s)
+{
+    int inside = 0;
+    for (int j = 0; j < 16; ++j)
+        for (int i = 0; i < 16; ++i) {
+            const double X = (double)d.x0 + (i + 0.5) * (double)d.w / 16.0, Y = (double)d.y0 + (j + 0.5) * (double)d.h / 16.0;
+            const double x = aff[0] * X + aff[1] * Y + aff[4], y = aff[2] * X + aff[3] * Y + aff[5];
+            inside += (x >= -1.0 && x <= (double)s.w && y >= -1.0 && y <= (double)s.h) ? 1 : 0;
+        }
+    return inside / 256.0;
 }
 
 int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
@@ -645,6 +865,54 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
                         name = "k_resample_tma<affine>";
                         e = cudaGetLastError();
                         tma_done = true;
+                    }
+                }
+            }
+        }
+        // persistent multi-stage TMA pipeline: same conditions
+        if (!tma_done && tex_ok && aff && P.aff_bounded && (s.pitch % 16) == 0 && !(a->tuning & (128 | 16 | 256)) &&
+            ((a->tuning & 8192) || affine_coverage(P.aff, d, s) >= TFM_PIPE_COVERAGE)) {
+            const double ex = (PIPE_TW - 1) * fabs(P.aff[0]) + (PIPE_TH - 1) * fabs(P.aff[1]);
+            const double ey = (PIPE_TW - 1) * fabs(P.aff[2]) + (PIPE_TH - 1) * fabs(P.aff[3]);
+            if (ex < 240.0 && ey < 240.0) {
+                PipeParams B;
+                // +1 low margin, +2 for floor/+1 tap, +2 slack (the 2^-23 quantisation of floor_frac_fast can round
+                // a coordinate up to the next integer), +3 for the aligned start; multiple of 4
+                B.bw = (((int)ceil(ex) + 8) + 3) & ~3;
+                B.bh = (int)ceil(ey) + 5;
+                B.stage_bytes = (B.bw * B.bh * 4 + 127) & ~127;
+                B.tiles_x = (P.dst_w + PIPE_TW - 1) / PIPE_TW;
+                B.tiles_y = (P.dst_h + PIPE_TH - 1) / PIPE_TH;
+                const size_t smem = (size_t)PIPE_STAGES * B.stage_bytes + PIPE_STAGES * (16 + 8 + 8) + 16;
+                CUtensorMap tm;
+                if (B.bw <= 256 && B.bh <= 256 && smem <= 200 * 1024 &&
+                    (long long)B.tiles_x * B.tiles_y < 0x3fffffffLL &&
+                    get_tensor_map(s.data, (int)s.w, (int)s.h, s.pitch, B.bw, B.bh, &tm)) {
+                    static int sm_count = 0;
+                    if (!sm_count) {
+                        int dev = 0;
+                        cudaGetDevice(&dev);
+                        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+                    }
+                    cudaError_t ea = cudaSuccess;
+                    if (smem > 48 * 1024)
+                        ea = cudaFuncSetAttribute(k_resample_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    int per_sm = 0;
+                    if (ea == cudaSuccess)
+                        ea = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_pipe<0>, PIPE_THREADS, smem);
+                    if (ea == cudaSuccess && per_sm > 0) {
+                        long long g = (long long)sm_count * per_sm;
+                        const long long nt = (long long)B.tiles_x * B.tiles_y;
+                        if (g > nt) g = nt;
+                        B.step_x = (int)(g % B.tiles_x);
+                        B.step_y = (int)(g / B.tiles_x);
+                        k_resample_pipe<0><<<(unsigned)g, PIPE_THREADS, smem, st>>>(P, tm, B);
+                        count_launch();
+                        name = "k_resample_pipe<affine>";
+                        e = cudaGetLastError();
+                        tma_done = true;
+                    } else {
+                        cudaGetLastError();
                     }
                 }
             }

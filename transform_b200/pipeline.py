@@ -78,6 +78,38 @@ class AsyncResampler:
         self._events[slot] = ev
         return Ticket(ev, out, status_host)
 
+    def submit_many(self, data, calls):
+        """One upload, several resamplings of the same frame: `calls` is a list of
+        (transform, out, method, kwargs).  The frame crosses PCIe once; each result goes back into its
+        own pinned buffer.  Returns one Ticket (its `.result()` is the list of outputs)."""
+        torch = self._torch
+        if not (dev.is_tensor(data) and not data.is_cuda and data.is_pinned()):
+            raise ValueError("AsyncResampler.submit_many: `data` must be a pinned CPU tensor")
+        for c in calls:
+            if not (dev.is_tensor(c[1]) and not c[1].is_cuda and c[1].is_pinned()):
+                raise ValueError("AsyncResampler.submit_many: every `out` must be a pinned CPU tensor")
+        slot = self._next
+        self._next = (slot + 1) % len(self._streams)
+        stream = self._streams[slot]
+        prev = self._events[slot]
+        if prev is not None:
+            prev.synchronize()
+        stream.wait_stream(torch.cuda.current_stream(self._device))
+        status_host = self._status[slot]
+        status_host.zero_()
+        with torch.cuda.stream(stream):
+            frame = data.to(self._device, non_blocking=True)          # the one H2D copy of this step
+            for (transform, out, method, kw) in calls:
+                kw = dict(kw or {})
+                bound = kw.pop("bound", "t")
+                transform.resample(frame, method=method, bound=bound, out=out, sync=False,
+                                   status_host=status_host, **kw)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            frame.record_stream(stream)
+        self._events[slot] = ev
+        return Ticket(ev, [c[1] for c in calls], status_host)
+
     def drain(self):
         for ev in self._events:
             if ev is not None:
