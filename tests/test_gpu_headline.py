@@ -289,3 +289,46 @@ def test_apply_config5_slices(tfm, oracle):
                 err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
                 assert float(err.max()) <= 1e-11, float(err.max())
         del out
+
+
+def test_staged_rectangles_reproduce_the_full_frame_8192(tfm):
+    """Multi-GPU shards at full size on one GPU: each output rectangle of a 2- and 3-way split (rows and
+    columns) is resampled against the staged source rectangle the planner assigns it, exactly as a rank
+    would, and must equal the same pixels of the unsharded call BIT FOR BIT (K1; K2 to 2e-6) -- for the kernels a shard
+    runs (texture gather / TMA pipeline on a proven-sufficient rectangle, generic kernel otherwise).
+    The named chain lands thousands of pixels on exact integer source columns, where the generic kernel
+    once took the tap index from floor() and the fraction from the fixed-point floor."""
+    import torch
+    from transform_b200 import _engine, _lib, sharding
+    n = 8192
+    src = frame(n, 1000)
+    c = (n - 1) / 2.0
+    cases = [(named_chain(tfm, n), "linear", {}), (tfm.Offset([3.25, -7.5]), "linear", {}),
+             (named_chain(tfm, n), "cubic", {}), (polar_chain(tfm, n), "Gaussian", {}),
+             (tfm.Composition([tfm.Offset([c, c]), tfm.Scale([0.6, 0.7]), tfm.Rotation(25, unit='deg'),
+                               tfm.Offset([-n / 2.0, -n / 2.0])]), "Gaussian", {})]
+    for tr, method, kw in cases:
+        want = tr.resample(src, method=method, precision="fp32", **kw)
+        for world, split in ((2, "rows"), (3, "cols")):
+            _, plans, _ = sharding.plan_rects(tr, (n, n), (n, n), method, "t", world, sharding._default_invert,
+                                              split=split)
+            for p in plans:
+                x0, y0, x1, y1 = p["rect"]
+                if p["whole"]:
+                    sub, origin = src, (0, 0)
+                elif p["box"] is None:
+                    assert float(want[y0:y1, x0:x1].abs().max()) == 0.0
+                    continue
+                else:
+                    bx0, by0, bx1, by1 = p["box"]
+                    sub, origin = src[by0:by1, bx0:bx1].contiguous(), (bx0, by0)
+                blk = sharding._default_resample_rect(tr, sub, origin, (n, n), p["rect"], (n, n), method, "t",
+                                                      dict(precision="fp32", **kw))
+                k = _lib.last_kernel()
+                dmax = float((blk - want[y0:y1, x0:x1]).abs().max())
+                if method == "Gaussian":
+                    # footprints that cross the image edge are summed by the texture border path in the full
+                    # frame and by the out-of-line edge path in a shard: same taps and weights, another order
+                    assert dmax <= 2e-6, (method, world, split, p["rect"], k, dmax)
+                else:
+                    assert dmax == 0.0, (method, world, split, p["rect"], k, dmax)

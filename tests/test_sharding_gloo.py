@@ -85,7 +85,7 @@ def test_row_blocks_and_boxes():
     assert pts[:, 1].min() == 3 and pts[:, 1].max() == 5 and pts[:, 0].max() == 39
     assert sharding.source_box(np.array([[np.nan, 1.0]]), 10, 10, 1) is None
     assert sharding.source_box(np.array([[-50.0, -50.0]]), 10, 10, 1) is None
-    assert sharding.source_box(np.array([[2.2, 3.7], [5.1, 4.0]]), 100, 100, 2, margin=0) == (0, 1, 9, 7)
+    assert sharding.source_box(np.array([[2.2, 3.7], [5.1, 4.0]]), 100, 100, 2, margin=0) == (0, 1, 16, 7)       # columns rounded out to multiples of 8
 
 
 # --------------------------------------------------------------------------------------------------

@@ -39,8 +39,8 @@ struct JacFastParams {
     int max_half;                            // cap on the footprint half-width (max_reg / 2)
     int *status;
     cudaTextureObject_t tex;                 // point-sampled, border = 0 (tap mode 2)
-    int tex_edges;                           // both bounds truncate and the whole image is staged: the texture's
-                                             // border IS the reference's truncated tap -- no edge classification
+    int tex_edges;                           // both bounds truncate: the texture's border IS the reference's truncated
+                                             // tap wherever the staged rectangle ends where the image ends
     float qscale;                            // log2(e) / oblur^2: exp(-q/oblur^2) = exp2(-q * qscale)
     float ob;                                // oblur
     float padval, half_pow, m2_over_pow;     // padding (helpers.pyx:1661-1662): pad_pow / 2, -2 / pad_pow
@@ -404,7 +404,16 @@ __device__ __forceinline__ TapRec gauss_setup(const JacFastParams &P, const floa
         oy = yi - half - P.src_y0;
         const float hf1 = (float)(half + 1);
         const bool inside = limx > 0 && limy > 0 && (unsigned)ox < (unsigned)limx && (unsigned)oy < (unsigned)limy;
-        fast = (inside || (TM == 2 && P.tex_edges)) &&
+        // texture taps, both boundaries truncate: beyond the staged rectangle the texture reads 0, which is
+        // right exactly where "beyond the rectangle" means "beyond the image" -- i.e. when the part of the
+        // footprint that lies inside the image lies inside the rectangle (always, for a whole image)
+        bool edges_ok = false;
+        if (TM == 2 && P.tex_edges) {
+            const int wx0 = max(xi - half, 0), wx1 = min(xi + half, P.full_w - 1);
+            const int wy0 = max(yi - half, 0), wy1 = min(yi + half, P.full_h - 1);
+            edges_ok = wx0 >= P.src_x0 && wx1 < P.src_x0 + P.src_w && wy0 >= P.src_y0 && wy1 < P.src_y0 + P.src_h;
+        }
+        fast = (inside || edges_ok) &&
                half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * (hf1 * hf1) < 100.0f;
     } else if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) {
         return rec;                                              // NaN / inf (as tfm_jacobian.cu)
@@ -738,8 +747,7 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
     if (!(a->tuning & (4096 | 32768)) && s.n_planes == 1 && s.w <= 131072 && s.h <= 65000 && (s.pitch % 32) == 0 &&
         (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 && get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &P.tex))
         tm = 2;
-    const bool whole = (s.x0 == 0 && s.y0 == 0 && s.full_h == s.h && s.full_w == s.w);
-    P.tex_edges = (tm == 2 && whole && a->bound_x == TFM_B_TRUNCATE && a->bound_y == TFM_B_TRUNCATE) ? 1 : 0;
+    P.tex_edges = (tm == 2 && a->bound_x == TFM_B_TRUNCATE && a->bound_y == TFM_B_TRUNCATE) ? 1 : 0;
 
     bool lin = true;
     for (int i = 0; i < a->n_ops; ++i) lin = lin && is_linear_like(a->chain[i]);

@@ -231,7 +231,8 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
                 fx[j] = (float)(cx[j] - cx[j]); fy[j] = (float)(cy[j] - cy[j]);
             }
         }
-        g[j] = tex2Dgather<float4>(tex, (float)(ix + 1), (float)(iy + 1), 0);
+        // texel index inside the staged rectangle (src_x0 = src_y0 = 0 for a whole image)
+        g[j] = tex2Dgather<float4>(tex, (float)(ix + 1 - P.src_x0), (float)(iy + 1 - P.src_y0), 0);
     }
     float r[4];
 #pragma unroll
@@ -604,7 +605,9 @@ k_resample_pipe(const __grid_constant__ ResampleParams P, const __grid_constant_
             const double ylo = cy0 + fmin((PIPE_TW - 1.0) * P.aff[2], 0.0) + fmin((PIPE_TH - 1.0) * P.aff[3], 0.0);
             // the box must start on a 16-byte boundary of the innermost axis: round down to a multiple of 4
             const int bx0 = ((int)floor(xlo) - 1) & ~3, by0 = (int)floor(ylo) - 1;     // |coordinate| < 2.5e8: host-proven
-            const bool empty = bx0 >= P.src_w || by0 >= P.src_h || bx0 + B.bw <= 0 || by0 + B.bh <= 0;
+            // box position inside the staged rectangle (the whole image: src_x0 = src_y0 = 0)
+            const int tx0 = bx0 - P.src_x0, ty0 = by0 - P.src_y0;
+            const bool empty = tx0 >= P.src_w || ty0 >= P.src_h || tx0 + B.bw <= 0 || ty0 + B.bh <= 0;
             s_info[s] = make_int4(bx0, by0, empty ? 1 : 0, 0);
             const uint32_t bar = smem_addr(&s_full[s]);
             if (empty) {
@@ -616,7 +619,7 @@ k_resample_pipe(const __grid_constant__ ResampleParams P, const __grid_constant_
                 asm volatile(
                     "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                     ::"r"(smem_addr(smem_raw + (size_t)s * B.stage_bytes)), "l"(reinterpret_cast<uint64_t>(&tmap)),
-                      "r"(bx0), "r"(by0), "r"(bar)
+                      "r"(tx0), "r"(ty0), "r"(bar)
                     : "memory");
             }
             tx += B.step_x; ty += B.step_y;
@@ -706,7 +709,7 @@ static double affine_coverage(const double *aff, const tfm_image &d, const tfm_i
     for (int j = 0; j < 16; ++j)
         for (int i = 0; i < 16; ++i) {
             const double X = (double)d.x0 + (i + 0.5) * (double)d.w / 16.0, Y = (double)d.y0 + (j + 0.5) * (double)d.h / 16.0;
-            const double x = aff[0] * X + aff[1] * Y + aff[4], y = aff[2] * X + aff[3] * Y + aff[5];
+            const double x = aff[0] * X + aff[1] * Y + aff[4] - (double)s.x0, y = aff[2] * X + aff[3] * Y + aff[5] - (double)s.y0;
             inside += (x >= -1.0 && x <= (double)s.w && y >= -1.0 && y <= (double)s.h) ? 1 : 0;
         }
     return inside / 256.0;
@@ -761,8 +764,9 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
 
     const bool subrect = (s.x0 != 0 || s.y0 != 0 || s.full_h != s.h || s.full_w != s.w);
     const long long src_elems = s.h * (s.pitch / (s.dtype == TFM_F64 ? 8 : 4));
-    const bool generic = subrect || a->bound_x != TFM_B_TRUNCATE || a->bound_y != TFM_B_TRUNCATE ||
-                         src_elems >= 0x7fffffffLL;      // the fast path indexes taps with 32-bit offsets
+    bool generic = subrect || a->bound_x != TFM_B_TRUNCATE || a->bound_y != TFM_B_TRUNCATE ||
+                   src_elems >= 0x7fffffffLL;            // the fast path indexes taps with 32-bit offsets
+    bool staged_fast = false;
     if ((a->bound_x == TFM_B_FORBID || a->bound_y == TFM_B_FORBID || subrect) && !a->status_dev)
         return TFM_EVALUE;
 
@@ -788,6 +792,32 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         P.aff_c[3] = (float)(15.5 * (fabs(P.aff[2]) + fabs(P.aff[3])) + 3.0) + P.aff_margin;
         P.aff_lim[0] = (float)s.w + P.aff_c[2];
         P.aff_lim[1] = (float)s.h + P.aff_c[3];
+    }
+    // A staged source rectangle (multi-GPU shard) under an affine map with truncate boundaries: when the host
+    // can PROVE that every in-image tap of this output rectangle lies inside the staged rectangle (an affine
+    // map takes its extremes at the corners), the texture-gather / TMA-pipeline kernels run on the staged
+    // rectangle as if it were the image -- same coordinates, tap indices shifted by the staged origin -- and
+    // what they read as 0 beyond it is beyond the image.  Anything unproven stays with the generic kernel,
+    // which checks every tap and raises the status word.
+    if (subrect && aff && P.aff_bounded && a->method == TFM_LINEAR && a->bound_x == TFM_B_TRUNCATE &&
+        a->bound_y == TFM_B_TRUNCATE && a->fillvalue == 0.0 && src_elems < 0x7fffffffLL && (s.x0 % 4) == 0) {
+        double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+        for (int k = 0; k < 4; ++k) {
+            const double X = (double)d.x0 + ((k & 1) ? (double)(d.w - 1) : 0.0), Y = (double)d.y0 + ((k & 2) ? (double)(d.h - 1) : 0.0);
+            const double x = P.aff[0] * X + P.aff[1] * Y + P.aff[4], y = P.aff[2] * X + P.aff[3] * Y + P.aff[5];
+            xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+        }
+        // taps floor(c) .. floor(c) + 1, one more on each side for the 2^-23 quantisation of the floor
+        const double cx0 = fmax(floor(xmin) - 1.0, 0.0), cx1 = fmin(floor(xmax) + 2.0, (double)s.full_w - 1.0);
+        const double cy0 = fmax(floor(ymin) - 1.0, 0.0), cy1 = fmin(floor(ymax) + 2.0, (double)s.full_h - 1.0);
+        const bool none = cx1 < cx0 || cy1 < cy0;                    // the rectangle maps wholly outside the image
+        staged_fast = none || (cx0 >= (double)s.x0 && cx1 <= (double)(s.x0 + s.w - 1) &&
+                               cy0 >= (double)s.y0 && cy1 <= (double)(s.y0 + s.h - 1));
+        if (staged_fast) {
+            generic = false;
+            // the empty-tile tests work in staged-local coordinates
+            P.aff_c[0] -= (float)s.x0; P.aff_c[1] -= (float)s.y0;
+        }
     }
     if (is_filter) {
         static const int base_size[] = {16, 6, 8, 2, 2, 2};                           // helpers.pyx:708
@@ -843,7 +873,7 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         // Opt-in (tuning bit 256): measured SLOWER than the texture gather on B200 (8192^2: named chain
         // 0.138 vs 0.090 ms, pure shift 0.227 vs 0.141 ms) -- per-CTA load latency is exposed in this
         // one-box-per-CTA form and the shared-memory taps cost more issue slots than one TLD4.
-        if (tex_ok && aff && P.aff_bounded && (a->tuning & 256) && (s.pitch % 16) == 0) {
+        if (tex_ok && aff && P.aff_bounded && (a->tuning & 256) && (s.pitch % 16) == 0 && !staged_fast) {
             const double ex = 31.0 * (fabs(P.aff[0]) + fabs(P.aff[1])), ey = 31.0 * (fabs(P.aff[2]) + fabs(P.aff[3]));
             if (ex < 200.0 && ey < 200.0) {
                 TmaBox B;
@@ -922,7 +952,7 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
             dim3 grid((unsigned)((P.dst_w + 31) / 32), (unsigned)((P.dst_h + 31) / 32), 1);
             if (grid.y > 65535u) return TFM_EUNSUPPORTED;
             const int sph = chain_sph_level(P.chain);
-            if (a->tuning & 128) {           // first form (4 pixels 8 rows apart, scalar stores): A/B runs only
+            if ((a->tuning & 128) && !staged_fast) { // first form (4 pixels 8 rows apart, scalar stores): A/B runs only
                 if (aff) k_resample_tex<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
                 else if (sph == 2) k_resample_tex<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
                 else if (sph == 1) k_resample_tex<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
@@ -938,9 +968,10 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
             }
             count_launch();
             e = cudaGetLastError();
-        } else if (s.dtype == TFM_F32 && d.dtype == TFM_F32)
-            e = launch1<float, float, Fast, float>(a->method, P, generic, aff, st, &name);
-        else
+        } else if (s.dtype == TFM_F32 && d.dtype == TFM_F32) {
+            if (staged_fast) { P.aff_c[0] += (float)s.x0; P.aff_c[1] += (float)s.y0; }
+            e = launch1<float, float, Fast, float>(a->method, P, generic || staged_fast, aff, st, &name);
+        } else
             return TFM_EUNSUPPORTED;
     } else {
         return TFM_EVALUE;

@@ -552,17 +552,21 @@ k_resample(const __grid_constant__ ResampleParams P)
             fracy[j] = __dsub_rn(y, fy);
             ffx[j] = (float)fracx[j];
             ffy[j] = (float)fracy[j];
-            if (FASTI && fabs(x) < TFM_SANE_COORD && fabs(y) < TFM_SANE_COORD) {
-                // every fast-mode variant (LDG gather, texture gather, this generic one) must round the
-                // fp32 fraction identically, so that a sharded run reproduces the unsharded one bit for bit
-                int iu;
-                floor_frac_fast(x, iu, ffx[j]);
-                floor_frac_fast(y, iu, ffy[j]);
-            }
             // |f| >= 2^51 (or NaN): the reference's float tap offsets are absorbed / invalid; every
             // tap shares the base index ("absurd coordinates").
             const bool okx = fabs(fx) < 2.0e15, oky = fabs(fy) < 2.0e15;
-            const long long bx = cast_i64(fx), by = cast_i64(fy);
+            long long bx = cast_i64(fx), by = cast_i64(fy);
+            if (FASTI && fabs(x) < TFM_SANE_COORD && fabs(y) < TFM_SANE_COORD) {
+                // every fast-mode variant (LDG gather, texture gather, TMA pipeline, this generic one) takes
+                // tap index AND fraction from the one fixed-point floor, so that a sharded run reproduces the
+                // unsharded one bit for bit.  (Index from floor() with the fraction from floor_frac_fast was
+                // a bug: a coordinate a hair below an integer k floors to k-1 but quantises to (k, 0.0).)
+                int iu, iv;
+                floor_frac_fast(x, iu, ffx[j]);
+                floor_frac_fast(y, iv, ffy[j]);
+                bx = iu;
+                by = iv;
+            }
 #pragma unroll
             for (int ty = 0; ty < NT; ++ty)
 #pragma unroll

@@ -15,6 +15,8 @@ whole frames per rank and no communication at all.
 The two device-side steps are injectable (`invert_points`, `resample_block`) so that the plan and
 the scatter/gather plumbing are testable with gloo on CPU-only machines.
 """
+import time
+
 import numpy as np
 
 HALO = {"n": 1, "l": 2, "c": 3}          # taps reach floor-1 .. floor+2 (cubic); +1 of slack
@@ -71,6 +73,10 @@ def source_box(coords, src_h, src_w, halo, margin=2):
     x1 = int(np.ceil(c[:, 0].max())) + halo + margin + 1
     y0 = int(np.floor(c[:, 1].min())) - halo - margin
     y1 = int(np.ceil(c[:, 1].max())) + halo + margin + 1
+    # columns on multiples of 8 pixels: the staged rectangle then has a 32-byte row pitch and 32-byte
+    # aligned rows, which the texture / 8-byte-load tap paths of the kernels need (else they fall back)
+    x0 = (x0 // 8) * 8
+    x1 = -(-x1 // 8) * 8
     x0, y0 = max(x0, 0), max(y0, 0)
     x1, y1 = min(x1, src_w), min(y1, src_h)
     if x1 <= x0 or y1 <= y0:
@@ -399,6 +405,9 @@ class ShardedResampler:
         self._recv = None
         self._out = None
         self._out_t = None
+        self._slabs = self._gath = None
+        self.profile = False                # True: synchronise between phases and record phase_ms
+        self.phase_ms = {}
         self.bytes_scatter = self.bytes_gather = self.bytes_root_out = self.bytes_rank_in = 0
 
     # -- what rank r needs of the source: (view-slices, origin) --
@@ -447,9 +456,14 @@ class ShardedResampler:
                     self._recv = torch.empty((y1 - y0, x1 - x0), dtype=self.src_tdt, device=self.dev)
                 sub, origin = self._recv, (x0, y0)
                 ops.append(dist.P2POp(dist.irecv, sub, self.g_rank(root), group=self.group))
+        if self.profile:
+            torch.cuda.synchronize(); dist.barrier(group=self.group); _t0 = time.perf_counter()
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        if self.profile:
+            torch.cuda.synchronize(); dist.barrier(group=self.group); _t1 = time.perf_counter()
+            self.phase_ms["scatter"] = (_t1 - _t0) * 1e3
         # ---- compute + gather, strip by strip: the all_gather of strip k is in flight while strip k+1
         # is being resampled (NCCL runs it on its own stream behind an event of the compute stream) ----
         x0, y0, x1, y1 = mine["rect"]
@@ -461,41 +475,53 @@ class ShardedResampler:
         strips = [(k * hs, min((k + 1) * hs, slab_h)) for k in range(self.nsub) if k * hs < slab_h]
         fill = float(self.kw.get("fillvalue", 0))
         works, gathered = [], []
-        for (a, b) in strips:
+        if self._out_t is None:
+            # first call: agree on the result dtype.  Decided by the compute step (precision / method rules
+            # of the engine), so one small block is resampled and its dtype reduced over the ranks.
+            code = -1
+            if sub is not None and y1 > y0 and x1 > x0:
+                probe = self.resample_rect(self.transform, sub if self.backend == "nccl" else sub.numpy(), origin, full,
+                                           (x0, y0, min(x0 + 8, x1), min(y0 + 8, y1)), self.shape, self.method,
+                                           self.bound, self.kw)
+                pdt = probe.dtype if torch.is_tensor(probe) else torch.from_numpy(np.zeros(0, probe.dtype)).dtype
+                code = 0 if pdt == torch.float32 else 1
+            codet = torch.tensor([code], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(codet, op=dist.ReduceOp.MAX, group=self.group)
+            self._out_t = torch.float32 if int(codet[0]) <= 0 else torch.float64
+        if self._out is None:
+            # persistent buffers: the full result, one slab and one gather target per strip
+            self._out = torch.empty((world * per, nx) if rows_split else (ny, world * per), dtype=self._out_t,
+                                    device=self.dev)
+            self._slabs = [torch.empty((b - a, slab_w), dtype=self._out_t, device=self.dev) for (a, b) in strips]
+            direct = rows_split and len(strips) == 1           # rank blocks are contiguous in the result
+            self._gath = [self._out if direct else
+                          torch.empty((world * (b - a), slab_w), dtype=self._out_t, device=self.dev) for (a, b) in strips]
+        out = self._out
+        for k, (a, b) in enumerate(strips):
             # the part of this strip that lies inside the rank's real rectangle (ragged tails are fill)
             ry0, ry1 = y0 + a, min(y0 + b, y1)
             rect = (x0, ry0, x1, ry1)
-            blk = None
+            slab = self._slabs[k]
+            whole_strip = (ry1 - ry0 == b - a) and (x1 - x0 == slab_w)
+            if not whole_strip or sub is None:
+                slab.fill_(fill)
             if sub is not None and ry1 > ry0 and x1 > x0:
-                whole_strip = (ry1 - ry0 == b - a) and (x1 - x0 == slab_w) and self._out_t is not None and \
-                    self.backend == "nccl"
-                dst = torch.empty((b - a, slab_w), dtype=self._out_t, device=self.dev) if whole_strip else None
+                dst = slab if (whole_strip and self.backend == "nccl") else None
                 blk = self.resample_rect(self.transform, sub if self.backend == "nccl" else sub.numpy(), origin,
                                          full, rect, self.shape, self.method, self.bound, self.kw, out=dst)
-                blk = blk if torch.is_tensor(blk) else torch.from_numpy(np.ascontiguousarray(blk))
-            if self._out_t is None:
-                # first call: agree on the result dtype (0 = f32, 1 = f64); a rank whose block maps nowhere
-                # has nothing to say
-                code = torch.tensor([-1 if blk is None else (0 if blk.dtype == torch.float32 else 1)],
-                                    dtype=torch.int64, device=self.dev)
-                dist.all_reduce(code, op=dist.ReduceOp.MAX, group=self.group)
-                self._out_t = torch.float32 if int(code[0]) <= 0 else torch.float64
-            if blk is not None and tuple(blk.shape) == (b - a, slab_w) and blk.dtype == self._out_t and \
-                    blk.device == self.dev:
-                slab = blk
-            else:
-                slab = torch.full((b - a, slab_w), fill, dtype=self._out_t, device=self.dev)
-                if blk is not None:
+                if dst is None:
+                    blk = blk if torch.is_tensor(blk) else torch.from_numpy(np.ascontiguousarray(blk))
                     slab[:ry1 - ry0, :x1 - x0] = blk.to(device=self.dev, dtype=self._out_t)
-            g = torch.empty((world * (b - a), slab_w), dtype=self._out_t, device=self.dev)
+            g = self._gath[k]
             works.append(dist.all_gather_into_tensor(g, slab, group=self.group, async_op=True))
             gathered.append(((a, b), g, slab))
-        if self._out is None or self._out.dtype != self._out_t:
-            self._out = torch.empty((world * per, nx) if rows_split else (ny, world * per), dtype=self._out_t,
-                                    device=self.dev)
-        out = self._out
+        if self.profile:
+            torch.cuda.synchronize(); dist.barrier(group=self.group); _t2 = time.perf_counter()
+            self.phase_ms["compute+gather"] = (_t2 - _t1) * 1e3
         for w, ((a, b), g, _) in zip(works, gathered):
             w.wait()
+            if g is out:
+                continue
             g3 = g.view(world, b - a, slab_w)
             if rows_split:
                 out.view(world, per, nx)[:, a:b, :] = g3
@@ -506,6 +532,9 @@ class ShardedResampler:
         self.bytes_root_out = self.bytes_scatter + (world - 1) * slab_h * slab_w * eso
         self.bytes_rank_in = (world - 1) * slab_h * slab_w * eso
         out = out[:ny] if rows_split else out[:, :nx]
+        if self.profile:
+            torch.cuda.synchronize(); _t3 = time.perf_counter()
+            self.phase_ms["assemble"] = (_t3 - _t2) * 1e3
         if sync and self.backend == "nccl":
             torch.cuda.current_stream().synchronize()
         return out
