@@ -10,9 +10,14 @@
  * Conventions (same as the reference, core.py:48-59): vectors are (X,Y) in the last axis, images
  * are row-major [Y][X]; pixel centres sit on integers; (0,0) is the centre of the first pixel.
  * All data pointers are DEVICE pointers unless a name ends in _host.  Calls are stream-ordered on
- * the cudaStream_t passed as `stream` (a void* here so the header needs no CUDA include), keep no
- * hidden global state, and may be issued concurrently on different streams / devices.  Nothing
- * throws across the boundary: every function returns a tfm_status.
+ * the cudaStream_t passed as `stream` (a void* here so the header needs no CUDA include) and may be
+ * issued concurrently on different streams / devices.  Nothing throws across the boundary: every
+ * function returns a tfm_status.
+ * Process-wide state, all of it: the launch counter behind tfm_launch_count(), the thread-local name
+ * behind tfm_last_kernel(), and two mutex-protected LRU caches of driver objects laid over CALLER memory
+ * (256 texture objects, 16 tensor maps, keyed by device / pointer / geometry -- they describe address
+ * ranges, not contents).  Neither cache ever blocks a stream: a texture object evicted while a launch
+ * may still read through it is destroyed later, once an event recorded behind that launch has completed.
  */
 #ifndef TFM_B200_H
 #define TFM_B200_H

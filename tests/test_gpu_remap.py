@@ -124,3 +124,32 @@ def test_remap_between_added_projections(tfm, oracle, src_proj, dst_proj):
     assert np.count_nonzero(out.data) > 0.7 * n * n
     with pytest.raises(NotImplementedError):
         tfm.WCS(dict(a, PV2_1=0.5))                               # non-default projection parameter
+
+
+@pytest.mark.parametrize("rot", [0.0, 17.0])
+def test_tan_to_car_fast_path_tables(tfm, oracle, rot):
+    """fp32 fast path of the TAN -> CAR remap: the fused WCS pair takes sin/cos of the CAR frame's native
+    longitude / latitude from per-tile angle-addition tables (tfm_chain.cuh, wcs_car_tables) -- batch of
+    planes (LDG kernel), single frame (texture-gather kernel), an axis-aligned and a rotated CD matrix,
+    an output grid that is not a multiple of the tile.  Against the oracle (2e-5, the fp32 tolerance) and
+    against the parity mode of the same library (coordinates agree to 1e-9 px)."""
+    n, m = 150, 171
+    c, s = np.cos(np.radians(rot)), np.sin(np.radians(rot))
+    tan = {'NAXIS': 2, 'NAXIS1': m, 'NAXIS2': n, 'CTYPE1': 'RA---TAN', 'CTYPE2': 'DEC--TAN', 'CUNIT1': 'deg',
+           'CUNIT2': 'deg', 'CRPIX1': m / 2 + 0.5, 'CRPIX2': n / 2 + 0.5, 'CRVAL1': 150.0, 'CRVAL2': 20.0,
+           'CD1_1': -0.02 * c, 'CD1_2': 0.02 * s, 'CD2_1': 0.02 * s, 'CD2_2': 0.02 * c}
+    car = dict(tan, CTYPE1='RA---CAR', CTYPE2='DEC--CAR')
+    frames = np.random.default_rng(14).random((3, n, m)).astype(np.float32)
+    total = tfm.Composition([tfm.WCS(car).inverse(), tfm.WCS(tan)])
+    from transform_b200 import _lib
+    batch = total.resample(frames, method='linear', shape=(3, n, m), precision='fp32')
+    assert _lib.last_kernel() == "k_resample<trunc>", _lib.last_kernel()
+    single = total.resample(np.ascontiguousarray(np.pad(frames[1], ((0, 0), (0, 5)))), method='linear',
+                            shape=(n, m), precision='fp32')             # 176 columns: 32-byte pitch -> texture path
+    assert _lib.last_kernel() == "k_resample_tex4<car-tan>", _lib.last_kernel()
+    for k in range(3):
+        want = oracle.resample(to_oracle(total), frames[k], method='linear', shape=(n, m))
+        assert_close_rel(batch[k], want, 2e-5, "frame %d rot %g" % (k, rot))
+    want1 = oracle.resample(to_oracle(total), np.pad(frames[1], ((0, 0), (0, 5))), method='linear', shape=(n, m))
+    assert_close_rel(single, want1, 2e-5, "texture path rot %g" % rot)
+    assert np.count_nonzero(batch[0]) > 0.5 * n * m

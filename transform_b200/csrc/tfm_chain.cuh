@@ -397,6 +397,106 @@ __device__ __forceinline__ void op_wcs_pair(const tfm_op &op, double &x, double 
     y = (op.p[17] * ox + op.p[18] * oy + op.p[20]) - 1.0;
 }
 
+// ---- per-tile tables for a fused WCS pair whose FIRST projection is CAR (the output frame of a
+// TAN -> CAR remap, BASELINE config 4).  Native longitude and latitude of a CAR pixel are AFFINE in the
+// pixel indices, phi = D2R (cd00 dx + cd01 dy), theta = D2R (cd10 dx + cd11 dy), so inside a tile their
+// cosines and sines follow from four small tables by the angle-addition formulas: 4 x (tile edge) sincos
+// per TILE instead of two per PIXEL (fp64 sincos is ~45 instructions; the pair op was 12 % of the HBM
+// roofline with them).  The celestial rotation and the second projection's CD^-1 are folded into three
+// 3-vectors (u, v, w) = (CDinv_B R)_{x,y} and R_z rows, so a TAN target costs 9 DFMA, one division and
+// two DFMA per pixel.
+struct WcsCarCoef {            // per-thread constants of the second half (registers)
+    double ux, uy, uz, vx, vy, vz, wx, wy, wz, cx, cy;
+};
+
+__device__ __forceinline__ void wcs_car_tables(const tfm_op &op, double TX0, double TY0, int ni, int nj,
+                                               double2 *aphi, double2 *bphi, double2 *ath, double2 *bth,
+                                               int tid, int nthreads)
+{
+    const double dx0 = (TX0 + 1.0) - op.p[0], dy0 = (TY0 + 1.0) - op.p[1];
+    for (int k = tid; k < 2 * (ni + nj); k += nthreads) {
+        double s, c;
+        if (k < ni) {
+            sincos(TFM_D2R * op.p[2] * (double)k, &s, &c);
+            aphi[k] = make_double2(c, s);
+        } else if (k < ni + nj) {
+            const int j = k - ni;
+            sincos(TFM_D2R * (op.p[2] * dx0 + op.p[3] * (dy0 + (double)j)), &s, &c);
+            bphi[j] = make_double2(c, s);
+        } else if (k < 2 * ni + nj) {
+            const int i = k - ni - nj;
+            sincos(TFM_D2R * op.p[4] * (double)i, &s, &c);
+            ath[i] = make_double2(c, s);
+        } else {
+            const int j = k - 2 * ni - nj;
+            sincos(TFM_D2R * (op.p[4] * dx0 + op.p[5] * (dy0 + (double)j)), &s, &c);
+            bth[j] = make_double2(c, s);
+        }
+    }
+}
+
+__device__ __forceinline__ WcsCarCoef wcs_car_coef(const tfm_op &op)
+{
+    // x = (c15 ox + c16 oy + crpix1_B) - 1 with (ox, oy) = (ny, -nx) R2D / nz for a TAN target, n = R m
+    const double *R = op.p + 6;
+    WcsCarCoef k;
+    k.ux = op.p[15] * R[3] - op.p[16] * R[0]; k.uy = op.p[15] * R[4] - op.p[16] * R[1]; k.uz = op.p[15] * R[5] - op.p[16] * R[2];
+    k.vx = op.p[17] * R[3] - op.p[18] * R[0]; k.vy = op.p[17] * R[4] - op.p[18] * R[1]; k.vz = op.p[17] * R[5] - op.p[18] * R[2];
+    k.wx = R[6]; k.wy = R[7]; k.wz = R[8];
+    k.cx = op.p[19] - 1.0; k.cy = op.p[20] - 1.0;
+    return k;
+}
+
+// pixel (i, j) of the tile whose tables were built for origin (TX0, TY0); target projection TAN
+__device__ __forceinline__ void wcs_car_tan_from_tables(const WcsCarCoef &k, int i, int j, const double2 *aphi,
+                                                        const double2 *bphi, const double2 *ath, const double2 *bth,
+                                                        double &x, double &y)
+{
+    const double2 a = aphi[i], b = bphi[j], c = ath[i], d = bth[j];
+    const double cp = a.x * b.x - a.y * b.y, sp = a.y * b.x + a.x * b.y;
+    const double ct = c.x * d.x - c.y * d.y, st = c.y * d.x + c.x * d.y;
+    const double mx = ct * cp, my = ct * sp, mz = st;
+    const double w = k.wx * mx + k.wy * my + k.wz * mz;
+    const double u = k.ux * mx + k.uy * my + k.uz * mz;
+    const double v = k.vx * mx + k.vy * my + k.vz * mz;
+    const double sc = (w > 0.0) ? TFM_R2D / w : nan("");           // theta <= 0: the far side of the sky
+    x = fma(u, sc, k.cx);
+    y = fma(v, sc, k.cy);
+}
+
+// Axis-aligned CD matrix of the CAR frame (cd01 = cd10 = 0: every FITS header without rotation, BASELINE
+// config 4): longitude depends on the COLUMN only, latitude on the ROW only, and with m = (ct cp, ct sp,
+// st) each of the three dot products is  ct (k_x cp + k_y sp) + k_z st = fma(ct[row], A[col], B[row]).
+// Per tile: one sincos and 6 flops per column and per row; per PIXEL: 3 DFMA, one reciprocal (hardware
+// seed + one Newton step: 2^-40, i.e. 4e-9 pixels at 4096), 3 more.  10 fp64 instructions instead of 35.
+__device__ __forceinline__ void wcs_car_sep_tables(const tfm_op &op, const WcsCarCoef &k, double TX0, double TY0,
+                                                   int ni, int nj, double4 *col, double4 *row, int tid, int nthreads)
+{
+    const double dx0 = (TX0 + 1.0) - op.p[0], dy0 = (TY0 + 1.0) - op.p[1];
+    for (int q = tid; q < ni + nj; q += nthreads) {
+        double s, c;
+        if (q < ni) {
+            sincos(TFM_D2R * op.p[2] * (dx0 + (double)q), &s, &c);
+            col[q] = make_double4(k.ux * c + k.uy * s, k.vx * c + k.vy * s, k.wx * c + k.wy * s, 0.0);
+        } else {
+            const int j = q - ni;
+            sincos(TFM_D2R * op.p[5] * (dy0 + (double)j), &s, &c);
+            row[j] = make_double4(c, k.uz * s, k.vz * s, k.wz * s);
+        }
+    }
+}
+
+__device__ __forceinline__ void wcs_car_tan_sep(const WcsCarCoef &k, const double4 a, const double4 b, double &x, double &y)
+{
+    const double w = fma(b.x, a.z, b.w), u = fma(b.x, a.x, b.y), v = fma(b.x, a.y, b.z);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+    r = fma(r, fma(-w, r, 1.0), r);
+    const double sc = (w > 0.0) ? TFM_R2D * r : nan("");           // theta <= 0: the far side of the sky
+    x = fma(u, sc, k.cx);
+    y = fma(v, sc, k.cy);
+}
+
 // "Heavy" ops are compiled only into dedicated kernel instantiations (template parameter SPH):
 //   0  none of them        1  WCS with linear axes, TAN or CAR (+ the fused WCS pair)
 //   2  every WCS projection and the pow()-based pincushion family

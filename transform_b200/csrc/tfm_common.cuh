@@ -22,7 +22,8 @@ int svd_hooks(int which, const double *in0, const double *in1, const double *in2
 
 
 // point-sampled, border-addressed texture object over a pitch-linear float image (cached; tfm_resample.cu)
-bool get_texture(const void *ptr, int w, int h, long long pitch, cudaTextureObject_t *out);
+bool get_texture(const void *ptr, int w, int h, long long pitch, cudaTextureObject_t *out, int *slot_out = nullptr);
+void texture_used(int slot, cudaStream_t st);      // record "this stream reads through the texture of `slot`"
 
 #ifdef __CUDACC__
 #define TFM_SANE_COORD 2.5e8   /* |coordinate| bound of the fast-mode floor/fraction (floor_frac_fast) */

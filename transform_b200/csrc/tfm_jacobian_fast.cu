@@ -740,12 +740,12 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
     // tap mode: texture gather where a pitch-linear texture can be laid over the source (one plane,
     // geometry within the 2-D texture limits), else 8-byte loads where rows are 8-byte aligned, else
     // 4-byte loads.  Tuning bits 4096 / 32768 force the 4-byte / 8-byte form for A/B runs.
-    int tm = 0;
+    int tm = 0, tex_slot = -1;
     if (!(a->tuning & 4096) && (reinterpret_cast<uintptr_t>(s.data) % 8) == 0 && (s.pitch % 8) == 0 &&
         (s.plane_pitch % 8) == 0)
         tm = 1;
     if (!(a->tuning & (4096 | 32768)) && s.n_planes == 1 && s.w <= 131072 && s.h <= 65000 && (s.pitch % 32) == 0 &&
-        (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 && get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &P.tex))
+        (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 && get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &P.tex, &tex_slot))
         tm = 2;
     P.tex_edges = (tm == 2 && a->bound_x == TFM_B_TRUNCATE && a->bound_y == TFM_B_TRUNCATE) ? 1 : 0;
 
@@ -794,6 +794,7 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
         }
 #undef TFM_CJ
         count_launch();
+        if (tm == 2) texture_used(tex_slot, st);
         set_last_kernel(tm == 2 ? "k_jacobian<fast32,const-J,tex>"
                                 : (tm == 1 ? "k_jacobian<fast32,const-J,ld64>" : "k_jacobian<fast32,const-J,ld32>"));
         *rc = cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
@@ -834,6 +835,7 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
     else if (tm == 1) k_jac_gauss_polar<1><<<grid, 256, 0, st>>>(P);
     else k_jac_gauss_polar<0><<<grid, 256, 0, st>>>(P);
     count_launch();
+    if (tm == 2) texture_used(tex_slot, st);
     set_last_kernel(tm == 2 ? "k_jacobian<fast32,analytic-polar,tex>"
                             : (tm == 1 ? "k_jacobian<fast32,analytic-polar,ld64>" : "k_jacobian<fast32,analytic-polar,ld32>"));
     *rc = cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;

@@ -155,8 +155,10 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
 //     x 4 rows fill whole 32-byte sectors anyway.)
 //   * the empty-tile test works from the tile centre and a host-computed half-extent;
 //   * floor/fraction in fixed point (floor_frac_fast).
-template <class A, bool AFF, int SPH>
-__global__ void __launch_bounds__(256)
+// WCSONLY: the chain is exactly one fused CAR -> TAN pair (a TAN -> CAR remap): an instantiation without
+// the chain interpreter -- 40 registers instead of 64, twice the resident warps for a latency-bound kernel
+template <class A, bool AFF, int SPH, bool WCSONLY = false>
+__global__ void __launch_bounds__(256, WCSONLY ? 6 : 1)
 k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -195,7 +197,7 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
             cx[j] = fma(P.aff[0], Xj, rx);
             cy[j] = fma(P.aff[2], Xj, ry);
         }
-    } else if (P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_POLAR) {
+    } else if (!WCSONLY && P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_POLAR) {
         __shared__ double2 s_ta[32], s_tb[32];
         __shared__ double s_ea[32], s_eb[32];
         const tfm_op &op0 = P.chain.ops[0];
@@ -207,7 +209,31 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
         for (int j = 0; j < 4; ++j)
             polar_from_tables(op0, TX0, TY0, px + 8 * j, py, s_ta, s_tb, s_ea, s_eb, cx[j], cy[j]);
         chain_eval_n<A, SPH, 4>(P.chain, cx, cy, 1);
-    } else {
+    } else if (WCSONLY || (SPH == 1 && P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_WCS_PAIR &&
+                           (P.chain.ops[0].flags & 0xffff) == (TFM_WCS_PROJ_CAR | (TFM_WCS_PROJ_TAN << 8)))) {
+        // CAR pixel -> sky -> TAN pixel: per-tile sincos tables (see wcs_car_tables, tfm_chain.cuh)
+        __shared__ double4 s_t0[32], s_t1[32];
+        const tfm_op &op0 = P.chain.ops[0];
+        const double TX0 = (double)(P.dst_x0 + (long long)blockIdx.x * 32);
+        const double TY0 = (double)(P.dst_y0 + (long long)blockIdx.y * 32);
+        const WcsCarCoef kc = wcs_car_coef(op0);
+        if (op0.p[3] == 0.0 && op0.p[4] == 0.0) {              // axis-aligned CD (CTA-uniform): separable form
+            wcs_car_sep_tables(op0, kc, TX0, TY0, 32, 32, s_t0, s_t1, threadIdx.x, 256);
+            __syncthreads();
+            const double4 b = s_t1[py];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wcs_car_tan_sep(kc, s_t0[px + 8 * j], b, cx[j], cy[j]);
+        } else {
+            double2 *const s_aphi = reinterpret_cast<double2 *>(s_t0), *const s_ath = s_aphi + 32;
+            double2 *const s_bphi = reinterpret_cast<double2 *>(s_t1), *const s_bth = s_bphi + 32;
+            wcs_car_tables(op0, TX0, TY0, 32, 32, s_aphi, s_bphi, s_ath, s_bth, threadIdx.x, 256);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                wcs_car_tan_from_tables(kc, px + 8 * j, py, s_aphi, s_bphi, s_ath, s_bth, cx[j], cy[j]);
+        }
+        if (!WCSONLY) chain_eval_n<A, SPH, 4>(P.chain, cx, cy, 1);
+    } else if (!WCSONLY) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             cx[j] = (double)(P.dst_x0 + X + 8 * j);
@@ -254,23 +280,61 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
 // Texture objects over caller memory are cached per (device, pointer, geometry): creating one costs
 // microseconds, a resample launch ~100.  A texture object refers to an address range, not to its
 // contents, so reuse after the caller rewrote (or re-allocated) the buffer is safe.
+//
+// This cache and the tensor-map cache below are the library's only process-wide state besides the launch
+// counter (include/tfm_b200.h says so).  Both are mutex-protected, LRU, and never block a stream: every
+// launch that reads through a texture records an event behind itself on its stream; an evicted object
+// whose last reader has not finished is parked and destroyed by a later call once that event has
+// completed (round 1 drained the whole device with cudaDeviceSynchronize() instead).
 struct TexKey {
     int dev; const void *ptr; int w, h; long long pitch;
     bool operator==(const TexKey &o) const { return dev == o.dev && ptr == o.ptr && w == o.w && h == o.h && pitch == o.pitch; }
 };
+struct TexEntry {
+    TexKey key;
+    cudaTextureObject_t obj = 0;
+    cudaEvent_t last_use = nullptr;          // recorded behind the latest launch that reads through obj
+    bool used = false;
+    unsigned long long stamp = 0;            // LRU clock
+};
+constexpr int TEX_CACHE = 256;
 static std::mutex g_tex_mu;
-static TexKey g_tex_keys[16];
-static cudaTextureObject_t g_tex_objs[16];
-static int g_tex_n = 0, g_tex_next = 0;
+static TexEntry g_tex[TEX_CACHE];
+static int g_tex_n = 0;
+static unsigned long long g_tex_clock = 0;
+struct TexParked { cudaTextureObject_t obj; cudaEvent_t ev; int dev; };
+static TexParked g_tex_parked[TEX_CACHE];
+static int g_tex_nparked = 0;
 
-bool get_texture(const void *ptr, int w, int h, long long pitch, cudaTextureObject_t *out)
+static void tex_reap_parked(int dev)         // destroy parked objects whose last reader has finished
+{
+    int k = 0;
+    for (int i = 0; i < g_tex_nparked; ++i) {
+        TexParked &p = g_tex_parked[i];
+        if (p.dev == dev && cudaEventQuery(p.ev) == cudaSuccess) {
+            cudaDestroyTextureObject(p.obj);
+            cudaEventDestroy(p.ev);
+        } else {
+            g_tex_parked[k++] = p;
+        }
+    }
+    cudaGetLastError();                      // cudaErrorNotReady from the queries is not an error
+    g_tex_nparked = k;
+}
+
+bool get_texture(const void *ptr, int w, int h, long long pitch, cudaTextureObject_t *out, int *slot_out)
 {
     int dev = 0;
     cudaGetDevice(&dev);
     TexKey key{dev, ptr, w, h, pitch};
     std::lock_guard<std::mutex> lock(g_tex_mu);
     for (int i = 0; i < g_tex_n; ++i)
-        if (g_tex_keys[i] == key) { *out = g_tex_objs[i]; return true; }
+        if (g_tex[i].key == key) {
+            g_tex[i].stamp = ++g_tex_clock;
+            *out = g_tex[i].obj;
+            if (slot_out) *slot_out = i;
+            return true;
+        }
     cudaResourceDesc rd;
     memset(&rd, 0, sizeof(rd));
     rd.resType = cudaResourceTypePitch2D;
@@ -288,20 +352,47 @@ bool get_texture(const void *ptr, int w, int h, long long pitch, cudaTextureObje
     td.normalizedCoords = 0;
     cudaTextureObject_t t = 0;
     if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (g_tex_nparked) tex_reap_parked(dev);
     int slot;
-    if (g_tex_n < 16) slot = g_tex_n++;
+    if (g_tex_n < TEX_CACHE) slot = g_tex_n++;
     else {
-        // eviction (more than 16 live source geometries): a kernel on some stream may still be reading
-        // through the victim, so drain the device before destroying it -- a rare, slow path
-        slot = g_tex_next;
-        g_tex_next = (g_tex_next + 1) & 15;
-        cudaDeviceSynchronize();
-        cudaDestroyTextureObject(g_tex_objs[slot]);
+        // evict the least recently used entry; a kernel on some stream may still be reading through it
+        slot = 0;
+        for (int i = 1; i < TEX_CACHE; ++i)
+            if (g_tex[i].stamp < g_tex[slot].stamp) slot = i;
+        TexEntry &v = g_tex[slot];
+        const bool busy = v.used && v.last_use && cudaEventQuery(v.last_use) != cudaSuccess;
+        cudaGetLastError();
+        if (busy && g_tex_nparked < TEX_CACHE) {
+            g_tex_parked[g_tex_nparked++] = TexParked{v.obj, v.last_use, v.key.dev};
+            v.last_use = nullptr;            // the parked record owns the event now
+        } else {
+            if (busy) cudaEventSynchronize(v.last_use);       // parking lot full: wait for this ONE reader
+            cudaDestroyTextureObject(v.obj);
+        }
+        v.used = false;
     }
-    g_tex_keys[slot] = key;
-    g_tex_objs[slot] = t;
+    g_tex[slot].key = key;
+    g_tex[slot].obj = t;
+    g_tex[slot].stamp = ++g_tex_clock;
     *out = t;
+    if (slot_out) *slot_out = slot;
     return true;
+}
+
+// call right after a launch on `st` that reads through the texture of `slot`
+void texture_used(int slot, cudaStream_t st)
+{
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_tex_mu);
+    TexEntry &e = g_tex[slot];
+    if (!e.last_use && cudaEventCreateWithFlags(&e.last_use, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        e.last_use = nullptr;
+        return;
+    }
+    cudaEventRecord(e.last_use, st);
+    e.used = true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -862,18 +953,22 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
     } else if (a->precision == TFM_PREC_FAST32) {
         // texture-gather variant: linear, truncate on both axes with the default fill 0, one plane,
         // geometry within the limits of pitch-linear 2-D textures
+        // (a batch of planes runs the texture kernel once per plane, each plane through its own object)
         cudaTextureObject_t tex = 0;
+        int tex_slot = -1;
+        const bool multi = s.n_planes > 1;
         const bool tex_ok = !generic && a->method == TFM_LINEAR && s.dtype == TFM_F32 && d.dtype == TFM_F32 &&
-                            a->fillvalue == 0.0 && s.n_planes == 1 && !(a->tuning & 16) &&
+                            a->fillvalue == 0.0 && !(a->tuning & 16) &&
+                            (!multi || ((s.plane_pitch % 512) == 0 && s.n_planes <= 192 && !(a->tuning & (128 | 256 | 8192)))) &&
                             s.w <= 131072 && s.h <= 65000 && (s.pitch % 32) == 0 &&
                             (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 &&
-                            get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &tex);
+                            get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &tex, &tex_slot);
         // TMA-staged variant: same conditions, host-composed affine map with a bounded source box
         bool tma_done = false;
         // Opt-in (tuning bit 256): measured SLOWER than the texture gather on B200 (8192^2: named chain
         // 0.138 vs 0.090 ms, pure shift 0.227 vs 0.141 ms) -- per-CTA load latency is exposed in this
         // one-box-per-CTA form and the shared-memory taps cost more issue slots than one TLD4.
-        if (tex_ok && aff && P.aff_bounded && (a->tuning & 256) && (s.pitch % 16) == 0 && !staged_fast) {
+        if (tex_ok && !multi && aff && P.aff_bounded && (a->tuning & 256) && (s.pitch % 16) == 0 && !staged_fast) {
             const double ex = 31.0 * (fabs(P.aff[0]) + fabs(P.aff[1])), ey = 31.0 * (fabs(P.aff[2]) + fabs(P.aff[3]));
             if (ex < 200.0 && ey < 200.0) {
                 TmaBox B;
@@ -900,7 +995,7 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
             }
         }
         // persistent multi-stage TMA pipeline: same conditions
-        if (!tma_done && tex_ok && aff && P.aff_bounded && (s.pitch % 16) == 0 && !(a->tuning & (128 | 16 | 256)) &&
+        if (!tma_done && tex_ok && !multi && aff && P.aff_bounded && (s.pitch % 16) == 0 && !(a->tuning & (128 | 16 | 256)) &&
             ((a->tuning & 8192) || affine_coverage(P.aff, d, s) >= TFM_PIPE_COVERAGE)) {
             const double ex = (PIPE_TW - 1) * fabs(P.aff[0]) + (PIPE_TH - 1) * fabs(P.aff[1]);
             const double ey = (PIPE_TW - 1) * fabs(P.aff[2]) + (PIPE_TH - 1) * fabs(P.aff[3]);
@@ -960,13 +1055,31 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
                 name = aff ? "k_resample_tex<affine>" : "k_resample_tex";
             } else {
                 const bool aff4 = aff && P.aff_bounded;
-                if (aff4) k_resample_tex4<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
-                else if (sph == 2) k_resample_tex4<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
-                else if (sph == 1) k_resample_tex4<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
-                else k_resample_tex4<Fast, false, 0><<<grid, 256, 0, st>>>(P, tex);
-                name = aff4 ? "k_resample_tex4<affine>" : "k_resample_tex4";
+                const bool wcs_only = !aff4 && P.chain.n == 1 && P.chain.ops[0].kind == TFM_OP_WCS_PAIR &&
+                                      (P.chain.ops[0].flags & 0xffff) == (TFM_WCS_PROJ_CAR | (TFM_WCS_PROJ_TAN << 8));
+                e = cudaSuccess;
+                for (long long k = 0; k < s.n_planes && e == cudaSuccess; ++k) {
+                    if (k > 0) {
+                        P.src = static_cast<const char *>(s.data) + k * s.plane_pitch;
+                        P.dst = static_cast<char *>(d.data) + k * d.plane_pitch;
+                        if (!get_texture(P.src, (int)s.w, (int)s.h, s.pitch, &tex, &tex_slot)) { e = cudaErrorUnknown; break; }
+                    }
+                    if (aff4) k_resample_tex4<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
+                    else if (wcs_only) k_resample_tex4<Fast, false, 1, true><<<grid, 256, 0, st>>>(P, tex);
+                    else if (sph == 2) k_resample_tex4<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
+                    else if (sph == 1) k_resample_tex4<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
+                    else k_resample_tex4<Fast, false, 0><<<grid, 256, 0, st>>>(P, tex);
+                    count_launch();
+                    texture_used(tex_slot, st);
+                    tex_slot = -1;
+                    e = cudaGetLastError();
+                }
+                name = aff4 ? "k_resample_tex4<affine>" : (wcs_only ? "k_resample_tex4<car-tan>" : "k_resample_tex4");
+                set_last_kernel(name);
+                return e == cudaSuccess ? TFM_OK : TFM_ECUDA;
             }
             count_launch();
+            texture_used(tex_slot, st);
             e = cudaGetLastError();
         } else if (s.dtype == TFM_F32 && d.dtype == TFM_F32) {
             if (staged_fast) { P.aff_c[0] += (float)s.x0; P.aff_c[1] += (float)s.y0; }

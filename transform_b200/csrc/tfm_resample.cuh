@@ -436,6 +436,31 @@ k_resample(const __grid_constant__ ResampleParams P)
             cx[j] = fma(P.aff[0], Xd, fma(P.aff[1], Yj, P.aff[4]));
             cy[j] = fma(P.aff[2], Xd, fma(P.aff[3], Yj, P.aff[5]));
         }
+    } else if (SPH == 1 && !A::exact && P.chain.n > 0 && P.chain.ops[0].kind == TFM_OP_WCS_PAIR &&
+               (P.chain.ops[0].flags & 0xffff) == (TFM_WCS_PROJ_CAR | (TFM_WCS_PROJ_TAN << 8))) {
+        // fused WCS pair, CAR pixel -> sky -> TAN pixel (a TAN -> CAR remap seen from its output grid):
+        // longitude / latitude are affine in the pixel, their sincos come from per-tile tables
+        __shared__ double4 s_t0[32], s_t1[8 * NPX];         // separable form: column / row tables;
+        const tfm_op &op0 = P.chain.ops[0];                   // general form: (aphi, ath) / (bphi, bth) pairs
+        const double TX0 = (double)(P.dst_x0 + (long long)blockIdx.x * 32);
+        const double TY0 = (double)(P.dst_y0 + (long long)blockIdx.y * (8 * NPX));
+        const WcsCarCoef kc = wcs_car_coef(op0);
+        if (op0.p[3] == 0.0 && op0.p[4] == 0.0) {              // axis-aligned CD (CTA-uniform)
+            wcs_car_sep_tables(op0, kc, TX0, TY0, 32, 8 * NPX, s_t0, s_t1, threadIdx.x, 256);
+            __syncthreads();
+            const double4 a = s_t0[px];
+#pragma unroll
+            for (int j = 0; j < NPX; ++j) wcs_car_tan_sep(kc, a, s_t1[py + 8 * j], cx[j], cy[j]);
+        } else {
+            double2 *const s_aphi = reinterpret_cast<double2 *>(s_t0), *const s_ath = s_aphi + 32;
+            double2 *const s_bphi = reinterpret_cast<double2 *>(s_t1), *const s_bth = s_bphi + 8 * NPX;
+            wcs_car_tables(op0, TX0, TY0, 32, 8 * NPX, s_aphi, s_bphi, s_ath, s_bth, threadIdx.x, 256);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NPX; ++j)
+                wcs_car_tan_from_tables(kc, px, py + 8 * j, s_aphi, s_bphi, s_ath, s_bth, cx[j], cy[j]);
+        }
+        chain_eval_n<A, SPH, NPX>(P.chain, cx, cy, 1);
     } else {
 #pragma unroll
         for (int j = 0; j < NPX; ++j) {
