@@ -377,7 +377,7 @@ def gpu_arm(args):
     # host buffers of this rank on the NUMA node of its GPU (matters for the end-to-end number at N > 1)
     from transform_b200 import _device as tdev
     all_cpus = os.sched_getaffinity(0)
-    numa_cpus = tdev.bind_to_gpu_numa(local)
+    numa_cpus = None if os.environ.get("TFM_BENCH_NO_NUMA") else tdev.bind_to_gpu_numa(local)
     # NCCL writes its version banner to stdout; park stdout on stderr until the JSON line is due
     sys.stdout.flush()
     saved_stdout = os.dup(1)
@@ -471,7 +471,7 @@ def gpu_arm(args):
 
     step_e2e_sync()
     barrier()
-    k_e2e = max(1, min(args.steps, 10))
+    k_e2e = max(1, min(args.steps, 20))
     t0 = time.perf_counter()
     for _ in range(k_e2e):
         step_e2e_sync()

@@ -36,6 +36,7 @@ struct JacFastParams {
     int bound_x, bound_y;
     int flux;                                // phot='flux': scale by |det J| (SVD.pyx:285-286)
     int lw;                                  // log2 of the warp patch width
+    int quads;                               // lanes 4k..4k+3 cover a 2 x 2 block (texture requests are per quad)
     int max_half;                            // cap on the footprint half-width (max_reg / 2)
     int *status;
     cudaTextureObject_t tex;                 // point-sampled, border = 0 (tap mode 2)
@@ -460,11 +461,23 @@ __device__ __forceinline__ float gauss_run(const JacFastParams &P, const float *
 
 // thread -> pixel map of a 32 x 32 tile: a warp covers a (1 << lw) x (32 >> lw) patch, repeated 4 times
 // 8 rows apart, so that the 32 footprints one tap load gathers from sit in a compact source patch
-__device__ __forceinline__ void patch_xy(int lw, int tid, int &tx, int &ty)
+// With `quads`, lanes 4k .. 4k+3 -- the group the texture unit serves as one request -- form a 2 x 2
+// block of output pixels instead of 4 pixels of one row, so that their footprints share sectors.
+__device__ __forceinline__ void patch_xy(int lw, int quads, int tid, int &tx, int &ty)
 {
     const int lane = tid & 31, wrp = tid >> 5;
-    tx = ((wrp & ((32 >> lw) - 1)) << lw) + (lane & ((1 << lw) - 1));
-    ty = (wrp >> (5 - lw)) * (32 >> lw) + (lane >> lw);
+    int lx, ly;
+    if (quads) {
+        const int q = lane & 3, rest = lane >> 2;                    // rest: 8 quads of the patch
+        const int qw = (1 << lw) >> 1;                               // quads per patch row
+        lx = ((rest & (qw - 1)) << 1) + (q & 1);
+        ly = ((rest / qw) << 1) + (q >> 1);
+    } else {
+        lx = lane & ((1 << lw) - 1);
+        ly = lane >> lw;
+    }
+    tx = ((wrp & ((32 >> lw) - 1)) << lw) + lx;
+    ty = (wrp >> (5 - lw)) * (32 >> lw) + ly;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -483,7 +496,7 @@ k_jac_gauss_const(const __grid_constant__ JacFastParams P)
     const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
     float *const dst_base = P.dst + (long long)blockIdx.z * P.dst_plane;
     int tx, ty;
-    patch_xy(P.lw, threadIdx.x, tx, ty);
+    patch_xy(P.lw, P.quads, threadIdx.x, tx, ty);
     const int X = blockIdx.x * FT + tx;
     if (X >= P.dst_w) return;
     const int Y0 = blockIdx.y * FT + ty;
@@ -558,7 +571,7 @@ k_jac_gauss_polar(const __grid_constant__ JacFastParams P)
     __syncthreads();
 
     int tx, ty;
-    patch_xy(P.lw, tid, tx, ty);
+    patch_xy(P.lw, P.quads, tid, tx, ty);
     const int X = blockIdx.x * FT + tx;
     if (X >= P.dst_w) return;
     const int Yt = blockIdx.y * FT + ty;
@@ -748,6 +761,7 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
         (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 && get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &P.tex, &tex_slot))
         tm = 2;
     P.tex_edges = (tm == 2 && a->bound_x == TFM_B_TRUNCATE && a->bound_y == TFM_B_TRUNCATE) ? 1 : 0;
+    const bool want_quads = (tm == 2) != ((a->tuning & 65536) != 0);   // default for texture taps; bit 65536 toggles
 
     bool lin = true;
     for (int i = 0; i < a->n_ops; ++i) lin = lin && is_linear_like(a->chain[i]);
@@ -831,6 +845,7 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
     if (a->tuning & 1024) P.lw = 5;
     if (a->tuning & 2048) P.lw = 2;
     if (a->tuning & 16384) P.lw = 4;
+    P.quads = (want_quads && P.lw >= 1 && P.lw <= 4) ? 1 : 0;
     if (tm == 2) k_jac_gauss_polar<2><<<grid, 256, 0, st>>>(P);
     else if (tm == 1) k_jac_gauss_polar<1><<<grid, 256, 0, st>>>(P);
     else k_jac_gauss_polar<0><<<grid, 256, 0, st>>>(P);
