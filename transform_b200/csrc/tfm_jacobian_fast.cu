@@ -41,7 +41,8 @@ struct JacFastParams {
     int *status;
     cudaTextureObject_t tex;                 // point-sampled, border = 0 (tap mode 2)
     int tex_edges;                           // both bounds truncate: the texture's border IS the reference's truncated
-                                             // tap wherever the staged rectangle ends where the image ends
+                                             // tap wherever the staged rectangle ends where the image ends (1);
+                                             // 2: the whole image is staged, so that is everywhere
     float qscale;                            // log2(e) / oblur^2: exp(-q/oblur^2) = exp2(-q * qscale)
     float ob;                                // oblur
     float padval, half_pow, m2_over_pow;     // padding (helpers.pyx:1661-1662): pad_pow / 2, -2 / pad_pow
@@ -399,23 +400,28 @@ __device__ __forceinline__ TapRec gauss_setup(const JacFastParams &P, const floa
         if ((P.bound_x == TFM_B_TRUNCATE && (xi + half < 0 || xi - half >= P.full_w)) ||
             (P.bound_y == TFM_B_TRUNCATE && (yi + half < 0 || yi - half >= P.full_h)))
             return rec;
-        // whole footprint (plus the alignment column of the 8-byte form) inside the staged source
-        const int limx = P.src_w - 2 * half - (CP ? 1 : 0), limy = P.src_h - 2 * half;
         ox = xi - half - P.src_x0;
         oy = yi - half - P.src_y0;
         const float hf1 = (float)(half + 1);
-        const bool inside = limx > 0 && limy > 0 && (unsigned)ox < (unsigned)limx && (unsigned)oy < (unsigned)limy;
-        // texture taps, both boundaries truncate: beyond the staged rectangle the texture reads 0, which is
-        // right exactly where "beyond the rectangle" means "beyond the image" -- i.e. when the part of the
-        // footprint that lies inside the image lies inside the rectangle (always, for a whole image)
-        bool edges_ok = false;
-        if (TM == 2 && P.tex_edges) {
-            const int wx0 = max(xi - half, 0), wx1 = min(xi + half, P.full_w - 1);
-            const int wy0 = max(yi - half, 0), wy1 = min(yi + half, P.full_h - 1);
-            edges_ok = wx0 >= P.src_x0 && wx1 < P.src_x0 + P.src_w && wy0 >= P.src_y0 && wy1 < P.src_y0 + P.src_h;
+        bool reach_ok;
+        if (TM == 2 && P.tex_edges == 2) {
+            // texture taps, truncate boundaries, the whole image staged: the texture's border IS the
+            // reference's truncated tap -- nothing to classify
+            reach_ok = true;
+        } else {
+            // whole footprint (plus the alignment column of the 8-byte form) inside the staged source
+            const int limx = P.src_w - 2 * half - (CP ? 1 : 0), limy = P.src_h - 2 * half;
+            reach_ok = limx > 0 && limy > 0 && (unsigned)ox < (unsigned)limx && (unsigned)oy < (unsigned)limy;
+            // texture taps on a staged rectangle: beyond it the texture reads 0, which is right exactly where
+            // "beyond the rectangle" means "beyond the image" -- i.e. when the part of the footprint that
+            // lies inside the image lies inside the rectangle
+            if (TM == 2 && P.tex_edges && !reach_ok) {
+                const int wx0 = max(xi - half, 0), wx1 = min(xi + half, P.full_w - 1);
+                const int wy0 = max(yi - half, 0), wy1 = min(yi + half, P.full_h - 1);
+                reach_ok = wx0 >= P.src_x0 && wx1 < P.src_x0 + P.src_w && wy0 >= P.src_y0 && wy1 < P.src_y0 + P.src_h;
+            }
         }
-        fast = (inside || edges_ok) &&
-               half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * (hf1 * hf1) < 100.0f;
+        fast = reach_ok && half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * (hf1 * hf1) < 100.0f;
     } else if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) {
         return rec;                                              // NaN / inf (as tfm_jacobian.cu)
     }
@@ -462,12 +468,17 @@ __device__ __forceinline__ float gauss_run(const JacFastParams &P, const float *
 // thread -> pixel map of a 32 x 32 tile: a warp covers a (1 << lw) x (32 >> lw) patch, repeated 4 times
 // 8 rows apart, so that the 32 footprints one tap load gathers from sit in a compact source patch
 // With `quads`, lanes 4k .. 4k+3 -- the group the texture unit serves as one request -- form a 2 x 2
-// block of output pixels instead of 4 pixels of one row, so that their footprints share sectors.
+// block (1) or a 1 x 4 column (2) of output pixels instead of 4 pixels of one row (0), whichever keeps the
+// four footprints closest in the source: the texture path is bound by sectors per request.
 __device__ __forceinline__ void patch_xy(int lw, int quads, int tid, int &tx, int &ty)
 {
     const int lane = tid & 31, wrp = tid >> 5;
     int lx, ly;
-    if (quads) {
+    if (quads == 2) {                                                // 1 x 4 column: patch height >= 4 (lw <= 3)
+        const int q = lane & 3, rest = lane >> 2;
+        lx = rest & ((1 << lw) - 1);
+        ly = ((rest >> lw) << 2) + q;
+    } else if (quads) {
         const int q = lane & 3, rest = lane >> 2;                    // rest: 8 quads of the patch
         const int qw = (1 << lw) >> 1;                               // quads per patch row
         lx = ((rest & (qw - 1)) << 1) + (q & 1);
@@ -761,6 +772,7 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
         (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 && get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &P.tex, &tex_slot))
         tm = 2;
     P.tex_edges = (tm == 2 && a->bound_x == TFM_B_TRUNCATE && a->bound_y == TFM_B_TRUNCATE) ? 1 : 0;
+    if (P.tex_edges && s.x0 == 0 && s.y0 == 0 && s.full_h == s.h && s.full_w == s.w) P.tex_edges = 2;   // whole image
     const bool want_quads = (tm == 2) != ((a->tuning & 65536) != 0);   // default for texture taps; bit 65536 toggles
 
     bool lin = true;
@@ -846,6 +858,19 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
     if (a->tuning & 2048) P.lw = 2;
     if (a->tuning & 16384) P.lw = 4;
     P.quads = (want_quads && P.lw >= 1 && P.lw <= 4) ? 1 : 0;
+    if (P.quads && P.lw <= 3) {
+        // source displacement per output step: along x the arc (radius x angular step), along y the radial
+        // step; a column of 4 pixels is the compact quad when the arc step dominates over the region
+        const double t1 = sqrt(op.p[0] * op.p[0] * op.p[6] * op.p[6]), g1 = fabs(op.p[3]);
+        const double t2 = sqrt(op.p[1] * op.p[1] * op.p[6] * op.p[6]), g0 = fabs(op.p[2]);
+        const double xm = (double)d.x0 + 0.5 * (double)d.w, ym = (double)d.y0 + 0.5 * (double)d.h;
+        const double rmid = fabs(op.p[2] * xm + op.p[3] * ym + op.p[5]);
+        const double rr = (op.flags & TFM_RAD_R0_NOT_NONE) ? 1.0 : rmid;       // log-polar: steps scale together
+        const double step_x = hypot(rr * t1, g0 * ((op.flags & TFM_RAD_R0_NOT_NONE) ? 1.0 : 1.0));
+        const double step_y = hypot(rr * t2, g1);
+        if (step_x > 2.0 * step_y) P.quads = 2;
+    }
+    if (a->tuning & 131072) P.quads = (P.lw <= 3) ? 2 : P.quads;
     if (tm == 2) k_jac_gauss_polar<2><<<grid, 256, 0, st>>>(P);
     else if (tm == 1) k_jac_gauss_polar<1><<<grid, 256, 0, st>>>(P);
     else k_jac_gauss_polar<0><<<grid, 256, 0, st>>>(P);
