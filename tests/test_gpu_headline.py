@@ -214,8 +214,14 @@ def test_jacobian_fp32_polar_8192(tfm, oracle):
     want = np.stack([oracle.resample_jacobian(otr, src64, method='g', rows=(y, y + 1), max_reg=cap)[0] for y in rows])
     knife = (np.arange(n) % (n // 8)) == 0
     ref = None
-    for tuning, name in ((0, "k_jacobian<fast32,analytic-polar,tex>"), (32768, "k_jacobian<fast32,analytic-polar,ld64>"),
-                         (4096, "k_jacobian<fast32,analytic-polar,ld32>"), (512, "k_jacobian<fast32>")):
+    # default = per-row spectral tables (the radius of this unwrap is constant along output rows); tuning bit
+    # 262144 forces the per-pixel closed form of the general polar op
+    for tuning, name in ((0, "k_jacobian<fast32,analytic-polar-rows,tex>"),
+                         (32768, "k_jacobian<fast32,analytic-polar-rows,ld64>"),
+                         (4096, "k_jacobian<fast32,analytic-polar-rows,ld32>"),
+                         (262144, "k_jacobian<fast32,analytic-polar,tex>"),
+                         (262144 | 32768, "k_jacobian<fast32,analytic-polar,ld64>"),
+                         (262144 | 4096, "k_jacobian<fast32,analytic-polar,ld32>"), (512, "k_jacobian<fast32>")):
         out = rad.resample(src, method='Gaussian', precision='fp32', tuning=tuning)
         assert _lib.last_kernel() == name, (tuning, _lib.last_kernel())
         got = out[rows].cpu().numpy()

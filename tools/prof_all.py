@@ -4,7 +4,7 @@
     python tools/prof_all.py <case>
 
 cases: linear_shift linear_named linear_rot45 nearest cubic hann lanczos linear_polar linear_parity
-       jacobian_polar jacobian_constj jacobian_fd jacobian_parity jacobian_hanning
+       jacobian_polar jacobian_polar_single jacobian_constj jacobian_fd jacobian_parity jacobian_hanning
        wcs_batch wcs_single apply_affine apply_radial fits_m32 fits_i16"""
 import sys
 
@@ -40,6 +40,7 @@ if case.startswith(("linear", "nearest", "cubic", "hann", "lanczos", "jacobian")
         "linear_polar": lambda: polar.resample(src, method="linear", precision="fp32", out=f32),
         "linear_parity": lambda: named.resample(src, method="linear", out=f64),
         "jacobian_polar": lambda: polar.resample(src, method="Gaussian", precision="fp32", out=f32),
+        "jacobian_polar_single": lambda: polar.resample(src, method="Gaussian", precision="fp32", out=f32, tuning=262144),
         "jacobian_constj": lambda: down.resample(src, method="Gaussian", precision="fp32", out=f32),
         "jacobian_fd": lambda: polar.resample(src, method="Gaussian", precision="fp32", out=f32, tuning=512),
         "jacobian_parity": lambda: polar.resample(src, method="Gaussian", out=f64),

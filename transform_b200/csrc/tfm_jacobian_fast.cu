@@ -170,26 +170,35 @@ __device__ __forceinline__ void gauss_taps_cp(const float *__restrict__ p0, int 
 // ncu, 8192^2 polar unwrap (profiles/r2_k2.md): the 8-byte LDG form is bound by the LSU data pipe --
 // 3.5 wavefronts per request (one per cache line the 32 footprints of a warp touch), 2 taps per lane;
 // the texture path returns 4 taps per lane per request through its own filter/write-back stage.
+// Weight state of the texture form, all of it packed over the two columns of a gather (lane .x = column c,
+// lane .y = column c + 1), so that no instruction is spent moving scalars in and out of register pairs (ncu
+// source view of the first form: 54 MOV-type instructions per pixel, 11 % of the kernel):
+//   W  = (w(c, b), w(c+1, b))               weights of the current column pair
+//   R  = (r(c)^2 cA, r(c+1)^2 cA)           W(c+2) = W(c) R(c),  R(c+2) = R(c) cA^4
+//   RB = (rb(0, b), rb(1, b))               first pair of the next row: W(0, b+1) = W(0, b) RB(b),
+//                                           RB(b+1) = RB(b) cC;  R(0, b+1) = R(0, b) cB^2
+struct TexRows {
+    float2 W, R, RB;
+    float cA4, cB2, cC;
+};
+
+__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
+
 // one row pair (r, r+1) of the texture form, texels already fetched; BOTH = false: row r+1 lies outside
-// the square
+// the square.  Leaves the row state on row r + 2.
 template <int HALF, bool BOTH>
-__device__ __forceinline__ void tex_row_pair(const float4 (&g)[HALF + 1], float2 &WR, float2 &STEP,
-                                             const float2 CC1, const float2 CA13, const float2 CA4,
+__device__ __forceinline__ void tex_row_pair(const float4 (&g)[HALF + 1], TexRows &S,
                                              float2 &val2, float2 &wgt2, float &val, float &wgt)
 {
     constexpr int NP = HALF + 1;
-    const float2 ta = __fmul2_rn(WR, make_float2(WR.y, WR.y));       // (w0 r0, r0^2) of row r
-    float2 Wa = make_float2(WR.x, ta.x);
-    float2 Ra = __fmul2_rn(make_float2(ta.y, ta.y), CA13);
-    WR = __fmul2_rn(WR, STEP);
-    STEP = __fmul2_rn(STEP, CC1);
-    float2 Wb = make_float2(0.f, 0.f), Rb = make_float2(0.f, 0.f);
+    const float2 CA4 = bc2(S.cA4), CB2 = bc2(S.cB2), CC = bc2(S.cC);
+    float2 Wa = S.W, Ra = S.R;
+    float2 Wb = __fmul2_rn(S.W, S.RB), Rb = __fmul2_rn(S.R, CB2);
     if (BOTH) {
-        const float2 tb = __fmul2_rn(WR, make_float2(WR.y, WR.y));
-        Wb = make_float2(WR.x, tb.x);
-        Rb = __fmul2_rn(make_float2(tb.y, tb.y), CA13);
-        WR = __fmul2_rn(WR, STEP);
-        STEP = __fmul2_rn(STEP, CC1);
+        const float2 RB1 = __fmul2_rn(S.RB, CC);
+        S.W = __fmul2_rn(Wb, RB1);
+        S.R = __fmul2_rn(Rb, CB2);
+        S.RB = __fmul2_rn(RB1, CC);
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -198,12 +207,12 @@ __device__ __forceinline__ void tex_row_pair(const float4 (&g)[HALF + 1], float2
             val2 = __ffma2_rn(make_float2(g[i].w, g[i].z), Wa, val2);
             wgt2 = __fadd2_rn(wgt2, Wa);
             Wa = __fmul2_rn(Wa, Ra);
-            Ra = __fmul2_rn(Ra, CA4);
+            if (i + 1 < HALF) Ra = __fmul2_rn(Ra, CA4);
             if (BOTH) {
                 val2 = __ffma2_rn(make_float2(g[i].x, g[i].y), Wb, val2);
                 wgt2 = __fadd2_rn(wgt2, Wb);
                 Wb = __fmul2_rn(Wb, Rb);
-                Rb = __fmul2_rn(Rb, CA4);
+                if (i + 1 < HALF) Rb = __fmul2_rn(Rb, CA4);
             }
         } else {                                             // last pair: column N is outside the square
             val = fmaf(g[i].w, Wa.x, val);
@@ -229,6 +238,7 @@ __device__ __forceinline__ void gauss_taps_tex(cudaTextureObject_t tex, int xs, 
     const float fx0 = (float)(xs + 1);
     float fy = (float)(ys + 1);
     float2 val2 = make_float2(0.0f, 0.0f), wgt2 = make_float2(0.0f, 0.0f);
+    TexRows S;
     if constexpr (HALF <= 2) {
         float4 g[NP][NP];
 #pragma unroll
@@ -236,31 +246,31 @@ __device__ __forceinline__ void gauss_taps_tex(cudaTextureObject_t tex, int xs, 
 #pragma unroll
             for (int i = 0; i < NP; ++i)
                 g[j][i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy + (float)(2 * j), 0);
-        const float cA2 = cA * cA, cA4s = cA2 * cA2;
-        const float2 CA4 = make_float2(cA4s, cA4s);
-        const float2 CA13 = make_float2(cA, cA * cA2);       // R2 = r0^2 * (cA, cA^3)
-        float2 WR = make_float2(w0, r0);                     // (first weight, first ratio) of the row
-        float2 STEP = make_float2(rb, cB);                   // row-to-row: w0 *= rb, r0 *= cB; rb *= cC
-        const float2 CC1 = make_float2(cC, 1.0f);
+        const float cA2 = cA * cA, r02 = r0 * r0;
+        S.W = __fmul2_rn(bc2(w0), make_float2(1.0f, r0));
+        S.R = __fmul2_rn(bc2(r02), make_float2(cA, cA * cA2));
+        S.RB = __fmul2_rn(bc2(rb), make_float2(1.0f, cB));
+        S.cA4 = cA2 * cA2; S.cB2 = cB * cB; S.cC = cC;
 #pragma unroll
-        for (int j = 0; j < HALF; ++j)
-            tex_row_pair<HALF, true>(g[j], WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
-        tex_row_pair<HALF, false>(g[HALF], WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
+        for (int j = 0; j < HALF; ++j) tex_row_pair<HALF, true>(g[j], S, val2, wgt2, val, wgt);
+        tex_row_pair<HALF, false>(g[HALF], S, val2, wgt2, val, wgt);
     } else {
-        const float cA2 = cA * cA, cA4s = cA2 * cA2;
-        const float2 CA4 = make_float2(cA4s, cA4s);
-        const float2 CA13 = make_float2(cA, cA * cA2);
-        float2 WR = make_float2(w0, r0);
-        float2 STEP = make_float2(rb, cB);
-        const float2 CC1 = make_float2(cC, 1.0f);
+        float4 g[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
+        const float cA2 = cA * cA, r02 = r0 * r0;
+        S.W = __fmul2_rn(bc2(w0), make_float2(1.0f, r0));
+        S.R = __fmul2_rn(bc2(r02), make_float2(cA, cA * cA2));
+        S.RB = __fmul2_rn(bc2(rb), make_float2(1.0f, cB));
+        S.cA4 = cA2 * cA2; S.cB2 = cB * cB; S.cC = cC;
 #pragma unroll 1
-        for (int j = 0; j < NP; ++j, fy += 2.0f) {
-            float4 g[NP];
+        for (int j = 0; j < HALF; ++j) {
+            fy += 2.0f;
+            tex_row_pair<HALF, true>(g, S, val2, wgt2, val, wgt);
 #pragma unroll
             for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
-            if (j < HALF) tex_row_pair<HALF, true>(g, WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
-            else tex_row_pair<HALF, false>(g, WR, STEP, CC1, CA13, CA4, val2, wgt2, val, wgt);
         }
+        tex_row_pair<HALF, false>(g, S, val2, wgt2, val, wgt);
     }
     val += val2.x + val2.y;
     wgt += wgt2.x + wgt2.y;
@@ -379,19 +389,18 @@ struct TapRec {
     float res;             // value of a pixel that needs no taps
 };
 
-// Classifies the pixel (all-out / slow path / recurrence) and prepares the recurrence.  Pixels the
-// recurrence cannot serve are finished here, out of line.
+// Classifies the pixel: 1 = the recurrence can serve it (floor / fraction of the source position in xi, yi,
+// xf, yf); 0 = finished here (`res` holds its value: all-out, or the out-of-line slow path).
 template <int TM>
-__device__ __forceinline__ TapRec gauss_setup(const JacFastParams &P, const float *__restrict__ src_base, double px, double py,
-                                              float Aq, float Bq, float Cq, int half, int &state)
+__device__ __forceinline__ int gauss_classify(const JacFastParams &P, const float *__restrict__ src_base, double px, double py,
+                                              float Aq, float Bq, float Cq, int half, int &xi, int &yi, float &xf, float &yf,
+                                              float &res, int &state, int fit = -1)
 {
-    TapRec rec;
     constexpr bool CP = (TM == 1);
-    rec.off = -1; rec.ys = 0; rec.half = half; rec.w0 = 0.0f; rec.r0 = 0.0f; rec.rb = 0.0f; rec.res = 0.0f;
+    res = 0.0f;
     const bool sane = (fabs(px) < TFM_SANE_COORD) && (fabs(py) < TFM_SANE_COORD);
     bool fast = false;
-    int xi = 0, yi = 0, ox = 0, oy = 0;
-    float xf = 0.0f, yf = 0.0f;
+    xi = 0; yi = 0; xf = 0.0f; yf = 0.0f;
     if (sane) {
         floor_frac_fast(px, xi, xf);
         floor_frac_fast(py, yi, yf);
@@ -399,9 +408,8 @@ __device__ __forceinline__ TapRec gauss_setup(const JacFastParams &P, const floa
         // weights are (helpers.pyx:1793-1800)
         if ((P.bound_x == TFM_B_TRUNCATE && (xi + half < 0 || xi - half >= P.full_w)) ||
             (P.bound_y == TFM_B_TRUNCATE && (yi + half < 0 || yi - half >= P.full_h)))
-            return rec;
-        ox = xi - half - P.src_x0;
-        oy = yi - half - P.src_y0;
+            return 0;
+        const int ox = xi - half - P.src_x0, oy = yi - half - P.src_y0;
         const float hf1 = (float)(half + 1);
         bool reach_ok;
         if (TM == 2 && P.tex_edges == 2) {
@@ -421,16 +429,34 @@ __device__ __forceinline__ TapRec gauss_setup(const JacFastParams &P, const floa
                 reach_ok = wx0 >= P.src_x0 && wx1 < P.src_x0 + P.src_w && wy0 >= P.src_y0 && wy1 < P.src_y0 + P.src_h;
             }
         }
-        fast = reach_ok && half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * (hf1 * hf1) < 100.0f;
+        // fit: the caller already knows whether the recurrence may run (size 1..6, exponents in range)
+        fast = reach_ok && (fit >= 0 ? fit != 0
+                                     : (half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * (hf1 * hf1) < 100.0f));
     } else if (!(fabs(px) < 4.0e18) || !(fabs(py) < 4.0e18)) {
-        return rec;                                              // NaN / inf (as tfm_jacobian.cu)
+        return 0;                                                // NaN / inf (as tfm_jacobian.cu)
     }
     if (!fast) {
         const SlowResult sr = gauss_slow(P, src_base, px, py, Aq, Bq, Cq, half);
         state |= sr.state;
-        rec.res = sr.res;
-        return rec;
+        res = sr.res;
+        return 0;
     }
+    return 1;
+}
+
+// Classifies the pixel and prepares the recurrence.  Pixels the recurrence cannot serve are finished
+// here, out of line.
+template <int TM>
+__device__ __forceinline__ TapRec gauss_setup(const JacFastParams &P, const float *__restrict__ src_base, double px, double py,
+                                              float Aq, float Bq, float Cq, int half, int &state, int fit = -1)
+{
+    TapRec rec;
+    constexpr bool CP = (TM == 1);
+    rec.off = -1; rec.ys = 0; rec.half = half; rec.w0 = 0.0f; rec.r0 = 0.0f; rec.rb = 0.0f; rec.res = 0.0f;
+    int xi, yi;
+    float xf, yf;
+    if (!gauss_classify<TM>(P, src_base, px, py, Aq, Bq, Cq, half, xi, yi, xf, yf, rec.res, state, fit)) return rec;
+    const int ox = xi - half - P.src_x0, oy = yi - half - P.src_y0;
     const bool first_out = CP && (ox & 1);
     const float hf = (float)half;
     const float a0 = xf - hf - (first_out ? 1.0f : 0.0f), b0 = yf - hf;
@@ -533,50 +559,206 @@ k_jac_gauss_const(const __grid_constant__ JacFastParams P)
 }
 
 // ---------------------------------------------------------------------------------------------
+// analytic polar map: one pixel
+// ---------------------------------------------------------------------------------------------
+constexpr int PTN = FT + 2;                 // table entries: grid points G0-1 .. G0+FT (edge-copy clamp reach)
+
+struct PolarTables {
+    double2 ta[PTN], tb[PTN];               // (cos, sin)(i tX), (cos, sin)(theta(X0, Y0) + j tY)
+    double ea[PTN], eb[PTN];                // log-polar: exp(i a10), r0 exp(rho(X0, Y0) + j a11)
+};
+
+// tables of the tile whose first grid point is (GX0, GY0); same formulas as polar_tables (tfm_chain.cuh)
+__device__ __forceinline__ void polar_fill_tables(const JacFastParams &P, PolarTables &T, int GX0, int GY0, int tid)
+{
+    const double X0 = (double)(GX0 - 1), Y0d = (double)(GY0 - 1);
+    const bool lg = P.lg != 0;
+    if (tid < 2 * PTN) {
+        const double tX = P.pa[0] * P.coeff, tY = P.pa[1] * P.coeff;
+        double s, c;
+        if (tid < PTN) {
+            sincos((double)tid * tX, &s, &c);
+            T.ta[tid] = make_double2(c, s);
+            if (lg) T.ea[tid] = exp((double)tid * P.pa[2]);
+        } else {
+            const int j = tid - PTN;
+            const double t0 = fma(P.pa[0], X0, fma(P.pa[1], Y0d, P.pa[4])) * P.coeff;
+            sincos(fma((double)j, tY, t0), &s, &c);
+            T.tb[j] = make_double2(c, s);
+            if (lg) {
+                const double rho0 = fma(P.pa[2], X0, fma(P.pa[3], Y0d, P.pa[5]));
+                T.eb[j] = P.r0 * exp(fma((double)j, P.pa[3], rho0));
+            }
+        }
+    }
+}
+
+struct PolarPix {
+    double px, py;         // source position
+    float Aq, Bq, Cq;      // padded quadratic form of the Gaussian, times qscale
+    float fl;              // phot='flux' factor (1 otherwise)
+    int half;              // footprint half-width
+};
+
+// Source position (fp64: cos/sin by angle addition from the tables), closed-form Jacobian (fp32), padded
+// quadratic form and footprint size of grid point (gx, gy) = tile point (tx, ly).
+__device__ __forceinline__ PolarPix polar_pixel(const JacFastParams &P, const PolarTables &T, int GX0, int GY0,
+                                                int tx, int ly, int gx, int gy)
+{
+    PolarPix o;
+    const bool lg = P.lg != 0;
+    const int GW = P.grid_w, GH = P.grid_h;
+    const double gxd = (double)gx, gyd = (double)gy;
+    const float sgn = P.ccw ? 1.0f : -1.0f;
+    const double2 ta = T.ta[tx + 1];
+    const double2 tb = T.tb[ly + 1];
+    double c = ta.x * tb.x - ta.y * tb.y, s = ta.y * tb.x + ta.x * tb.y;
+    double r = lg ? T.ea[tx + 1] * T.eb[ly + 1] : fma(P.pa[2], gxd, fma(P.pa[3], gyd, P.pa[5]));
+    const double x1 = fma(c, r, P.ox), y1 = fma(P.ccw ? s : -s, r, P.oy);
+    o.px = x1; o.py = y1;
+    if (P.has_a2) {
+        o.px = fma(P.a2[0], x1, fma(P.a2[1], y1, P.a2[4]));
+        o.py = fma(P.a2[2], x1, fma(P.a2[3], y1, P.a2[5]));
+    }
+    // ---- closed-form Jacobian, fp32.  Grid-edge pixels copy their inner neighbour
+    // (helpers.pyx:1244-1247): there (only) cos, sin and radius are re-derived at the clamped point.
+    // Inputs are rounded from the fp64 values of the pixel, which do not depend on how the grid
+    // is tiled: row-block shards reproduce the full frame.
+    const int jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
+    const int jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
+    if (jx != gx || jy != gy) {
+        const double2 ca = T.ta[jx - (GX0 - 1)], cb = T.tb[jy - (GY0 - 1)];
+        c = ca.x * cb.x - ca.y * cb.y;
+        s = ca.y * cb.x + ca.x * cb.y;
+        r = lg ? T.ea[jx - (GX0 - 1)] * T.eb[jy - (GY0 - 1)]
+               : fma(P.pa[2], (double)jx, fma(P.pa[3], (double)jy, P.pa[5]));
+    }
+    const float cf = (float)c, sf = (float)s, rf = (float)r;
+    const float drX = lg ? rf * P.p2f : P.p2f, drY = lg ? rf * P.p3f : P.p3f;
+    const float rs = rf * sf, rc = rf * cf;
+    // x1 = r cos + ox, y1 = sgn r sin + oy
+    float j00 = fmaf(cf, drX, -rs * P.tXf), j01 = fmaf(cf, drY, -rs * P.tYf);
+    float j10 = sgn * fmaf(sf, drX, rc * P.tXf), j11 = sgn * fmaf(sf, drY, rc * P.tYf);
+    if (P.has_a2) {
+        const float k00 = P.a2f[0] * j00 + P.a2f[1] * j10, k01 = P.a2f[0] * j01 + P.a2f[1] * j11;
+        const float k10 = P.a2f[2] * j00 + P.a2f[3] * j10, k11 = P.a2f[2] * j01 + P.a2f[3] * j11;
+        j00 = k00; j01 = k01; j10 = k10; j11 = k11;
+    }
+    // ---- padded quadratic form and footprint size ----
+    float q00, q01, q11, inv_smin;
+    gaussian_quadratic(j00, j01, j10, j11, P.padval, P.half_pow, P.m2_over_pow, q00, q01, q11, inv_smin);
+    float ratio = P.ob * inv_smin;
+    if (fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) ratio = exact_half_ratio(P, j00, j01, j10, j11);
+    int half = (ratio < 1.0e9f) ? __float2int_ru(ratio) : 1000000000;
+    o.half = min(half, P.max_half);
+    o.Aq = q00 * P.qscale; o.Bq = q01 * P.qscale; o.Cq = q11 * P.qscale;
+    o.fl = P.flux ? fabsf(j00 * j11 - j01 * j10) : 1.0f;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------
 // analytic polar kernel
 // ---------------------------------------------------------------------------------------------
-// Two phases per thread, joined by a 9-word record per pixel in shared memory (written and read by
-// the same thread: no barrier):
-//   A  source position, closed-form Jacobian, padded quadratic form, footprint size, recurrence set-up
-//   B  the tap loops
-// In one loop the two halves compete for 64 registers: ncu showed ~25 % of the L1 wavefronts of the
-// one-phase form to be spill traffic and every launch constant re-fetched per pixel.  Apart, phase A
-// keeps its constants in registers and phase B holds nothing but tap state.
+// One thread = 4 pixels of a 32 x 32 tile, 8 rows apart.  (A two-phase form -- prologue records of the 4
+// pixels parked in shared memory, then the tap loops -- was built and measured no faster; removed.)
 template <int TM>
 __global__ void __launch_bounds__(256, TFM_K2F_MINBLOCKS)
 k_jac_gauss_polar(const __grid_constant__ JacFastParams P)
 {
-    constexpr int TN = FT + 2;              // table entries: grid points G0-1 .. G0+FT (edge-copy clamp reach)
-    __shared__ double2 s_ta[TN], s_tb[TN];  // (cos, sin)(i tX), (cos, sin)(theta(X0, Y0) + j tY)
-    __shared__ double s_ea[TN], s_eb[TN];   // log-polar: exp(i a10), r0 exp(rho(X0, Y0) + j a11)
-#if TFM_K2F_TWOPHASE
-    __shared__ float4 s_r0[4][256];         // w0, r0, rb, cA
-    __shared__ float4 s_r1[4][256];         // cB, cC, res / flux factor, bits of off
-    __shared__ int2 s_r2[4][256];           // half | first_out << 8 (-1: row beyond the output), window row (tap mode 2)
-#endif
-
+    __shared__ PolarTables T;
     const int tid = threadIdx.x;
     const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
     const int GX0 = P.dst_x0 + (int)blockIdx.x * FT, GY0 = P.dst_y0 + (int)blockIdx.y * FT;
-    const double X0 = (double)(GX0 - 1), Y0d = (double)(GY0 - 1);
-    const bool lg = P.lg != 0;
-    if (tid < 2 * TN) {
-        // same formulas as polar_tables (tfm_chain.cuh)
-        const double tX = P.pa[0] * P.coeff, tY = P.pa[1] * P.coeff;
-        double s, c;
-        if (tid < TN) {
-            sincos((double)tid * tX, &s, &c);
-            s_ta[tid] = make_double2(c, s);
-            if (lg) s_ea[tid] = exp((double)tid * P.pa[2]);
-        } else {
-            const int j = tid - TN;
+    polar_fill_tables(P, T, GX0, GY0, tid);
+    __syncthreads();
+
+    int tx, ty;
+    patch_xy(P.lw, P.quads, tid, tx, ty);
+    const int X = blockIdx.x * FT + tx;
+    if (X >= P.dst_w) return;
+    const int Yt = blockIdx.y * FT + ty;
+    int state = 0;
+    const int gx = P.dst_x0 + X;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int ly = ty + 8 * j;
+        if (Yt + 8 * j >= P.dst_h) break;
+        const PolarPix q = polar_pixel(P, T, GX0, GY0, tx, ly, gx, P.dst_y0 + Yt + 8 * j);
+        const TapRec rec = gauss_setup<TM>(P, src_base, q.px, q.py, q.Aq, q.Bq, q.Cq, q.half, state);
+        float res = rec.res * q.fl;
+        if (rec.off >= 0)
+            res = q.fl * gauss_run<0, TM>(P, src_base, rec.off, rec.ys, rec.half, rec.w0, rec.r0, rec.rb,
+                                          fast_ex2(-2.0f * q.Aq), fast_ex2(-2.0f * q.Bq), fast_ex2(-2.0f * q.Cq));
+        P.dst[(long long)blockIdx.z * P.dst_plane + (long long)(Yt + 8 * j) * P.dst_pe + X] = res;
+    }
+    if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// analytic polar kernel, radius constant along output rows
+// ---------------------------------------------------------------------------------------------
+// ncu source view of k_jac_gauss_polar at 8192^2 (profiles/r2_kernels.md): 478 instructions per pixel, 261 of
+// them BEFORE the first tap -- Jacobian, eigenvalues of J J^T, padding (8 MUFU), footprint size, and the launch
+// constants all of that re-reads per pixel.  In the common unwrap (no radius term in X: p2 = 0, no trailing
+// affine map) the radius depends on the output row only, and J = B(theta) J0(row) with B orthogonal, so
+//     Q = f(J J^T) = B f(J0 J0^T) B^T:
+// eigenvalues, padding, footprint size, flux factor and the fitness of the recurrence are per-ROW numbers
+// (one table entry per tile row, 34 evaluations per tile instead of 1024) and a pixel only rotates the row's
+// quadratic form by its angle: 11 fp32 operations.  Sines are stored with the sense of rotation folded in
+// (sin(sgn theta) = sgn sin(theta)), which also removes the sign handling from the source position.
+struct PolarRowTables {
+    double2 ta[PTN], tb[PTN];               // (cos, sgn sin)(i tX), (cos, sgn sin)(theta(X0, row))
+    double r[PTN];                          // radius of the row
+    float4 q[PTN];                          // f(J0 J0^T) x qscale: m00, sgn m01, m11; |det J0| (flux)
+    int half[PTN];                          // footprint half-width; -1 - half: the recurrence is unfit for the row
+};
+
+template <int TM>
+__global__ void __launch_bounds__(256, TFM_K2F_MINBLOCKS)
+k_jac_gauss_polar_rows(const __grid_constant__ JacFastParams P)
+{
+    __shared__ PolarRowTables T;
+    const int tid = threadIdx.x;
+    const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
+    const int GX0 = P.dst_x0 + (int)blockIdx.x * FT, GY0 = P.dst_y0 + (int)blockIdx.y * FT;
+    if (tid < 3 * PTN) {
+        // same formulas as polar_fill_tables / polar_tables (tfm_chain.cuh): the source position of a pixel is
+        // bit-identical with the other kernels'
+        const double X0 = (double)(GX0 - 1), Y0d = (double)(GY0 - 1);
+        const double sg = P.ccw ? 1.0 : -1.0;
+        double sn, cs;
+        if (tid < PTN) {
+            sincos((double)tid * (P.pa[0] * P.coeff), &sn, &cs);
+            T.ta[tid] = make_double2(cs, sg * sn);
+        } else if (tid < 2 * PTN) {
+            const int j = tid - PTN;
             const double t0 = fma(P.pa[0], X0, fma(P.pa[1], Y0d, P.pa[4])) * P.coeff;
-            sincos(fma((double)j, tY, t0), &s, &c);
-            s_tb[j] = make_double2(c, s);
-            if (lg) {
-                const double rho0 = fma(P.pa[2], X0, fma(P.pa[3], Y0d, P.pa[5]));
-                s_eb[j] = P.r0 * exp(fma((double)j, P.pa[3], rho0));
-            }
+            sincos(fma((double)j, P.pa[1] * P.coeff, t0), &sn, &cs);
+            T.tb[j] = make_double2(cs, sg * sn);
+        } else {
+            const int j = tid - 2 * PTN;
+            const double gyd = (double)(GY0 - 1 + j);
+            const double r = P.lg ? P.r0 * exp(fma((double)j, P.pa[3], fma(P.pa[3], Y0d, P.pa[5])))
+                                  : fma(P.pa[3], gyd, P.pa[5]);
+            T.r[j] = r;
+            // J0 = [[0, drY], [r tX, r tY]]: the Jacobian at angle 0 without the sense of rotation
+            const float rf = (float)r;
+            const float drY = P.lg ? rf * P.p3f : P.p3f;
+            const float j10 = rf * P.tXf, j11 = rf * P.tYf;
+            float q00, q01, q11, inv_smin;
+            gaussian_quadratic(0.0f, drY, j10, j11, P.padval, P.half_pow, P.m2_over_pow, q00, q01, q11, inv_smin);
+            float ratio = P.ob * inv_smin;
+            if (fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) ratio = exact_half_ratio(P, 0.0f, drY, j10, j11);
+            int half = (ratio < 1.0e9f) ? __float2int_ru(ratio) : 1000000000;
+            half = min(half, P.max_half);
+            const float m00 = q00 * P.qscale, m01 = q01 * P.qscale, m11 = q11 * P.qscale;
+            // exponents of the recurrence over the window, whatever the angle: Aq + Cq is the trace,
+            // |Bq| at most the radius of the form's circle
+            const float hd = 0.5f * (m00 - m11), hf1 = (float)(half + 1);
+            const float bmax = sqrtf(hd * hd + m01 * m01);
+            const bool fit = half >= 1 && half <= 6 && (m00 + m11 + 2.0f * bmax) * (hf1 * hf1) < 120.0f;   // weights stay normal fp32
+            T.q[j] = make_float4(m00, P.ccw ? m01 : -m01, m11, P.flux ? fabsf(drY * j10) : 1.0f);
+            T.half[j] = fit ? half : -1 - half;
         }
     }
     __syncthreads();
@@ -587,101 +769,44 @@ k_jac_gauss_polar(const __grid_constant__ JacFastParams P)
     if (X >= P.dst_w) return;
     const int Yt = blockIdx.y * FT + ty;
     int state = 0;
-
-    // ------------------------------- phase A -------------------------------
-    {
-        const int gx = P.dst_x0 + X;
-        const int GW = P.grid_w, GH = P.grid_h;
-        const double2 ta = s_ta[tx + 1];
-        const double gxd = (double)gx;
-        double gyd = (double)(P.dst_y0 + Yt);
-        const float sgn = P.ccw ? 1.0f : -1.0f;
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j, gyd += 8.0) {
-            const int ly = ty + 8 * j;
-#if TFM_K2F_TWOPHASE
-            if (Yt + 8 * j >= P.dst_h) { s_r2[j][tid] = make_int2(-1, 0); continue; }
-#else
-            if (Yt + 8 * j >= P.dst_h) break;
-#endif
-            const int gy = P.dst_y0 + Yt + 8 * j;
-            // ---- source position (fp64): cos/sin by angle addition from the tables ----
-            const double2 tb = s_tb[ly + 1];
-            double c = ta.x * tb.x - ta.y * tb.y, s = ta.y * tb.x + ta.x * tb.y;
-            double r = lg ? s_ea[tx + 1] * s_eb[ly + 1] : fma(P.pa[2], gxd, fma(P.pa[3], gyd, P.pa[5]));
-            const double x1 = fma(c, r, P.ox), y1 = fma(P.ccw ? s : -s, r, P.oy);
-            double px = x1, py = y1;
-            if (P.has_a2) {
-                px = fma(P.a2[0], x1, fma(P.a2[1], y1, P.a2[4]));
-                py = fma(P.a2[2], x1, fma(P.a2[3], y1, P.a2[5]));
-            }
-            // ---- closed-form Jacobian, fp32.  Grid-edge pixels copy their inner neighbour
-            // (helpers.pyx:1244-1247): there (only) cos, sin and radius are re-derived at the clamped point.
-            // Inputs are rounded from the fp64 values of the pixel, which do not depend on how the grid
-            // is tiled: row-block shards reproduce the full frame.
-            const int jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
-            const int jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
-            if (jx != gx || jy != gy) {
-                const double2 ca = s_ta[jx - (GX0 - 1)], cb = s_tb[jy - (GY0 - 1)];
-                c = ca.x * cb.x - ca.y * cb.y;
-                s = ca.y * cb.x + ca.x * cb.y;
-                r = lg ? s_ea[jx - (GX0 - 1)] * s_eb[jy - (GY0 - 1)]
-                       : fma(P.pa[2], (double)jx, fma(P.pa[3], (double)jy, P.pa[5]));
-            }
-            const float cf = (float)c, sf = (float)s, rf = (float)r;
-            const float drX = lg ? rf * P.p2f : P.p2f, drY = lg ? rf * P.p3f : P.p3f;
-            const float rs = rf * sf, rc = rf * cf;
-            // x1 = r cos + ox, y1 = sgn r sin + oy
-            float j00 = fmaf(cf, drX, -rs * P.tXf), j01 = fmaf(cf, drY, -rs * P.tYf);
-            float j10 = sgn * fmaf(sf, drX, rc * P.tXf), j11 = sgn * fmaf(sf, drY, rc * P.tYf);
-            if (P.has_a2) {
-                const float k00 = P.a2f[0] * j00 + P.a2f[1] * j10, k01 = P.a2f[0] * j01 + P.a2f[1] * j11;
-                const float k10 = P.a2f[2] * j00 + P.a2f[3] * j10, k11 = P.a2f[2] * j01 + P.a2f[3] * j11;
-                j00 = k00; j01 = k01; j10 = k10; j11 = k11;
-            }
-            // ---- padded quadratic form and footprint size ----
-            float q00, q01, q11, inv_smin;
-            gaussian_quadratic(j00, j01, j10, j11, P.padval, P.half_pow, P.m2_over_pow, q00, q01, q11, inv_smin);
-            float ratio = P.ob * inv_smin;
-            if (fabsf(ratio - rintf(ratio)) < 4e-5f * ratio) ratio = exact_half_ratio(P, j00, j01, j10, j11);
-            int half = (ratio < 1.0e9f) ? __float2int_ru(ratio) : 1000000000;
-            half = min(half, P.max_half);
-            const float Aq = q00 * P.qscale, Bq = q01 * P.qscale, Cq = q11 * P.qscale;
-            const TapRec rec = gauss_setup<TM>(P, src_base, px, py, Aq, Bq, Cq, half, state);
-            const float fl = P.flux ? fabsf(j00 * j11 - j01 * j10) : 1.0f;
-#if TFM_K2F_TWOPHASE
-            s_r0[j][tid] = make_float4(rec.w0, rec.r0, rec.rb, fast_ex2(-2.0f * Aq));
-            s_r1[j][tid] = make_float4(fast_ex2(-2.0f * Bq), fast_ex2(-2.0f * Cq), rec.off >= 0 ? fl : rec.res * fl,
-                                       __int_as_float(rec.off));
-            s_r2[j][tid] = make_int2(rec.half, rec.ys);
-#else
-            float res = rec.res * fl;
-            if (rec.off >= 0)
-                res = fl * gauss_run<0, TM>(P, src_base, rec.off, rec.ys, rec.half, rec.w0, rec.r0, rec.rb,
-                                            fast_ex2(-2.0f * Aq), fast_ex2(-2.0f * Bq), fast_ex2(-2.0f * Cq));
-            P.dst[(long long)blockIdx.z * P.dst_plane + (long long)(Yt + 8 * j) * P.dst_pe + X] = res;
-#endif
-        }
-    }
-
-#if TFM_K2F_TWOPHASE
-    // ------------------------------- phase B -------------------------------
+    const int gx = P.dst_x0 + X;
+    const int GW = P.grid_w, GH = P.grid_h;
+    const double2 ta = T.ta[tx + 1];
+    const int jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
     float *drow = P.dst + (long long)blockIdx.z * P.dst_plane + (long long)Yt * P.dst_pe + X;
 #pragma unroll 1
     for (int j = 0; j < 4; ++j, drow += 8 * P.dst_pe) {
-        const int2 hy = s_r2[j][tid];
-        const int hf = hy.x;
-        if (hf < 0) break;                                       // rows beyond the output
-        const float4 b = s_r1[j][tid];
-        const int off = __float_as_int(b.w);
-        float res = b.z;
-        if (off >= 0) {
-            const float4 a = s_r0[j][tid];
-            res *= gauss_run<0, TM>(P, src_base, off, hy.y, hf, a.x, a.y, a.z, a.w, b.x, b.y);
+        const int ly = ty + 8 * j;
+        if (Yt + 8 * j >= P.dst_h) break;
+        const int gy = P.dst_y0 + Yt + 8 * j;
+        const double2 tb = T.tb[ly + 1];
+        double c = ta.x * tb.x - ta.y * tb.y, s = ta.y * tb.x + ta.x * tb.y;
+        const double r = T.r[ly + 1];
+        const double px = fma(c, r, P.ox), py = fma(s, r, P.oy);
+        // grid-edge pixels copy the Jacobian of their inner neighbour (helpers.pyx:1244-1247)
+        const int jy = gy < 1 ? 1 : (gy > GH - 2 ? GH - 2 : gy);
+        int jt = ly + 1;
+        if (jx != gx || jy != gy) {
+            jt = jy - (GY0 - 1);
+            const double2 ca = T.ta[jx - (GX0 - 1)], cb = T.tb[jt];
+            c = ca.x * cb.x - ca.y * cb.y;
+            s = ca.y * cb.x + ca.x * cb.y;
         }
-        *drow = res;
+        const float4 m = T.q[jt];
+        const int ht = T.half[jt];
+        const int half = ht < 0 ? -1 - ht : ht;
+        const float cf = (float)c, sf = (float)s;
+        const float c2 = cf * cf, s2 = sf * sf, cs2 = 2.0f * cf * sf;
+        const float Aq = fmaf(c2, m.x, fmaf(s2, m.z, -cs2 * m.y));
+        const float Cq = fmaf(s2, m.x, fmaf(c2, m.z, cs2 * m.y));
+        const float Bq = fmaf(0.5f * cs2, m.x - m.z, (c2 - s2) * m.y);
+        const TapRec rec = gauss_setup<TM>(P, src_base, px, py, Aq, Bq, Cq, half, state, ht >= 0 ? 1 : 0);
+        float res = rec.res;
+        if (rec.off >= 0)
+            res = gauss_run<0, TM>(P, src_base, rec.off, rec.ys, rec.half, rec.w0, rec.r0, rec.rb,
+                                   fast_ex2(-2.0f * Aq), fast_ex2(-2.0f * Bq), fast_ex2(-2.0f * Cq));
+        *drow = res * m.w;
     }
-#endif
     if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
 }
 
@@ -871,13 +996,24 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
         if (step_x > 2.0 * step_y) P.quads = 2;
     }
     if (a->tuning & 131072) P.quads = (P.lw <= 3) ? 2 : P.quads;
-    if (tm == 2) k_jac_gauss_polar<2><<<grid, 256, 0, st>>>(P);
-    else if (tm == 1) k_jac_gauss_polar<1><<<grid, 256, 0, st>>>(P);
-    else k_jac_gauss_polar<0><<<grid, 256, 0, st>>>(P);
+    // radius constant along output rows (no radius term in X, no trailing affine map): per-row spectral tables
+    const bool rows = op.p[2] == 0.0 && !P.has_a2 && !(a->tuning & 262144);
+    if (rows) {
+        if (tm == 2) k_jac_gauss_polar_rows<2><<<grid, 256, 0, st>>>(P);
+        else if (tm == 1) k_jac_gauss_polar_rows<1><<<grid, 256, 0, st>>>(P);
+        else k_jac_gauss_polar_rows<0><<<grid, 256, 0, st>>>(P);
+    } else {
+        if (tm == 2) k_jac_gauss_polar<2><<<grid, 256, 0, st>>>(P);
+        else if (tm == 1) k_jac_gauss_polar<1><<<grid, 256, 0, st>>>(P);
+        else k_jac_gauss_polar<0><<<grid, 256, 0, st>>>(P);
+    }
     count_launch();
     if (tm == 2) texture_used(tex_slot, st);
-    set_last_kernel(tm == 2 ? "k_jacobian<fast32,analytic-polar,tex>"
-                            : (tm == 1 ? "k_jacobian<fast32,analytic-polar,ld64>" : "k_jacobian<fast32,analytic-polar,ld32>"));
+    static const char *const names[2][3] = {
+        {"k_jacobian<fast32,analytic-polar,ld32>", "k_jacobian<fast32,analytic-polar,ld64>", "k_jacobian<fast32,analytic-polar,tex>"},
+        {"k_jacobian<fast32,analytic-polar-rows,ld32>", "k_jacobian<fast32,analytic-polar-rows,ld64>",
+         "k_jacobian<fast32,analytic-polar-rows,tex>"}};
+    set_last_kernel(names[rows ? 1 : 0][tm]);
     *rc = cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
     return 1;
 }
