@@ -214,9 +214,11 @@ def test_jacobian_fp32_polar_8192(tfm, oracle):
     want = np.stack([oracle.resample_jacobian(otr, src64, method='g', rows=(y, y + 1), max_reg=cap)[0] for y in rows])
     knife = (np.arange(n) % (n // 8)) == 0
     ref = None
-    # default = per-row spectral tables (the radius of this unwrap is constant along output rows); tuning bit
-    # 262144 forces the per-pixel closed form of the general polar op
-    for tuning, name in ((0, "k_jacobian<fast32,analytic-polar-rows,tex>"),
+    # default = per-row spectral tables (the radius of this unwrap is constant along output rows) with two output
+    # rows sharing each set of texture fetches; tuning bit 524288 = one pixel per set of fetches, 262144 = the
+    # per-pixel closed form of the general polar op
+    for tuning, name in ((0, "k_jacobian<fast32,analytic-polar-rows,tex,row-pairs>"),
+                         (524288, "k_jacobian<fast32,analytic-polar-rows,tex>"),
                          (32768, "k_jacobian<fast32,analytic-polar-rows,ld64>"),
                          (4096, "k_jacobian<fast32,analytic-polar-rows,ld32>"),
                          (262144, "k_jacobian<fast32,analytic-polar,tex>"),

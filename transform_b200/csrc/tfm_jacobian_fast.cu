@@ -713,14 +713,8 @@ struct PolarRowTables {
     int half[PTN];                          // footprint half-width; -1 - half: the recurrence is unfit for the row
 };
 
-template <int TM>
-__global__ void __launch_bounds__(256, TFM_K2F_MINBLOCKS)
-k_jac_gauss_polar_rows(const __grid_constant__ JacFastParams P)
+__device__ __forceinline__ void polar_fill_row_tables(const JacFastParams &P, PolarRowTables &T, int GX0, int GY0, int tid)
 {
-    __shared__ PolarRowTables T;
-    const int tid = threadIdx.x;
-    const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
-    const int GX0 = P.dst_x0 + (int)blockIdx.x * FT, GY0 = P.dst_y0 + (int)blockIdx.y * FT;
     if (tid < 3 * PTN) {
         // same formulas as polar_fill_tables / polar_tables (tfm_chain.cuh): the source position of a pixel is
         // bit-identical with the other kernels'
@@ -761,6 +755,17 @@ k_jac_gauss_polar_rows(const __grid_constant__ JacFastParams P)
             T.half[j] = fit ? half : -1 - half;
         }
     }
+}
+
+template <int TM>
+__global__ void __launch_bounds__(256, TFM_K2F_MINBLOCKS)
+k_jac_gauss_polar_rows(const __grid_constant__ JacFastParams P)
+{
+    __shared__ PolarRowTables T;
+    const int tid = threadIdx.x;
+    const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
+    const int GX0 = P.dst_x0 + (int)blockIdx.x * FT, GY0 = P.dst_y0 + (int)blockIdx.y * FT;
+    polar_fill_row_tables(P, T, GX0, GY0, tid);
     __syncthreads();
 
     int tx, ty;
@@ -806,6 +811,240 @@ k_jac_gauss_polar_rows(const __grid_constant__ JacFastParams P)
             res = gauss_run<0, TM>(P, src_base, rec.off, rec.ys, rec.half, rec.w0, rec.r0, rec.rb,
                                    fast_ex2(-2.0f * Aq), fast_ex2(-2.0f * Bq), fast_ex2(-2.0f * Cq));
         *drow = res * m.w;
+    }
+    if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// analytic polar kernel, per-row tables, two output rows per set of texture fetches
+// ---------------------------------------------------------------------------------------------
+// ncu on k_jac_gauss_polar_rows (profiles/r2_kernels.md): 339 instructions per pixel at 49 % issue
+// utilisation, texture write-back 92 % busy -- a gather returns 512 bytes per warp and the path moves 32 bytes
+// per clock, so the fetches ARE the run time.  Most texels are fetched twice: where one output row maps less
+// than a source pixel away from the next (the radial direction of an unwrap), the (2 HALF + 1)^2 windows of the
+// output pixels (X, Y) and (X, Y + 1) start at most one texel apart in each axis, so BOTH lie inside the
+// (2 HALF + 2)^2 texels that (HALF + 1)^2 gathers return anyway: 28-40 % fewer texels written back per pixel.
+// The shared window starts at the smaller of the two window origins per axis.  A pixel whose own window
+// starts one column (row) later runs its recurrence from the shared origin all the same and leaves the first
+// column (row) out; one whose window starts on the shared origin leaves the last out.  Left-out taps are
+// selected away value AND weight: a NaN outside a pixel's own square must not reach it (the reference's window
+// is the square, helpers.pyx:1678-1679).
+// Pairs are the GLOBAL grid rows (2m, 2m + 1): the tile grid starts on the even row at or below the row block's
+// first, and a pixel whose partner lies outside the block still computes the partner's window -- every pixel's
+// arithmetic depends on its own global pair only, so any split into row blocks reproduces the full frame bit
+// for bit.  A pair whose windows do not fit one shared window (different footprint sizes, one of the two not
+// served by the recurrence) takes the one-pixel form.
+struct PairPix {
+    TexRows S;
+    float2 val2, wgt2;
+    bool mx, my;           // own window starts one column / row after the shared origin
+};
+
+template <int HALF>
+__device__ __forceinline__ void pair_rows(const float4 (&g)[HALF + 1], PairPix &A, const bool use_a, const bool use_b)
+{
+    constexpr int NP = HALF + 1;
+    TexRows &S = A.S;
+    const float2 CA4 = bc2(S.cA4), CB2 = bc2(S.cB2), CC = bc2(S.cC);
+    float2 Wa = S.W, Ra = S.R;
+    float2 Wb = __fmul2_rn(S.W, S.RB), Rb = __fmul2_rn(S.R, CB2);
+    {
+        const float2 RB1 = __fmul2_rn(S.RB, CC);
+        S.W = __fmul2_rn(Wb, RB1);
+        S.R = __fmul2_rn(Rb, CB2);
+        S.RB = __fmul2_rn(RB1, CC);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        // gather order: x = (c, r+1), y = (c+1, r+1), z = (c+1, r), w = (c, r)
+        float2 va = make_float2(g[i].w, g[i].z), vb = make_float2(g[i].x, g[i].y);
+        float2 wa = Wa, wb = Wb;
+        if (i == 0) {                                        // column 0 belongs to the pixel only if its window starts here
+            va.x = A.mx ? 0.0f : va.x; wa.x = A.mx ? 0.0f : wa.x;
+            vb.x = A.mx ? 0.0f : vb.x; wb.x = A.mx ? 0.0f : wb.x;
+        }
+        if (i == NP - 1) {                                   // column 2 HALF + 1 only if it starts one later
+            va.y = A.mx ? va.y : 0.0f; wa.y = A.mx ? wa.y : 0.0f;
+            vb.y = A.mx ? vb.y : 0.0f; wb.y = A.mx ? wb.y : 0.0f;
+        }
+        if (use_a) { A.val2 = __ffma2_rn(va, wa, A.val2); A.wgt2 = __fadd2_rn(A.wgt2, wa); }
+        if (use_b) { A.val2 = __ffma2_rn(vb, wb, A.val2); A.wgt2 = __fadd2_rn(A.wgt2, wb); }
+        if (i + 1 < NP) {
+            Wa = __fmul2_rn(Wa, Ra); Wb = __fmul2_rn(Wb, Rb);
+            if (i + 2 < NP) { Ra = __fmul2_rn(Ra, CA4); Rb = __fmul2_rn(Rb, CA4); }
+        }
+    }
+}
+
+template <int HALF>
+__device__ __forceinline__ void pair_taps_tex(cudaTextureObject_t tex, int ux, int uy, PairPix &A, PairPix &B)
+{
+    constexpr int NP = HALF + 1;
+    const float fx0 = (float)(ux + 1);
+    float fy = (float)(uy + 1);
+    if constexpr (HALF <= 1) {
+        float4 g[NP][NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+                g[j][i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy + (float)(2 * j), 0);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            pair_rows<HALF>(g[j], A, j == 0 ? !A.my : true, j == NP - 1 ? A.my : true);
+            pair_rows<HALF>(g[j], B, j == 0 ? !B.my : true, j == NP - 1 ? B.my : true);
+        }
+    } else {
+        float4 g[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
+        pair_rows<HALF>(g, A, !A.my, true);
+        pair_rows<HALF>(g, B, !B.my, true);
+#pragma unroll 1
+        for (int j = 1; j < NP - 1; ++j) {
+            fy += 2.0f;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
+            pair_rows<HALF>(g, A, true, true);
+            pair_rows<HALF>(g, B, true, true);
+        }
+        fy += 2.0f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
+        pair_rows<HALF>(g, A, true, A.my);
+        pair_rows<HALF>(g, B, true, B.my);
+    }
+}
+
+// recurrence of one pixel of a pair, started at the shared window's origin (dx, dy in {0, 1} before its own)
+__device__ __forceinline__ void pair_begin(PairPix &A, float Aq, float Bq, float Cq, float xf, float yf, int half, int dx, int dy)
+{
+    const float a0 = xf - (float)(half + dx), b0 = yf - (float)(half + dy);
+    const float w0 = fast_ex2(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
+    const float r0 = fast_ex2(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
+    const float rb = fast_ex2(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
+    const float cA = fast_ex2(-2.0f * Aq), cB = fast_ex2(-2.0f * Bq);
+    const float cA2 = cA * cA, r02 = r0 * r0;
+    A.S.W = __fmul2_rn(bc2(w0), make_float2(1.0f, r0));
+    A.S.R = __fmul2_rn(bc2(r02), make_float2(cA, cA * cA2));
+    A.S.RB = __fmul2_rn(bc2(rb), make_float2(1.0f, cB));
+    A.S.cA4 = cA2 * cA2; A.S.cB2 = cB * cB; A.S.cC = fast_ex2(-2.0f * Cq);
+    A.val2 = make_float2(0.0f, 0.0f); A.wgt2 = make_float2(0.0f, 0.0f);
+    A.mx = dx != 0; A.my = dy != 0;
+}
+
+__device__ __forceinline__ float pair_end(const PairPix &A)
+{
+    const float val = A.val2.x + A.val2.y, wgt = A.wgt2.x + A.wgt2.y;
+    return (wgt > 0.0f) ? val * fast_rcp(wgt) : 0.0f;
+}
+
+// one pixel of a pair on its own (its partner's window does not fit): the one-pixel texture form
+__device__ __noinline__ float pair_single(const JacFastParams &P, float Aq, float Bq, float Cq, float xf, float yf, int half,
+                                          int xs, int ys)
+{
+    const float a0 = xf - (float)half, b0 = yf - (float)half;
+    const float w0 = fast_ex2(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
+    const float r0 = fast_ex2(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
+    const float rb = fast_ex2(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
+    float val = 0.0f, wgt = 0.0f;
+    gauss_taps_any<2>(P.tex, xs, ys, half, nullptr, 0, false, w0, r0, rb, fast_ex2(-2.0f * Aq), fast_ex2(-2.0f * Bq),
+                      fast_ex2(-2.0f * Cq), val, wgt);
+    return (wgt > 0.0f) ? val * fast_rcp(wgt) : 0.0f;
+}
+
+#ifndef TFM_K2P_MINBLOCKS
+#define TFM_K2P_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, TFM_K2P_MINBLOCKS)
+k_jac_gauss_polar_rows_pair(const __grid_constant__ JacFastParams P)
+{
+    __shared__ PolarRowTables T;
+    const int tid = threadIdx.x;
+    const float *const src_base = P.src + (long long)blockIdx.z * P.src_plane;
+    const int ybase = P.dst_y0 & ~1;                         // global row of the tile grid's first row (even)
+    const int GX0 = P.dst_x0 + (int)blockIdx.x * FT, GY0 = ybase + (int)blockIdx.y * FT;
+    polar_fill_row_tables(P, T, GX0, GY0, tid);
+    __syncthreads();
+
+    const int lane = tid & 31, wrp = tid >> 5;
+    int lx, pr;                                              // column and pair row inside the 8 x 8 patch
+    if (P.quads == 2) { pr = lane & 3; lx = lane >> 2; }     // lanes 4k .. 4k+3: 4 pairs of one column
+    else { lx = lane & 7; pr = lane >> 3; }
+    const int GW = P.grid_w, GH = P.grid_h;
+    int state = 0;
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        const int patch = wrp + 8 * k;                       // 4 x 4 patches of 8 x 8 pixels
+        const int tx = ((patch & 3) << 3) + lx, ly = ((patch >> 2) << 3) + 2 * pr;
+        const int X = blockIdx.x * FT + tx;
+        const int gx = P.dst_x0 + X, gy = GY0 + ly;          // global grid point of the pair's first pixel
+        const int Y = gy - P.dst_y0;                         // its row inside the block (-1: the partner of row 0)
+        if (X >= P.dst_w || Y >= P.dst_h) continue;
+        const double2 ta = T.ta[tx + 1];
+        const int jx = gx < 1 ? 1 : (gx > GW - 2 ? GW - 2 : gx);
+        double pxy[2][2];
+        float Q[2][3], fl[2];
+        int hf[2], fit[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double2 tb = T.tb[ly + e + 1];
+            double c = ta.x * tb.x - ta.y * tb.y, s = ta.y * tb.x + ta.x * tb.y;
+            const double r = T.r[ly + e + 1];
+            pxy[e][0] = fma(c, r, P.ox); pxy[e][1] = fma(s, r, P.oy);
+            const int gye = gy + e;
+            const int jy = gye < 1 ? 1 : (gye > GH - 2 ? GH - 2 : gye);
+            int jt = ly + e + 1;
+            if (jx != gx || jy != gye) {
+                jt = jy - (GY0 - 1);
+                const double2 ca = T.ta[jx - (GX0 - 1)], cb = T.tb[jt];
+                c = ca.x * cb.x - ca.y * cb.y;
+                s = ca.y * cb.x + ca.x * cb.y;
+            }
+            const float4 m = T.q[jt];
+            const int ht = T.half[jt];
+            hf[e] = ht < 0 ? -1 - ht : ht;
+            fit[e] = ht >= 0 ? 1 : 0;
+            const float cf = (float)c, sf = (float)s;
+            const float c2 = cf * cf, s2 = sf * sf, cs2 = 2.0f * cf * sf;
+            Q[e][0] = fmaf(c2, m.x, fmaf(s2, m.z, -cs2 * m.y));
+            Q[e][2] = fmaf(s2, m.x, fmaf(c2, m.z, cs2 * m.y));
+            Q[e][1] = fmaf(0.5f * cs2, m.x - m.z, (c2 - s2) * m.y);
+            fl[e] = m.w;
+        }
+        const bool in_a = Y >= 0, in_b = Y + 1 < P.dst_h;
+        int xia, yia, xib, yib, sta = 0, stb = 0;
+        float xfa, yfa, xfb, yfb, resa, resb;
+        const int ka = gauss_classify<2>(P, src_base, pxy[0][0], pxy[0][1], Q[0][0], Q[0][1], Q[0][2], hf[0], xia, yia, xfa, yfa, resa, sta, fit[0]);
+        const int kb = gauss_classify<2>(P, src_base, pxy[1][0], pxy[1][1], Q[1][0], Q[1][1], Q[1][2], hf[1], xib, yib, xfb, yfb, resb, stb, fit[1]);
+        if (in_a) state |= sta;
+        if (in_b) state |= stb;
+        const int h = hf[0];
+        const int oxa = xia - h, oya = yia - h, oxb = xib - hf[1], oyb = yib - hf[1];
+        const int ux = min(oxa, oxb), uy = min(oya, oyb);
+        const bool joint = ka && kb && hf[1] == h && max(oxa, oxb) - ux <= 1 && max(oya, oyb) - uy <= 1;
+        if (joint) {
+            PairPix A, B;
+            pair_begin(A, Q[0][0], Q[0][1], Q[0][2], xfa, yfa, h, oxa - ux, oya - uy);
+            pair_begin(B, Q[1][0], Q[1][1], Q[1][2], xfb, yfb, h, oxb - ux, oyb - uy);
+            const int txs = ux - P.src_x0, tys = uy - P.src_y0;
+            switch (h) {
+            case 1: pair_taps_tex<1>(P.tex, txs, tys, A, B); break;
+            case 2: pair_taps_tex<2>(P.tex, txs, tys, A, B); break;
+            case 3: pair_taps_tex<3>(P.tex, txs, tys, A, B); break;
+            case 4: pair_taps_tex<4>(P.tex, txs, tys, A, B); break;
+            case 5: pair_taps_tex<5>(P.tex, txs, tys, A, B); break;
+            default: pair_taps_tex<6>(P.tex, txs, tys, A, B); break;
+            }
+            resa = pair_end(A);
+            resb = pair_end(B);
+        } else {
+            if (ka) resa = pair_single(P, Q[0][0], Q[0][1], Q[0][2], xfa, yfa, h, oxa - P.src_x0, oya - P.src_y0);
+            if (kb) resb = pair_single(P, Q[1][0], Q[1][1], Q[1][2], xfb, yfb, hf[1], oxb - P.src_x0, oyb - P.src_y0);
+        }
+        float *d = P.dst + (long long)blockIdx.z * P.dst_plane + (long long)Y * P.dst_pe + X;
+        if (in_a) d[0] = resa * fl[0];
+        if (in_b) d[P.dst_pe] = resb * fl[1];
     }
     if (state && P.status) atomicOr(P.status, (state & 2 ? 1 : 0) | (state & 4 ? 2 : 0));
 }
@@ -998,7 +1237,33 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
     if (a->tuning & 131072) P.quads = (P.lw <= 3) ? 2 : P.quads;
     // radius constant along output rows (no radius term in X, no trailing affine map): per-row spectral tables
     const bool rows = op.p[2] == 0.0 && !P.has_a2 && !(a->tuning & 262144);
-    if (rows) {
+    // two output rows per set of fetches: worth it where one output row maps at most about one source pixel from
+    // the next (bound from the closed form over the whole output GRID, not the block: row blocks of one job must
+    // all take the same kernel)
+    bool pairs = false;
+    if (rows && tm == 2 && !(a->tuning & 524288)) {
+        const bool lgp = P.lg != 0;
+        double vmax = 0.0;
+        for (int k = 0; k < 2; ++k) {
+            const double v = op.p[3] * (k ? (double)d.full_h : 0.0) + op.p[5];
+            vmax = fmax(vmax, lgp ? v : fabs(v));
+        }
+        const double rmax = lgp ? op.p[7] * exp(vmax) : vmax;
+        const double dsy = lgp ? rmax * hypot(op.p[1] * op.p[6], op.p[3]) : hypot(rmax * op.p[1] * op.p[6], op.p[3]);
+        pairs = dsy <= 1.05;
+    }
+    if (pairs) {
+        dim3 pgrid(grid.x, (unsigned)((P.dst_h + (P.dst_y0 & 1) + FT - 1) / FT), grid.z);
+        if (P.quads) {
+            // lanes 4k .. 4k+3: 4 pairs of one column (8 output rows) or of one row (4 output columns), whichever
+            // spans less of the source at the middle of the grid
+            const double rmid = P.lg ? 1.0 : fabs(op.p[3] * 0.5 * (double)d.full_h + op.p[5]);
+            const double ax = hypot(rmid * op.p[0] * op.p[6], op.p[2]), ay = hypot(rmid * op.p[1] * op.p[6], op.p[3]);
+            P.quads = (3.0 * ax > 7.0 * ay) ? 2 : 1;
+            if (a->tuning & 131072) P.quads = 3 - P.quads;
+        }
+        k_jac_gauss_polar_rows_pair<<<pgrid, 256, 0, st>>>(P);
+    } else if (rows) {
         if (tm == 2) k_jac_gauss_polar_rows<2><<<grid, 256, 0, st>>>(P);
         else if (tm == 1) k_jac_gauss_polar_rows<1><<<grid, 256, 0, st>>>(P);
         else k_jac_gauss_polar_rows<0><<<grid, 256, 0, st>>>(P);
@@ -1013,7 +1278,7 @@ int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc)
         {"k_jacobian<fast32,analytic-polar,ld32>", "k_jacobian<fast32,analytic-polar,ld64>", "k_jacobian<fast32,analytic-polar,tex>"},
         {"k_jacobian<fast32,analytic-polar-rows,ld32>", "k_jacobian<fast32,analytic-polar-rows,ld64>",
          "k_jacobian<fast32,analytic-polar-rows,tex>"}};
-    set_last_kernel(names[rows ? 1 : 0][tm]);
+    set_last_kernel(pairs ? "k_jacobian<fast32,analytic-polar-rows,tex,row-pairs>" : names[rows ? 1 : 0][tm]);
     *rc = cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
     return 1;
 }
