@@ -153,3 +153,39 @@ def test_tan_to_car_fast_path_tables(tfm, oracle, rot):
     want1 = oracle.resample(to_oracle(total), np.pad(frames[1], ((0, 0), (0, 5))), method='linear', shape=(n, m))
     assert_close_rel(single, want1, 2e-5, "texture path rot %g" % rot)
     assert np.count_nonzero(batch[0]) > 0.5 * n * m
+
+
+@pytest.mark.parametrize("kind", ["car-tan", "affine", "polar"])
+def test_texture_batch_kernel(tfm, oracle, kind):
+    """A batch of planes through the texture path runs k_resample_tex4_batch: a CTA computes the coordinates of
+    its tile once and serves up to 8 planes with them (16 texture objects per launch).  Every plane must equal
+    the one-launch-per-plane form (tuning bit 1048576) bit for bit -- same coordinates, same gathers -- for plane
+    counts that end inside a group of 8 and inside a launch of 16, on an output grid that is not a multiple of
+    the tile; and the oracle to the fp32 tolerance."""
+    import torch
+    from transform_b200 import _lib
+    n, m = 160, 384                                              # plane pitch 160 * 384 * 4 bytes: a multiple of 512
+    if kind == "car-tan":
+        tan = {'NAXIS': 2, 'NAXIS1': m, 'NAXIS2': n, 'CTYPE1': 'RA---TAN', 'CTYPE2': 'DEC--TAN', 'CUNIT1': 'deg',
+               'CUNIT2': 'deg', 'CRPIX1': m / 2 + 0.5, 'CRPIX2': n / 2 + 0.5, 'CRVAL1': 150.0, 'CRVAL2': 20.0,
+               'CDELT1': -0.02, 'CDELT2': 0.02}
+        tr = tfm.Composition([tfm.WCS(dict(tan, CTYPE1='RA---CAR', CTYPE2='DEC--CAR')).inverse(), tfm.WCS(tan)])
+        name = "k_resample_tex4_batch<car-tan>"
+    elif kind == "affine":
+        tr = tfm.Composition([tfm.Scale(1.3, dim=2), tfm.Rotation(30, unit='deg'), tfm.Offset([-m / 2.0, -n / 2.0])])
+        name = "k_resample_tex4_batch<affine>"
+    else:
+        tr = tfm.Composition([tfm.Scale([m / (2 * np.pi), 0.5]), tfm.Radial(origin=[m / 2.0 - 0.3, n / 2.0 + 0.2])])
+        name = "k_resample_tex4_batch"
+    g = torch.Generator(device="cuda").manual_seed(77)
+    for nz in (2, 8, 11, 17, 33):
+        frames = torch.rand((nz, n, m), device="cuda", dtype=torch.float32, generator=g)
+        shape = (nz, n - 3, m - 5)
+        got = tr.resample(frames, method='linear', precision='fp32', shape=shape)
+        assert _lib.last_kernel() == name, (_lib.last_kernel(), nz)
+        ref = tr.resample(frames, method='linear', precision='fp32', shape=shape, tuning=1048576)
+        assert _lib.last_kernel() == name.replace("_batch", ""), _lib.last_kernel()
+        assert torch.equal(got, ref), (kind, nz, float((got - ref).abs().max()))
+        for k in (0, nz - 1):
+            want = oracle.resample(to_oracle(tr), frames[k].cpu().numpy(), method='linear', shape=shape[1:])
+            assert_close_rel(got[k].cpu().numpy(), want, 2e-5, "%s plane %d of %d" % (kind, k, nz))

@@ -157,16 +157,25 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
 //   * floor/fraction in fixed point (floor_frac_fast).
 // WCSONLY: the chain is exactly one fused CAR -> TAN pair (a TAN -> CAR remap): an instantiation without
 // the chain interpreter -- 40 registers instead of 64, twice the resident warps for a latency-bound kernel
-template <class A, bool AFF, int SPH, bool WCSONLY = false>
-__global__ void __launch_bounds__(256, WCSONLY ? 6 : 1)
-k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex)
+// Batches of planes (frames resampled through the same chain): the coordinates, the per-tile tables and the
+// floor/fraction of a pixel do not depend on the plane, only the gather, the three lerps and the store do.
+// NZ > 1: a CTA serves its tile for up to NZ consecutive planes (texof(z) = texture object of plane z of the
+// launch, blockIdx.z selects the group of NZ) -- 73 instructions per pixel for the first plane of a TAN -> CAR
+// remap, ~15 for each further one.
+constexpr int TEX_BATCH_MAX = 16;          // texture objects per launch
+struct TexBatch { cudaTextureObject_t tex[TEX_BATCH_MAX]; int n; };
+
+template <class A, bool AFF, int SPH, bool WCSONLY, int NZ, class TexOf>
+__device__ __forceinline__ void resample_tex4_body(const ResampleParams &P, const TexOf texof, const int nz_total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = lane & 7;
     const int py = (warp << 2) + (lane >> 3);
     const int X = blockIdx.x * 32 + px;
     const int Y = blockIdx.y * 32 + py;
-    float *const drow = reinterpret_cast<float *>(static_cast<char *>(P.dst) + (long long)Y * P.dst_pitch) + X;
+    const int z0 = NZ > 1 ? (int)blockIdx.z * NZ : 0;
+    const int nz = NZ > 1 ? min(NZ, nz_total - z0) : 1;
+    float *drow = reinterpret_cast<float *>(static_cast<char *>(P.dst) + (long long)z0 * P.dst_plane + (long long)Y * P.dst_pitch) + X;
     const bool row_in = Y < P.dst_h;
     const bool full = row_in && (blockIdx.x * 32 + 32 <= (unsigned)P.dst_w);
 
@@ -176,11 +185,13 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
         const float cxc = fmaf(P.aff_f[0], xc, fmaf(P.aff_f[1], yc, P.aff_c[0]));
         const float cyc = fmaf(P.aff_f[2], xc, fmaf(P.aff_f[3], yc, P.aff_c[1]));
         if (cxc < -P.aff_c[2] || cxc > P.aff_lim[0] || cyc < -P.aff_c[3] || cyc > P.aff_lim[1]) {
-            if (full) { drow[0] = 0.f; drow[8] = 0.f; drow[16] = 0.f; drow[24] = 0.f; }
-            else if (row_in) {
+            for (int z = 0; z < nz; ++z, drow = reinterpret_cast<float *>(reinterpret_cast<char *>(drow) + P.dst_plane)) {
+                if (full) { drow[0] = 0.f; drow[8] = 0.f; drow[16] = 0.f; drow[24] = 0.f; }
+                else if (row_in) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (X + 8 * j < P.dst_w) drow[8 * j] = 0.0f;
+                    for (int j = 0; j < 4; ++j)
+                        if (X + 8 * j < P.dst_w) drow[8 * j] = 0.0f;
+                }
             }
             return;
         }
@@ -242,7 +253,7 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
         chain_eval_n<A, SPH, 4>(P.chain, cx, cy);
     }
 
-    float4 g[4];
+    float tcx[4], tcy[4];
     float fx[4], fy[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -258,23 +269,46 @@ k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t te
             }
         }
         // texel index inside the staged rectangle (src_x0 = src_y0 = 0 for a whole image)
-        g[j] = tex2Dgather<float4>(tex, (float)(ix + 1 - P.src_x0), (float)(iy + 1 - P.src_y0), 0);
+        tcx[j] = (float)(ix + 1 - P.src_x0);
+        tcy[j] = (float)(iy + 1 - P.src_y0);
     }
-    float r[4];
+#pragma unroll(NZ > 1 ? 2 : 1)
+    for (int z = 0; z < nz; ++z, drow = reinterpret_cast<float *>(reinterpret_cast<char *>(drow) + P.dst_plane)) {
+        const cudaTextureObject_t tex = texof(z0 + z);
+        float4 g[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        // gather order: x = (i0,j1), y = (i1,j1), z = (i1,j0), w = (i0,j0)
-        const float v00 = g[j].w, v01 = g[j].z, v10 = g[j].x, v11 = g[j].y;
-        const float top = fmaf(fx[j], v01 - v00, v00);
-        const float bot = fmaf(fx[j], v11 - v10, v10);
-        r[j] = fmaf(fy[j], bot - top, top);
-    }
-    if (full) { drow[0] = r[0]; drow[8] = r[1]; drow[16] = r[2]; drow[24] = r[3]; }
-    else if (row_in) {
+        for (int j = 0; j < 4; ++j) g[j] = tex2Dgather<float4>(tex, tcx[j], tcy[j], 0);
+        float r[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (X + 8 * j < P.dst_w) drow[8 * j] = r[j];
+        for (int j = 0; j < 4; ++j) {
+            // gather order: x = (i0,j1), y = (i1,j1), z = (i1,j0), w = (i0,j0)
+            const float v00 = g[j].w, v01 = g[j].z, v10 = g[j].x, v11 = g[j].y;
+            const float top = fmaf(fx[j], v01 - v00, v00);
+            const float bot = fmaf(fx[j], v11 - v10, v10);
+            r[j] = fmaf(fy[j], bot - top, top);
+        }
+        if (full) { drow[0] = r[0]; drow[8] = r[1]; drow[16] = r[2]; drow[24] = r[3]; }
+        else if (row_in) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (X + 8 * j < P.dst_w) drow[8 * j] = r[j];
+        }
     }
+}
+
+template <class A, bool AFF, int SPH, bool WCSONLY = false>
+__global__ void __launch_bounds__(256, WCSONLY ? 6 : 1)
+k_resample_tex4(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex)
+{
+    resample_tex4_body<A, AFF, SPH, WCSONLY, 1>(P, [tex](int) { return tex; }, 1);
+}
+
+constexpr int TEX_PLANES_PER_CTA = 8;
+template <class A, bool AFF, int SPH, bool WCSONLY = false>
+__global__ void __launch_bounds__(256, WCSONLY ? 6 : 1)
+k_resample_tex4_batch(const __grid_constant__ ResampleParams P, const __grid_constant__ TexBatch TB)
+{
+    resample_tex4_body<A, AFF, SPH, WCSONLY, TEX_PLANES_PER_CTA>(P, [&TB](int z) { return TB.tex[z]; }, TB.n);
 }
 
 // Texture objects over caller memory are cached per (device, pointer, geometry): creating one costs
@@ -1058,23 +1092,52 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
                 const bool wcs_only = !aff4 && P.chain.n == 1 && P.chain.ops[0].kind == TFM_OP_WCS_PAIR &&
                                       (P.chain.ops[0].flags & 0xffff) == (TFM_WCS_PROJ_CAR | (TFM_WCS_PROJ_TAN << 8));
                 e = cudaSuccess;
-                for (long long k = 0; k < s.n_planes && e == cudaSuccess; ++k) {
-                    if (k > 0) {
-                        P.src = static_cast<const char *>(s.data) + k * s.plane_pitch;
-                        P.dst = static_cast<char *>(d.data) + k * d.plane_pitch;
-                        if (!get_texture(P.src, (int)s.w, (int)s.h, s.pitch, &tex, &tex_slot)) { e = cudaErrorUnknown; break; }
+                if (s.n_planes == 1 || (a->tuning & 1048576)) {    // bit 1048576: one launch per plane (A/B runs)
+                    for (long long k = 0; k < s.n_planes && e == cudaSuccess; ++k) {
+                        if (k > 0) {
+                            P.src = static_cast<const char *>(s.data) + k * s.plane_pitch;
+                            P.dst = static_cast<char *>(d.data) + k * d.plane_pitch;
+                            if (!get_texture(P.src, (int)s.w, (int)s.h, s.pitch, &tex, &tex_slot)) { e = cudaErrorUnknown; break; }
+                        }
+                        if (aff4) k_resample_tex4<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
+                        else if (wcs_only) k_resample_tex4<Fast, false, 1, true><<<grid, 256, 0, st>>>(P, tex);
+                        else if (sph == 2) k_resample_tex4<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
+                        else if (sph == 1) k_resample_tex4<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
+                        else k_resample_tex4<Fast, false, 0><<<grid, 256, 0, st>>>(P, tex);
+                        count_launch();
+                        texture_used(tex_slot, st);
+                        tex_slot = -1;
+                        e = cudaGetLastError();
                     }
-                    if (aff4) k_resample_tex4<Fast, true, 0><<<grid, 256, 0, st>>>(P, tex);
-                    else if (wcs_only) k_resample_tex4<Fast, false, 1, true><<<grid, 256, 0, st>>>(P, tex);
-                    else if (sph == 2) k_resample_tex4<Fast, false, 2><<<grid, 256, 0, st>>>(P, tex);
-                    else if (sph == 1) k_resample_tex4<Fast, false, 1><<<grid, 256, 0, st>>>(P, tex);
-                    else k_resample_tex4<Fast, false, 0><<<grid, 256, 0, st>>>(P, tex);
-                    count_launch();
-                    texture_used(tex_slot, st);
-                    tex_slot = -1;
-                    e = cudaGetLastError();
+                    name = aff4 ? "k_resample_tex4<affine>" : (wcs_only ? "k_resample_tex4<car-tan>" : "k_resample_tex4");
+                } else {
+                    // a batch of planes: up to TEX_BATCH_MAX texture objects per launch, a CTA computes the
+                    // coordinates of its tile once for TEX_PLANES_PER_CTA planes
+                    for (long long k0 = 0; k0 < s.n_planes && e == cudaSuccess; k0 += TEX_BATCH_MAX) {
+                        TexBatch TB;
+                        int slots[TEX_BATCH_MAX];
+                        TB.n = (int)std::min<long long>(TEX_BATCH_MAX, s.n_planes - k0);
+                        for (int z = 0; z < TEX_BATCH_MAX; ++z) { TB.tex[z] = 0; slots[z] = -1; }
+                        for (int z = 0; z < TB.n; ++z) {
+                            if (k0 + z == 0) { TB.tex[0] = tex; slots[0] = tex_slot; tex_slot = -1; continue; }
+                            const char *pz = static_cast<const char *>(s.data) + (k0 + z) * s.plane_pitch;
+                            if (!get_texture(pz, (int)s.w, (int)s.h, s.pitch, &TB.tex[z], &slots[z])) { e = cudaErrorUnknown; break; }
+                        }
+                        if (e != cudaSuccess) break;
+                        P.src = static_cast<const char *>(s.data) + k0 * s.plane_pitch;
+                        P.dst = static_cast<char *>(d.data) + k0 * d.plane_pitch;
+                        dim3 bgrid(grid.x, grid.y, (unsigned)((TB.n + TEX_PLANES_PER_CTA - 1) / TEX_PLANES_PER_CTA));
+                        if (aff4) k_resample_tex4_batch<Fast, true, 0><<<bgrid, 256, 0, st>>>(P, TB);
+                        else if (wcs_only) k_resample_tex4_batch<Fast, false, 1, true><<<bgrid, 256, 0, st>>>(P, TB);
+                        else if (sph == 2) k_resample_tex4_batch<Fast, false, 2><<<bgrid, 256, 0, st>>>(P, TB);
+                        else if (sph == 1) k_resample_tex4_batch<Fast, false, 1><<<bgrid, 256, 0, st>>>(P, TB);
+                        else k_resample_tex4_batch<Fast, false, 0><<<bgrid, 256, 0, st>>>(P, TB);
+                        count_launch();
+                        for (int z = 0; z < TB.n; ++z) texture_used(slots[z], st);
+                        e = cudaGetLastError();
+                    }
+                    name = aff4 ? "k_resample_tex4_batch<affine>" : (wcs_only ? "k_resample_tex4_batch<car-tan>" : "k_resample_tex4_batch");
                 }
-                name = aff4 ? "k_resample_tex4<affine>" : (wcs_only ? "k_resample_tex4<car-tan>" : "k_resample_tex4");
                 set_last_kernel(name);
                 return e == cudaSuccess ? TFM_OK : TFM_ECUDA;
             }
