@@ -580,6 +580,80 @@ k_jacobian(const __grid_constant__ JacParams P)
         const double xf_of = __dsub_rn(px, fxs), yf_of = __dsub_rn(py, fys);
         const double ob = P.oblur;
         double val = 0, wgt = 0;
+        // Footprint wholly inside the image and the staged rectangle (nearly every pixel): no boundary rule can
+        // fire, so the taps are consecutive elements of consecutive rows.  Same operations on the same operands in
+        // the same order as the general loop below -- bit-identical -- minus what does not depend on the tap:
+        // ncu on the general loop (profiles/r2_kernels.md, jacobian_parity): 8,500 instructions per pixel,
+        // ~190 per tap, of which the weight itself (two dot products, exp) is under 50.  Row terms J01 y0 and
+        // J11 y0 are formed once per row; tap offsets count in doubles (exact integers) instead of converting;
+        // |.| before squaring is dropped ((-v)(-v) is v v exactly).  (flags 0x200: tuning bit 2097152 disables it.)
+        const long long wx0 = xs - half, wy0 = ys - half;
+        const bool inside = !(P.flags & 0x200) && half <= 16384 &&
+                            wx0 >= P.src_x0 && wx0 >= 0 && wx0 + 2LL * half < min((long long)P.full_w, (long long)P.src_x0 + P.src_w) &&
+                            wy0 >= P.src_y0 && wy0 >= 0 && wy0 + 2LL * half < min((long long)P.full_h, (long long)P.src_y0 + P.src_h);
+        if (inside) {
+            const char *prow = src_base + (wy0 - P.src_y0) * P.src_pitch + (wx0 - P.src_x0) * (long long)sizeof(SrcT);
+            const bool lean = (P.filter == TFM_FILT_GAUSSIAN) && (ob == 1.0);
+            const int n = 2 * half + 1;
+            const double first = -(double)half;
+            // Gaussian: exp(-(xf^2 + yf^2)) = exp(-(A a^2 + 2 B a b + C b^2)) in the tap offsets (a, b), A, B, C
+            // from J and oblur.  The recurrence is taken when no weight of the window can leave the normal
+            // range (flags 0x400: tuning bit 4194304 keeps one exp per tap, bit-identical with the general loop).
+            double qA = 0, qB = 0, qC = 0, cA = 0;
+            bool recur = false;
+            if (P.filter == TFM_FILT_GAUSSIAN && !(P.flags & 0x400)) {
+                const double io2 = 1.0 / (ob * ob);
+                qA = (J[0] * J[0] + J[2] * J[2]) * io2;
+                qB = (J[0] * J[1] + J[2] * J[3]) * io2;
+                qC = (J[1] * J[1] + J[3] * J[3]) * io2;
+                const double hh = (double)(half + 1);
+                recur = (qA + 2.0 * fabs(qB) + qC) * (hh * hh) < 600.0;
+                cA = exp(-2.0 * qA);
+            }
+            double yrd = first;
+            for (int j = 0; j < n; ++j, yrd += 1.0, prow += P.src_pitch) {
+                const SrcT *const p = reinterpret_cast<const SrcT *>(prow);
+                const double y0 = __dadd_rn(yrd, yf_of);
+                const double a1 = __dmul_rn(J[1], y0), a3 = __dmul_rn(J[3], y0);
+                double xrd = first;
+                if (recur) {
+                    // w(a + 1) = w(a) r(a), r(a + 1) = r(a) exp(-2A): two multiplications per tap instead of an
+                    // exp (~40 instructions).  Both are restarted from exp() every row and every 32 taps, so a
+                    // weight carries at most ~32^2 / 2 roundings: 1e-13 relative, inside the stated 1e-11.
+                    for (int i0 = 0; i0 < n; i0 += 32) {
+                        const double x0 = __dadd_rn(first + (double)i0, xf_of);
+                        double w = exp(-((qA * x0 + 2.0 * (qB * y0)) * x0 + qC * (y0 * y0)));
+                        double r = exp(-(qA * (2.0 * x0 + 1.0) + 2.0 * (qB * y0)));
+                        const int i1 = min(n, i0 + 32);
+#pragma unroll 4
+                        for (int i = i0; i < i1; ++i) {
+                            wgt = __dadd_rn(wgt, w);
+                            val = __dadd_rn(val, __dmul_rn((double)__ldg(p + i), w));
+                            w *= r;
+                            r *= cA;
+                        }
+                    }
+                } else if (lean) {
+#pragma unroll 2
+                    for (int i = 0; i < n; ++i, xrd += 1.0) {
+                        const double x0 = __dadd_rn(xrd, xf_of);
+                        const double xf = __dadd_rn(__dmul_rn(J[0], x0), a1), yf = __dadd_rn(__dmul_rn(J[2], x0), a3);
+                        const double filt = exp(-__dadd_rn(__dmul_rn(xf, xf), __dmul_rn(yf, yf)));
+                        wgt = __dadd_rn(wgt, filt);
+                        val = __dadd_rn(val, __dmul_rn((double)__ldg(p + i), filt));
+                    }
+                } else {
+                    for (int i = 0; i < n; ++i, xrd += 1.0) {
+                        const double x0 = __dadd_rn(xrd, xf_of);
+                        double xf = fabs(__dadd_rn(__dmul_rn(J[0], x0), a1)), yf = fabs(__dadd_rn(__dmul_rn(J[2], x0), a3));
+                        if (ob != 1.0) { xf = __ddiv_rn(xf, ob); yf = __ddiv_rn(yf, ob); }
+                        const double filt = filt_eval<double>(P.filter, xf, yf);
+                        wgt = __dadd_rn(wgt, filt);
+                        val = __dadd_rn(val, __dmul_rn((double)__ldg(p + i), filt));
+                    }
+                }
+            }
+        } else
         for (int yr = -half; yr <= half; ++yr) {
             const double y0 = __dadd_rn((double)yr, yf_of);
             for (int xr = -half; xr <= half; ++xr) {
@@ -886,7 +960,8 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     P.dst_h = (int)d.h; P.dst_w = (int)d.w; P.dst_x0 = d.x0; P.dst_y0 = d.y0;
     P.grid_h = (int)d.full_h; P.grid_w = (int)d.full_w;
     P.bound_x = a->bound_x; P.bound_y = a->bound_y; P.filter = a->filter;
-    P.flags = (a->flags & 0xff) | ((a->tuning & 512) ? 0x100 : 0);
+    P.flags = (a->flags & 0xff) | ((a->tuning & 512) ? 0x100 : 0) | ((a->tuning & 2097152) ? 0x200 : 0) |
+              ((a->tuning & 4194304) ? 0x400 : 0);
     P.src_f64 = s.dtype == TFM_F64; P.dst_f64 = d.dtype == TFM_F64;
     P.oblur = a->oblur; P.pad_pow = a->pad_pow; P.jump_thresh = a->jump_thresh;
     // helpers.pyx:1612-1615: padval 1 for tent/Hanning/Tukey, 3 for Lanczos/Gaussian
