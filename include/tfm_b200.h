@@ -292,6 +292,41 @@ typedef struct tfm_apply_args {
 
 TFM_API int tfm_apply(const tfm_apply_args *args, void *stream);
 
+/* ---- K3-ND: Transform.apply for Linear-family chains of dimension 3..8 ----
+ * Replaces Linear._forward / _reverse (basic.py:141-176) under Transform.apply (core.py:255-292) for the
+ * transforms the reference builds in more than two dimensions: Linear with an N x N matrix, Scale, Offset
+ * and Rotation from axis pairs or Euler angles (basic.py:338-506; tests/test_02_basic.py:170-186).
+ * One op = (vector + add_before) -> matrix . vector -> (+ add_after); the host resolves the direction
+ * (forward: +pre, matrix, +post; reverse: -post, matinv, -pre -- x - p is x + (-p) exactly).
+ * The matrix product is rounded as NumPy rounds np.matmul(m, v[..., None]) for a [dim, dim] matrix and
+ * [..., dim, 1] stacks (NumPy 2.3 / OpenBLAS 0.3.30, x86-64): pinned bit for bit for dim = 3 in both memory
+ * orders and for dim = 4 transposed views; dim >= 4 otherwise holds 4 ulp of sum |m_ik v_k|.
+ * Components dim.. of each vector are copied through (core.py:271-276, 287-292). */
+#define TFM_LIN_ND_MAX 8
+typedef struct tfm_linear_nd_op {
+    int32_t flags;                                   /* TFM_LIN_HAS_PRE (add_before), TFM_LIN_HAS_POST (add_after),
+                                                        TFM_LIN_HAS_MATRIX, TFM_LIN_MAT_FORDER */
+    int32_t reserved;
+    double matrix[TFM_LIN_ND_MAX * TFM_LIN_ND_MAX];  /* row-major [dim][dim] */
+    double add_before[TFM_LIN_ND_MAX];
+    double add_after[TFM_LIN_ND_MAX];
+} tfm_linear_nd_op;
+
+typedef struct tfm_apply_nd_args {
+    int32_t abi_version;
+    int32_t n_ops;                                   /* <= TFM_MAX_OPS */
+    const tfm_linear_nd_op *chain;                   /* host pointer, execution order */
+    int32_t dim;                                     /* 1..TFM_LIN_ND_MAX, the same for every op */
+    int32_t vec_len;                                 /* >= dim; components dim.. are copied through */
+    const void *in;
+    void *out;
+    int64_t n_vec;
+    int32_t dtype;                                   /* tfm_dtype of in and out (arithmetic is fp64) */
+    int32_t reserved;
+} tfm_apply_nd_args;
+
+TFM_API int tfm_apply_linear_nd(const tfm_apply_nd_args *args, void *stream);
+
 /* ---- K0: FITS pixel decode (the step before the path: file -> device image) ----
  * Replaces what astropy.io.fits does for the reference when it opens the file (core.py:991-1023,
  * DataWrapper on a file name / HDU): big-endian BITPIX samples -> native floating point, with

@@ -12,6 +12,7 @@
 // CTAs) keeps UNROLL packets in flight per thread.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "tfm_chain.cuh"
 #include "tfm_common.cuh"
 
@@ -185,6 +186,95 @@ int apply_dispatch(const tfm_apply_args *a, cudaStream_t st)
 #undef TFM_LAUNCH
     count_launch();
     set_last_kernel(name);
+    return cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3-ND: Linear-family chains of dimension 3..8 (basic.py:141-176 under core.py:255-292)
+// ---------------------------------------------------------------------------------------------
+// Streaming, grid-stride, one vector per thread and iteration.  Row i of the matrix product is rounded as
+// NumPy's np.matmul(m, v[..., None]) rounds it (measured against NumPy 2.3 / OpenBLAS 0.3.30 on x86-64,
+// the way DESIGN.md section 2 describes the 2 x 2 case): C-contiguous matrix s = m_i1 v_1, s = fma(m_i0, v_0, s),
+// then s = fma(m_ik, v_k, s) for k = 2..; a transposed view (Rotation's matinv) of dimension <= 3 runs the
+// chain from k = 0.  dim = 2 reduces to the two orders of the 2-D opcode.
+struct LinNdParams {
+    const void *in;
+    void *out;
+    long long n_vec;
+    int vec_len, dim, n_ops, pad;
+    tfm_linear_nd_op ops[TFM_MAX_OPS];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_apply_linear_nd(const __grid_constant__ LinNdParams P)
+{
+    const T *in = static_cast<const T *>(P.in);
+    T *out = static_cast<T *>(P.out);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int L = P.vec_len, D = P.dim;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_vec; i += stride) {
+        const T *vi = in + i * L;
+        T *vo = out + i * L;
+        double v[TFM_LIN_ND_MAX], w[TFM_LIN_ND_MAX];
+#pragma unroll
+        for (int k = 0; k < TFM_LIN_ND_MAX; ++k) v[k] = (k < D) ? (double)vi[k] : 0.0;
+        for (int o = 0; o < P.n_ops; ++o) {
+            const tfm_linear_nd_op &op = P.ops[o];
+            if (op.flags & TFM_LIN_HAS_PRE) {
+#pragma unroll
+                for (int k = 0; k < TFM_LIN_ND_MAX; ++k) if (k < D) v[k] = __dadd_rn(v[k], op.add_before[k]);
+            }
+            if (op.flags & TFM_LIN_HAS_MATRIX) {
+                const bool from0 = (op.flags & TFM_LIN_MAT_FORDER) && D <= 3;
+#pragma unroll
+                for (int r = 0; r < TFM_LIN_ND_MAX; ++r) {
+                    if (r >= D) { w[r] = 0.0; continue; }
+                    const double *m = op.matrix + r * D;
+                    double s;
+                    if (D == 1) s = __dmul_rn(m[0], v[0]);
+                    else if (from0) s = __fma_rn(m[1], v[1], __dmul_rn(m[0], v[0]));
+                    else s = __fma_rn(m[0], v[0], __dmul_rn(m[1], v[1]));
+#pragma unroll
+                    for (int k = 2; k < TFM_LIN_ND_MAX; ++k) if (k < D) s = __fma_rn(m[k], v[k], s);
+                    w[r] = s;
+                }
+#pragma unroll
+                for (int k = 0; k < TFM_LIN_ND_MAX; ++k) v[k] = w[k];
+            }
+            if (op.flags & TFM_LIN_HAS_POST) {
+#pragma unroll
+                for (int k = 0; k < TFM_LIN_ND_MAX; ++k) if (k < D) v[k] = __dadd_rn(v[k], op.add_after[k]);
+            }
+        }
+        for (int k = D; k < L; ++k) vo[k] = vi[k];
+#pragma unroll
+        for (int k = 0; k < TFM_LIN_ND_MAX; ++k) if (k < D) vo[k] = (T)v[k];
+    }
+}
+
+int apply_linear_nd_dispatch(const tfm_apply_nd_args *a, cudaStream_t st)
+{
+    if (!a || a->abi_version != TFM_ABI_VERSION) return TFM_EVALUE;
+    if (a->n_ops < 0 || a->n_ops > TFM_MAX_OPS || (a->n_ops && !a->chain)) return TFM_EVALUE;
+    if (a->dim < 1 || a->dim > TFM_LIN_ND_MAX || a->vec_len < a->dim || a->n_vec < 0) return TFM_EVALUE;
+    if (a->dtype != TFM_F32 && a->dtype != TFM_F64) return TFM_EVALUE;
+    if (a->n_vec == 0) return TFM_OK;
+    if (!a->in || !a->out) return TFM_EVALUE;
+    LinNdParams P;
+    memset(&P, 0, sizeof(P));
+    P.in = a->in; P.out = a->out; P.n_vec = a->n_vec; P.vec_len = a->vec_len; P.dim = a->dim; P.n_ops = a->n_ops;
+    for (int i = 0; i < a->n_ops; ++i) P.ops[i] = a->chain[i];
+    if (a->dtype == TFM_F64) {
+        const int grid = resident_grid((const void *)k_apply_linear_nd<double>, a->n_vec);
+        k_apply_linear_nd<double><<<grid, 256, 0, st>>>(P);
+        set_last_kernel("k_apply_linear_nd<f64>");
+    } else {
+        const int grid = resident_grid((const void *)k_apply_linear_nd<float>, a->n_vec);
+        k_apply_linear_nd<float><<<grid, 256, 0, st>>>(P);
+        set_last_kernel("k_apply_linear_nd<f32>");
+    }
+    count_launch();
     return cudaGetLastError() == cudaSuccess ? TFM_OK : TFM_ECUDA;
 }
 

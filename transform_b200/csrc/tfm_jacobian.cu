@@ -588,6 +588,15 @@ k_jacobian(const __grid_constant__ JacParams P)
         // J11 y0 are formed once per row; tap offsets count in doubles (exact integers) instead of converting;
         // |.| before squaring is dropped ((-v)(-v) is v v exactly).  (flags 0x200: tuning bit 2097152 disables it.)
         const long long wx0 = xs - half, wy0 = ys - half;
+        // A footprint wholly beyond a truncated edge: every tap sets tflag and none adds its value
+        // (helpers.pyx:1754-1755, 1774-1775, 1793-1796), so the pixel is 0 / wgt = 0 whatever the weights are --
+        // unless the other axis forbids, where the reference raises from inside the same loop.  These pixels carry
+        // the largest footprints of an unwrap (its corners): in the profile of the general loop they were 3/4 of
+        // all taps evaluated.
+        const bool all_out = !(P.flags & 0x200) && P.bound_x != TFM_B_FORBID && P.bound_y != TFM_B_FORBID &&
+                             ((P.bound_x == TFM_B_TRUNCATE && (xs + half < 0 || wx0 >= P.full_w)) ||
+                              (P.bound_y == TFM_B_TRUNCATE && (ys + half < 0 || wy0 >= P.full_h)));
+        if (all_out) { drow[X] = (DstT)0; continue; }
         const bool inside = !(P.flags & 0x200) && half <= 16384 &&
                             wx0 >= P.src_x0 && wx0 >= 0 && wx0 + 2LL * half < min((long long)P.full_w, (long long)P.src_x0 + P.src_w) &&
                             wy0 >= P.src_y0 && wy0 >= 0 && wy0 + 2LL * half < min((long long)P.full_h, (long long)P.src_y0 + P.src_h);

@@ -406,8 +406,10 @@ __device__ __forceinline__ int gauss_classify(const JacFastParams &P, const floa
         floor_frac_fast(py, yi, yf);
         // a footprint entirely beyond a truncated edge: every tap is skipped, the pixel is 0 whatever the
         // weights are (helpers.pyx:1793-1800)
-        if ((P.bound_x == TFM_B_TRUNCATE && (xi + half < 0 || xi - half >= P.full_w)) ||
-            (P.bound_y == TFM_B_TRUNCATE && (yi + half < 0 || yi - half >= P.full_h)))
+        // (not when the other axis forbids: the reference raises from inside the same loop)
+        if (P.bound_x != TFM_B_FORBID && P.bound_y != TFM_B_FORBID &&
+            ((P.bound_x == TFM_B_TRUNCATE && (xi + half < 0 || xi - half >= P.full_w)) ||
+             (P.bound_y == TFM_B_TRUNCATE && (yi + half < 0 || yi - half >= P.full_h))))
             return 0;
         const int ox = xi - half - P.src_x0, oy = yi - half - P.src_y0;
         const float hf1 = (float)(half + 1);
