@@ -9,8 +9,9 @@
  *                       M-vectors.  NumPy 2.3.5 + OpenBLAS 0.3.30 on x86-64 evaluates the 2x2 case
  *                       as fma(m[i][0], x, fl(m[i][1]*y)) for a C-contiguous matrix and as
  *                       fma(m[i][1], y, fl(m[i][0]*x)) for a transposed view (gemv N vs T
- *                       kernels; measured bit-exact in the authoring container).  This is the
- *                       arithmetic convention of the CUDA fp64-exact mode as well.
+ *                       kernels; measured bit-exact in the authoring container), and continues a
+ *                       3x3 row with one more fma in either case.  This is the arithmetic
+ *                       convention of the CUDA fp64-exact mode as well.
  *   orc_svd2x2          helpers.pyx:1845-1894 (svd2x2_fast)
  *   orc_svc2x2          helpers.pyx:1901-1916 (svc2x2_fast)
  *   orc_interp_jacobian helpers.pyx:1542-1803 (interpND_jacobian) with the repairs listed in
@@ -30,10 +31,15 @@
 #define ORC_EFORBID 2       /* -> ValueError: 'forbid' boundary violated (helpers.pyx:1753,1774) */
 
 /* out[n][rows] = M[rows][cols] . v[n][cols]   (v may have a wider stride: extra components)
- * f_order = 0: M was C-contiguous in the reference  -> acc = fl(m[i][last]*v[last]), fma downwards
+ * The order in which np.matmul(m, v[..., None]) accumulates a row, measured in the authoring container
+ * (NumPy 2.3.5, OpenBLAS 0.3.30, x86-64; tests/test_oracle_kat.py::test_matvec_rounding_matches_numpy
+ * re-measures it wherever the CPU suite runs):
+ * f_order = 0: M was C-contiguous in the reference  -> acc = fl(m[i][1]*v[1]); fma(m[i][0], v[0], acc);
+ *              then fma(m[i][k], v[k], acc) for k = 2..  (bit-exact for 2 x 2: 6000/6000, 3 x 3: 6000/6000)
  * f_order = 1: M was a transposed (Fortran) view, e.g. Rotation's matinv = out.transpose()
- *              (basic.py:501)                      -> acc = fl(m[i][0]*v[0]), fma upwards
- * Both measured bit-exact against np.matmul (6000/6000 each) in the authoring container. */
+ *              (basic.py:501)                      -> cols <= 3: acc = fl(m[i][0]*v[0]), fma upwards
+ *              (2 x 2 and 3 x 3 bit-exact); cols = 4: the f_order = 0 order (bit-exact, 720/720).
+ * Anything larger is not pinned (OpenBLAS' vectorised kernels sum partial accumulators): a few ulp. */
 void orc_matvec_fma(const double *M, int rows, int cols, int f_order,
                     const double *v, int64_t n, int64_t v_stride,
                     double *out, int64_t out_stride)
@@ -44,13 +50,15 @@ void orc_matvec_fma(const double *M, int rows, int cols, int f_order,
         for (int i = 0; i < rows; ++i) {
             const double *mi = M + (size_t)i * cols;
             double acc;
-            if (f_order) {
+            if (cols == 1) {
+                acc = mi[0] * vp[0];
+            } else if (f_order && cols <= 3) {
                 acc = mi[0] * vp[0];
                 for (int k = 1; k < cols; ++k)
                     acc = fma(mi[k], vp[k], acc);
             } else {
-                acc = mi[cols - 1] * vp[cols - 1];
-                for (int k = cols - 2; k >= 0; --k)
+                acc = fma(mi[0], vp[0], mi[1] * vp[1]);
+                for (int k = 2; k < cols; ++k)
                     acc = fma(mi[k], vp[k], acc);
             }
             op[i] = acc;

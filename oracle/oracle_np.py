@@ -104,8 +104,10 @@ def _dptr(a):
 def _matvec(m, v, f_order=False):
     """np.matmul(m, v[...,None])[...,0] (basic.py:150-152, 168-170) with a *defined* rounding that
     reproduces NumPy 2.3.5/OpenBLAS 0.3.30 on x86-64 (see oracle_c.c::orc_matvec_fma):
-      C-contiguous m:            acc = fl(m[i,-1]*v[-1]); acc = fma(m[i,k], v[k], acc), k descending
-      transposed view (f_order): acc = fl(m[i,0]*v[0]);   acc = fma(m[i,k], v[k], acc), k ascending"""
+      C-contiguous m:            acc = fma(m[i,0], v[0], fl(m[i,1]*v[1])); acc = fma(m[i,k], v[k], acc), k = 2..
+      transposed view (f_order): acc = fl(m[i,0]*v[0]); acc = fma(m[i,k], v[k], acc), k ascending (<= 3 columns;
+                                 4 columns: as C-contiguous)
+    pinned bit for bit for 2 x 2, 3 x 3 (both orders) and transposed 4 x 4; larger products are unpinned."""
     if MATVEC_IMPL == "numpy":
         mm = np.asarray(m, dtype=np.float64)
         if f_order and mm.flags.c_contiguous:
@@ -418,6 +420,26 @@ def _first_leaf_is_dim_pin(t, invert):
             return isinstance(t, _Pin) and t.dim is not None
 
 
+def linear_dim(t):
+    """Dimension of a transform made of Linear ops only (None otherwise): the size of its matrices / offsets."""
+    if isinstance(t, Linear):
+        for a in (t.matrix, t.matinv):
+            if a is not None:
+                return int(a.shape[0])
+        for a in (t.pre, t.post):
+            if a is not None and np.ndim(a) == 1:
+                return int(np.shape(a)[0])
+        return None
+    if isinstance(t, Inverse):
+        return linear_dim(t.t)
+    if isinstance(t, Composition):
+        dims = [linear_dim(x) for x in t.ops]
+        if not dims or any(d is None for d in dims):
+            return None
+        return max(dims)
+    return None
+
+
 def apply(t, data, invert=False):
     """Transform.apply for 2-D transforms (core.py:218-294): extra trailing components are
     passed through unchanged (core.py:271-276, 287-292)."""
@@ -429,6 +451,9 @@ def apply(t, data, invert=False):
     n = 2
     if isinstance(t, Identity):
         return d
+    nd = linear_dim(t)                           # Linear-family chains of dimension 3..8 (basic.py:141-176)
+    if nd is not None and nd > 2:
+        n = nd
     if isinstance(t, _Pin):                      # idim = dim, or 0 = every component (core.py:271-292)
         n = t.idim
         if n == 0:

@@ -186,3 +186,57 @@ def test_pincushion_kats_and_modes(tfm, oracle):
     q = tfm.Quadpin(dim=2, strength=0.3, length=10.0)
     assert np.array_equal(q.apply(iv), oracle.apply(to_oracle(q), iv))
     assert np.array_equal(q.apply(iv), np.trunc(q.apply(iv.astype(float))))
+
+
+def test_linear_nd_reference_kats(tfm):
+    """The reference's own 3-D Rotation tests (tests/test_02_basic.py:170-186) through the K3-ND kernel."""
+    from transform_b200 import _lib
+    d0 = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1]])
+    a = tfm.Rotation([[1, 2, 90], [0, 1, 90]], unit='deg')
+    assert a.idim == 3
+    d1 = a.apply(d0)
+    assert _lib.last_kernel() == "k_apply_linear_nd<f64>"
+    assert np.all(np.isclose(d1, np.array([[0, 0, 1], [-1, 0, 0], [0, -1, 0]]), atol=1e-15))
+    a = tfm.Rotation([[0, 1, 90], [1, 2, 90]], unit='deg')
+    b = tfm.Rotation(euler=np.array([90, 0, 90]), unit='deg')
+    d1a, d1b = a.apply(d0), b.apply(d0)
+    assert np.all(np.isclose(d1a, d1b, atol=1e-15))
+    assert np.all(np.isclose(d1a, np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0]]), atol=1e-15))
+    assert np.all(np.isclose(b.invert(d1b), d0, atol=1e-15))
+    assert "%s" % a == "Transform( Linear/Rotation )"
+    with pytest.raises(ValueError):
+        a.apply(np.zeros((4, 2)))                                # core.py:284-285: too few components
+
+
+@pytest.mark.parametrize("dim", [3, 4, 5, 8])
+def test_linear_nd_random_chains(tfm, oracle, dim):
+    """Linear-family chains of dimension 3..8 (Scale o Linear o Offset, forward and inverted, pass-through
+    components, device tensors) against the oracle: bit for bit in 3-D, where the oracle's matrix-product order
+    is pinned against NumPy; within 4 ulp of sum |m_ik v_k| per op beyond."""
+    import torch
+    rng = np.random.default_rng(100 + dim)
+    m = rng.standard_normal((dim, dim)) + 2.0 * np.eye(dim)
+    tr = tfm.Composition([tfm.Scale(rng.uniform(0.5, 2.0, size=dim)),
+                          tfm.Linear(matrix=m, pre=rng.uniform(-1, 1, size=dim), post=rng.uniform(-1, 1, size=dim)),
+                          tfm.Offset(rng.uniform(-3, 3, size=dim))])
+    cases = [tr, tr.inverse()]
+    if dim == 3:
+        cases.append(tfm.Composition([tfm.Rotation(euler=rng.uniform(-180, 180, size=3), unit='deg'),
+                                      tfm.Offset([1.0, -2.0, 0.5])]))
+    for n, extra in ((0, 0), (1, 0), (1000, 0), (777, 2)):
+        v = rng.uniform(-100.0, 100.0, size=(n, dim + extra))
+        for c in cases:
+            for inv in (False, True):
+                got = c.apply(v, invert=inv)
+                want = oracle.apply(to_oracle(c), v, invert=inv)
+                assert got.shape == want.shape and got.dtype == np.float64
+                if dim == 3:
+                    assert np.array_equal(got, want), (n, extra, inv)
+                else:
+                    assert np.allclose(got, want, rtol=1e-13, atol=1e-12), (dim, n, inv, np.abs(got - want).max())
+                if extra:
+                    assert np.array_equal(got[:, dim:], v[:, dim:])
+    vt = torch.from_numpy(rng.uniform(-10, 10, size=(500, dim))).cuda()
+    out = tr.apply(vt)
+    assert out.is_cuda and out.dtype == torch.float64
+    assert np.array_equal(out.cpu().numpy(), tr.apply(vt.cpu().numpy()))

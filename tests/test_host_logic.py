@@ -143,7 +143,8 @@ def test_lowering_order_and_directions():
     with pytest.raises(AssertionError):
         t.Composition([t.Scale([0.0, 1.0]), B])._chain(True)
     with pytest.raises(NotImplementedError):
-        t.Scale(3, dim=3)._chain(False)                                   # outside the GPU path: loud
+        t.Scale(3, dim=9)._chain(False)                                   # outside the GPU path: loud
+    assert isinstance(t.Scale(3, dim=3)._chain(False)[0], L.TfmLinearNdOp)  # 3..8-D: the K3-ND op (apply only)
     rad = t.Radial(origin=[1.0, 2.0], r0=0.0, ccw=True)._chain(False)[0]
     assert rad.kind == L.OP_RADIAL and rad.flags == (L.RAD_CCW | L.RAD_POS_ONLY | L.RAD_R0_NOT_NONE | L.RAD_ORIGIN_NONZERO)
     assert list(rad.p)[:2] == [1.0, 2.0]
@@ -320,3 +321,33 @@ def test_product_never_touches_the_oracle_or_a_cpu_fallback():
         L.LIB_PATH = saved
         L._lib = None
         L.load()
+
+
+def test_linear_nd_lowering():
+    """Linear-family transforms of dimension 3..8 lower to tfm_linear_nd_op (K3-ND): matrix row-major, the
+    direction resolved into (add_before, matrix, add_after), the memory order of a transposed matinv carried as
+    a flag.  Image resampling stays 2-D."""
+    import transform_b200 as t
+    from transform_b200 import _lib as L
+    rot = t.Rotation(euler=np.array([90, 0, 90]), unit='deg')
+    assert rot.idim == 3
+    fwd, rev = rot._chain(False), rot._chain(True)
+    assert len(fwd) == 1 and isinstance(fwd[0], L.TfmLinearNdOp)
+    assert fwd[0].flags == L.LIN_HAS_MATRIX and rev[0].flags == (L.LIN_HAS_MATRIX | L.LIN_MAT_FORDER)
+    m = rot.params['matrix']
+    assert np.array_equal(np.array(fwd[0].matrix[:9]).reshape(3, 3), m)
+    assert np.array_equal(np.array(rev[0].matrix[:9]).reshape(3, 3), m.T)
+    lin = t.Linear(matrix=np.diag([1.0, 2.0, 4.0]), pre=np.array([1., 2., 3.]), post=np.array([-1., -2., -3.]))
+    f, r = lin._chain(False)[0], lin._chain(True)[0]
+    assert list(f.add_before[:3]) == [1., 2., 3.] and list(f.add_after[:3]) == [-1., -2., -3.]
+    assert list(r.add_before[:3]) == [1., 2., 3.] and list(r.add_after[:3]) == [-1., -2., -3.]   # -post, -pre
+    comp = t.Composition([t.Scale([1., 2., 3.]), rot, t.Offset([1., 1., 1.])])
+    assert comp.idim == 3 and len(comp._chain(False)) == 3
+    with pytest.raises(ValueError):
+        comp.resample(np.zeros((4, 4), dtype=np.float32))        # core.py:566-571: idim vs data dimensions
+    with pytest.raises(NotImplementedError):
+        comp.resample(np.zeros((4, 4, 4), dtype=np.float32))     # volumes are not on the GPU path
+    with pytest.raises(NotImplementedError):
+        L.make_chain(comp._chain(False))                         # never inside a 2-D opcode chain
+    with pytest.raises(NotImplementedError):
+        t.Linear(matrix=np.eye(9))._chain(False)                 # dimension > 8

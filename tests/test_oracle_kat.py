@@ -248,3 +248,28 @@ def test_projection_closed_forms(oracle):
         x, y = oracle._project(proj, phi, th)
         p2, t2 = oracle._deproject(proj, x, y)
         assert np.allclose(p2, phi, atol=1e-9) and np.allclose(t2, th, atol=1e-9), proj
+
+
+def test_matvec_rounding_matches_numpy(oracle):
+    """The order in which np.matmul(m, v[..., None]) accumulates a row (basic.py:150-152, 168-170), restated in
+    oracle_c.c::orc_matvec_fma and used by the CUDA fp64 mode (K1/K3 for 2 x 2, K3-ND beyond): bit for bit for
+    2 x 2 and 3 x 3 matrices in both memory orders and for transposed 4 x 4 views.  Re-measured here against
+    the NumPy of whatever machine runs the CPU suite."""
+    rng = np.random.default_rng(20)
+    for n, orders in ((2, (False, True)), (3, (False, True)), (4, (True,))):
+        for f_order in orders:
+            for _ in range(200):
+                m = rng.standard_normal((n, n))
+                v = rng.standard_normal((7, n)) * 10.0 ** rng.integers(-3, 4)
+                mm = np.ascontiguousarray(m.T).T if f_order else m
+                want = np.matmul(mm, v[..., None])[..., 0]
+                got = oracle._matvec(m, v, f_order)
+                assert np.array_equal(got, want), (n, f_order)
+    # larger products are not pinned: a few ulp of sum |m_ik v_k|
+    for n in (4, 5, 8):
+        m = rng.standard_normal((n, n))
+        v = rng.standard_normal((50, n))
+        want = np.matmul(m, v[..., None])[..., 0]
+        got = oracle._matvec(m, v, False)
+        scale = np.abs(m) @ np.abs(v).T
+        assert np.all(np.abs(got - want) <= 4 * np.finfo(float).eps * scale.T)

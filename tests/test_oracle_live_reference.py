@@ -171,3 +171,33 @@ def test_mirror_boundary_departure_R9(oracle):
     big = np.pad(src, 40, mode='symmetric')
     c = oracle.interp_grid_jacobian(big, edge + 40.0, method='g', bound='t')
     assert np.allclose(b, c, rtol=0, atol=1e-12)          # shifted coordinates round their fractions differently
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_apply_linear_3d_random_cases(ref, oracle, seed):
+    """Linear-family transforms beyond two dimensions (basic.py:141-176, 338-506: Rotation from axis pairs or
+    Euler angles, Scale, Offset, a general matrix with pre/post offsets) through Transform.apply, forward and
+    inverted, with pass-through components: the oracle equals the live reference bit for bit in 3-D."""
+    import transform_b200 as t                                   # host-side mirror: params only (no GPU here)
+    from conftest import to_oracle
+    rng = np.random.default_rng(9100 + seed)
+    eul = rng.uniform(-180, 180, size=3)
+    sc = rng.uniform(0.5, 2.0, size=3)
+    off = rng.uniform(-5, 5, size=3)
+    m = rng.standard_normal((3, 3))
+    pre, post = rng.uniform(-1, 1, size=3), rng.uniform(-1, 1, size=3)
+    cases = {
+        "euler": lambda p: p.Rotation(euler=eul, unit='deg'),
+        "pairs": lambda p: p.Rotation([[1, 2, eul[0]], [0, 1, eul[1]]], unit='deg'),
+        "chain": lambda p: p.Composition([p.Scale(sc), p.Rotation(euler=eul, unit='deg'), p.Offset(off)]),
+        "general": lambda p: p.Linear(matrix=m, pre=pre, post=post),
+    }
+    v = rng.uniform(-50.0, 50.0, size=(int(rng.integers(1, 300)), int(rng.integers(3, 6))))
+    for name, make in cases.items():
+        r, mine = make(ref), make(t)
+        q = to_oracle(mine)
+        for invert in (False, True):
+            want = r.apply(v.copy(), invert=invert)
+            got = oracle.apply(q, v.copy(), invert=invert)
+            assert got.shape == want.shape
+            assert np.array_equal(got, want), (seed, name, invert, np.abs(got - want).max())

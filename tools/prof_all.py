@@ -4,8 +4,8 @@
     python tools/prof_all.py <case>
 
 cases: linear_shift linear_named linear_rot45 nearest cubic hann lanczos linear_polar linear_parity
-       jacobian_polar jacobian_polar_single jacobian_constj jacobian_fd jacobian_parity jacobian_hanning
-       wcs_batch wcs_single apply_affine apply_radial fits_m32 fits_i16"""
+       jacobian_polar jacobian_polar_rows jacobian_polar_single jacobian_constj jacobian_fd jacobian_parity jacobian_hanning
+       wcs_batch wcs_single apply_affine apply_radial apply_nd fits_m32 fits_i16"""
 import sys
 
 import numpy as np
@@ -41,6 +41,7 @@ if case.startswith(("linear", "nearest", "cubic", "hann", "lanczos", "jacobian")
         "linear_parity": lambda: named.resample(src, method="linear", out=f64),
         "jacobian_polar": lambda: polar.resample(src, method="Gaussian", precision="fp32", out=f32),
         "jacobian_polar_single": lambda: polar.resample(src, method="Gaussian", precision="fp32", out=f32, tuning=262144),
+        "jacobian_polar_rows": lambda: polar.resample(src, method="Gaussian", precision="fp32", out=f32, tuning=524288),
         "jacobian_constj": lambda: down.resample(src, method="Gaussian", precision="fp32", out=f32),
         "jacobian_fd": lambda: polar.resample(src, method="Gaussian", precision="fp32", out=f32, tuning=512),
         "jacobian_parity": lambda: polar.resample(src, method="Gaussian", out=f64),
@@ -56,6 +57,10 @@ elif case.startswith("wcs"):
     frames = torch.rand((nb, m, m) if nb > 1 else (m, m), generator=g, device="cuda", dtype=torch.float32)
     out = torch.empty_like(frames)
     fn = lambda: total.resample(frames, method="linear", precision="fp32", out=out, shape=tuple(frames.shape))  # noqa: E731
+elif case == "apply_nd":
+    v = (torch.rand((2 * 10 ** 8, 3), generator=g, device="cuda", dtype=torch.float64) - 0.5) * 8192
+    tr = t.Composition([t.Scale([1.5, 2, 0.5]), t.Rotation(euler=np.array([10.0, 20.0, 30.0]), unit="deg"), t.Offset([3, 4, 5])])
+    fn = lambda: tr.apply(v)  # noqa: E731
 elif case.startswith("apply"):
     v = (torch.rand((2 * 10 ** 8, 2), generator=g, device="cuda", dtype=torch.float64) - 0.5) * 8192
     mid = t.Rotation(30, unit="deg") if case == "apply_affine" else t.Radial(origin=[0.1, 0.2])

@@ -379,6 +379,42 @@ def apply(chain_ops, data, precision=None, tuning=0):
     return dev.to_host(out) if from_numpy else out
 
 
+def apply_linear_nd(nd_ops, dim, data):
+    """K3-ND driver: data [..., L >= dim] through a chain of Linear-family ops of dimension `dim` (3..8);
+    the first `dim` components are transformed, the rest copied through.  float64 arithmetic and result
+    (the reference's np.matmul on float64 stacks)."""
+    lib = L.load()
+    from_numpy = not dev.is_cuda_tensor(data)
+    if from_numpy:
+        t = dev.to_device(np.asarray(data), np.float64)
+    else:
+        t = data.contiguous()
+        if dev.np_dtype_of(t) != np.float64:
+            t = t.double()
+    vec_len = int(t.shape[-1])
+    n_vec = t.numel() // max(vec_len, 1)
+    out = dev.torch_mod().empty_like(t)
+    n = len(nd_ops)
+    if n > L.MAX_OPS:
+        raise NotImplementedError("transform_b200: chains longer than %d elements are not supported" % L.MAX_OPS)
+    arr = (L.TfmLinearNdOp * max(n, 1))()
+    for i, o in enumerate(nd_ops):
+        arr[i] = o
+    a = L.TfmApplyNdArgs()
+    a.abi_version = L.ABI_VERSION
+    a.n_ops = n
+    a.chain = ctypes.cast(arr, ctypes.POINTER(L.TfmLinearNdOp))
+    a.dim = int(dim)
+    a.vec_len = vec_len
+    a.inp = t.data_ptr() if t.numel() else None
+    a.out = out.data_ptr() if t.numel() else None
+    a.n_vec = n_vec
+    a.dtype = L.F64
+    rc = lib.tfm_apply_linear_nd(ctypes.byref(a), dev.stream_ptr())
+    L.raise_for_status(rc, "tfm_apply_linear_nd")
+    return dev.to_host(out) if from_numpy else out
+
+
 def svd2x2(M):
     """Device svd2x2 on one matrix (test hook, helpers.pyx:1807-1808) -> U, s, V."""
     lib = L.load()

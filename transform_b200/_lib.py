@@ -79,7 +79,25 @@ class TfmApplyArgs(ctypes.Structure):
                 ("precision", ctypes.c_int32), ("tuning", ctypes.c_int32)]
 
 
-EXPORTED_SYMBOLS = ("tfm_resample", "tfm_resample_jacobian", "tfm_apply", "tfm_svd2x2", "tfm_svc2x2",
+LIN_ND_MAX = 8
+
+
+class TfmLinearNdOp(ctypes.Structure):
+    """One Linear-family op of dimension 1..8 (include/tfm_b200.h: tfm_linear_nd_op)."""
+    _fields_ = [("flags", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("matrix", ctypes.c_double * (LIN_ND_MAX * LIN_ND_MAX)),
+                ("add_before", ctypes.c_double * LIN_ND_MAX), ("add_after", ctypes.c_double * LIN_ND_MAX)]
+
+
+class TfmApplyNdArgs(ctypes.Structure):
+    _fields_ = [("abi_version", ctypes.c_int32), ("n_ops", ctypes.c_int32),
+                ("chain", ctypes.POINTER(TfmLinearNdOp)),
+                ("dim", ctypes.c_int32), ("vec_len", ctypes.c_int32),
+                ("inp", ctypes.c_void_p), ("out", ctypes.c_void_p),
+                ("n_vec", ctypes.c_int64), ("dtype", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+EXPORTED_SYMBOLS = ("tfm_resample", "tfm_resample_jacobian", "tfm_apply", "tfm_apply_linear_nd", "tfm_svd2x2", "tfm_svc2x2",
                     "tfm_simple_jacobian", "tfm_jump_detect", "tfm_jacobian_grid", "tfm_fits_decode",
                     "tfm_abi_version", "tfm_strerror", "tfm_launch_count", "tfm_last_kernel")
 
@@ -112,6 +130,8 @@ def load():
     lib.tfm_resample_jacobian.argtypes = [ctypes.POINTER(TfmJacobianArgs), ctypes.c_void_p]
     lib.tfm_apply.restype = ctypes.c_int
     lib.tfm_apply.argtypes = [ctypes.POINTER(TfmApplyArgs), ctypes.c_void_p]
+    lib.tfm_apply_linear_nd.restype = ctypes.c_int
+    lib.tfm_apply_linear_nd.argtypes = [ctypes.POINTER(TfmApplyNdArgs), ctypes.c_void_p]
     vp, i64 = ctypes.c_void_p, ctypes.c_int64
     lib.tfm_fits_decode.restype = ctypes.c_int
     lib.tfm_fits_decode.argtypes = [vp, ctypes.c_int32, i64, ctypes.c_double, ctypes.c_double, ctypes.c_int32, vp, vp]
@@ -157,6 +177,8 @@ def make_chain(ops):
         raise NotImplementedError("transform_b200: chains longer than %d elements are not supported" % MAX_OPS)
     arr = (TfmOp * max(n, 1))()
     for i, o in enumerate(ops):
+        if not isinstance(o, TfmOp):
+            raise NotImplementedError("transform_b200: a transform of dimension > 2 inside a 2-D chain")
         arr[i] = o
     return arr, n
 

@@ -89,9 +89,11 @@ class Linear(Transform):
         return dimspec
 
     def _lower(self, direction):
-        if self.idim > 2 or self.odim > 2 or self.idim != self.odim:
-            raise NotImplementedError("transform_b200: Linear transforms of dimension > 2 (or "
-                                      "non-square) are outside the GPU hot path")
+        if self.idim != self.odim or self.idim > L.LIN_ND_MAX:
+            raise NotImplementedError("transform_b200: non-square Linear transforms (or dimension > %d) "
+                                      "are outside the GPU hot path" % L.LIN_ND_MAX)
+        if self.idim > 2:
+            return self._lower_nd(direction)
         p = self.params
         m = p['matrix'] if direction == L.FWD else p['matinv']
         fp = _fingerprint(m, p['pre'], p['post'])
@@ -101,6 +103,37 @@ class Linear(Transform):
             return hit[1]
         memo[direction] = (fp, self._lower_uncached(direction, p, m))
         return memo[direction][1]
+
+    def _lower_nd(self, direction):
+        """Dimension 3..8 (basic.py:141-176): one tfm_linear_nd_op for the K3-ND kernel; only Transform.apply
+        takes these (image resampling is 2-D)."""
+        p = self.params
+        d = self.idim
+        op = L.TfmLinearNdOp()
+        flags = 0
+        m = p['matrix'] if direction == L.FWD else p['matinv']
+        if m is not None:
+            m = np.asarray(m, dtype=np.float64)
+            flags |= L.LIN_HAS_MATRIX
+            if not m.flags.c_contiguous:         # a transposed view (Rotation.matinv): np.matmul rounds differently
+                flags |= L.LIN_MAT_FORDER
+            for i in range(d):
+                for j in range(d):
+                    op.matrix[i * d + j] = float(m[i, j])
+        # forward: +pre, matrix, +post; reverse: -post, matinv, -pre (x - p == x + (-p) exactly)
+        before, after, sign = (p['pre'], p['post'], 1.0) if direction == L.FWD else (p['post'], p['pre'], -1.0)
+        if before is not None:
+            flags |= L.LIN_HAS_PRE
+            v = np.broadcast_to(np.asarray(before, dtype=np.float64), (d,))
+            for i in range(d):
+                op.add_before[i] = sign * float(v[i])
+        if after is not None:
+            flags |= L.LIN_HAS_POST
+            v = np.broadcast_to(np.asarray(after, dtype=np.float64), (d,))
+            for i in range(d):
+                op.add_after[i] = sign * float(v[i])
+        op.flags = flags
+        return [op] if flags else []
 
     @staticmethod
     def _lower_uncached(direction, p, m):

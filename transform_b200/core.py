@@ -57,7 +57,7 @@ class Transform:
         constructed with `dim=` that comes first writes its result back into the integer copy of its
         input (basic.py:962-965 and twins), i.e. truncates it to int64; reproduced by an opcode flag."""
         ops = self._chain(invert)
-        if ops and ops[0].kind == L.OP_PIN and getattr(ops[0], "_writes_back", False):
+        if ops and isinstance(ops[0], L.TfmOp) and ops[0].kind == L.OP_PIN and getattr(ops[0], "_writes_back", False):
             ops[0].flags |= L.PIN_TRUNC
         return ops
 
@@ -78,7 +78,14 @@ class Transform:
         if len(data.shape) == 0 or nlast < dim:
             raise ValueError("This %s requires %d dimensions; data have %d" % (self.__str__(), dim, nlast))
         if dim > 2:
-            raise NotImplementedError("transform_b200: only 1-D and 2-D transforms are on the GPU path")
+            # Linear-family chains of dimension 3..8 (Linear / Scale / Offset / Rotation from axis pairs or Euler
+            # angles, basic.py:141-176, 338-506): the K3-ND kernel
+            if not all(isinstance(o, L.TfmLinearNdOp) for o in ops):
+                raise NotImplementedError("transform_b200: beyond 2-D only Linear-family transforms of one "
+                                          "dimension are on the GPU path")
+            if not ops:
+                return data
+            return _engine.apply_linear_nd(ops, dim, data)
         if not ops:
             return data                         # Identity._forward returns its argument (core.py:1381-1385)
         if dim == 0 and getattr(self, "_elementwise", False) and nlast != 2:

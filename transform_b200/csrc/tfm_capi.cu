@@ -51,6 +51,11 @@ int tfm_apply(const tfm_apply_args *args, void *stream)
     return tfm::apply_dispatch(args, static_cast<cudaStream_t>(stream));
 }
 
+int tfm_apply_linear_nd(const tfm_apply_nd_args *args, void *stream)
+{
+    return tfm::apply_linear_nd_dispatch(args, static_cast<cudaStream_t>(stream));
+}
+
 int tfm_simple_jacobian(const double *index, int64_t ny, int64_t nx, double *Js, void *stream)
 {
     return tfm::jacobian_helpers(0, index, nullptr, ny, nx, 0.0, Js, nullptr, static_cast<cudaStream_t>(stream));

@@ -13,6 +13,7 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st);
 int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st);
 int jacobian_fast_dispatch(const tfm_jacobian_args *a, cudaStream_t st, int *rc);   // tfm_jacobian_fast.cu
 int apply_dispatch(const tfm_apply_args *a, cudaStream_t st);
+int apply_linear_nd_dispatch(const tfm_apply_nd_args *a, cudaStream_t st);
 int jacobian_helpers(int which, const void *in0, const void *in1, long long ny, long long nx, double thresh,
                      void *out, void *scratch, cudaStream_t st);
 int fits_decode_dispatch(const void *raw, int bitpix, long long n, double bscale, double bzero,
