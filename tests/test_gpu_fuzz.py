@@ -108,5 +108,8 @@ def test_k2_random_cases(tfm, oracle, seed):
         assert_close_rel(got, want, 1e-10, (seed, letter, bound))
         fast = tr.resample(src, method=letter, bound=bound, precision='fp32')
         err = np.abs(fast - want)
-        # isolated pixels may take the neighbouring footprint size (ceil of an fp32 quantity)
+        # isolated pixels may take the neighbouring footprint size (ceil of an fp32 quantity): their number is
+        # bounded AND so is their size -- a window one tap wider or narrower trades one row/column of the weight
+        # (at most ~1/3 of it for the smallest, 3 x 3, window) of uniform [0,1) samples for another
         assert np.median(err) < 2e-5 and (err > 5e-4).sum() <= max(3, err.size // 200), (seed, letter, bound, err.max())
+        assert err.max() <= 0.3, (seed, letter, bound, err.max())

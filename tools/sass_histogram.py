@@ -49,8 +49,9 @@ def main():
             short = re.sub(r"\(tfm::\w+Params.*$", "", dn).replace("tfm::", "").replace("void ", "")
             f.write("| `%s` | %d | %s |\n" % (short[:100], total, " | ".join(str(marks[m]) if marks[m] else "" for m in MARK)))
         f.write("\n## Headline kernels, top mnemonics\n\n")
-        for pat in ("k_resample_pipe", "k_resample_tex4<tfm::Fast, true", "k_jac_gauss_polar<2>", "k_jac_gauss_const<2, 2>",
-                    "k_apply"):
+        for pat in ("k_resample_pipe", "k_resample_tex4<tfm::Fast, true", "k_resample_tex4_batch<tfm::Fast, false, 1, true",
+                    "k_jac_gauss_polar_rows_pair", "k_jac_gauss_polar_rows<2>", "k_jac_gauss_polar<2>",
+                    "k_jac_gauss_const<2, 2>", "k_apply_f64x2", "k_apply_linear_nd<double>"):
             for dn, total, marks, cnt in keep:
                 if pat in dn.replace("(int)", "").replace("(bool)1", "true").replace("(bool)0", "false"):
                     f.write("* `%s` (%d): %s\n" % (dn[:90], total, ", ".join("%s %d" % kv for kv in cnt.most_common(14))))
