@@ -273,6 +273,29 @@ typedef struct tfm_jacobian_args {
 
 TFM_API int tfm_resample_jacobian(const tfm_jacobian_args *args, void *stream);
 
+/* ---- `tuning`: kernel-variant selectors for A/B measurements (bench.py breakdown, ncu captures, parity tests
+ * that pin one variant against another).  0 = the library's own choice; every bit only ever selects another
+ * CORRECT variant of the same computation.  Values are stable within an ABI version.
+ *   tfm_resample (K1)
+ *     1..3      warp patch of the load/store kernel (2: 16 x 2, 3: 8 x 4)
+ *     4         do not pre-compose affine chains
+ *     16        no texture-gather variants (plain loads)
+ *     64        2 x 2 windowed filters through the general filter kernel
+ *     128       texture gather, first form (4 pixels 8 rows apart)
+ *     256       TMA-staged, one box per CTA
+ *     8192      force the persistent TMA pipeline whatever the coverage of the map
+ *     1048576   batches of planes: one launch per plane instead of the plane-batch kernel
+ *   tfm_resample_jacobian (K2)
+ *     8, 32     tile height 16 / 8 of the general kernel
+ *     512       general (finite-difference) kernel even where a closed-form kernel applies
+ *     1024, 2048, 16384   warp patch widths
+ *     4096, 32768         4-byte / 8-byte tap loads instead of texture gathers
+ *     65536, 131072       lane-to-pixel maps of a texture request group
+ *     262144    analytic polar: per-pixel closed form instead of per-row tables
+ *     524288    analytic polar with per-row tables: one pixel per set of fetches instead of row pairs
+ *     2097152   parity mode: the general tap loop only (no interior loop, no all-out shortcut)
+ *     4194304   parity mode: one exp per tap instead of the fp64 weight recurrence */
+
 /* ---- K3: streaming Transform.apply over vector arrays ----
  * Replaces Transform.apply / invert on [..., vec_len] arrays (core.py:218-315) including the
  * pass-through of components beyond the transform's dimension (core.py:271-276, 287-292).

@@ -838,7 +838,8 @@ k_jac_gauss_polar_rows(const __grid_constant__ JacFastParams P)
 // served by the recurrence) takes the one-pixel form.
 struct PairPix {
     TexRows S;
-    float2 val2, wgt2;
+    float2 val2, wgt2;     // packed accumulators: inner column pairs
+    float val, wgt;        // scalar accumulators: first and last column pair
     bool mx, my;           // own window starts one column / row after the shared origin
 };
 
@@ -859,18 +860,24 @@ __device__ __forceinline__ void pair_rows(const float4 (&g)[HALF + 1], PairPix &
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         // gather order: x = (c, r+1), y = (c+1, r+1), z = (c+1, r), w = (c, r)
-        float2 va = make_float2(g[i].w, g[i].z), vb = make_float2(g[i].x, g[i].y);
-        float2 wa = Wa, wb = Wb;
-        if (i == 0) {                                        // column 0 belongs to the pixel only if its window starts here
-            va.x = A.mx ? 0.0f : va.x; wa.x = A.mx ? 0.0f : wa.x;
-            vb.x = A.mx ? 0.0f : vb.x; wb.x = A.mx ? 0.0f : wb.x;
+        if (i == 0 || i == NP - 1) {
+            // first / last column pair: one column always belongs to the pixel, the other only if its window starts
+            // on the shared origin (first pair) or one later (last pair) -- scalar, the doubtful lane under a predicate
+            // (selecting lanes of a packed pair costs a select AND a move per operand: 44 of the 173 instructions of
+            // a row pair in the first form of this kernel; measured 1.079 -> 1.066 ms)
+            const bool xin = (i == 0) ? !A.mx : true, yin = (i == NP - 1) ? A.mx : true;
+            if (use_a) {
+                if (xin) { A.val = fmaf(g[i].w, Wa.x, A.val); A.wgt += Wa.x; }
+                if (yin) { A.val = fmaf(g[i].z, Wa.y, A.val); A.wgt += Wa.y; }
+            }
+            if (use_b) {
+                if (xin) { A.val = fmaf(g[i].x, Wb.x, A.val); A.wgt += Wb.x; }
+                if (yin) { A.val = fmaf(g[i].y, Wb.y, A.val); A.wgt += Wb.y; }
+            }
+        } else {
+            if (use_a) { A.val2 = __ffma2_rn(make_float2(g[i].w, g[i].z), Wa, A.val2); A.wgt2 = __fadd2_rn(A.wgt2, Wa); }
+            if (use_b) { A.val2 = __ffma2_rn(make_float2(g[i].x, g[i].y), Wb, A.val2); A.wgt2 = __fadd2_rn(A.wgt2, Wb); }
         }
-        if (i == NP - 1) {                                   // column 2 HALF + 1 only if it starts one later
-            va.y = A.mx ? va.y : 0.0f; wa.y = A.mx ? wa.y : 0.0f;
-            vb.y = A.mx ? vb.y : 0.0f; wb.y = A.mx ? wb.y : 0.0f;
-        }
-        if (use_a) { A.val2 = __ffma2_rn(va, wa, A.val2); A.wgt2 = __fadd2_rn(A.wgt2, wa); }
-        if (use_b) { A.val2 = __ffma2_rn(vb, wb, A.val2); A.wgt2 = __fadd2_rn(A.wgt2, wb); }
         if (i + 1 < NP) {
             Wa = __fmul2_rn(Wa, Ra); Wb = __fmul2_rn(Wb, Rb);
             if (i + 2 < NP) { Ra = __fmul2_rn(Ra, CA4); Rb = __fmul2_rn(Rb, CA4); }
@@ -932,12 +939,13 @@ __device__ __forceinline__ void pair_begin(PairPix &A, float Aq, float Bq, float
     A.S.RB = __fmul2_rn(bc2(rb), make_float2(1.0f, cB));
     A.S.cA4 = cA2 * cA2; A.S.cB2 = cB * cB; A.S.cC = fast_ex2(-2.0f * Cq);
     A.val2 = make_float2(0.0f, 0.0f); A.wgt2 = make_float2(0.0f, 0.0f);
+    A.val = 0.0f; A.wgt = 0.0f;
     A.mx = dx != 0; A.my = dy != 0;
 }
 
 __device__ __forceinline__ float pair_end(const PairPix &A)
 {
-    const float val = A.val2.x + A.val2.y, wgt = A.wgt2.x + A.wgt2.y;
+    const float val = A.val + (A.val2.x + A.val2.y), wgt = A.wgt + (A.wgt2.x + A.wgt2.y);
     return (wgt > 0.0f) ? val * fast_rcp(wgt) : 0.0f;
 }
 
