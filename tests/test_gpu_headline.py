@@ -340,3 +340,34 @@ def test_staged_rectangles_reproduce_the_full_frame_8192(tfm):
                     assert dmax <= 2e-6, (method, world, split, p["rect"], k, dmax)
                 else:
                     assert dmax == 0.0, (method, world, split, p["rect"], k, dmax)
+
+
+def test_config4_tan_to_car_batch_4096(tfm, oracle):
+    """BASELINE config 4 at its frame size: a batch of 4096^2 frames, TAN -> CAR (bench.config4_transform), fp32
+    fast path -- the plane-batch texture kernel (k_resample_tex4_batch<car-tan>; 18 planes: two launches of 16 and
+    2, groups of 8, 8, 2) and the one-launch-per-plane form, both against the oracle on sampled rows of the first,
+    a middle and the last plane (1e-5 of the data range, the fp32 tolerance of linear interpolation) and against
+    each other bit for bit on every pixel."""
+    import sys
+    import os
+    import torch
+    from transform_b200 import _lib
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    total, _, n = bench.config4_transform(tfm)
+    nb = 18
+    g = torch.Generator(device="cuda").manual_seed(44)
+    frames = torch.rand((nb, n, n), generator=g, device="cuda", dtype=torch.float32)
+    got = total.resample(frames, method="linear", precision="fp32", shape=(nb, n, n))
+    assert _lib.last_kernel() == "k_resample_tex4_batch<car-tan>", _lib.last_kernel()
+    ref = total.resample(frames, method="linear", precision="fp32", shape=(nb, n, n), tuning=1048576)
+    assert _lib.last_kernel() == "k_resample_tex4<car-tan>", _lib.last_kernel()
+    assert torch.equal(got, ref)
+    rows = sample_rows(n, 48)
+    otr = to_oracle(total)
+    for k in (0, 9, nb - 1):
+        src64 = frames[k].cpu().numpy().astype(np.float64)
+        want = oracle_rows(oracle, otr, src64, rows, method="linear")
+        err, emax, emed = err_stats(got[k][rows].cpu().numpy(), want)
+        assert emax <= 1e-5, (k, emax, emed)
+    assert float(got.abs().max()) > 0.5                          # the frames overlap: not a field of zeros
