@@ -500,6 +500,25 @@ def gpu_arm(args):
     barrier()
     s_e2e = (time.perf_counter() - t0) / k_e2e
     ok = ok and bool(torch.equal(h_lin[1], h_lin[0]) and torch.equal(h_jac[1], h_jac[0]))
+    # the same host<->device traffic with NO kernels, all ranks at once: what this box lets the end-to-end number be
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    scratch = torch.empty_like(src)
+
+    def copies_only():
+        with torch.cuda.stream(s_up):
+            scratch.copy_(h_src, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_lin[1].copy_(out_lin, non_blocking=True)
+            h_jac[1].copy_(out_jac, non_blocking=True)
+
+    copies_only()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        copies_only()
+    barrier()
+    s_copy = (time.perf_counter() - t0) / k_e2e
+    del scratch
     # parity mode end to end (float64 results: twice the download)
     h64 = [torch.empty((n, n), dtype=torch.float64).pin_memory() for _ in range(2)]
 
@@ -549,10 +568,10 @@ def gpu_arm(args):
                               {"linear": float(ms1[0]), "jacobian": float(ms1[1])}, reps=max(3, min(args.steps, 10)))
 
     # max over ranks
-    tt = torch.tensor([ms_total, s_e2e, s_e2e_sync, ms_par, s_e2e_par], device="cuda", dtype=torch.float64)
+    tt = torch.tensor([ms_total, s_e2e, s_e2e_sync, ms_par, s_e2e_par, s_copy], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, s_e2e, s_e2e_sync, ms_par, s_e2e_par = (float(v) for v in tt)
+    ms_total, s_e2e, s_e2e_sync, ms_par, s_e2e_par, s_copy = (float(v) for v in tt)
 
     if rank == 0:
         px_step = 2.0 * n * n * world
@@ -593,6 +612,9 @@ def gpu_arm(args):
                         "steps": k_e2e, "matches_resident_result": ok,
                         "mode": "transform_b200.AsyncResampler.submit_many, 4 streams: one upload of the frame per "
                                 "step, H2D / kernels / D2H of consecutive steps overlap; pinned host buffers",
+                        "copies_only_ceiling_value": px_step / s_copy / 1e6,
+                        "copies_only_note": "the same pinned H2D / D2H traffic per step with no kernels, all ranks at once, "
+                                            "two streams per rank: the most this box lets `e2e.value` be",
                         "synchronous_calls_value": px_step / s_e2e_sync / 1e6,
                         "synchronous_calls_note": "plain Transform.resample(host, out=host) twice per step: two uploads",
                         "host_affinity": "NVML ideal CPU set of the rank's GPU (%d cores)" % len(numa_cpus)

@@ -43,6 +43,9 @@ struct JacParams {
     // constant-Jacobian path (fast mode, Gaussian, the whole chain is affine): everything that depends
     // on J alone is computed once on the host, in fp64
     int lw;                                  // log2 of the warp patch width in the footprint phase
+    cudaTextureObject_t tex;                 // fast mode, Gaussian: point-sampled texture over the whole source
+    int tex_ok;                              // 0 none; 1 footprints inside the image only; 2 both bounds truncate:
+                                             // the texture's border IS the reference's truncated tap
     int aff_const;
     int aff_half;                            // footprint half-width
     double aff[6];                           // source = A . grid + b
@@ -738,9 +741,32 @@ k_jacobian(const __grid_constant__ JacParams P)
         const float L2E = 1.4426950408889634f;
         const float Aq = q00 * iob * iob * L2E, Bq = q01 * iob * iob * L2E, Cq = q11 * iob * iob * L2E;
         const float h2 = (float)half * (float)half + 2.0f * (float)half + 1.0f;
-        const bool recur_ok = gauss && inside && half >= 1 && half <= 6 &&
-                              (Aq + 2.0f * fabsf(Bq) + Cq) * h2 < 100.0f;
-        if (recur_ok) {
+        const bool recur_fit = gauss && half >= 1 && half <= 6 && (Aq + 2.0f * fabsf(Bq) + Cq) * h2 < 100.0f;
+        const bool recur_ok = recur_fit && inside;
+        bool tex_done = false;
+        if constexpr (sizeof(SrcT) == 4) {
+            // texture-gather taps (as the lean kernels of tfm_jacobian_fast.cu): 2 x 2 taps per fetch, and with
+            // truncate boundaries the border texel is the truncated tap, so edge footprints need no slow path
+            if (recur_fit && sane32 && P.tex_ok && (inside || P.tex_ok == 2)) {
+                const float a0 = (float)(-half) + xf_of, b0 = (float)(-half) + yf_of;
+                const float w0 = fast_ex2(-((Aq * a0 + 2.0f * Bq * b0) * a0 + Cq * b0 * b0));
+                const float r0 = fast_ex2(-(Aq * (2.0f * a0 + 1.0f) + 2.0f * Bq * b0));
+                const float rb = fast_ex2(-(Cq * (2.0f * b0 + 1.0f) + 2.0f * Bq * a0));
+                const float cA = fast_ex2(-2.0f * Aq), cB = fast_ex2(-2.0f * Bq), cC = fast_ex2(-2.0f * Cq);
+                const int tx0 = xi - half, ty0 = yi - half;
+                switch (half) {
+                case 1: gauss_taps_tex<1>(P.tex, tx0, ty0, w0, r0, rb, cA, cB, cC, val, wgt); break;
+                case 2: gauss_taps_tex<2>(P.tex, tx0, ty0, w0, r0, rb, cA, cB, cC, val, wgt); break;
+                case 3: gauss_taps_tex<3>(P.tex, tx0, ty0, w0, r0, rb, cA, cB, cC, val, wgt); break;
+                case 4: gauss_taps_tex<4>(P.tex, tx0, ty0, w0, r0, rb, cA, cB, cC, val, wgt); break;
+                case 5: gauss_taps_tex<5>(P.tex, tx0, ty0, w0, r0, rb, cA, cB, cC, val, wgt); break;
+                default: gauss_taps_tex<6>(P.tex, tx0, ty0, w0, r0, rb, cA, cB, cC, val, wgt); break;
+                }
+                tex_done = true;
+            }
+        }
+        if (tex_done) {
+        } else if (recur_ok) {
             // exp(-(xf^2+yf^2)) = exp2(-(A a^2 + 2B ab + C b^2)): three exp2 per pixel row set, two
             // multiplies per tap
             const float a0 = (float)(-half) + xf_of, b0 = (float)(-half) + yf_of;
@@ -962,6 +988,7 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
     }
 
     JacParams P;
+    P.tex = 0; P.tex_ok = 0;
     P.src = s.data; P.dst = d.data; P.src_pitch = s.pitch; P.dst_pitch = d.pitch;
     P.src_plane = s.plane_pitch; P.dst_plane = d.plane_pitch; P.n_planes = (int)s.n_planes;
     P.src_h = (int)s.h; P.src_w = (int)s.w; P.src_x0 = (int)s.x0; P.src_y0 = (int)s.y0;
@@ -1045,9 +1072,18 @@ int jacobian_dispatch(const tfm_jacobian_args *a, cudaStream_t st)
         else return TFM_EUNSUPPORTED;
         name = "k_jacobian<exact64>";
     } else if (a->precision == TFM_PREC_FAST32) {
-        if (s.dtype == TFM_F32 && d.dtype == TFM_F32) TFM_JLAUNCH(Fast, float, float, float);
-        else return TFM_EUNSUPPORTED;
-        name = "k_jacobian<fast32>";
+        if (s.dtype != TFM_F32 || d.dtype != TFM_F32) return TFM_EUNSUPPORTED;
+        // Gaussian taps through the texture unit where a pitch-linear texture can be laid over the WHOLE source
+        // (one plane, geometry within the 2-D texture limits); tuning bits 4096 / 32768 keep plain loads
+        int tex_slot = -1;
+        if (a->filter == TFM_FILT_GAUSSIAN && !(a->tuning & (4096 | 32768)) && s.n_planes == 1 && s.x0 == 0 && s.y0 == 0 &&
+            s.full_h == s.h && s.full_w == s.w && s.w <= 131072 && s.h <= 65000 && (s.pitch % 32) == 0 &&
+            (reinterpret_cast<uintptr_t>(s.data) % 512) == 0 &&
+            get_texture(s.data, (int)s.w, (int)s.h, s.pitch, &P.tex, &tex_slot))
+            P.tex_ok = (a->bound_x == TFM_B_TRUNCATE && a->bound_y == TFM_B_TRUNCATE) ? 2 : 1;
+        TFM_JLAUNCH(Fast, float, float, float);
+        texture_used(tex_slot, st);
+        name = P.tex_ok ? "k_jacobian<fast32,tex>" : "k_jacobian<fast32>";
     } else {
         return TFM_EVALUE;
     }

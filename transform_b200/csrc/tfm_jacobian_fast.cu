@@ -170,111 +170,7 @@ __device__ __forceinline__ void gauss_taps_cp(const float *__restrict__ p0, int 
 // ncu, 8192^2 polar unwrap (profiles/r2_k2.md): the 8-byte LDG form is bound by the LSU data pipe --
 // 3.5 wavefronts per request (one per cache line the 32 footprints of a warp touch), 2 taps per lane;
 // the texture path returns 4 taps per lane per request through its own filter/write-back stage.
-// Weight state of the texture form, all of it packed over the two columns of a gather (lane .x = column c,
-// lane .y = column c + 1), so that no instruction is spent moving scalars in and out of register pairs (ncu
-// source view of the first form: 54 MOV-type instructions per pixel, 11 % of the kernel):
-//   W  = (w(c, b), w(c+1, b))               weights of the current column pair
-//   R  = (r(c)^2 cA, r(c+1)^2 cA)           W(c+2) = W(c) R(c),  R(c+2) = R(c) cA^4
-//   RB = (rb(0, b), rb(1, b))               first pair of the next row: W(0, b+1) = W(0, b) RB(b),
-//                                           RB(b+1) = RB(b) cC;  R(0, b+1) = R(0, b) cB^2
-struct TexRows {
-    float2 W, R, RB;
-    float cA4, cB2, cC;
-};
-
-__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
-
-// one row pair (r, r+1) of the texture form, texels already fetched; BOTH = false: row r+1 lies outside
-// the square.  Leaves the row state on row r + 2.
-template <int HALF, bool BOTH>
-__device__ __forceinline__ void tex_row_pair(const float4 (&g)[HALF + 1], TexRows &S,
-                                             float2 &val2, float2 &wgt2, float &val, float &wgt)
-{
-    constexpr int NP = HALF + 1;
-    const float2 CA4 = bc2(S.cA4), CB2 = bc2(S.cB2), CC = bc2(S.cC);
-    float2 Wa = S.W, Ra = S.R;
-    float2 Wb = __fmul2_rn(S.W, S.RB), Rb = __fmul2_rn(S.R, CB2);
-    if (BOTH) {
-        const float2 RB1 = __fmul2_rn(S.RB, CC);
-        S.W = __fmul2_rn(Wb, RB1);
-        S.R = __fmul2_rn(Rb, CB2);
-        S.RB = __fmul2_rn(RB1, CC);
-    }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        // gather order: x = (c, r+1), y = (c+1, r+1), z = (c+1, r), w = (c, r)
-        if (i < HALF) {
-            val2 = __ffma2_rn(make_float2(g[i].w, g[i].z), Wa, val2);
-            wgt2 = __fadd2_rn(wgt2, Wa);
-            Wa = __fmul2_rn(Wa, Ra);
-            if (i + 1 < HALF) Ra = __fmul2_rn(Ra, CA4);
-            if (BOTH) {
-                val2 = __ffma2_rn(make_float2(g[i].x, g[i].y), Wb, val2);
-                wgt2 = __fadd2_rn(wgt2, Wb);
-                Wb = __fmul2_rn(Wb, Rb);
-                if (i + 1 < HALF) Rb = __fmul2_rn(Rb, CA4);
-            }
-        } else {                                             // last pair: column N is outside the square
-            val = fmaf(g[i].w, Wa.x, val);
-            wgt += Wa.x;
-            if (BOTH) {
-                val = fmaf(g[i].x, Wb.x, val);
-                wgt += Wb.x;
-            }
-        }
-    }
-}
-
-// The texture unit answers after several hundred cycles and a warp consumes its texels in order: what
-// hides the latency is the number of fetches in flight.  ncu on the first form (fetch, use, fetch, ...,
-// 2-3 in flight): 56 % of the stall samples on the first FFMA2 after a fetch.  Here the fetches of the
-// WHOLE footprint (HALF <= 2: 4 or 9 TLD4, 16 or 36 registers) or of a whole row pair (HALF + 1 TLD4) are
-// issued before the first weight is formed.
-template <int HALF>
-__device__ __forceinline__ void gauss_taps_tex(cudaTextureObject_t tex, int xs, int ys, float w0, float r0, float rb,
-                                               float cA, float cB, float cC, float &val, float &wgt)
-{
-    constexpr int NP = HALF + 1;
-    const float fx0 = (float)(xs + 1);
-    float fy = (float)(ys + 1);
-    float2 val2 = make_float2(0.0f, 0.0f), wgt2 = make_float2(0.0f, 0.0f);
-    TexRows S;
-    if constexpr (HALF <= 2) {
-        float4 g[NP][NP];
-#pragma unroll
-        for (int j = 0; j < NP; ++j)
-#pragma unroll
-            for (int i = 0; i < NP; ++i)
-                g[j][i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy + (float)(2 * j), 0);
-        const float cA2 = cA * cA, r02 = r0 * r0;
-        S.W = __fmul2_rn(bc2(w0), make_float2(1.0f, r0));
-        S.R = __fmul2_rn(bc2(r02), make_float2(cA, cA * cA2));
-        S.RB = __fmul2_rn(bc2(rb), make_float2(1.0f, cB));
-        S.cA4 = cA2 * cA2; S.cB2 = cB * cB; S.cC = cC;
-#pragma unroll
-        for (int j = 0; j < HALF; ++j) tex_row_pair<HALF, true>(g[j], S, val2, wgt2, val, wgt);
-        tex_row_pair<HALF, false>(g[HALF], S, val2, wgt2, val, wgt);
-    } else {
-        float4 g[NP];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
-        const float cA2 = cA * cA, r02 = r0 * r0;
-        S.W = __fmul2_rn(bc2(w0), make_float2(1.0f, r0));
-        S.R = __fmul2_rn(bc2(r02), make_float2(cA, cA * cA2));
-        S.RB = __fmul2_rn(bc2(rb), make_float2(1.0f, cB));
-        S.cA4 = cA2 * cA2; S.cB2 = cB * cB; S.cC = cC;
-#pragma unroll 1
-        for (int j = 0; j < HALF; ++j) {
-            fy += 2.0f;
-            tex_row_pair<HALF, true>(g, S, val2, wgt2, val, wgt);
-#pragma unroll
-            for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
-        }
-        tex_row_pair<HALF, false>(g, S, val2, wgt2, val, wgt);
-    }
-    val += val2.x + val2.y;
-    wgt += wgt2.x + wgt2.y;
-}
+// (TexRows, tex_row_pair, gauss_taps_tex: tfm_jacobian_common.cuh -- the general kernel of tfm_jacobian.cu uses them too)
 
 template <int TM>
 __device__ __forceinline__ void gauss_taps_any(cudaTextureObject_t tex, int xs, int ys, int half, const float *p0, int pe, bool first_out,
