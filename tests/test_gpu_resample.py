@@ -437,3 +437,38 @@ def test_antialias_switch_through_resample(tfm, oracle):
     assert not np.allclose(on, want)
     with pytest.raises(TypeError):
         tr.resample(src, method='Gaussian', antialias=False, bogus=1)
+
+
+def test_repeated_device_calls_reuse_their_plan(tfm):
+    """Repeated device-to-device calls reuse the argument block of the first call (_engine._PLANS).  The reuse
+    must be invisible: changing the transform's parameters, the tensors or any option produces the result of a
+    fresh call; a hit gives the bits of the first call."""
+    import torch
+    from transform_b200 import _engine
+    n = 257
+    g = torch.Generator(device="cuda").manual_seed(9)
+    src = torch.rand((n, n), generator=g, device="cuda", dtype=torch.float32)
+    out = torch.empty_like(src)
+    tr = tfm.Composition([tfm.Scale(1.3, dim=2), tfm.Rotation(30, unit='deg'), tfm.Offset([-n / 2.0, -n / 2.0])])
+    _engine._PLANS.clear()
+    for method in ("linear", "Gaussian"):
+        first = tr.resample(src, method=method, precision="fp32", out=out).clone()
+        nplans = len(_engine._PLANS)
+        assert nplans >= 1
+        again = tr.resample(src, method=method, precision="fp32", out=out)
+        assert again is out and torch.equal(again, first) and len(_engine._PLANS) == nplans       # a hit
+        # the source changes in place: same plan, new result
+        src2 = src.clone()
+        src.mul_(0.5)
+        half = tr.resample(src, method=method, precision="fp32", out=out).clone()
+        assert len(_engine._PLANS) == nplans
+        assert torch.allclose(half, 0.5 * first, rtol=1e-6, atol=1e-7)
+        src.copy_(src2)
+        # another option, another tensor, mutated parameters: each a fresh call with the right answer
+        other = tr.resample(src, method=method, precision="fp32", out=out, bound='e').clone()
+        assert torch.equal(other, tr.resample(src.clone(), method=method, precision="fp32", bound='e'))
+        tr.params['list'][1].params['matrix'][0, 1] *= 1.5        # in-place edit of a member's matrix
+        edited = tr.resample(src, method=method, precision="fp32", out=out).clone()
+        fresh = tr.resample(src.clone(), method=method, precision="fp32")
+        assert torch.equal(edited, fresh) and not torch.equal(edited, first)
+        tr.params['list'][1].params['matrix'][0, 1] /= 1.5
