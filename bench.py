@@ -254,6 +254,10 @@ def extra_configs(t, torch, np, timed):
         ms = timed(lambda: trx.resample(src8, method="linear", precision="fp32", out=dst8), reps=10)
         out["linear_%s_8192_fp32_ms" % name] = ms
         out["linear_%s_8192_fp32_roofline_frac" % name] = ALG_BYTES / (ms * 1e-3) / 1e9 / peak
+        if name in ("rot5", "shift"):
+            ms = timed(lambda: trx.resample(src8, method="cubic", precision="fp32", out=dst8), reps=10)
+            out["cubic_%s_8192_fp32_ms" % name] = ms
+            out["cubic_%s_8192_fp32_roofline_frac" % name] = ALG_BYTES / (ms * 1e-3) / 1e9 / peak
     # anti-aliased down-scaling (the constant-Jacobian kernel) and the reference's windowed input-plane filters
     trd = t.Composition([t.Offset([n8 / 2.0 + 0.3, n8 / 2.0 - 0.2]), t.Scale([0.6, 0.7]), t.Rotation(25, unit="deg"),
                          t.Offset([-n8 / 2.0, -n8 / 2.0])])

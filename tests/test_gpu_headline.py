@@ -125,6 +125,37 @@ def test_linear_fp32_full_coverage_maps(tfm, oracle, case):
             assert torch.equal(out, ref), (case, tuning, k)
 
 
+@pytest.mark.parametrize("case", ["shift", "rot5", "rot45", "scale0p8"])
+def test_cubic_fp32_full_coverage_maps(tfm, oracle, case):
+    """interpND's cubic method (helpers.pyx:741-789) at 8192^2 on maps that cover the source: the cubic
+    instantiation of the persistent TMA pipeline (default) and the load/store kernel (tuning bit 16) against the
+    oracle on sampled rows (2e-5: sixteen fp32 taps, overshoot up to 1.3x the data range) and against each other
+    bit for bit -- same coordinates, same floor/fraction, same Hermite order."""
+    from transform_b200 import _lib
+    import torch
+    n = 8192
+    src = frame(n, 11)
+    tr = {"shift": tfm.Offset([3.25, -7.5]),
+          "rot5": tfm.Wrap(tfm.Rotation(5, unit='deg'), tfm.Offset([-n / 2.0, -n / 2.0])),
+          "rot45": tfm.Wrap(tfm.Rotation(45, unit='deg'), tfm.Offset([-n / 2.0, -n / 2.0])),
+          "scale0p8": tfm.Scale(0.8, dim=2)}[case]
+    rows = sample_rows(n, 48)
+    want = oracle_rows(oracle, to_oracle(tr), src.cpu().numpy(), rows, method='cubic')
+    out = tr.resample(src, method='cubic', precision='fp32')
+    assert _lib.last_kernel() == "k_resample_pipe<affine,cubic>", (case, _lib.last_kernel())
+    err, emax, emed = err_stats(out[rows].cpu().numpy(), want)
+    assert emax <= 2e-5, (case, emax, emed)
+    ref = tr.resample(src, method='cubic', precision='fp32', tuning=16)
+    assert _lib.last_kernel() == "k_resample<trunc,affine>", _lib.last_kernel()
+    assert torch.equal(out, ref), (case, float((out - ref).abs().max()))
+    # a ragged output grid (not a multiple of the 64 x 32 tile) and a smaller frame
+    m = 1000
+    small = src[:m, :1024].contiguous()
+    a = tr.resample(small, method='cubic', precision='fp32', shape=(m - 7, 1024 - 13))
+    b = tr.resample(small, method='cubic', precision='fp32', shape=(m - 7, 1024 - 13), tuning=16)
+    assert torch.equal(a, b), case
+
+
 def test_nearest_fp32_config2(tfm, oracle):
     """BASELINE config 2, nearest: indices bit-exact.  In the fast path the host pre-composes the
     affine chain, which can move a coordinate by an ulp: a mismatch is legal only where the

@@ -657,6 +657,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 
 // out-of-line: the 8 pixels of one consumer thread straight from global memory (never taken unless the
 // box arithmetic of host and device disagree)
+template <int CUBIC>
 static __device__ __noinline__ void pipe_redo_row(const ResampleParams &P, double Xd, double rx, double ry, float *drow, int X)
 {
     for (int k = 0; k < 8; ++k) {
@@ -666,6 +667,14 @@ static __device__ __noinline__ void pipe_redo_row(const ResampleParams &P, doubl
         float fx, fy;
         floor_frac_fast(fma(P.aff[0], Xj, rx), ix, fx);
         floor_frac_fast(fma(P.aff[2], Xj, ry), iy, fy);
+        if (CUBIC) {
+            float rows[4];
+            for (int t = 0; t < 4; ++t)
+                rows[t] = hermite_fast(tap_trunc<float, float>(P, P.src, ix - 1, iy - 1 + t), tap_trunc<float, float>(P, P.src, ix, iy - 1 + t),
+                                       tap_trunc<float, float>(P, P.src, ix + 1, iy - 1 + t), tap_trunc<float, float>(P, P.src, ix + 2, iy - 1 + t), fx);
+            drow[8 * k] = hermite_fast(rows[0], rows[1], rows[2], rows[3], fy);
+            continue;
+        }
         const float v00 = tap_trunc<float, float>(P, P.src, ix, iy), v01 = tap_trunc<float, float>(P, P.src, ix + 1, iy);
         const float v10 = tap_trunc<float, float>(P, P.src, ix, iy + 1), v11 = tap_trunc<float, float>(P, P.src, ix + 1, iy + 1);
         const float top = fmaf(fx, v01 - v00, v00);
@@ -686,7 +695,9 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
     }
 }
 
-template <int DUMMY = 0>
+// CUBIC = 1: the 4 x 4 Hermite taps of interpND's cubic method (helpers.pyx:741-789, fast-mode arithmetic of
+// k_resample: hermite_fast along x, then along y) from the same staged boxes, one texel wider on every side.
+template <int CUBIC = 0>
 __global__ void __launch_bounds__(PIPE_THREADS)
 k_resample_pipe(const __grid_constant__ ResampleParams P, const __grid_constant__ CUtensorMap tmap,
                 const __grid_constant__ PipeParams B)
@@ -729,7 +740,7 @@ k_resample_pipe(const __grid_constant__ ResampleParams P, const __grid_constant_
             const double xlo = cx0 + fmin((PIPE_TW - 1.0) * P.aff[0], 0.0) + fmin((PIPE_TH - 1.0) * P.aff[1], 0.0);
             const double ylo = cy0 + fmin((PIPE_TW - 1.0) * P.aff[2], 0.0) + fmin((PIPE_TH - 1.0) * P.aff[3], 0.0);
             // the box must start on a 16-byte boundary of the innermost axis: round down to a multiple of 4
-            const int bx0 = ((int)floor(xlo) - 1) & ~3, by0 = (int)floor(ylo) - 1;     // |coordinate| < 2.5e8: host-proven
+            const int bx0 = ((int)floor(xlo) - 1 - CUBIC) & ~3, by0 = (int)floor(ylo) - 1 - CUBIC;   // |coordinate| < 2.5e8: host-proven
             // box position inside the staged rectangle (the whole image: src_x0 = src_y0 = 0)
             const int tx0 = bx0 - P.src_x0, ty0 = by0 - P.src_y0;
             const bool empty = tx0 >= P.src_w || ty0 >= P.src_h || tx0 + B.bw <= 0 || ty0 + B.bh <= 0;
@@ -790,6 +801,18 @@ k_resample_pipe(const __grid_constant__ ResampleParams P, const __grid_constant_
                     // the host sized the box so that every tap of the tile lies inside it; should rounding ever
                     // disagree, the tap index is neutralised here and the thread redoes its pixels from global
                     // memory below
+                    if (CUBIC) {
+                        // taps lx - 1 .. lx + 2, ly - 1 .. ly + 2 must lie inside the box
+                        const bool out = (lx - 1u) >= (unsigned)(bw - 3) || (ly - 1u) >= (unsigned)(B.bh - 3);
+                        bad = bad || out;
+                        const float *tp = tile + (out ? 0 : (int)((ly - 1u) * (unsigned)bw + (lx - 1u)));
+                        float rows[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            rows[t] = hermite_fast(tp[t * bw], tp[t * bw + 1], tp[t * bw + 2], tp[t * bw + 3], fx);
+                        r[j] = hermite_fast(rows[0], rows[1], rows[2], rows[3], fy);
+                        continue;
+                    }
                     const bool out = lx >= (unsigned)(bw - 1) || ly >= (unsigned)(B.bh - 1);
                     bad = bad || out;
                     const float *tp = tile + (out ? 0 : (int)(ly * (unsigned)bw + lx));
@@ -807,7 +830,7 @@ k_resample_pipe(const __grid_constant__ ResampleParams P, const __grid_constant_
                     if (X + 32 * h + 8 * j < P.dst_w) d[8 * j] = r[j];
             }
         }
-        if (bad && row_in) pipe_redo_row(P, Xd, rx, ry, drow, X);
+        if (bad && row_in) pipe_redo_row<CUBIC>(P, Xd, rx, ry, drow, X);
         // this warp is done with stage s: one arrival per consumer warp releases it to the producer
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_empty[s])) : "memory");
@@ -991,6 +1014,9 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         cudaTextureObject_t tex = 0;
         int tex_slot = -1;
         const bool multi = s.n_planes > 1;
+        // the TMA pipeline also serves the cubic method (4 x 4 taps from the same staged boxes); it needs no texture
+        const bool cubic_pipe = !generic && a->method == TFM_CUBIC && s.dtype == TFM_F32 && d.dtype == TFM_F32 &&
+                                a->fillvalue == 0.0 && s.n_planes == 1 && !(a->tuning & (16 | 128 | 256));
         const bool tex_ok = !generic && a->method == TFM_LINEAR && s.dtype == TFM_F32 && d.dtype == TFM_F32 &&
                             a->fillvalue == 0.0 && !(a->tuning & 16) &&
                             (!multi || ((s.plane_pitch % 512) == 0 && s.n_planes <= 192 && !(a->tuning & (128 | 256 | 8192)))) &&
@@ -1029,16 +1055,18 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
             }
         }
         // persistent multi-stage TMA pipeline: same conditions
-        if (!tma_done && tex_ok && !multi && aff && P.aff_bounded && (s.pitch % 16) == 0 && !(a->tuning & (128 | 16 | 256)) &&
+        if (!tma_done && (tex_ok || cubic_pipe) && !multi && aff && P.aff_bounded && (s.pitch % 16) == 0 && !(a->tuning & (128 | 16 | 256)) &&
             ((a->tuning & 8192) || affine_coverage(P.aff, d, s) >= TFM_PIPE_COVERAGE)) {
+            const int cub = cubic_pipe ? 1 : 0;
             const double ex = (PIPE_TW - 1) * fabs(P.aff[0]) + (PIPE_TH - 1) * fabs(P.aff[1]);
             const double ey = (PIPE_TW - 1) * fabs(P.aff[2]) + (PIPE_TH - 1) * fabs(P.aff[3]);
             if (ex < 240.0 && ey < 240.0) {
                 PipeParams B;
                 // +1 low margin, +2 for floor/+1 tap, +2 slack (the 2^-23 quantisation of floor_frac_fast can round
                 // a coordinate up to the next integer), +3 for the aligned start; multiple of 4
-                B.bw = (((int)ceil(ex) + 8) + 3) & ~3;
-                B.bh = (int)ceil(ey) + 5;
+                // cubic: one more texel on every side
+                B.bw = (((int)ceil(ex) + 8 + 2 * cub) + 3) & ~3;
+                B.bh = (int)ceil(ey) + 5 + 2 * cub;
                 B.stage_bytes = (B.bw * B.bh * 4 + 127) & ~127;
                 B.tiles_x = (P.dst_w + PIPE_TW - 1) / PIPE_TW;
                 B.tiles_y = (P.dst_h + PIPE_TH - 1) / PIPE_TH;
@@ -1054,20 +1082,22 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
                         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
                     }
                     cudaError_t ea = cudaSuccess;
+                    const void *kfn = cub ? (const void *)k_resample_pipe<1> : (const void *)k_resample_pipe<0>;
                     if (smem > 48 * 1024)
-                        ea = cudaFuncSetAttribute(k_resample_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        ea = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     int per_sm = 0;
                     if (ea == cudaSuccess)
-                        ea = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_pipe<0>, PIPE_THREADS, smem);
+                        ea = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, PIPE_THREADS, smem);
                     if (ea == cudaSuccess && per_sm > 0) {
                         long long g = (long long)sm_count * per_sm;
                         const long long nt = (long long)B.tiles_x * B.tiles_y;
                         if (g > nt) g = nt;
                         B.step_x = (int)(g % B.tiles_x);
                         B.step_y = (int)(g / B.tiles_x);
-                        k_resample_pipe<0><<<(unsigned)g, PIPE_THREADS, smem, st>>>(P, tm, B);
+                        if (cub) k_resample_pipe<1><<<(unsigned)g, PIPE_THREADS, smem, st>>>(P, tm, B);
+                        else k_resample_pipe<0><<<(unsigned)g, PIPE_THREADS, smem, st>>>(P, tm, B);
                         count_launch();
-                        name = "k_resample_pipe<affine>";
+                        name = cub ? "k_resample_pipe<affine,cubic>" : "k_resample_pipe<affine>";
                         e = cudaGetLastError();
                         tma_done = true;
                     } else {
