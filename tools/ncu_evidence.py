@@ -98,6 +98,16 @@ def main():
             f.write("| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n")
             for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
                 f.write("| `%s` | %d | %.1f | %.1f | %.1f%% |\n" % (k[:110], len(v), sum(v), sum(v) / len(v), 100 * sum(v) / total))
+            # the timed step of bench.py is two launches: the linear kernel of the named chain and the Jacobian kernel
+            lin = [v for k, v in agg.items() if "k_resample_tex4<tfm::Fast, 1, 0, 0>" in k]
+            jac = [v for k, v in agg.items() if "k_jac_gauss_polar_rows_pair" in k]
+            if lin and jac:
+                ml, mj = sum(lin[0]) / len(lin[0]), sum(jac[0]) / len(jac[0])
+                f.write("\nThe timed step is one launch of each of `k_resample_tex4<Fast, 1, 0, 0>` (mean %.1f us) and "
+                        "`k_jac_gauss_polar_rows_pair` (mean %.1f us): the Jacobian kernel's share of the step is %.1f %% here; "
+                        "the bench line's live `roofline.share_of_step` must agree (the other launches of the list are the "
+                        "parity-mode step, the end-to-end legs and the A/B variants of the breakdown).\n"
+                        % (ml, mj, 100 * mj / (ml + mj)))
     print(json.dumps(traffic, indent=1))
 
 

@@ -3,7 +3,7 @@
 
     python tools/prof_all.py <case>
 
-cases: linear_shift linear_named linear_rot45 nearest cubic hann lanczos linear_polar linear_parity
+cases: linear_shift linear_named linear_rot45 nearest cubic cubic_shift cubic_ldg hann lanczos linear_polar linear_parity
        jacobian_polar jacobian_polar_rows jacobian_polar_single jacobian_constj jacobian_fd jacobian_parity jacobian_hanning
        wcs_batch wcs_single apply_affine apply_radial apply_nd fits_m32 fits_i16"""
 import sys
@@ -35,6 +35,8 @@ if case.startswith(("linear", "nearest", "cubic", "hann", "lanczos", "jacobian")
             src, method="linear", precision="fp32", out=f32),
         "nearest": lambda: named.resample(src, method="nearest", precision="fp32", out=f32),
         "cubic": lambda: named.resample(src, method="cubic", precision="fp32", out=f32),
+        "cubic_shift": lambda: t.Offset([3.25, -7.5]).resample(src, method="cubic", precision="fp32", out=f32),
+        "cubic_ldg": lambda: named.resample(src, method="cubic", precision="fp32", out=f32, tuning=16),
         "hann": lambda: named.resample(src, method="hann", precision="fp32", out=f32),
         "lanczos": lambda: named.resample(src, method="zlanczos", precision="fp32", out=f32),
         "linear_polar": lambda: polar.resample(src, method="linear", precision="fp32", out=f32),

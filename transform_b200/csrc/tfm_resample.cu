@@ -1056,7 +1056,8 @@ int resample_dispatch(const tfm_resample_args *a, cudaStream_t st)
         }
         // persistent multi-stage TMA pipeline: same conditions
         if (!tma_done && (tex_ok || cubic_pipe) && !multi && aff && P.aff_bounded && (s.pitch % 16) == 0 && !(a->tuning & (128 | 16 | 256)) &&
-            ((a->tuning & 8192) || affine_coverage(P.aff, d, s) >= TFM_PIPE_COVERAGE)) {
+            ((a->tuning & 8192) || cubic_pipe || affine_coverage(P.aff, d, s) >= TFM_PIPE_COVERAGE)) {
+            // (cubic: the pipeline wins whatever the coverage -- named chain, 42 % covered: 0.28 vs 0.33 ms)
             const int cub = cubic_pipe ? 1 : 0;
             const double ex = (PIPE_TW - 1) * fabs(P.aff[0]) + (PIPE_TH - 1) * fabs(P.aff[1]);
             const double ey = (PIPE_TW - 1) * fabs(P.aff[2]) + (PIPE_TH - 1) * fabs(P.aff[3]);
