@@ -1,24 +1,30 @@
-// tfm_jacobian_fast.cu -- K2, fast mode (fp32), Gaussian filter: the two lean kernels.
+// tfm_jacobian_fast.cu -- K2, fast mode (fp32), Gaussian filter: the lean closed-form kernels.
 //
 // Same algorithm as tfm_jacobian.cu (interpND_grid(..., antialias=True), helpers.pyx:1293-1530:
 // jacobian() + interpND_jacobian() with the Gaussian of helpers.pyx:1734-1735), for the two map
 // families whose Jacobian has a closed form, so that nothing of the reference's finite-difference
 // machinery (coordinate halo tile, cell differences, jump flags) has to exist:
-//   k_jac_gauss_const<HALF>   the whole chain is affine: J, the quadratic form of the Gaussian, the
-//                             footprint size and the recurrence constants are launch constants
-//   k_jac_gauss_polar         the chain is one fused polar op [affine, Radial^-1, affine] (the polar /
-//                             log-polar unwrap): coordinates and J per pixel from per-tile angle tables
-// Both are chosen by the HOST (jacobian_fast_dispatch): the conditions under which the closed form
+//   k_jac_gauss_const<HALF>       the whole chain is affine: J, the quadratic form of the Gaussian, the
+//                                 footprint size and the recurrence constants are launch constants
+//   k_jac_gauss_polar             the chain is one fused polar op [affine, Radial^-1, affine] (the polar /
+//                                 log-polar unwrap): coordinates and J per pixel from per-tile angle tables
+//   k_jac_gauss_polar_rows        ... whose radius is constant along output rows: eigenvalues, padding and
+//                                 footprint size per tile ROW, a pixel only rotates the row's quadratic form
+//   k_jac_gauss_polar_rows_pair   ... and whose rows map <= ~1 source pixel apart: two output rows share each
+//                                 set of texture fetches (the kernel of bench.py's Jacobian call)
+// All are chosen by the HOST (jacobian_fast_dispatch): the conditions under which the closed form
 // stands for the reference's +-1-pixel central difference and under which jump_detect cannot flag a
-// cell are properties of the map and the output grid, not of a tile.
+// cell are properties of the map and the output grid, not of a tile -- and every row block of a sharded
+// job must take the same kernel.
 //
-// Why a second translation unit: ncu on k_jacobian<Fast> (8192^2 polar unwrap, profiles/r2_k2.md)
+// Why a second translation unit: ncu on k_jacobian<Fast> (8192^2 polar unwrap, profiles/r1_kernels.md)
 // showed 646 instructions per pixel at 61 % issue utilisation, of which only ~200 were footprint taps;
 // ~350 were per-pixel prologue (fp64 <-> fp32 conversions on the XU pipe, 64-bit index arithmetic,
 // paths for every filter / boundary / precision sharing one register allocation) and ~60 per-tile
 // tests executed by every thread.  Here every constant arrives as the type it is used in, indices
 // are 32-bit, floor/fraction is fixed point (floor_frac_fast), and pixels whose footprint is not
-// wholly inside the staged source take one out-of-line slow path.
+// wholly inside the staged source take one out-of-line slow path.  The measured history of the polar
+// unwrap at 8192^2 (2.05 -> 1.07 ms) is in DESIGN.md section 4.
 #include "tfm_jacobian_common.cuh"
 
 namespace tfm {
@@ -114,7 +120,7 @@ __device__ __forceinline__ void gauss_taps2(const float *__restrict__ p0, int pe
     wgt += wgt2.x + wgt2.y;
 }
 
-// The same footprint with 8-byte loads.  ncu on the row-pair form (profiles/r2_k2.md): the kernel is
+// The same footprint with 8-byte loads.  ncu on the row-pair form (profiles/r2_kernels.md): the kernel is
 // bound by the L1TEX sector stage, not by instruction issue -- one 4-byte tap load of a warp touches
 // ~13 sectors (32 footprints spread along an arc), and there are (2*HALF+1)^2 of them per pixel.  An
 // 8-byte load of two horizontally adjacent taps touches the SAME sectors, so loading column PAIRS
@@ -167,7 +173,7 @@ __device__ __forceinline__ void gauss_taps_cp(const float *__restrict__ p0, int 
 // reference's square (always the LAST ones) are simply not accumulated -- no selects.  Out-of-range
 // texels read 0 (border mode), which is the reference's truncated tap (weight counted, value skipped,
 // helpers.pyx:1740 vs 1793-1796): with truncate boundaries NO pixel needs the slow path.
-// ncu, 8192^2 polar unwrap (profiles/r2_k2.md): the 8-byte LDG form is bound by the LSU data pipe --
+// ncu, 8192^2 polar unwrap (profiles/r2_kernels.md): the 8-byte LDG form is bound by the LSU data pipe --
 // 3.5 wavefronts per request (one per cache line the 32 footprints of a warp touch), 2 taps per lane;
 // the texture path returns 4 taps per lane per request through its own filter/write-back stage.
 // (TexRows, tex_row_pair, gauss_taps_tex: tfm_jacobian_common.cuh -- the general kernel of tfm_jacobian.cu uses them too)

@@ -142,7 +142,7 @@ k_resample_tex(const __grid_constant__ ResampleParams P, cudaTextureObject_t tex
 // ---------------------------------------------------------------------------------------------
 // texture-gather variant, second form: 4 pixels of ONE output row per thread
 // ---------------------------------------------------------------------------------------------
-// ncu on k_resample_tex (8192^2, pure shift, profiles/r2_k1.md): 60.8 instructions per pixel at 83 %
+// ncu on k_resample_tex (8192^2, pure shift, profiles/r2_kernels.md): 60.8 instructions per pixel at 83 %
 // issue utilisation -- the kernel was issue-bound before it was texture-bound.  Of the 60.8, 16 were
 // the per-thread share of the empty-tile test, 14 the four stores (each with its own bounds check and
 // 64-bit row address), 20 the two floor/fraction extractions.  Here:
@@ -620,7 +620,7 @@ static bool get_tensor_map(const void *ptr, int w, int h, long long pitch, int b
 // persistent, multi-stage TMA pipeline (fp32 fast path, linear, affine map, truncate / fill 0)
 // ---------------------------------------------------------------------------------------------
 // The texture-gather kernels stop at the texture unit's write-back (88 % busy at 0.135 ms for a pure
-// shift, profiles/r2_k1.md): every source pixel crosses it four times.  Here HBM -> shared memory is one
+// shift, profiles/r2_kernels.md): every source pixel crosses it four times.  Here HBM -> shared memory is one
 // bulk tensor copy per tile -- the source bounding box of a 32 x 32 output tile under an affine map has
 // a size the host knows -- and the four taps are LDS.  What made the one-box-per-CTA form of round 1
 // slow (exposed TMA latency, per-CTA set-up, mbarrier polling) is removed by making the CTAs persistent:
