@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 20 --warmup 3 --no-extra > gpurun_out/g32_bench8.json 2> gpurun_out/g32_bench8.err; echo rc=$?; tail -3 gpurun_out/g32_bench8.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/g32_bench8.json 2> gpurun_out/g32_bench8.err; echo rc=$?; tail -3 gpurun_out/g32_bench8.err
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/g32_bench8.json'))
