@@ -351,3 +351,6 @@ def test_linear_nd_lowering():
         L.make_chain(comp._chain(False))                         # never inside a 2-D opcode chain
     with pytest.raises(NotImplementedError):
         t.Linear(matrix=np.eye(9))._chain(False)                 # dimension > 8
+    mixed = t.Composition([t.Scale([1., 2., 3., 4.]), rot])          # a 4-D and a 3-D member: one kernel dimension only
+    with pytest.raises(NotImplementedError):
+        mixed.apply(np.zeros((5, 4)))

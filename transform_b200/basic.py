@@ -110,6 +110,7 @@ class Linear(Transform):
         p = self.params
         d = self.idim
         op = L.TfmLinearNdOp()
+        op.reserved = d                          # host-side note of the op's dimension (the C side ignores it)
         flags = 0
         m = p['matrix'] if direction == L.FWD else p['matinv']
         if m is not None:

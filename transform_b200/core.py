@@ -80,7 +80,7 @@ class Transform:
         if dim > 2:
             # Linear-family chains of dimension 3..8 (Linear / Scale / Offset / Rotation from axis pairs or Euler
             # angles, basic.py:141-176, 338-506): the K3-ND kernel
-            if not all(isinstance(o, L.TfmLinearNdOp) for o in ops):
+            if not all(isinstance(o, L.TfmLinearNdOp) and o.reserved == dim for o in ops):
                 raise NotImplementedError("transform_b200: beyond 2-D only Linear-family transforms of one "
                                           "dimension are on the GPU path")
             if not ops:
