@@ -299,3 +299,35 @@ def test_hann_window_and_flux_match_reference_svdpyx(tfm, oracle):
             fast = tr.resample(src.astype(np.float32), method='W', bound='e', shape=want.shape, pad_pow=64,
                                jump_detect=0, phot=phot, precision='fp32')
             assert float(np.abs(fast - want).max()) <= 1e-5 * max(1.0, float(np.abs(want).max())), (case, phot)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_row_pair_kernel_ragged_shapes(tfm, oracle, seed):
+    """The row-pair form of the analytic polar kernel (two output rows per set of texture fetches) on ragged
+    output grids -- odd heights, widths that are not a multiple of the tile, grids smaller than one tile row --
+    clockwise and counter-clockwise, with and without phot='flux': against the oracle (fp32 tolerance of the
+    Jacobian method, outliers bounded in number and size) and against the one-pixel form of the same kernel
+    (tuning bit 524288; 2e-5: same taps and weights, another summation order)."""
+    import torch
+    from transform_b200 import _lib
+    rng = np.random.default_rng(500 + seed)
+    sh, sw = int(rng.integers(160, 400)), 8 * int(rng.integers(24, 60))       # 32-byte pitch: the texture path
+    ny, nx = int(rng.integers(3, 300)), int(rng.integers(700, 1500))          # angular step^2 < 1e-4 needs nx > 628
+    src = rng.random((sh, sw)).astype(np.float32)
+    c = [sw / 2.0 + rng.uniform(-3, 3), sh / 2.0 + rng.uniform(-3, 3)]
+    # one output row = 0.62 .. 0.95 source pixels of radius (rows beyond the image are part of the test)
+    tr = tfm.Composition([tfm.Scale([nx / (2 * np.pi), rng.uniform(1.05, 1.6)]),
+                          tfm.Radial(origin=c, ccw=bool(seed & 1))])
+    dsrc = torch.from_numpy(src).cuda()
+    for phot in ("radiance", "flux"):
+        got = tr.resample(dsrc, method='G', precision='fp32', shape=(ny, nx), phot=phot)
+        assert _lib.last_kernel() == "k_jacobian<fast32,analytic-polar-rows,tex,row-pairs>", _lib.last_kernel()
+        one = tr.resample(dsrc, method='G', precision='fp32', shape=(ny, nx), phot=phot, tuning=524288)
+        assert _lib.last_kernel() == "k_jacobian<fast32,analytic-polar-rows,tex>", _lib.last_kernel()
+        scale = max(1.0, float(one.abs().max()))
+        assert float((got - one).abs().max()) <= 2e-5 * scale, (seed, phot, float((got - one).abs().max()))
+        want = oracle.resample_jacobian(to_oracle(tr), src, method='g', shape=(ny, nx), phot=phot,
+                                        max_reg=max(2, 2 * int(np.ceil(0.25 * max(sh, sw)))))
+        err = np.abs(got.cpu().numpy() - want) / scale
+        assert np.median(err) < 2e-5 and (err > 5e-4).sum() <= max(3, err.size // 200) and err.max() <= 0.3, \
+            (seed, phot, float(err.max()), int((err > 5e-4).sum()))
