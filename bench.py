@@ -70,24 +70,65 @@ def config(n_gpus, extra=None):
 # clocks sampler (nvidia-smi polled while the timed region runs)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """One streaming `nvidia-smi -lms 20` process for the duration of the timed region."""
+    """SM clock and throttle reasons of one GPU while the timed region runs: NVML polled from a thread every
+    ~2 ms (a 20-step timed region lasts ~25 ms: `nvidia-smi -lms` delivers one or two samples in that time);
+    falls back to one streaming `nvidia-smi -lms 20` process when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []                       # (sm_mhz, sm_max_mhz, set of reasons, time)
+        self.window = [None, None]              # only samples taken inside the timed region count
         self.proc = None
         self.thread = None
+        self.stop = threading.Event()
+        self.source = None
+
+    def _nvml_loop(self, nv, handle, sm_max):
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        while not self.stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.samples.append((float(mhz), float(sm_max), {nm for b, nm in bits if mask & b}, time.perf_counter()))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _pump(self):
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             if len(f) >= 6:
-                self.samples.append(f)
+                try:
+                    self.samples.append((float(f[0]), float(f[1]),
+                                         {nm for nm, v in zip(self.NAMES, f[2:6]) if v.lower().startswith("active")},
+                                         time.perf_counter()))
+                except ValueError:
+                    continue
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            sm_max = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle, sm_max), daemon=True)
+            self.thread.start()
+            self.source = "nvml, 2 ms"
+            return self
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -96,37 +137,42 @@ class ClockSampler:
             self.thread.start()
             time.sleep(0.3)                       # let the sampler come up before the timed region
             self.samples.clear()
+            self.source = "nvidia-smi -lms 20"
         except Exception:
             self.proc = None
         return self
 
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
-            if self.thread is not None:
-                self.thread.join(timeout=5)
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+
+    def begin(self):
+        self.window[0] = time.perf_counter()
+
+    def end(self):
+        self.window[1] = time.perf_counter()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-            except (ValueError, IndexError):
-                continue
-            for nm, v in zip(names, s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+        t0, t1 = self.window
+        if t0 is not None and t1 is not None:
+            inside = [s for s in self.samples if t0 <= s[3] <= t1]
+            if inside:                          # (the nvidia-smi fallback may deliver nothing inside a short region)
+                self.samples = inside
+        sm = sorted(s[0] for s in self.samples)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        reasons = set()
+        for s in self.samples:
+            reasons |= s[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": sorted(reasons),
+                "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -437,11 +483,13 @@ def gpu_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
+        clk.begin()
         e0.record()
         for k in range(args.steps):
             step(ev=evs[k])
         e1.record()
         barrier()
+        clk.end()
     ms_total = e0.elapsed_time(e1)
     launches = L.launch_count() - launches0
     ms_lin = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / args.steps
