@@ -46,9 +46,8 @@ N_IMG = 8192
 METRIC = "output Mpix/s, resample linear+jacobian 8192^2"
 UNIT = "Mpix/s"
 ALG_BYTES = 2 * N_IMG * N_IMG * 4            # fp32 out + fp32 in, each once
-CPU_KIND = {"linear": "reference (the reference's own compiled interpND from oracle/_ref, fed by a port of "
-                      "Composition.invert that calls np.matmul on [...,2,1] stacks exactly as basic.py:150-152; the "
-                      "reference's .py files cannot travel to the GPU box)",
+CPU_KIND = {"linear": "reference (the reference's own Composition.invert and interpND: core.py, basic.py and helpers.pyx "
+                      "compiled from the files where they lie into oracle/_ref, which travels to the GPU box)",
             "jacobian": "port (C restatement, bit-identical to the reference's own code built with the repairs of "
                         "oracle/build_ref_repaired.py and ~30x faster per core than it)"}
 
@@ -208,7 +207,10 @@ def cpu_rows(arm, seconds_per_leg):
 
 def cpu_kind(arm):
     k = dict(CPU_KIND)
-    if arm.kind_lin != "reference":
+    if arm.kind_lin == "reference-interp":
+        k["linear"] = ("reference interpND (oracle/_ref/helpers*.so) fed by a port of Composition.invert that calls "
+                       "np.matmul on [...,2,1] stacks exactly as basic.py:150-152 (oracle/_ref/core*.so is missing)")
+    elif arm.kind_lin != "reference":
         k["linear"] = "port (oracle/_ref/helpers*.so is missing: the NumPy restatement of interpND)"
     return k
 

@@ -3,10 +3,11 @@ imported by bench.py's `cpu_baseline` leg and its `--impl reference` arm, never 
 
 What is timed, per workload:
   linear   : Transform.resample(method='linear') as the reference executes it --
-             pixel grid (core.py:574-578) -> Composition._reverse with np.matmul on [...,2,1]
-             stacks (basic.py:160-176; oracle_np with MATVEC_IMPL='numpy') -> interpND.
-             interpND is the REFERENCE'S OWN compiled module (oracle/_ref/helpers*.so, built
-             from /root/reference/transform/helpers.pyx) when present, else the oracle port.
+             pixel grid (core.py:574-578) -> Composition.invert (core.py:1556-1559 over basic.py:160-176,
+             np.matmul on [...,2,1] stacks) -> interpND.  All three are the REFERENCE'S OWN code when
+             oracle/_ref holds its compiled modules (core / basic / helpers, built by oracle/build_ref.py from
+             the files where they lie under /root/reference): impl kind 'reference'.  With only helpers*.so
+             the chain is oracle_np's port with MATVEC_IMPL='numpy' ('reference-interp'); with nothing, the port.
   jacobian : the repaired interpND_grid pipeline (oracle_np.resample_jacobian: NumPy jacobian()
              + the C restatement of the compiled interpND_jacobian loop).  The reference's own
              version cannot run, so this leg is always the port.
@@ -58,10 +59,17 @@ def _linear_rows(args):
     y0, y1 = args
     src, chain, n = _G["src"], _G["chain"], _G["n"]
     interp = _G["interp"]
+    ref_chain = _G.get("ref_chain")
     out = None
     for ya in range(y0, y1, 64):
         yb = min(y1, ya + 64)
-        coords = chain.reverse(o.pixel_grid(n, n, ya, yb))
+        if ref_chain is not None:
+            # the reference's own code end to end: its integer pixel grid (core.py:574-578, rows ya:yb of it), its
+            # Composition.invert (core.py:298-315, 1556-1559 -> basic.py:160-176), its compiled interpND
+            grid = np.mgrid[0:n, ya:yb].transpose()
+            coords = ref_chain.invert(grid)
+        else:
+            coords = chain.reverse(o.pixel_grid(n, n, ya, yb))
         blk = interp(src, coords, method="l", bound="t")
         out = blk if out is None else out
     return float(out[0, 0])
@@ -99,10 +107,20 @@ def _setup(kind, n, src):
     impl = "port"
     if kind == "linear":
         _G["chain"] = affine_chain(n)
+        _G.pop("ref_chain", None)
         if have_ref_helpers():
             import ref_import
             _G["interp"] = ref_import.load_ref_helpers().interpND
-            impl = "reference"
+            impl = "reference-interp"
+            try:
+                # the reference's own Transform classes, compiled from core.py / basic.py into oracle/_ref
+                ref = ref_import.load_reference_compiled()
+                _G["ref_chain"] = ref.Composition([ref.Scale(1.3, dim=2), ref.Rotation(30, unit="deg"),
+                                                   ref.Offset([-n / 2.0, -n / 2.0])])
+                _G["interp"] = ref.interpND
+                impl = "reference"
+            except Exception:
+                pass
         else:
             _G["interp"] = o.interpND
         return _linear_rows, impl

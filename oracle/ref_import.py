@@ -67,6 +67,57 @@ def load_ref_svd():
     return _load_ext("SVD", "tfm_ref_SVD")
 
 
+def load_reference_compiled():
+    """The reference's own classes (core.py, basic.py) and helpers, all as compiled by oracle/build_ref.py into
+    oracle/_ref -- importable on the GPU box, where /root/reference does not exist.  Returns a module-like
+    namespace `transform` with the reference's public names (Composition, Scale, Rotation, Offset, Radial, ...)."""
+    if "transform" in sys.modules and getattr(sys.modules["transform"], "_tfm_is_reference", False):
+        return sys.modules["transform"]
+    import types
+    try:
+        import astropy  # noqa: F401
+    except ImportError:
+        sys.path.insert(0, os.path.join(HERE, "astropy_stub"))
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    for name in ("helpers", "core", "basic"):
+        if not os.path.exists(os.path.join(_REFDIR, name + suffix)):
+            raise ImportError("oracle/_ref/%s%s not built (run oracle/build_ref.py where the reference is present)" % (name, suffix))
+    pkg = types.ModuleType("transform")
+    pkg.__path__ = []                          # a package with no directory: its members are registered below
+    pkg.__package__ = "transform"
+    saved = {k: sys.modules.get(k) for k in ("transform", "transform.helpers", "transform.core", "transform.basic")}
+    try:
+        sys.modules["transform"] = pkg
+        helpers = load_ref_helpers()
+        sys.modules["transform.helpers"] = helpers
+        pkg.helpers = helpers
+        for name in ("core", "basic"):
+            full = "transform." + name
+            path = os.path.join(_REFDIR, name + suffix)
+            loader = importlib.machinery.ExtensionFileLoader(full, path)
+            spec = importlib.util.spec_from_file_location(full, path, loader=loader)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[full] = mod
+            loader.exec_module(mod)
+            setattr(pkg, name, mod)
+            for k, v in vars(mod).items():
+                if not k.startswith("_"):
+                    setattr(pkg, k, v)
+        for k, v in vars(helpers).items():
+            if not k.startswith("_") and not hasattr(pkg, k):
+                setattr(pkg, k, v)
+    except Exception:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        raise
+    pkg._tfm_is_reference = True
+    pkg._tfm_compiled = True
+    return pkg
+
+
 def load_reference():
     """Import the unmodified reference package; container only."""
     if not have_reference_sources():

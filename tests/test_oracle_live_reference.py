@@ -201,3 +201,53 @@ def test_apply_linear_3d_random_cases(ref, oracle, seed):
             got = oracle.apply(q, v.copy(), invert=invert)
             assert got.shape == want.shape
             assert np.array_equal(got, want), (seed, name, invert, np.abs(got - want).max())
+
+
+def test_compiled_reference_classes_equal_the_source_import(tmp_path):
+    """oracle/build_ref.py also compiles the reference's core.py / basic.py (where they lie) into oracle/_ref, so
+    that bench.py's reference arm can drive the reference's OWN Composition.invert on the GPU box, where
+    /root/reference does not exist.  The compiled classes must be the reference: same results, bit for bit, as
+    the source import (run in a subprocess: both register a package named `transform`)."""
+    import subprocess
+    import ref_import
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+import ref_import
+ref = ref_import.%s()
+n = 96
+src = np.random.default_rng(0).random((n, n)).astype(np.float32)
+v = np.random.default_rng(1).random((200, 3)) * 60
+aff = ref.Composition([ref.Scale(1.3, dim=2), ref.Rotation(30, unit="deg"), ref.Offset([-n / 2.0, -n / 2.0])])
+rad = ref.Composition([ref.Scale([n / (2 * np.pi), 1.4]), ref.Radial(origin=[47.5, 47.5])])
+out = {"lin": aff.resample(src, method="linear"), "cub": aff.resample(src, method="cubic"),
+       "near": rad.resample(src, method="nearest"), "inv": rad.invert(v), "fwd": aff.apply(v),
+       "pin": ref.Cubicpin(idim=2, odim=2, strength=0.1, length=30.0).apply(v[:, :2]),
+       "rot3": ref.Rotation(euler=np.array([10.0, 20.0, 30.0]), unit="deg").apply(v)}
+np.savez(%r, **out)
+print(str(aff))
+'''
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    res = {}
+    for which in ("load_reference_compiled", "load_reference"):
+        path = str(tmp_path / (which + ".npz"))
+        r = subprocess.run([sys.executable, "-c", code % (here, which, path)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[which] = (np.load(path), r.stdout.strip())
+    a, b = res["load_reference_compiled"], res["load_reference"]
+    assert a[1] == b[1]                                           # the stringifier protocol too
+    for k in b[0].files:
+        assert np.array_equal(a[0][k], b[0][k], equal_nan=True), k
+
+
+def test_cpu_arm_linear_leg_is_the_reference():
+    """The linear leg of the CPU baseline runs the reference's own classes when oracle/_ref holds them."""
+    import cpu_baseline as cb
+    arm = cb.CpuArm(512, 2, seed=0)
+    try:
+        assert arm.kind_lin == "reference", arm.kind_lin
+        t, px = arm.linear(64)
+        assert px == 64 * 512 and t > 0
+    finally:
+        arm.close()
