@@ -240,3 +240,22 @@ def test_linear_nd_random_chains(tfm, oracle, dim):
     out = tr.apply(vt)
     assert out.is_cuda and out.dtype == torch.float64
     assert np.array_equal(out.cpu().numpy(), tr.apply(vt.cpu().numpy()))
+
+
+def test_linear_nd_matches_reference_golden(tfm):
+    """K3-ND against golden vectors of the unmodified reference (tests/golden/linear_nd_golden.npz): bit for bit in
+    3-D (Rotation from Euler angles / axis pairs, Scale o Rotation o Offset, a general matrix with offsets; forward
+    and inverted; pass-through components), 1e-13 relative for the 4-D chain."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_linear_nd_golden as mk
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "linear_nd_golden.npz"))
+    a = {k[4:]: G[k] for k in G.files if k.startswith("arg/")}
+    for key in [k for k in G.files if not k.startswith("arg/")]:
+        case, vn, d = key.split("/")
+        got = mk.build(tfm, case, a).apply(a[vn].copy(), invert=(d == "inv"))
+        if case == "chain4":
+            assert np.allclose(got, G[key], rtol=1e-13, atol=1e-12), key
+        else:
+            assert np.array_equal(got, G[key]), key

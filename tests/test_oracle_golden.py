@@ -5,6 +5,7 @@ indices; affine chains); <= 1e-12 relative for chains through libm transcendenta
 last bit may differ between machines."""
 import importlib.util
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -235,3 +236,28 @@ def test_antialiased_path_matches_repaired_reference(oracle, key):
     name, kw = _aa_kwargs(key)
     got = oracle.interp_grid_jacobian(GOLD["src64"], GOLD["aa/%s/coords" % name], **kw)
     assert np.array_equal(got, GOLD[key], equal_nan=True), key
+
+
+def _linear_nd_cases():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_linear_nd_golden as mk
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "linear_nd_golden.npz"))
+    a = {k[4:]: G[k] for k in G.files if k.startswith("arg/")}
+    return mk, G, a
+
+
+def test_linear_nd_oracle_matches_reference_golden(oracle):
+    """Linear-family transforms in 3-D / 4-D (basic.py:141-176, 338-506) through Transform.apply: the oracle against
+    golden vectors of the unmodified reference (tests/golden/make_linear_nd_golden.py) -- bit for bit in 3-D, where the
+    row order of np.matmul is pinned; 4 ulp of sum |m_ik v_k| for the 4-D chain."""
+    import transform_b200 as t
+    from conftest import to_oracle
+    mk, G, a = _linear_nd_cases()
+    for key in [k for k in G.files if not k.startswith("arg/")]:
+        case, vn, d = key.split("/")
+        q = to_oracle(mk.build(t, case, a))
+        got = oracle.apply(q, a[vn].copy(), invert=(d == "inv"))
+        if case == "chain4":
+            assert np.allclose(got, G[key], rtol=1e-13, atol=1e-12), key
+        else:
+            assert np.array_equal(got, G[key]), key
