@@ -165,3 +165,17 @@ def test_sharded_resampler_world2(case):
     assert r["bytes"][1] > 0
     if case[0] == "polar":
         assert r["split"] == "cols", r                            # wedges beat annuli
+
+
+@pytest.mark.parametrize("case", [("affine", "linear", "cols", 2, (61, 77)), ("polar", "Gaussian", "auto", 2, None)])
+def test_sharded_resampler_world3(case):
+    """Three ranks: ragged rectangles (the last rank's part is narrower, 77 and 128 columns do not divide by 3), the
+    same exactness and staging checks as with two."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29800 + (os.getpid() % 90)
+    mp.spawn(_worker_sr, args=(3, port, case, ret), nprocs=3, join=True)
+    r = dict(ret)
+    assert all(r["ok%d" % k] for k in range(3)), r
+    assert all(r["nan%d" % k] == 0 for k in range(3)), r
+    assert r["bytes"][0] > 0 and r["bytes"][1] > 0
