@@ -31,6 +31,9 @@ def have_reference_sources():
 def _load_ext(modname, fullname):
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
     path = os.path.join(_REFDIR, modname + suffix)
+    if not os.path.exists(path) and modname in ("helpers", "SVD", "core", "basic") and have_reference_sources():
+        import build_ref                       # a fresh checkout in the authoring container: build on first use
+        build_ref.build()
     if not os.path.exists(path):
         raise ImportError("oracle/_ref/%s%s not built (run oracle/build_ref.py)" % (modname, suffix))
     loader = importlib.machinery.ExtensionFileLoader(modname, path)
@@ -79,6 +82,9 @@ def load_reference_compiled():
     except ImportError:
         sys.path.insert(0, os.path.join(HERE, "astropy_stub"))
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    if have_reference_sources() and not all(os.path.exists(os.path.join(_REFDIR, nm + suffix)) for nm in ("helpers", "core", "basic")):
+        import build_ref
+        build_ref.build()
     for name in ("helpers", "core", "basic"):
         if not os.path.exists(os.path.join(_REFDIR, name + suffix)):
             raise ImportError("oracle/_ref/%s%s not built (run oracle/build_ref.py where the reference is present)" % (name, suffix))
