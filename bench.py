@@ -276,6 +276,18 @@ def traffic_for(kernel_key):
         return None
 
 
+def ncu_for(kernel_key):
+    """Pipe utilisations and hit rates of the same committed capture (what bounds a kernel that is not HBM-bound)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            v = json.load(f).get(kernel_key)
+        return {k: v[k] for k in ("issue_active_pct", "tex_writeback_pct", "l1tex_throughput_pct", "dram_throughput_pct",
+                                  "l1_hit_pct", "l2_hit_pct", "source") if k in v}
+    except Exception:
+        return None
+
+
 def extra_configs(t, torch, np, timed):
     """BASELINE configs 2, 4 and 5 at full size (untimed for `value`; reported in `breakdown`)."""
     out = {}
@@ -649,6 +661,7 @@ def gpu_arm(args):
                              "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                              "traffic": traffic_for("jacobian" if dom_is_jac else "linear"),
+                             "ncu": ncu_for("jacobian" if dom_is_jac else "linear"),
                              "algorithmic_bytes_per_launch": ALG_BYTES,
                              "share_of_step": dom_ms / (ms_lin + ms_jac),
                              "note": "the Jacobian kernel is bound by instruction issue and the texture pipe, not by "
@@ -657,6 +670,7 @@ def gpu_arm(args):
                                  "map": "pure shift (every source pixel is read once: DRAM traffic = algorithmic bytes)",
                                  "kernel": kernels["linear_shift"], "ms": ms_shift, "achieved": shift_gbs,
                                  "frac": shift_gbs / peak, "traffic": traffic_for("linear_shift"),
+                                 "ncu": ncu_for("linear_shift"),
                                  "named_chain": {"kernel": kernels["linear"], "ms": ms_lin, "achieved": lin_gbs,
                                                  "frac_of_algorithmic_bytes": lin_gbs / peak,
                                                  "traffic": traffic_for("linear"),

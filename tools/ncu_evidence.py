@@ -74,8 +74,20 @@ def main():
                 wr = to_bytes(r[h.index("dram__bytes_write.sum")], units[h.index("dram__bytes_write.sum")])
                 f.write("\nDRAM traffic per launch: %.1f MB read + %.1f MB write = %.1f MB\n\n" % (rd / 1e6, wr / 1e6, (rd + wr) / 1e6))
                 if case in TRAFFIC_KEY:
-                    traffic[TRAFFIC_KEY[case]] = {"dram_bytes": rd + wr, "kernel": name[:110], "case": case,
-                                                  "source": "profiles/%s_kernels.md" % rnd}
+                    def pct(k):
+                        try:
+                            return float(r[h.index(k)].replace(",", ""))
+                        except (ValueError, IndexError):
+                            return None
+                    traffic[TRAFFIC_KEY[case]] = {
+                        "dram_bytes": rd + wr, "kernel": name[:110], "case": case,
+                        "source": "profiles/%s_kernels.md" % rnd,
+                        # what bounds the kernel when it is not HBM (same capture)
+                        "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "tex_writeback_pct": pct("l1tex__tex_writeback_active.avg.pct_of_peak_sustained_elapsed"),
+                        "l1tex_throughput_pct": pct("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+                        "dram_throughput_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                        "l1_hit_pct": pct("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": pct("lts__t_sector_hit_rate.pct")}
     with open(os.path.join(here, "profiles", "traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1)
     if launches:
