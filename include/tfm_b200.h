@@ -64,8 +64,12 @@ typedef enum tfm_op_kind {
                               reference: it is how interpND(source, index, ...) / interpND_grid
                               (helpers.pyx:379, 1293), which take a precomputed coordinate array,
                               run through the same kernels.  Must be the first element of a chain. */
-    TFM_OP_PIN = 5         /* per-axis pincushion family: Quadpin (basic.py:846-1017), Cubicpin
+    TFM_OP_PIN = 5,        /* per-axis pincushion family: Quadpin (basic.py:846-1017), Cubicpin
                               (1020-1175), Poly / Quarticpin (1178-1462, forward only) */
+    TFM_OP_SIP = 6         /* SIP polynomial distortion of a FITS header (CTYPE '...-SIP'): the
+                              pix2foc stage of astropy's all_pix2world / all_world2pix
+                              (core.py:1727, 1742).  Precedes a TFM_OP_WCS in the pixel -> world
+                              direction and follows it in the world -> pixel direction. */
 } tfm_op_kind;
 
 typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
@@ -104,11 +108,26 @@ typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
 #define TFM_WCS_PROJ_SIN 4   /* orthographic (xi=eta=0)  eq. 59-60 */
 #define TFM_WCS_PROJ_ARC 5   /* zenithal equidistant     eq. 67-68 */
 #define TFM_WCS_PROJ_ZEA 6   /* zenithal equal-area      eq. 69-70 */
-#define TFM_WCS_PROJ_CEA 7   /* cylindrical equal-area (lambda=1) eq. 80-81 */
+#define TFM_WCS_PROJ_CEA 7   /* cylindrical equal-area    eq. 80-81; lambda = p[21] (PV2_1; 0 reads as the default 1) */
 #define TFM_WCS_PROJ_MER 8   /* Mercator                 eq. 85-86 */
 #define TFM_WCS_PROJ_SFL 9   /* Sanson-Flamsteed         eq. 87-88 */
 #define TFM_WCS_PROJ_AIT 10  /* Hammer-Aitoff            eq. 108-110 */
 #define TFM_WCS_PROJ_MAX 10
+
+/* TFM_OP_SIP  (Shupe et al. 2005; PARITY UNPINNED like the spherical projections: astropy is absent)
+ *   p[0] the BIT PATTERN of a device pointer to float64 coef[2][TFM_SIP_DIM][TFM_SIP_DIM]:
+ *        coef[0][p][q] = A_p_q, coef[1][p][q] = B_p_q (absent keywords are 0); the table must stay
+ *        allocated while launches that use it are in flight
+ *   p[1] A_ORDER   p[2] B_ORDER  (0..TFM_SIP_MAX_ORDER)     p[3..4] CRPIX (1-based, FITS)
+ *   fwd: u = x + 1 - CRPIX1, v = y + 1 - CRPIX2;  x += sum A_p_q u^p v^q,  y += sum B_p_q u^p v^q
+ *   rev: the fixed-point iteration of all_world2pix, pix <- pix0 - f(pix), which uses the FORWARD
+ *        polynomials only (AP_p_q / BP_p_q are ignored there too); iterated per point until the
+ *        step is below 1e-12 pixel or TFM_SIP_MAXITER evaluations (astropy's maxiter = 20; its
+ *        stopping rule is 1e-4 pixel on the worst point of the batch, so its result depends on the
+ *        batch -- this one does not, and agrees with it to within that tolerance) */
+#define TFM_SIP_MAX_ORDER 9
+#define TFM_SIP_DIM 10
+#define TFM_SIP_MAXITER 20
 
 /* TFM_OP_INDEX
  *   p[0] the BIT PATTERN of a device pointer to float64 index[ny][nx][2] (dense, (X,Y) last axis)

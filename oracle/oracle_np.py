@@ -26,8 +26,8 @@ Pinning (see tests/test_oracle_golden.py and tests/golden/make_golden.py):
     x boundaries t/e/p x jump detection on/off x oblur, golden fixtures `aa/*` and live random sweeps.
     R9 (mirror boundary) and R12 (non-square jump_detect) are the two deliberate departures and are
     outside that pin; it is also cross-checked against SVD.pyx::map_coordinates on affine maps.
-  * PARITY UNPINNED: the spherical projections (TAN, CAR, STG, SIN, ARC, ZEA, CEA, MER, SFL, AIT) --
-    astropy/wcslib is absent and unpinned (setup.py:27-32) -- and phot='flux' (documented at
+  * PARITY UNPINNED: the spherical projections (TAN, CAR, STG, SIN, ARC, ZEA, CEA, MER, SFL, AIT) and
+    the SIP distortion (class SIP) -- astropy/wcslib is absent and unpinned (setup.py:27-32) -- and phot='flux' (documented at
     core.py:521-533 but not implemented by the reference).
 
 Arithmetic conventions that the CUDA path reproduces bit-for-bit in its fp64-exact mode:
@@ -981,7 +981,7 @@ def _jacobian_rows(coords, ya, yb, ny, jump_thresh):
 _R0 = 180.0 / np.pi
 
 
-def _deproject(proj, x, y):
+def _deproject(proj, x, y, lam=1.0):
     """Projection-plane (x, y) [deg] -> native (phi, theta) [deg]; Calabretta & Greisen 2002, in the
     paper's own angle form (the CUDA path works on unit vectors: the two derivations cross-check)."""
     with np.errstate(all="ignore"):
@@ -1002,7 +1002,7 @@ def _deproject(proj, x, y):
         if proj == "CAR":
             return x, y                                                      # eq. 83-84
         if proj == "CEA":
-            return x, np.degrees(np.arcsin(y / _R0))                         # eq. 81, lambda = 1
+            return x, np.degrees(np.arcsin(lam * y / _R0))                   # eq. 81 (lambda = PV2_1, default 1)
         if proj == "MER":
             return x, 2.0 * np.degrees(np.arctan(np.exp(y / _R0))) - 90.0    # eq. 86
         if proj == "SFL":
@@ -1020,7 +1020,7 @@ def _deproject(proj, x, y):
     raise ValueError(proj)
 
 
-def _project(proj, phi, theta):
+def _project(proj, phi, theta, lam=1.0):
     """Native (phi, theta) [deg] -> projection-plane (x, y) [deg]."""
     ph, th = np.radians(phi), np.radians(theta)
     with np.errstate(all="ignore"):
@@ -1039,7 +1039,7 @@ def _project(proj, phi, theta):
         if proj == "CAR":
             return phi, theta
         if proj == "CEA":
-            return phi, _R0 * np.sin(th)
+            return phi, _R0 * np.sin(th) / lam                               # eq. 80
         if proj == "MER":
             return phi, np.where(np.abs(theta) < 90, _R0 * np.log(np.tan(np.radians(90.0 + theta) / 2.0)), np.nan)
         if proj == "SFL":
@@ -1062,9 +1062,10 @@ class WCS(Op):
     Deliberately written with the explicit Euler-angle formulas per point -- not with the 3x3
     rotation matrix the CUDA path uses -- so that the two derivations check each other.
     proj: None (linear axes), 'TAN', 'CAR', or one of STG SIN ARC ZEA CEA MER SFL AIT (default
-    projection parameters).  cd = CDELT_i * PC_ij."""
+    projection parameters, except CEA's lambda = PV2_1).  cd = CDELT_i * PC_ij."""
 
-    def __init__(self, crpix, cd, crval, proj=None, lonpole=None, latpole=None):
+    def __init__(self, crpix, cd, crval, proj=None, lonpole=None, latpole=None, cea_lambda=1.0):
+        self.cea_lambda = float(cea_lambda)
         self.crpix = np.asarray(crpix, dtype=np.float64)
         self.cd = np.asarray(cd, dtype=np.float64)
         self.cdinv = np.linalg.inv(self.cd)
@@ -1107,7 +1108,7 @@ class WCS(Op):
             out[..., 0] = ix + self.crval[0]
             out[..., 1] = iy + self.crval[1]
             return out
-        phi, theta = _deproject(self.proj, ix, iy)
+        phi, theta = _deproject(self.proj, ix, iy, self.cea_lambda)
         ph, th, dp = np.radians(phi - self.phi_p), np.radians(theta), np.radians(self.delta_p)
         # eq. (2); the latitude is taken with atan2(z, hypot(x, y)) instead of asin(z) -- the
         # well-conditioned form wcslib switches to near the poles (sphx2s)
@@ -1136,10 +1137,73 @@ class WCS(Op):
             theta = np.degrees(np.arctan2(zz, np.hypot(xx, yy)))
             phi = np.where(phi > 180.0, phi - 360.0, phi)
             phi = np.where(phi <= -180.0, phi + 360.0, phi)
-            ix, iy = _project(self.proj, phi, theta)
+            ix, iy = _project(self.proj, phi, theta, self.cea_lambda)
         px = self.cdinv[0, 0] * ix + self.cdinv[0, 1] * iy
         py = self.cdinv[1, 0] * ix + self.cdinv[1, 1] * iy
         out = np.empty(v.shape, dtype=np.float64)
         out[..., 0] = (px + self.crpix[0]) - 1.0
         out[..., 1] = (py + self.crpix[1]) - 1.0
         return out
+
+
+class SIP(Op):
+    """SIP polynomial distortion (Shupe et al. 2005, "The SIP convention for representing distortion
+    in FITS image headers"): the pix2foc stage of astropy's all_pix2world / all_world2pix, which
+    core.py:1727 and 1742 call.  PARITY UNPINNED (astropy absent from /root/reference and from
+    this image); restated from the convention and from the documented algorithm of all_world2pix.
+
+    a[p, q] = A_p_q, b[p, q] = B_p_q (terms with p + q above the order are ignored), crpix 1-based.
+      forward (pixel, origin 0 -> distortion-corrected pixel):  u = x + 1 - CRPIX1, v = y + 1 - CRPIX2,
+              x' = x + sum A_p_q u^p v^q,  y' = y + sum B_p_q u^p v^q
+      reverse: all_world2pix's fixed-point iteration pix <- pix0 - f(pix) on the FORWARD polynomials
+              (AP_/BP_ are not used), run to convergence per point (step < 1e-12 pixel, at most 20
+              evaluations = astropy's maxiter).  astropy stops when the worst point of the batch
+              moves less than 1e-4 pixel, so it agrees with this only to that tolerance.
+    Written as an explicit sum of powers -- the CUDA op is a nested Horner form -- so that the
+    two cross-check."""
+
+    MAXITER = 20
+
+    def __init__(self, crpix, a, b):
+        self.crpix = np.asarray(crpix, dtype=np.float64)
+        self.a = np.asarray(a, dtype=np.float64)
+        self.b = np.asarray(b, dtype=np.float64)
+
+    @staticmethod
+    def _poly(c, u, v):
+        m = c.shape[0] - 1
+        out = np.zeros(np.broadcast(u, v).shape, dtype=np.float64)
+        for p in range(m + 1):
+            for q in range(m + 1 - p):
+                if c[p, q] != 0.0:
+                    out = out + c[p, q] * np.power(u, p) * np.power(v, q)
+        return out
+
+    def _f(self, v):
+        uu = (v[..., 0] + 1.0) - self.crpix[0]
+        vv = (v[..., 1] + 1.0) - self.crpix[1]
+        return np.stack((self._poly(self.a, uu, vv), self._poly(self.b, uu, vv)), axis=-1)
+
+    def forward(self, v):
+        v = np.asarray(v, dtype=np.float64)
+        return v + self._f(v)
+
+    def reverse(self, v):
+        pix0 = np.asarray(v, dtype=np.float64)
+        pix = pix0.copy()
+        active = np.ones(pix.shape[:-1], dtype=bool)
+        with np.errstate(all="ignore"):
+            for _ in range(self.MAXITER):
+                new = pix0 - self._f(pix)
+                d2 = np.sum((new - pix) ** 2, axis=-1)
+                pix = np.where(active[..., None], new, pix)
+                active = active & (d2 >= 1e-24)
+                if not active.any():
+                    break
+        return pix
+
+
+def WCS_SIP(wcs, sip):
+    """all_pix2world / all_world2pix of a header with a SIP distortion: forward = SIP then the core
+    WCS, reverse = core WCS then the SIP inversion."""
+    return Composition([wcs, sip])

@@ -326,6 +326,8 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             y = A::add(iy, op.p[11]);
             return;
         }
+        if constexpr (LVL >= 2)                            // CEA: y = r0 sin(theta) / lambda (eq. 80), PV2_1 in p[21]
+            if (proj == TFM_WCS_PROJ_CEA && op.p[21] != 0.0) iy *= op.p[21];
         double mx, my, mz;
         wcs_deproject<LVL>(proj, ix, iy, mx, my, mz);      // un-normalised: only angles are taken below
         const double lx = R[0] * mx + R[1] * my + R[2] * mz;
@@ -350,11 +352,49 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             const double my = R[1] * lx + R[4] * ly + R[7] * lz;
             const double mz = R[2] * lx + R[5] * ly + R[8] * lz;
             wcs_project<LVL>(proj, mx, my, mz, ix, iy);    // NaN on the far side of the sky (TAN, SIN)
+            if constexpr (LVL >= 2)
+                if (proj == TFM_WCS_PROJ_CEA && op.p[21] != 0.0) iy /= op.p[21];
         }
         double px = A::add(A::mul(op.p[6], ix), A::mul(op.p[7], iy));
         double py = A::add(A::mul(op.p[8], ix), A::mul(op.p[9], iy));
         x = A::sub(A::add(px, op.p[0]), 1.0);
         y = A::sub(A::add(py, op.p[1]), 1.0);
+    }
+}
+
+// ---- SIP distortion (Shupe et al. 2005): the pix2foc stage of all_pix2world / all_world2pix ----
+// PARITY UNPINNED (astropy absent).  f(u, v) = sum_{p+q <= order} C_p_q u^p v^q as a Horner form in u of
+// Horner forms in v; the coefficient table is read through the read-only path at warp-uniform addresses.
+__device__ __forceinline__ double sip_poly(const double *c, int order, double u, double v)
+{
+    double s = 0.0;
+    for (int p = order; p >= 0; --p) {
+        const double *row = c + p * TFM_SIP_DIM;
+        double t = 0.0;
+        for (int q = order - p; q >= 0; --q) t = fma(t, v, __ldg(row + q));
+        s = fma(s, u, t);
+    }
+    return s;
+}
+
+__device__ __forceinline__ void op_sip(const tfm_op &op, double &x, double &y)
+{
+    const double *coef = reinterpret_cast<const double *>(__double_as_longlong(op.p[0]));
+    const int ao = (int)op.p[1], bo = (int)op.p[2];
+    const double *ca = coef, *cb = coef + TFM_SIP_DIM * TFM_SIP_DIM;
+    if (op.dir == TFM_FWD) {            // pixel -> focal plane (still in pixel units, origin 0)
+        const double u = (x + 1.0) - op.p[3], v = (y + 1.0) - op.p[4];
+        x += sip_poly(ca, ao, u, v);
+        y += sip_poly(cb, bo, u, v);
+    } else {                            // focal plane -> pixel: pix <- pix0 - f(pix), as all_world2pix iterates
+        const double x0 = x, y0 = y;
+        for (int k = 0; k < TFM_SIP_MAXITER; ++k) {
+            const double u = (x + 1.0) - op.p[3], v = (y + 1.0) - op.p[4];
+            const double nx = x0 - sip_poly(ca, ao, u, v), ny = y0 - sip_poly(cb, bo, u, v);
+            const double dx = nx - x, dy = ny - y;
+            x = nx; y = ny;
+            if (!(dx * dx + dy * dy >= 1e-24)) break;       // converged (or NaN: nothing left to refine)
+        }
     }
 }
 
@@ -499,13 +539,13 @@ __device__ __forceinline__ void wcs_car_tan_sep(const WcsCarCoef &k, const doubl
 
 // "Heavy" ops are compiled only into dedicated kernel instantiations (template parameter SPH):
 //   0  none of them        1  WCS with linear axes, TAN or CAR (+ the fused WCS pair)
-//   2  every WCS projection and the pow()-based pincushion family
+//   2  every WCS projection, the SIP distortion and the pow()-based pincushion family
 static inline int chain_sph_level(const ChainDev &ch)
 {
     int lvl = 0;
     for (int i = 0; i < ch.n; ++i) {
         const tfm_op &op = ch.ops[i];
-        if (op.kind == TFM_OP_PIN) lvl = 2;
+        if (op.kind == TFM_OP_PIN || op.kind == TFM_OP_SIP) lvl = 2;
         else if (op.kind == TFM_OP_WCS_PAIR) lvl = lvl < 1 ? 1 : lvl;
         else if (op.kind == TFM_OP_WCS) {
             const int need = ((op.flags & 0xff) > TFM_WCS_PROJ_CAR) ? 2 : 1;
@@ -681,9 +721,15 @@ static inline bool chain_ops_valid(const tfm_op *ops, int n)
 {
     for (int i = 0; i < n; ++i) {
         const tfm_op &op = ops[i];
-        if (op.kind < TFM_OP_IDENTITY || op.kind > TFM_OP_PIN) return false;
+        if (op.kind < TFM_OP_IDENTITY || op.kind > TFM_OP_SIP) return false;
         if (op.dir != TFM_FWD && op.dir != TFM_REV) return false;
         if (op.kind == TFM_OP_WCS && ((op.flags & 0xff) < 0 || (op.flags & 0xff) > TFM_WCS_PROJ_MAX)) return false;
+        if (op.kind == TFM_OP_SIP) {
+            long long bits;
+            memcpy(&bits, &op.p[0], sizeof bits);
+            if (bits == 0) return false;                    // no coefficient table
+            if (!(op.p[1] >= 0 && op.p[1] <= TFM_SIP_MAX_ORDER && op.p[2] >= 0 && op.p[2] <= TFM_SIP_MAX_ORDER)) return false;
+        }
         if (op.kind == TFM_OP_PIN) {
             const int k = op.flags & 3;
             if (k > TFM_PIN_POLY) return false;
@@ -725,6 +771,7 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
         case TFM_OP_WCS: if constexpr (SPH >= 1) op_wcs<A, SPH>(op, x, y); break;
         case TFM_OP_WCS_PAIR: if constexpr (SPH >= 1) op_wcs_pair(op, x, y); break;
         case TFM_OP_PIN: if constexpr (SPH >= 2) op_pin<A>(op, x, y); break;
+        case TFM_OP_SIP: if constexpr (SPH >= 2) op_sip(op, x, y); break;
         case TFM_OP_POLAR: op_polar(op, x, y); break;
         case TFM_OP_INDEX: op_index(op, x, y); break;
         default: break;                                     // identity
@@ -797,6 +844,12 @@ __device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N],
             if constexpr (SPH >= 2) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) op_pin<A>(op, x[k], y[k]);
+            }
+            break;
+        case TFM_OP_SIP:
+            if constexpr (SPH >= 2) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) op_sip(op, x[k], y[k]);
             }
             break;
         case TFM_OP_POLAR:

@@ -9,12 +9,13 @@ itself cites (core.py:38-42, 1655-1658):
 
   * Header       ordered, dict-like FITS header with the astropy methods core.py uses
   * read_fits    primary-HDU reader (BITPIX 8/16/32/64/-32/-64, big-endian, BSCALE/BZERO)
-  * WCSParams    CRPIX/CRVAL/CDELT + CD | PC | CROTA2 linear part (paper I) and the TAN / CAR
-                 spherical projections with LONPOLE/LATPOLE defaults (paper II); `lower()` packs
-                 them into the TFM_OP_WCS opcode evaluated by the CUDA library.
+  * WCSParams    CRPIX/CRVAL/CDELT + CD | PC | CROTA2 linear part (paper I), ten spherical
+                 projections with LONPOLE/LATPOLE defaults (paper II), CEA's lambda (PV2_1) and the
+                 SIP polynomial distortion (Shupe et al. 2005); `lower()` packs them into the
+                 TFM_OP_WCS (+ TFM_OP_SIP) opcodes evaluated by the CUDA library.
 
 PARITY: the linear part is pinned by the reference's own test (tests/test_01_core.py:160-169,
-sample.fits).  TAN / CAR are PARITY UNPINNED (no astropy/wcslib to diff against).
+sample.fits).  The spherical projections and SIP are PARITY UNPINNED (no astropy/wcslib to diff against).
 """
 import copy
 import math
@@ -290,6 +291,10 @@ class WCSParams:
         self.lonpole = None
         self.latpole = None
         self.pixel_shape = None
+        self.cea_lambda = 1.0          # PV2_1 of a CEA projection (paper II eq. 80)
+        self.sip_a = None              # SIP: (A_ORDER+1)^2 array, sip_a[p, q] = A_p_q (Shupe et al. 2005)
+        self.sip_b = None
+        self._sip_dev = {}             # (device, table bytes) -> resident coefficient table
         if header is not None:
             self._from_header(header)
 
@@ -317,13 +322,12 @@ class WCSParams:
             self.cdelt[i] = float(get('CDELT%d' % a, 1.0))
             self.ctype[i] = str(get('CTYPE%d' % a, '')).strip()
             self.cunit[i] = str(get('CUNIT%d' % a, '')).strip()
-        # projection parameters: only the defaults are on the GPU path (PV2_1 = 1 is CEA's default lambda)
+        self._read_sip(h)
         for k in h.keys():
-            if isinstance(k, str) and k.startswith('PV') and '_' in k and k[2:].replace('_', '').isdigit():
-                val = float(h[k])
-                if val != 0.0 and not (k == 'PV2_1' and val == 1.0):
-                    raise NotImplementedError("transform_b200: projection parameter %s = %r "
-                                              "(only default PVi_m values are on the GPU path)" % (k, h[k]))
+            if isinstance(k, str) and (k[:5] in ('CPDIS', 'CQDIS', 'D2IMD') or k[:4] == 'D2IM'
+                                       or (k[:2] in ('DP', 'DQ') and k[2:3].isdigit())):
+                raise NotImplementedError("transform_b200: table-lookup distortion keyword %s "
+                                          "(Paper IV / D2IM) is not on the GPU path" % k)
         has_cd = any(('CD%d_%d' % (i + 1, j + 1)) in h for i in range(naxis) for j in range(naxis))
         has_pc = any(('PC%d_%d' % (i + 1, j + 1)) in h for i in range(naxis) for j in range(naxis))
         if has_cd:
@@ -351,8 +355,124 @@ class WCSParams:
             self.lonpole = float(h['LONPOLE'])
         if 'LATPOLE' in h:
             self.latpole = float(h['LATPOLE'])
+        self._read_pv(h)               # after LONPOLE / LATPOLE: PVi_3 / PVi_4 override them
         if all(('NAXIS%d' % (i + 1)) in h for i in range(naxis)):
             self.pixel_shape = [int(h['NAXIS%d' % (i + 1)]) for i in range(naxis)]
+
+    def _read_pv(self, h):
+        """PVi_m projection parameters (paper II section 2.3 and table 13).  On the GPU path: lambda of
+        CEA (PV<lat>_1), LONPOLE / LATPOLE given as PV<lng>_3 / PV<lng>_4 (they override the
+        keywords, as in wcslib's wcsset) and explicit statements of a projection's default
+        (phi0, theta0) in PV<lng>_1 / PV<lng>_2; anything else raises."""
+        pv = {}
+        for k in h.keys():
+            if isinstance(k, str) and k.startswith('PV') and '_' in k and k[2:].replace('_', '').isdigit():
+                i, m = k[2:].split('_')
+                pv[(int(i), int(m))] = float(h[k])
+        if not pv:
+            return
+        try:
+            proj = self.projection()
+        except NotImplementedError:
+            proj = None
+        name = _PROJ_NAME.get(proj[0]) if proj is not None else None
+        lng, lat = 1, 2
+        for (i, m), val in sorted(pv.items()):
+            ok = False
+            if proj is not None and i == lng:
+                if m == 0:
+                    ok = (val == 0.0)                      # PVi_0: no offset of the fiducial point
+                elif m == 1:
+                    ok = (val == proj[3])
+                elif m == 2:
+                    ok = (val == proj[4])
+                elif m == 3:
+                    self.lonpole, ok = val, True
+                elif m == 4:
+                    self.latpole, ok = val, True
+            elif proj is not None and i == lat:
+                if name == 'CEA' and m == 1:
+                    if not (0.0 < val <= 1.0):
+                        raise ValueError("WCS: CEA needs 0 < PV2_1 <= 1, got %r" % val)
+                    self.cea_lambda, ok = val, True
+                else:
+                    ok = (val == 0.0) and name in ('TAN', 'CAR', 'STG', 'SIN', 'ARC', 'ZEA', 'MER', 'SFL', 'AIT')
+            else:
+                ok = (val == 0.0)
+            if not ok:
+                raise NotImplementedError("transform_b200: projection parameter PV%d_%d = %r is not on "
+                                          "the GPU path (CEA's lambda, LONPOLE/LATPOLE as PVi_3/PVi_4 "
+                                          "and default values are)" % (i, m, val))
+
+    def _read_sip(self, h):
+        """A_ORDER / B_ORDER / A_p_q / B_p_q (Shupe et al. 2005).  astropy applies them whenever
+        the keywords are present, with or without the '-SIP' suffix of CTYPE; AP_/BP_ (the
+        inverse polynomials) are not used by all_world2pix and are ignored here too."""
+        has_a, has_b = 'A_ORDER' in h, 'B_ORDER' in h
+        if not (has_a or has_b):
+            return
+        if not (has_a and has_b):
+            raise ValueError("WCS: Both A_ORDER and B_ORDER must be provided for a SIP distortion")
+        tabs = []
+        for L_ in ('A', 'B'):
+            m = int(h[L_ + '_ORDER'])
+            if not (0 <= m <= L.SIP_MAX_ORDER):
+                raise ValueError("WCS: %s_ORDER = %d is outside 0..%d" % (L_, m, L.SIP_MAX_ORDER))
+            t = np.zeros((m + 1, m + 1))
+            for p in range(m + 1):
+                for q in range(m + 1 - p):
+                    key = '%s_%d_%d' % (L_, p, q)
+                    if key in h:
+                        t[p, q] = float(h[key])
+            tabs.append(t)
+        self.sip_a, self.sip_b = tabs
+
+    def has_sip(self):
+        return self.sip_a is not None and self.sip_b is not None
+
+    def sip_table(self):
+        """float64 [2][SIP_DIM][SIP_DIM]: the layout TFM_OP_SIP reads (include/tfm_b200.h)."""
+        t = np.zeros((2, L.SIP_DIM, L.SIP_DIM))
+        for k, c in enumerate((self.sip_a, self.sip_b)):
+            c = np.asarray(c, dtype=np.float64)
+            if c.ndim != 2 or c.shape[0] != c.shape[1] or c.shape[0] > L.SIP_DIM:
+                raise ValueError("WCS: SIP coefficient arrays must be square, order <= %d" % L.SIP_MAX_ORDER)
+            m = c.shape[0] - 1
+            for p in range(m + 1):
+                for q in range(m + 1):
+                    if p + q <= m:
+                        t[k, p, q] = c[p, q]
+                    elif c[p, q] != 0.0:
+                        raise ValueError("WCS: SIP term %s_%d_%d exceeds the polynomial order %d"
+                                         % ('AB'[k], p, q, m))
+        return t
+
+    def _sip_op(self, direction):
+        """TFM_OP_SIP with its coefficient table resident on the current device (uploaded once per
+        device and table contents; the tensor lives as long as this object)."""
+        from . import _device as dev
+        import struct
+        torch = dev.require_cuda()
+        tab = self.sip_table()
+        key = (int(torch.cuda.current_device()), tab.tobytes())
+        t = self._sip_dev.get(key)
+        if t is None:
+            t = dev.to_device(tab, np.float64, slot="sip")
+            self._sip_dev = {k: v for k, v in self._sip_dev.items() if k[0] != key[0]}
+            self._sip_dev[key] = t
+        op = L.TfmOp()
+        op.kind, op.dir, op.flags = L.OP_SIP, direction, 0
+        op.p[0] = struct.unpack("d", struct.pack("q", int(t.data_ptr())))[0]
+        op.p[1], op.p[2] = float(np.asarray(self.sip_a).shape[0] - 1), float(np.asarray(self.sip_b).shape[0] - 1)
+        op.p[3], op.p[4] = float(self.crpix[0]), float(self.crpix[1])
+        return op
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == '_sip_dev' else copy.deepcopy(v, memo)
+        return new
 
     def copy(self):
         return copy.deepcopy(self)
@@ -457,10 +577,22 @@ class WCSParams:
             for i in range(3):
                 for j in range(3):
                     op.p[12 + 3 * i + j] = float(R[i, j])
+            if proj[0] == L.WCS_PROJ_CEA:
+                op.p[21] = float(self.cea_lambda)
+        if self.has_sip():
+            # all_pix2world: pix2foc (SIP) then the core; all_world2pix: the core, then the SIP
+            # fixed-point inversion (core.py:1727, 1742)
+            return [self._sip_op(direction), op] if direction == L.FWD else [op, self._sip_op(direction)]
         return [op]
 
-    def to_header(self):
-        """The keys astropy's WCS.to_header() emits that core.py relies on (core.py:1074, 1208-1234)."""
+    def to_header(self, relax=None):
+        """The keys astropy's WCS.to_header() emits that core.py relies on (core.py:1074, 1208-1234).
+
+        As in astropy, the default (the way core.py calls it) writes standard keywords only: the SIP
+        coefficients are left out and the '-SIP' suffix is taken off CTYPE -- so the header remap()
+        writes for a SIP template describes the undistorted frame (a property of the reference, kept).
+        relax=True writes A_ORDER / B_ORDER / A_p_q / B_p_q and keeps the suffix."""
+        do_sip = bool(relax) and self.has_sip()
         h = Header()
         h['WCSAXES'] = self.naxis
         for i in range(self.naxis):
@@ -477,11 +609,24 @@ class WCSParams:
                 h['CUNIT%d' % (i + 1)] = self.cunit[i]
         for i in range(self.naxis):
             if self.ctype[i]:
-                h['CTYPE%d' % (i + 1)] = self.ctype[i]
+                c = self.ctype[i]
+                if self.has_sip() and not do_sip and c.upper().endswith('-SIP'):
+                    c = c[:-4]
+                h['CTYPE%d' % (i + 1)] = c
         for i in range(self.naxis):
             h['CRVAL%d' % (i + 1)] = float(self.crval[i])
         if self.projection() is not None:
             _, _, phi_p = self.celestial_pole()
             h['LONPOLE'] = float(phi_p)
             h['LATPOLE'] = float(90.0 if self.latpole is None else self.latpole)
+            if self.projection()[0] == L.WCS_PROJ_CEA and self.cea_lambda != 1.0:
+                h['PV2_1'] = float(self.cea_lambda)
+        if do_sip:
+            for L_, c in (('A', np.asarray(self.sip_a)), ('B', np.asarray(self.sip_b))):
+                m = c.shape[0] - 1
+                h['%s_ORDER' % L_] = m
+                for p in range(m + 1):
+                    for q in range(m + 1 - p):
+                        if c[p, q] != 0.0:
+                            h['%s_%d_%d' % (L_, p, q)] = float(c[p, q])
         return h

@@ -199,8 +199,9 @@ class WCS(Transform):
     """Pixel (origin 0) <-> world coordinates from a FITS header (core.py:1650-1747).
 
     Where the reference calls astropy's all_pix2world / all_world2pix (core.py:1727, 1742), this
-    lowers the header to a TFM_OP_WCS opcode: linear part, plus TAN or CAR with the celestial
-    rotation when CTYPE says so."""
+    lowers the header to a TFM_OP_WCS opcode: linear part, plus one of ten spherical projections with
+    the celestial rotation when CTYPE says so, preceded (pixel -> world) or followed (world -> pixel)
+    by a TFM_OP_SIP when the header carries a SIP polynomial distortion (A_ORDER / B_ORDER ...)."""
 
     def __init__(self, dingus):
         if isinstance(dingus, DataWrapper):
