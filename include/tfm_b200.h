@@ -66,10 +66,15 @@ typedef enum tfm_op_kind {
                               run through the same kernels.  Must be the first element of a chain. */
     TFM_OP_PIN = 5,        /* per-axis pincushion family: Quadpin (basic.py:846-1017), Cubicpin
                               (1020-1175), Poly / Quarticpin (1178-1462, forward only) */
-    TFM_OP_SIP = 6         /* SIP polynomial distortion of a FITS header (CTYPE '...-SIP'): the
+    TFM_OP_SIP = 6,        /* SIP polynomial distortion of a FITS header (CTYPE '...-SIP'): the
                               pix2foc stage of astropy's all_pix2world / all_world2pix
                               (core.py:1727, 1742).  Precedes a TFM_OP_WCS in the pixel -> world
                               direction and follows it in the world -> pixel direction. */
+    TFM_OP_TPV = 7         /* TPV polynomial distortion (CTYPE '...-TPV', PV1_m / PV2_m, m = 0..39): acts on
+                              the intermediate world coordinates between the linear part of a header and
+                              its gnomonic projection -- wcslib's "sequent distortion" inside wcsp2s / wcss2p,
+                              which all_pix2world / all_world2pix call (core.py:1727, 1742).  The host lowers
+                              such a header to {WCS linear part, TPV, WCS projection part}. */
 } tfm_op_kind;
 
 typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
@@ -105,7 +110,7 @@ typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
 #define TFM_WCS_PROJ_CAR 2
 /* further projections of paper II (Calabretta & Greisen 2002), default projection parameters only */
 #define TFM_WCS_PROJ_STG 3   /* stereographic            eq. 56-57 */
-#define TFM_WCS_PROJ_SIN 4   /* orthographic (xi=eta=0)  eq. 59-60 */
+#define TFM_WCS_PROJ_SIN 4   /* orthographic              eq. 59-60; slant (xi, eta) = p[21], p[22] (PV2_1, PV2_2), eq. 61-62 */
 #define TFM_WCS_PROJ_ARC 5   /* zenithal equidistant     eq. 67-68 */
 #define TFM_WCS_PROJ_ZEA 6   /* zenithal equal-area      eq. 69-70 */
 #define TFM_WCS_PROJ_CEA 7   /* cylindrical equal-area    eq. 80-81; lambda = p[21] (PV2_1; 0 reads as the default 1) */
@@ -128,6 +133,21 @@ typedef enum tfm_dir { TFM_FWD = 0, TFM_REV = 1 } tfm_dir;
 #define TFM_SIP_MAX_ORDER 9
 #define TFM_SIP_DIM 10
 #define TFM_SIP_MAXITER 20
+
+/* TFM_OP_TPV  (the TPV convention of the FITS WCS registry, as written by SCAMP; PARITY UNPINNED)
+ *   p[0] the BIT PATTERN of a device pointer to float64 coef[2][TFM_TPV_NCOEF]: coef[0][m] = PV1_m,
+ *        coef[1][m] = PV2_m (defaults: PV1_1 = PV2_1 = 1, everything else 0)
+ *   p[1..4] inverse of the linear part [[PV1_1, PV1_2], [PV2_2, PV2_1]], row-major (the reverse direction's
+ *        quasi-Newton step)
+ *   fwd: xi' = P1(xi, eta), eta' = P2(eta, xi) with r = sqrt(xi^2 + eta^2) and
+ *        P(x, y) = c0 + c1 x + c2 y + c3 r + c4 x^2 + c5 xy + c6 y^2 + c7 x^3 + c8 x^2 y + c9 x y^2 + c10 y^3
+ *                + c11 r^3 + c12 x^4 + ... + c16 y^4 + c17 x^5 + ... + c22 y^5 + c23 r^5 + c24 x^6 + ...
+ *                + c30 y^6 + c31 x^7 + ... + c38 y^7 + c39 r^7       (degrees, like the CD matrix's output)
+ *   rev: v <- v - Minv.(T(v) - target) from v = Minv.(target - c0), per point, until the step is below
+ *        1e-13 degree or TFM_TPV_MAXITER evaluations (wcslib inverts the same map iteratively to its own
+ *        tolerance; both converge to the root) */
+#define TFM_TPV_NCOEF 40
+#define TFM_TPV_MAXITER 30
 
 /* TFM_OP_INDEX
  *   p[0] the BIT PATTERN of a device pointer to float64 index[ny][nx][2] (dense, (X,Y) last axis)

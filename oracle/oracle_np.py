@@ -27,7 +27,7 @@ Pinning (see tests/test_oracle_golden.py and tests/golden/make_golden.py):
     R9 (mirror boundary) and R12 (non-square jump_detect) are the two deliberate departures and are
     outside that pin; it is also cross-checked against SVD.pyx::map_coordinates on affine maps.
   * PARITY UNPINNED: the spherical projections (TAN, CAR, STG, SIN, ARC, ZEA, CEA, MER, SFL, AIT) and
-    the SIP distortion (class SIP) -- astropy/wcslib is absent and unpinned (setup.py:27-32) -- and phot='flux' (documented at
+    the SIP / TPV distortions (classes SIP, TPV) -- astropy/wcslib is absent and unpinned (setup.py:27-32) -- and phot='flux' (documented at
     core.py:521-533 but not implemented by the reference).
 
 Arithmetic conventions that the CUDA path reproduces bit-for-bit in its fp64-exact mode:
@@ -981,10 +981,20 @@ def _jacobian_rows(coords, ya, yb, ny, jump_thresh):
 _R0 = 180.0 / np.pi
 
 
-def _deproject(proj, x, y, lam=1.0):
+def _deproject(proj, x, y, lam=1.0, slant=(0.0, 0.0)):
     """Projection-plane (x, y) [deg] -> native (phi, theta) [deg]; Calabretta & Greisen 2002, in the
     paper's own angle form (the CUDA path works on unit vectors: the two derivations cross-check)."""
     with np.errstate(all="ignore"):
+        if proj == "SIN" and tuple(slant) != (0.0, 0.0):                     # slant orthographic, eq. 61-62
+            # xi-eta form of paper II section 5.1.5: with X = x / r0, Y = y / r0 and s = 1 - sin(theta),
+            # (xi^2 + eta^2 + 1) s^2 - 2 (X xi + Y eta + 1) s + X^2 + Y^2 = 0; the root nearer the pole
+            xi, eta = slant
+            X, Y = x / _R0, y / _R0
+            a, b, c = xi * xi + eta * eta + 1.0, X * xi + Y * eta + 1.0, X * X + Y * Y
+            s = c / (b + np.sqrt(b * b - a * c))                             # = (b - sqrt) / a; NaN beyond the limb
+            theta = 90.0 - 2.0 * np.degrees(np.arcsin(np.sqrt(s / 2.0)))     # 1 - sin(theta) = s, stable at the pole
+            phi = np.degrees(np.arctan2(X - xi * s, -(Y - eta * s)))
+            return phi, theta
         if proj in ("TAN", "STG", "SIN", "ARC", "ZEA"):                      # zenithal, eq. 14-15
             R = np.hypot(x, y)
             phi = np.where(R == 0, 0.0, np.degrees(np.arctan2(x, -y)))
@@ -1020,10 +1030,16 @@ def _deproject(proj, x, y, lam=1.0):
     raise ValueError(proj)
 
 
-def _project(proj, phi, theta, lam=1.0):
+def _project(proj, phi, theta, lam=1.0, slant=(0.0, 0.0)):
     """Native (phi, theta) [deg] -> projection-plane (x, y) [deg]."""
     ph, th = np.radians(phi), np.radians(theta)
     with np.errstate(all="ignore"):
+        if proj == "SIN" and tuple(slant) != (0.0, 0.0):                     # eq. 61-62
+            xi, eta = slant
+            vis = theta >= -np.degrees(np.arctan(xi * np.sin(ph) - eta * np.cos(ph)))   # wcslib's bounds check
+            x = _R0 * (np.cos(th) * np.sin(ph) + xi * (1.0 - np.sin(th)))
+            y = -_R0 * (np.cos(th) * np.cos(ph) - eta * (1.0 - np.sin(th)))
+            return np.where(vis, x, np.nan), np.where(vis, y, np.nan)
         if proj in ("TAN", "STG", "SIN", "ARC", "ZEA"):
             if proj == "TAN":
                 R = np.where(theta > 0, _R0 / np.tan(th), np.nan)            # eq. 54
@@ -1064,8 +1080,9 @@ class WCS(Op):
     proj: None (linear axes), 'TAN', 'CAR', or one of STG SIN ARC ZEA CEA MER SFL AIT (default
     projection parameters, except CEA's lambda = PV2_1).  cd = CDELT_i * PC_ij."""
 
-    def __init__(self, crpix, cd, crval, proj=None, lonpole=None, latpole=None, cea_lambda=1.0):
+    def __init__(self, crpix, cd, crval, proj=None, lonpole=None, latpole=None, cea_lambda=1.0, sin_slant=(0.0, 0.0)):
         self.cea_lambda = float(cea_lambda)
+        self.sin_slant = (float(sin_slant[0]), float(sin_slant[1]))
         self.crpix = np.asarray(crpix, dtype=np.float64)
         self.cd = np.asarray(cd, dtype=np.float64)
         self.cdinv = np.linalg.inv(self.cd)
@@ -1108,7 +1125,7 @@ class WCS(Op):
             out[..., 0] = ix + self.crval[0]
             out[..., 1] = iy + self.crval[1]
             return out
-        phi, theta = _deproject(self.proj, ix, iy, self.cea_lambda)
+        phi, theta = _deproject(self.proj, ix, iy, self.cea_lambda, self.sin_slant)
         ph, th, dp = np.radians(phi - self.phi_p), np.radians(theta), np.radians(self.delta_p)
         # eq. (2); the latitude is taken with atan2(z, hypot(x, y)) instead of asin(z) -- the
         # well-conditioned form wcslib switches to near the poles (sphx2s)
@@ -1137,7 +1154,7 @@ class WCS(Op):
             theta = np.degrees(np.arctan2(zz, np.hypot(xx, yy)))
             phi = np.where(phi > 180.0, phi - 360.0, phi)
             phi = np.where(phi <= -180.0, phi + 360.0, phi)
-            ix, iy = _project(self.proj, phi, theta, self.cea_lambda)
+            ix, iy = _project(self.proj, phi, theta, self.cea_lambda, self.sin_slant)
         px = self.cdinv[0, 0] * ix + self.cdinv[0, 1] * iy
         py = self.cdinv[1, 0] * ix + self.cdinv[1, 1] * iy
         out = np.empty(v.shape, dtype=np.float64)
@@ -1207,3 +1224,66 @@ def WCS_SIP(wcs, sip):
     """all_pix2world / all_world2pix of a header with a SIP distortion: forward = SIP then the core
     WCS, reverse = core WCS then the SIP inversion."""
     return Composition([wcs, sip])
+
+
+class TPV(Op):
+    """The TPV polynomial distortion ('RA---TPV' / 'DEC--TPV' headers, PV1_m / PV2_m, m = 0..39; the
+    convention of the FITS WCS registry written by SCAMP): wcslib applies it to the intermediate world
+    coordinates (xi, eta) [deg] between the linear part and the gnomonic projection, inside the wcsp2s /
+    wcss2p that astropy's all_pix2world / all_world2pix call (core.py:1727, 1742).  PARITY UNPINNED.
+
+    tab[0][m] = PV1_m, tab[1][m] = PV2_m.  With r = sqrt(xi^2 + eta^2):
+      xi'  = PV1_0 + PV1_1 xi + PV1_2 eta + PV1_3 r + PV1_4 xi^2 + PV1_5 xi eta + PV1_6 eta^2 + PV1_7 xi^3 + ...
+             + PV1_11 r^3 + ... + PV1_23 r^5 + ... + PV1_39 r^7
+      eta' = the same with the roles of xi and eta exchanged and PV2_m.
+    Written as an explicit list of (power of own axis, power of other axis, power of r) -- the CUDA op
+    accumulates each degree in Horner fashion -- so that the two cross-check.  reverse: Newton-like iteration on
+    the constant linear part, to convergence (wcslib iterates to its own tolerance on the same root)."""
+
+    TERMS = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1),
+             (2, 0, 0), (1, 1, 0), (0, 2, 0),
+             (3, 0, 0), (2, 1, 0), (1, 2, 0), (0, 3, 0), (0, 0, 3),
+             (4, 0, 0), (3, 1, 0), (2, 2, 0), (1, 3, 0), (0, 4, 0),
+             (5, 0, 0), (4, 1, 0), (3, 2, 0), (2, 3, 0), (1, 4, 0), (0, 5, 0), (0, 0, 5),
+             (6, 0, 0), (5, 1, 0), (4, 2, 0), (3, 3, 0), (2, 4, 0), (1, 5, 0), (0, 6, 0),
+             (7, 0, 0), (6, 1, 0), (5, 2, 0), (4, 3, 0), (3, 4, 0), (2, 5, 0), (1, 6, 0), (0, 7, 0), (0, 0, 7)]
+    MAXITER = 30
+
+    def __init__(self, tab):
+        self.tab = np.asarray(tab, dtype=np.float64)
+        assert self.tab.shape == (2, 40) and len(self.TERMS) == 40
+
+    def _axis(self, c, own, other):
+        r = np.hypot(own, other)
+        out = np.zeros(np.broadcast(own, other).shape)
+        for m, (a, b, k) in enumerate(self.TERMS):
+            if c[m] != 0.0:
+                out = out + c[m] * np.power(own, a) * np.power(other, b) * np.power(r, k)
+        return out
+
+    def forward(self, v):
+        v = np.asarray(v, dtype=np.float64)
+        return np.stack((self._axis(self.tab[0], v[..., 0], v[..., 1]),
+                         self._axis(self.tab[1], v[..., 1], v[..., 0])), axis=-1)
+
+    def reverse(self, v):
+        t = np.asarray(v, dtype=np.float64)
+        M = np.array([[self.tab[0, 1], self.tab[0, 2]], [self.tab[1, 2], self.tab[1, 1]]])
+        Mi = np.linalg.inv(M)
+        x = (t - np.array([self.tab[0, 0], self.tab[1, 0]])) @ Mi.T
+        active = np.ones(x.shape[:-1], dtype=bool)
+        with np.errstate(all="ignore"):
+            for _ in range(self.MAXITER):
+                step = (self.forward(x) - t) @ Mi.T
+                x = np.where(active[..., None], x - step, x)
+                active = active & (np.sum(step * step, axis=-1) >= 1e-26)
+                if not active.any():
+                    break
+        return x
+
+
+def WCS_TPV(crpix, cd, crval, tab, lonpole=None, latpole=None):
+    """A '-TPV' header: linear part -> TPV polynomial -> TAN -> celestial rotation."""
+    lin = WCS(crpix, cd, [0.0, 0.0], None)
+    prj = WCS([1.0, 1.0], np.eye(2), crval, "TAN", lonpole, latpole)
+    return Composition([prj, TPV(tab), lin])

@@ -74,8 +74,11 @@ def to_oracle(tr):
         proj = w.projection()
         from transform_b200.fitswcs import _PROJ_NAME
         code = None if proj is None else _PROJ_NAME[proj[0]]
-        core = o.WCS(w.crpix, w.linear_matrix(), w.crval, code, w.lonpole, w.latpole,
-                     cea_lambda=w.cea_lambda)
+        if w.tpv is not None:
+            core = o.WCS_TPV(w.crpix, w.linear_matrix(), w.crval, w.tpv, w.lonpole, w.latpole)
+        else:
+            core = o.WCS(w.crpix, w.linear_matrix(), w.crval, code, w.lonpole, w.latpole,
+                         cea_lambda=w.cea_lambda, sin_slant=w.sin_slant)
         if w.has_sip():
             return o.WCS_SIP(core, o.SIP(w.crpix, w.sip_a, w.sip_b))
         return core

@@ -123,7 +123,7 @@ def test_remap_between_added_projections(tfm, oracle, src_proj, dst_proj):
     assert_close_rel(fast, want, 2e-5, "fp32")
     assert np.count_nonzero(out.data) > 0.7 * n * n
     with pytest.raises(NotImplementedError):
-        tfm.WCS(dict(a, PV2_1=0.5))                               # non-default projection parameter
+        tfm.WCS(dict(a, PV2_3=0.5))                               # a projection parameter outside the GPU path
 
 
 @pytest.mark.parametrize("rot", [0.0, 17.0])

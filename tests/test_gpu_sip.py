@@ -1,4 +1,4 @@
-"""GPU: SIP distortion (TFM_OP_SIP) and CEA's lambda through K3 (apply / invert), K1 (resample) and K2
+"""GPU: SIP / TPV distortions (TFM_OP_SIP, TFM_OP_TPV), CEA's lambda and the slant orthographic projection through K3 (apply / invert), K1 (resample) and K2
 (Jacobian resample) -- SURVEY.md section 8f rank 4.
 
 PARITY UNPINNED by the reference (its WCS arithmetic is astropy's, absent: core.py:1727, 1742).  The
@@ -133,3 +133,74 @@ def test_cea_lambda(tfm, oracle):
     assert np.abs(a.invert(w[ok]) - p[ok]).max() < 1e-7
     one = tfm.WCS(dict(hdr, PV2_1=1.0))
     assert np.nanmax(np.abs(one.apply(p)[:, 1] - w[:, 1])) > 1.0         # lambda matters
+
+
+def test_tpv_apply_invert_resample(tfm, oracle):
+    """A '-TPV' header (SCAMP's polynomial on the intermediate world coordinates, all 40 slots in use somewhere):
+    K3 both ways over the 2048^2 detector against the oracle's explicit term list, then K1 / K2 resampling of the
+    frame onto the undistorted TAN grid.  PARITY UNPINNED (wcslib absent)."""
+    from test_sip import tpv_header
+    from transform_b200 import _lib
+    a = tfm.WCS(tpv_header())
+    oa = to_oracle(a)
+    ops = a._chain(False)
+    assert [op.kind for op in ops] == [_lib.OP_WCS, _lib.OP_TPV, _lib.OP_WCS]
+    assert [op.kind for op in a._chain(True)] == [_lib.OP_WCS, _lib.OP_TPV, _lib.OP_WCS]
+    p = np.random.default_rng(21).random((20000, 2)) * 2048 - 0.5
+    w, ow = a.apply(p), oracle.apply(oa, p)
+    dlon = ((w[:, 0] - ow[:, 0] + 180.0) % 360.0 - 180.0) * np.cos(np.radians(ow[:, 1]))
+    assert np.abs(dlon).max() < 1e-10 and np.abs(w[:, 1] - ow[:, 1]).max() < 1e-10
+    plain = tfm.WCS({k: v for k, v in tpv_header().items() if not k.startswith('PV')})
+    assert 5e-5 < np.abs(plain.apply(p)[:, 1] - w[:, 1]).max() < 2e-3       # a fraction of an arcsecond .. arcseconds
+    back = a.invert(w)
+    assert np.abs(back - p).max() < 1e-6
+    assert np.abs(back - oracle.apply(oa, ow, invert=True)).max() < 1e-6
+    # resampling: a coarser plate scale so that world-coordinate rounding stays far below the tolerance
+    n = 144
+    hdr = tpv_header(NAXIS1=n, NAXIS2=n, CRPIX1=n / 2 + 0.5, CRPIX2=n / 2 + 2.0, CD1_1=-3.0e-3, CD1_2=0.0,
+                     CD2_1=0.0, CD2_2=3.0e-3)
+    tan = {k: v for k, v in hdr.items() if not k.startswith('PV')}
+    tan['CTYPE1'], tan['CTYPE2'] = 'RA---TAN', 'DEC--TAN'
+    frame = np.random.default_rng(22).random((n, n)).astype(np.float32)
+    total = tfm.Composition([tfm.WCS(tan).inverse(), tfm.WCS(hdr)])
+    ot = to_oracle(total)
+    g = oracle.pixel_grid(n, n)
+    moved = np.hypot(*(ot.reverse(g) - g).reshape(-1, 2).T)
+    assert 1.0 < moved.max() < 20.0                                      # 0.43-degree field: the high orders bite
+    want = oracle.resample(ot, frame, method='linear', shape=(n, n))
+    assert_close_rel(total.resample(frame, method='linear', shape=(n, n)), want, 1e-9, "parity")
+    assert_close_rel(total.resample(frame, method='linear', shape=(n, n), precision='fp32'), want, 2e-5, "fp32")
+    wantj = oracle.resample_jacobian(ot, frame, method='g', shape=(n, n))
+    assert_close_rel(total.resample(frame, method='G', shape=(n, n)), wantj, 1e-9, "jacobian parity")
+    assert_close_rel(total.resample(frame, method='G', shape=(n, n), precision='fp32'), wantj, 2e-4, "jacobian fp32")
+    out = tfm.Identity().remap((frame, hdr), template=tan, method='linear')
+    assert_close_rel(out.data, total.resample(frame, method='linear', shape=(n, n)), 1e-15, "remap == composed chain")
+
+
+@pytest.mark.parametrize("slant", [(0.2, -0.3), (0.0, 0.8390996311772799), (-0.05, 0.0)])
+def test_slant_orthographic(tfm, oracle, slant):
+    """SIN with (xi, eta) = (PV2_1, PV2_2) (paper II eq. 61-62; the middle case is the NCP projection of a field at
+    declination 50 degrees): a 46-degree field so that the slant terms matter, both ways, NaN beyond the limb."""
+    hdr = {'NAXIS': 2, 'NAXIS1': 2048, 'NAXIS2': 2048, 'CTYPE1': 'RA---SIN', 'CTYPE2': 'DEC--SIN', 'CUNIT1': 'deg',
+           'CUNIT2': 'deg', 'CRPIX1': 1024.5, 'CRPIX2': 1024.5, 'CRVAL1': 83.0, 'CRVAL2': 50.0, 'CDELT1': -0.0225,
+           'CDELT2': 0.0225, 'PV2_1': slant[0], 'PV2_2': slant[1]}
+    a = tfm.WCS(hdr)
+    oa = to_oracle(a)
+    assert oa.sin_slant == (slant[0], slant[1])
+    p = np.random.default_rng(23).random((8000, 2)) * 2048
+    w, ow = a.apply(p), oracle.apply(oa, p)
+    assert np.array_equal(np.isnan(w), np.isnan(ow))
+    ok = ~np.isnan(ow).any(axis=1)
+    assert ok.mean() > 0.9
+    dlon = ((w[ok, 0] - ow[ok, 0] + 180.0) % 360.0 - 180.0) * np.cos(np.radians(ow[ok, 1]))
+    assert np.abs(dlon).max() < 1e-10 and np.abs(w[ok, 1] - ow[ok, 1]).max() < 1e-10
+    back = a.invert(w[ok])
+    assert np.abs(back - p[ok]).max() < 1e-7
+    straight = tfm.WCS({k: v for k, v in hdr.items() if not k.startswith('PV')})
+    assert np.nanmax(np.abs(straight.apply(p)[:, 1] - w[:, 1])) > 0.05       # the slant is really in
+    # the far side of the sky is NaN in the world -> pixel direction, as in the oracle
+    sky = np.stack((np.random.default_rng(24).random(4000) * 360, np.random.default_rng(25).random(4000) * 180 - 90), -1)
+    bp, obp = a.invert(sky), oracle.apply(oa, sky, invert=True)
+    assert np.array_equal(np.isnan(bp), np.isnan(obp)) and 0.2 < np.isnan(obp[:, 0]).mean() < 0.8
+    vis = ~np.isnan(obp[:, 0])
+    assert np.abs(bp[vis] - obp[vis]).max() < 1e-7

@@ -202,7 +202,9 @@ def test_header_and_wcs_parameters():
     with pytest.raises(NotImplementedError):
         t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---ZPN', 'CTYPE2': 'DEC--ZPN'})).projection()
     with pytest.raises(NotImplementedError):
-        t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---SIN', 'CTYPE2': 'DEC--SIN', 'PV2_1': 0.1}))
+        t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---ARC', 'CTYPE2': 'DEC--ARC', 'PV2_1': 0.1}))
+    slant = t.WCSParams(t.Header({'NAXIS': 2, 'CTYPE1': 'RA---SIN', 'CTYPE2': 'DEC--SIN', 'PV2_1': 0.1, 'PV2_2': -0.2}))
+    assert slant.sin_slant == (0.1, -0.2) and list(slant.lower(L.FWD)[0].p)[21:23] == [0.1, -0.2]
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/sample.fits"), reason="reference fixture not on this box")

@@ -182,32 +182,56 @@ def test_sip_lowering_needs_a_device_and_abi_constants():
         assert lib.tfm_apply(ctypes.byref(v), None) == L.ECUDA          # fails for want of a device, loudly
 
 
-def test_sip_device_functions_compiled_for_the_host(tmp_path):
-    """The text of the CUDA op (sip_poly / op_sip in csrc/tfm_chain.cuh), compiled by g++ with the CUDA
-    qualifiers and intrinsics stubbed out, against the oracle: forward 1e-11 px, inverse 1e-9 px, orders 2..9.
-    A check of the kernel's arithmetic that needs no GPU; the GPU tests repeat it through the library."""
+def _host_build_of_device_ops(tmp_path):
+    """The text of the cold CUDA ops (sip_poly .. tpv_cold in csrc/tfm_chain.cuh and the slant-SIN pair), compiled
+    by g++ with the CUDA qualifiers and intrinsics stubbed out.  Test infrastructure: a check of the kernels'
+    arithmetic that needs no GPU; the GPU tests repeat it through the library."""
     import subprocess
     src = open(os.path.join(ROOT, "transform_b200", "csrc", "tfm_chain.cuh")).read()
     i0 = src.index("__device__ __forceinline__ double sip_poly(")
     i1 = src.index("// Internal opcode (never crosses the C ABI): a WCS pixel->world op")
+    j0 = src.index("struct SlantVec {")
+    j1 = src.index("template <class A, int LVL>\n__device__ __forceinline__ void op_wcs(")
     harness = r'''
 #include <cmath>
 #include <cstring>
 #include "%s"
 #define __device__
 #define __forceinline__ inline
+#define __noinline__
+#define TFM_R2D 57.29577951308232
 static inline double __ldg(const double *p) { return *p; }
 static inline long long __double_as_longlong(double d) { long long b; memcpy(&b, &d, 8); return b; }
 using std::fma;
 %s
-extern "C" void run(const tfm_op *op, double *xy, long n) { for (long k = 0; k < n; ++k) op_sip(*op, xy[2 * k], xy[2 * k + 1]); }
-''' % (os.path.join(ROOT, "include", "tfm_b200.h"), src[i0:i1])
-    cpp = tmp_path / "sip_host.cpp"
+%s
+extern "C" void run_sip(const tfm_op *op, double *xy, long n) { for (long k = 0; k < n; ++k) op_sip(*op, xy[2 * k], xy[2 * k + 1]); }
+extern "C" void run_tpv(const tfm_op *op, double *xy, long n) { for (long k = 0; k < n; ++k) op_tpv(*op, xy[2 * k], xy[2 * k + 1]); }
+extern "C" void run_slant(double xi, double eta, int fwd, const double *in, double *out, long n) {
+    for (long k = 0; k < n; ++k) {
+        if (fwd) wcs_sin_slant_deproject(xi, eta, in[3 * k], in[3 * k + 1], out[3 * k], out[3 * k + 1], out[3 * k + 2]);
+        else { wcs_sin_slant_project(xi, eta, in[3 * k], in[3 * k + 1], in[3 * k + 2], out[3 * k], out[3 * k + 1]); out[3 * k + 2] = 0.0; }
+    }
+}
+''' % (os.path.join(ROOT, "include", "tfm_b200.h"), src[i0:i1], src[j0:j1])
+    cpp = tmp_path / "ops_host.cpp"
     cpp.write_text(harness)
-    so = tmp_path / "sip_host.so"
+    so = tmp_path / "ops_host.so"
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", str(cpp), "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
-    lib.run.argtypes = [ctypes.POINTER(L.TfmOp), ctypes.c_void_p, ctypes.c_long]
+    for f in (lib.run_sip, lib.run_tpv):
+        f.argtypes = [ctypes.POINTER(L.TfmOp), ctypes.c_void_p, ctypes.c_long]
+    lib.run_slant.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    return lib
+
+
+def _ptr_as_double(arr):
+    return np.array([arr.ctypes.data], dtype=np.int64).view(np.float64)[0]
+
+
+def test_sip_device_functions_compiled_for_the_host(tmp_path):
+    """op_sip against the oracle: forward 1e-11 px, inverse 1e-9 px, orders 2..9."""
+    lib = _host_build_of_device_ops(tmp_path)
     for order in (2, 3, 5, 9):
         rng = np.random.default_rng(100 + order)
         hdr = {'NAXIS': 2, 'CTYPE1': 'RA---TAN-SIP', 'CTYPE2': 'DEC--TAN-SIP', 'CRPIX1': 500.5, 'CRPIX2': 520.0,
@@ -224,14 +248,126 @@ extern "C" void run(const tfm_op *op, double *xy, long n) { for (long k = 0; k <
         for direction in (L.FWD, L.REV):
             op = L.TfmOp()
             op.kind, op.dir = L.OP_SIP, direction
-            op.p[0] = np.array([tab.ctypes.data], dtype=np.int64).view(np.float64)[0]
+            op.p[0] = _ptr_as_double(tab)
             op.p[1], op.p[2] = float(w.sip_a.shape[0] - 1), float(w.sip_b.shape[0] - 1)
             op.p[3], op.p[4] = float(w.crpix[0]), float(w.crpix[1])
             xy = pix.copy()
-            lib.run(ctypes.byref(op), xy.ctypes.data, len(xy))
+            lib.run_sip(ctypes.byref(op), xy.ctypes.data, len(xy))
             if direction == L.FWD:
                 assert np.abs(xy - s.forward(pix)).max() < 1e-11, order
             else:
                 want = s.reverse(pix)
                 ok = np.abs(s.forward(want) - pix).max(axis=1) < 1e-9          # where the iteration converges
                 assert ok.mean() > 0.7 and np.abs(xy[ok] - want[ok]).max() < 1e-9, order
+
+
+def tpv_header(**more):
+    """A '-TPV' header of the kind SCAMP writes: a third-order polynomial with radial terms (about 0.2 % of
+    the field), plus single terms of every higher degree so that all 40 slots are exercised somewhere."""
+    h = {'NAXIS': 2, 'NAXIS1': 2048, 'NAXIS2': 2048, 'CTYPE1': 'RA---TPV', 'CTYPE2': 'DEC--TPV', 'CUNIT1': 'deg',
+         'CUNIT2': 'deg', 'CRPIX1': 1024.5, 'CRPIX2': 1000.25, 'CRVAL1': 210.3, 'CRVAL2': -12.7,
+         'CD1_1': -7.3e-5, 'CD1_2': 2.0e-6, 'CD2_1': 2.1e-6, 'CD2_2': 7.3e-5,
+         'PV1_0': 1.2e-5, 'PV1_1': 1.0007, 'PV1_2': 3.0e-4, 'PV1_3': 2.0e-4, 'PV1_4': 1.1e-3, 'PV1_5': -2.0e-3,
+         'PV1_6': 7.0e-4, 'PV1_7': -4.0e-2, 'PV1_8': 1.0e-2, 'PV1_9': -3.5e-2, 'PV1_10': 5.0e-3, 'PV1_11': 2.0e-2,
+         'PV1_14': 0.3, 'PV1_17': 2.0, 'PV1_23': -1.0, 'PV1_27': 10.0, 'PV1_31': 50.0, 'PV1_39': -30.0,
+         'PV2_0': -2.3e-5, 'PV2_1': 0.9995, 'PV2_2': -2.0e-4, 'PV2_4': -9.0e-4, 'PV2_5': 1.5e-3, 'PV2_6': -4.0e-4,
+         'PV2_7': -4.1e-2, 'PV2_9': -3.9e-2, 'PV2_11': -1.0e-2, 'PV2_12': 0.2, 'PV2_16': -0.1, 'PV2_22': 1.5,
+         'PV2_24': 8.0, 'PV2_30': -6.0, 'PV2_38': 40.0}
+    h.update(more)
+    return h
+
+
+def test_tpv_oracle_and_header():
+    """The TPV polynomial by hand (every kind of term: powers of the own axis, cross terms, odd powers of r, with
+    the roles of xi and eta exchanged on axis 2), its inverse as a root, the header reader and the lowering order."""
+    tab = np.zeros((2, 40))
+    tab[0, [0, 1, 2, 3, 5, 11, 19, 39]] = [1e-3, 1.01, 2e-2, 3e-2, 0.5, 0.7, 1.1, 1.3]
+    tab[1, [0, 1, 2, 6, 8, 23, 30]] = [-2e-3, 0.98, -1e-2, 0.4, 0.6, 0.9, 1.2]
+    t = o.TPV(tab)
+    xi, eta = 0.31, -0.17
+    r = np.hypot(xi, eta)
+    want = [1e-3 + 1.01 * xi + 2e-2 * eta + 3e-2 * r + 0.5 * xi * eta + 0.7 * r ** 3 + 1.1 * xi ** 3 * eta ** 2 + 1.3 * r ** 7,
+            -2e-3 + 0.98 * eta - 1e-2 * xi + 0.4 * xi ** 2 + 0.6 * eta ** 2 * xi + 0.9 * r ** 5 + 1.2 * xi ** 6]
+    assert np.allclose(t.forward(np.array([[xi, eta]]))[0], want, rtol=0, atol=1e-15)
+    w = F.WCSParams(F.Header(tpv_header()))
+    assert w.is_tpv() and w.projection()[0] == L.WCS_PROJ_TAN and w.tpv.shape == (2, 40)
+    assert w.tpv[0, 1] == 1.0007 and w.tpv[0, 39] == -30.0 and w.tpv[1, 3] == 0.0 and w.tpv[1, 38] == 40.0
+    assert w.lonpole is None and w.cea_lambda == 1.0            # PV1_3 is a coefficient here, not LONPOLE
+    t = o.TPV(w.tpv)
+    v = np.random.default_rng(9).random((4000, 2)) * 0.15 - 0.075          # the field of the header, degrees
+    f = t.forward(v)
+    assert 1e-4 < np.abs(f - v).max() < 2e-3                    # up to ~7 arcsec = 25 pixels
+    assert np.abs(t.reverse(f) - v).max() < 1e-13
+    from scipy.optimize import root
+    for q in f[:10]:
+        sol = root(lambda z: t.forward(z[None, :])[0] - q, q, tol=1e-15)
+        assert sol.success and np.abs(sol.x - t.reverse(q[None, :])[0]).max() < 1e-12
+    full = o.WCS_TPV(w.crpix, w.linear_matrix(), w.crval, w.tpv)
+    plain = o.WCS(w.crpix, w.linear_matrix(), w.crval, 'TAN')
+    p = np.random.default_rng(10).random((2000, 2)) * 2048
+    sky = full.forward(p)
+    assert np.abs(full.reverse(sky) - p).max() < 1e-7
+    assert 1e-4 < np.abs(sky - plain.forward(p))[:, 1].max() < 2e-3
+    # defaults: a -TPV header without PV keywords is plain TAN
+    bare = F.WCSParams(F.Header({k: v for k, v in tpv_header().items() if not k.startswith('PV')}))
+    assert bare.tpv is None and bare.is_tpv()
+    h2 = w.to_header()
+    assert h2['PV1_39'] == -30.0 and h2['PV2_1'] == 0.9995 and 'PV2_3' not in h2 and h2['CTYPE1'] == 'RA---TPV'
+    assert np.array_equal(F.WCSParams(h2).tpv, w.tpv)
+    with pytest.raises(ValueError):
+        F.WCSParams(F.Header(tpv_header(PV1_40=1.0)))
+    with pytest.raises(ValueError):
+        F.WCSParams(F.Header(tpv_header(PV3_1=1.0)))
+    import torch
+    if not torch.cuda.is_available():
+        from transform_b200._device import NoCudaDevice
+        with pytest.raises(NoCudaDevice):
+            t_ = __import__("transform_b200").WCS(tpv_header())
+            t_.apply(np.zeros((2, 2)))
+    hdr = open(os.path.join(ROOT, "include", "tfm_b200.h")).read()
+    assert int(re.search(r"TFM_OP_TPV\s*=\s*(\d+)", hdr).group(1)) == L.OP_TPV
+    assert int(re.search(r"#define TFM_TPV_NCOEF\s+(\d+)", hdr).group(1)) == L.TPV_NCOEF == len(o.TPV.TERMS)
+    assert int(re.search(r"#define TFM_TPV_MAXITER\s+(\d+)", hdr).group(1)) == L.TPV_MAXITER == o.TPV.MAXITER
+
+
+def test_tpv_and_slant_device_functions_compiled_for_the_host(tmp_path):
+    """op_tpv (forward 1e-15 degree, inverse 1e-13) and the slant orthographic pair (unit-vector form on the
+    device, angle form in the oracle: 1e-12) against the oracle."""
+    lib = _host_build_of_device_ops(tmp_path)
+    w = F.WCSParams(F.Header(tpv_header()))
+    tab = np.ascontiguousarray(w.tpv)
+    t = o.TPV(tab)
+    Minv = np.linalg.inv(np.array([[tab[0, 1], tab[0, 2]], [tab[1, 2], tab[1, 1]]]))
+    v = np.random.default_rng(11).random((5000, 2)) * 0.15 - 0.075
+    for direction in (L.FWD, L.REV):
+        op = L.TfmOp()
+        op.kind, op.dir = L.OP_TPV, direction
+        op.p[0] = _ptr_as_double(tab)
+        op.p[1], op.p[2], op.p[3], op.p[4] = Minv.ravel()
+        xy = v.copy()
+        lib.run_tpv(ctypes.byref(op), xy.ctypes.data, len(xy))
+        want = t.forward(v) if direction == L.FWD else t.reverse(v)
+        assert np.abs(xy - want).max() < (1e-15 if direction == L.FWD else 1e-13)
+    r0 = 180.0 / np.pi
+    rng = np.random.default_rng(12)
+    phi, theta = rng.random(4000) * 360 - 180, rng.random(4000) * 100 - 10
+    for sl in ((0.2, -0.3), (0.0, 1.0 / np.tan(np.radians(50.0))), (-0.05, 0.0)):       # the middle one is "NCP"
+        ph, th = np.radians(phi), np.radians(theta)
+        m = np.ascontiguousarray(np.stack((np.cos(th) * np.cos(ph), np.cos(th) * np.sin(ph), np.sin(th)), -1))
+        out = np.zeros_like(m)
+        lib.run_slant(sl[0], sl[1], 0, m.ctypes.data, out.ctypes.data, len(m))
+        x, y = o._project("SIN", phi, theta, 1.0, sl)
+        assert np.array_equal(np.isnan(out[:, 0]), np.isnan(x)) and 0.5 < np.isnan(x).mean() * 10 < 9
+        ok = ~np.isnan(x)
+        assert np.abs(out[ok, 0] - x[ok]).max() < 1e-12 and np.abs(out[ok, 1] - y[ok]).max() < 1e-12
+        xy = np.ascontiguousarray(np.stack((x[ok], y[ok], np.zeros(ok.sum())), -1))
+        back = np.zeros_like(xy)
+        lib.run_slant(sl[0], sl[1], 1, xy.ctypes.data, back.ctypes.data, len(xy))
+        p2, t2 = o._deproject("SIN", x[ok], y[ok], 1.0, sl)
+        got_phi = np.degrees(np.arctan2(back[:, 1], back[:, 0]))
+        got_theta = np.degrees(np.arctan2(back[:, 2], np.hypot(back[:, 0], back[:, 1])))
+        near = np.abs(t2 - theta[ok]) < 1e-6                     # the nearer root is the point projected
+        assert near.mean() > 0.8
+        assert np.abs(got_theta - t2)[near].max() < 1e-9
+        assert np.abs(((got_phi - p2 + 180) % 360 - 180) * np.cos(np.radians(t2)))[near].max() < 1e-9
+    assert np.allclose(o._project("SIN", phi, np.abs(theta) + 1, 1.0, (0.0, 0.0)), o._project("SIN", phi, np.abs(theta) + 1))

@@ -17,8 +17,9 @@ OP_NPARAM = 24
 # status codes
 OK, EVALUE, EDIRECTION, EFORBID, ECUDA, EUNSUPPORTED, ESTAGED = range(7)
 # op kinds / directions
-OP_IDENTITY, OP_LINEAR, OP_RADIAL, OP_WCS, OP_INDEX, OP_PIN, OP_SIP = range(7)
+OP_IDENTITY, OP_LINEAR, OP_RADIAL, OP_WCS, OP_INDEX, OP_PIN, OP_SIP, OP_TPV = range(8)
 SIP_MAX_ORDER, SIP_DIM, SIP_MAXITER = 9, 10, 20
+TPV_NCOEF, TPV_MAXITER = 40, 30
 PIN_QUAD, PIN_CUBIC, PIN_POLY, PIN_SHIFTED, PIN_DIM1, PIN_TRUNC, PIN_MAX_DEGREE = 0, 1, 2, 4, 8, 16, 8
 FWD, REV = 0, 1
 # flags

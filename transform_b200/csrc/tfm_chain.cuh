@@ -311,6 +311,44 @@ __device__ __forceinline__ void wcs_project_all(int proj, double mx, double my, 
     }
 }
 
+// ---- slant orthographic projection: SIN with (xi, eta) = (PV2_1, PV2_2), paper II eq. 61-62 ----
+// x = r0 [cos t sin p + xi (1 - sin t)], y = -r0 [cos t cos p - eta (1 - sin t)], i.e. in native unit-vector form
+// ix = r0 (m_y + xi s), iy = -r0 (m_x - eta s) with s = 1 - m_z; the inverse is the smaller root of
+// (xi^2 + eta^2 + 1) s^2 - 2 (X xi + Y eta + 1) s + X^2 + Y^2 = 0 (the solution nearer the native pole).
+// Out of line (cold): inlined 8-wide into the texture kernels they took the SPH = 2 instantiation from 70 to
+// 200 registers.
+struct SlantVec { double x, y, z; };
+
+static __device__ __noinline__ SlantVec sin_slant_deproject_cold(double xi, double eta, double ix, double iy)
+{
+    const double X = ix / TFM_R2D, Y = iy / TFM_R2D;
+    const double a = xi * xi + eta * eta + 1.0, b = X * xi + Y * eta + 1.0, c = X * X + Y * Y;
+    const double disc = b * b - a * c;
+    const double s = (disc >= 0.0) ? c / (b + sqrt(disc)) : nan("");      // = (b - sqrt(disc)) / a, stable near 0
+    return SlantVec{-Y + eta * s, X - xi * s, 1.0 - s};
+}
+
+static __device__ __noinline__ SlantVec sin_slant_project_cold(double xi, double eta, double mx, double my, double mz)
+{
+    const double s = 1.0 - mz;
+    const bool visible = mz + xi * my - eta * mx >= 0.0;                  // theta >= -atan(xi sin p - eta cos p)
+    return SlantVec{visible ? TFM_R2D * (my + xi * s) : nan(""), visible ? -TFM_R2D * (mx - eta * s) : nan(""), 0.0};
+}
+
+__device__ __forceinline__ void wcs_sin_slant_deproject(double xi, double eta, double ix, double iy,
+                                                        double &mx, double &my, double &mz)
+{
+    const SlantVec v = sin_slant_deproject_cold(xi, eta, ix, iy);
+    mx = v.x; my = v.y; mz = v.z;
+}
+
+__device__ __forceinline__ void wcs_sin_slant_project(double xi, double eta, double mx, double my, double mz,
+                                                      double &ix, double &iy)
+{
+    const SlantVec v = sin_slant_project_cold(xi, eta, mx, my, mz);
+    ix = v.x; iy = v.y;
+}
+
 template <class A, int LVL>
 __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
 {
@@ -329,7 +367,14 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
         if constexpr (LVL >= 2)                            // CEA: y = r0 sin(theta) / lambda (eq. 80), PV2_1 in p[21]
             if (proj == TFM_WCS_PROJ_CEA && op.p[21] != 0.0) iy *= op.p[21];
         double mx, my, mz;
-        wcs_deproject<LVL>(proj, ix, iy, mx, my, mz);      // un-normalised: only angles are taken below
+        if constexpr (LVL >= 2) {
+            if (proj == TFM_WCS_PROJ_SIN && (op.p[21] != 0.0 || op.p[22] != 0.0))
+                wcs_sin_slant_deproject(op.p[21], op.p[22], ix, iy, mx, my, mz);
+            else
+                wcs_deproject<LVL>(proj, ix, iy, mx, my, mz);
+        } else {
+            wcs_deproject<LVL>(proj, ix, iy, mx, my, mz);  // un-normalised: only angles are taken below
+        }
         const double lx = R[0] * mx + R[1] * my + R[2] * mz;
         const double ly = R[3] * mx + R[4] * my + R[5] * mz;
         const double lz = R[6] * mx + R[7] * my + R[8] * mz;
@@ -351,9 +396,15 @@ __device__ __forceinline__ void op_wcs(const tfm_op &op, double &x, double &y)
             const double mx = R[0] * lx + R[3] * ly + R[6] * lz;       // R^T l
             const double my = R[1] * lx + R[4] * ly + R[7] * lz;
             const double mz = R[2] * lx + R[5] * ly + R[8] * lz;
-            wcs_project<LVL>(proj, mx, my, mz, ix, iy);    // NaN on the far side of the sky (TAN, SIN)
-            if constexpr (LVL >= 2)
+            if constexpr (LVL >= 2) {
+                if (proj == TFM_WCS_PROJ_SIN && (op.p[21] != 0.0 || op.p[22] != 0.0))
+                    wcs_sin_slant_project(op.p[21], op.p[22], mx, my, mz, ix, iy);
+                else
+                    wcs_project<LVL>(proj, mx, my, mz, ix, iy);
                 if (proj == TFM_WCS_PROJ_CEA && op.p[21] != 0.0) iy /= op.p[21];
+            } else {
+                wcs_project<LVL>(proj, mx, my, mz, ix, iy);    // NaN on the far side of the sky (TAN, SIN)
+            }
         }
         double px = A::add(A::mul(op.p[6], ix), A::mul(op.p[7], iy));
         double py = A::add(A::mul(op.p[8], ix), A::mul(op.p[9], iy));
@@ -377,7 +428,12 @@ __device__ __forceinline__ double sip_poly(const double *c, int order, double u,
     return s;
 }
 
-__device__ __forceinline__ void op_sip(const tfm_op &op, double &x, double &y)
+// Cold ops are kept OUT of line: inlined into the N-wide interpreter their loops were unrolled per pixel and took
+// the SPH = 2 texture kernel from 70 to 200 registers (cuobjdump --dump-resource-usage); results by value, a
+// reference argument would live on the stack.
+struct ChainXY { double x, y; };
+
+static __device__ __noinline__ ChainXY sip_cold(const tfm_op &op, double x, double y)
 {
     const double *coef = reinterpret_cast<const double *>(__double_as_longlong(op.p[0]));
     const int ao = (int)op.p[1], bo = (int)op.p[2];
@@ -396,6 +452,70 @@ __device__ __forceinline__ void op_sip(const tfm_op &op, double &x, double &y)
             if (!(dx * dx + dy * dy >= 1e-24)) break;       // converged (or NaN: nothing left to refine)
         }
     }
+    return ChainXY{x, y};
+}
+
+__device__ __forceinline__ void op_sip(const tfm_op &op, double &x, double &y)
+{
+    const ChainXY r = sip_cold(op, x, y);
+    x = r.x; y = r.y;
+}
+
+// ---- TPV distortion: polynomial in the intermediate world coordinates (xi, eta) and r = hypot(xi, eta) ----
+// PARITY UNPINNED (wcslib absent).  One axis: c[0..39] in the order of the convention (include/tfm_b200.h);
+// x is the axis' own coordinate, y the other one.  Degree d contributes sum_k c_k x^(d-k) y^k -- accumulated as
+// acc <- acc x + c_k y^k -- plus c r^d for odd d.
+__device__ __forceinline__ double tpv_poly(const double *c, double x, double y)
+{
+    const double r = sqrt(x * x + y * y), r2 = r * r;
+    double s = __ldg(c), rp = r;
+    int m = 1;
+#pragma unroll 1                        // rolled: fully unrolled, the 80 coefficient loads took 200 registers
+    for (int d = 1; d <= 7; ++d) {
+        double acc = __ldg(c + m), yp = 1.0;
+#pragma unroll 1
+        for (int k = 1; k <= d; ++k) {
+            yp *= y;
+            acc = fma(acc, x, __ldg(c + m + k) * yp);
+        }
+        s += acc;
+        m += d + 1;
+        if (d & 1) {
+            s = fma(__ldg(c + m), rp, s);
+            rp *= r2;
+            ++m;
+        }
+    }
+    return s;
+}
+
+static __device__ __noinline__ ChainXY tpv_cold(const tfm_op &op, double x, double y)
+{
+    const double *c1 = reinterpret_cast<const double *>(__double_as_longlong(op.p[0]));
+    const double *c2 = c1 + TFM_TPV_NCOEF;
+    if (op.dir == TFM_FWD) {
+        const double xi = x, eta = y;
+        x = tpv_poly(c1, xi, eta);
+        y = tpv_poly(c2, eta, xi);
+    } else {                            // quasi-Newton on the constant linear part (p[1..4] = its inverse)
+        const double tx = x, ty = y;
+        const double ax = tx - __ldg(c1), ay = ty - __ldg(c2);
+        double vx = fma(op.p[1], ax, op.p[2] * ay), vy = fma(op.p[3], ax, op.p[4] * ay);
+        for (int k = 0; k < TFM_TPV_MAXITER; ++k) {
+            const double ex = tpv_poly(c1, vx, vy) - tx, ey = tpv_poly(c2, vy, vx) - ty;
+            const double dx = fma(op.p[1], ex, op.p[2] * ey), dy = fma(op.p[3], ex, op.p[4] * ey);
+            vx -= dx; vy -= dy;
+            if (!(dx * dx + dy * dy >= 1e-26)) break;
+        }
+        x = vx; y = vy;
+    }
+    return ChainXY{x, y};
+}
+
+__device__ __forceinline__ void op_tpv(const tfm_op &op, double &x, double &y)
+{
+    const ChainXY r = tpv_cold(op, x, y);
+    x = r.x; y = r.y;
 }
 
 // Internal opcode (never crosses the C ABI): a WCS pixel->world op directly followed by a WCS
@@ -539,16 +659,16 @@ __device__ __forceinline__ void wcs_car_tan_sep(const WcsCarCoef &k, const doubl
 
 // "Heavy" ops are compiled only into dedicated kernel instantiations (template parameter SPH):
 //   0  none of them        1  WCS with linear axes, TAN or CAR (+ the fused WCS pair)
-//   2  every WCS projection, the SIP distortion and the pow()-based pincushion family
+//   2  every WCS projection, the SIP / TPV distortions and the pow()-based pincushion family
 static inline int chain_sph_level(const ChainDev &ch)
 {
     int lvl = 0;
     for (int i = 0; i < ch.n; ++i) {
         const tfm_op &op = ch.ops[i];
-        if (op.kind == TFM_OP_PIN || op.kind == TFM_OP_SIP) lvl = 2;
+        if (op.kind == TFM_OP_PIN || op.kind == TFM_OP_SIP || op.kind == TFM_OP_TPV) lvl = 2;
         else if (op.kind == TFM_OP_WCS_PAIR) lvl = lvl < 1 ? 1 : lvl;
         else if (op.kind == TFM_OP_WCS) {
-            const int need = ((op.flags & 0xff) > TFM_WCS_PROJ_CAR) ? 2 : 1;
+            const int need = ((op.flags & 0xff) > TFM_WCS_PROJ_CAR) ? 2 : 1;   // (slant SIN is > CAR)
             lvl = lvl < need ? need : lvl;
         }
     }
@@ -721,9 +841,14 @@ static inline bool chain_ops_valid(const tfm_op *ops, int n)
 {
     for (int i = 0; i < n; ++i) {
         const tfm_op &op = ops[i];
-        if (op.kind < TFM_OP_IDENTITY || op.kind > TFM_OP_SIP) return false;
+        if (op.kind < TFM_OP_IDENTITY || op.kind > TFM_OP_TPV) return false;
         if (op.dir != TFM_FWD && op.dir != TFM_REV) return false;
         if (op.kind == TFM_OP_WCS && ((op.flags & 0xff) < 0 || (op.flags & 0xff) > TFM_WCS_PROJ_MAX)) return false;
+        if (op.kind == TFM_OP_TPV) {
+            long long bits;
+            memcpy(&bits, &op.p[0], sizeof bits);
+            if (bits == 0) return false;                    // no coefficient table
+        }
         if (op.kind == TFM_OP_SIP) {
             long long bits;
             memcpy(&bits, &op.p[0], sizeof bits);
@@ -772,6 +897,7 @@ __device__ __forceinline__ void chain_eval(const ChainDev &ch, double &x, double
         case TFM_OP_WCS_PAIR: if constexpr (SPH >= 1) op_wcs_pair(op, x, y); break;
         case TFM_OP_PIN: if constexpr (SPH >= 2) op_pin<A>(op, x, y); break;
         case TFM_OP_SIP: if constexpr (SPH >= 2) op_sip(op, x, y); break;
+        case TFM_OP_TPV: if constexpr (SPH >= 2) op_tpv(op, x, y); break;
         case TFM_OP_POLAR: op_polar(op, x, y); break;
         case TFM_OP_INDEX: op_index(op, x, y); break;
         default: break;                                     // identity
@@ -850,6 +976,12 @@ __device__ __forceinline__ void chain_eval_n(const ChainDev &ch, double (&x)[N],
             if constexpr (SPH >= 2) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) op_sip(op, x[k], y[k]);
+            }
+            break;
+        case TFM_OP_TPV:
+            if constexpr (SPH >= 2) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) op_tpv(op, x[k], y[k]);
             }
             break;
         case TFM_OP_POLAR:

@@ -10,12 +10,12 @@ itself cites (core.py:38-42, 1655-1658):
   * Header       ordered, dict-like FITS header with the astropy methods core.py uses
   * read_fits    primary-HDU reader (BITPIX 8/16/32/64/-32/-64, big-endian, BSCALE/BZERO)
   * WCSParams    CRPIX/CRVAL/CDELT + CD | PC | CROTA2 linear part (paper I), ten spherical
-                 projections with LONPOLE/LATPOLE defaults (paper II), CEA's lambda (PV2_1) and the
-                 SIP polynomial distortion (Shupe et al. 2005); `lower()` packs them into the
-                 TFM_OP_WCS (+ TFM_OP_SIP) opcodes evaluated by the CUDA library.
+                 projections with LONPOLE/LATPOLE defaults (paper II), CEA's lambda, SIN's slant, the
+                 SIP (Shupe et al. 2005) and TPV polynomial distortions; `lower()` packs them into
+                 the TFM_OP_WCS (+ TFM_OP_SIP / TFM_OP_TPV) opcodes evaluated by the CUDA library.
 
 PARITY: the linear part is pinned by the reference's own test (tests/test_01_core.py:160-169,
-sample.fits).  The spherical projections and SIP are PARITY UNPINNED (no astropy/wcslib to diff against).
+sample.fits).  The spherical projections, SIP and TPV are PARITY UNPINNED (no astropy/wcslib to diff against).
 """
 import copy
 import math
@@ -255,6 +255,7 @@ _PROJ = {"TAN": (L.WCS_PROJ_TAN, 0.0, 90.0), "CAR": (L.WCS_PROJ_CAR, 0.0, 0.0),
          "CEA": (L.WCS_PROJ_CEA, 0.0, 0.0), "MER": (L.WCS_PROJ_MER, 0.0, 0.0),
          "SFL": (L.WCS_PROJ_SFL, 0.0, 0.0), "AIT": (L.WCS_PROJ_AIT, 0.0, 0.0)}
 _PROJ_NAME = {v[0]: k for k, v in _PROJ.items()}
+_PROJ["TPV"] = _PROJ["TAN"]        # TAN with the PVi_m polynomial distortion of the TPV convention (TFM_OP_TPV)
 
 
 def _sph_to_vec(lon_deg, lat_deg):
@@ -292,6 +293,8 @@ class WCSParams:
         self.latpole = None
         self.pixel_shape = None
         self.cea_lambda = 1.0          # PV2_1 of a CEA projection (paper II eq. 80)
+        self.sin_slant = (0.0, 0.0)    # (xi, eta) = (PV2_1, PV2_2) of a SIN projection (paper II eq. 61-62)
+        self.tpv = None                # TPV: float64 [2][40], tpv[0][m] = PV1_m, tpv[1][m] = PV2_m
         self.sip_a = None              # SIP: (A_ORDER+1)^2 array, sip_a[p, q] = A_p_q (Shupe et al. 2005)
         self.sip_b = None
         self._sip_dev = {}             # (device, table bytes) -> resident coefficient table
@@ -377,6 +380,16 @@ class WCSParams:
             proj = None
         name = _PROJ_NAME.get(proj[0]) if proj is not None else None
         lng, lat = 1, 2
+        if self.is_tpv():
+            # every PV1_m / PV2_m of a -TPV header is a coefficient of the distortion polynomial
+            tab = np.zeros((2, L.TPV_NCOEF))
+            tab[0, 1] = tab[1, 1] = 1.0
+            for (i, m), val in pv.items():
+                if i not in (1, 2) or not (0 <= m < L.TPV_NCOEF):
+                    raise ValueError("WCS: PV%d_%d is not a term of the TPV polynomial (m = 0..39 on axes 1, 2)" % (i, m))
+                tab[i - 1, m] = val
+            self.tpv = tab
+            return
         for (i, m), val in sorted(pv.items()):
             ok = False
             if proj is not None and i == lng:
@@ -395,14 +408,18 @@ class WCSParams:
                     if not (0.0 < val <= 1.0):
                         raise ValueError("WCS: CEA needs 0 < PV2_1 <= 1, got %r" % val)
                     self.cea_lambda, ok = val, True
+                elif name == 'SIN' and m in (1, 2):
+                    sl = list(self.sin_slant)
+                    sl[m - 1] = val
+                    self.sin_slant, ok = tuple(sl), True
                 else:
                     ok = (val == 0.0) and name in ('TAN', 'CAR', 'STG', 'SIN', 'ARC', 'ZEA', 'MER', 'SFL', 'AIT')
             else:
                 ok = (val == 0.0)
             if not ok:
                 raise NotImplementedError("transform_b200: projection parameter PV%d_%d = %r is not on "
-                                          "the GPU path (CEA's lambda, LONPOLE/LATPOLE as PVi_3/PVi_4 "
-                                          "and default values are)" % (i, m, val))
+                                          "the GPU path (CEA's lambda, SIN's slant, the TPV polynomial, "
+                                          "LONPOLE/LATPOLE as PVi_3/PVi_4 and default values are)" % (i, m, val))
 
     def _read_sip(self, h):
         """A_ORDER / B_ORDER / A_p_q / B_p_q (Shupe et al. 2005).  astropy applies them whenever
@@ -430,6 +447,40 @@ class WCSParams:
     def has_sip(self):
         return self.sip_a is not None and self.sip_b is not None
 
+    def is_tpv(self):
+        return self.naxis >= 2 and all(len(c) >= 8 and c[4] == '-' and c[5:8].upper() == 'TPV' for c in self.ctype[:2])
+
+    def _table_on_device(self, tab, slot):
+        """Coefficient table resident on the current device: uploaded once per device and table contents;
+        the tensor lives as long as this object."""
+        from . import _device as dev
+        torch = dev.require_cuda()
+        key = (int(torch.cuda.current_device()), slot, tab.tobytes())
+        t = self._sip_dev.get(key)
+        if t is None:
+            t = dev.to_device(tab, np.float64, slot=slot)
+            self._sip_dev = {k: v for k, v in self._sip_dev.items() if k[:2] != key[:2]}
+            self._sip_dev[key] = t
+        return t
+
+    def _tpv_op(self, direction):
+        """TFM_OP_TPV (include/tfm_b200.h): the polynomial table on the device, the inverse of its linear part."""
+        import struct
+        tab = np.ascontiguousarray(self.tpv, dtype=np.float64)
+        if tab.shape != (2, L.TPV_NCOEF):
+            raise ValueError("WCS: the TPV table must be [2][%d]" % L.TPV_NCOEF)
+        M = np.array([[tab[0, 1], tab[0, 2]], [tab[1, 2], tab[1, 1]]])
+        if abs(np.linalg.det(M)) < 1e-300:
+            raise ValueError("WCS: the linear part of the TPV polynomial is singular")
+        Minv = np.linalg.inv(M)
+        t = self._table_on_device(tab, "tpv")
+        op = L.TfmOp()
+        op.kind, op.dir, op.flags = L.OP_TPV, direction, 0
+        op.p[0] = struct.unpack("d", struct.pack("q", int(t.data_ptr())))[0]
+        op.p[1], op.p[2], op.p[3], op.p[4] = (float(Minv[0, 0]), float(Minv[0, 1]),
+                                              float(Minv[1, 0]), float(Minv[1, 1]))
+        return op
+
     def sip_table(self):
         """float64 [2][SIP_DIM][SIP_DIM]: the layout TFM_OP_SIP reads (include/tfm_b200.h)."""
         t = np.zeros((2, L.SIP_DIM, L.SIP_DIM))
@@ -450,16 +501,8 @@ class WCSParams:
     def _sip_op(self, direction):
         """TFM_OP_SIP with its coefficient table resident on the current device (uploaded once per
         device and table contents; the tensor lives as long as this object)."""
-        from . import _device as dev
         import struct
-        torch = dev.require_cuda()
-        tab = self.sip_table()
-        key = (int(torch.cuda.current_device()), tab.tobytes())
-        t = self._sip_dev.get(key)
-        if t is None:
-            t = dev.to_device(tab, np.float64, slot="sip")
-            self._sip_dev = {k: v for k, v in self._sip_dev.items() if k[0] != key[0]}
-            self._sip_dev[key] = t
+        t = self._table_on_device(self.sip_table(), "sip")
         op = L.TfmOp()
         op.kind, op.dir, op.flags = L.OP_SIP, direction, 0
         op.p[0] = struct.unpack("d", struct.pack("q", int(t.data_ptr())))[0]
@@ -579,11 +622,27 @@ class WCSParams:
                     op.p[12 + 3 * i + j] = float(R[i, j])
             if proj[0] == L.WCS_PROJ_CEA:
                 op.p[21] = float(self.cea_lambda)
+            elif proj[0] == L.WCS_PROJ_SIN:
+                op.p[21], op.p[22] = float(self.sin_slant[0]), float(self.sin_slant[1])
+        ops = [op]
+        if self.tpv is not None and proj is not None:
+            # wcslib applies the TPV polynomial to the intermediate world coordinates, between the linear part
+            # and the gnomonic projection: {linear part with CRVAL = 0 and no projection, TPV, projection part
+            # with CRPIX = 1 and a unit matrix}
+            lin, prj = L.TfmOp(), L.TfmOp()
+            lin.kind, lin.dir, lin.flags = L.OP_WCS, direction, L.WCS_PROJ_NONE
+            prj.kind, prj.dir, prj.flags = L.OP_WCS, direction, op.flags
+            for k in range(L.OP_NPARAM):
+                lin.p[k] = op.p[k] if k < 10 else 0.0
+                prj.p[k] = op.p[k] if k >= 10 else 0.0
+            prj.p[0] = prj.p[1] = 1.0
+            prj.p[2] = prj.p[5] = prj.p[6] = prj.p[9] = 1.0
+            ops = [lin, self._tpv_op(direction), prj] if direction == L.FWD else [prj, self._tpv_op(direction), lin]
         if self.has_sip():
             # all_pix2world: pix2foc (SIP) then the core; all_world2pix: the core, then the SIP
             # fixed-point inversion (core.py:1727, 1742)
-            return [self._sip_op(direction), op] if direction == L.FWD else [op, self._sip_op(direction)]
-        return [op]
+            return [self._sip_op(direction)] + ops if direction == L.FWD else ops + [self._sip_op(direction)]
+        return ops
 
     def to_header(self, relax=None):
         """The keys astropy's WCS.to_header() emits that core.py relies on (core.py:1074, 1208-1234).
@@ -621,6 +680,13 @@ class WCSParams:
             h['LATPOLE'] = float(90.0 if self.latpole is None else self.latpole)
             if self.projection()[0] == L.WCS_PROJ_CEA and self.cea_lambda != 1.0:
                 h['PV2_1'] = float(self.cea_lambda)
+            if self.projection()[0] == L.WCS_PROJ_SIN and self.sin_slant != (0.0, 0.0):
+                h['PV2_1'], h['PV2_2'] = float(self.sin_slant[0]), float(self.sin_slant[1])
+            if self.tpv is not None:
+                for i in range(2):
+                    for m in range(L.TPV_NCOEF):
+                        if self.tpv[i][m] != (1.0 if m == 1 else 0.0):
+                            h['PV%d_%d' % (i + 1, m)] = float(self.tpv[i][m])
         if do_sip:
             for L_, c in (('A', np.asarray(self.sip_a)), ('B', np.asarray(self.sip_b))):
                 m = c.shape[0] - 1
