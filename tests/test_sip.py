@@ -107,6 +107,11 @@ def test_sip_header_reader():
     assert np.array_equal(w2.sip_a, w.sip_a) and np.array_equal(w2.sip_b, w.sip_b) and w2.ctype == w.ctype
     c = w.copy()
     assert c.sip_a is not w.sip_a and np.array_equal(c.sip_a, w.sip_a) and c._sip_dev == {}
+    import pickle
+    w._sip_dev = {'stand-in for a device tensor': object}               # the cache never travels with the object
+    c = pickle.loads(pickle.dumps(w))
+    assert c._sip_dev == {} and np.array_equal(c.sip_b, w.sip_b)
+    w._sip_dev = {}
     with pytest.raises(ValueError):                                     # astropy: both orders or none
         F.WCSParams(F.Header({k: v for k, v in sip_header().items() if k != 'B_ORDER'}))
     with pytest.raises(ValueError):

@@ -510,6 +510,12 @@ class WCSParams:
         op.p[3], op.p[4] = float(self.crpix[0]), float(self.crpix[1])
         return op
 
+    def __getstate__(self):
+        # the device-resident coefficient tables are a cache: never pickled (another process uploads its own)
+        st = dict(self.__dict__)
+        st['_sip_dev'] = {}
+        return st
+
     def __deepcopy__(self, memo):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
