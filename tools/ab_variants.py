@@ -36,6 +36,8 @@ if what == "k2":
     for tun in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0").split(",")]:
         out["radial_t%d_ms" % tun] = round(timed(lambda: tr_rad.resample(src, method="G", precision="fp32", out=dst, tuning=tun), 10), 4)
         out["radial_t%d_k" % tun] = _lib.last_kernel()
+        out["radial_t%d_sum" % tun] = float(dst.double().sum().item())      # variants must agree bit for bit
+        out["radial_t%d_absdiff_checksum" % tun] = float((dst[1:] - dst[:-1]).abs().double().sum().item())
         out["named_t%d_ms" % tun] = round(timed(lambda: tr_aff.resample(src, method="G", precision="fp32", out=dst, tuning=tun), 10), 4)
         out["down_t%d_ms" % tun] = round(timed(lambda: tr_dn.resample(src, method="G", precision="fp32", out=dst, tuning=tun), 10), 4)
 else:

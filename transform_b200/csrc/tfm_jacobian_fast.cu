@@ -24,7 +24,7 @@
 // tests executed by every thread.  Here every constant arrives as the type it is used in, indices
 // are 32-bit, floor/fraction is fixed point (floor_frac_fast), and pixels whose footprint is not
 // wholly inside the staged source take one out-of-line slow path.  The measured history of the polar
-// unwrap at 8192^2 (2.05 -> 1.07 ms) is in DESIGN.md section 4.
+// unwrap at 8192^2 (2.05 -> 1.04 ms) is in DESIGN.md section 4.
 #include "tfm_jacobian_common.cuh"
 
 namespace tfm {
@@ -787,6 +787,9 @@ __device__ __forceinline__ void pair_rows(const float4 (&g)[HALF + 1], PairPix &
     }
 }
 
+#ifndef TFM_K2P_DB
+#define TFM_K2P_DB 4             // largest half-width served by the double-buffered form
+#endif
 template <int HALF>
 __device__ __forceinline__ void pair_taps_tex(cudaTextureObject_t tex, int ux, int uy, PairPix &A, PairPix &B)
 {
@@ -804,6 +807,28 @@ __device__ __forceinline__ void pair_taps_tex(cudaTextureObject_t tex, int ux, i
         for (int j = 0; j < NP; ++j) {
             pair_rows<HALF>(g[j], A, j == 0 ? !A.my : true, j == NP - 1 ? A.my : true);
             pair_rows<HALF>(g[j], B, j == 0 ? !B.my : true, j == NP - 1 ? B.my : true);
+        }
+    } else if constexpr (HALF <= TFM_K2P_DB) {
+        // double-buffered: the next row pair's gathers are issued before the current one is consumed (rows fully
+        // unrolled).  With 80 registers (3 resident CTAs) 1.064 -> 1.037 ms on the 8192^2 unwrap, bit-identical
+        // output; at 64 registers it spills (1.136 ms); windows of half-width 5 and 6 (TFM_K2P_DB = 5, 6) change
+        // nothing on that map and spill more, so they keep the rolled loop below.
+        float4 g[NP], gn[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) g[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            if (j + 1 < NP) {
+                fy += 2.0f;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) gn[i] = tex2Dgather<float4>(tex, fx0 + (float)(2 * i), fy, 0);
+            }
+            pair_rows<HALF>(g, A, j == 0 ? !A.my : true, j == NP - 1 ? A.my : true);
+            pair_rows<HALF>(g, B, j == 0 ? !B.my : true, j == NP - 1 ? B.my : true);
+            if (j + 1 < NP) {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) g[i] = gn[i];
+            }
         }
     } else {
         float4 g[NP];
@@ -866,7 +891,7 @@ __device__ __noinline__ float pair_single(const JacFastParams &P, float Aq, floa
 }
 
 #ifndef TFM_K2P_MINBLOCKS
-#define TFM_K2P_MINBLOCKS 4
+#define TFM_K2P_MINBLOCKS 3    // 80 registers: what the double-buffered row pairs need (4 CTAs / 64 registers: spills)
 #endif
 __global__ void __launch_bounds__(256, TFM_K2P_MINBLOCKS)
 k_jac_gauss_polar_rows_pair(const __grid_constant__ JacFastParams P)
