@@ -126,6 +126,30 @@ def test_sip_header_reader():
     assert not F.WCSParams(F.Header({'NAXIS': 2, 'CTYPE1': 'RA---TAN', 'CTYPE2': 'DEC--TAN'})).has_sip()
 
 
+def test_foreign_wcs_object_keeps_its_distortion():
+    """An astropy-like WCS object (anything with to_header) handed to DataWrapper / WCS: converted through
+    to_header(relax=True) so that its SIP coefficients survive; objects whose to_header takes no argument still work."""
+    from transform_b200.remap import _as_wcs
+    inner = F.WCSParams(F.Header(sip_header()))
+
+    class Relaxed:
+        pixel_shape = (4096, 4096)
+
+        def to_header(self, relax=None):
+            return dict(inner.to_header(relax=relax).items())
+
+    class Plain:
+        def to_header(self):
+            return dict(inner.to_header().items())
+
+    w = _as_wcs(Relaxed())
+    assert w.has_sip() and np.array_equal(w.sip_a, inner.sip_a) and w.pixel_shape == [4096, 4096]
+    assert w.ctype == ['RA---TAN-SIP', 'DEC--TAN-SIP']
+    w = _as_wcs(Plain())
+    assert not w.has_sip() and w.ctype == ['RA---TAN', 'DEC--TAN']
+    assert t.WCS(Relaxed()).params['wcs'].has_sip()
+
+
 def test_projection_parameters():
     base = {'NAXIS': 2, 'CTYPE1': 'CRLN-CEA', 'CTYPE2': 'CRLT-CEA', 'CRPIX1': 100.0, 'CRPIX2': 120.0,
             'CRVAL1': 30.0, 'CRVAL2': 0.0, 'CDELT1': 0.1, 'CDELT2': 0.1}

@@ -29,7 +29,11 @@ def _as_wcs(obj):
     if isinstance(obj, WCSParams):
         return obj
     if hasattr(obj, 'to_header'):                                         # astropy WCS (duck-typed)
-        w = WCSParams(Header(dict(obj.to_header())))
+        try:
+            hdr = obj.to_header(relax=True)       # the conversion must not lose a SIP distortion the object carries
+        except TypeError:
+            hdr = obj.to_header()
+        w = WCSParams(Header(dict(hdr)))
         if getattr(obj, 'pixel_shape', None) is not None:
             w.pixel_shape = list(obj.pixel_shape)
         return w
@@ -210,6 +214,8 @@ class WCS(Transform):
             wcs_obj = dingus.wcs
         elif isinstance(dingus, WCSParams):
             wcs_obj = dingus
+        elif hasattr(dingus, 'to_header') and not isinstance(dingus, (Header, dict)):
+            wcs_obj = _as_wcs(dingus)              # an astropy.wcs.WCS (core.py:1688-1689), duck-typed
         else:
             wcs_obj = DataWrapper(dingus).wcs
         n = wcs_obj.naxis
